@@ -1,0 +1,168 @@
+"""The NumPy oracle vs. fixtures produced by the reference's own code (tests/golden/make_golden.py).
+
+Transcendental-free outputs (anchors, IoU, matches, labels, kept sets) must be bit-exact;
+outputs downstream of exp/log are compared at a few ulp."""
+import hashlib
+
+import numpy as np
+import pytest
+
+from oracle import box_utils, losses, nms, ssd
+from oracle.anchor_generator import AnchorGenerator
+from oracle.training_target_creation import create_targets, get_training_targets, match_boxes
+
+
+def sha(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+ANCHOR_CASES = ['shipped_640x640', 'nine_640x896', 'shipped_896x1344', 'shipped_200x333']
+
+
+@pytest.mark.parametrize('name', ANCHOR_CASES)
+def test_anchors_bit_exact(golden, name):
+    g = golden('anchors')
+    H, W, _ = g[name + '/args']
+    gen = AnchorGenerator(scale_multipliers=list(g[name + '/sm']))
+    a = gen(int(H), int(W))
+    assert a.dtype == np.float32 and tuple(a.shape) == tuple(g[name + '/shape'])
+    assert list(gen.num_anchors_per_feature_map) == list(g[name + '/per_map'])
+    assert np.array_equal(a[:64], g[name + '/head']) and np.array_equal(a[-64:], g[name + '/tail'])
+    assert sha(a) == str(g[name + '/sha256'])
+    if name == 'shipped_200x333':
+        assert np.array_equal(a, g[name + '/full'])
+        for i, r in enumerate(gen.raw_anchors):
+            assert np.array_equal(r, g[name + '/raw%d' % i])
+
+
+def test_known_answers_from_survey():
+    a = AnchorGenerator()(640, 640)
+    assert a.shape == (51150, 4)
+    assert np.array_equal(a[0] * 640, np.array([-12, -12, 20, 20], np.float32))
+    np.testing.assert_allclose(a[1] * 640, [-7.3137083, -18.627417, 15.313709, 26.627417], rtol=1e-7)
+    b = np.array([[0.1, 0.2, 0.5, 0.9]], np.float32)
+    assert np.array_equal(box_utils.encode(b, b), np.zeros([1, 4], np.float32))
+    small = np.array([[0.5, 0.5, 0.5001, 0.5001]], np.float32)
+    assert box_utils.iou(small, small)[0, 0] < 1.0     # area/(area+1e-8)
+
+
+def test_box_utils(golden):
+    g = golden('box_utils')
+    assert np.array_equal(box_utils.iou(g['b1'], g['b2']), g['iou'])
+    assert np.array_equal(box_utils.intersection(g['b1'], g['b2']), g['intersection'])
+    assert np.array_equal(box_utils.area(g['b2']), g['area'])
+    assert np.array_equal(box_utils.encode(g['pair'], g['b2']), g['encode'])
+    assert np.array_equal(box_utils.decode(g['codes'], g['b2']), g['decode'])
+    assert np.array_equal(box_utils.batch_decode(g['bcodes'], g['anchors']), g['batch_decode'])
+
+
+MATCH_CASES = ['random12', 'random40', 'tiny_ties', 'quirk', 'single', 'empty']
+THR = {'p5n5': (0.5, 0.5), 'p5n4': (0.5, 0.4), 'p7n3': (0.7, 0.3)}
+
+
+@pytest.mark.parametrize('case', MATCH_CASES)
+@pytest.mark.parametrize('tag', list(THR))
+def test_matching(golden, case, tag):
+    g = golden('matching')
+    anc, gt, lab = g['anchors'], g[case + '/gt'], g[case + '/labels']
+    pt, nt = THR[tag]
+    reg, cls, m = get_training_targets(anc, gt, lab, pt, nt)
+    assert m.dtype == np.int32 and cls.dtype == np.int32 and reg.dtype == np.float32
+    assert np.array_equal(m, g['%s/%s/matches' % (case, tag)])
+    assert np.array_equal(cls, g['%s/%s/cls' % (case, tag)])
+    assert np.array_equal(reg, g['%s/%s/reg' % (case, tag)])
+
+
+@pytest.mark.parametrize('case', [c for c in MATCH_CASES if c != 'empty'])
+def test_matching_no_force(golden, case):
+    g = golden('matching')
+    anc, gt, lab = g['anchors'], g[case + '/gt'], g[case + '/labels']
+    m = match_boxes(anc, gt, 0.5, 0.4, force_match_groundtruth=False)
+    assert np.array_equal(m, g[case + '/noforce_p5n4/matches'])
+    reg, cls = create_targets(anc, gt, lab, m)
+    assert np.array_equal(cls, g[case + '/noforce_p5n4/cls'])
+    assert np.array_equal(reg, g[case + '/noforce_p5n4/reg'])
+
+
+def test_quirk_fixture_really_hits_the_quirk(golden):
+    """GT0 and GT1 force the same anchor; GT0 is below 0.1 IoU, GT1 is not -> the anchor gets GT0."""
+    g = golden('matching')
+    ids, vals = g['quirk/forced_ids'], g['quirk/forced_vals']
+    assert ids[0] == ids[1] and vals[0] < 0.1 <= vals[1]
+    assert g['quirk/p5n5/matches'][ids[0]] == 0
+    assert g['quirk/noforce_p5n4/matches'][ids[0]] != 0
+
+
+@pytest.mark.parametrize('tag', ['p5n5', 'p5n4'])
+def test_cfg1_full_size(golden, syn, tag):
+    g = golden('cfg1_matching')
+    cfg = syn.CONFIGS[1]
+    anc = AnchorGenerator(scale_multipliers=cfg['scale_multipliers'])(cfg['H'], cfg['W'])
+    gt = syn.make_groundtruth(1, 1, cfg['G'], cfg['H'], cfg['W'], cfg['C'])
+    assert np.array_equal(gt['boxes'], g['gt_boxes']), 'synthetic generator drifted from the fixture'
+    pt, nt = THR[tag]
+    reg, cls, m = get_training_targets(anc, gt['boxes'][0], gt['labels'][0], pt, nt)
+    assert sha(m) == str(g[tag + '/matches_sha256'])
+    assert sha(cls) == str(g[tag + '/cls_sha256'])
+    idx = g[tag + '/nonbg_idx']
+    assert np.array_equal(m[idx], g[tag + '/nonbg_matches'])
+    assert np.array_equal(reg[idx], g[tag + '/reg_rows'])
+
+
+@pytest.mark.parametrize('tag', ['p5n5', 'p5n4'])
+def test_losses(golden, tag):
+    g = golden('losses')
+    gt = {'boxes': g['gt_boxes'], 'labels': g['gt_labels'], 'num_boxes': g['num_boxes']}
+    C = int(g['C'])
+    pt, nt = THR[tag]
+    for gamma, alpha in [(2.0, 0.25), (1.5, 0.4)]:
+        r = ssd.loss(g['anchors'], g['codes'], g['logits'], gt, {'gamma': gamma, 'alpha': alpha}, C,
+                     pt, nt, return_all=True)
+        key = '%s/g%s_a%s/' % (tag, gamma, alpha)
+        assert r['localization_loss'] == g[key + 'localization_loss']
+        assert r['classification_loss'] == g[key + 'classification_loss']
+        assert np.array_equal(r['matches'], g[tag + '/matches'])
+        assert np.array_equal(r['cls_targets'], g[tag + '/cls_targets'])
+        assert np.array_equal(r['reg_targets'], g[tag + '/reg_targets'])
+        if gamma == 2.0:
+            assert np.array_equal(r['cls_losses'], g[tag + '/cls_losses'])
+            assert np.array_equal(r['loc_losses'], g[tag + '/loc_losses'])
+    assert (g[tag + '/matches'] == -2).any() == (tag == 'p5n4')
+
+
+@pytest.mark.parametrize('tag', ['s05_i5_k10', 's15_i6_k25', 's30_i3_k3'])
+@pytest.mark.parametrize('use_c', [True, False])
+def test_postprocess(golden, tag, use_c):
+    g = golden('postprocess')
+    st, it, K = g[tag + '/params']
+    b, s, c, n = nms.batch_multiclass_non_max_suppression(g['codes'], g['anchors'], g['scores'], st, it,
+                                                          int(K), use_c=use_c)
+    assert np.array_equal(n, g[tag + '/num']) and n.sum() > 0
+    assert np.array_equal(c, g[tag + '/classes'])
+    assert np.array_equal(s, g[tag + '/scores'])
+    assert np.array_equal(b, g[tag + '/boxes'])
+
+
+def test_get_predictions(golden):
+    g = golden('postprocess')
+    p = ssd.get_predictions(g['anchors'], g['codes'], g['logits'])
+    for k in ['boxes', 'labels', 'scores', 'num_boxes']:
+        assert np.array_equal(p[k], g['get_predictions/' + k]), k
+    assert np.array_equal(losses.sigmoid(g['logits']), g['scores'])
+
+
+def test_nms_restatement_vs_torchvision():
+    """Independent cross-check of the NonMaxSuppressionV3 restatement (kept sets)."""
+    torch = pytest.importorskip('torch')
+    tv = pytest.importorskip('torchvision')
+    rng = np.random.default_rng(3)
+    for trial in range(5):
+        n = 400
+        ctr = rng.uniform(0, 1, (n, 2)); sz = rng.uniform(0.02, 0.3, (n, 2))
+        b = np.concatenate([ctr - sz / 2, ctr + sz / 2], 1).astype(np.float32).clip(0, 1)
+        s = rng.uniform(0, 1, n).astype(np.float32)
+        mine = nms.non_max_suppression_v3(b, s, 50, 0.5, 0.05)
+        keep = tv.ops.nms(torch.from_numpy(b[:, [1, 0, 3, 2]]), torch.from_numpy(s), 0.5).numpy()
+        keep = np.array([k for k in keep if s[k] > 0.05][:50])
+        assert np.array_equal(mine, keep)
+        assert np.array_equal(mine, nms.non_max_suppression_v3(b, s, 50, 0.5, 0.05, use_c=False))
