@@ -1,0 +1,180 @@
+/*
+ * ssdk.h -- C ABI of the B200-native per-anchor detection hot path ("single-shot-detector kernels").
+ *
+ * Drop-in boundary for TropComplique/single-shot-detector.  The reference has no FFI of its own
+ * (it is pure TensorFlow-1.x Python); each entry point below names the reference function it
+ * replaces (paths relative to the reference root).  INTEGRATION.md shows the ctypes binding.
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes; no C++/torch types.
+ *   - Every function returns 0 (SSDK_OK) or a negative ssdk_status; ssdk_last_error() returns a
+ *     thread-local, human readable message for the last failure on the calling thread.
+ *   - All tensor pointers are DEVICE pointers on the context's device unless the function name
+ *     ends in _host (then they are host pointers; pinned memory gives full PCIe speed).
+ *     The caller owns every input and output buffer; the library keeps nothing after return
+ *     except its private workspace inside the context.
+ *   - Work is enqueued on the context's CUDA stream and is asynchronous w.r.t. the host unless
+ *     noted ("synchronous").  One context per host thread per GPU; contexts are independent.
+ *   - float = IEEE binary32, int = int32.  Boxes are [ymin, xmin, ymax, xmax], normalised.
+ *   - `matches` values: >=0 index of the matched ground-truth box, -1 background, -2 ignore.
+ *   - There is no CPU fallback: without a CUDA device every compute entry point fails.
+ */
+#ifndef SSDK_H_
+#define SSDK_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SSDK_VERSION 100  /* 0.1.0 */
+
+#if defined(__GNUC__)
+#define SSDK_API __attribute__((visibility("default")))
+#else
+#define SSDK_API
+#endif
+
+typedef enum ssdk_status {
+    SSDK_OK = 0,
+    SSDK_ERR_ARG = -1,     /* bad argument value (also the reference's two asserts) */
+    SSDK_ERR_SHAPE = -2,   /* shape / size / alignment not supported */
+    SSDK_ERR_CUDA = -3,    /* CUDA runtime error */
+    SSDK_ERR_NCCL = -4,    /* reserved: collective error */
+    SSDK_ERR_NOMEM = -5    /* workspace allocation failed */
+} ssdk_status;
+
+typedef struct ssdk_ctx ssdk_ctx;
+
+/* ---- library / context ------------------------------------------------------------------ */
+SSDK_API int ssdk_version(void);
+SSDK_API const char* ssdk_last_error(void);
+/* stream: a cudaStream_t (NULL = legacy default stream).  Creates the context on `device`. */
+SSDK_API int ssdk_ctx_create(int device, void* stream, ssdk_ctx** out);
+SSDK_API int ssdk_ctx_set_stream(ssdk_ctx* ctx, void* stream);
+SSDK_API int ssdk_ctx_destroy(ssdk_ctx* ctx);
+/* Bytes of private workspace currently held (grows on demand, never shrinks). */
+SSDK_API int64_t ssdk_ctx_workspace_bytes(const ssdk_ctx* ctx);
+/* Counts kernel launches issued through this context since creation (bench.py's gpu_launches). */
+SSDK_API int64_t ssdk_ctx_launch_count(const ssdk_ctx* ctx);
+/* cudaStreamSynchronize on the context's stream (synchronous). */
+SSDK_API int ssdk_ctx_synchronize(ssdk_ctx* ctx);
+
+/* ---- anchors: detector/anchor_generator.py:40-120 (AnchorGenerator.__call__), :123-170 ---- */
+/* Host-only arithmetic on shapes (no GPU needed): per-level counts h*w*per_location
+ * (anchor_generator.py:59-62) and their sum. */
+SSDK_API int ssdk_num_anchors(int image_height, int image_width, const int* strides, int num_levels,
+                     int anchors_per_location, int64_t* out_total, int32_t* out_per_level);
+/* scales: HOST float[num_levels * per_location] (= float32(multiplier * scale), :75);
+ * ratios: HOST float[per_location] (:71); strides: HOST int[num_levels].
+ * out_anchors: DEVICE float[A,4] normalised, unclipped (:110-118);
+ * out_raw (may be NULL): DEVICE float[A,4] absolute pixel anchors, levels concatenated (:105). */
+SSDK_API int ssdk_anchors(ssdk_ctx* ctx, int image_height, int image_width, const int* strides,
+                 const float* scales, const float* ratios, int num_levels,
+                 int anchors_per_location, float* out_anchors, float* out_raw);
+
+/* ---- box utilities: detector/utils/box_utils.py ------------------------------------------ */
+SSDK_API int ssdk_area(ssdk_ctx* ctx, const float* boxes, int64_t n, float* out);                 /* :53-61  */
+SSDK_API int ssdk_intersection(ssdk_ctx* ctx, const float* boxes1, int64_t n, const float* boxes2,
+                      int64_t m, float* out /*[n,m]*/);                                   /* :30-50  */
+SSDK_API int ssdk_iou(ssdk_ctx* ctx, const float* boxes1, int64_t n, const float* boxes2, int64_t m,
+             float* out /*[n,m]*/);                                                       /* :14-27  */
+SSDK_API int ssdk_encode(ssdk_ctx* ctx, const float* boxes, const float* anchors, int64_t n,
+                float* out /*[n,4]*/);                                                    /* :80-111 */
+SSDK_API int ssdk_decode(ssdk_ctx* ctx, const float* codes, const float* anchors, int64_t n,
+                float* out /*[n,4]*/);                                                    /* :114-142 */
+/* codes [B,A,4], anchors [A,4] -> clip(decode, 0, 1) [B,A,4] */
+SSDK_API int ssdk_batch_decode(ssdk_ctx* ctx, const float* codes, const float* anchors, int64_t B,
+                      int64_t A, float* out);                                             /* :145-173 */
+
+/* ---- target assignment: detector/training_target_creation.py ------------------------------ */
+/* Batched match_boxes (:48-130).  gt_boxes [B,Gmax,4]; num_boxes DEVICE int[B] (NULL = every
+ * image has Gmax boxes); images with 0 boxes get all -1 (get_training_targets :24-37).
+ * Thresholds are doubles because the reference compares them as Python floats (:94).
+ * Gmax <= 4096. */
+SSDK_API int ssdk_match_boxes(ssdk_ctx* ctx, const float* anchors, int64_t A, const float* gt_boxes,
+                     const int32_t* num_boxes, int B, int Gmax, double positives_threshold,
+                     double negatives_threshold, int force_match_groundtruth,
+                     int32_t* out_matches /*[B,A]*/);
+/* create_targets (:133-176): reg [B,A,4], cls [B,A] (label+1, 0 = background). */
+SSDK_API int ssdk_create_targets(ssdk_ctx* ctx, const float* anchors, int64_t A, const float* gt_boxes,
+                        const int32_t* gt_labels, int B, int Gmax, const int32_t* matches,
+                        float* out_reg, int32_t* out_cls);
+/* get_training_targets (:5-45) for a batch == SSD._create_targets (detector/ssd.py:165-199):
+ * matching (force match on) + targets in one pass. */
+SSDK_API int ssdk_training_targets(ssdk_ctx* ctx, const float* anchors, int64_t A, const float* gt_boxes,
+                          const int32_t* gt_labels, const int32_t* num_boxes, int B, int Gmax,
+                          double positives_threshold, double negatives_threshold,
+                          float* out_reg, int32_t* out_cls, int32_t* out_matches);
+
+/* ---- losses: detector/losses.py ----------------------------------------------------------- */
+/* localization_loss (:4-19): predictions/targets [B,A,4], weights [B,A] -> out [B,A]. */
+SSDK_API int ssdk_localization_loss(ssdk_ctx* ctx, const float* predictions, const float* targets,
+                           const float* weights, int64_t B, int64_t A, float* out);
+/* focal_loss (:22-50) with dense one-hot float targets [B,A,C] exactly as the reference API. */
+SSDK_API int ssdk_focal_loss(ssdk_ctx* ctx, const float* logits, const float* targets,
+                    const float* weights, int64_t B, int64_t A, int C, double gamma, double alpha,
+                    float* out /*[B,A]*/);
+
+/* SSD.loss (detector/ssd.py:71-133) given the targets: focal loss with weights (matches >= -1)
+ * on one_hot(cls)[..., 1:], smooth-L1 with weights (matches >= 0), matched count.
+ *   logits [B,A,C] (16-byte aligned), codes [B,A,4], reg_targets [B,A,4], cls_targets [B,A],
+ *   matches [B,A].
+ *   out_sums: DEVICE double[3] = { sum(loc_losses), sum(cls_losses), num_matches } for THIS
+ *             shard (un-normalised, so that ranks can all-reduce them; ssd.py:121-122,131-132).
+ *   out_cls_losses / out_loc_losses: optional DEVICE float[B,A] per-anchor vectors (the tensors
+ *             the reference's summaries consume, ssd.py:127-128); NULL to skip. */
+SSDK_API int ssdk_ssd_loss(ssdk_ctx* ctx, const float* logits, const float* codes, const float* reg_targets,
+                  const int32_t* cls_targets, const int32_t* matches, int64_t B, int64_t A, int C,
+                  double gamma, double alpha, double* out_sums, float* out_cls_losses,
+                  float* out_loc_losses);
+/* normalizer = max(num_matches, 1) (ssd.py:123); out_losses: DEVICE float[2] =
+ * { localization_loss, classification_loss } (ssd.py:133).  `sums` are the (all-reduced) sums. */
+SSDK_API int ssdk_loss_finalize(ssdk_ctx* ctx, const double* sums, float* out_losses);
+
+/* Whole training-side hot path for a batch of images resident in HBM:
+ * targets (ssd.py:84) + losses (ssd.py:89-133).  Any of out_reg/out_cls/out_matches may be NULL,
+ * in which case context workspace is used for them. */
+SSDK_API int ssdk_ssd_targets_and_loss(ssdk_ctx* ctx, const float* anchors, const float* logits,
+                              const float* codes, const float* gt_boxes, const int32_t* gt_labels,
+                              const int32_t* num_boxes, int B, int64_t A, int C, int Gmax,
+                              double positives_threshold, double negatives_threshold,
+                              double gamma, double alpha, double* out_sums, float* out_reg,
+                              int32_t* out_cls, int32_t* out_matches, float* out_cls_losses,
+                              float* out_loc_losses);
+/* Same call with HOST buffers (synchronous): copies inputs H2D, runs, copies
+ * out_sums (double[3]) and out_losses (float[2], normalised with the LOCAL count) back. */
+SSDK_API int ssdk_ssd_targets_and_loss_host(ssdk_ctx* ctx, const float* anchors, const float* logits,
+                                   const float* codes, const float* gt_boxes,
+                                   const int32_t* gt_labels, const int32_t* num_boxes, int B,
+                                   int64_t A, int C, int Gmax, double positives_threshold,
+                                   double negatives_threshold, double gamma, double alpha,
+                                   double* out_sums, float* out_losses);
+
+/* ---- post-processing: detector/utils/nms.py, detector/ssd.py:42-69 ------------------------ */
+#define SSDK_INPUT_SCORES 0        /* `scores` are probabilities (batch_multiclass_nms, nms.py:48) */
+#define SSDK_INPUT_LOGITS 1        /* `scores` are logits; sigmoid is fused (SSD.get_predictions, ssd.py:60) */
+#define SSDK_BOXES_ENCODED 0       /* `codes` are box codes, decoded against `anchors` and clipped (nms.py:76-77) */
+#define SSDK_BOXES_DECODED 2       /* `codes` are final boxes [B,A,4]; anchors ignored (multiclass_nms, nms.py:6) */
+/* batch_multiclass_non_max_suppression (nms.py:48-102) with tf.image.non_max_suppression
+ * (TF 1.12 NonMaxSuppressionV3) semantics per class: candidates score > score_threshold,
+ * greedy in descending score (ties: lower anchor index), suppress iff IoU > iou_threshold,
+ * at most K per class; class-major concatenation, zero padding to C*K, num_boxes per image.
+ *   codes [B,A,4], anchors [A,4], scores [B,A,C];
+ *   out_boxes [B,C*K,4], out_scores [B,C*K], out_classes int[B,C*K], out_num int[B].
+ *   out_anchor_idx (may be NULL): int[B,C*K] anchor index of each kept box, -1 padding. */
+SSDK_API int ssdk_postprocess(ssdk_ctx* ctx, const float* codes, const float* anchors, const float* scores,
+                     int flags, int B, int64_t A, int C, double score_threshold,
+                     double iou_threshold, int K, float* out_boxes, float* out_scores,
+                     int32_t* out_classes, int32_t* out_num, int32_t* out_anchor_idx);
+/* Same with HOST buffers (synchronous). */
+SSDK_API int ssdk_postprocess_host(ssdk_ctx* ctx, const float* codes, const float* anchors,
+                          const float* scores, int flags, int B, int64_t A, int C,
+                          double score_threshold, double iou_threshold, int K, float* out_boxes,
+                          float* out_scores, int32_t* out_classes, int32_t* out_num);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SSDK_H_ */

@@ -1,0 +1,107 @@
+"""ctypes binding of libssdk.so (include/ssdk.h) -- the thin C-ABI layer under the Python mirror.
+
+There is NO fallback: if the shared library has not been built, or no CUDA device is present, every
+compute call raises.  Device memory, streams and (for multi-GPU) torch.distributed come from PyTorch;
+all arithmetic happens in the hand-written sm_100a kernels of csrc/.
+"""
+import ctypes
+import os
+import threading
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'lib', 'libssdk.so')
+
+c_int, c_i64, c_double, c_void_p = ctypes.c_int, ctypes.c_int64, ctypes.c_double, ctypes.c_void_p
+P = c_void_p  # every tensor argument is passed as a raw address
+
+# name -> argtypes (after the leading ctx pointer where has_ctx); mirrors include/ssdk.h declaration by declaration
+_SIGNATURES = {
+    'ssdk_version': (None, []),
+    'ssdk_last_error': (ctypes.c_char_p, []),
+    'ssdk_ctx_create': (c_int, [c_int, P, ctypes.POINTER(P)]),
+    'ssdk_ctx_set_stream': (c_int, [P, P]),
+    'ssdk_ctx_destroy': (c_int, [P]),
+    'ssdk_ctx_workspace_bytes': (c_i64, [P]),
+    'ssdk_ctx_launch_count': (c_i64, [P]),
+    'ssdk_ctx_synchronize': (c_int, [P]),
+    'ssdk_num_anchors': (c_int, [c_int, c_int, P, c_int, c_int, ctypes.POINTER(c_i64), P]),
+    'ssdk_anchors': (c_int, [P, c_int, c_int, P, P, P, c_int, c_int, P, P]),
+    'ssdk_area': (c_int, [P, P, c_i64, P]),
+    'ssdk_intersection': (c_int, [P, P, c_i64, P, c_i64, P]),
+    'ssdk_iou': (c_int, [P, P, c_i64, P, c_i64, P]),
+    'ssdk_encode': (c_int, [P, P, P, c_i64, P]),
+    'ssdk_decode': (c_int, [P, P, P, c_i64, P]),
+    'ssdk_batch_decode': (c_int, [P, P, P, c_i64, c_i64, P]),
+    'ssdk_match_boxes': (c_int, [P, P, c_i64, P, P, c_int, c_int, c_double, c_double, c_int, P]),
+    'ssdk_create_targets': (c_int, [P, P, c_i64, P, P, c_int, c_int, P, P, P]),
+    'ssdk_training_targets': (c_int, [P, P, c_i64, P, P, P, c_int, c_int, c_double, c_double, P, P, P]),
+    'ssdk_localization_loss': (c_int, [P, P, P, P, c_i64, c_i64, P]),
+    'ssdk_focal_loss': (c_int, [P, P, P, P, c_i64, c_i64, c_int, c_double, c_double, P]),
+    'ssdk_ssd_loss': (c_int, [P, P, P, P, P, P, c_i64, c_i64, c_int, c_double, c_double, P, P, P]),
+    'ssdk_loss_finalize': (c_int, [P, P, P]),
+    'ssdk_ssd_targets_and_loss': (c_int, [P, P, P, P, P, P, P, c_int, c_i64, c_int, c_int, c_double, c_double,
+                                          c_double, c_double, P, P, P, P, P, P]),
+    'ssdk_ssd_targets_and_loss_host': (c_int, [P, P, P, P, P, P, P, c_int, c_i64, c_int, c_int, c_double, c_double,
+                                               c_double, c_double, P, P]),
+    'ssdk_postprocess': (c_int, [P, P, P, P, c_int, c_int, c_i64, c_int, c_double, c_double, c_int, P, P, P, P, P]),
+    'ssdk_postprocess_host': (c_int, [P, P, P, P, c_int, c_int, c_i64, c_int, c_double, c_double, c_int, P, P, P, P]),
+}
+
+SSDK_INPUT_SCORES, SSDK_INPUT_LOGITS = 0, 1
+SSDK_BOXES_ENCODED, SSDK_BOXES_DECODED = 0, 2
+
+_lib = None
+_lock = threading.Lock()
+_contexts = {}
+
+
+class SsdkError(RuntimeError):
+    pass
+
+
+def load():
+    """dlopen libssdk.so and declare every entry point; raises if the extension is missing."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is None:
+            if not os.path.exists(LIB_PATH):
+                raise SsdkError(
+                    'CUDA extension not built: %s is missing. Run `python -c "import __graft_entry__ as g; g.build()"` '
+                    '(or make -C single-shot-detector_b200/csrc). There is no CPU fallback.' % LIB_PATH)
+            lib = ctypes.CDLL(LIB_PATH)
+            for name, (restype, argtypes) in _SIGNATURES.items():
+                fn = getattr(lib, name)       # AttributeError if the .so does not export a declared symbol
+                fn.restype = c_int if restype is None else restype
+                fn.argtypes = argtypes
+            _lib = lib
+    return _lib
+
+
+def check(status):
+    if status != 0:
+        msg = load().ssdk_last_error().decode('utf-8', 'replace')
+        if status in (-1, -2):
+            raise ValueError('ssdk: ' + msg)
+        raise SsdkError('ssdk error %d: %s' % (status, msg))
+
+
+def context(device_index):
+    """One library context per (thread, device)."""
+    key = (threading.get_ident(), int(device_index))
+    ctx = _contexts.get(key)
+    if ctx is None:
+        lib = load()
+        h = P()
+        check(lib.ssdk_ctx_create(int(device_index), None, ctypes.byref(h)))
+        ctx = _contexts[key] = h
+    return ctx
+
+
+def launch_count(device_index=0):
+    return int(load().ssdk_ctx_launch_count(context(device_index)))
+
+
+def workspace_bytes(device_index=0):
+    return int(load().ssdk_ctx_workspace_bytes(context(device_index)))

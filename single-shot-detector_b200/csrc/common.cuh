@@ -1,0 +1,165 @@
+// Shared host/device helpers for libssdk (sm_100a).  See include/ssdk.h for the ABI.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+
+#include "../../include/ssdk.h"
+
+// ----------------------------------------------------------------------------------------------
+// context + error plumbing
+// ----------------------------------------------------------------------------------------------
+struct ssdk_buf {
+    void* p = nullptr;
+    size_t cap = 0;
+};
+
+struct ssdk_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    int num_sms = 148;
+    int64_t launches = 0;
+    // private workspace (grows on demand)
+    ssdk_buf ws_gtbest;      // matcher: per-(image, gt) packed (iou, anchor) keys
+    ssdk_buf ws_partials;    // loss: per-CTA partial sums
+    ssdk_buf ws_reg, ws_cls, ws_matches;   // targets when the caller does not want them
+    ssdk_buf ws_cand;        // postprocess: candidate keys  [B][cap] u64
+    ssdk_buf ws_counts;      // postprocess: per-image counters + per-(image,class) segment tables
+    ssdk_buf ws_seg;         // postprocess: per-(image,class) kept boxes/scores/anchors
+    ssdk_buf ws_stage[8];    // *_host entry points: device staging
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+};
+
+void ssdk_set_error(const char* fmt, ...);
+int ssdk_ensure(ssdk_ctx* ctx, ssdk_buf* b, size_t bytes);
+
+#define SSDK_CHECK_CUDA(expr)                                                              \
+    do {                                                                                   \
+        cudaError_t _e = (expr);                                                           \
+        if (_e != cudaSuccess) {                                                           \
+            ssdk_set_error("%s failed at %s:%d: %s", #expr, __FILE__, __LINE__,            \
+                           cudaGetErrorString(_e));                                        \
+            return SSDK_ERR_CUDA;                                                          \
+        }                                                                                  \
+    } while (0)
+
+#define SSDK_CHECK_LAUNCH(ctx)                                                             \
+    do {                                                                                   \
+        (ctx)->launches++;                                                                 \
+        SSDK_CHECK_CUDA(cudaGetLastError());                                               \
+    } while (0)
+
+#define SSDK_REQUIRE(cond, code, ...)                                                      \
+    do {                                                                                   \
+        if (!(cond)) {                                                                     \
+            ssdk_set_error(__VA_ARGS__);                                                   \
+            return (code);                                                                 \
+        }                                                                                  \
+    } while (0)
+
+#define SSDK_TRY(expr)                                                                     \
+    do {                                                                                   \
+        int _s = (expr);                                                                   \
+        if (_s != SSDK_OK) return _s;                                                      \
+    } while (0)
+
+static inline int ssdk_ctx_enter(ssdk_ctx* ctx) {
+    if (!ctx) {
+        ssdk_set_error("null context");
+        return SSDK_ERR_ARG;
+    }
+    SSDK_CHECK_CUDA(cudaSetDevice(ctx->device));
+    return SSDK_OK;
+}
+
+// ----------------------------------------------------------------------------------------------
+// Parity-critical float32 arithmetic.  The reference executes one TF kernel per Python-level op,
+// so every operation rounds separately: explicit _rn intrinsics keep nvcc from contracting
+// a*b+c into an FMA and force IEEE division / sqrt.
+// ----------------------------------------------------------------------------------------------
+#define SSDK_EPS 1e-8f  // detector/constants.py:12
+
+__device__ __forceinline__ float f_add(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ float f_sub(float a, float b) { return __fsub_rn(a, b); }
+__device__ __forceinline__ float f_mul(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ float f_div(float a, float b) { return __fdiv_rn(a, b); }
+
+// area: box_utils.py:53-61
+__device__ __forceinline__ float box_area(const float4 b) {
+    return f_mul(f_sub(b.z, b.x), f_sub(b.w, b.y));
+}
+// intersection: box_utils.py:30-50
+__device__ __forceinline__ float box_intersection(const float4 a, const float4 b) {
+    const float ih = fmaxf(0.0f, f_sub(fminf(a.z, b.z), fmaxf(a.x, b.x)));
+    const float iw = fmaxf(0.0f, f_sub(fminf(a.w, b.w), fmaxf(a.y, b.y)));
+    return f_mul(ih, iw);
+}
+// iou: box_utils.py:14-27  ((a1 + a2) - inter, + eps, divide, clip)
+__device__ __forceinline__ float box_iou_areas(const float4 a, float area_a, const float4 b, float area_b) {
+    const float inter = box_intersection(a, b);
+    const float uni = f_sub(f_add(area_a, area_b), inter);
+    const float q = f_div(inter, f_add(uni, SSDK_EPS));
+    return fminf(fmaxf(q, 0.0f), 1.0f);
+}
+
+// encode: box_utils.py:80-111 (to_center_coordinates :64-77); scale factors constants.py:15
+__device__ __forceinline__ float4 box_encode(const float4 box, const float4 anchor) {
+    float ha = f_sub(anchor.z, anchor.x), wa = f_sub(anchor.w, anchor.y);
+    const float cya = f_add(anchor.x, f_mul(0.5f, ha)), cxa = f_add(anchor.y, f_mul(0.5f, wa));
+    float h = f_sub(box.z, box.x), w = f_sub(box.w, box.y);
+    const float cy = f_add(box.x, f_mul(0.5f, h)), cx = f_add(box.y, f_mul(0.5f, w));
+    ha = f_add(ha, SSDK_EPS); wa = f_add(wa, SSDK_EPS);
+    h = f_add(h, SSDK_EPS); w = f_add(w, SSDK_EPS);
+    float4 t;
+    t.x = f_mul(f_div(f_sub(cy, cya), ha), 10.0f);
+    t.y = f_mul(f_div(f_sub(cx, cxa), wa), 10.0f);
+    t.z = f_mul(logf(f_div(h, ha)), 5.0f);
+    t.w = f_mul(logf(f_div(w, wa)), 5.0f);
+    return t;
+}
+
+// decode: box_utils.py:114-142
+__device__ __forceinline__ float4 box_decode(const float4 code, const float4 anchor) {
+    const float ha = f_sub(anchor.z, anchor.x), wa = f_sub(anchor.w, anchor.y);
+    const float cya = f_add(anchor.x, f_mul(0.5f, ha)), cxa = f_add(anchor.y, f_mul(0.5f, wa));
+    const float ty = f_div(code.x, 10.0f), tx = f_div(code.y, 10.0f);
+    const float th = f_div(code.z, 5.0f), tw = f_div(code.w, 5.0f);
+    const float h = f_mul(expf(th), ha), w = f_mul(expf(tw), wa);
+    const float cy = f_add(f_mul(ty, ha), cya), cx = f_add(f_mul(tx, wa), cxa);
+    const float hh = f_mul(0.5f, h), hw = f_mul(0.5f, w);
+    return make_float4(f_sub(cy, hh), f_sub(cx, hw), f_add(cy, hh), f_add(cx, hw));
+}
+
+__device__ __forceinline__ float4 box_clip01(float4 b) {
+    b.x = fminf(fmaxf(b.x, 0.0f), 1.0f); b.y = fminf(fmaxf(b.y, 0.0f), 1.0f);
+    b.z = fminf(fmaxf(b.z, 0.0f), 1.0f); b.w = fminf(fmaxf(b.w, 0.0f), 1.0f);
+    return b;
+}
+
+// TF 1.12 NonMaxSuppressionV3 suppression test (external to the reference; see oracle/nms.py).
+__device__ __forceinline__ bool nms_iou_greater(const float4 bi, const float4 bj, float thr) {
+    const float ymin_i = fminf(bi.x, bi.z), xmin_i = fminf(bi.y, bi.w);
+    const float ymax_i = fmaxf(bi.x, bi.z), xmax_i = fmaxf(bi.y, bi.w);
+    const float ymin_j = fminf(bj.x, bj.z), xmin_j = fminf(bj.y, bj.w);
+    const float ymax_j = fmaxf(bj.x, bj.z), xmax_j = fmaxf(bj.y, bj.w);
+    const float area_i = f_mul(f_sub(ymax_i, ymin_i), f_sub(xmax_i, xmin_i));
+    const float area_j = f_mul(f_sub(ymax_j, ymin_j), f_sub(xmax_j, xmin_j));
+    if (area_i <= 0.0f || area_j <= 0.0f) return false;
+    const float ih = fmaxf(f_sub(fminf(ymax_i, ymax_j), fmaxf(ymin_i, ymin_j)), 0.0f);
+    const float iw = fmaxf(f_sub(fminf(xmax_i, xmax_j), fmaxf(xmin_i, xmin_j)), 0.0f);
+    const float inter = f_mul(ih, iw);
+    const float iou = f_div(inter, f_sub(f_add(area_i, area_j), inter));
+    return iou > thr;
+}
+
+// streaming (read-once) 128-bit load that does not allocate in L1
+__device__ __forceinline__ float4 ld_stream_f4(const float4* p) {
+    float4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+    return v;
+}
+
+static inline int ceil_div_i(long long a, long long b) { return (int)((a + b - 1) / b); }

@@ -1,0 +1,238 @@
+// Target assignment: GT x anchor IoU, per-anchor argmax + thresholds, per-GT forced match, box-coder targets.
+// Replaces detector/training_target_creation.py (match_boxes :48-130, create_targets :133-176,
+// get_training_targets :5-45) and the per-image tf.map_fn of detector/ssd.py:165-199.
+//
+// The reference materialises the [G,A] IoU matrix plus a [G,A] int32 one-hot per image.  Here nothing of size
+// G*A ever reaches memory: one thread owns one anchor, GT boxes are staged in shared memory, the per-anchor
+// argmax is a register scan in GT order (strict '>' == tf.argmax's first maximum), and the per-GT argmax over
+// anchors is a (value, lowest index) reduction: warp REDUX.MAX on the IoU bit pattern (IoU >= 0, so the uint
+// order is the float order) -> shared-memory atomicMax -> one global atomicMax per (CTA, GT) on the packed key
+//     key = iou_bits << 32 | (0xFFFFFFFF - anchor_index)      (ties -> LOWEST anchor index, as tf.argmax axis=1).
+// A second, tiny kernel applies the forced matches, including the reference's row-id quirk (:117).
+#include "common.cuh"
+
+#define MATCH_THREADS 256
+#define GT_CHUNK 512
+
+// matches value from the thresholds: training_target_creation.py:92-100
+__device__ __forceinline__ int threshold_match(int best_g, float best_v, float pos_thr, float neg_thr, bool same_thr) {
+    if (best_v >= pos_thr) return best_g;
+    if (same_thr) return -1;
+    return (neg_thr > best_v) ? -1 : -2;
+}
+
+template <bool WRITE_TARGETS>
+__global__ void __launch_bounds__(MATCH_THREADS) match_kernel(
+    const float4* __restrict__ anchors, int A, const float4* __restrict__ gt_boxes, const int* __restrict__ gt_labels,
+    const int* __restrict__ num_boxes, int Gmax, float pos_thr, float neg_thr, int same_thr,
+    unsigned long long* __restrict__ gt_best /*[B,Gmax], zeroed; may be NULL (no forced matching)*/,
+    int* __restrict__ matches, float4* __restrict__ reg, int* __restrict__ cls) {
+    __shared__ float4 s_box[GT_CHUNK];
+    __shared__ float s_area[GT_CHUNK];
+    __shared__ unsigned long long s_best[GT_CHUNK];
+
+    const int b = blockIdx.y;
+    const int a = blockIdx.x * MATCH_THREADS + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    const bool valid = a < A;
+    const int N = num_boxes ? min(max(num_boxes[b], 0), Gmax) : Gmax;
+    const float4* gtb = gt_boxes + (size_t)b * Gmax;
+
+    float4 anc = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (valid) anc = anchors[a];
+    const float area_a = box_area(anc);
+
+    float best_v = 0.0f;   // IoU is clipped to [0,1]: starting from (0, index 0) with strict '>' is tf.argmax
+    int best_g = 0;
+
+    for (int g0 = 0; g0 < N; g0 += GT_CHUNK) {
+        const int n = min(GT_CHUNK, N - g0);
+        __syncthreads();
+        for (int t = threadIdx.x; t < n; t += MATCH_THREADS) {
+            const float4 gb = gtb[g0 + t];
+            s_box[t] = gb;
+            s_area[t] = box_area(gb);
+            s_best[t] = 0ull;
+        }
+        __syncthreads();
+        for (int t = 0; t < n; ++t) {
+            const float4 gb = s_box[t];
+            // iou(groundtruth_boxes, anchors): box_utils.py:14-27.  inter == 0 -> 0 / (union + eps) == 0 exactly.
+            const float inter = box_intersection(gb, anc);
+            float v = 0.0f;
+            if (valid && inter > 0.0f) {
+                const float uni = f_sub(f_add(s_area[t], area_a), inter);
+                v = fminf(fmaxf(f_div(inter, f_add(uni, SSDK_EPS)), 0.0f), 1.0f);
+            }
+            if (v > best_v) { best_v = v; best_g = g0 + t; }           // :90-91 (first max over GT)
+            if (gt_best) {                                              // :112,120 (first max over anchors)
+                const unsigned bits = __float_as_uint(v);
+                const unsigned wmax = __reduce_max_sync(0xffffffffu, bits);
+                if (wmax != 0u) {
+                    const unsigned ball = __ballot_sync(0xffffffffu, bits == wmax);
+                    if (lane == __ffs(ball) - 1)
+                        atomicMax(&s_best[t], ((unsigned long long)wmax << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned)a));
+                }
+            }
+        }
+        if (gt_best) {
+            __syncthreads();
+            for (int t = threadIdx.x; t < n; t += MATCH_THREADS)
+                if (s_best[t] != 0ull) atomicMax(&gt_best[(size_t)b * Gmax + g0 + t], s_best[t]);
+        }
+    }
+    if (!valid) return;
+    const int m = (N > 0) ? threshold_match(best_g, best_v, pos_thr, neg_thr, same_thr != 0) : -1;   // :24-37
+    const size_t o = (size_t)b * A + a;
+    matches[o] = m;
+    if (WRITE_TARGETS) {                                               // create_targets :133-176
+        if (m >= 0) {
+            reg[o] = box_encode(gtb[m], anc);
+            cls[o] = gt_labels[(size_t)b * Gmax + m] + 1;
+        } else {
+            reg[o] = make_float4(0.f, 0.f, 0.f, 0.f);
+            cls[o] = 0;
+        }
+    }
+}
+
+// Forced matches: training_target_creation.py:105-126.  For GT g: fid[g] = first anchor with the row maximum,
+// ok[g] = (row maximum >= 0.1).  Anchor a is overridden iff some ok GT picked it; the value written is the
+// LOWEST GT index among all GTs that picked a, ok or not (argmax over the unmasked one-hot, :117).
+template <bool WRITE_TARGETS>
+__global__ void __launch_bounds__(256) force_match_kernel(
+    const float4* __restrict__ anchors, int A, const float4* __restrict__ gt_boxes, const int* __restrict__ gt_labels,
+    const int* __restrict__ num_boxes, int Gmax, const unsigned long long* __restrict__ gt_best,
+    int* __restrict__ matches, float4* __restrict__ reg, int* __restrict__ cls) {
+    extern __shared__ int s_dyn[];
+    int* s_fid = s_dyn;                                  // [Gmax]
+    unsigned char* s_ok = (unsigned char*)(s_dyn + Gmax);  // [Gmax]
+    const int b = blockIdx.x;
+    const int N = num_boxes ? min(max(num_boxes[b], 0), Gmax) : Gmax;
+    for (int g = threadIdx.x; g < N; g += blockDim.x) {
+        const unsigned long long key = gt_best[(size_t)b * Gmax + g];
+        // key == 0: the whole IoU row is 0 -> argmax is anchor 0, value 0
+        s_fid[g] = key ? (int)(0xFFFFFFFFu - (unsigned)(key & 0xFFFFFFFFull)) : 0;
+        s_ok[g] = __uint_as_float((unsigned)(key >> 32)) >= 0.1f;
+    }
+    __syncthreads();
+    for (int g = threadIdx.x; g < N; g += blockDim.x) {
+        const int a = s_fid[g];
+        bool first = true, any_ok = false;
+        for (int h = 0; h < N; ++h) {
+            if (s_fid[h] == a) {
+                if (h < g) first = false;
+                any_ok |= (s_ok[h] != 0);
+            }
+        }
+        if (first && any_ok) {
+            const size_t o = (size_t)b * A + a;
+            matches[o] = g;
+            if (WRITE_TARGETS) {
+                reg[o] = box_encode(gt_boxes[(size_t)b * Gmax + g], anchors[a]);
+                cls[o] = gt_labels[(size_t)b * Gmax + g] + 1;
+            }
+        }
+    }
+}
+
+// create_targets alone (:133-176), for callers that bring their own matches.
+__global__ void __launch_bounds__(256) create_targets_kernel(
+    const float4* __restrict__ anchors, int A, const float4* __restrict__ gt_boxes, const int* __restrict__ gt_labels,
+    int Gmax, const int* __restrict__ matches, float4* __restrict__ reg, int* __restrict__ cls) {
+    const int b = blockIdx.y;
+    const int a = blockIdx.x * blockDim.x + threadIdx.x;
+    if (a >= A) return;
+    const size_t o = (size_t)b * A + a;
+    const int m = matches[o];
+    if (m >= 0 && m < Gmax) {
+        reg[o] = box_encode(gt_boxes[(size_t)b * Gmax + m], anchors[a]);
+        cls[o] = gt_labels[(size_t)b * Gmax + m] + 1;
+    } else {
+        reg[o] = make_float4(0.f, 0.f, 0.f, 0.f);
+        cls[o] = 0;
+    }
+}
+
+static bool aligned16(const void* p) { return ((uintptr_t)p & 15) == 0; }
+
+int ssdk_match_impl(ssdk_ctx* ctx, const float* anchors, int64_t A, const float* gt_boxes, const int32_t* gt_labels,
+                    const int32_t* num_boxes, int B, int Gmax, double pos_thr, double neg_thr, int force,
+                    float* out_reg, int32_t* out_cls, int32_t* out_matches) {
+    SSDK_TRY(ssdk_ctx_enter(ctx));
+    SSDK_REQUIRE(pos_thr >= neg_thr, SSDK_ERR_ARG,
+                 "positives_threshold (%g) must be >= negatives_threshold (%g)", pos_thr, neg_thr);  // :86
+    SSDK_REQUIRE(B >= 0 && A >= 0 && Gmax >= 0, SSDK_ERR_ARG, "match: negative size");
+    SSDK_REQUIRE(A < (1ll << 31) && B <= 65535, SSDK_ERR_SHAPE, "match: A must be < 2^31 and B <= 65535");
+    SSDK_REQUIRE(Gmax <= 4096, SSDK_ERR_SHAPE, "match: at most 4096 ground-truth boxes per image (got %d)", Gmax);
+    if (B == 0 || A == 0) return SSDK_OK;
+    SSDK_REQUIRE(anchors && out_matches && (Gmax == 0 || gt_boxes), SSDK_ERR_ARG, "match: null pointer");
+    const bool targets = out_reg != nullptr || out_cls != nullptr;
+    if (targets) SSDK_REQUIRE(out_reg && out_cls && (Gmax == 0 || gt_labels), SSDK_ERR_ARG, "match: targets need reg, cls and labels");
+    SSDK_REQUIRE(aligned16(anchors) && aligned16(gt_boxes) && aligned16(out_reg), SSDK_ERR_SHAPE,
+                 "match: box arrays must be 16-byte aligned");
+    unsigned long long* best = nullptr;
+    if (force && Gmax > 0) {
+        const size_t bytes = (size_t)B * Gmax * sizeof(unsigned long long);
+        SSDK_TRY(ssdk_ensure(ctx, &ctx->ws_gtbest, bytes));
+        best = (unsigned long long*)ctx->ws_gtbest.p;
+        SSDK_CHECK_CUDA(cudaMemsetAsync(best, 0, bytes, ctx->stream));
+    }
+    const dim3 grid(ceil_div_i(A, MATCH_THREADS), B);
+    const int same = (pos_thr == neg_thr) ? 1 : 0;   // compared as Python floats in the reference (:94)
+    if (targets)
+        match_kernel<true><<<grid, MATCH_THREADS, 0, ctx->stream>>>(
+            (const float4*)anchors, (int)A, (const float4*)gt_boxes, gt_labels, num_boxes, Gmax, (float)pos_thr,
+            (float)neg_thr, same, best, out_matches, (float4*)out_reg, out_cls);
+    else
+        match_kernel<false><<<grid, MATCH_THREADS, 0, ctx->stream>>>(
+            (const float4*)anchors, (int)A, (const float4*)gt_boxes, gt_labels, num_boxes, Gmax, (float)pos_thr,
+            (float)neg_thr, same, best, out_matches, nullptr, nullptr);
+    SSDK_CHECK_LAUNCH(ctx);
+    if (best) {
+        const size_t smem = (size_t)Gmax * 5 + 16;
+        if (targets)
+            force_match_kernel<true><<<B, 256, smem, ctx->stream>>>((const float4*)anchors, (int)A, (const float4*)gt_boxes,
+                                                                   gt_labels, num_boxes, Gmax, best, out_matches,
+                                                                   (float4*)out_reg, out_cls);
+        else
+            force_match_kernel<false><<<B, 256, smem, ctx->stream>>>((const float4*)anchors, (int)A, (const float4*)gt_boxes,
+                                                                    gt_labels, num_boxes, Gmax, best, out_matches, nullptr,
+                                                                    nullptr);
+        SSDK_CHECK_LAUNCH(ctx);
+    }
+    return SSDK_OK;
+}
+
+extern "C" {
+
+int ssdk_match_boxes(ssdk_ctx* ctx, const float* anchors, int64_t A, const float* gt_boxes, const int32_t* num_boxes,
+                     int B, int Gmax, double pos_thr, double neg_thr, int force, int32_t* out_matches) {
+    return ssdk_match_impl(ctx, anchors, A, gt_boxes, nullptr, num_boxes, B, Gmax, pos_thr, neg_thr, force, nullptr,
+                           nullptr, out_matches);
+}
+
+int ssdk_training_targets(ssdk_ctx* ctx, const float* anchors, int64_t A, const float* gt_boxes, const int32_t* gt_labels,
+                          const int32_t* num_boxes, int B, int Gmax, double pos_thr, double neg_thr, float* out_reg,
+                          int32_t* out_cls, int32_t* out_matches) {
+    SSDK_REQUIRE(out_reg && out_cls, SSDK_ERR_ARG, "ssdk_training_targets: out_reg/out_cls are required");
+    return ssdk_match_impl(ctx, anchors, A, gt_boxes, gt_labels, num_boxes, B, Gmax, pos_thr, neg_thr, 1, out_reg, out_cls,
+                           out_matches);
+}
+
+int ssdk_create_targets(ssdk_ctx* ctx, const float* anchors, int64_t A, const float* gt_boxes, const int32_t* gt_labels,
+                        int B, int Gmax, const int32_t* matches, float* out_reg, int32_t* out_cls) {
+    SSDK_TRY(ssdk_ctx_enter(ctx));
+    SSDK_REQUIRE(B >= 0 && A >= 0 && Gmax >= 0 && A < (1ll << 31) && B <= 65535, SSDK_ERR_ARG, "create_targets: bad sizes");
+    if (B == 0 || A == 0) return SSDK_OK;
+    SSDK_REQUIRE(anchors && matches && out_reg && out_cls && (Gmax == 0 || (gt_boxes && gt_labels)), SSDK_ERR_ARG,
+                 "create_targets: null pointer");
+    SSDK_REQUIRE(aligned16(anchors) && aligned16(gt_boxes) && aligned16(out_reg), SSDK_ERR_SHAPE,
+                 "create_targets: box arrays must be 16-byte aligned");
+    create_targets_kernel<<<dim3(ceil_div_i(A, 256), B), 256, 0, ctx->stream>>>(
+        (const float4*)anchors, (int)A, (const float4*)gt_boxes, gt_labels, Gmax, matches, (float4*)out_reg, out_cls);
+    SSDK_CHECK_LAUNCH(ctx);
+    return SSDK_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,455 @@
+// Inference post-processing: score threshold -> per-(image, class) candidate lists -> sort -> greedy NMS -> pack.
+// Replaces detector/utils/nms.py:48-102 (batch_multiclass_non_max_suppression), :6-45
+// (multiclass_non_max_suppression), the sigmoid of detector/ssd.py:60 and TensorFlow 1.12's NonMaxSuppressionV3
+// (external C++ kernel called at nms.py:33; semantics restated in oracle/nms.py).
+//
+// Pipeline (all on the context's stream, no host synchronisation):
+//   1. filter_kernel      streams the [B,A,C] scores (or logits) once with 128-bit no-allocate loads and appends
+//                         a packed 64-bit key per (anchor, class) with score > threshold to the image's
+//                         candidate list (one warp-aggregated atomic per warp).  This is the HBM-bound kernel.
+//                         key = class | ~order(score) | anchor  ->  ascending u64 order == class ascending,
+//                         score descending, anchor index ascending.
+//                         The reference's `is_confident` anchor pre-filter (nms.py:71-74, '>=') only removes
+//                         anchors that have no candidate at all (candidates need '>'), so it cannot change any
+//                         output and is not materialised.
+//   2. sort_kernel        one CTA per image sorts the keys in shared memory (bitonic); images with more candidates
+//                         than fit fall back to a multi-CTA bitonic sort in global memory.  Also records the
+//                         [start, end) of every class segment.
+//   3. nms_kernel         one warp per (image, class): candidates are taken 32 at a time in sorted order, decoded
+//                         (box_utils.py:114-142) and clipped (nms.py:77) on the fly, tested against the boxes kept
+//                         so far (shared memory), then resolved inside the tile with warp ballots; stops at K.
+//   4. pack_kernel        class-major concatenation, zero padding to C*K and num_boxes (nms.py:83-93).
+#include <cooperative_groups.h>
+
+#include "common.cuh"
+
+namespace cg = cooperative_groups;
+
+#define FILTER_THREADS 256
+#define FILTER_UNROLL 4
+#define SORT_THREADS 1024
+#define SORT_SMEM_KEYS 16384          // 128 KB of keys
+#define NMS_WARPS 4
+
+struct KeyFormat {
+    int abits;       // bits for the anchor index
+    int cshift;      // 32 + abits
+};
+
+__device__ __forceinline__ unsigned order_desc(float s) {
+    unsigned u = __float_as_uint(s);
+    u = (u & 0x80000000u) ? ~u : (u | 0x80000000u);   // ascending total order of floats
+    return ~u;                                        // descending
+}
+__device__ __forceinline__ float key_score(unsigned long long key, KeyFormat f) {
+    unsigned u = ~(unsigned)((key >> f.abits) & 0xFFFFFFFFull);
+    u = (u & 0x80000000u) ? (u & 0x7FFFFFFFu) : ~u;
+    return __uint_as_float(u);
+}
+__device__ __forceinline__ int key_anchor(unsigned long long key, KeyFormat f) {
+    return (int)(key & ((1ull << f.abits) - 1ull));
+}
+__device__ __forceinline__ int key_class(unsigned long long key, KeyFormat f) { return (int)(key >> f.cshift); }
+__device__ __forceinline__ unsigned long long make_key(int c, float s, int a, KeyFormat f) {
+    return ((unsigned long long)c << f.cshift) | ((unsigned long long)order_desc(s) << f.abits) | (unsigned long long)a;
+}
+
+// ---------------------------------------------------------------------------------------------- 1. filter
+template <bool IS_LOGITS>
+__device__ __forceinline__ bool is_candidate(float v, float thr, float x_lo, float* score) {
+    if (IS_LOGITS) {
+        if (!(v > x_lo)) return false;                               // cheap reject in logit space (with margin)
+        const float s = f_div(1.0f, f_add(1.0f, expf(-v)));         // tf.sigmoid (ssd.py:60)
+        *score = s;
+        return s > thr;
+    }
+    *score = v;
+    return v > thr;                                                  // NonMaxSuppressionV3: strict '>'
+}
+
+template <bool IS_LOGITS>
+__global__ void __launch_bounds__(FILTER_THREADS) filter_kernel(
+    const float* __restrict__ scores, long long per_image /*A*C*/, int C, float thr, float x_lo, KeyFormat fmt,
+    unsigned long long* __restrict__ cand, long long cap, int* __restrict__ counts) {
+    const int b = blockIdx.y;
+    const float* base = scores + (size_t)b * per_image;
+    unsigned long long* out = cand + (size_t)b * cap;
+    int* count = counts + b;
+    const int lane = threadIdx.x & 31;
+    const unsigned lt_mask = (1u << lane) - 1u;
+
+    // peel to 16-byte alignment: head scalars | body float4 | tail scalars
+    const unsigned mis = (unsigned)(((uintptr_t)base >> 2) & 3);
+    long long head = mis ? (4 - mis) : 0;
+    if (head > per_image) head = per_image;
+    const long long nbody4 = (per_image - head) >> 2;
+    const long long tail0 = head + (nbody4 << 2);
+    const float4* body = (const float4*)(base + head);
+
+    if (blockIdx.x == 0 && threadIdx.x < 32) {
+        // head + tail elements (< 8 in total), one lane each, plain atomics
+        long long e = -1;
+        if (lane < head) e = lane;
+        else if (lane - head < per_image - tail0) e = tail0 + (lane - head);
+        if (e >= 0) {
+            float s;
+            if (is_candidate<IS_LOGITS>(base[e], thr, x_lo, &s)) {
+                const int a = (int)(e / C), c = (int)(e - (long long)a * C);
+                const int pos = atomicAdd(count, 1);
+                if (pos < cap) out[pos] = make_key(c, s, a, fmt);
+            }
+        }
+    }
+
+    const long long stride = (long long)gridDim.x * FILTER_THREADS * FILTER_UNROLL;
+    for (long long i0 = (long long)blockIdx.x * FILTER_THREADS * FILTER_UNROLL; i0 < nbody4; i0 += stride) {
+        float4 v[FILTER_UNROLL];
+        bool inb[FILTER_UNROLL];
+#pragma unroll
+        for (int u = 0; u < FILTER_UNROLL; ++u) {
+            const long long i = i0 + u * FILTER_THREADS + threadIdx.x;
+            inb[u] = i < nbody4;
+            v[u] = inb[u] ? ld_stream_f4(body + i) : make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+        }
+#pragma unroll
+        for (int u = 0; u < FILTER_UNROLL; ++u) {
+            const float lim = IS_LOGITS ? x_lo : thr;
+            const float mx = fmaxf(fmaxf(v[u].x, v[u].y), fmaxf(v[u].z, v[u].w));
+            const bool maybe = inb[u] && (mx > lim);
+            if (!__any_sync(0xffffffffu, maybe)) continue;            // warp-uniform fast path
+            const float vals[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+            float sc[4];
+            unsigned bal[4];
+            bool hit[4];
+            int total = 0;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                hit[j] = maybe && is_candidate<IS_LOGITS>(vals[j], thr, x_lo, &sc[j]);
+                bal[j] = __ballot_sync(0xffffffffu, hit[j]);
+                total += __popc(bal[j]);
+            }
+            if (total == 0) continue;
+            int basepos = 0;
+            if (lane == 0) basepos = atomicAdd(count, total);          // one atomic per warp
+            basepos = __shfl_sync(0xffffffffu, basepos, 0);
+            const long long e0 = head + ((i0 + u * FILTER_THREADS + threadIdx.x) << 2);
+            int run = 0;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                if (hit[j]) {
+                    const long long e = e0 + j;
+                    const int a = (int)(e / C), c = (int)(e - (long long)a * C);
+                    const long long pos = (long long)basepos + run + __popc(bal[j] & lt_mask);
+                    if (pos < cap) out[pos] = make_key(c, sc[j], a, fmt);
+                }
+                run += __popc(bal[j]);
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------- 2. sort
+__device__ __forceinline__ void mark_segments(const unsigned long long* keys, long long i, long long n, KeyFormat fmt,
+                                              int* seg_start, int* seg_end) {
+    const int c = key_class(keys[i], fmt);
+    if (i == 0 || key_class(keys[i - 1], fmt) != c) seg_start[c] = (int)i;
+    if (i == n - 1 || key_class(keys[i + 1], fmt) != c) seg_end[c] = (int)(i + 1);
+}
+
+// grid (nblk, B).  Images with n <= SORT_SMEM_KEYS: block 0 sorts in shared memory, the other blocks leave.
+// Larger images: all nblk blocks run a bitonic network on the global list (padded to a power of two with ~0 keys),
+// separated by a per-image software barrier (the launch is cooperative when nblk > 1, so blocks are co-resident).
+__global__ void __launch_bounds__(SORT_THREADS) sort_kernel(unsigned long long* __restrict__ cand, long long cap,
+                                                            const int* __restrict__ counts, KeyFormat fmt, int C,
+                                                            int* __restrict__ seg_start, int* __restrict__ seg_end,
+                                                            unsigned* __restrict__ barriers) {
+    extern __shared__ __align__(16) unsigned long long s_keys[];
+    const int b = blockIdx.y;
+    unsigned long long* keys = cand + (size_t)b * cap;
+    long long n = counts[b];
+    if (n > cap) n = cap;
+    int* sstart = seg_start + (size_t)b * C;
+    int* send = seg_end + (size_t)b * C;
+    if (n == 0) return;
+
+    if (n <= SORT_SMEM_KEYS) {
+        if (blockIdx.x != 0) return;
+        int P = 1;
+        while (P < n) P <<= 1;
+        for (int i = threadIdx.x; i < P; i += SORT_THREADS) s_keys[i] = (i < n) ? keys[i] : ~0ull;
+        __syncthreads();
+        for (int k = 2; k <= P; k <<= 1) {
+            for (int j = k >> 1; j > 0; j >>= 1) {
+                for (int t = threadIdx.x; t < (P >> 1); t += SORT_THREADS) {
+                    const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));   // lower index of the pair
+                    const int l = i | j;
+                    const unsigned long long x = s_keys[i], y = s_keys[l];
+                    const bool up = (i & k) == 0;
+                    if ((x > y) == up) { s_keys[i] = y; s_keys[l] = x; }
+                }
+                __syncthreads();
+            }
+        }
+        for (int i = threadIdx.x; i < n; i += SORT_THREADS) {
+            keys[i] = s_keys[i];
+            mark_segments(s_keys, i, n, fmt, sstart, send);
+        }
+        return;
+    }
+
+    // ---- large image: global bitonic sort shared by the nblk blocks of this image
+    long long P = 1;
+    while (P < n) P <<= 1;                      // P <= cap (cap is a power of two)
+    const long long gsize = (long long)gridDim.x * SORT_THREADS;
+    const long long gtid = (long long)blockIdx.x * SORT_THREADS + threadIdx.x;
+    unsigned* bar = barriers + b;
+    unsigned epoch = 0;
+    auto image_barrier = [&]() {
+        __syncthreads();
+        if (gridDim.x > 1) {
+            ++epoch;
+            if (threadIdx.x == 0) {
+                __threadfence();
+                atomicAdd(bar, 1u);
+                while (atomicAdd(bar, 0u) < epoch * gridDim.x) __nanosleep(64);
+                __threadfence();
+            }
+            __syncthreads();
+        }
+    };
+    for (long long i = n + gtid; i < P; i += gsize) keys[i] = ~0ull;
+    image_barrier();
+    for (long long k = 2; k <= P; k <<= 1) {
+        for (long long j = k >> 1; j > 0; j >>= 1) {
+            for (long long t = gtid; t < (P >> 1); t += gsize) {
+                const long long i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+                const long long l = i | j;
+                const unsigned long long x = keys[i], y = keys[l];
+                const bool up = (i & k) == 0;
+                if ((x > y) == up) { keys[i] = y; keys[l] = x; }
+            }
+            image_barrier();
+        }
+    }
+    for (long long i = gtid; i < n; i += gsize) mark_segments(keys, i, n, fmt, sstart, send);
+}
+
+// ---------------------------------------------------------------------------------------------- 3. NMS
+template <bool DECODED>
+__global__ void __launch_bounds__(NMS_WARPS * 32) nms_kernel(
+    const unsigned long long* __restrict__ cand, long long cap, KeyFormat fmt, const int* __restrict__ seg_start,
+    const int* __restrict__ seg_end, const float4* __restrict__ codes, const float4* __restrict__ anchors, long long A,
+    int B, int C, int K, float iou_thr, float4* __restrict__ seg_box, float* __restrict__ seg_score,
+    int* __restrict__ seg_anchor, int* __restrict__ seg_kept) {
+    extern __shared__ float4 s_kept_all[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long seg = (long long)blockIdx.x * NMS_WARPS + warp;
+    if (seg >= (long long)B * C) return;
+    const int b = (int)(seg / C);
+    const int start = seg_start[seg], end = seg_end[seg];
+    const int n = end - start;
+    float4* s_kept = s_kept_all + (size_t)warp * K;
+    const unsigned long long* keys = cand + (size_t)b * cap + start;
+    const size_t obase = (size_t)seg * K;
+    int kept = 0;
+
+    for (int base = 0; base < n && kept < K; base += 32) {
+        const int i = base + lane;
+        bool alive = i < n;
+        float4 box = make_float4(0.f, 0.f, 0.f, 0.f);
+        float score = 0.f;
+        int a = 0;
+        if (alive) {
+            const unsigned long long key = keys[i];
+            a = key_anchor(key, fmt);
+            score = key_score(key, fmt);
+            if (DECODED) box = codes[(size_t)b * A + a];
+            else box = box_clip01(box_decode(codes[(size_t)b * A + a], anchors[a]));   // nms.py:76-77
+        }
+        // against boxes kept from earlier tiles
+        for (int j = 0; j < kept; ++j)
+            if (alive && nms_iou_greater(box, s_kept[j], iou_thr)) alive = false;
+        // inside the tile: the lowest alive lane is the next box in score order
+        unsigned mask = __ballot_sync(0xffffffffu, alive);
+        while (mask != 0u && kept < K) {
+            const int l = __ffs(mask) - 1;
+            float4 kb;
+            kb.x = __shfl_sync(0xffffffffu, box.x, l); kb.y = __shfl_sync(0xffffffffu, box.y, l);
+            kb.z = __shfl_sync(0xffffffffu, box.z, l); kb.w = __shfl_sync(0xffffffffu, box.w, l);
+            if (lane == l) {
+                s_kept[kept] = box;
+                seg_box[obase + kept] = box;
+                seg_score[obase + kept] = score;
+                seg_anchor[obase + kept] = a;
+            }
+            ++kept;
+            if (alive && lane > l && nms_iou_greater(box, kb, iou_thr)) alive = false;
+            mask = __ballot_sync(0xffffffffu, alive) & ~((2u << l) - 1u);
+        }
+        __syncwarp();
+    }
+    if (lane == 0) seg_kept[seg] = kept;
+}
+
+// ---------------------------------------------------------------------------------------------- 4. pack
+__global__ void __launch_bounds__(256) pack_kernel(const float4* __restrict__ seg_box, const float* __restrict__ seg_score,
+                                                   const int* __restrict__ seg_anchor, const int* __restrict__ seg_kept,
+                                                   int C, int K, float4* __restrict__ out_boxes, float* __restrict__ out_scores,
+                                                   int* __restrict__ out_classes, int* __restrict__ out_num,
+                                                   int* __restrict__ out_anchor) {
+    extern __shared__ int s_off[];   // [C+1]
+    const int b = blockIdx.x;
+    const int* kept = seg_kept + (size_t)b * C;
+    if (threadIdx.x == 0) {
+        int t = 0;
+        for (int c = 0; c < C; ++c) { s_off[c] = t; t += kept[c]; }
+        s_off[C] = t;
+        out_num[b] = t;                                              // nms.py:81
+    }
+    __syncthreads();
+    const int total = s_off[C];
+    const size_t M = (size_t)C * K;
+    float4* ob = out_boxes + b * M;
+    float* os = out_scores + b * M;
+    int* oc = out_classes + b * M;
+    int* oa = out_anchor ? out_anchor + b * M : nullptr;
+    for (int idx = threadIdx.x; idx < C * K; idx += blockDim.x) {     // selected entries, class-major (nms.py:42-44)
+        const int c = idx / K, j = idx - c * K;
+        if (j < kept[c]) {
+            const size_t src = ((size_t)b * C + c) * K + j;
+            const int dst = s_off[c] + j;
+            ob[dst] = seg_box[src];
+            os[dst] = seg_score[src];
+            oc[dst] = c;
+            if (oa) oa[dst] = seg_anchor[src];
+        }
+    }
+    for (int idx = total + threadIdx.x; idx < C * K; idx += blockDim.x) {   // zero padding (nms.py:84-89)
+        ob[idx] = make_float4(0.f, 0.f, 0.f, 0.f);
+        os[idx] = 0.f;
+        oc[idx] = 0;
+        if (oa) oa[idx] = -1;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------- host side
+static int bits_for(long long n) {   // bits needed to represent values in [0, n)
+    int b = 1;
+    while ((1ll << b) < n) ++b;
+    return b;
+}
+
+static bool aligned16(const void* p) { return ((uintptr_t)p & 15) == 0; }
+
+extern "C" int ssdk_postprocess(ssdk_ctx* ctx, const float* codes, const float* anchors, const float* scores, int flags,
+                                int B, int64_t A, int C, double score_threshold, double iou_threshold, int K,
+                                float* out_boxes, float* out_scores, int32_t* out_classes, int32_t* out_num,
+                                int32_t* out_anchor_idx) {
+    SSDK_TRY(ssdk_ctx_enter(ctx));
+    SSDK_REQUIRE(B >= 0 && A >= 0 && C > 0 && K > 0, SSDK_ERR_ARG, "ssdk_postprocess: bad sizes (B=%d A=%lld C=%d K=%d)", B,
+                 (long long)A, C, K);
+    SSDK_REQUIRE(B <= 65535, SSDK_ERR_SHAPE, "ssdk_postprocess: batch %d > 65535", B);
+    if (B == 0) return SSDK_OK;
+    SSDK_REQUIRE(out_boxes && out_scores && out_classes && out_num, SSDK_ERR_ARG, "ssdk_postprocess: null output");
+    const bool decoded = (flags & SSDK_BOXES_DECODED) != 0;
+    const bool is_logits = (flags & SSDK_INPUT_LOGITS) != 0;
+    SSDK_REQUIRE(A == 0 || (codes && scores && (decoded || anchors)), SSDK_ERR_ARG, "ssdk_postprocess: null input");
+    SSDK_REQUIRE(aligned16(codes) && aligned16(anchors) && aligned16(out_boxes), SSDK_ERR_SHAPE,
+                 "ssdk_postprocess: box arrays must be 16-byte aligned");
+    SSDK_REQUIRE(((uintptr_t)scores & 3) == 0, SSDK_ERR_SHAPE, "ssdk_postprocess: scores must be 4-byte aligned");
+    const long long per_image = (long long)A * C;
+    SSDK_REQUIRE(per_image < (1ll << 31), SSDK_ERR_SHAPE, "ssdk_postprocess: A*C must be < 2^31");
+    SSDK_REQUIRE((size_t)NMS_WARPS * K * sizeof(float4) <= 200 * 1024, SSDK_ERR_SHAPE,
+                 "ssdk_postprocess: max_boxes_per_class %d too large", K);
+    KeyFormat fmt;
+    fmt.abits = bits_for(A > 1 ? A : 2);
+    fmt.cshift = 32 + fmt.abits;
+    SSDK_REQUIRE(fmt.cshift + bits_for(C > 1 ? C : 2) <= 64, SSDK_ERR_SHAPE, "ssdk_postprocess: A=%lld x C=%d does not fit the key",
+                 (long long)A, C);
+
+    // workspace: candidate keys (worst case: every (anchor, class) is a candidate; power of two per image for the
+    // bitonic fallback), counters + segment tables (zeroed every call), per-segment NMS results
+    long long cap = 1024;
+    while (cap < per_image) cap <<= 1;
+    SSDK_TRY(ssdk_ensure(ctx, &ctx->ws_cand, (size_t)B * cap * sizeof(unsigned long long)));
+    const size_t n_int = (size_t)B * 2 + 3 * (size_t)B * C;            // counts[B], barriers[B], start, end, kept
+    SSDK_TRY(ssdk_ensure(ctx, &ctx->ws_counts, n_int * sizeof(int)));
+    const size_t seg_elems = (size_t)B * C * K;
+    SSDK_TRY(ssdk_ensure(ctx, &ctx->ws_seg, seg_elems * (sizeof(float4) + sizeof(float) + sizeof(int))));
+    unsigned long long* cand = (unsigned long long*)ctx->ws_cand.p;
+    int* counts = (int*)ctx->ws_counts.p;
+    unsigned* barriers = (unsigned*)(counts + B);
+    int* seg_start = counts + 2 * (size_t)B;
+    int* seg_end = seg_start + (size_t)B * C;
+    int* seg_kept = seg_end + (size_t)B * C;
+    float4* seg_box = (float4*)ctx->ws_seg.p;
+    float* seg_score = (float*)(seg_box + seg_elems);
+    int* seg_anchor = (int*)(seg_score + seg_elems);
+    SSDK_CHECK_CUDA(cudaMemsetAsync(counts, 0, n_int * sizeof(int), ctx->stream));
+
+    const float thr = (float)score_threshold;
+    if (per_image > 0) {
+        // 1. filter
+        float x_lo = -INFINITY;
+        if (is_logits) {
+            if (score_threshold >= 1.0) x_lo = INFINITY;
+            else if (score_threshold > 0.0) {
+                const double lg = log(score_threshold / (1.0 - score_threshold));
+                x_lo = (float)(lg - 1e-3 * (1.0 + fabs(lg)));
+            }
+        }
+        long long chunks = (per_image / 4 + FILTER_THREADS * FILTER_UNROLL - 1) / (FILTER_THREADS * FILTER_UNROLL);
+        long long gx = ((long long)ctx->num_sms * 16 + B - 1) / B;
+        if (gx > chunks) gx = chunks;
+        if (gx < 1) gx = 1;
+        const dim3 fgrid((unsigned)gx, B);
+        if (is_logits)
+            filter_kernel<true><<<fgrid, FILTER_THREADS, 0, ctx->stream>>>(scores, per_image, C, thr, x_lo, fmt, cand, cap, counts);
+        else
+            filter_kernel<false><<<fgrid, FILTER_THREADS, 0, ctx->stream>>>(scores, per_image, C, thr, x_lo, fmt, cand, cap, counts);
+        SSDK_CHECK_LAUNCH(ctx);
+
+        // 2. sort (+ segment table)
+        const size_t sort_smem = (size_t)SORT_SMEM_KEYS * sizeof(unsigned long long);
+        SSDK_CHECK_CUDA(cudaFuncSetAttribute(sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sort_smem));
+        int nblk = 1;
+        if (per_image > SORT_SMEM_KEYS) {
+            int occ = 0;
+            SSDK_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sort_kernel, SORT_THREADS, sort_smem));
+            nblk = (ctx->num_sms * (occ > 0 ? occ : 1)) / B;
+            if (nblk < 1) nblk = 1;
+            if (nblk > 64) nblk = 64;
+        }
+        const dim3 sgrid(nblk, B);
+        if (nblk > 1) {
+            void* args[] = {(void*)&cand, (void*)&cap, (void*)&counts, (void*)&fmt, (void*)&C,
+                            (void*)&seg_start, (void*)&seg_end, (void*)&barriers};
+            SSDK_CHECK_CUDA(cudaLaunchCooperativeKernel((void*)sort_kernel, sgrid, dim3(SORT_THREADS), args, sort_smem, ctx->stream));
+            ctx->launches++;
+        } else {
+            sort_kernel<<<sgrid, SORT_THREADS, sort_smem, ctx->stream>>>(cand, cap, counts, fmt, C, seg_start, seg_end, barriers);
+            SSDK_CHECK_LAUNCH(ctx);
+        }
+
+        // 3. NMS, one warp per (image, class)
+        const size_t nms_smem = (size_t)NMS_WARPS * K * sizeof(float4);
+        const int ngrid = ceil_div_i((long long)B * C, NMS_WARPS);
+        if (decoded) {
+            SSDK_CHECK_CUDA(cudaFuncSetAttribute(nms_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)nms_smem));
+            nms_kernel<true><<<ngrid, NMS_WARPS * 32, nms_smem, ctx->stream>>>(cand, cap, fmt, seg_start, seg_end, (const float4*)codes,
+                                                                              (const float4*)anchors, A, B, C, K, (float)iou_threshold,
+                                                                              seg_box, seg_score, seg_anchor, seg_kept);
+        } else {
+            SSDK_CHECK_CUDA(cudaFuncSetAttribute(nms_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)nms_smem));
+            nms_kernel<false><<<ngrid, NMS_WARPS * 32, nms_smem, ctx->stream>>>(cand, cap, fmt, seg_start, seg_end, (const float4*)codes,
+                                                                               (const float4*)anchors, A, B, C, K, (float)iou_threshold,
+                                                                               seg_box, seg_score, seg_anchor, seg_kept);
+        }
+        SSDK_CHECK_LAUNCH(ctx);
+    }
+    // 4. pack
+    pack_kernel<<<B, 256, (size_t)(C + 1) * sizeof(int), ctx->stream>>>(seg_box, seg_score, seg_anchor, seg_kept, C, K, (float4*)out_boxes,
+                                                                       out_scores, out_classes, out_num, out_anchor_idx);
+    SSDK_CHECK_LAUNCH(ctx);
+    return SSDK_OK;
+}

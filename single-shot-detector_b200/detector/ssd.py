@@ -1,0 +1,106 @@
+"""SSD head with the reference's interface (detector/ssd.py): anchors + raw predictions in, losses or
+detections out.  The network (feature extractor, box predictor) is NOT part of this package: any callables
+producing `encoded_boxes` [B,A,4] and `class_predictions` [B,A,C] (layout of box_predictor.py:67-104) plug in."""
+import torch
+
+from .. import _lib
+from .._tensors import Call, ptr
+from .constants import MIN_LEVEL, NEGATIVES_THRESHOLD, POSITIVES_THRESHOLD  # noqa: F401
+from .training_target_creation import batch_training_targets
+from .utils.nms import batch_multiclass_non_max_suppression
+
+
+class _ShapeOnly:
+    def __init__(self, shape):
+        self.shape = shape
+
+
+class SSD:
+    def __init__(self, images, feature_extractor, anchor_generator, box_predictor, num_classes):
+        """Same arguments as the reference (ssd.py:10-40).  `images`: [B, H, W, 3] tensor (only its shape is
+        used here); `feature_extractor(images)` and `box_predictor(features)` are the caller's network."""
+        self.num_classes = num_classes
+        image_features = feature_extractor(images)
+        image_height, image_width = int(images.shape[1]), int(images.shape[2])           # ssd.py:28-29
+        self.raw_predictions = box_predictor(image_features)                               # ssd.py:37
+        device = self.raw_predictions['class_predictions'].device \
+            if isinstance(self.raw_predictions['class_predictions'], torch.Tensor) else None
+        self.anchors = anchor_generator(image_height, image_width,
+                                        device=device if device is not None and device.type == 'cuda' else None)  # ssd.py:31
+        self.num_anchors_per_feature_map = anchor_generator.num_anchors_per_feature_map   # ssd.py:35
+        self.process_group = None      # set to a torch.distributed group (or True for WORLD) to all-reduce the sums
+
+    @classmethod
+    def from_predictions(cls, image_height, image_width, raw_predictions, anchor_generator, num_classes):
+        """Convenience constructor when the head outputs already exist."""
+        shape = (raw_predictions['encoded_boxes'].shape[0], int(image_height), int(image_width), 3)
+        fake_images = _ShapeOnly(shape)
+        return cls(fake_images, lambda x: None, anchor_generator, lambda f: raw_predictions, num_classes)
+
+    # ------------------------------------------------------------------ inference (ssd.py:42-69)
+    def get_predictions(self, score_threshold=0.05, iou_threshold=0.5, max_boxes_per_class=20):
+        """Returns {'boxes' [B,N,4], 'labels' [B,N] int, 'scores' [B,N], 'num_boxes' [B]}, N = C * max_boxes_per_class.
+        The sigmoid of ssd.py:60 is fused into the score-threshold pass."""
+        boxes, scores, classes, num = batch_multiclass_non_max_suppression(
+            self.raw_predictions['encoded_boxes'], self.anchors, self.raw_predictions['class_predictions'],
+            score_threshold=score_threshold, iou_threshold=iou_threshold,
+            max_boxes_per_class=max_boxes_per_class, scores_are_logits=True)
+        return {'boxes': boxes, 'labels': classes, 'scores': scores, 'num_boxes': num}
+
+    # ------------------------------------------------------------------ training (ssd.py:71-133)
+    def loss_sums(self, groundtruth, params, per_anchor=False):
+        """Un-normalised shard sums: float64 CUDA tensor [3] = (sum loc_losses, sum cls_losses, num_matches).
+        With per_anchor=True also returns the tensors the reference's summaries consume (ssd.py:125-129)."""
+        from . import ssd as this_module      # thresholds are module constants, as in ssd.py:187-188
+        call = Call()
+        logits = call.tensor(self.raw_predictions['class_predictions'], torch.float32)
+        B, A, C = logits.shape
+        codes = call.tensor(self.raw_predictions['encoded_boxes'], torch.float32, (B, A, 4))
+        anchors = call.tensor(self.anchors, torch.float32, (A, 4))
+        gt = call.tensor(groundtruth['boxes'], torch.float32)
+        G = gt.shape[1]
+        labels = call.tensor(groundtruth['labels'], torch.int32, (B, G))
+        num = call.tensor(groundtruth['num_boxes'], torch.int32, (B,))
+        sums = call.empty([3], torch.float64)
+        extra = {}
+        if per_anchor:
+            extra = {'reg_targets': call.empty([B, A, 4], torch.float32), 'cls_targets': call.empty([B, A], torch.int32),
+                     'matches': call.empty([B, A], torch.int32), 'cls_losses': call.empty([B, A], torch.float32),
+                     'loc_losses': call.empty([B, A], torch.float32)}
+        _lib.check(_lib.load().ssdk_ssd_targets_and_loss(
+            call.ctx(), ptr(anchors), ptr(logits), ptr(codes), ptr(gt), ptr(labels), ptr(num), B, A, C, G,
+            float(this_module.POSITIVES_THRESHOLD), float(this_module.NEGATIVES_THRESHOLD),
+            float(params['gamma']), float(params['alpha']), ptr(sums),
+            ptr(extra.get('reg_targets')), ptr(extra.get('cls_targets')), ptr(extra.get('matches')),
+            ptr(extra.get('cls_losses')), ptr(extra.get('loc_losses'))))
+        self._call = call
+        return (sums, extra) if per_anchor else sums
+
+    def loss(self, groundtruth, params):
+        """Returns {'localization_loss', 'classification_loss'}: two float32 scalars (0-d CUDA tensors), each
+        sum / max(num_matches, 1) (ssd.py:121-133).  When `self.process_group` is set the three sums are
+        all-reduced over the image shards first, so every rank returns the global losses."""
+        sums = self.loss_sums(groundtruth, params)
+        if self.process_group is not None:
+            import torch.distributed as dist
+            dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=None if self.process_group is True else self.process_group)
+        call = self._call
+        out = call.empty([2], torch.float32)
+        _lib.check(_lib.load().ssdk_loss_finalize(call.ctx(), ptr(sums), ptr(out)))
+        self.num_matches = sums[2]
+        if call.numpy_mode:
+            o = out.cpu().numpy()
+            return {'localization_loss': o[0], 'classification_loss': o[1]}
+        return {'localization_loss': out[0], 'classification_loss': out[1]}
+
+    def _create_targets(self, groundtruth):
+        """reference ssd.py:165-199: reg_targets [B,A,4], cls_targets [B,A], matches [B,A]."""
+        from . import ssd as this_module
+        return batch_training_targets(self.anchors, groundtruth['boxes'], groundtruth['labels'], groundtruth['num_boxes'],
+                                      positives_threshold=this_module.POSITIVES_THRESHOLD,
+                                      negatives_threshold=this_module.NEGATIVES_THRESHOLD)
+
+    def matches_per_level(self, matches):
+        """Matched-anchor count per image and FPN level, [B, L] (the quantity behind ssd.py:152-163)."""
+        w = (matches >= 0).to(torch.float32)
+        return torch.stack([c.sum(dim=1) for c in torch.split(w, self.num_anchors_per_feature_map, dim=1)], dim=1)
