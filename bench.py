@@ -1,0 +1,451 @@
+"""bench.py -- images/sec of the per-anchor detection hot path at 896x640 (BASELINE.json metric).
+
+One "step" per GPU = the training-side path (target assignment + focal / smooth-L1 loss, SSD.loss) over one
+cfg2 batch (16 images, 107,415 anchors, 90 classes, 20 GT boxes/image) PLUS the inference-side path
+(sigmoid + decode + per-class NMS, SSD.get_predictions, 0.05 / 0.5 / 100) over one cfg3 batch (32 images).
+value = images processed by all ranks per second ((16 + 32) * n_gpus / step time); the two sub-paths are also
+reported separately under "breakdown".
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
+
+--impl reference times the reference's CPU semantics (the NumPy/C oracle port; TensorFlow cannot be installed
+here) on the host cores, on a bounded sample of the same workload.
+"""
+import argparse
+import importlib
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+PKG = 'single-shot-detector_b200'
+
+TRAIN_CFG, INFER_CFG = 2, 3
+SCORE_THR, IOU_THR, K_PER_CLASS = 0.05, 0.5, 100
+PARAMS = {'gamma': 2.0, 'alpha': 0.25}
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=30)
+    ap.add_argument('--warmup', type=int, default=5)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--e2e-steps', type=int, default=0, help='steps of the host-buffer (e2e) loop; 0 = min(steps, 10)')
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--cpu-sample', type=int, default=2, help='cpu_baseline sample: this many train images + 2x infer images')
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------ workload
+def algorithmic_bytes(A, C, G, K):
+    """bytes per image, each tensor counted once."""
+    train = 4 * A * C + 56 * A + 20 * G
+    infer = 4 * A * C + 32 * A + 24 * C * K + 4
+    loss_kernel = 4 * A * C + 16 * A + 16 * A + 8 * A          # logits + codes + reg_targets + (cls, matches)
+    filter_kernel = 4 * A * C                                   # scores read once (+ the few candidates written)
+    return train, infer, loss_kernel, filter_kernel
+
+
+def make_host_inputs(syn, rank, pin):
+    import torch
+    out = {}
+    for name, cfg_id, kind in (('train', TRAIN_CFG, 'train'), ('infer', INFER_CFG, 'realistic')):
+        cfg = syn.CONFIGS[cfg_id]
+        B, H, W, C, G = cfg['B'], cfg['H'], cfg['W'], cfg['C'], cfg['G']
+        first = rank * B
+        out[name] = dict(cfg=cfg, B=B, H=H, W=W, C=C, G=G, first=first, kind=kind)
+    return out
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 100 ms while the timed regions run."""
+    Q = ('timestamp,index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,'
+         'clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+         'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, gpu_index):
+        self.path = tempfile.mktemp(prefix='clocks_', suffix='.csv')
+        self.proc = None
+        self.windows = []
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(gpu_index), '--query-gpu=' + self.Q,
+                                          '--format=csv,noheader,nounits', '-lms', '100'],
+                                         stdout=open(self.path, 'w'), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def window(self, t0, t1):
+        self.windows.append((t0, t1))
+
+    def finish(self):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        rows = []
+        import datetime
+        for line in open(self.path):
+            f = [x.strip() for x in line.split(',')]
+            if len(f) < 10:
+                continue
+            try:
+                ts = datetime.datetime.strptime(f[0], '%Y/%m/%d %H:%M:%S.%f').timestamp()
+                rows.append((ts, float(f[2]), float(f[3]), f[5:]))
+            except Exception:
+                continue
+        try:
+            os.unlink(self.path)
+        except OSError:
+            pass
+        inside = [r for r in rows if any(t0 - 0.05 <= r[0] <= t1 + 0.05 for t0, t1 in self.windows)]
+        use = inside if inside else rows
+        if not use:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['no samples']}
+        names = ['active', 'hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        reasons = set()
+        for r in use:
+            for n, v in zip(names[1:], r[3][1:]):
+                if v.lower().startswith('active'):
+                    reasons.add(n)
+        return {'sm_mhz': float(np.median([r[1] for r in use])), 'sm_max_mhz': use[0][2],
+                'reasons': sorted(reasons), 'samples': len(use), 'samples_in_timed_region': len(inside)}
+
+
+# ------------------------------------------------------------------------------------------------ CPU reference arm
+def cpu_reference(n_train, n_infer, steps, warmup, threads):
+    """Reference semantics on the host cores: the oracle port (NumPy float32 op for op + C NonMaxSuppressionV3),
+    one image per task on a thread pool, as the reference's tf.map_fn does with parallel_iterations."""
+    from concurrent.futures import ThreadPoolExecutor
+    from oracle import ssd as ossd
+    from oracle.anchor_generator import AnchorGenerator as OracleGen
+    from oracle import nms as onms
+    syn = importlib.import_module(PKG + '.synthetic')
+    onms._lib()
+    tc, ic = syn.CONFIGS[TRAIN_CFG], syn.CONFIGS[INFER_CFG]
+    anchors = OracleGen(scale_multipliers=tc['scale_multipliers'])(tc['H'], tc['W'])
+    A = anchors.shape[0]
+    gt = syn.make_groundtruth(TRAIN_CFG, n_train, tc['G'], tc['H'], tc['W'], tc['C'])
+    t_logits = syn.make_logits('train', TRAIN_CFG, n_train, A, tc['C'])
+    t_codes = syn.make_codes(TRAIN_CFG, n_train, A)
+    igt = syn.make_groundtruth(INFER_CFG, n_infer, ic['G'], ic['H'], ic['W'], ic['C'])
+    i_logits = syn.make_logits('realistic', INFER_CFG, n_infer, A, ic['C'], anchors, igt)
+    i_codes = syn.make_codes(INFER_CFG, n_infer, A)
+
+    def train_image(b):
+        g = {k: v[b:b + 1] for k, v in gt.items()}
+        r = ossd.loss(anchors, t_codes[b:b + 1], t_logits[b:b + 1], g, PARAMS, tc['C'], return_all=True)
+        return r['loc_sum64'], r['cls_sum64'], float(r['num_matches'])
+
+    def infer_image(b):
+        p = ossd.get_predictions(anchors, i_codes[b:b + 1], i_logits[b:b + 1], SCORE_THR, IOU_THR, K_PER_CLASS)
+        return int(p['num_boxes'][0])
+
+    def step(pool):
+        futs = [pool.submit(train_image, b) for b in range(n_train)] + [pool.submit(infer_image, b) for b in range(n_infer)]
+        res = [f.result() for f in futs]
+        tr = np.array(res[:n_train], np.float64).sum(axis=0)
+        norm = max(tr[2], 1.0)
+        return tr[0] / norm, tr[1] / norm, sum(res[n_train:])
+
+    with ThreadPoolExecutor(max_workers=threads) as pool:
+        for _ in range(warmup):
+            step(pool)
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            out = step(pool)
+        dt = time.perf_counter() - t0
+    return (n_train + n_infer) * steps / dt, dt / steps, out
+
+
+def host_threads():
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    threads = host_threads()
+    n_train, n_infer = 4, 8          # bounded sample of the step (same 1:2 train:infer mix as the GPU arm)
+    steps, warmup = max(1, args.steps), max(0, args.warmup)
+    # keep the whole run within a few minutes whatever K the driver asks for
+    ips, sec, _ = cpu_reference(n_train, n_infer, 1, 0, threads)
+    budget = 150.0
+    if sec * (steps + warmup) > budget:
+        scale = max(1, int(budget / max(sec, 1e-3)))
+        warmup = min(warmup, max(1, scale // 10))
+        steps_run = max(1, scale - warmup)
+    else:
+        steps_run = steps
+    ips, sec, _ = cpu_reference(n_train, n_infer, steps_run, warmup, threads)
+    syn = importlib.import_module(PKG + '.synthetic')
+    line = {
+        'impl': 'reference', 'metric': 'images_per_sec_target_assign_focal_loss_and_decode_nms_896x640',
+        'value': ips, 'unit': 'images/s', 'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup,
+        'steps_timed': steps_run, 'ms_per_step': sec * 1e3, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+        'dtype': 'f32', 'data': 'synthetic',
+        'config': workload_config(syn, sample='%d train + %d infer images per step (bounded sample of the 16 + 32 step)' % (n_train, n_infer)),
+        'cpu_baseline': {'value': ips, 'unit': 'images/s', 'cores': threads, 'kind': 'port',
+                         'sample': '%d steps x (%d train + %d infer images), oracle port (NumPy f32 + C NMS), one image per thread-pool task'
+                                   % (steps_run, n_train, n_infer)},
+        'e2e': {'value': ips, 'unit': 'images/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'gpu_launches': 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(syn, sample=None):
+    tc, ic = syn.CONFIGS[TRAIN_CFG], syn.CONFIGS[INFER_CFG]
+    cfg = {
+        'workload': 'per step and GPU: SSD.loss (targets + focal/smooth-L1) on cfg2 batch %d  +  SSD.get_predictions '
+                    '(sigmoid, decode, per-class NMS %.2f/%.1f/%d) on cfg3 batch %d; 640x896, 5 FPN levels x 9 anchors '
+                    '= 107415 anchors, 90 classes, 20 GT boxes/image' % (tc['B'], SCORE_THR, IOU_THR, K_PER_CLASS, ic['B']),
+        'train_batch_per_gpu': tc['B'], 'infer_batch_per_gpu': ic['B'],
+        'logits': 'train: N(-4.595,1) prior-bias init; infer: N(-7,1) background + N(1.5,1.5) on anchors with IoU>=0.4 to a GT',
+        'l2': 'inputs per step (0.62 GB + 1.24 GB of logits) exceed the 126 MB L2; no flush needed',
+        'parallelism': 'image-sharded, one all-reduce of 3 doubles per step',
+    }
+    if sample:
+        cfg['sample'] = sample
+    return cfg
+
+
+# ------------------------------------------------------------------------------------------------ GPU arm
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    assert torch.cuda.is_available(), 'bench.py needs a GPU (no CPU fallback)'
+    torch.cuda.set_device(local_rank)
+    dev = torch.device('cuda', local_rank)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+    pkg = importlib.import_module(PKG)
+    syn = importlib.import_module(PKG + '.synthetic')
+    lib = pkg._lib
+
+    tc, ic = syn.CONFIGS[TRAIN_CFG], syn.CONFIGS[INFER_CFG]
+    H, W, C = tc['H'], tc['W'], tc['C']
+    gen = pkg.AnchorGenerator(scale_multipliers=tc['scale_multipliers'])
+    anchors = gen(H, W, device=dev)
+    A = anchors.shape[0]
+    anchors_np = anchors.cpu().numpy()
+    Bt, Bi, G = tc['B'], ic['B'], tc['G']
+
+    # ---- synthetic inputs in pinned host memory (what the e2e loop copies from), then resident copies in HBM
+    def pinned(shape, dtype):
+        return torch.empty(shape, dtype=dtype, pin_memory=True)
+
+    h_tlog, h_tcod = pinned([Bt, A, C], torch.float32), pinned([Bt, A, 4], torch.float32)
+    h_ilog, h_icod = pinned([Bi, A, C], torch.float32), pinned([Bi, A, 4], torch.float32)
+    gt = syn.make_groundtruth(TRAIN_CFG, Bt, G, H, W, C, first_image=rank * Bt)
+    igt = syn.make_groundtruth(INFER_CFG, Bi, G, H, W, C, first_image=rank * Bi)
+    syn.make_logits('train', TRAIN_CFG, Bt, A, C, first_image=rank * Bt, out=h_tlog.numpy())
+    syn.make_codes(TRAIN_CFG, Bt, A, first_image=rank * Bt, out=h_tcod.numpy())
+    syn.make_logits('realistic', INFER_CFG, Bi, A, C, anchors_np, igt, first_image=rank * Bi, out=h_ilog.numpy())
+    syn.make_codes(INFER_CFG, Bi, A, first_image=rank * Bi, out=h_icod.numpy())
+    d_tlog, d_tcod, d_ilog, d_icod = (t.to(dev) for t in (h_tlog, h_tcod, h_ilog, h_icod))
+    d_gt = {k: torch.from_numpy(v).to(dev) for k, v in gt.items()}
+
+    raw_t = {'encoded_boxes': d_tcod, 'class_predictions': d_tlog}
+    raw_i = {'encoded_boxes': d_icod, 'class_predictions': d_ilog}
+    ssd_t = pkg.SSD.from_predictions(H, W, raw_t, gen, C)
+    ssd_i = pkg.SSD.from_predictions(H, W, raw_i, gen, C)
+    if world > 1:
+        ssd_t.process_group = True
+
+    def step_resident():
+        losses = ssd_t.loss(d_gt, PARAMS)
+        pred = ssd_i.get_predictions(SCORE_THR, IOU_THR, K_PER_CLASS)
+        return losses, pred
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    for _ in range(max(args.warmup, 3)):
+        out = step_resident()
+    barrier()
+
+    # ---- timed region 1: inputs resident in HBM, CUDA events on the launching stream, max over ranks
+    l0 = lib.launch_count(local_rank)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    w0 = time.time()
+    ev0.record()
+    for _ in range(args.steps):
+        out = step_resident()
+    ev1.record()
+    barrier()
+    w1 = time.time()
+    ms = ev0.elapsed_time(ev1)
+    launches = lib.launch_count(local_rank) - l0
+    if sampler:
+        sampler.window(w0, w1)
+    t_ms = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+    ms_per_step = t_ms.item() / args.steps
+    value = (Bt + Bi) * world / (ms_per_step * 1e-3)
+    losses, pred = out
+    check = {'localization_loss': float(losses['localization_loss']), 'classification_loss': float(losses['classification_loss']),
+             'detections_image0': int(pred['num_boxes'][0])}
+
+    # ---- sub-path timings (same resident inputs), each its own event-timed loop
+    def timed(fn, n):
+        for _ in range(3):
+            fn()
+        barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(n):
+            fn()
+        b.record()
+        barrier()
+        t = torch.tensor([a.elapsed_time(b)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return t.item() / n
+    ms_train = timed(lambda: ssd_t.loss(d_gt, PARAMS), args.steps)
+    ms_infer = timed(lambda: ssd_i.get_predictions(SCORE_THR, IOU_THR, K_PER_CLASS), args.steps)
+
+    # ---- per-kernel durations (library-side CUDA events on the launching stream) for the roofline object
+    lib.set_profiling(True, local_rank)
+    for _ in range(min(args.steps, 10)):
+        step_resident()
+    prof = lib.profile_read(local_rank)
+    lib.set_profiling(False, local_rank)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
+    except Exception:
+        pass
+    peak = float(peaks.get('hbm_gbs', 6650.0))
+    peak_src = 'MEASURED_PEAKS.json hbm_gbs (of measured)' if 'hbm_gbs' in peaks else 'fallback 6650 GB/s (of fallback)'
+    b_train, b_infer, b_loss, b_filter = algorithmic_bytes(A, C, G, K_PER_CLASS)
+
+    def kernel_roof(name, bytes_per_launch):
+        tot, n = prof[name]
+        if n == 0:
+            return None
+        avg_ms = tot / n
+        ach = bytes_per_launch / (avg_ms * 1e-3) / 1e9
+        return {'kernel': name, 'bound': 'hbm', 'achieved': ach, 'peak': peak, 'unit': 'GB/s', 'frac': ach / peak,
+                'traffic': None, 'avg_launch_ms': avg_ms, 'algorithmic_bytes_per_launch': bytes_per_launch, 'peak_source': peak_src}
+    roof_loss = kernel_roof('ssd_loss', b_loss * Bt)
+    roof_filter = kernel_roof('filter', b_filter * Bi)
+    step_kernel_ms = {k: (v[0] / max(1, min(args.steps, 10))) for k, v in prof.items() if v[1]}
+    dominant = max((r for r in (roof_loss, roof_filter) if r), key=lambda r: r['avg_launch_ms'])
+    dominant = dict(dominant)
+    dominant['share_of_step_kernel_time'] = dominant['avg_launch_ms'] / max(1e-9, sum(step_kernel_ms.values()))
+
+    # ---- timed region 2 (e2e): the same step through the public API with HOST buffers; every step copies its inputs
+    #      from pinned host memory to the device and reads the results back (ssdk_*_host entry points)
+    h_raw_t = {'encoded_boxes': h_tcod.numpy(), 'class_predictions': h_tlog.numpy()}
+    h_raw_i = {'encoded_boxes': h_icod.numpy(), 'class_predictions': h_ilog.numpy()}
+    ssd_ht = pkg.SSD.from_predictions(H, W, h_raw_t, gen, C)
+    ssd_hi = pkg.SSD.from_predictions(H, W, h_raw_i, gen, C)
+    if world > 1:
+        ssd_ht.process_group = True
+    M = C * K_PER_CLASS
+    h_out = {'boxes': pinned([Bi, M, 4], torch.float32).numpy(), 'scores': pinned([Bi, M], torch.float32).numpy(),
+             'labels': pinned([Bi, M], torch.int32).numpy(), 'num_boxes': pinned([Bi], torch.int32).numpy()}
+
+    def step_host():
+        lo = ssd_ht.loss(gt, PARAMS)
+        pr = ssd_hi.get_predictions(SCORE_THR, IOU_THR, K_PER_CLASS, out=h_out)
+        return lo, pr
+    e2e_steps = args.e2e_steps or min(args.steps, 10)
+    for _ in range(2):
+        eo = step_host()
+    barrier()
+    w0 = time.time()
+    ev0.record()
+    for _ in range(e2e_steps):
+        eo = step_host()
+    ev1.record()
+    barrier()
+    w1 = time.time()
+    if sampler:
+        sampler.window(w0, w1)
+    t_ms = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+    e2e_ms = t_ms.item() / e2e_steps
+    h2d = sum(t.numel() * t.element_size() for t in (h_tlog, h_tcod, h_ilog, h_icod)) + 2 * anchors_np.nbytes + \
+        sum(v.nbytes for v in gt.values())
+    d2h = sum(v.nbytes for v in h_out.values()) + 32
+    e2e = {'value': (Bt + Bi) * world / (e2e_ms * 1e-3), 'unit': 'images/s', 'h2d_bytes_per_step': int(h2d),
+           'd2h_bytes_per_step': int(d2h), 'ms_per_step': e2e_ms, 'steps': e2e_steps,
+           'api': 'SSD.loss / SSD.get_predictions with NumPy (pinned) buffers -> ssdk_ssd_targets_and_loss_host, ssdk_postprocess_host',
+           'check': {'localization_loss': float(eo[0]['localization_loss']), 'classification_loss': float(eo[0]['classification_loss']),
+                     'detections_image0': int(eo[1]['num_boxes'][0])}}
+    clocks = sampler.finish() if sampler else None
+
+    if world > 1:
+        dist.barrier()
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        threads = host_threads()
+        n_t, n_i = args.cpu_sample, 2 * args.cpu_sample
+        ips, sec, _ = cpu_reference(n_t, n_i, 2, 1, threads)
+        cpu = {'value': ips, 'unit': 'images/s', 'cores': threads, 'kind': 'port',
+               'sample': '2 steps x (%d train + %d infer images) of the same workload, oracle port (NumPy f32 op-for-op + C '
+                         'NonMaxSuppressionV3), one image per thread-pool task' % (n_t, n_i)}
+
+    line = {
+        'metric': 'images_per_sec_target_assign_focal_loss_and_decode_nms_896x640',
+        'value': value, 'unit': 'images/s', 'n_gpus': world, 'steps': args.steps, 'warmup': max(args.warmup, 3),
+        'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+        'dtype': 'f32', 'data': 'synthetic', 'config': workload_config(syn),
+        'clocks': clocks, 'e2e': e2e, 'gpu_launches': int(launches),
+        'roofline': dominant,
+        'cpu_baseline': cpu,
+        'breakdown': {
+            'train_images_per_sec': Bt * world / (ms_train * 1e-3), 'train_ms_per_step': ms_train,
+            'train_frac_of_hbm_roofline': (b_train * Bt / (ms_train * 1e-3) / 1e9) / peak,
+            'infer_images_per_sec': Bi * world / (ms_infer * 1e-3), 'infer_ms_per_step': ms_infer,
+            'infer_frac_of_hbm_roofline': (b_infer * Bi / (ms_infer * 1e-3) / 1e9) / peak,
+            'algorithmic_bytes_per_image': {'train': b_train, 'infer': b_infer},
+            'kernel_ms_per_step': step_kernel_ms,
+            'roofline_ssd_loss': roof_loss, 'roofline_filter': roof_filter,
+        },
+        'check': check,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    a = parse()
+    if a.impl == 'reference':
+        run_reference(a)
+    else:
+        run_ours(a)

@@ -58,6 +58,13 @@ SSDK_API int ssdk_ctx_destroy(ssdk_ctx* ctx);
 SSDK_API int64_t ssdk_ctx_workspace_bytes(const ssdk_ctx* ctx);
 /* Counts kernel launches issued through this context since creation (bench.py's gpu_launches). */
 SSDK_API int64_t ssdk_ctx_launch_count(const ssdk_ctx* ctx);
+/* Optional per-kernel timing with CUDA events on the context's stream (for bench.py's roofline line; adds two
+ * event records per kernel while enabled).  ssdk_ctx_profile_read synchronises the stream and returns, per kernel
+ * id, the accumulated milliseconds and launch counts since the last reset.  Ids: 0 anchors, 1 match,
+ * 2 force_match, 3 ssd_loss, 4 loss_reduce, 5 filter, 6 sort, 7 nms, 8 pack, 9 other. */
+#define SSDK_NUM_KERNEL_IDS 10
+SSDK_API int ssdk_ctx_set_profiling(ssdk_ctx* ctx, int enable);
+SSDK_API int ssdk_ctx_profile_read(ssdk_ctx* ctx, double* out_ms, int64_t* out_calls, int n, int reset);
 /* cudaStreamSynchronize on the context's stream (synchronous). */
 SSDK_API int ssdk_ctx_synchronize(ssdk_ctx* ctx);
 

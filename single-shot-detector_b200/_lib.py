@@ -24,6 +24,8 @@ _SIGNATURES = {
     'ssdk_ctx_workspace_bytes': (c_i64, [P]),
     'ssdk_ctx_launch_count': (c_i64, [P]),
     'ssdk_ctx_synchronize': (c_int, [P]),
+    'ssdk_ctx_set_profiling': (c_int, [P, c_int]),
+    'ssdk_ctx_profile_read': (c_int, [P, P, P, c_int, c_int]),
     'ssdk_num_anchors': (c_int, [c_int, c_int, P, c_int, c_int, ctypes.POINTER(c_i64), P]),
     'ssdk_anchors': (c_int, [P, c_int, c_int, P, P, P, c_int, c_int, P, P]),
     'ssdk_area': (c_int, [P, P, c_i64, P]),
@@ -97,6 +99,22 @@ def context(device_index):
         check(lib.ssdk_ctx_create(int(device_index), None, ctypes.byref(h)))
         ctx = _contexts[key] = h
     return ctx
+
+
+KERNEL_IDS = ['anchors', 'match', 'force_match', 'ssd_loss', 'loss_reduce', 'filter', 'sort', 'nms', 'pack', 'other']
+
+
+def set_profiling(enable, device_index=0):
+    check(load().ssdk_ctx_set_profiling(context(device_index), 1 if enable else 0))
+
+
+def profile_read(device_index=0, reset=True):
+    """{kernel name: (total ms, launches)} measured with CUDA events on the context's stream."""
+    n = len(KERNEL_IDS)
+    ms = (c_double * n)()
+    calls = (c_i64 * n)()
+    check(load().ssdk_ctx_profile_read(context(device_index), ctypes.cast(ms, P), ctypes.cast(calls, P), n, 1 if reset else 0))
+    return {k: (ms[i], int(calls[i])) for i, k in enumerate(KERNEL_IDS)}
 
 
 def launch_count(device_index=0):

@@ -89,7 +89,7 @@ extern "C" int ssdk_anchors(ssdk_ctx* ctx, int H, int W, const int* strides, con
     SSDK_REQUIRE(total < (1ll << 31), SSDK_ERR_SHAPE, "too many anchors");
     for (int l = L; l <= SSDK_MAX_LEVELS; ++l) p.start[l] = (int)total;
     for (int k = 0; k < per_loc; ++k) p.ratios[k] = ratios[k];
-    anchors_kernel<<<ceil_div_i(total, 256), 256, 0, ctx->stream>>>(p, (float4*)out, (float4*)raw);
-    SSDK_CHECK_LAUNCH(ctx);
+    SSDK_KERNEL(ctx, SSDK_K_ANCHORS,
+                anchors_kernel<<<ceil_div_i(total, 256), 256, 0, ctx->stream>>>(p, (float4*)out, (float4*)raw));
     return SSDK_OK;
 }

@@ -33,7 +33,52 @@ int ssdk_ensure(ssdk_ctx* ctx, ssdk_buf* b, size_t bytes) {
     return SSDK_OK;
 }
 
+static int prof_drain(ssdk_ctx* ctx) {
+    if (ctx->prof_n == 0) return SSDK_OK;
+    SSDK_CHECK_CUDA(cudaStreamSynchronize(ctx->stream));
+    for (int i = 0; i < ctx->prof_n; ++i) {
+        float ms = 0.f;
+        SSDK_CHECK_CUDA(cudaEventElapsedTime(&ms, ctx->prof_ev[2 * i], ctx->prof_ev[2 * i + 1]));
+        ctx->prof_ms[ctx->prof_id[i]] += ms;
+        ctx->prof_calls[ctx->prof_id[i]] += 1;
+    }
+    ctx->prof_n = 0;
+    return SSDK_OK;
+}
+
+int ssdk_prof_begin(ssdk_ctx* ctx, int id) {
+    if (ctx->prof_n >= SSDK_PROFILE_EVENTS && prof_drain(ctx) != SSDK_OK) return -1;
+    const int slot = ctx->prof_n++;
+    ctx->prof_id[slot] = id;
+    cudaEventRecord(ctx->prof_ev[2 * slot], ctx->stream);
+    return slot;
+}
+
+void ssdk_prof_end(ssdk_ctx* ctx, int slot) { cudaEventRecord(ctx->prof_ev[2 * slot + 1], ctx->stream); }
+
 extern "C" {
+
+int ssdk_ctx_set_profiling(ssdk_ctx* ctx, int enable) {
+    SSDK_TRY(ssdk_ctx_enter(ctx));
+    if (enable && !ctx->prof_ev) {
+        ctx->prof_ev = new cudaEvent_t[2 * SSDK_PROFILE_EVENTS];
+        for (int i = 0; i < 2 * SSDK_PROFILE_EVENTS; ++i) SSDK_CHECK_CUDA(cudaEventCreate(&ctx->prof_ev[i]));
+    }
+    SSDK_TRY(prof_drain(ctx));
+    ctx->profiling = enable ? 1 : 0;
+    return SSDK_OK;
+}
+
+int ssdk_ctx_profile_read(ssdk_ctx* ctx, double* out_ms, int64_t* out_calls, int n, int reset) {
+    SSDK_TRY(ssdk_ctx_enter(ctx));
+    SSDK_TRY(prof_drain(ctx));
+    for (int i = 0; i < n && i < SSDK_K_COUNT; ++i) {
+        if (out_ms) out_ms[i] = ctx->prof_ms[i];
+        if (out_calls) out_calls[i] = ctx->prof_calls[i];
+    }
+    if (reset) for (int i = 0; i < SSDK_K_COUNT; ++i) { ctx->prof_ms[i] = 0; ctx->prof_calls[i] = 0; }
+    return SSDK_OK;
+}
 
 int ssdk_version(void) { return SSDK_VERSION; }
 
@@ -79,6 +124,10 @@ int ssdk_ctx_destroy(ssdk_ctx* ctx) {
                         &ctx->ws_cand, &ctx->ws_counts, &ctx->ws_seg};
     for (ssdk_buf* b : bufs) if (b->p) cudaFree(b->p);
     for (ssdk_buf& b : ctx->ws_stage) if (b.p) cudaFree(b.p);
+    if (ctx->prof_ev) {
+        for (int i = 0; i < 2 * SSDK_PROFILE_EVENTS; ++i) cudaEventDestroy(ctx->prof_ev[i]);
+        delete[] ctx->prof_ev;
+    }
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     for (int i = 0; i < 4; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
     delete ctx;

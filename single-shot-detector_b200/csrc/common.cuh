@@ -15,6 +15,13 @@ struct ssdk_buf {
     size_t cap = 0;
 };
 
+// kernel ids for the optional per-kernel event timing (ssdk_ctx_set_profiling)
+enum ssdk_kernel_id {
+    SSDK_K_ANCHORS = 0, SSDK_K_MATCH, SSDK_K_FORCE_MATCH, SSDK_K_LOSS, SSDK_K_LOSS_REDUCE, SSDK_K_FILTER,
+    SSDK_K_SORT, SSDK_K_NMS, SSDK_K_PACK, SSDK_K_OTHER, SSDK_K_COUNT
+};
+#define SSDK_PROFILE_EVENTS 2048
+
 struct ssdk_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
@@ -28,6 +35,13 @@ struct ssdk_ctx {
     ssdk_buf ws_counts;      // postprocess: per-image counters + per-(image,class) segment tables
     ssdk_buf ws_seg;         // postprocess: per-(image,class) kept boxes/scores/anchors
     ssdk_buf ws_stage[8];    // *_host entry points: device staging
+    // profiling: pairs of events around kernels, drained by ssdk_ctx_profile_read
+    int profiling = 0;
+    int prof_n = 0;
+    cudaEvent_t* prof_ev = nullptr;          // [2 * SSDK_PROFILE_EVENTS]
+    int prof_id[SSDK_PROFILE_EVENTS];
+    double prof_ms[SSDK_K_COUNT] = {0};
+    long long prof_calls[SSDK_K_COUNT] = {0};
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
 };
@@ -49,6 +63,17 @@ int ssdk_ensure(ssdk_ctx* ctx, ssdk_buf* b, size_t bytes);
     do {                                                                                   \
         (ctx)->launches++;                                                                 \
         SSDK_CHECK_CUDA(cudaGetLastError());                                               \
+    } while (0)
+
+// Bracket one kernel launch with events when profiling is on (no cost otherwise).
+int ssdk_prof_begin(ssdk_ctx* ctx, int id);
+void ssdk_prof_end(ssdk_ctx* ctx, int slot);
+#define SSDK_KERNEL(ctx, id, ...)                                                          \
+    do {                                                                                   \
+        const int _slot = (ctx)->profiling ? ssdk_prof_begin((ctx), (id)) : -1;            \
+        __VA_ARGS__;                                                                       \
+        if (_slot >= 0) ssdk_prof_end((ctx), _slot);                                       \
+        SSDK_CHECK_LAUNCH(ctx);                                                            \
     } while (0)
 
 #define SSDK_REQUIRE(cond, code, ...)                                                      \

@@ -282,10 +282,10 @@ static int launch_loss(ssdk_ctx* ctx, int grid, size_t smem, const float* logits
                        LossSmemLayout L, float* cls_losses, float* loc_losses, double* partials) {
     auto kern = ssd_loss_kernel<GM, PA>;
     SSDK_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<grid, LOSS_THREADS, smem, ctx->stream>>>(logits, (const float4*)codes, (const float4*)reg_t, cls_t, matches, NA, C,
-                                                    rows, (float)gamma, (float)alpha, (float)(1.0 - alpha), L, cls_losses,
-                                                    loc_losses, partials);
-    SSDK_CHECK_LAUNCH(ctx);
+    SSDK_KERNEL(ctx, SSDK_K_LOSS,
+                kern<<<grid, LOSS_THREADS, smem, ctx->stream>>>(logits, (const float4*)codes, (const float4*)reg_t, cls_t, matches,
+                                                                NA, C, rows, (float)gamma, (float)alpha, (float)(1.0 - alpha), L,
+                                                                cls_losses, loc_losses, partials));
     return SSDK_OK;
 }
 
@@ -337,8 +337,7 @@ int ssdk_ssd_loss(ssdk_ctx* ctx, const float* logits, const float* codes, const 
     else if (!pa) st = launch_loss<1, false>(ctx, (int)grid, smem, logits, codes, reg_targets, cls_targets, matches, NA, C, rows, gamma, alpha, L, out_cls_losses, out_loc_losses, partials);
     else st = launch_loss<1, true>(ctx, (int)grid, smem, logits, codes, reg_targets, cls_targets, matches, NA, C, rows, gamma, alpha, L, out_cls_losses, out_loc_losses, partials);
     SSDK_TRY(st);
-    loss_reduce_kernel<<<1, 256, 0, ctx->stream>>>(partials, (int)grid, out_sums);
-    SSDK_CHECK_LAUNCH(ctx);
+    SSDK_KERNEL(ctx, SSDK_K_LOSS_REDUCE, loss_reduce_kernel<<<1, 256, 0, ctx->stream>>>(partials, (int)grid, out_sums));
     return SSDK_OK;
 }
 

@@ -180,26 +180,26 @@ int ssdk_match_impl(ssdk_ctx* ctx, const float* anchors, int64_t A, const float*
     }
     const dim3 grid(ceil_div_i(A, MATCH_THREADS), B);
     const int same = (pos_thr == neg_thr) ? 1 : 0;   // compared as Python floats in the reference (:94)
-    if (targets)
-        match_kernel<true><<<grid, MATCH_THREADS, 0, ctx->stream>>>(
-            (const float4*)anchors, (int)A, (const float4*)gt_boxes, gt_labels, num_boxes, Gmax, (float)pos_thr,
-            (float)neg_thr, same, best, out_matches, (float4*)out_reg, out_cls);
-    else
-        match_kernel<false><<<grid, MATCH_THREADS, 0, ctx->stream>>>(
-            (const float4*)anchors, (int)A, (const float4*)gt_boxes, gt_labels, num_boxes, Gmax, (float)pos_thr,
-            (float)neg_thr, same, best, out_matches, nullptr, nullptr);
-    SSDK_CHECK_LAUNCH(ctx);
+    SSDK_KERNEL(ctx, SSDK_K_MATCH,
+        if (targets)
+            match_kernel<true><<<grid, MATCH_THREADS, 0, ctx->stream>>>(
+                (const float4*)anchors, (int)A, (const float4*)gt_boxes, gt_labels, num_boxes, Gmax, (float)pos_thr,
+                (float)neg_thr, same, best, out_matches, (float4*)out_reg, out_cls);
+        else
+            match_kernel<false><<<grid, MATCH_THREADS, 0, ctx->stream>>>(
+                (const float4*)anchors, (int)A, (const float4*)gt_boxes, gt_labels, num_boxes, Gmax, (float)pos_thr,
+                (float)neg_thr, same, best, out_matches, nullptr, nullptr));
     if (best) {
         const size_t smem = (size_t)Gmax * 5 + 16;
-        if (targets)
-            force_match_kernel<true><<<B, 256, smem, ctx->stream>>>((const float4*)anchors, (int)A, (const float4*)gt_boxes,
-                                                                   gt_labels, num_boxes, Gmax, best, out_matches,
-                                                                   (float4*)out_reg, out_cls);
-        else
-            force_match_kernel<false><<<B, 256, smem, ctx->stream>>>((const float4*)anchors, (int)A, (const float4*)gt_boxes,
-                                                                    gt_labels, num_boxes, Gmax, best, out_matches, nullptr,
-                                                                    nullptr);
-        SSDK_CHECK_LAUNCH(ctx);
+        SSDK_KERNEL(ctx, SSDK_K_FORCE_MATCH,
+            if (targets)
+                force_match_kernel<true><<<B, 256, smem, ctx->stream>>>((const float4*)anchors, (int)A, (const float4*)gt_boxes,
+                                                                       gt_labels, num_boxes, Gmax, best, out_matches,
+                                                                       (float4*)out_reg, out_cls);
+            else
+                force_match_kernel<false><<<B, 256, smem, ctx->stream>>>((const float4*)anchors, (int)A, (const float4*)gt_boxes,
+                                                                        gt_labels, num_boxes, Gmax, best, out_matches, nullptr,
+                                                                        nullptr));
     }
     return SSDK_OK;
 }

@@ -403,11 +403,11 @@ extern "C" int ssdk_postprocess(ssdk_ctx* ctx, const float* codes, const float* 
         if (gx > chunks) gx = chunks;
         if (gx < 1) gx = 1;
         const dim3 fgrid((unsigned)gx, B);
-        if (is_logits)
-            filter_kernel<true><<<fgrid, FILTER_THREADS, 0, ctx->stream>>>(scores, per_image, C, thr, x_lo, fmt, cand, cap, counts);
-        else
-            filter_kernel<false><<<fgrid, FILTER_THREADS, 0, ctx->stream>>>(scores, per_image, C, thr, x_lo, fmt, cand, cap, counts);
-        SSDK_CHECK_LAUNCH(ctx);
+        SSDK_KERNEL(ctx, SSDK_K_FILTER,
+            if (is_logits)
+                filter_kernel<true><<<fgrid, FILTER_THREADS, 0, ctx->stream>>>(scores, per_image, C, thr, x_lo, fmt, cand, cap, counts);
+            else
+                filter_kernel<false><<<fgrid, FILTER_THREADS, 0, ctx->stream>>>(scores, per_image, C, thr, x_lo, fmt, cand, cap, counts));
 
         // 2. sort (+ segment table)
         const size_t sort_smem = (size_t)SORT_SMEM_KEYS * sizeof(unsigned long long);
@@ -424,16 +424,19 @@ extern "C" int ssdk_postprocess(ssdk_ctx* ctx, const float* codes, const float* 
         if (nblk > 1) {
             void* args[] = {(void*)&cand, (void*)&cap, (void*)&counts, (void*)&fmt, (void*)&C,
                             (void*)&seg_start, (void*)&seg_end, (void*)&barriers};
-            SSDK_CHECK_CUDA(cudaLaunchCooperativeKernel((void*)sort_kernel, sgrid, dim3(SORT_THREADS), args, sort_smem, ctx->stream));
-            ctx->launches++;
+            SSDK_KERNEL(ctx, SSDK_K_SORT,
+                        SSDK_CHECK_CUDA(cudaLaunchCooperativeKernel((void*)sort_kernel, sgrid, dim3(SORT_THREADS), args, sort_smem,
+                                                                    ctx->stream)));
         } else {
-            sort_kernel<<<sgrid, SORT_THREADS, sort_smem, ctx->stream>>>(cand, cap, counts, fmt, C, seg_start, seg_end, barriers);
-            SSDK_CHECK_LAUNCH(ctx);
+            SSDK_KERNEL(ctx, SSDK_K_SORT,
+                        sort_kernel<<<sgrid, SORT_THREADS, sort_smem, ctx->stream>>>(cand, cap, counts, fmt, C, seg_start, seg_end,
+                                                                                   barriers));
         }
 
         // 3. NMS, one warp per (image, class)
         const size_t nms_smem = (size_t)NMS_WARPS * K * sizeof(float4);
         const int ngrid = ceil_div_i((long long)B * C, NMS_WARPS);
+        const int nms_slot = ctx->profiling ? ssdk_prof_begin(ctx, SSDK_K_NMS) : -1;
         if (decoded) {
             SSDK_CHECK_CUDA(cudaFuncSetAttribute(nms_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)nms_smem));
             nms_kernel<true><<<ngrid, NMS_WARPS * 32, nms_smem, ctx->stream>>>(cand, cap, fmt, seg_start, seg_end, (const float4*)codes,
@@ -445,11 +448,13 @@ extern "C" int ssdk_postprocess(ssdk_ctx* ctx, const float* codes, const float* 
                                                                                (const float4*)anchors, A, B, C, K, (float)iou_threshold,
                                                                                seg_box, seg_score, seg_anchor, seg_kept);
         }
+        if (nms_slot >= 0) ssdk_prof_end(ctx, nms_slot);
         SSDK_CHECK_LAUNCH(ctx);
     }
     // 4. pack
-    pack_kernel<<<B, 256, (size_t)(C + 1) * sizeof(int), ctx->stream>>>(seg_box, seg_score, seg_anchor, seg_kept, C, K, (float4*)out_boxes,
-                                                                       out_scores, out_classes, out_num, out_anchor_idx);
-    SSDK_CHECK_LAUNCH(ctx);
+    SSDK_KERNEL(ctx, SSDK_K_PACK,
+                pack_kernel<<<B, 256, (size_t)(C + 1) * sizeof(int), ctx->stream>>>(seg_box, seg_score, seg_anchor, seg_kept, C, K,
+                                                                                   (float4*)out_boxes, out_scores, out_classes,
+                                                                                   out_num, out_anchor_idx));
     return SSDK_OK;
 }

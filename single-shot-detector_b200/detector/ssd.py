@@ -1,6 +1,7 @@
 """SSD head with the reference's interface (detector/ssd.py): anchors + raw predictions in, losses or
 detections out.  The network (feature extractor, box predictor) is NOT part of this package: any callables
 producing `encoded_boxes` [B,A,4] and `class_predictions` [B,A,C] (layout of box_predictor.py:67-104) plug in."""
+import numpy as np
 import torch
 
 from .. import _lib
@@ -29,6 +30,7 @@ class SSD:
                                         device=device if device is not None and device.type == 'cuda' else None)  # ssd.py:31
         self.num_anchors_per_feature_map = anchor_generator.num_anchors_per_feature_map   # ssd.py:35
         self.process_group = None      # set to a torch.distributed group (or True for WORLD) to all-reduce the sums
+        self._anchors_host = None
 
     @classmethod
     def from_predictions(cls, image_height, image_width, raw_predictions, anchor_generator, num_classes):
@@ -37,10 +39,60 @@ class SSD:
         fake_images = _ShapeOnly(shape)
         return cls(fake_images, lambda x: None, anchor_generator, lambda f: raw_predictions, num_classes)
 
+    # ------------------------------------------------------------------ host (NumPy) buffers
+    def _host_mode(self):
+        return isinstance(self.raw_predictions['class_predictions'], np.ndarray)
+
+    def _host_args(self):
+        """Head outputs given as NumPy arrays are handed to the *_host C entry points as they are (zero-copy on
+        the Python side; pinned memory gives full PCIe speed)."""
+        logits = np.ascontiguousarray(self.raw_predictions['class_predictions'], dtype=np.float32)
+        codes = np.ascontiguousarray(self.raw_predictions['encoded_boxes'], dtype=np.float32)
+        if self._anchors_host is None:
+            self._anchors_host = np.ascontiguousarray(self.anchors.cpu().numpy())
+        return logits, codes, self._anchors_host
+
+    def _ctx(self):
+        dev = self.anchors.device
+        h = _lib.context(dev.index if dev.index is not None else torch.cuda.current_device())
+        _lib.check(_lib.load().ssdk_ctx_set_stream(h, torch.cuda.current_stream(dev).cuda_stream))
+        return h
+
+    def _get_predictions_host(self, score_threshold, iou_threshold, max_boxes_per_class, out=None):
+        logits, codes, anchors = self._host_args()
+        B, A, C = logits.shape
+        K = int(max_boxes_per_class)
+        if out is None:
+            out = {'boxes': np.empty([B, C * K, 4], np.float32), 'scores': np.empty([B, C * K], np.float32),
+                   'labels': np.empty([B, C * K], np.int32), 'num_boxes': np.empty([B], np.int32)}
+        _lib.check(_lib.load().ssdk_postprocess_host(
+            self._ctx(), codes.ctypes.data, anchors.ctypes.data, logits.ctypes.data,
+            _lib.SSDK_INPUT_LOGITS | _lib.SSDK_BOXES_ENCODED, B, A, C, float(score_threshold), float(iou_threshold), K,
+            out['boxes'].ctypes.data, out['scores'].ctypes.data, out['labels'].ctypes.data, out['num_boxes'].ctypes.data))
+        return out
+
+    def _loss_host(self, groundtruth, params):
+        from . import ssd as this_module
+        logits, codes, anchors = self._host_args()
+        B, A, C = logits.shape
+        gt = np.ascontiguousarray(groundtruth['boxes'], dtype=np.float32)
+        labels = np.ascontiguousarray(groundtruth['labels'], dtype=np.int32)
+        num = np.ascontiguousarray(groundtruth['num_boxes'], dtype=np.int32)
+        sums = np.zeros([3], np.float64)
+        losses = np.zeros([2], np.float32)
+        _lib.check(_lib.load().ssdk_ssd_targets_and_loss_host(
+            self._ctx(), anchors.ctypes.data, logits.ctypes.data, codes.ctypes.data, gt.ctypes.data, labels.ctypes.data,
+            num.ctypes.data, B, A, C, gt.shape[1], float(this_module.POSITIVES_THRESHOLD),
+            float(this_module.NEGATIVES_THRESHOLD), float(params['gamma']), float(params['alpha']),
+            sums.ctypes.data, losses.ctypes.data))
+        return sums, losses
+
     # ------------------------------------------------------------------ inference (ssd.py:42-69)
-    def get_predictions(self, score_threshold=0.05, iou_threshold=0.5, max_boxes_per_class=20):
+    def get_predictions(self, score_threshold=0.05, iou_threshold=0.5, max_boxes_per_class=20, out=None):
         """Returns {'boxes' [B,N,4], 'labels' [B,N] int, 'scores' [B,N], 'num_boxes' [B]}, N = C * max_boxes_per_class.
         The sigmoid of ssd.py:60 is fused into the score-threshold pass."""
+        if self._host_mode():
+            return self._get_predictions_host(score_threshold, iou_threshold, max_boxes_per_class, out)
         boxes, scores, classes, num = batch_multiclass_non_max_suppression(
             self.raw_predictions['encoded_boxes'], self.anchors, self.raw_predictions['class_predictions'],
             score_threshold=score_threshold, iou_threshold=iou_threshold,
@@ -80,6 +132,17 @@ class SSD:
         """Returns {'localization_loss', 'classification_loss'}: two float32 scalars (0-d CUDA tensors), each
         sum / max(num_matches, 1) (ssd.py:121-133).  When `self.process_group` is set the three sums are
         all-reduced over the image shards first, so every rank returns the global losses."""
+        if self._host_mode():
+            sums, losses = self._loss_host(groundtruth, params)
+            if self.process_group is not None:
+                import torch.distributed as dist
+                t = torch.from_numpy(sums).to(self.anchors.device)
+                dist.all_reduce(t, op=dist.ReduceOp.SUM, group=None if self.process_group is True else self.process_group)
+                sums = t.cpu().numpy()
+                norm = max(sums[2], 1.0)
+                losses = np.array([sums[0] / norm, sums[1] / norm], np.float32)
+            self.num_matches = sums[2]
+            return {'localization_loss': losses[0], 'classification_loss': losses[1]}
         sums = self.loss_sums(groundtruth, params)
         if self.process_group is not None:
             import torch.distributed as dist
