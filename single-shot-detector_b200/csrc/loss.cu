@@ -8,8 +8,11 @@
 //     (cp.async.bulk global->shared, mbarrier complete_tx) for the next tiles of `rows` consecutive anchors
 //     (rows*C contiguous floats) together with the tile's matches / cls_targets, while all warps compute on the
 //     current stage;
-//   * every warp takes anchor rows of the tile, lanes stride over the C classes (conflict-free LDS), the one
-//     positive class of a matched row is handled apart, ignored rows (matches == -2) are skipped;
+//   * the tile is summed FLAT (128-bit LDS, no per-element index math) as if every element were a negative;
+//     beforehand one thread per anchor row patches the exceptions in shared memory: the positive class of a
+//     matched row is evaluated apart and overwritten with -inf, ignored rows (matches == -2) become -inf
+//     (the negative term of -inf is exactly 0).  When per-anchor outputs are requested a row mapping is used
+//     instead (warps over rows, lanes over classes, shuffle reduction per row);
 //   * per element: e = exp(-|x|) (MUFU.EX2), r = 1/(1+e) (MUFU.RCP), p = x>=0 ? r : e*r,
 //     q = 1-(1-p) (the reference's own cancellation, losses.py:38,41), softplus = max(x,0) + e*P7(e) with a
 //     degree-7 minimax polynomial for log1p(e)/e on the FMA pipe (rel. error 2e-7), term = q^gamma * softplus;
@@ -178,7 +181,9 @@ __global__ void __launch_bounds__(LOSS_THREADS) ssd_loss_kernel(
             __syncthreads();
         }
 
-        // ---- localisation loss + matched count: one thread per anchor row of the tile (ssd.py:89,117,121)
+        // ---- per-row work, one thread per anchor row of the tile: localisation loss + matched count
+        //      (ssd.py:89,117,121) and, on the flat path, the row "patches" described below
+        float tile_acc = 0.0f;
         if (tid < nrows) {
             const int m = s_m[tid];
             float l = 0.0f;
@@ -188,35 +193,64 @@ __global__ void __launch_bounds__(LOSS_THREADS) ssd_loss_kernel(
                 acc_cnt += 1.0;
             }
             if (loc_losses) loc_losses[n0 + tid] = l;
-        }
-
-        // ---- focal loss: warps over rows, lanes over classes (ssd.py:96-109, losses.py:34-50)
-        float tile_acc = 0.0f;
-        float* out = s_out + (k & 1) * rows;
-        for (int r = warp; r < nrows; r += LOSS_WARPS) {
-            const int m = s_m[r];
-            float row = 0.0f;
-            if (m >= -1) {                                       // not_ignore (ssd.py:103)
-                const int tc = s_c[r] - 1;                       // one_hot(cls, C+1)[1:] -> class index, -1 = background
-                const float* x = s_x + r * C;
-                float neg = 0.0f;
-                if (tc < 0 || tc >= C) {
-                    for (int c = lane; c < C; c += 32) neg += focal_negative<GAMMA_MODE>(x[c], gamma);
-                    row = one_minus_alpha * neg;
+            if (!PER_ANCHOR) {
+                // Flat path: afterwards every element of the tile is summed as a NEGATIVE (target 0, weight 1).
+                // Rows that are not like that are patched in shared memory first: the positive class of a
+                // matched row is evaluated here and replaced by -inf, an ignored row (matches == -2, weight 0,
+                // ssd.py:103) is replaced by -inf entirely; focal_negative(-inf) == 0 exactly.
+                float* x = s_x + tid * C;
+                if (m < -1) {
+                    for (int c = 0; c < C; ++c) x[c] = -INFINITY;
                 } else {
-                    for (int c = lane; c < C; c += 32)
-                        if (c != tc) neg += focal_negative<GAMMA_MODE>(x[c], gamma);
-                    row = one_minus_alpha * neg;
-                    if (lane == (tc & 31)) row += alpha * focal_positive<GAMMA_MODE>(x[tc], gamma);
+                    const int tc = s_c[tid] - 1;                 // one_hot(cls, C+1)[1:] -> class index, -1 = background
+                    if (tc >= 0 && tc < C) {
+                        tile_acc = alpha * focal_positive<GAMMA_MODE>(x[tc], gamma);
+                        x[tc] = -INFINITY;
+                    }
                 }
             }
-            if (PER_ANCHOR) {
+        }
+
+        if (PER_ANCHOR) {
+            // ---- focal loss, row mapping: warps over rows, lanes over classes (ssd.py:96-109, losses.py:34-50)
+            float* out = s_out + (k & 1) * rows;
+            for (int r = warp; r < nrows; r += LOSS_WARPS) {
+                const int m = s_m[r];
+                float row = 0.0f;
+                if (m >= -1) {                                       // not_ignore (ssd.py:103)
+                    const int tc = s_c[r] - 1;
+                    const float* x = s_x + r * C;
+                    float neg = 0.0f;
+                    if (tc < 0 || tc >= C) {
+                        for (int c = lane; c < C; c += 32) neg += focal_negative<GAMMA_MODE>(x[c], gamma);
+                        row = one_minus_alpha * neg;
+                    } else {
+                        for (int c = lane; c < C; c += 32)
+                            if (c != tc) neg += focal_negative<GAMMA_MODE>(x[c], gamma);
+                        row = one_minus_alpha * neg;
+                        if (lane == (tc & 31)) row += alpha * focal_positive<GAMMA_MODE>(x[tc], gamma);
+                    }
+                }
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) row += __shfl_xor_sync(0xffffffffu, row, o);
                 if (lane == 0) { out[r] = row; tile_acc += row; }
-            } else {
-                tile_acc += row;
             }
+        } else {
+            // ---- focal loss, flat mapping: the tile is one contiguous run of nrows*C floats (a multiple of 4 for
+            //      full tiles); 128-bit LDS, four independent chains per thread and iteration
+            __syncthreads();                                         // patches visible
+            const int n4 = (nrows * C) >> 2;
+            const float4* x4 = (const float4*)s_x;
+            float neg = 0.0f;
+#pragma unroll 2
+            for (int i = tid; i < n4; i += LOSS_THREADS) {
+                const float4 v = x4[i];
+                neg += (focal_negative<GAMMA_MODE>(v.x, gamma) + focal_negative<GAMMA_MODE>(v.y, gamma)) +
+                       (focal_negative<GAMMA_MODE>(v.z, gamma) + focal_negative<GAMMA_MODE>(v.w, gamma));
+            }
+            for (int i = (n4 << 2) + tid; i < nrows * C; i += LOSS_THREADS)   // ragged last tile only
+                neg += focal_negative<GAMMA_MODE>(s_x[i], gamma);
+            tile_acc += one_minus_alpha * neg;
         }
         acc_cls += (double)tile_acc;
 
@@ -229,6 +263,7 @@ __global__ void __launch_bounds__(LOSS_THREADS) ssd_loss_kernel(
             }
         }
         if (PER_ANCHOR) {
+            const float* out = s_out + (k & 1) * rows;
             for (int i = tid; i < nrows; i += LOSS_THREADS) cls_losses[n0 + i] = out[i];
         }
     }

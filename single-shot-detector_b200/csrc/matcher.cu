@@ -42,6 +42,18 @@ __global__ void __launch_bounds__(MATCH_THREADS) match_kernel(
     if (valid) anc = anchors[a];
     const float area_a = box_area(anc);
 
+    // Bounding box of the warp's 32 consecutive anchors (neighbouring cells of one FPN level): a GT box that does
+    // not overlap it has intersection 0 -- hence IoU exactly 0 -- with every lane, and is skipped warp-uniformly.
+    float wy0 = valid ? anc.x : INFINITY, wx0 = valid ? anc.y : INFINITY;
+    float wy1 = valid ? anc.z : -INFINITY, wx1 = valid ? anc.w : -INFINITY;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        wy0 = fminf(wy0, __shfl_xor_sync(0xffffffffu, wy0, o));
+        wx0 = fminf(wx0, __shfl_xor_sync(0xffffffffu, wx0, o));
+        wy1 = fmaxf(wy1, __shfl_xor_sync(0xffffffffu, wy1, o));
+        wx1 = fmaxf(wx1, __shfl_xor_sync(0xffffffffu, wx1, o));
+    }
+
     float best_v = 0.0f;   // IoU is clipped to [0,1]: starting from (0, index 0) with strict '>' is tf.argmax
     int best_g = 0;
 
@@ -57,6 +69,7 @@ __global__ void __launch_bounds__(MATCH_THREADS) match_kernel(
         __syncthreads();
         for (int t = 0; t < n; ++t) {
             const float4 gb = s_box[t];
+            if (gb.z <= wy0 || gb.x >= wy1 || gb.w <= wx0 || gb.y >= wx1) continue;   // no lane intersects: all IoU == 0
             // iou(groundtruth_boxes, anchors): box_utils.py:14-27.  inter == 0 -> 0 / (union + eps) == 0 exactly.
             const float inter = box_intersection(gb, anc);
             float v = 0.0f;

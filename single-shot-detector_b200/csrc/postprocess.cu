@@ -15,9 +15,10 @@
 //   2. sort_kernel        one CTA per image sorts the keys in shared memory (bitonic); images with more candidates
 //                         than fit fall back to a multi-CTA bitonic sort in global memory.  Also records the
 //                         [start, end) of every class segment.
-//   3. nms_kernel         one warp per (image, class): candidates are taken 32 at a time in sorted order, decoded
+//   3. nms_kernel         one CTA per (image, class): candidates are taken 128 at a time in sorted order, decoded
 //                         (box_utils.py:114-142) and clipped (nms.py:77) on the fly, tested against the boxes kept
-//                         so far (shared memory), then resolved inside the tile with warp ballots; stops at K.
+//                         so far (shared memory); inside the chunk a 128x128 suppression bit matrix is built in
+//                         parallel (warp ballots give the alive set) and walked greedily; stops at K.
 //   4. pack_kernel        class-major concatenation, zero padding to C*K and num_boxes (nms.py:83-93).
 #include <cooperative_groups.h>
 
@@ -29,7 +30,7 @@ namespace cg = cooperative_groups;
 #define FILTER_UNROLL 4
 #define SORT_THREADS 1024
 #define SORT_SMEM_KEYS 16384          // 128 KB of keys
-#define NMS_WARPS 4
+#define NMS_THREADS 128
 
 struct KeyFormat {
     int abits;       // bits for the anchor index
@@ -235,60 +236,136 @@ __global__ void __launch_bounds__(SORT_THREADS) sort_kernel(unsigned long long* 
 }
 
 // ---------------------------------------------------------------------------------------------- 3. NMS
+// One CTA (NMS_THREADS threads) per (image, class) segment; the sorted candidates are consumed in chunks of
+// NMS_THREADS.  Per chunk: (a) every thread decodes one candidate and tests it against the boxes kept so far
+// (shared memory); (b) every surviving thread builds its row of the chunk's suppression bit matrix
+// (bit j set <=> j comes later in score order and IoU(t, j) > threshold); (c) one thread walks the rows in score
+// order (keep t unless an earlier kept row removed it, then OR its row into the removed set) until K boxes are
+// kept; (d) the kept boxes are appended to the kept list and to the segment's output.
+struct NmsBox {          // corners min/max-normalised as NonMaxSuppressionV3 does, area <= 0 never suppresses
+    float ymin, xmin, ymax, xmax;
+};
+
+__device__ __forceinline__ float nms_area(const NmsBox b) { return f_mul(f_sub(b.ymax, b.ymin), f_sub(b.xmax, b.xmin)); }
+
+__device__ __forceinline__ bool nms_suppresses(const NmsBox a, float area_a, const NmsBox b, float area_b, float thr) {
+    if (area_a <= 0.0f || area_b <= 0.0f) return false;
+    const float ih = fmaxf(f_sub(fminf(a.ymax, b.ymax), fmaxf(a.ymin, b.ymin)), 0.0f);
+    const float iw = fmaxf(f_sub(fminf(a.xmax, b.xmax), fmaxf(a.xmin, b.xmin)), 0.0f);
+    const float inter = f_mul(ih, iw);
+    if (inter <= 0.0f) return thr < 0.0f;                      // iou == 0 (union > 0 because both areas are)
+    return f_div(inter, f_sub(f_add(area_a, area_b), inter)) > thr;
+}
+
 template <bool DECODED>
-__global__ void __launch_bounds__(NMS_WARPS * 32) nms_kernel(
+__global__ void __launch_bounds__(NMS_THREADS) nms_kernel(
     const unsigned long long* __restrict__ cand, long long cap, KeyFormat fmt, const int* __restrict__ seg_start,
     const int* __restrict__ seg_end, const float4* __restrict__ codes, const float4* __restrict__ anchors, long long A,
-    int B, int C, int K, float iou_thr, float4* __restrict__ seg_box, float* __restrict__ seg_score,
+    int C, int K, float iou_thr, float4* __restrict__ seg_box, float* __restrict__ seg_score,
     int* __restrict__ seg_anchor, int* __restrict__ seg_kept) {
-    extern __shared__ float4 s_kept_all[];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const long long seg = (long long)blockIdx.x * NMS_WARPS + warp;
-    if (seg >= (long long)B * C) return;
-    const int b = (int)(seg / C);
-    const int start = seg_start[seg], end = seg_end[seg];
-    const int n = end - start;
-    float4* s_kept = s_kept_all + (size_t)warp * K;
+    extern __shared__ __align__(16) unsigned char nms_smem[];
+    NmsBox* s_kept = (NmsBox*)nms_smem;                         // [K]
+    float* s_kept_area = (float*)(s_kept + K);                  // [K]
+    __shared__ NmsBox s_box[NMS_THREADS];
+    __shared__ float4 s_raw[NMS_THREADS];
+    __shared__ float s_area[NMS_THREADS];
+    __shared__ float s_score[NMS_THREADS];
+    __shared__ int s_anchor[NMS_THREADS];
+    __shared__ unsigned s_mask[NMS_THREADS][NMS_THREADS / 32];
+    __shared__ unsigned s_alive[NMS_THREADS / 32];
+    __shared__ int s_list[NMS_THREADS];
+    __shared__ int s_cnt;
+
+    const int seg = blockIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int b = seg / C;
+    const int start = seg_start[seg];
+    const int n = seg_end[seg] - start;
+    if (n <= 0) {
+        if (tid == 0) seg_kept[seg] = 0;
+        return;
+    }
     const unsigned long long* keys = cand + (size_t)b * cap + start;
     const size_t obase = (size_t)seg * K;
     int kept = 0;
 
-    for (int base = 0; base < n && kept < K; base += 32) {
-        const int i = base + lane;
+    for (int base = 0; base < n && kept < K; base += NMS_THREADS) {
+        const int i = base + tid;
         bool alive = i < n;
-        float4 box = make_float4(0.f, 0.f, 0.f, 0.f);
-        float score = 0.f;
-        int a = 0;
+        NmsBox box = {0.f, 0.f, 0.f, 0.f};
+        float area = 0.f;
         if (alive) {
             const unsigned long long key = keys[i];
-            a = key_anchor(key, fmt);
-            score = key_score(key, fmt);
-            if (DECODED) box = codes[(size_t)b * A + a];
-            else box = box_clip01(box_decode(codes[(size_t)b * A + a], anchors[a]));   // nms.py:76-77
+            const int a = key_anchor(key, fmt);
+            float4 raw;
+            if (DECODED) raw = codes[(size_t)b * A + a];
+            else raw = box_clip01(box_decode(codes[(size_t)b * A + a], anchors[a]));        // nms.py:76-77
+            box.ymin = fminf(raw.x, raw.z); box.xmin = fminf(raw.y, raw.w);
+            box.ymax = fmaxf(raw.x, raw.z); box.xmax = fmaxf(raw.y, raw.w);
+            area = nms_area(box);
+            s_raw[tid] = raw;
+            s_score[tid] = key_score(key, fmt);
+            s_anchor[tid] = a;
+            // (a) against the boxes kept from earlier chunks
+            for (int j = 0; j < kept && alive; ++j)
+                if (nms_suppresses(box, area, s_kept[j], s_kept_area[j], iou_thr)) alive = false;
         }
-        // against boxes kept from earlier tiles
-        for (int j = 0; j < kept; ++j)
-            if (alive && nms_iou_greater(box, s_kept[j], iou_thr)) alive = false;
-        // inside the tile: the lowest alive lane is the next box in score order
-        unsigned mask = __ballot_sync(0xffffffffu, alive);
-        while (mask != 0u && kept < K) {
-            const int l = __ffs(mask) - 1;
-            float4 kb;
-            kb.x = __shfl_sync(0xffffffffu, box.x, l); kb.y = __shfl_sync(0xffffffffu, box.y, l);
-            kb.z = __shfl_sync(0xffffffffu, box.z, l); kb.w = __shfl_sync(0xffffffffu, box.w, l);
-            if (lane == l) {
-                s_kept[kept] = box;
-                seg_box[obase + kept] = box;
-                seg_score[obase + kept] = score;
-                seg_anchor[obase + kept] = a;
+        s_box[tid] = box;
+        s_area[tid] = area;
+        const unsigned bal = __ballot_sync(0xffffffffu, alive);
+        if (lane == 0) s_alive[warp] = bal;
+        __syncthreads();
+        // (b) row t of the suppression matrix, restricted to alive later candidates
+#pragma unroll
+        for (int w = 0; w < NMS_THREADS / 32; ++w) {
+            unsigned word = 0u;
+            if (alive && w >= warp) {
+                unsigned todo = s_alive[w];
+                if (w == warp) todo &= ~((2u << lane) - 1u);             // strictly later in score order
+                while (todo) {
+                    const int jj = __ffs(todo) - 1;
+                    todo &= todo - 1;
+                    const int j = w * 32 + jj;
+                    if (nms_suppresses(box, area, s_box[j], s_area[j], iou_thr)) word |= 1u << jj;
+                }
             }
-            ++kept;
-            if (alive && lane > l && nms_iou_greater(box, kb, iou_thr)) alive = false;
-            mask = __ballot_sync(0xffffffffu, alive) & ~((2u << l) - 1u);
+            s_mask[tid][w] = word;
         }
-        __syncwarp();
+        __syncthreads();
+        // (c) greedy walk in score order
+        if (tid == 0) {
+            unsigned removed[NMS_THREADS / 32];
+#pragma unroll
+            for (int w = 0; w < NMS_THREADS / 32; ++w) removed[w] = ~s_alive[w];
+            int cnt = 0;
+#pragma unroll
+            for (int w = 0; w < NMS_THREADS / 32; ++w) {
+                for (int jj = 0; jj < 32 && kept + cnt < K; ++jj) {
+                    if (!((removed[w] >> jj) & 1u)) {
+                        const int t = w * 32 + jj;
+                        s_list[cnt++] = t;
+#pragma unroll
+                        for (int v = 0; v < NMS_THREADS / 32; ++v) removed[v] |= s_mask[t][v];
+                    }
+                }
+            }
+            s_cnt = cnt;
+        }
+        __syncthreads();
+        // (d) append
+        const int cnt = s_cnt;
+        if (tid < cnt) {
+            const int t = s_list[tid];
+            s_kept[kept + tid] = s_box[t];
+            s_kept_area[kept + tid] = s_area[t];
+            seg_box[obase + kept + tid] = s_raw[t];
+            seg_score[obase + kept + tid] = s_score[t];
+            seg_anchor[obase + kept + tid] = s_anchor[t];
+        }
+        kept += cnt;
+        __syncthreads();
     }
-    if (lane == 0) seg_kept[seg] = kept;
+    if (tid == 0) seg_kept[seg] = kept;
 }
 
 // ---------------------------------------------------------------------------------------------- 4. pack
@@ -359,7 +436,7 @@ extern "C" int ssdk_postprocess(ssdk_ctx* ctx, const float* codes, const float* 
     SSDK_REQUIRE(((uintptr_t)scores & 3) == 0, SSDK_ERR_SHAPE, "ssdk_postprocess: scores must be 4-byte aligned");
     const long long per_image = (long long)A * C;
     SSDK_REQUIRE(per_image < (1ll << 31), SSDK_ERR_SHAPE, "ssdk_postprocess: A*C must be < 2^31");
-    SSDK_REQUIRE((size_t)NMS_WARPS * K * sizeof(float4) <= 200 * 1024, SSDK_ERR_SHAPE,
+    SSDK_REQUIRE((size_t)K * 20 <= 180 * 1024, SSDK_ERR_SHAPE,
                  "ssdk_postprocess: max_boxes_per_class %d too large", K);
     KeyFormat fmt;
     fmt.abits = bits_for(A > 1 ? A : 2);
@@ -433,20 +510,20 @@ extern "C" int ssdk_postprocess(ssdk_ctx* ctx, const float* codes, const float* 
                                                                                    barriers));
         }
 
-        // 3. NMS, one warp per (image, class)
-        const size_t nms_smem = (size_t)NMS_WARPS * K * sizeof(float4);
-        const int ngrid = ceil_div_i((long long)B * C, NMS_WARPS);
+        // 3. NMS, one CTA per (image, class)
+        const size_t nms_smem = (size_t)K * (sizeof(NmsBox) + sizeof(float));
+        const int ngrid = B * C;
         const int nms_slot = ctx->profiling ? ssdk_prof_begin(ctx, SSDK_K_NMS) : -1;
         if (decoded) {
             SSDK_CHECK_CUDA(cudaFuncSetAttribute(nms_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)nms_smem));
-            nms_kernel<true><<<ngrid, NMS_WARPS * 32, nms_smem, ctx->stream>>>(cand, cap, fmt, seg_start, seg_end, (const float4*)codes,
-                                                                              (const float4*)anchors, A, B, C, K, (float)iou_threshold,
-                                                                              seg_box, seg_score, seg_anchor, seg_kept);
+            nms_kernel<true><<<ngrid, NMS_THREADS, nms_smem, ctx->stream>>>(cand, cap, fmt, seg_start, seg_end, (const float4*)codes,
+                                                                           (const float4*)anchors, A, C, K, (float)iou_threshold,
+                                                                           seg_box, seg_score, seg_anchor, seg_kept);
         } else {
             SSDK_CHECK_CUDA(cudaFuncSetAttribute(nms_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)nms_smem));
-            nms_kernel<false><<<ngrid, NMS_WARPS * 32, nms_smem, ctx->stream>>>(cand, cap, fmt, seg_start, seg_end, (const float4*)codes,
-                                                                               (const float4*)anchors, A, B, C, K, (float)iou_threshold,
-                                                                               seg_box, seg_score, seg_anchor, seg_kept);
+            nms_kernel<false><<<ngrid, NMS_THREADS, nms_smem, ctx->stream>>>(cand, cap, fmt, seg_start, seg_end, (const float4*)codes,
+                                                                            (const float4*)anchors, A, C, K, (float)iou_threshold,
+                                                                            seg_box, seg_score, seg_anchor, seg_kept);
         }
         if (nms_slot >= 0) ssdk_prof_end(ctx, nms_slot);
         SSDK_CHECK_LAUNCH(ctx);
