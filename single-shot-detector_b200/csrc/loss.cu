@@ -3,26 +3,30 @@
 //
 // The reference materialises one_hot(cls_targets)[B,A,C+1], its slice, nlpt, p, p_t, the modulating factor, the
 // weighted loss and their product -- eight [B,A,C] float tensors -- and reads the logits several times.  Here
-// the logits are streamed from HBM exactly once:
-//   * a persistent CTA owns a ring of shared-memory stages; one thread issues TMA bulk copies
-//     (cp.async.bulk global->shared, mbarrier complete_tx) for the next tiles of `rows` consecutive anchors
-//     (rows*C contiguous floats) together with the tile's matches / cls_targets, while all warps compute on the
-//     current stage;
-//   * the tile is summed FLAT (128-bit LDS, no per-element index math) as if every element were a negative;
-//     beforehand one thread per anchor row patches the exceptions in shared memory: the positive class of a
-//     matched row is evaluated apart and overwritten with -inf, ignored rows (matches == -2) become -inf
-//     (the negative term of -inf is exactly 0).  When per-anchor outputs are requested a row mapping is used
-//     instead (warps over rows, lanes over classes, shuffle reduction per row);
-//   * per element: e = exp(-|x|) (MUFU.EX2), r = 1/(1+e) (MUFU.RCP), p = x>=0 ? r : e*r,
-//     q = 1-(1-p) (the reference's own cancellation, losses.py:38,41), softplus = max(x,0) + e*P7(e) with a
-//     degree-7 minimax polynomial for log1p(e)/e on the FMA pipe (rel. error 2e-7), term = q^gamma * softplus;
+// the logits are streamed from HBM exactly once by a persistent, warp-specialised kernel:
+//   * CTA = 8 consumer warps + 1 producer warp, a ring of shared-memory stages with full/empty mbarriers.
+//     The producer's elected lane issues TMA bulk copies (cp.async.bulk global->shared, complete_tx on the
+//     stage's `full` barrier) of the next tile: 8*rpw consecutive anchors = 8*rpw*C contiguous floats, plus the
+//     tile's matches / cls_targets.  No __syncthreads in the steady state.
+//   * each consumer warp owns rpw rows of the tile (a contiguous, 16-byte aligned run of rpw*C floats):
+//       - lanes < rpw do the per-row work: smooth-L1 + matched count for matched rows, and the row "patches":
+//         the positive class of a matched row is evaluated apart (full-precision libm) and overwritten with
+//         -inf, an ignored row (matches == -2, weight 0, ssd.py:103) is overwritten with -inf entirely;
+//       - then the run is summed FLAT as if every element were a negative: 128-bit LDS, no index math,
+//         focal_negative(-inf) == 0 exactly.  Per element: e = exp(-|x|) (MUFU.EX2), r = 1/(1+e) (MUFU.RCP),
+//         1-p_t = x>=0 ? r : 1-r, softplus = max(x,0) + e*P7(e) (degree-7 minimax polynomial for log1p(e)/e,
+//         relative error 2e-7); the polynomial and the products run on packed FFMA2/FMUL2/FADD2
+//         (fma.rn.f32x2, two elements per issue slot) because the kernel is issue-bound, not FMA-pipe-bound;
+//       - the warp releases the stage (fence.proxy.async + arrive on `empty`).
+//     When per-anchor outputs are requested (PER_ANCHOR) a row mapping is used instead: lanes over classes,
+//     shuffle reduction per row, the reference's 1-(1-p) rounding reproduced per element.
 //   * sums are carried per thread in double across tiles, reduced warp -> CTA, written as per-CTA partials and
 //     combined in a fixed order by a second kernel: deterministic, no float atomics.
 #include "common.cuh"
 
-#define LOSS_THREADS 256
-#define LOSS_WARPS (LOSS_THREADS / 32)
-#define LOSS_MAX_ROWS 256
+#define LOSS_CONSUMER_WARPS 8
+#define LOSS_THREADS ((LOSS_CONSUMER_WARPS + 1) * 32)
+#define LOSS_MAX_STAGES 4
 
 // ---------------------------------------------------------------------------------------------- PTX helpers
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
@@ -32,6 +36,9 @@ __device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned coun
 }
 __device__ __forceinline__ void mbar_arrive_expect_tx(unsigned long long* bar, unsigned bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
     unsigned done;
@@ -65,22 +72,53 @@ __device__ __forceinline__ float rcp_approx(float x) {
     return y;
 }
 
+// packed pairs of floats (Blackwell FFMA2 / FMUL2 / FADD2: one issue slot for two elements)
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pack2(float lo, float hi) {
+    f32x2 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void unpack2(f32x2 v, float& lo, float& hi) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
+    f32x2 d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
+    f32x2 d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) {
+    f32x2 d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ f32x2 splat2(float c) { return pack2(c, c); }
+
 // ---------------------------------------------------------------------------------------------- per-element math
-// log1p(e) for e in [0,1]:  e * P7(e), minimax fit of log1p(e)/e (relative error 1.9e-7)
+// log1p(e)/e on [0,1]: degree-7 minimax polynomial (relative error 1.9e-7)
+#define L1P_C7 -8.539209655e-03f
+#define L1P_C6 4.408963566e-02f
+#define L1P_C5 -1.076817184e-01f
+#define L1P_C4 1.774524181e-01f
+#define L1P_C3 -2.449546295e-01f
+#define L1P_C2 3.327547979e-01f
+#define L1P_C1 -4.999740540e-01f
+#define L1P_C0 9.999998057e-01f
+
 __device__ __forceinline__ float log1p_unit(float e) {
-    float p = -8.539209655e-03f;
-    p = fmaf(p, e, 4.408963566e-02f);
-    p = fmaf(p, e, -1.076817184e-01f);
-    p = fmaf(p, e, 1.774524181e-01f);
-    p = fmaf(p, e, -2.449546295e-01f);
-    p = fmaf(p, e, 3.327547979e-01f);
-    p = fmaf(p, e, -4.999740540e-01f);
-    p = fmaf(p, e, 9.999998057e-01f);
+    float p = L1P_C7;
+    p = fmaf(p, e, L1P_C6); p = fmaf(p, e, L1P_C5); p = fmaf(p, e, L1P_C4); p = fmaf(p, e, L1P_C3);
+    p = fmaf(p, e, L1P_C2); p = fmaf(p, e, L1P_C1); p = fmaf(p, e, L1P_C0);
     return p * e;
 }
 
-// Negative-class term without the (1-alpha) factor: (1 - p_t)^gamma * nlpt with targets == 0
-// (losses.py:36-41: nlpt = max(x,0) + log1p(exp(-|x|)), p_t = 1 - p, modulating factor (1 - p_t)^gamma).
+// Negative-class term without the (1-alpha) factor, reference rounding: (1 - p_t)^gamma * nlpt with targets == 0
+// (losses.py:36-41: nlpt = max(x,0) + log1p(exp(-|x|)), p_t = 1 - p, modulating factor (1 - (1 - p))^gamma).
 template <int GAMMA_MODE>
 __device__ __forceinline__ float focal_negative(float x, float gamma) {
     const float e = ex2_approx(-fabsf(x) * 1.4426950408889634f);
@@ -90,6 +128,32 @@ __device__ __forceinline__ float focal_negative(float x, float gamma) {
     const float nlpt = fmaxf(x, 0.0f) + log1p_unit(e);
     const float mod = (GAMMA_MODE == 0) ? q * q : powf(q, gamma);
     return mod * nlpt;
+}
+
+// Two negatives at once, packed: returns acc + mod * nlpt for both lanes of the pair.
+// 1 - p_t is formed as  x >= 0 ? r : 1 - r  with r = 1/(1+e) = sigmoid(|x|): for x < 0 this is the same quantity
+// as the reference's 1 - fl(1 - p) (r is fl(1 - p) to within an ulp), for x >= 0 the reference's 1 - (1 - p)
+// is exact (Sterbenz) and equals p = r.
+template <int GAMMA_MODE>
+__device__ __forceinline__ f32x2 focal_negative2(float x0, float x1, float gamma, f32x2 acc) {
+    const float e0 = ex2_approx(-fabsf(x0) * 1.4426950408889634f);
+    const float e1 = ex2_approx(-fabsf(x1) * 1.4426950408889634f);
+    const f32x2 e = pack2(e0, e1);
+    f32x2 p = fma2(splat2(L1P_C7), e, splat2(L1P_C6));
+    p = fma2(p, e, splat2(L1P_C5)); p = fma2(p, e, splat2(L1P_C4)); p = fma2(p, e, splat2(L1P_C3));
+    p = fma2(p, e, splat2(L1P_C2)); p = fma2(p, e, splat2(L1P_C1)); p = fma2(p, e, splat2(L1P_C0));
+    const f32x2 nlpt = fma2(p, e, pack2(fmaxf(x0, 0.0f), fmaxf(x1, 0.0f)));    // max(x,0) + log1p(exp(-|x|))
+    float d0, d1;
+    unpack2(add2(e, splat2(1.0f)), d0, d1);
+    const float r0 = rcp_approx(d0), r1 = rcp_approx(d1);
+    float c0, c1;
+    unpack2(fma2(pack2(r0, r1), splat2(-1.0f), splat2(1.0f)), c0, c1);         // 1 - r
+    const float q0 = (x0 >= 0.0f) ? r0 : c0, q1 = (x1 >= 0.0f) ? r1 : c1;
+    if (GAMMA_MODE == 0) {
+        const f32x2 q = pack2(q0, q1);
+        return fma2(mul2(q, q), nlpt, acc);
+    }
+    return fma2(pack2(powf(q0, gamma), powf(q1, gamma)), nlpt, acc);
 }
 
 // Positive-class term without the alpha factor (targets == 1): (1 - p)^gamma * (max(x,0) - x + log1p(exp(-|x|))).
@@ -123,102 +187,98 @@ struct LossSmemLayout {
 template <int GAMMA_MODE, bool PER_ANCHOR>
 __global__ void __launch_bounds__(LOSS_THREADS) ssd_loss_kernel(
     const float* __restrict__ logits, const float4* __restrict__ codes, const float4* __restrict__ reg_t,
-    const int* __restrict__ cls_t, const int* __restrict__ matches, long long NA, int C, int rows, float gamma,
-    float alpha, float one_minus_alpha, LossSmemLayout L, float* __restrict__ cls_losses, float* __restrict__ loc_losses,
-    double* __restrict__ partials /*[grid][3]*/) {
+    const int* __restrict__ cls_t, const int* __restrict__ matches, long long NA, int C, int rpw /*rows per warp*/,
+    float gamma, float alpha, float one_minus_alpha, LossSmemLayout L, float* __restrict__ cls_losses,
+    float* __restrict__ loc_losses, double* __restrict__ partials /*[grid][3]*/) {
     extern __shared__ __align__(128) unsigned char smem[];
-    unsigned long long* full = (unsigned long long*)smem;                 // [stages]
+    unsigned long long* full = (unsigned long long*)smem;                 // [stages]  producer -> consumers
+    unsigned long long* empty = full + LOSS_MAX_STAGES;                   // [stages]  consumers -> producer
     unsigned char* stage0 = smem + 128;
-    float* s_out = (float*)(stage0 + (size_t)L.stages * L.stage_bytes);    // [2][rows] per-anchor cls losses
+    __shared__ double s_red[LOSS_CONSUMER_WARPS][3];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int rows = rpw * LOSS_CONSUMER_WARPS;
     const long long ntiles = (NA + rows - 1) / rows;
     const long long first = blockIdx.x, step = gridDim.x;
 
     if (tid == 0) {
-        for (unsigned s = 0; s < L.stages; ++s) mbar_init(&full[s], 1);
+        for (unsigned s = 0; s < L.stages; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], LOSS_CONSUMER_WARPS);
+        }
         fence_mbar_init();
     }
     __syncthreads();
 
-    auto issue = [&](long long tile, unsigned s) {
-        // full tiles only (the caller handles the ragged last tile with plain loads)
-        const long long n0 = tile * rows;
-        unsigned char* st = stage0 + (size_t)s * L.stage_bytes;
-        mbar_arrive_expect_tx(&full[s], L.tile_bytes + 2 * L.meta_bytes);
-        bulk_g2s(st, logits + n0 * C, L.tile_bytes, &full[s]);
-        bulk_g2s(st + L.tile_bytes, matches + n0, L.meta_bytes, &full[s]);
-        bulk_g2s(st + L.tile_bytes + L.meta_bytes, cls_t + n0, L.meta_bytes, &full[s]);
-    };
-    auto is_full = [&](long long tile) { return (tile + 1) * rows <= NA; };
-
-    if (tid == 0) {
-        for (unsigned s = 0; s < L.stages; ++s) {
-            const long long t = first + (long long)s * step;
-            if (t < ntiles && is_full(t)) issue(t, s);
+    if (warp == LOSS_CONSUMER_WARPS) {
+        // =========================================================================== producer warp
+        long long k = 0;
+        for (long long tile = first; tile < ntiles; tile += step, ++k) {
+            const unsigned s = (unsigned)(k % L.stages);
+            if (k >= L.stages) mbar_wait(&empty[s], (unsigned)(((k / L.stages) - 1) & 1));
+            unsigned char* st = stage0 + (size_t)s * L.stage_bytes;
+            const long long n0 = tile * rows;
+            if ((tile + 1) * rows <= NA) {
+                if (lane == 0) {
+                    mbar_arrive_expect_tx(&full[s], L.tile_bytes + 2 * L.meta_bytes);
+                    bulk_g2s(st, logits + n0 * C, L.tile_bytes, &full[s]);
+                    bulk_g2s(st + L.tile_bytes, matches + n0, L.meta_bytes, &full[s]);
+                    bulk_g2s(st + L.tile_bytes + L.meta_bytes, cls_t + n0, L.meta_bytes, &full[s]);
+                }
+            } else {
+                // ragged last tile of the whole problem: plain loads by the producer warp, rows beyond NA are
+                // marked ignored (-2) so that the consumers skip them
+                const int nrows = (int)(NA - n0);
+                float* sx = (float*)st;
+                int* sm = (int*)(st + L.tile_bytes);
+                int* sc = (int*)(st + L.tile_bytes + L.meta_bytes);
+                for (int i = lane; i < rows * C; i += 32) sx[i] = (i < nrows * C) ? logits[n0 * C + i] : -INFINITY;
+                for (int i = lane; i < rows; i += 32) {
+                    sm[i] = (i < nrows) ? matches[n0 + i] : -2;
+                    sc[i] = (i < nrows) ? cls_t[n0 + i] : 0;
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&full[s]);
+            }
         }
+        return;
     }
 
+    // =============================================================================== consumer warps
     double acc_cls = 0.0, acc_loc = 0.0, acc_cnt = 0.0;
-
+    const int r0 = warp * rpw;                       // first row of this warp inside a tile
     long long k = 0;
     for (long long tile = first; tile < ntiles; tile += step, ++k) {
         const unsigned s = (unsigned)(k % L.stages);
-        const unsigned parity = (unsigned)((k / L.stages) & 1);
         unsigned char* st = stage0 + (size_t)s * L.stage_bytes;
-        float* s_x = (float*)st;
-        int* s_m = (int*)(st + L.tile_bytes);
-        int* s_c = (int*)(st + L.tile_bytes + L.meta_bytes);
-        const long long n0 = tile * rows;
-        const int nrows = (int)min((long long)rows, NA - n0);
+        float* s_x = (float*)st + (size_t)r0 * C;                         // this warp's rpw*C floats
+        const int* s_m = (const int*)(st + L.tile_bytes) + r0;
+        const int* s_c = (const int*)(st + L.tile_bytes + L.meta_bytes) + r0;
+        const long long n0 = tile * rows + r0;                            // global anchor index of the warp's first row
+        mbar_wait(&full[s], (unsigned)((k / L.stages) & 1));
 
-        if (is_full(tile)) {
-            mbar_wait(&full[s], parity);
-        } else {
-            // ragged last tile: plain cooperative loads
-            for (int i = tid; i < nrows * C; i += LOSS_THREADS) s_x[i] = logits[n0 * C + i];
-            for (int i = tid; i < nrows; i += LOSS_THREADS) { s_m[i] = matches[n0 + i]; s_c[i] = cls_t[n0 + i]; }
-            __syncthreads();
-        }
-
-        // ---- per-row work, one thread per anchor row of the tile: localisation loss + matched count
-        //      (ssd.py:89,117,121) and, on the flat path, the row "patches" described below
+        // ---- per-row work, one lane per anchor row: localisation loss + matched count (ssd.py:89,117,121)
         float tile_acc = 0.0f;
-        if (tid < nrows) {
-            const int m = s_m[tid];
+        int m = -2;
+        if (lane < rpw && n0 + lane < NA) {
+            m = s_m[lane];
             float l = 0.0f;
             if (m >= 0) {
-                l = smooth_l1_4(codes[n0 + tid], reg_t[n0 + tid]);
+                l = smooth_l1_4(codes[n0 + lane], reg_t[n0 + lane]);
                 acc_loc += (double)l;
                 acc_cnt += 1.0;
             }
-            if (loc_losses) loc_losses[n0 + tid] = l;
-            if (!PER_ANCHOR) {
-                // Flat path: afterwards every element of the tile is summed as a NEGATIVE (target 0, weight 1).
-                // Rows that are not like that are patched in shared memory first: the positive class of a
-                // matched row is evaluated here and replaced by -inf, an ignored row (matches == -2, weight 0,
-                // ssd.py:103) is replaced by -inf entirely; focal_negative(-inf) == 0 exactly.
-                float* x = s_x + tid * C;
-                if (m < -1) {
-                    for (int c = 0; c < C; ++c) x[c] = -INFINITY;
-                } else {
-                    const int tc = s_c[tid] - 1;                 // one_hot(cls, C+1)[1:] -> class index, -1 = background
-                    if (tc >= 0 && tc < C) {
-                        tile_acc = alpha * focal_positive<GAMMA_MODE>(x[tc], gamma);
-                        x[tc] = -INFINITY;
-                    }
-                }
-            }
+            if (loc_losses) loc_losses[n0 + lane] = l;
         }
 
         if (PER_ANCHOR) {
-            // ---- focal loss, row mapping: warps over rows, lanes over classes (ssd.py:96-109, losses.py:34-50)
-            float* out = s_out + (k & 1) * rows;
-            for (int r = warp; r < nrows; r += LOSS_WARPS) {
-                const int m = s_m[r];
+            // ---- focal loss, row mapping: lanes over classes (ssd.py:96-109, losses.py:34-50)
+            float mine = 0.0f;                       // lane r keeps the loss of row r
+            for (int r = 0; r < rpw; ++r) {
+                const int mr = __shfl_sync(0xffffffffu, m, r);
                 float row = 0.0f;
-                if (m >= -1) {                                       // not_ignore (ssd.py:103)
-                    const int tc = s_c[r] - 1;
+                if (mr >= -1) {                                      // not_ignore (ssd.py:103)
+                    const int tc = s_c[r] - 1;                       // one_hot(cls, C+1)[1:] -> class index, -1 = background
                     const float* x = s_x + r * C;
                     float neg = 0.0f;
                     if (tc < 0 || tc >= C) {
@@ -233,38 +293,47 @@ __global__ void __launch_bounds__(LOSS_THREADS) ssd_loss_kernel(
                 }
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) row += __shfl_xor_sync(0xffffffffu, row, o);
-                if (lane == 0) { out[r] = row; tile_acc += row; }
+                if (lane == r) mine = row;
+            }
+            if (lane < rpw && n0 + lane < NA) {
+                cls_losses[n0 + lane] = mine;
+                tile_acc = mine;
             }
         } else {
-            // ---- focal loss, flat mapping: the tile is one contiguous run of nrows*C floats (a multiple of 4 for
-            //      full tiles); 128-bit LDS, four independent chains per thread and iteration
-            __syncthreads();                                         // patches visible
-            const int n4 = (nrows * C) >> 2;
-            const float4* x4 = (const float4*)s_x;
-            float neg = 0.0f;
-#pragma unroll 2
-            for (int i = tid; i < n4; i += LOSS_THREADS) {
-                const float4 v = x4[i];
-                neg += (focal_negative<GAMMA_MODE>(v.x, gamma) + focal_negative<GAMMA_MODE>(v.y, gamma)) +
-                       (focal_negative<GAMMA_MODE>(v.z, gamma) + focal_negative<GAMMA_MODE>(v.w, gamma));
+            // ---- patches (see the header), then the flat sum
+            if (lane < rpw) {
+                float* x = s_x + lane * C;
+                if (m < -1) {
+                    for (int c = 0; c < C; ++c) x[c] = -INFINITY;
+                } else {
+                    const int tc = s_c[lane] - 1;
+                    if (tc >= 0 && tc < C) {
+                        tile_acc = alpha * focal_positive<GAMMA_MODE>(x[tc], gamma);
+                        x[tc] = -INFINITY;
+                    }
+                }
             }
-            for (int i = (n4 << 2) + tid; i < nrows * C; i += LOSS_THREADS)   // ragged last tile only
-                neg += focal_negative<GAMMA_MODE>(s_x[i], gamma);
-            tile_acc += one_minus_alpha * neg;
+            __syncwarp();
+            const int n4 = (rpw * C) >> 2;                           // rpw % 4 == 0 -> exact
+            const float4* x4 = (const float4*)s_x;
+            f32x2 a01 = 0ull, a23 = 0ull;
+#pragma unroll 2
+            for (int i = lane; i < n4; i += 32) {
+                const float4 v = x4[i];
+                a01 = focal_negative2<GAMMA_MODE>(v.x, v.y, gamma, a01);
+                a23 = focal_negative2<GAMMA_MODE>(v.z, v.w, gamma, a23);
+            }
+            float s0, s1;
+            unpack2(add2(a01, a23), s0, s1);
+            tile_acc += one_minus_alpha * (s0 + s1);
         }
         acc_cls += (double)tile_acc;
 
-        __syncthreads();   // every warp is done with stage s (and s_out[k&1] is complete)
-        if (tid == 0) {
-            const long long nt = tile + (long long)L.stages * step;
-            if (nt < ntiles && is_full(nt)) {
-                fence_proxy_async();
-                issue(nt, s);
-            }
-        }
-        if (PER_ANCHOR) {
-            const float* out = s_out + (k & 1) * rows;
-            for (int i = tid; i < nrows; i += LOSS_THREADS) cls_losses[n0 + i] = out[i];
+        // ---- release the stage: generic-proxy writes (patches) must be ordered before the next TMA write
+        __syncwarp();
+        if (lane == 0) {
+            fence_proxy_async();
+            mbar_arrive(&empty[s]);
         }
     }
 
@@ -275,13 +344,12 @@ __global__ void __launch_bounds__(LOSS_THREADS) ssd_loss_kernel(
         acc_loc += __shfl_xor_sync(0xffffffffu, acc_loc, o);
         acc_cnt += __shfl_xor_sync(0xffffffffu, acc_cnt, o);
     }
-    __shared__ double s_red[LOSS_WARPS][3];
     if (lane == 0) { s_red[warp][0] = acc_loc; s_red[warp][1] = acc_cls; s_red[warp][2] = acc_cnt; }
-    __syncthreads();
+    asm volatile("bar.sync 1, %0;" ::"n"(LOSS_CONSUMER_WARPS * 32) : "memory");   // consumers only (the producer has left)
     if (tid < 3) {
         double t = 0.0;
 #pragma unroll
-        for (int w = 0; w < LOSS_WARPS; ++w) t += s_red[w][tid];
+        for (int w = 0; w < LOSS_CONSUMER_WARPS; ++w) t += s_red[w][tid];
         partials[(size_t)blockIdx.x * 3 + tid] = t;
     }
 }
@@ -313,13 +381,13 @@ static bool aligned16(const void* p) { return ((uintptr_t)p & 15) == 0; }
 
 template <int GM, bool PA>
 static int launch_loss(ssdk_ctx* ctx, int grid, size_t smem, const float* logits, const float* codes, const float* reg_t,
-                       const int* cls_t, const int* matches, long long NA, int C, int rows, double gamma, double alpha,
+                       const int* cls_t, const int* matches, long long NA, int C, int rpw, double gamma, double alpha,
                        LossSmemLayout L, float* cls_losses, float* loc_losses, double* partials) {
     auto kern = ssd_loss_kernel<GM, PA>;
     SSDK_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     SSDK_KERNEL(ctx, SSDK_K_LOSS,
                 kern<<<grid, LOSS_THREADS, smem, ctx->stream>>>(logits, (const float4*)codes, (const float4*)reg_t, cls_t, matches,
-                                                                NA, C, rows, (float)gamma, (float)alpha, (float)(1.0 - alpha), L,
+                                                                NA, C, rpw, (float)gamma, (float)alpha, (float)(1.0 - alpha), L,
                                                                 cls_losses, loc_losses, partials));
     return SSDK_OK;
 }
@@ -340,25 +408,28 @@ int ssdk_ssd_loss(ssdk_ctx* ctx, const float* logits, const float* codes, const 
     SSDK_REQUIRE(logits && codes && reg_targets && cls_targets && matches, SSDK_ERR_ARG, "ssdk_ssd_loss: null pointer");
     SSDK_REQUIRE(aligned16(logits) && aligned16(codes) && aligned16(reg_targets) && aligned16(cls_targets) && aligned16(matches),
                  SSDK_ERR_SHAPE, "ssdk_ssd_loss: inputs must be 16-byte aligned");
-    SSDK_REQUIRE(C <= 8192, SSDK_ERR_SHAPE, "ssdk_ssd_loss: num_classes %d > 8192 not supported", C);
 
-    // tile = `rows` anchors (multiple of 8 so that rows*C*4 and rows*4 are multiples of 16), ~20 KB per stage
-    int rows = (int)((20480 / (4 * (long long)C)) / 8 * 8);
-    if (rows < 8) rows = 8;
-    if (rows > LOSS_MAX_ROWS) rows = LOSS_MAX_ROWS;
+    // tile = 8 consumer warps x rpw rows; rpw is a multiple of 4 (so rpw*C*4 and rpw*4 bytes are multiples of 16)
+    // and at most 32 (one lane per row); about 24 KB per stage
+    int rpw = (int)(24576 / (32 * (long long)C)) / 4 * 4;
+    if (rpw < 4) rpw = 4;
+    if (rpw > 32) rpw = 32;
+    const int rows = rpw * LOSS_CONSUMER_WARPS;
     LossSmemLayout L;
     L.tile_bytes = (unsigned)rows * C * 4;
     L.meta_bytes = (unsigned)rows * 4;
     L.stage_bytes = L.tile_bytes + 2 * L.meta_bytes;
-    L.stages = 3;
-    while (L.stages > 1 && 128 + (size_t)L.stages * L.stage_bytes + 2 * rows * 4 > 200 * 1024) L.stages--;
-    const size_t smem = 128 + (size_t)L.stages * L.stage_bytes + 2 * (size_t)rows * 4;
-    SSDK_REQUIRE(smem <= 227 * 1024, SSDK_ERR_SHAPE, "ssdk_ssd_loss: tile does not fit shared memory (C=%d)", C);
+    L.stages = 2;
+    SSDK_REQUIRE(128 + 2 * (size_t)L.stage_bytes <= 200 * 1024, SSDK_ERR_SHAPE,
+                 "ssdk_ssd_loss: num_classes %d too large for the fused kernel (limit about 780); use ssdk_focal_loss", C);
+    if (L.stage_bytes < 12 * 1024) L.stages = 4;
+    else if (L.stage_bytes < 20 * 1024) L.stages = 3;
+    const size_t smem = 128 + (size_t)L.stages * L.stage_bytes;
 
     const long long ntiles = (NA + rows - 1) / rows;
-    int per_sm = (int)((220 * 1024) / (smem + 1024));
+    int per_sm = (int)((227 * 1024) / (smem + 1024 + 256));
     if (per_sm < 1) per_sm = 1;
-    if (per_sm > 4) per_sm = 4;
+    if (per_sm > 5) per_sm = 5;
     long long grid = (long long)ctx->num_sms * per_sm;
     if (grid > ntiles) grid = ntiles;
 
@@ -367,10 +438,10 @@ int ssdk_ssd_loss(ssdk_ctx* ctx, const float* logits, const float* codes, const 
     const bool pa = out_cls_losses != nullptr;
     const bool g2 = (gamma == 2.0);
     int st;
-    if (g2 && !pa) st = launch_loss<0, false>(ctx, (int)grid, smem, logits, codes, reg_targets, cls_targets, matches, NA, C, rows, gamma, alpha, L, out_cls_losses, out_loc_losses, partials);
-    else if (g2 && pa) st = launch_loss<0, true>(ctx, (int)grid, smem, logits, codes, reg_targets, cls_targets, matches, NA, C, rows, gamma, alpha, L, out_cls_losses, out_loc_losses, partials);
-    else if (!pa) st = launch_loss<1, false>(ctx, (int)grid, smem, logits, codes, reg_targets, cls_targets, matches, NA, C, rows, gamma, alpha, L, out_cls_losses, out_loc_losses, partials);
-    else st = launch_loss<1, true>(ctx, (int)grid, smem, logits, codes, reg_targets, cls_targets, matches, NA, C, rows, gamma, alpha, L, out_cls_losses, out_loc_losses, partials);
+    if (g2 && !pa) st = launch_loss<0, false>(ctx, (int)grid, smem, logits, codes, reg_targets, cls_targets, matches, NA, C, rpw, gamma, alpha, L, out_cls_losses, out_loc_losses, partials);
+    else if (g2 && pa) st = launch_loss<0, true>(ctx, (int)grid, smem, logits, codes, reg_targets, cls_targets, matches, NA, C, rpw, gamma, alpha, L, out_cls_losses, out_loc_losses, partials);
+    else if (!pa) st = launch_loss<1, false>(ctx, (int)grid, smem, logits, codes, reg_targets, cls_targets, matches, NA, C, rpw, gamma, alpha, L, out_cls_losses, out_loc_losses, partials);
+    else st = launch_loss<1, true>(ctx, (int)grid, smem, logits, codes, reg_targets, cls_targets, matches, NA, C, rpw, gamma, alpha, L, out_cls_losses, out_loc_losses, partials);
     SSDK_TRY(st);
     SSDK_KERNEL(ctx, SSDK_K_LOSS_REDUCE, loss_reduce_kernel<<<1, 256, 0, ctx->stream>>>(partials, (int)grid, out_sums));
     return SSDK_OK;
@@ -379,8 +450,7 @@ int ssdk_ssd_loss(ssdk_ctx* ctx, const float* logits, const float* codes, const 
 int ssdk_loss_finalize(ssdk_ctx* ctx, const double* sums, float* out_losses) {
     SSDK_TRY(ssdk_ctx_enter(ctx));
     SSDK_REQUIRE(sums && out_losses, SSDK_ERR_ARG, "ssdk_loss_finalize: null pointer");
-    loss_finalize_kernel<<<1, 1, 0, ctx->stream>>>(sums, out_losses);
-    SSDK_CHECK_LAUNCH(ctx);
+    SSDK_KERNEL(ctx, SSDK_K_OTHER, loss_finalize_kernel<<<1, 1, 0, ctx->stream>>>(sums, out_losses));
     return SSDK_OK;
 }
 

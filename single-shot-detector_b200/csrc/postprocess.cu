@@ -15,10 +15,10 @@
 //   2. sort_kernel        one CTA per image sorts the keys in shared memory (bitonic); images with more candidates
 //                         than fit fall back to a multi-CTA bitonic sort in global memory.  Also records the
 //                         [start, end) of every class segment.
-//   3. nms_kernel         one CTA per (image, class): candidates are taken 128 at a time in sorted order, decoded
+//   3. nms_kernel         one warp per (image, class): candidates are taken 32 at a time in sorted order, decoded
 //                         (box_utils.py:114-142) and clipped (nms.py:77) on the fly, tested against the boxes kept
-//                         so far (shared memory); inside the chunk a 128x128 suppression bit matrix is built in
-//                         parallel (warp ballots give the alive set) and walked greedily; stops at K.
+//                         so far (shared memory); inside the tile a 32x32 suppression bit matrix is built (one
+//                         column per lane, warp ballot = alive set) and walked greedily with shuffles; stops at K.
 //   4. pack_kernel        class-major concatenation, zero padding to C*K and num_boxes (nms.py:83-93).
 #include <cooperative_groups.h>
 
@@ -30,7 +30,7 @@ namespace cg = cooperative_groups;
 #define FILTER_UNROLL 4
 #define SORT_THREADS 1024
 #define SORT_SMEM_KEYS 16384          // 128 KB of keys
-#define NMS_THREADS 128
+#define NMS_WARPS 4
 
 struct KeyFormat {
     int abits;       // bits for the anchor index
@@ -236,152 +236,166 @@ __global__ void __launch_bounds__(SORT_THREADS) sort_kernel(unsigned long long* 
 }
 
 // ---------------------------------------------------------------------------------------------- 3. NMS
-// One CTA (NMS_THREADS threads) per (image, class) segment; the sorted candidates are consumed in chunks of
-// NMS_THREADS.  Per chunk: (a) every thread decodes one candidate and tests it against the boxes kept so far
-// (shared memory); (b) every surviving thread builds its row of the chunk's suppression bit matrix
-// (bit j set <=> j comes later in score order and IoU(t, j) > threshold); (c) one thread walks the rows in score
-// order (keep t unless an earlier kept row removed it, then OR its row into the removed set) until K boxes are
-// kept; (d) the kept boxes are appended to the kept list and to the segment's output.
-struct NmsBox {          // corners min/max-normalised as NonMaxSuppressionV3 does, area <= 0 never suppresses
+// One warp per (image, class) segment; the sorted candidates are consumed 32 at a time (one per lane).
+// Per tile: (a) every lane decodes its candidate and tests it against the boxes kept so far (shared memory,
+// broadcast reads); (b) every lane builds its COLUMN of the tile's 32x32 suppression bit matrix (bit t set <=>
+// lane t comes earlier in score order and IoU(t, lane) > threshold); (c) the warp walks the alive lanes in score
+// order with shuffles -- lane j is kept iff no already kept lane is in its column -- until K boxes are kept;
+// (d) the kept lanes append themselves (rank by popc) to the kept list and to the segment's output.
+// Only tests against KEPT boxes and inside a 32-tile are ever made, so the work is O(n * kept + 32 n).
+struct NmsBox {          // corners min/max-normalised as NonMaxSuppressionV3 does; area <= 0 never suppresses
     float ymin, xmin, ymax, xmax;
 };
 
-__device__ __forceinline__ float nms_area(const NmsBox b) { return f_mul(f_sub(b.ymax, b.ymin), f_sub(b.xmax, b.xmin)); }
-
-__device__ __forceinline__ bool nms_suppresses(const NmsBox a, float area_a, const NmsBox b, float area_b, float thr) {
-    if (area_a <= 0.0f || area_b <= 0.0f) return false;
+// IoU(a, b) > thr with the exact float32 semantics of  inter / (area_a + area_b - inter) > thr  (IEEE divide).
+// nms_fast decides without the division whenever |inter - thr*union| > 2^-18 * |thr| * union (both roundings
+// involved are below 2^-23 relative, so outside that band the comparison is certain) and flags the rest as
+// ambiguous; nms_exact is the division.  Splitting the two lets four independent tests be in flight per lane.
+__device__ __forceinline__ void nms_fast(const NmsBox a, float area_a, const NmsBox b, float area_b, float thr, float band,
+                                         bool& yes, bool& ambiguous) {
     const float ih = fmaxf(f_sub(fminf(a.ymax, b.ymax), fmaxf(a.ymin, b.ymin)), 0.0f);
     const float iw = fmaxf(f_sub(fminf(a.xmax, b.xmax), fmaxf(a.xmin, b.xmin)), 0.0f);
     const float inter = f_mul(ih, iw);
-    if (inter <= 0.0f) return thr < 0.0f;                      // iou == 0 (union > 0 because both areas are)
+    const float uni = f_sub(f_add(area_a, area_b), inter);
+    const bool valid = (area_a > 0.0f) && (area_b > 0.0f);      // NonMaxSuppressionV3: area <= 0 never suppresses
+    const float d = fmaf(-thr, uni, inter);
+    const float m = band * uni;
+    yes = valid && (d > m);
+    ambiguous = valid && (fabsf(d) <= m);
+}
+__device__ __forceinline__ bool nms_exact(const NmsBox a, float area_a, const NmsBox b, float area_b, float thr) {
+    const float ih = fmaxf(f_sub(fminf(a.ymax, b.ymax), fmaxf(a.ymin, b.ymin)), 0.0f);
+    const float iw = fmaxf(f_sub(fminf(a.xmax, b.xmax), fmaxf(a.xmin, b.xmin)), 0.0f);
+    const float inter = f_mul(ih, iw);
     return f_div(inter, f_sub(f_add(area_a, area_b), inter)) > thr;
 }
 
 template <bool DECODED>
-__global__ void __launch_bounds__(NMS_THREADS) nms_kernel(
+__global__ void __launch_bounds__(NMS_WARPS * 32) nms_kernel(
     const unsigned long long* __restrict__ cand, long long cap, KeyFormat fmt, const int* __restrict__ seg_start,
     const int* __restrict__ seg_end, const float4* __restrict__ codes, const float4* __restrict__ anchors, long long A,
-    int C, int K, float iou_thr, float4* __restrict__ seg_box, float* __restrict__ seg_score,
+    long long nseg, int C, int K, float iou_thr, float4* __restrict__ seg_box, float* __restrict__ seg_score,
     int* __restrict__ seg_anchor, int* __restrict__ seg_kept) {
     extern __shared__ __align__(16) unsigned char nms_smem[];
-    NmsBox* s_kept = (NmsBox*)nms_smem;                         // [K]
-    float* s_kept_area = (float*)(s_kept + K);                  // [K]
-    __shared__ NmsBox s_box[NMS_THREADS];
-    __shared__ float4 s_raw[NMS_THREADS];
-    __shared__ float s_area[NMS_THREADS];
-    __shared__ float s_score[NMS_THREADS];
-    __shared__ int s_anchor[NMS_THREADS];
-    __shared__ unsigned s_mask[NMS_THREADS][NMS_THREADS / 32];
-    __shared__ unsigned s_alive[NMS_THREADS / 32];
-    __shared__ int s_list[NMS_THREADS];
-    __shared__ int s_cnt;
-
-    const int seg = blockIdx.x;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int b = seg / C;
+    __shared__ NmsBox s_tile[NMS_WARPS][32];
+    __shared__ float s_tile_area[NMS_WARPS][32];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long seg = (long long)blockIdx.x * NMS_WARPS + warp;
+    if (seg >= nseg) return;
+    NmsBox* s_kept = (NmsBox*)nms_smem + (size_t)warp * K;                                  // [K] per warp
+    float* s_kept_area = (float*)((NmsBox*)nms_smem + (size_t)NMS_WARPS * K) + (size_t)warp * K;
+    const int b = (int)(seg / C);
     const int start = seg_start[seg];
     const int n = seg_end[seg] - start;
-    if (n <= 0) {
-        if (tid == 0) seg_kept[seg] = 0;
-        return;
-    }
     const unsigned long long* keys = cand + (size_t)b * cap + start;
     const size_t obase = (size_t)seg * K;
+    const float band = fabsf(iou_thr) * 3.814697265625e-06f;
+    const unsigned lt_mask = (1u << lane) - 1u;
     int kept = 0;
 
-    for (int base = 0; base < n && kept < K; base += NMS_THREADS) {
-        const int i = base + tid;
+    for (int base = 0; base < n && kept < K; base += 32) {
+        const int i = base + lane;
         bool alive = i < n;
         NmsBox box = {0.f, 0.f, 0.f, 0.f};
-        float area = 0.f;
+        float4 raw = make_float4(0.f, 0.f, 0.f, 0.f);
+        float area = 0.f, score = 0.f;
+        int a = 0;
         if (alive) {
             const unsigned long long key = keys[i];
-            const int a = key_anchor(key, fmt);
-            float4 raw;
+            a = key_anchor(key, fmt);
+            score = key_score(key, fmt);
             if (DECODED) raw = codes[(size_t)b * A + a];
             else raw = box_clip01(box_decode(codes[(size_t)b * A + a], anchors[a]));        // nms.py:76-77
             box.ymin = fminf(raw.x, raw.z); box.xmin = fminf(raw.y, raw.w);
             box.ymax = fmaxf(raw.x, raw.z); box.xmax = fmaxf(raw.y, raw.w);
-            area = nms_area(box);
-            s_raw[tid] = raw;
-            s_score[tid] = key_score(key, fmt);
-            s_anchor[tid] = a;
-            // (a) against the boxes kept from earlier chunks
-            for (int j = 0; j < kept && alive; ++j)
-                if (nms_suppresses(box, area, s_kept[j], s_kept_area[j], iou_thr)) alive = false;
+            area = f_mul(f_sub(box.ymax, box.ymin), f_sub(box.xmax, box.xmin));
         }
-        s_box[tid] = box;
-        s_area[tid] = area;
-        const unsigned bal = __ballot_sync(0xffffffffu, alive);
-        if (lane == 0) s_alive[warp] = bal;
-        __syncthreads();
-        // (b) row t of the suppression matrix, restricted to alive later candidates
+        s_tile[warp][lane] = box;
+        s_tile_area[warp][lane] = area;
+        // (a) against the boxes kept from earlier tiles, four independent tests in flight
+        for (int j = 0; j < kept; j += 4) {
+            bool hit = false, amb = false;
 #pragma unroll
-        for (int w = 0; w < NMS_THREADS / 32; ++w) {
-            unsigned word = 0u;
-            if (alive && w >= warp) {
-                unsigned todo = s_alive[w];
-                if (w == warp) todo &= ~((2u << lane) - 1u);             // strictly later in score order
-                while (todo) {
-                    const int jj = __ffs(todo) - 1;
-                    todo &= todo - 1;
-                    const int j = w * 32 + jj;
-                    if (nms_suppresses(box, area, s_box[j], s_area[j], iou_thr)) word |= 1u << jj;
+            for (int u = 0; u < 4; ++u) {
+                const int jj = min(j + u, kept - 1);
+                bool y, am;
+                nms_fast(box, area, s_kept[jj], s_kept_area[jj], iou_thr, band, y, am);
+                hit |= y; amb |= am;
+            }
+            if (amb && !hit) {                                   // rare: within 2^-18 of the threshold
+                for (int u = 0; u < 4; ++u) {
+                    const int jj = min(j + u, kept - 1);
+                    if (area > 0.0f && s_kept_area[jj] > 0.0f) hit |= nms_exact(box, area, s_kept[jj], s_kept_area[jj], iou_thr);
                 }
             }
-            s_mask[tid][w] = word;
+            if (hit) alive = false;
+            if ((j & 12) == 12 && !__any_sync(0xffffffffu, alive)) break;
         }
-        __syncthreads();
+        __syncwarp();
+        // (b) column of the tile's suppression matrix: earlier alive lanes t that suppress this lane
+        const unsigned alive_mask = __ballot_sync(0xffffffffu, alive);
+        unsigned col = 0u;
+        if (alive_mask & (alive_mask - 1u)) {                    // at least two alive candidates
+#pragma unroll 4
+            for (int t = 0; t < 31; ++t) {
+                bool y, am;
+                nms_fast(box, area, s_tile[warp][t], s_tile_area[warp][t], iou_thr, band, y, am);
+                if (am) y = nms_exact(box, area, s_tile[warp][t], s_tile_area[warp][t], iou_thr);
+                if (y && t < lane && ((alive_mask >> t) & 1u)) col |= 1u << t;
+            }
+        }
         // (c) greedy walk in score order
-        if (tid == 0) {
-            unsigned removed[NMS_THREADS / 32];
-#pragma unroll
-            for (int w = 0; w < NMS_THREADS / 32; ++w) removed[w] = ~s_alive[w];
-            int cnt = 0;
-#pragma unroll
-            for (int w = 0; w < NMS_THREADS / 32; ++w) {
-                for (int jj = 0; jj < 32 && kept + cnt < K; ++jj) {
-                    if (!((removed[w] >> jj) & 1u)) {
-                        const int t = w * 32 + jj;
-                        s_list[cnt++] = t;
-#pragma unroll
-                        for (int v = 0; v < NMS_THREADS / 32; ++v) removed[v] |= s_mask[t][v];
-                    }
-                }
-            }
-            s_cnt = cnt;
+        unsigned keep = 0u;
+        int room = K - kept;
+        for (unsigned todo = alive_mask; todo && room > 0;) {
+            const int j = __ffs(todo) - 1;
+            todo &= todo - 1;
+            const unsigned cj = __shfl_sync(0xffffffffu, col, j);
+            if (!(cj & keep)) { keep |= 1u << j; --room; }
         }
-        __syncthreads();
-        // (d) append
-        const int cnt = s_cnt;
-        if (tid < cnt) {
-            const int t = s_list[tid];
-            s_kept[kept + tid] = s_box[t];
-            s_kept_area[kept + tid] = s_area[t];
-            seg_box[obase + kept + tid] = s_raw[t];
-            seg_score[obase + kept + tid] = s_score[t];
-            seg_anchor[obase + kept + tid] = s_anchor[t];
+        // (d) append the kept lanes in score order
+        if ((keep >> lane) & 1u) {
+            const int pos = kept + __popc(keep & lt_mask);
+            s_kept[pos] = box;
+            s_kept_area[pos] = area;
+            seg_box[obase + pos] = raw;
+            seg_score[obase + pos] = score;
+            seg_anchor[obase + pos] = a;
         }
-        kept += cnt;
-        __syncthreads();
+        kept += __popc(keep);
+        __syncwarp();
     }
-    if (tid == 0) seg_kept[seg] = kept;
+    if (lane == 0) seg_kept[seg] = kept;
 }
 
 // ---------------------------------------------------------------------------------------------- 4. pack
+#define PACK_SLOTS_PER_BLOCK 1024
 __global__ void __launch_bounds__(256) pack_kernel(const float4* __restrict__ seg_box, const float* __restrict__ seg_score,
                                                    const int* __restrict__ seg_anchor, const int* __restrict__ seg_kept,
                                                    int C, int K, float4* __restrict__ out_boxes, float* __restrict__ out_scores,
                                                    int* __restrict__ out_classes, int* __restrict__ out_num,
                                                    int* __restrict__ out_anchor) {
-    extern __shared__ int s_off[];   // [C+1]
-    const int b = blockIdx.x;
+    extern __shared__ int s_off[];   // [C+1] exclusive prefix sums of the per-class kept counts
+    const int b = blockIdx.y;
     const int* kept = seg_kept + (size_t)b * C;
-    if (threadIdx.x == 0) {
-        int t = 0;
-        for (int c = 0; c < C; ++c) { s_off[c] = t; t += kept[c]; }
-        s_off[C] = t;
-        out_num[b] = t;                                              // nms.py:81
+    if (threadIdx.x < 32) {
+        const int lane = threadIdx.x;
+        const int per = (C + 31) / 32;
+        const int c0 = min(lane * per, C), c1 = min(c0 + per, C);
+        int mine = 0;
+        for (int c = c0; c < c1; ++c) mine += kept[c];
+        int incl = mine;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int v = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += v;
+        }
+        int run = incl - mine;
+        for (int c = c0; c < c1; ++c) { s_off[c] = run; run += kept[c]; }
+        if (lane == 31) {
+            s_off[C] = incl;
+            if (blockIdx.x == 0) out_num[b] = incl;                  // nms.py:81
+        }
     }
     __syncthreads();
     const int total = s_off[C];
@@ -390,9 +404,11 @@ __global__ void __launch_bounds__(256) pack_kernel(const float4* __restrict__ se
     float* os = out_scores + b * M;
     int* oc = out_classes + b * M;
     int* oa = out_anchor ? out_anchor + b * M : nullptr;
-    for (int idx = threadIdx.x; idx < C * K; idx += blockDim.x) {     // selected entries, class-major (nms.py:42-44)
+    const int lo = blockIdx.x * PACK_SLOTS_PER_BLOCK;
+    const int hi = min(lo + PACK_SLOTS_PER_BLOCK, C * K);
+    for (int idx = lo + threadIdx.x; idx < hi; idx += blockDim.x) {
         const int c = idx / K, j = idx - c * K;
-        if (j < kept[c]) {
+        if (j < kept[c]) {                                            // selected entries, class-major (nms.py:42-44)
             const size_t src = ((size_t)b * C + c) * K + j;
             const int dst = s_off[c] + j;
             ob[dst] = seg_box[src];
@@ -400,12 +416,12 @@ __global__ void __launch_bounds__(256) pack_kernel(const float4* __restrict__ se
             oc[dst] = c;
             if (oa) oa[dst] = seg_anchor[src];
         }
-    }
-    for (int idx = total + threadIdx.x; idx < C * K; idx += blockDim.x) {   // zero padding (nms.py:84-89)
-        ob[idx] = make_float4(0.f, 0.f, 0.f, 0.f);
-        os[idx] = 0.f;
-        oc[idx] = 0;
-        if (oa) oa[idx] = -1;
+        if (idx >= total) {                                           // zero padding (nms.py:84-89)
+            ob[idx] = make_float4(0.f, 0.f, 0.f, 0.f);
+            os[idx] = 0.f;
+            oc[idx] = 0;
+            if (oa) oa[idx] = -1;
+        }
     }
 }
 
@@ -436,7 +452,7 @@ extern "C" int ssdk_postprocess(ssdk_ctx* ctx, const float* codes, const float* 
     SSDK_REQUIRE(((uintptr_t)scores & 3) == 0, SSDK_ERR_SHAPE, "ssdk_postprocess: scores must be 4-byte aligned");
     const long long per_image = (long long)A * C;
     SSDK_REQUIRE(per_image < (1ll << 31), SSDK_ERR_SHAPE, "ssdk_postprocess: A*C must be < 2^31");
-    SSDK_REQUIRE((size_t)K * 20 <= 180 * 1024, SSDK_ERR_SHAPE,
+    SSDK_REQUIRE((size_t)NMS_WARPS * K * 20 <= 180 * 1024, SSDK_ERR_SHAPE,
                  "ssdk_postprocess: max_boxes_per_class %d too large", K);
     KeyFormat fmt;
     fmt.abits = bits_for(A > 1 ? A : 2);
@@ -510,27 +526,30 @@ extern "C" int ssdk_postprocess(ssdk_ctx* ctx, const float* codes, const float* 
                                                                                    barriers));
         }
 
-        // 3. NMS, one CTA per (image, class)
-        const size_t nms_smem = (size_t)K * (sizeof(NmsBox) + sizeof(float));
-        const int ngrid = B * C;
+        // 3. NMS, one warp per (image, class)
+        const size_t nms_smem = (size_t)NMS_WARPS * K * (sizeof(NmsBox) + sizeof(float));
+        const long long nseg = (long long)B * C;
+        const int ngrid = ceil_div_i(nseg, NMS_WARPS);
         const int nms_slot = ctx->profiling ? ssdk_prof_begin(ctx, SSDK_K_NMS) : -1;
         if (decoded) {
             SSDK_CHECK_CUDA(cudaFuncSetAttribute(nms_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)nms_smem));
-            nms_kernel<true><<<ngrid, NMS_THREADS, nms_smem, ctx->stream>>>(cand, cap, fmt, seg_start, seg_end, (const float4*)codes,
-                                                                           (const float4*)anchors, A, C, K, (float)iou_threshold,
-                                                                           seg_box, seg_score, seg_anchor, seg_kept);
+            nms_kernel<true><<<ngrid, NMS_WARPS * 32, nms_smem, ctx->stream>>>(cand, cap, fmt, seg_start, seg_end, (const float4*)codes,
+                                                                              (const float4*)anchors, A, nseg, C, K,
+                                                                              (float)iou_threshold, seg_box, seg_score, seg_anchor,
+                                                                              seg_kept);
         } else {
             SSDK_CHECK_CUDA(cudaFuncSetAttribute(nms_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)nms_smem));
-            nms_kernel<false><<<ngrid, NMS_THREADS, nms_smem, ctx->stream>>>(cand, cap, fmt, seg_start, seg_end, (const float4*)codes,
-                                                                            (const float4*)anchors, A, C, K, (float)iou_threshold,
-                                                                            seg_box, seg_score, seg_anchor, seg_kept);
+            nms_kernel<false><<<ngrid, NMS_WARPS * 32, nms_smem, ctx->stream>>>(cand, cap, fmt, seg_start, seg_end, (const float4*)codes,
+                                                                               (const float4*)anchors, A, nseg, C, K,
+                                                                               (float)iou_threshold, seg_box, seg_score, seg_anchor,
+                                                                               seg_kept);
         }
         if (nms_slot >= 0) ssdk_prof_end(ctx, nms_slot);
         SSDK_CHECK_LAUNCH(ctx);
     }
     // 4. pack
     SSDK_KERNEL(ctx, SSDK_K_PACK,
-                pack_kernel<<<B, 256, (size_t)(C + 1) * sizeof(int), ctx->stream>>>(seg_box, seg_score, seg_anchor, seg_kept, C, K,
+                pack_kernel<<<dim3(ceil_div_i((long long)C * K, PACK_SLOTS_PER_BLOCK), B), 256, (size_t)(C + 1) * sizeof(int), ctx->stream>>>(seg_box, seg_score, seg_anchor, seg_kept, C, K,
                                                                                    (float4*)out_boxes, out_scores, out_classes,
                                                                                    out_num, out_anchor_idx));
     return SSDK_OK;
