@@ -9,7 +9,7 @@ All arithmetic runs in hand-written sm_100a CUDA kernels (csrc/) behind the C AB
 The directory name contains a hyphen: import it with importlib.import_module('single-shot-detector_b200')
 (or `import ssd_b200`, the alias module at the repository root).
 """
-from . import _lib, config, parallel  # noqa: F401
+from . import _lib, config, graph, parallel  # noqa: F401
 from .detector import SSD  # noqa: F401
 from .detector.anchor_generator import AnchorGenerator  # noqa: F401
 from .detector.losses import focal_loss, localization_loss  # noqa: F401

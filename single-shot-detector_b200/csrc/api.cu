@@ -33,6 +33,19 @@ int ssdk_ensure(ssdk_ctx* ctx, ssdk_buf* b, size_t bytes) {
     return SSDK_OK;
 }
 
+// Raise a kernel's dynamic shared-memory limit once per (context, kernel) instead of on every launch.
+int ssdk_set_max_smem(ssdk_ctx* ctx, const void* func, int bytes) {
+    int slot = -1;
+    for (int i = 0; i < 16; ++i) {
+        if (ctx->smem_func[i] == func) { slot = i; break; }
+        if (ctx->smem_func[i] == nullptr && slot < 0) slot = i;
+    }
+    if (slot >= 0 && ctx->smem_func[slot] == func && ctx->smem_bytes[slot] >= bytes) return SSDK_OK;
+    SSDK_CHECK_CUDA(cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    if (slot >= 0) { ctx->smem_func[slot] = func; ctx->smem_bytes[slot] = bytes; }
+    return SSDK_OK;
+}
+
 static int prof_drain(ssdk_ctx* ctx) {
     if (ctx->prof_n == 0) return SSDK_OK;
     SSDK_CHECK_CUDA(cudaStreamSynchronize(ctx->stream));

@@ -42,11 +42,16 @@ struct ssdk_ctx {
     int prof_id[SSDK_PROFILE_EVENTS];
     double prof_ms[SSDK_K_COUNT] = {0};
     long long prof_calls[SSDK_K_COUNT] = {0};
+    // cudaFuncSetAttribute(MaxDynamicSharedMemorySize) results, so that the steady state makes no such call
+    const void* smem_func[16] = {nullptr};
+    int smem_bytes[16] = {0};
+    int sort_occupancy = 0;
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
 };
 
 void ssdk_set_error(const char* fmt, ...);
+int ssdk_set_max_smem(ssdk_ctx* ctx, const void* func, int bytes);
 int ssdk_ensure(ssdk_ctx* ctx, ssdk_buf* b, size_t bytes);
 
 #define SSDK_CHECK_CUDA(expr)                                                              \

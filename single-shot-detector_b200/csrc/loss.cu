@@ -466,7 +466,7 @@ static int launch_loss(ssdk_ctx* ctx, int grid, size_t smem, const float* logits
                        const int* cls_t, const int* matches, long long NA, int C, int rpw, double gamma, double alpha,
                        LossSmemLayout L, float* cls_losses, float* loc_losses, double* partials) {
     auto kern = ssd_loss_kernel<GM, PA>;
-    SSDK_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    SSDK_TRY(ssdk_set_max_smem(ctx, (const void*)kern, (int)smem));
     SSDK_KERNEL(ctx, SSDK_K_LOSS,
                 kern<<<grid, LOSS_THREADS, smem, ctx->stream>>>(logits, (const float4*)codes, (const float4*)reg_t, cls_t, matches,
                                                                 NA, C, rpw, (float)gamma, (float)alpha, (float)(1.0 - alpha), L,

@@ -504,11 +504,12 @@ extern "C" int ssdk_postprocess(ssdk_ctx* ctx, const float* codes, const float* 
 
         // 2. sort (+ segment table)
         const size_t sort_smem = (size_t)SORT_SMEM_KEYS * sizeof(unsigned long long);
-        SSDK_CHECK_CUDA(cudaFuncSetAttribute(sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sort_smem));
+        SSDK_TRY(ssdk_set_max_smem(ctx, (const void*)sort_kernel, (int)sort_smem));
         int nblk = 1;
         if (per_image > SORT_SMEM_KEYS) {
-            int occ = 0;
-            SSDK_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sort_kernel, SORT_THREADS, sort_smem));
+            if (ctx->sort_occupancy == 0)
+                SSDK_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->sort_occupancy, sort_kernel, SORT_THREADS, sort_smem));
+            const int occ = ctx->sort_occupancy;
             nblk = (ctx->num_sms * (occ > 0 ? occ : 1)) / B;
             if (nblk < 1) nblk = 1;
             if (nblk > 64) nblk = 64;
@@ -532,13 +533,13 @@ extern "C" int ssdk_postprocess(ssdk_ctx* ctx, const float* codes, const float* 
         const int ngrid = ceil_div_i(nseg, NMS_WARPS);
         const int nms_slot = ctx->profiling ? ssdk_prof_begin(ctx, SSDK_K_NMS) : -1;
         if (decoded) {
-            SSDK_CHECK_CUDA(cudaFuncSetAttribute(nms_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)nms_smem));
+            SSDK_TRY(ssdk_set_max_smem(ctx, (const void*)nms_kernel<true>, (int)nms_smem));
             nms_kernel<true><<<ngrid, NMS_WARPS * 32, nms_smem, ctx->stream>>>(cand, cap, fmt, seg_start, seg_end, (const float4*)codes,
                                                                               (const float4*)anchors, A, nseg, C, K,
                                                                               (float)iou_threshold, seg_box, seg_score, seg_anchor,
                                                                               seg_kept);
         } else {
-            SSDK_CHECK_CUDA(cudaFuncSetAttribute(nms_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)nms_smem));
+            SSDK_TRY(ssdk_set_max_smem(ctx, (const void*)nms_kernel<false>, (int)nms_smem));
             nms_kernel<false><<<ngrid, NMS_WARPS * 32, nms_smem, ctx->stream>>>(cand, cap, fmt, seg_start, seg_end, (const float4*)codes,
                                                                                (const float4*)anchors, A, nseg, C, K,
                                                                                (float)iou_threshold, seg_box, seg_score, seg_anchor,
