@@ -228,11 +228,12 @@ struct LossSmemLayout {
 };
 
 template <int GAMMA_MODE, bool PER_ANCHOR>
-__global__ void __launch_bounds__(LOSS_THREADS) ssd_loss_kernel(
+__global__ void __launch_bounds__(LOSS_THREADS, 4) ssd_loss_kernel(
     const float* __restrict__ logits, const float4* __restrict__ codes, const float4* __restrict__ reg_t,
     const int* __restrict__ cls_t, const int* __restrict__ matches, long long NA, int C, int rpw /*rows per warp*/,
     float gamma, float alpha, float one_minus_alpha, LossSmemLayout L, float* __restrict__ cls_losses,
-    float* __restrict__ loc_losses, double* __restrict__ partials /*[grid][3]*/) {
+    float* __restrict__ loc_losses, double* __restrict__ partials /*[grid][3]*/, unsigned* __restrict__ ticket /*zero between launches*/,
+    double* __restrict__ out_sums /*[3]*/) {
     extern __shared__ __align__(128) unsigned char smem[];
     unsigned long long* full = (unsigned long long*)smem;                 // [stages]  producer -> consumers
     unsigned long long* empty = full + LOSS_MAX_STAGES;                   // [stages]  consumers -> producer
@@ -433,23 +434,31 @@ __global__ void __launch_bounds__(LOSS_THREADS) ssd_loss_kernel(
 #pragma unroll
         for (int w = 0; w < LOSS_CONSUMER_WARPS; ++w) t += s_red[w][tid];
         partials[(size_t)blockIdx.x * 3 + tid] = t;
+        __threadfence();
     }
-}
-
-// Sum the per-CTA partials in a fixed order -> out_sums[3] = { sum loc, sum cls, num_matches }.
-__global__ void __launch_bounds__(256) loss_reduce_kernel(const double* __restrict__ partials, int n, double* __restrict__ out) {
-    __shared__ double s[256][3];
-    double t[3] = {0.0, 0.0, 0.0};
-    for (int i = threadIdx.x; i < n; i += 256)
-        for (int j = 0; j < 3; ++j) t[j] += partials[(size_t)i * 3 + j];
-    for (int j = 0; j < 3; ++j) s[threadIdx.x][j] = t[j];
-    __syncthreads();
-    for (int o = 128; o > 0; o >>= 1) {
-        if (threadIdx.x < o)
-            for (int j = 0; j < 3; ++j) s[threadIdx.x][j] += s[threadIdx.x + o][j];
-        __syncthreads();
+    // ---- the CTA that finishes last sums the per-CTA partials in a fixed order (deterministic whichever CTA it is)
+    //      -> out_sums[3] = { sum loc, sum cls, num_matches }, and re-arms the ticket counter for the next launch
+    __shared__ int s_last;
+    __shared__ double s_fin[64][3];
+    asm volatile("bar.sync 1, %0;" ::"n"(LOSS_CONSUMER_WARPS * 32) : "memory");
+    if (tid == 0) s_last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+    asm volatile("bar.sync 1, %0;" ::"n"(LOSS_CONSUMER_WARPS * 32) : "memory");
+    if (!s_last) return;
+    __threadfence();
+    if (tid < 64) {
+        double t[3] = {0.0, 0.0, 0.0};
+        for (int i = tid; i < (int)gridDim.x; i += 64)
+            for (int j = 0; j < 3; ++j) t[j] += __ldcg(&partials[(size_t)i * 3 + j]);
+        for (int j = 0; j < 3; ++j) s_fin[tid][j] = t[j];
     }
-    if (threadIdx.x < 3) out[threadIdx.x] = s[0][threadIdx.x];
+    asm volatile("bar.sync 1, %0;" ::"n"(LOSS_CONSUMER_WARPS * 32) : "memory");
+    for (int o = 32; o > 0; o >>= 1) {
+        if (tid < o)
+            for (int j = 0; j < 3; ++j) s_fin[tid][j] += s_fin[tid + o][j];
+        asm volatile("bar.sync 1, %0;" ::"n"(LOSS_CONSUMER_WARPS * 32) : "memory");
+    }
+    if (tid < 3) out_sums[tid] = s_fin[0][tid];
+    if (tid == 0) *ticket = 0u;
 }
 
 // normalizer = max(num_matches, 1) and the two scalar losses: ssd.py:123,131-133
@@ -464,13 +473,13 @@ static bool aligned16(const void* p) { return ((uintptr_t)p & 15) == 0; }
 template <int GM, bool PA>
 static int launch_loss(ssdk_ctx* ctx, int grid, size_t smem, const float* logits, const float* codes, const float* reg_t,
                        const int* cls_t, const int* matches, long long NA, int C, int rpw, double gamma, double alpha,
-                       LossSmemLayout L, float* cls_losses, float* loc_losses, double* partials) {
+                       LossSmemLayout L, float* cls_losses, float* loc_losses, double* partials, unsigned* ticket, double* out_sums) {
     auto kern = ssd_loss_kernel<GM, PA>;
     SSDK_TRY(ssdk_set_max_smem(ctx, (const void*)kern, (int)smem));
     SSDK_KERNEL(ctx, SSDK_K_LOSS,
                 kern<<<grid, LOSS_THREADS, smem, ctx->stream>>>(logits, (const float4*)codes, (const float4*)reg_t, cls_t, matches,
                                                                 NA, C, rpw, (float)gamma, (float)alpha, (float)(1.0 - alpha), L,
-                                                                cls_losses, loc_losses, partials));
+                                                                cls_losses, loc_losses, partials, ticket, out_sums));
     return SSDK_OK;
 }
 
@@ -509,23 +518,28 @@ int ssdk_ssd_loss(ssdk_ctx* ctx, const float* logits, const float* codes, const 
     const size_t smem = 128 + (size_t)L.stages * L.stage_bytes;
 
     const long long ntiles = (NA + rows - 1) / rows;
-    int per_sm = (int)((227 * 1024) / (smem + 1024 + 256));
+    int per_sm = (int)((227 * 1024) / (smem + 1024 + 2048));   // + reserved + static shared memory
     if (per_sm < 1) per_sm = 1;
     if (per_sm > 5) per_sm = 5;
     long long grid = (long long)ctx->num_sms * per_sm;
     if (grid > ntiles) grid = ntiles;
 
-    SSDK_TRY(ssdk_ensure(ctx, &ctx->ws_partials, (size_t)grid * 3 * sizeof(double)));
-    double* partials = (double*)ctx->ws_partials.p;
+    // per-CTA partials + the ticket counter of the fused final reduction (zeroed when allocated, re-armed by the kernel)
+    const size_t part_bytes = 16 + (size_t)ctx->num_sms * 8 * 3 * sizeof(double);
+    if (ctx->ws_partials.cap < part_bytes) {
+        SSDK_TRY(ssdk_ensure(ctx, &ctx->ws_partials, part_bytes));
+        SSDK_CHECK_CUDA(cudaMemsetAsync(ctx->ws_partials.p, 0, 16, ctx->stream));
+    }
+    unsigned* ticket = (unsigned*)ctx->ws_partials.p;
+    double* partials = (double*)((char*)ctx->ws_partials.p + 16);
     const bool pa = out_cls_losses != nullptr;
     const bool g2 = (gamma == 2.0);
     int st;
-    if (g2 && !pa) st = launch_loss<0, false>(ctx, (int)grid, smem, logits, codes, reg_targets, cls_targets, matches, NA, C, rpw, gamma, alpha, L, out_cls_losses, out_loc_losses, partials);
-    else if (g2 && pa) st = launch_loss<0, true>(ctx, (int)grid, smem, logits, codes, reg_targets, cls_targets, matches, NA, C, rpw, gamma, alpha, L, out_cls_losses, out_loc_losses, partials);
-    else if (!pa) st = launch_loss<1, false>(ctx, (int)grid, smem, logits, codes, reg_targets, cls_targets, matches, NA, C, rpw, gamma, alpha, L, out_cls_losses, out_loc_losses, partials);
-    else st = launch_loss<1, true>(ctx, (int)grid, smem, logits, codes, reg_targets, cls_targets, matches, NA, C, rpw, gamma, alpha, L, out_cls_losses, out_loc_losses, partials);
+    if (g2 && !pa) st = launch_loss<0, false>(ctx, (int)grid, smem, logits, codes, reg_targets, cls_targets, matches, NA, C, rpw, gamma, alpha, L, out_cls_losses, out_loc_losses, partials, ticket, out_sums);
+    else if (g2 && pa) st = launch_loss<0, true>(ctx, (int)grid, smem, logits, codes, reg_targets, cls_targets, matches, NA, C, rpw, gamma, alpha, L, out_cls_losses, out_loc_losses, partials, ticket, out_sums);
+    else if (!pa) st = launch_loss<1, false>(ctx, (int)grid, smem, logits, codes, reg_targets, cls_targets, matches, NA, C, rpw, gamma, alpha, L, out_cls_losses, out_loc_losses, partials, ticket, out_sums);
+    else st = launch_loss<1, true>(ctx, (int)grid, smem, logits, codes, reg_targets, cls_targets, matches, NA, C, rpw, gamma, alpha, L, out_cls_losses, out_loc_losses, partials, ticket, out_sums);
     SSDK_TRY(st);
-    SSDK_KERNEL(ctx, SSDK_K_LOSS_REDUCE, loss_reduce_kernel<<<1, 256, 0, ctx->stream>>>(partials, (int)grid, out_sums));
     return SSDK_OK;
 }
 

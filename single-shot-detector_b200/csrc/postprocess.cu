@@ -15,10 +15,10 @@
 //   2. sort_kernel        one CTA per image sorts the keys in shared memory (bitonic); images with more candidates
 //                         than fit fall back to a multi-CTA bitonic sort in global memory.  Also records the
 //                         [start, end) of every class segment.
-//   3. nms_kernel         one warp per (image, class): candidates are taken 32 at a time in sorted order, decoded
-//                         (box_utils.py:114-142) and clipped (nms.py:77) on the fly, tested against the boxes kept
-//                         so far (shared memory); inside the tile a 32x32 suppression bit matrix is built (one
-//                         column per lane, warp ballot = alive set) and walked greedily with shuffles; stops at K.
+//   3. nms_kernel         one CTA per (image, class): candidates are taken 64 at a time in sorted order (four threads
+//                         per candidate), decoded (box_utils.py:114-142) and clipped (nms.py:77) on the fly, tested
+//                         against the boxes kept so far (shared memory); inside the chunk a 64x64 suppression bit
+//                         matrix is built in parallel and walked greedily by one thread; stops at K.
 //   4. pack_kernel        class-major concatenation, zero padding to C*K and num_boxes (nms.py:83-93).
 #include <cooperative_groups.h>
 
@@ -30,7 +30,8 @@ namespace cg = cooperative_groups;
 #define FILTER_UNROLL 4
 #define SORT_THREADS 1024
 #define SORT_SMEM_KEYS 16384          // 128 KB of keys
-#define NMS_WARPS 4
+#define NMS_THREADS 256
+#define NMS_CH 64                    // candidates per chunk: four threads each
 
 struct KeyFormat {
     int abits;       // bits for the anchor index
@@ -236,13 +237,6 @@ __global__ void __launch_bounds__(SORT_THREADS) sort_kernel(unsigned long long* 
 }
 
 // ---------------------------------------------------------------------------------------------- 3. NMS
-// One warp per (image, class) segment; the sorted candidates are consumed 32 at a time (one per lane).
-// Per tile: (a) every lane decodes its candidate and tests it against the boxes kept so far (shared memory,
-// broadcast reads); (b) every lane builds its COLUMN of the tile's 32x32 suppression bit matrix (bit t set <=>
-// lane t comes earlier in score order and IoU(t, lane) > threshold); (c) the warp walks the alive lanes in score
-// order with shuffles -- lane j is kept iff no already kept lane is in its column -- until K boxes are kept;
-// (d) the kept lanes append themselves (rank by popc) to the kept list and to the segment's output.
-// Only tests against KEPT boxes and inside a 32-tile are ever made, so the work is O(n * kept + 32 n).
 struct NmsBox {          // corners min/max-normalised as NonMaxSuppressionV3 does; area <= 0 never suppresses
     float ymin, xmin, ymax, xmax;
 };
@@ -270,31 +264,45 @@ __device__ __forceinline__ bool nms_exact(const NmsBox a, float area_a, const Nm
     return f_div(inter, f_sub(f_add(area_a, area_b), inter)) > thr;
 }
 
+// One CTA per (image, class) segment, NMS_CH candidates per chunk in sorted order, four threads per candidate:
+//   (a) every candidate is decoded + clipped and tested against the boxes kept from earlier chunks (shared memory);
+//       the four threads of a candidate split the kept list and OR their verdicts with shuffles;
+//   (b) column c of the chunk's suppression bit matrix (bit t set <=> t < c, t survived (a), IoU(t, c) > threshold) is
+//       built the same way, the four threads splitting t;
+//   (c) one thread walks the surviving candidates in score order: c is kept iff no kept t is in its column; stops at K;
+//   (d) kept candidates append themselves (rank by popcount) to the kept list and to the segment's output.
+// All IoU tests of a chunk run in parallel; only (c), a few hundred cycles of bit operations, is serial.
 template <bool DECODED>
-__global__ void __launch_bounds__(NMS_WARPS * 32) nms_kernel(
+__global__ void __launch_bounds__(NMS_THREADS) nms_kernel(
     const unsigned long long* __restrict__ cand, long long cap, KeyFormat fmt, const int* __restrict__ seg_start,
     const int* __restrict__ seg_end, const float4* __restrict__ codes, const float4* __restrict__ anchors, long long A,
     long long nseg, int C, int K, float iou_thr, float4* __restrict__ seg_box, float* __restrict__ seg_score,
     int* __restrict__ seg_anchor, int* __restrict__ seg_kept) {
     extern __shared__ __align__(16) unsigned char nms_smem[];
-    __shared__ NmsBox s_tile[NMS_WARPS][32];
-    __shared__ float s_tile_area[NMS_WARPS][32];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const long long seg = (long long)blockIdx.x * NMS_WARPS + warp;
-    if (seg >= nseg) return;
-    NmsBox* s_kept = (NmsBox*)nms_smem + (size_t)warp * K;                                  // [K] per warp
-    float* s_kept_area = (float*)((NmsBox*)nms_smem + (size_t)NMS_WARPS * K) + (size_t)warp * K;
-    const int b = (int)(seg / C);
+    __shared__ NmsBox s_tile[NMS_CH];
+    __shared__ float s_tile_area[NMS_CH];
+    __shared__ unsigned long long s_col[NMS_CH];
+    __shared__ __align__(8) unsigned char s_alive8[NMS_CH / 8];
+    __shared__ unsigned long long s_keep;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const long long seg = blockIdx.x;
     const int start = seg_start[seg];
     const int n = seg_end[seg] - start;
+    if (n <= 0) {
+        if (tid == 0) seg_kept[seg] = 0;
+        return;
+    }
+    NmsBox* s_kept = (NmsBox*)nms_smem;                 // [K]
+    float* s_kept_area = (float*)(s_kept + K);          // [K]
+    const int b = (int)(seg / C);
     const unsigned long long* keys = cand + (size_t)b * cap + start;
     const size_t obase = (size_t)seg * K;
     const float band = fabsf(iou_thr) * 3.814697265625e-06f;
-    const unsigned lt_mask = (1u << lane) - 1u;
+    const int c = tid >> 2, q = tid & 3;               // candidate slot in the chunk, position in the quad
     int kept = 0;
 
-    for (int base = 0; base < n && kept < K; base += 32) {
-        const int i = base + lane;
+    for (int base = 0; base < n && kept < K; base += NMS_CH) {
+        const int i = base + c;
         bool alive = i < n;
         NmsBox box = {0.f, 0.f, 0.f, 0.f};
         float4 raw = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -310,62 +318,71 @@ __global__ void __launch_bounds__(NMS_WARPS * 32) nms_kernel(
             box.ymax = fmaxf(raw.x, raw.z); box.xmax = fmaxf(raw.y, raw.w);
             area = f_mul(f_sub(box.ymax, box.ymin), f_sub(box.xmax, box.xmin));
         }
-        s_tile[warp][lane] = box;
-        s_tile_area[warp][lane] = area;
-        // (a) against the boxes kept from earlier tiles, four independent tests in flight
-        for (int j = 0; j < kept; j += 4) {
-            bool hit = false, amb = false;
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const int jj = min(j + u, kept - 1);
+        // (a) against the boxes kept from earlier chunks
+        int hit = 0;
+        if (alive) {
+            for (int j = q; j < kept; j += 4) {
                 bool y, am;
-                nms_fast(box, area, s_kept[jj], s_kept_area[jj], iou_thr, band, y, am);
-                hit |= y; amb |= am;
+                nms_fast(box, area, s_kept[j], s_kept_area[j], iou_thr, band, y, am);
+                if (am) y = nms_exact(box, area, s_kept[j], s_kept_area[j], iou_thr);     // rare: within 2^-18 of the threshold
+                hit |= y ? 1 : 0;
             }
-            if (amb && !hit) {                                   // rare: within 2^-18 of the threshold
-                for (int u = 0; u < 4; ++u) {
-                    const int jj = min(j + u, kept - 1);
-                    if (area > 0.0f && s_kept_area[jj] > 0.0f) hit |= nms_exact(box, area, s_kept[jj], s_kept_area[jj], iou_thr);
+        }
+        hit |= __shfl_xor_sync(0xffffffffu, hit, 1);
+        hit |= __shfl_xor_sync(0xffffffffu, hit, 2);
+        alive = alive && !hit;
+        if (q == 0) { s_tile[c] = box; s_tile_area[c] = area; }
+        const unsigned bal = __ballot_sync(0xffffffffu, alive && q == 0);     // bits 0,4,8,..,28 = the warp's 8 candidates
+        if (lane == 0) {
+            unsigned bits = 0u;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) bits |= ((bal >> (4 * k)) & 1u) << k;
+            s_alive8[warp] = (unsigned char)bits;
+        }
+        __syncthreads();
+        const unsigned long long alive_mask = *(const unsigned long long*)s_alive8;
+        // (b) column of the chunk's suppression matrix
+        unsigned long long col = 0ull;
+        if (alive && (alive_mask & (alive_mask - 1ull))) {                   // at least two survivors in the chunk
+            for (int t = q; t < c; t += 4) {
+                if ((alive_mask >> t) & 1ull) {
+                    bool y, am;
+                    nms_fast(box, area, s_tile[t], s_tile_area[t], iou_thr, band, y, am);
+                    if (am) y = nms_exact(box, area, s_tile[t], s_tile_area[t], iou_thr);
+                    if (y) col |= 1ull << t;
                 }
             }
-            if (hit) alive = false;
-            if ((j & 12) == 12 && !__any_sync(0xffffffffu, alive)) break;
         }
-        __syncwarp();
-        // (b) column of the tile's suppression matrix: earlier alive lanes t that suppress this lane
-        const unsigned alive_mask = __ballot_sync(0xffffffffu, alive);
-        unsigned col = 0u;
-        if (alive_mask & (alive_mask - 1u)) {                    // at least two alive candidates
-#pragma unroll 4
-            for (int t = 0; t < 31; ++t) {
-                bool y, am;
-                nms_fast(box, area, s_tile[warp][t], s_tile_area[warp][t], iou_thr, band, y, am);
-                if (am) y = nms_exact(box, area, s_tile[warp][t], s_tile_area[warp][t], iou_thr);
-                if (y && t < lane && ((alive_mask >> t) & 1u)) col |= 1u << t;
-            }
-        }
+        col |= __shfl_xor_sync(0xffffffffu, col, 1);
+        col |= __shfl_xor_sync(0xffffffffu, col, 2);
+        if (q == 0) s_col[c] = col;
+        __syncthreads();
         // (c) greedy walk in score order
-        unsigned keep = 0u;
-        int room = K - kept;
-        for (unsigned todo = alive_mask; todo && room > 0;) {
-            const int j = __ffs(todo) - 1;
-            todo &= todo - 1;
-            const unsigned cj = __shfl_sync(0xffffffffu, col, j);
-            if (!(cj & keep)) { keep |= 1u << j; --room; }
+        if (tid == 0) {
+            unsigned long long keep = 0ull;
+            int room = K - kept;
+            for (unsigned long long todo = alive_mask; todo && room > 0;) {
+                const int j = __ffsll((long long)todo) - 1;
+                todo &= todo - 1ull;
+                if (!(s_col[j] & keep)) { keep |= 1ull << j; --room; }
+            }
+            s_keep = keep;
         }
-        // (d) append the kept lanes in score order
-        if ((keep >> lane) & 1u) {
-            const int pos = kept + __popc(keep & lt_mask);
+        __syncthreads();
+        const unsigned long long keep = s_keep;
+        // (d) append the kept candidates in score order
+        if (q == 0 && ((keep >> c) & 1ull)) {
+            const int pos = kept + __popcll(keep & ((1ull << c) - 1ull));
             s_kept[pos] = box;
             s_kept_area[pos] = area;
             seg_box[obase + pos] = raw;
             seg_score[obase + pos] = score;
             seg_anchor[obase + pos] = a;
         }
-        kept += __popc(keep);
-        __syncwarp();
+        kept += __popcll(keep);
+        __syncthreads();
     }
-    if (lane == 0) seg_kept[seg] = kept;
+    if (tid == 0) seg_kept[seg] = kept;
 }
 
 // ---------------------------------------------------------------------------------------------- 4. pack
@@ -452,7 +469,7 @@ extern "C" int ssdk_postprocess(ssdk_ctx* ctx, const float* codes, const float* 
     SSDK_REQUIRE(((uintptr_t)scores & 3) == 0, SSDK_ERR_SHAPE, "ssdk_postprocess: scores must be 4-byte aligned");
     const long long per_image = (long long)A * C;
     SSDK_REQUIRE(per_image < (1ll << 31), SSDK_ERR_SHAPE, "ssdk_postprocess: A*C must be < 2^31");
-    SSDK_REQUIRE((size_t)NMS_WARPS * K * 20 <= 180 * 1024, SSDK_ERR_SHAPE,
+    SSDK_REQUIRE((size_t)K * 20 <= 180 * 1024, SSDK_ERR_SHAPE,
                  "ssdk_postprocess: max_boxes_per_class %d too large", K);
     KeyFormat fmt;
     fmt.abits = bits_for(A > 1 ? A : 2);
@@ -528,19 +545,19 @@ extern "C" int ssdk_postprocess(ssdk_ctx* ctx, const float* codes, const float* 
         }
 
         // 3. NMS, one warp per (image, class)
-        const size_t nms_smem = (size_t)NMS_WARPS * K * (sizeof(NmsBox) + sizeof(float));
+        const size_t nms_smem = (size_t)K * (sizeof(NmsBox) + sizeof(float));
         const long long nseg = (long long)B * C;
-        const int ngrid = ceil_div_i(nseg, NMS_WARPS);
+        const int ngrid = (int)nseg;
         const int nms_slot = ctx->profiling ? ssdk_prof_begin(ctx, SSDK_K_NMS) : -1;
         if (decoded) {
             SSDK_TRY(ssdk_set_max_smem(ctx, (const void*)nms_kernel<true>, (int)nms_smem));
-            nms_kernel<true><<<ngrid, NMS_WARPS * 32, nms_smem, ctx->stream>>>(cand, cap, fmt, seg_start, seg_end, (const float4*)codes,
+            nms_kernel<true><<<ngrid, NMS_THREADS, nms_smem, ctx->stream>>>(cand, cap, fmt, seg_start, seg_end, (const float4*)codes,
                                                                               (const float4*)anchors, A, nseg, C, K,
                                                                               (float)iou_threshold, seg_box, seg_score, seg_anchor,
                                                                               seg_kept);
         } else {
             SSDK_TRY(ssdk_set_max_smem(ctx, (const void*)nms_kernel<false>, (int)nms_smem));
-            nms_kernel<false><<<ngrid, NMS_WARPS * 32, nms_smem, ctx->stream>>>(cand, cap, fmt, seg_start, seg_end, (const float4*)codes,
+            nms_kernel<false><<<ngrid, NMS_THREADS, nms_smem, ctx->stream>>>(cand, cap, fmt, seg_start, seg_end, (const float4*)codes,
                                                                                (const float4*)anchors, A, nseg, C, K,
                                                                                (float)iou_threshold, seg_box, seg_score, seg_anchor,
                                                                                seg_kept);
