@@ -30,8 +30,9 @@ namespace cg = cooperative_groups;
 #define FILTER_UNROLL 4
 #define SORT_THREADS 1024
 #define SORT_SMEM_KEYS 16384          // 128 KB of keys
-#define NMS_THREADS 256
-#define NMS_CH 64                    // candidates per chunk: four threads each
+#define NMS_THREADS 512
+#define NMS_CH 64                    // candidates per chunk
+#define NMS_TPC (NMS_THREADS / NMS_CH)  // threads per candidate (a power of two <= 32)
 
 struct KeyFormat {
     int abits;       // bits for the anchor index
@@ -264,125 +265,222 @@ __device__ __forceinline__ bool nms_exact(const NmsBox a, float area_a, const Nm
     return f_div(inter, f_sub(f_add(area_a, area_b), inter)) > thr;
 }
 
-// One CTA per (image, class) segment, NMS_CH candidates per chunk in sorted order, four threads per candidate:
+// Segments with at most 32 candidates (the vast majority: background classes) are resolved by ONE WARP each, one
+// candidate per lane: decode, a 32x32 suppression bit matrix (one column per lane), a greedy walk with shuffles.
+// Larger segments are pushed to a queue for nms_kernel, which spends a whole CTA on each of them.
+#define NMS_SMALL_WARPS 8
+template <bool DECODED>
+__global__ void __launch_bounds__(NMS_SMALL_WARPS * 32) nms_small_kernel(
+    const unsigned long long* __restrict__ cand, long long cap, KeyFormat fmt, const int* __restrict__ seg_start,
+    const int* __restrict__ seg_end, const float4* __restrict__ codes, const float4* __restrict__ anchors, long long A,
+    long long nseg, int C, int K, float iou_thr, float4* __restrict__ seg_box, float* __restrict__ seg_score,
+    int* __restrict__ seg_anchor, int* __restrict__ seg_kept, int* __restrict__ heavy_queue, int* __restrict__ heavy_count) {
+    __shared__ NmsBox s_tile[NMS_SMALL_WARPS][32];
+    __shared__ float s_tile_area[NMS_SMALL_WARPS][32];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long seg = (long long)blockIdx.x * NMS_SMALL_WARPS + warp;
+    if (seg >= nseg) return;
+    const int start = seg_start[seg];
+    const int n = seg_end[seg] - start;
+    if (n <= 0) {
+        if (lane == 0) seg_kept[seg] = 0;
+        return;
+    }
+    if (n > 32) {
+        if (lane == 0) heavy_queue[atomicAdd(heavy_count, 1)] = (int)seg;
+        return;
+    }
+    const int b = (int)(seg / C);
+    const size_t obase = (size_t)seg * K;
+    const float band = fabsf(iou_thr) * 3.814697265625e-06f;
+    bool alive = lane < n;
+    NmsBox box = {0.f, 0.f, 0.f, 0.f};
+    float4 raw = make_float4(0.f, 0.f, 0.f, 0.f);
+    float area = 0.f, score = 0.f;
+    int a = 0;
+    if (alive) {
+        const unsigned long long key = cand[(size_t)b * cap + start + lane];
+        a = key_anchor(key, fmt);
+        score = key_score(key, fmt);
+        if (DECODED) raw = codes[(size_t)b * A + a];
+        else raw = box_clip01(box_decode(codes[(size_t)b * A + a], anchors[a]));            // nms.py:76-77
+        box.ymin = fminf(raw.x, raw.z); box.xmin = fminf(raw.y, raw.w);
+        box.ymax = fmaxf(raw.x, raw.z); box.xmax = fmaxf(raw.y, raw.w);
+        area = f_mul(f_sub(box.ymax, box.ymin), f_sub(box.xmax, box.xmin));
+    }
+    s_tile[warp][lane] = box;
+    s_tile_area[warp][lane] = area;
+    __syncwarp();
+    // column of the suppression matrix: earlier lanes t that suppress this lane
+    unsigned col = 0u;
+    if (n > 1) {
+        for (int t = 0; t < n - 1; ++t) {
+            bool y, am;
+            nms_fast(box, area, s_tile[warp][t], s_tile_area[warp][t], iou_thr, band, y, am);
+            if (am) y = nms_exact(box, area, s_tile[warp][t], s_tile_area[warp][t], iou_thr);
+            if (y && t < lane) col |= 1u << t;
+        }
+    }
+    // greedy walk in score order
+    unsigned keep = 0u;
+    int room = K;
+    for (unsigned todo = __ballot_sync(0xffffffffu, alive); todo && room > 0;) {
+        const int j = __ffs(todo) - 1;
+        todo &= todo - 1;
+        const unsigned cj = __shfl_sync(0xffffffffu, col, j);
+        if (!(cj & keep)) { keep |= 1u << j; --room; }
+    }
+    if ((keep >> lane) & 1u) {
+        const int pos = __popc(keep & ((1u << lane) - 1u));
+        seg_box[obase + pos] = raw;
+        seg_score[obase + pos] = score;
+        seg_anchor[obase + pos] = a;
+    }
+    if (lane == 0) seg_kept[seg] = __popc(keep);
+}
+
+// One CTA per queued (image, class) segment, NMS_CH candidates per chunk in sorted order, NMS_TPC threads per candidate:
 //   (a) every candidate is decoded + clipped and tested against the boxes kept from earlier chunks (shared memory);
-//       the four threads of a candidate split the kept list and OR their verdicts with shuffles;
+//       the threads of a candidate split the kept list and OR their verdicts with shuffles;
 //   (b) column c of the chunk's suppression bit matrix (bit t set <=> t < c, t survived (a), IoU(t, c) > threshold) is
-//       built the same way, the four threads splitting t;
-//   (c) one thread walks the surviving candidates in score order: c is kept iff no kept t is in its column; stops at K;
+//       built the same way, the threads splitting t;
+//   (c) warp 0 resolves the greedy order WITHOUT walking it: a candidate is removed as soon as one of its suppressors is
+//       known to be kept, and kept as soon as all of them are known to be removed; every round decides at least the first
+//       undecided candidate, in practice a handful of rounds of ballots decide all 64;  the result is cut at K;
 //   (d) kept candidates append themselves (rank by popcount) to the kept list and to the segment's output.
-// All IoU tests of a chunk run in parallel; only (c), a few hundred cycles of bit operations, is serial.
 template <bool DECODED>
 __global__ void __launch_bounds__(NMS_THREADS) nms_kernel(
     const unsigned long long* __restrict__ cand, long long cap, KeyFormat fmt, const int* __restrict__ seg_start,
     const int* __restrict__ seg_end, const float4* __restrict__ codes, const float4* __restrict__ anchors, long long A,
     long long nseg, int C, int K, float iou_thr, float4* __restrict__ seg_box, float* __restrict__ seg_score,
-    int* __restrict__ seg_anchor, int* __restrict__ seg_kept) {
+    int* __restrict__ seg_anchor, int* __restrict__ seg_kept, const int* __restrict__ heavy_queue,
+    const int* __restrict__ heavy_count) {
     extern __shared__ __align__(16) unsigned char nms_smem[];
     __shared__ NmsBox s_tile[NMS_CH];
     __shared__ float s_tile_area[NMS_CH];
     __shared__ unsigned long long s_col[NMS_CH];
-    __shared__ __align__(8) unsigned char s_alive8[NMS_CH / 8];
+    __shared__ unsigned s_alive32[2][2];               // [chunk parity][word]: survivors of (a), set with atomicOr
     __shared__ unsigned long long s_keep;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const long long seg = blockIdx.x;
-    const int start = seg_start[seg];
-    const int n = seg_end[seg] - start;
-    if (n <= 0) {
-        if (tid == 0) seg_kept[seg] = 0;
-        return;
-    }
     NmsBox* s_kept = (NmsBox*)nms_smem;                 // [K]
     float* s_kept_area = (float*)(s_kept + K);          // [K]
-    const int b = (int)(seg / C);
-    const unsigned long long* keys = cand + (size_t)b * cap + start;
-    const size_t obase = (size_t)seg * K;
     const float band = fabsf(iou_thr) * 3.814697265625e-06f;
-    const int c = tid >> 2, q = tid & 3;               // candidate slot in the chunk, position in the quad
-    int kept = 0;
-
-    for (int base = 0; base < n && kept < K; base += NMS_CH) {
-        const int i = base + c;
-        bool alive = i < n;
-        NmsBox box = {0.f, 0.f, 0.f, 0.f};
-        float4 raw = make_float4(0.f, 0.f, 0.f, 0.f);
-        float area = 0.f, score = 0.f;
-        int a = 0;
-        if (alive) {
-            const unsigned long long key = keys[i];
-            a = key_anchor(key, fmt);
-            score = key_score(key, fmt);
-            if (DECODED) raw = codes[(size_t)b * A + a];
-            else raw = box_clip01(box_decode(codes[(size_t)b * A + a], anchors[a]));        // nms.py:76-77
-            box.ymin = fminf(raw.x, raw.z); box.xmin = fminf(raw.y, raw.w);
-            box.ymax = fmaxf(raw.x, raw.z); box.xmax = fmaxf(raw.y, raw.w);
-            area = f_mul(f_sub(box.ymax, box.ymin), f_sub(box.xmax, box.xmin));
-        }
-        // (a) against the boxes kept from earlier chunks
-        int hit = 0;
-        if (alive) {
-            for (int j = q; j < kept; j += 4) {
-                bool y, am;
-                nms_fast(box, area, s_kept[j], s_kept_area[j], iou_thr, band, y, am);
-                if (am) y = nms_exact(box, area, s_kept[j], s_kept_area[j], iou_thr);     // rare: within 2^-18 of the threshold
-                hit |= y ? 1 : 0;
-            }
-        }
-        hit |= __shfl_xor_sync(0xffffffffu, hit, 1);
-        hit |= __shfl_xor_sync(0xffffffffu, hit, 2);
-        alive = alive && !hit;
-        if (q == 0) { s_tile[c] = box; s_tile_area[c] = area; }
-        const unsigned bal = __ballot_sync(0xffffffffu, alive && q == 0);     // bits 0,4,8,..,28 = the warp's 8 candidates
-        if (lane == 0) {
-            unsigned bits = 0u;
-#pragma unroll
-            for (int k = 0; k < 8; ++k) bits |= ((bal >> (4 * k)) & 1u) << k;
-            s_alive8[warp] = (unsigned char)bits;
-        }
+    const int c = tid / NMS_TPC, q = tid % NMS_TPC;    // candidate slot in the chunk, position among its threads
+    const int nheavy = *heavy_count;
+    for (int item = blockIdx.x; item < nheavy; item += gridDim.x) {
+        const long long seg = heavy_queue[item];
+        const int start = seg_start[seg];
+        const int n = seg_end[seg] - start;
+        const int b = (int)(seg / C);
+        const unsigned long long* keys = cand + (size_t)b * cap + start;
+        const size_t obase = (size_t)seg * K;
+        int kept = 0;
+        if (tid < 4) s_alive32[tid >> 1][tid & 1] = 0u;
         __syncthreads();
-        const unsigned long long alive_mask = *(const unsigned long long*)s_alive8;
-        // (b) column of the chunk's suppression matrix
-        unsigned long long col = 0ull;
-        if (alive && (alive_mask & (alive_mask - 1ull))) {                   // at least two survivors in the chunk
-            for (int t = q; t < c; t += 4) {
-                if ((alive_mask >> t) & 1ull) {
+
+        // the candidate of the NEXT chunk (key -> code -> anchor: dependent global loads) is fetched while the current
+        // chunk is processed
+        unsigned long long nkey = 0ull;
+        float4 ncode = make_float4(0.f, 0.f, 0.f, 0.f), nanc = make_float4(0.f, 0.f, 0.f, 0.f);
+        auto fetch = [&](int i) {
+            if (i < n) {
+                nkey = keys[i];
+                const int na = key_anchor(nkey, fmt);
+                ncode = codes[(size_t)b * A + na];
+                if (!DECODED) nanc = anchors[na];
+            }
+        };
+        fetch(c);
+        int parity = 0;
+        for (int base = 0; base < n && kept < K; base += NMS_CH, parity ^= 1) {
+            const int i = base + c;
+            bool alive = i < n;
+            NmsBox box = {0.f, 0.f, 0.f, 0.f};
+            float4 raw = make_float4(0.f, 0.f, 0.f, 0.f);
+            float area = 0.f, score = 0.f;
+            int a = 0;
+            if (alive) {
+                a = key_anchor(nkey, fmt);
+                score = key_score(nkey, fmt);
+                if (DECODED) raw = ncode;
+                else raw = box_clip01(box_decode(ncode, nanc));                              // nms.py:76-77
+                box.ymin = fminf(raw.x, raw.z); box.xmin = fminf(raw.y, raw.w);
+                box.ymax = fmaxf(raw.x, raw.z); box.xmax = fmaxf(raw.y, raw.w);
+                area = f_mul(f_sub(box.ymax, box.ymin), f_sub(box.xmax, box.xmin));
+            }
+            fetch(i + NMS_CH);
+            // (a) against the boxes kept from earlier chunks
+            int hit = 0;
+            if (alive) {
+                for (int j = q; j < kept; j += NMS_TPC) {
                     bool y, am;
-                    nms_fast(box, area, s_tile[t], s_tile_area[t], iou_thr, band, y, am);
-                    if (am) y = nms_exact(box, area, s_tile[t], s_tile_area[t], iou_thr);
-                    if (y) col |= 1ull << t;
+                    nms_fast(box, area, s_kept[j], s_kept_area[j], iou_thr, band, y, am);
+                    if (am) y = nms_exact(box, area, s_kept[j], s_kept_area[j], iou_thr); // rare: within 2^-18 of the threshold
+                    hit |= y ? 1 : 0;
                 }
             }
-        }
-        col |= __shfl_xor_sync(0xffffffffu, col, 1);
-        col |= __shfl_xor_sync(0xffffffffu, col, 2);
-        if (q == 0) s_col[c] = col;
-        __syncthreads();
-        // (c) greedy walk in score order
-        if (tid == 0) {
-            unsigned long long keep = 0ull;
-            int room = K - kept;
-            for (unsigned long long todo = alive_mask; todo && room > 0;) {
-                const int j = __ffsll((long long)todo) - 1;
-                todo &= todo - 1ull;
-                if (!(s_col[j] & keep)) { keep |= 1ull << j; --room; }
+#pragma unroll
+            for (int o = 1; o < NMS_TPC; o <<= 1) hit |= __shfl_xor_sync(0xffffffffu, hit, o);
+            alive = alive && !hit;
+            if (q == 0) {
+                s_tile[c] = box;
+                s_tile_area[c] = area;
+                if (alive) atomicOr(&s_alive32[parity][c >> 5], 1u << (c & 31));
             }
-            s_keep = keep;
+            if (tid < 2) s_alive32[parity ^ 1][tid] = 0u;      // the buffer of the next chunk (last read two barriers ago)
+            __syncthreads();
+            const unsigned long long alive_mask = ((unsigned long long)s_alive32[parity][1] << 32) | s_alive32[parity][0];
+            // (b) column of the chunk's suppression matrix
+            unsigned long long col = 0ull;
+            if (alive && (alive_mask & (alive_mask - 1ull))) {               // at least two survivors in the chunk
+                for (int t = q; t < c; t += NMS_TPC) {
+                    if ((alive_mask >> t) & 1ull) {
+                        bool y, am;
+                        nms_fast(box, area, s_tile[t], s_tile_area[t], iou_thr, band, y, am);
+                        if (am) y = nms_exact(box, area, s_tile[t], s_tile_area[t], iou_thr);
+                        if (y) col |= 1ull << t;
+                    }
+                }
+            }
+#pragma unroll
+            for (int o = 1; o < NMS_TPC; o <<= 1) col |= __shfl_xor_sync(0xffffffffu, col, o);
+            if (q == 0) s_col[c] = col;
+            __syncthreads();
+            // (c) greedy order by resolution rounds (warp 0: lane l owns candidates l and l + 32)
+            if (warp == 0) {
+                const unsigned long long col_lo = s_col[lane], col_hi = s_col[lane + 32];
+                unsigned long long keep = 0ull, gone = ~alive_mask, und = alive_mask;
+                while (und) {
+                    int st_lo = 0, st_hi = 0;                                // 1 = kept, 2 = removed
+                    if ((und >> lane) & 1ull) st_lo = (col_lo & keep) ? 2 : ((col_lo & ~gone) == 0ull ? 1 : 0);
+                    if ((und >> (lane + 32)) & 1ull) st_hi = (col_hi & keep) ? 2 : ((col_hi & ~gone) == 0ull ? 1 : 0);
+                    const unsigned long long k_new = ((unsigned long long)__ballot_sync(0xffffffffu, st_hi == 1) << 32) | __ballot_sync(0xffffffffu, st_lo == 1);
+                    const unsigned long long g_new = ((unsigned long long)__ballot_sync(0xffffffffu, st_hi == 2) << 32) | __ballot_sync(0xffffffffu, st_lo == 2);
+                    keep |= k_new;
+                    gone |= g_new;
+                    und &= ~(k_new | g_new);
+                }
+                int extra = __popcll(keep) - (K - kept);                      // at most K in total: drop the lowest-scored
+                while (extra > 0) { keep &= ~(1ull << (63 - __clzll((long long)keep))); --extra; }
+                if (lane == 0) s_keep = keep;
+            }
+            __syncthreads();
+            const unsigned long long keep = s_keep;
+            // (d) append the kept candidates in score order
+            if (q == 0 && ((keep >> c) & 1ull)) {
+                const int pos = kept + __popcll(keep & ((1ull << c) - 1ull));
+                s_kept[pos] = box;
+                s_kept_area[pos] = area;
+                seg_box[obase + pos] = raw;
+                seg_score[obase + pos] = score;
+                seg_anchor[obase + pos] = a;
+            }
+            kept += __popcll(keep);
+            __syncthreads();
         }
-        __syncthreads();
-        const unsigned long long keep = s_keep;
-        // (d) append the kept candidates in score order
-        if (q == 0 && ((keep >> c) & 1ull)) {
-            const int pos = kept + __popcll(keep & ((1ull << c) - 1ull));
-            s_kept[pos] = box;
-            s_kept_area[pos] = area;
-            seg_box[obase + pos] = raw;
-            seg_score[obase + pos] = score;
-            seg_anchor[obase + pos] = a;
-        }
-        kept += __popcll(keep);
+        if (tid == 0) seg_kept[seg] = kept;
         __syncthreads();
     }
-    if (tid == 0) seg_kept[seg] = kept;
 }
 
 // ---------------------------------------------------------------------------------------------- 4. pack
@@ -482,7 +580,7 @@ extern "C" int ssdk_postprocess(ssdk_ctx* ctx, const float* codes, const float* 
     long long cap = 1024;
     while (cap < per_image) cap <<= 1;
     SSDK_TRY(ssdk_ensure(ctx, &ctx->ws_cand, (size_t)B * cap * sizeof(unsigned long long)));
-    const size_t n_int = (size_t)B * 2 + 3 * (size_t)B * C;            // counts[B], barriers[B], start, end, kept
+    const size_t n_int = (size_t)B * 2 + 4 * (size_t)B * C + 4;        // counts[B], barriers[B], start, end, kept, heavy queue + its count
     SSDK_TRY(ssdk_ensure(ctx, &ctx->ws_counts, n_int * sizeof(int)));
     const size_t seg_elems = (size_t)B * C * K;
     SSDK_TRY(ssdk_ensure(ctx, &ctx->ws_seg, seg_elems * (sizeof(float4) + sizeof(float) + sizeof(int))));
@@ -492,6 +590,8 @@ extern "C" int ssdk_postprocess(ssdk_ctx* ctx, const float* codes, const float* 
     int* seg_start = counts + 2 * (size_t)B;
     int* seg_end = seg_start + (size_t)B * C;
     int* seg_kept = seg_end + (size_t)B * C;
+    int* heavy_queue = seg_kept + (size_t)B * C;
+    int* heavy_count = heavy_queue + (size_t)B * C;
     float4* seg_box = (float4*)ctx->ws_seg.p;
     float* seg_score = (float*)(seg_box + seg_elems);
     int* seg_anchor = (int*)(seg_score + seg_elems);
@@ -544,25 +644,35 @@ extern "C" int ssdk_postprocess(ssdk_ctx* ctx, const float* codes, const float* 
                                                                                    barriers));
         }
 
-        // 3. NMS, one warp per (image, class)
+        // 3. NMS: one warp per small segment (<= 32 candidates), then one CTA per queued large segment
         const size_t nms_smem = (size_t)K * (sizeof(NmsBox) + sizeof(float));
         const long long nseg = (long long)B * C;
-        const int ngrid = (int)nseg;
+        const int sgrid_nms = ceil_div_i(nseg, NMS_SMALL_WARPS);
+        long long hgrid = (long long)ctx->num_sms * 4;
+        if (hgrid > nseg) hgrid = nseg;
+        const float4* c4 = (const float4*)codes;
+        const float4* a4 = (const float4*)anchors;
+        const float iou_f = (float)iou_threshold;
         const int nms_slot = ctx->profiling ? ssdk_prof_begin(ctx, SSDK_K_NMS) : -1;
         if (decoded) {
             SSDK_TRY(ssdk_set_max_smem(ctx, (const void*)nms_kernel<true>, (int)nms_smem));
-            nms_kernel<true><<<ngrid, NMS_THREADS, nms_smem, ctx->stream>>>(cand, cap, fmt, seg_start, seg_end, (const float4*)codes,
-                                                                              (const float4*)anchors, A, nseg, C, K,
-                                                                              (float)iou_threshold, seg_box, seg_score, seg_anchor,
-                                                                              seg_kept);
+            nms_small_kernel<true><<<sgrid_nms, NMS_SMALL_WARPS * 32, 0, ctx->stream>>>(
+                cand, cap, fmt, seg_start, seg_end, c4, a4, A, nseg, C, K, iou_f, seg_box, seg_score, seg_anchor, seg_kept,
+                heavy_queue, heavy_count);
+            nms_kernel<true><<<(int)hgrid, NMS_THREADS, nms_smem, ctx->stream>>>(
+                cand, cap, fmt, seg_start, seg_end, c4, a4, A, nseg, C, K, iou_f, seg_box, seg_score, seg_anchor, seg_kept,
+                heavy_queue, heavy_count);
         } else {
             SSDK_TRY(ssdk_set_max_smem(ctx, (const void*)nms_kernel<false>, (int)nms_smem));
-            nms_kernel<false><<<ngrid, NMS_THREADS, nms_smem, ctx->stream>>>(cand, cap, fmt, seg_start, seg_end, (const float4*)codes,
-                                                                               (const float4*)anchors, A, nseg, C, K,
-                                                                               (float)iou_threshold, seg_box, seg_score, seg_anchor,
-                                                                               seg_kept);
+            nms_small_kernel<false><<<sgrid_nms, NMS_SMALL_WARPS * 32, 0, ctx->stream>>>(
+                cand, cap, fmt, seg_start, seg_end, c4, a4, A, nseg, C, K, iou_f, seg_box, seg_score, seg_anchor, seg_kept,
+                heavy_queue, heavy_count);
+            nms_kernel<false><<<(int)hgrid, NMS_THREADS, nms_smem, ctx->stream>>>(
+                cand, cap, fmt, seg_start, seg_end, c4, a4, A, nseg, C, K, iou_f, seg_box, seg_score, seg_anchor, seg_kept,
+                heavy_queue, heavy_count);
         }
         if (nms_slot >= 0) ssdk_prof_end(ctx, nms_slot);
+        ctx->launches++;
         SSDK_CHECK_LAUNCH(ctx);
     }
     // 4. pack
