@@ -61,8 +61,8 @@ SSDK_API int64_t ssdk_ctx_launch_count(const ssdk_ctx* ctx);
 /* Optional per-kernel timing with CUDA events on the context's stream (for bench.py's roofline line; adds two
  * event records per kernel while enabled).  ssdk_ctx_profile_read synchronises the stream and returns, per kernel
  * id, the accumulated milliseconds and launch counts since the last reset.  Ids: 0 anchors, 1 match,
- * 2 force_match, 3 ssd_loss, 4 loss_reduce, 5 filter, 6 sort, 7 nms, 8 pack, 9 other. */
-#define SSDK_NUM_KERNEL_IDS 10
+ * 2 force_match, 3 ssd_loss, 4 loss_reduce, 5 filter, 6 sort, 7 nms, 8 pack, 9 other, 10 ssd_loss_backward. */
+#define SSDK_NUM_KERNEL_IDS 11
 SSDK_API int ssdk_ctx_set_profiling(ssdk_ctx* ctx, int enable);
 SSDK_API int ssdk_ctx_profile_read(ssdk_ctx* ctx, double* out_ms, int64_t* out_calls, int n, int reset);
 /* cudaStreamSynchronize on the context's stream (synchronous). */
@@ -136,6 +136,19 @@ SSDK_API int ssdk_ssd_loss(ssdk_ctx* ctx, const float* logits, const float* code
                   const int32_t* cls_targets, const int32_t* matches, int64_t B, int64_t A, int C,
                   double gamma, double alpha, double* out_sums, float* out_cls_losses,
                   float* out_loc_losses);
+/* Backward of SSD.loss (what the reference gets from TF autodiff at model.py:115-118 through ssd.py:89-133 and
+ * losses.py:4-50; targets and weights are constants, ssd.py:197): gradients of
+ *     upstream[0] * localization_loss + upstream[1] * classification_loss
+ * w.r.t. logits [B,A,C] and codes [B,A,4].
+ *   sums:     DEVICE double[3] as produced by ssdk_ssd_loss and, on several GPUs, all-reduced: only sums[2]
+ *             (the GLOBAL num_matches) is read; normalizer = max(sums[2], 1) (ssd.py:123).
+ *   upstream: DEVICE float[2] = { dL/d localization_loss, dL/d classification_loss }, e.g. the config's
+ *             localization_loss_weight / classification_loss_weight (model.py:86-87); NULL = {1, 1}.
+ *   grad_logits [B,A,C], grad_codes [B,A,4]: DEVICE outputs, every element is written. */
+SSDK_API int ssdk_ssd_loss_backward(ssdk_ctx* ctx, const float* logits, const float* codes, const float* reg_targets,
+                           const int32_t* cls_targets, const int32_t* matches, int64_t B, int64_t A, int C,
+                           double gamma, double alpha, const double* sums, const float* upstream,
+                           float* grad_logits, float* grad_codes);
 /* normalizer = max(num_matches, 1) (ssd.py:123); out_losses: DEVICE float[2] =
  * { localization_loss, classification_loss } (ssd.py:133).  `sums` are the (all-reduced) sums. */
 SSDK_API int ssdk_loss_finalize(ssdk_ctx* ctx, const double* sums, float* out_losses);

@@ -41,6 +41,7 @@ _SIGNATURES = {
     'ssdk_focal_loss': (c_int, [P, P, P, P, c_i64, c_i64, c_int, c_double, c_double, P]),
     'ssdk_ssd_loss': (c_int, [P, P, P, P, P, P, c_i64, c_i64, c_int, c_double, c_double, P, P, P]),
     'ssdk_loss_finalize': (c_int, [P, P, P]),
+    'ssdk_ssd_loss_backward': (c_int, [P, P, P, P, P, P, c_i64, c_i64, c_int, c_double, c_double, P, P, P, P]),
     'ssdk_ssd_targets_and_loss': (c_int, [P, P, P, P, P, P, P, c_int, c_i64, c_int, c_int, c_double, c_double,
                                           c_double, c_double, P, P, P, P, P, P]),
     'ssdk_ssd_targets_and_loss_host': (c_int, [P, P, P, P, P, P, P, c_int, c_i64, c_int, c_int, c_double, c_double,
@@ -101,7 +102,8 @@ def context(device_index):
     return ctx
 
 
-KERNEL_IDS = ['anchors', 'match', 'force_match', 'ssd_loss', 'loss_reduce', 'filter', 'sort', 'nms', 'pack', 'other']
+KERNEL_IDS = ['anchors', 'match', 'force_match', 'ssd_loss', 'loss_reduce', 'filter', 'sort', 'nms', 'pack', 'other',
+              'ssd_loss_backward']
 
 
 def set_profiling(enable, device_index=0):

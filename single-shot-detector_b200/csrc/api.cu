@@ -33,16 +33,23 @@ int ssdk_ensure(ssdk_ctx* ctx, ssdk_buf* b, size_t bytes) {
     return SSDK_OK;
 }
 
-// Raise a kernel's dynamic shared-memory limit once per (context, kernel) instead of on every launch.
+// Raise a kernel's dynamic shared-memory limit once per (device, kernel) instead of on every launch.  The attribute is
+// a property of the function on the device, not of a context, so the record is process-wide (contexts of other host
+// threads -- e.g. the autograd engine's -- launch the same kernels) and the limit is only ever raised.
+#include <mutex>
+static std::mutex g_smem_mutex;
+static struct { int device; const void* func; int bytes; } g_smem[64];
+static int g_smem_n = 0;
+
 int ssdk_set_max_smem(ssdk_ctx* ctx, const void* func, int bytes) {
+    std::lock_guard<std::mutex> lock(g_smem_mutex);
     int slot = -1;
-    for (int i = 0; i < 16; ++i) {
-        if (ctx->smem_func[i] == func) { slot = i; break; }
-        if (ctx->smem_func[i] == nullptr && slot < 0) slot = i;
-    }
-    if (slot >= 0 && ctx->smem_func[slot] == func && ctx->smem_bytes[slot] >= bytes) return SSDK_OK;
+    for (int i = 0; i < g_smem_n; ++i)
+        if (g_smem[i].device == ctx->device && g_smem[i].func == func) { slot = i; break; }
+    if (slot >= 0 && g_smem[slot].bytes >= bytes) return SSDK_OK;
     SSDK_CHECK_CUDA(cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-    if (slot >= 0) { ctx->smem_func[slot] = func; ctx->smem_bytes[slot] = bytes; }
+    if (slot < 0 && g_smem_n < 64) slot = g_smem_n++;
+    if (slot >= 0) { g_smem[slot].device = ctx->device; g_smem[slot].func = func; g_smem[slot].bytes = bytes; }
     return SSDK_OK;
 }
 

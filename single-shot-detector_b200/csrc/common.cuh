@@ -18,7 +18,7 @@ struct ssdk_buf {
 // kernel ids for the optional per-kernel event timing (ssdk_ctx_set_profiling)
 enum ssdk_kernel_id {
     SSDK_K_ANCHORS = 0, SSDK_K_MATCH, SSDK_K_FORCE_MATCH, SSDK_K_LOSS, SSDK_K_LOSS_REDUCE, SSDK_K_FILTER,
-    SSDK_K_SORT, SSDK_K_NMS, SSDK_K_PACK, SSDK_K_OTHER, SSDK_K_COUNT
+    SSDK_K_SORT, SSDK_K_NMS, SSDK_K_PACK, SSDK_K_OTHER, SSDK_K_LOSS_BACKWARD, SSDK_K_COUNT
 };
 #define SSDK_PROFILE_EVENTS 2048
 
@@ -42,9 +42,6 @@ struct ssdk_ctx {
     int prof_id[SSDK_PROFILE_EVENTS];
     double prof_ms[SSDK_K_COUNT] = {0};
     long long prof_calls[SSDK_K_COUNT] = {0};
-    // cudaFuncSetAttribute(MaxDynamicSharedMemorySize) results, so that the steady state makes no such call
-    const void* smem_func[16] = {nullptr};
-    int smem_bytes[16] = {0};
     int sort_occupancy = 0;
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};

@@ -22,101 +22,9 @@
 //     shuffle reduction per row, the reference's 1-(1-p) rounding reproduced per element.
 //   * sums are carried per thread in double across tiles, reduced warp -> CTA, written as per-CTA partials and
 //     combined in a fixed order by a second kernel: deterministic, no float atomics.
-#include "common.cuh"
-
-#define LOSS_CONSUMER_WARPS 8
-#define LOSS_THREADS ((LOSS_CONSUMER_WARPS + 1) * 32)
-#define LOSS_MAX_STAGES 4
-
-// ---------------------------------------------------------------------------------------------- PTX helpers
-__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned long long* bar, unsigned bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
-    unsigned done;
-    do {
-        asm volatile(
-            "{\n"
-            ".reg .pred p;\n"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-            "selp.u32 %0, 1, 0, p;\n"
-            "}\n"
-            : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
-    } while (!done);
-}
-// TMA bulk copy global -> shared, completion signalled on an mbarrier (SASS: UBLKCP)
-__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
-                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
-                 : "memory");
-}
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-
-__device__ __forceinline__ float ex2_approx(float x) {
-    float y;
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-    return y;
-}
-__device__ __forceinline__ float rcp_approx(float x) {
-    float y;
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-    return y;
-}
-
-// packed pairs of floats (Blackwell FFMA2 / FMUL2 / FADD2: one issue slot for two elements)
-typedef unsigned long long f32x2;
-__device__ __forceinline__ f32x2 pack2(float lo, float hi) {
-    f32x2 r;
-    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
-    return r;
-}
-__device__ __forceinline__ void unpack2(f32x2 v, float& lo, float& hi) {
-    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
-}
-__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
-    f32x2 d;
-    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
-    return d;
-}
-__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
-    f32x2 d;
-    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
-    return d;
-}
-__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) {
-    f32x2 d;
-    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
-    return d;
-}
-__device__ __forceinline__ f32x2 splat2(float c) { return pack2(c, c); }
+#include "stream.cuh"
 
 // ---------------------------------------------------------------------------------------------- per-element math
-// log1p(e)/e on [0,1]: degree-7 minimax polynomial (relative error 1.9e-7)
-#define L1P_C7 -8.539209655e-03f
-#define L1P_C6 4.408963566e-02f
-#define L1P_C5 -1.076817184e-01f
-#define L1P_C4 1.774524181e-01f
-#define L1P_C3 -2.449546295e-01f
-#define L1P_C2 3.327547979e-01f
-#define L1P_C1 -4.999740540e-01f
-#define L1P_C0 9.999998057e-01f
-
-__device__ __forceinline__ float log1p_unit(float e) {
-    float p = L1P_C7;
-    p = fmaf(p, e, L1P_C6); p = fmaf(p, e, L1P_C5); p = fmaf(p, e, L1P_C4); p = fmaf(p, e, L1P_C3);
-    p = fmaf(p, e, L1P_C2); p = fmaf(p, e, L1P_C1); p = fmaf(p, e, L1P_C0);
-    return p * e;
-}
-
 // Negative-class term without the (1-alpha) factor, reference rounding: (1 - p_t)^gamma * nlpt with targets == 0
 // (losses.py:36-41: nlpt = max(x,0) + log1p(exp(-|x|)), p_t = 1 - p, modulating factor (1 - (1 - p))^gamma).
 template <int GAMMA_MODE>
@@ -220,12 +128,6 @@ __device__ __forceinline__ float smooth_l1_4(const float4 a, const float4 b) {
 }
 
 // ---------------------------------------------------------------------------------------------- kernel
-struct LossSmemLayout {
-    unsigned tile_bytes;    // rows*C*4 (multiple of 16)
-    unsigned meta_bytes;    // rows*4   (multiple of 16)
-    unsigned stage_bytes;   // tile + 2*meta
-    unsigned stages;
-};
 
 template <int GAMMA_MODE, bool PER_ANCHOR>
 __global__ void __launch_bounds__(LOSS_THREADS, 4) ssd_loss_kernel(

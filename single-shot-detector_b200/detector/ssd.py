@@ -16,6 +16,24 @@ class _ShapeOnly:
         self.shape = shape
 
 
+class _SSDLossFunction(torch.autograd.Function):
+    """SSD.loss as a differentiable torch op: forward = targets + fused loss, backward = ssdk_ssd_loss_backward."""
+
+    @staticmethod
+    def forward(ctx, logits, codes, head, groundtruth, params):
+        losses = head._loss_forward(groundtruth, params, keep_targets=True)
+        ctx.head = head
+        ctx.saved = head._saved
+        return torch.stack([losses['localization_loss'], losses['classification_loss']])
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        head = ctx.head
+        head._saved = ctx.saved
+        grads = head.loss_backward(grad_out.contiguous())
+        return grads['class_predictions'], grads['encoded_boxes'], None, None, None
+
+
 class SSD:
     def __init__(self, images, feature_extractor, anchor_generator, box_predictor, num_classes):
         """Same arguments as the reference (ssd.py:10-40).  `images`: [B, H, W, 3] tensor (only its shape is
@@ -100,7 +118,7 @@ class SSD:
         return {'boxes': boxes, 'labels': classes, 'scores': scores, 'num_boxes': num}
 
     # ------------------------------------------------------------------ training (ssd.py:71-133)
-    def loss_sums(self, groundtruth, params, per_anchor=False):
+    def loss_sums(self, groundtruth, params, per_anchor=False, keep_targets=False):
         """Un-normalised shard sums: float64 CUDA tensor [3] = (sum loc_losses, sum cls_losses, num_matches).
         With per_anchor=True also returns the tensors the reference's summaries consume (ssd.py:125-129)."""
         from . import ssd as this_module      # thresholds are module constants, as in ssd.py:187-188
@@ -115,10 +133,11 @@ class SSD:
         num = call.tensor(groundtruth['num_boxes'], torch.int32, (B,))
         sums = call.empty([3], torch.float64)
         extra = {}
-        if per_anchor:
+        if per_anchor or keep_targets:
             extra = {'reg_targets': call.empty([B, A, 4], torch.float32), 'cls_targets': call.empty([B, A], torch.int32),
-                     'matches': call.empty([B, A], torch.int32), 'cls_losses': call.empty([B, A], torch.float32),
-                     'loc_losses': call.empty([B, A], torch.float32)}
+                     'matches': call.empty([B, A], torch.int32)}
+        if per_anchor:
+            extra.update({'cls_losses': call.empty([B, A], torch.float32), 'loc_losses': call.empty([B, A], torch.float32)})
         _lib.check(_lib.load().ssdk_ssd_targets_and_loss(
             call.ctx(), ptr(anchors), ptr(logits), ptr(codes), ptr(gt), ptr(labels), ptr(num), B, A, C, G,
             float(this_module.POSITIVES_THRESHOLD), float(this_module.NEGATIVES_THRESHOLD),
@@ -126,6 +145,9 @@ class SSD:
             ptr(extra.get('reg_targets')), ptr(extra.get('cls_targets')), ptr(extra.get('matches')),
             ptr(extra.get('cls_losses')), ptr(extra.get('loc_losses'))))
         self._call = call
+        if keep_targets:          # what loss_backward needs: the inputs of the loss kernel and the (later all-reduced) sums
+            self._saved = dict(logits=logits, codes=codes, sums=sums, gamma=float(params['gamma']), alpha=float(params['alpha']),
+                               **{k: extra[k] for k in ('reg_targets', 'cls_targets', 'matches')})
         return (sums, extra) if per_anchor else sums
 
     def loss(self, groundtruth, params):
@@ -143,7 +165,14 @@ class SSD:
                 losses = np.array([sums[0] / norm, sums[1] / norm], np.float32)
             self.num_matches = sums[2]
             return {'localization_loss': losses[0], 'classification_loss': losses[1]}
-        sums = self.loss_sums(groundtruth, params)
+        logits_in, codes_in = self.raw_predictions['class_predictions'], self.raw_predictions['encoded_boxes']
+        if torch.is_grad_enabled() and isinstance(logits_in, torch.Tensor) and (logits_in.requires_grad or codes_in.requires_grad):
+            out = _SSDLossFunction.apply(logits_in, codes_in, self, groundtruth, params)      # differentiable (model.py:115-118)
+            return {'localization_loss': out[0], 'classification_loss': out[1]}
+        return self._loss_forward(groundtruth, params, keep_targets=False)
+
+    def _loss_forward(self, groundtruth, params, keep_targets):
+        sums = self.loss_sums(groundtruth, params, keep_targets=keep_targets)
         if self.process_group is not None:
             import torch.distributed as dist
             dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=None if self.process_group is True else self.process_group)
@@ -155,6 +184,36 @@ class SSD:
             o = out.cpu().numpy()
             return {'localization_loss': o[0], 'classification_loss': o[1]}
         return {'localization_loss': out[0], 'classification_loss': out[1]}
+
+    def loss_backward(self, upstream=None):
+        """Gradients of  upstream[0] * localization_loss + upstream[1] * classification_loss  w.r.t. the head outputs,
+        for the last `loss(...)` / `loss_with_gradients(...)` call: {'class_predictions': [B,A,C], 'encoded_boxes': [B,A,4]}.
+        This is what the reference obtains from TF autodiff (model.py:115-118); targets and weights are constants
+        (ssd.py:197).  `upstream`: None (= 1, 1), a pair of floats (the config's loss weights, model.py:86-87) or a
+        float32 CUDA tensor [2].  Uses the global (all-reduced) matched count as normaliser."""
+        sv = getattr(self, '_saved', None)
+        if sv is None:
+            raise RuntimeError('loss_backward() needs a preceding loss_with_gradients() or differentiable loss() call')
+        logits, codes = sv['logits'], sv['codes']
+        B, A, C = logits.shape
+        call = Call(logits.device)
+        up = None
+        if upstream is not None:
+            up = call.tensor(upstream, torch.float32, (2,)) if isinstance(upstream, torch.Tensor) else \
+                torch.tensor([float(upstream[0]), float(upstream[1])], dtype=torch.float32, device=logits.device)
+        g_logits = call.empty([B, A, C], torch.float32)
+        g_codes = call.empty([B, A, 4], torch.float32)
+        _lib.check(_lib.load().ssdk_ssd_loss_backward(
+            call.ctx(), ptr(logits), ptr(codes), ptr(sv['reg_targets']), ptr(sv['cls_targets']), ptr(sv['matches']), B, A, C,
+            sv['gamma'], sv['alpha'], ptr(sv['sums']), ptr(up), ptr(g_logits), ptr(g_codes)))
+        self._call_bw = (call, up)
+        return {'class_predictions': g_logits, 'encoded_boxes': g_codes}
+
+    def loss_with_gradients(self, groundtruth, params, upstream=None):
+        """One training step of the hot path without autograd: (losses, gradients) = forward (targets + losses, sums
+        all-reduced when `process_group` is set) followed by loss_backward(upstream)."""
+        losses = self._loss_forward(groundtruth, params, keep_targets=True)
+        return losses, self.loss_backward(upstream)
 
     def _create_targets(self, groundtruth):
         """reference ssd.py:165-199: reg_targets [B,A,4], cls_targets [B,A], matches [B,A]."""

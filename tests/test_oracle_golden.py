@@ -166,3 +166,59 @@ def test_nms_restatement_vs_torchvision():
         keep = np.array([k for k in keep if s[k] > 0.05][:50])
         assert np.array_equal(mine, keep)
         assert np.array_equal(mine, nms.non_max_suppression_v3(b, s, 50, 0.5, 0.05, use_c=False))
+
+
+# ------------------------------------------------------------------------------------------------ gradient oracle
+def _small_train_case(syn, seed=5, B=2, C=4, G=3, H=64, W=96):
+    from oracle.anchor_generator import AnchorGenerator as OracleGen
+    anchors = OracleGen()(H, W)
+    A = anchors.shape[0]
+    gt = syn.make_groundtruth(seed, B, G, H, W, C)
+    logits = syn.make_logits('realistic', seed, B, A, C, anchors, gt)
+    codes = (syn.make_codes(seed, B, A) * np.float32(0.7)).astype(np.float32)
+    return anchors, gt, logits, codes, C
+
+
+@pytest.mark.parametrize('thr', [(0.5, 0.5), (0.5, 0.4)])
+def test_gradient_oracle_forward64_matches_pinned_forward(syn, thr):
+    """forward64 (the function the gradient oracle differentiates) == the float32 forward oracle, which the golden
+    fixtures pin to the reference's own code."""
+    from oracle import losses_grad as og, ssd as ossd
+    anchors, gt, logits, codes, C = _small_train_case(syn)
+    params = {'gamma': 2.0, 'alpha': 0.25}
+    want = ossd.loss(anchors, codes, logits, gt, params, C, positives_threshold=thr[0], negatives_threshold=thr[1])
+    loc, cls = og.forward64(anchors, codes, logits, gt, params, C, positives_threshold=thr[0], negatives_threshold=thr[1])
+    assert abs(loc - float(want['localization_loss'])) <= 2e-6 * abs(loc)
+    assert abs(cls - float(want['classification_loss'])) <= 2e-6 * abs(cls)
+
+
+@pytest.mark.parametrize('gamma,alpha', [(2.0, 0.25), (1.5, 0.4)])
+def test_gradient_oracle_matches_finite_differences(syn, gamma, alpha):
+    from oracle import losses_grad as og
+    anchors, gt, logits, codes, C = _small_train_case(syn)
+    params = {'gamma': gamma, 'alpha': alpha}
+    up = (0.7, 1.3)
+    parts = og._parts(anchors, gt, C, 0.5, 0.4)
+    g = og.ssd_loss_grad(anchors, codes, logits, gt, params, C, upstream=up, parts=parts)
+    assert g['num_matches'] > 0 and (parts[3] == 0).any(), 'case must contain matched and ignored anchors'
+
+    def total(lg, cd):
+        loc, cls = og.forward64(anchors, cd, lg, gt, params, C, parts=parts)
+        return up[0] * loc + up[1] * cls
+    rng = np.random.default_rng(0)
+    x64, c64 = logits.astype(np.float64), codes.astype(np.float64)
+    matched_rows = np.argwhere(parts[2] > 0)
+    picks = [tuple(rng.integers(0, s) for s in x64.shape) for _ in range(40)]
+    picks += [(b, a, int(np.argmax(parts[1][b, a]))) for b, a in matched_rows[:20]]            # positive-class elements
+    h = 1e-5
+    for idx in picks:
+        xp, xm = x64.copy(), x64.copy()
+        xp[idx] += h; xm[idx] -= h
+        fd = (total(xp, c64) - total(xm, c64)) / (2 * h)
+        assert abs(fd - g['class_predictions'][idx]) <= 1e-6 * abs(fd) + 3e-10, (idx, fd, g['class_predictions'][idx])   # 3e-10: float64 round-off of the O(1) total / h
+    for b, a in list(matched_rows[:10]) + [(0, 0)]:
+        for k in range(4):
+            cp, cm = c64.copy(), c64.copy()
+            cp[b, a, k] += h; cm[b, a, k] -= h
+            fd = (total(x64, cp) - total(x64, cm)) / (2 * h)
+            assert abs(fd - g['encoded_boxes'][b, a, k]) <= 1e-6 * abs(fd) + 3e-10
