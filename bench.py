@@ -31,6 +31,7 @@ PKG = 'single-shot-detector_b200'
 TRAIN_CFG, INFER_CFG = 2, 3
 SCORE_THR, IOU_THR, K_PER_CLASS = 0.05, 0.5, 100
 PARAMS = {'gamma': 2.0, 'alpha': 0.25}
+UPSTREAM = (1.0, 1.0)          # localization_loss_weight, classification_loss_weight of the shipped configs
 
 
 def parse():
@@ -228,6 +229,15 @@ def workload_config(syn, sample=None):
 
 
 # ------------------------------------------------------------------------------------------------ GPU arm
+def finish_rank(world):
+    """Multi-rank teardown.  Destroying an NCCL communicator that live CUDA graphs still reference can block for
+    minutes; all results are out by now, so flush and leave the process without running that teardown."""
+    if world > 1:
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -348,11 +358,14 @@ def run_ours(args):
         return timed_loop(run, n)[0] / n
     ms_train = timed(lambda: ssd_t.loss(d_gt, PARAMS), args.steps)
     ms_infer = timed(lambda: ssd_i.get_predictions(SCORE_THR, IOU_THR, K_PER_CLASS), args.steps)
+    # forward + backward of the training side: targets, losses, all-reduce, gradients w.r.t. both heads
+    ms_train_fb = timed(lambda: ssd_t.loss_with_gradients(d_gt, PARAMS, upstream=UPSTREAM), args.steps)
 
     # ---- per-kernel durations (library-side CUDA events on the launching stream) for the roofline object
     lib.set_profiling(True, local_rank)
     for _ in range(min(args.steps, 10)):
         step_resident()
+        ssd_t.loss_backward(UPSTREAM)
     prof = lib.profile_read(local_rank)
     lib.set_profiling(False, local_rank)
     peaks = {}
@@ -374,7 +387,9 @@ def run_ours(args):
                 'traffic': None, 'avg_launch_ms': avg_ms, 'algorithmic_bytes_per_launch': bytes_per_launch, 'peak_source': peak_src}
     roof_loss = kernel_roof('ssd_loss', b_loss * Bt)
     roof_filter = kernel_roof('filter', b_filter * Bi)
-    step_kernel_ms = {k: (v[0] / max(1, min(args.steps, 10))) for k, v in prof.items() if v[1]}
+    b_backward = 8 * A * C + 56 * A                 # logits read + grad written; codes, reg_targets, grad_codes, cls, matches
+    roof_backward = kernel_roof('ssd_loss_backward', b_backward * Bt)
+    step_kernel_ms = {k: (v[0] / max(1, min(args.steps, 10))) for k, v in prof.items() if v[1] and k != 'ssd_loss_backward'}
     dominant = max((r for r in (roof_loss, roof_filter) if r), key=lambda r: r['avg_launch_ms'])
     dominant = dict(dominant)
     dominant['share_of_step_kernel_time'] = dominant['avg_launch_ms'] / max(1e-9, sum(step_kernel_ms.values()))
@@ -415,8 +430,7 @@ def run_ours(args):
     if world > 1:
         dist.barrier()
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
+        finish_rank(world)
         return
 
     cpu = None
@@ -444,13 +458,14 @@ def run_ours(args):
             'infer_frac_of_hbm_roofline': (b_infer * Bi / (ms_infer * 1e-3) / 1e9) / peak,
             'algorithmic_bytes_per_image': {'train': b_train, 'infer': b_infer},
             'kernel_ms_per_step': step_kernel_ms,
-            'roofline_ssd_loss': roof_loss, 'roofline_filter': roof_filter,
+            'roofline_ssd_loss': roof_loss, 'roofline_filter': roof_filter, 'roofline_ssd_loss_backward': roof_backward,
+            'train_fwd_bwd_images_per_sec': Bt * world / (ms_train_fb * 1e-3), 'train_fwd_bwd_ms_per_step': ms_train_fb,
+            'train_fwd_bwd_frac_of_hbm_roofline': ((b_train + 8 * A * C // 2 + 16 * A) * Bt / (ms_train_fb * 1e-3) / 1e9) / peak,
         },
         'check': check,
     }
     print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    finish_rank(world)
 
 
 if __name__ == '__main__':

@@ -5,14 +5,14 @@ TAG=${2:-r01}
 OUT=gpurun_out
 mkdir -p $OUT
 nvidia-smi -L > $OUT/${TAG}_multi_gpus.txt
-timeout 600 python -m pytest tests/test_multi_gpu.py -m gpu -x -q > $OUT/${TAG}_multi_pytest.log 2>&1; echo "pytest exit $?" >> $OUT/${TAG}_multi_pytest.log
+timeout 240 python -m pytest tests/test_multi_gpu.py -m gpu -x -q > $OUT/${TAG}_multi_pytest.log 2>&1; echo "pytest exit $?" >> $OUT/${TAG}_multi_pytest.log
 tail -5 $OUT/${TAG}_multi_pytest.log
 for n in 1 2 4 8; do
   if [ $n -le $N ]; then
     if [ $n -eq 1 ]; then
-      timeout 600 python bench.py --gpus 1 --no-cpu-baseline > $OUT/${TAG}_scale_n$n.json 2> $OUT/${TAG}_scale_n$n.err
+      timeout 240 python bench.py --gpus 1 --no-cpu-baseline > $OUT/${TAG}_scale_n$n.json 2> $OUT/${TAG}_scale_n$n.err
     else
-      timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 29511 \
+      timeout 240 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 29511 \
         bench.py --gpus $n --no-cpu-baseline > $OUT/${TAG}_scale_n$n.json 2> $OUT/${TAG}_scale_n$n.err
     fi
     echo "n=$n exit $?"; python - <<PY
