@@ -377,6 +377,13 @@ def run_ours(args):
     peak_src = 'MEASURED_PEAKS.json hbm_gbs (of measured)' if 'hbm_gbs' in peaks else 'fallback 6650 GB/s (of fallback)'
     b_train, b_infer, b_loss, b_filter = algorithmic_bytes(A, C, G, K_PER_CLASS)
 
+    # DRAM traffic per launch from the committed `ncu --set full` capture of this same command (profiles/ncu_traffic.json,
+    # written by scripts/ncu_traffic.py); null for kernels that capture does not contain
+    try:
+        ncu_traffic = json.load(open(os.path.join(ROOT, 'profiles', 'ncu_traffic.json')))
+    except Exception:
+        ncu_traffic = {}
+
     def kernel_roof(name, bytes_per_launch):
         tot, n = prof[name]
         if n == 0:
@@ -384,7 +391,7 @@ def run_ours(args):
         avg_ms = tot / n
         ach = bytes_per_launch / (avg_ms * 1e-3) / 1e9
         return {'kernel': name, 'bound': 'hbm', 'achieved': ach, 'peak': peak, 'unit': 'GB/s', 'frac': ach / peak,
-                'traffic': None, 'avg_launch_ms': avg_ms, 'algorithmic_bytes_per_launch': bytes_per_launch, 'peak_source': peak_src}
+                'traffic': (ncu_traffic.get(name + '_kernel') or {}).get('dram_bytes_per_launch'), 'avg_launch_ms': avg_ms, 'algorithmic_bytes_per_launch': bytes_per_launch, 'peak_source': peak_src}
     roof_loss = kernel_roof('ssd_loss', b_loss * Bt)
     roof_filter = kernel_roof('filter', b_filter * Bi)
     b_backward = 8 * A * C + 56 * A                 # logits read + grad written; codes, reg_targets, grad_codes, cls, matches
