@@ -149,6 +149,19 @@ SSDK_API int ssdk_ssd_loss_backward(ssdk_ctx* ctx, const float* logits, const fl
                            const int32_t* cls_targets, const int32_t* matches, int64_t B, int64_t A, int C,
                            double gamma, double alpha, const double* sums, const float* upstream,
                            float* grad_logits, float* grad_codes);
+/* Forward and backward of SSD.loss in ONE pass over the logits (a training step reads class_predictions once and
+ * writes its gradient once).  The normaliser must therefore be known before the pass:
+ *   num_matches: DEVICE double[1], the GLOBAL matched-anchor count (ssdk_count_matches on this shard's `matches`,
+ *                all-reduced by the caller on several GPUs); normalizer = max(*num_matches, 1) (ssd.py:123).
+ *   out_sums:    DEVICE double[3] = this shard's un-normalised { sum loc_losses, sum cls_losses, num_matches }, as
+ *                ssdk_ssd_loss produces (all-reduce + ssdk_loss_finalize give the reported losses).
+ * Other arguments as ssdk_ssd_loss_backward. */
+SSDK_API int ssdk_ssd_loss_forward_backward(ssdk_ctx* ctx, const float* logits, const float* codes, const float* reg_targets,
+                                   const int32_t* cls_targets, const int32_t* matches, int64_t B, int64_t A, int C,
+                                   double gamma, double alpha, const double* num_matches, const float* upstream,
+                                   double* out_sums, float* grad_logits, float* grad_codes);
+/* out_count: DEVICE double[1] = number of entries of matches[n] that are >= 0 (ssd.py:89,121-122). */
+SSDK_API int ssdk_count_matches(ssdk_ctx* ctx, const int32_t* matches, int64_t n, double* out_count);
 /* normalizer = max(num_matches, 1) (ssd.py:123); out_losses: DEVICE float[2] =
  * { localization_loss, classification_loss } (ssd.py:133).  `sums` are the (all-reduced) sums. */
 SSDK_API int ssdk_loss_finalize(ssdk_ctx* ctx, const double* sums, float* out_losses);
@@ -188,7 +201,17 @@ SSDK_API int ssdk_postprocess(ssdk_ctx* ctx, const float* codes, const float* an
                      int flags, int B, int64_t A, int C, double score_threshold,
                      double iou_threshold, int K, float* out_boxes, float* out_scores,
                      int32_t* out_classes, int32_t* out_num, int32_t* out_anchor_idx);
-/* Same with HOST buffers (synchronous). */
+/* ssdk_postprocess plus the two consumers that directly follow it in the reference:
+ *   box_scaler: DEVICE float[B,4] (16-byte aligned) or NULL -- boxes /= box_scaler[b] (model.py:67-68: undoes the
+ *               resize / padding of the input pipeline), an IEEE division per coordinate;
+ *   final_score_threshold: keeps only detections with score > it, order preserved, outputs re-packed and
+ *               out_num updated (inference/detector.py:54-58: `to_keep = scores > score_threshold`); pass
+ *               -INFINITY to keep everything. */
+SSDK_API int ssdk_detect(ssdk_ctx* ctx, const float* codes, const float* anchors, const float* scores, int flags, int B,
+                int64_t A, int C, double score_threshold, double iou_threshold, int K, const float* box_scaler,
+                double final_score_threshold, float* out_boxes, float* out_scores, int32_t* out_classes,
+                int32_t* out_num);
+/* Same as ssdk_postprocess with HOST buffers (synchronous). */
 SSDK_API int ssdk_postprocess_host(ssdk_ctx* ctx, const float* codes, const float* anchors,
                           const float* scores, int flags, int B, int64_t A, int C,
                           double score_threshold, double iou_threshold, int K, float* out_boxes,

@@ -41,12 +41,15 @@ _SIGNATURES = {
     'ssdk_focal_loss': (c_int, [P, P, P, P, c_i64, c_i64, c_int, c_double, c_double, P]),
     'ssdk_ssd_loss': (c_int, [P, P, P, P, P, P, c_i64, c_i64, c_int, c_double, c_double, P, P, P]),
     'ssdk_loss_finalize': (c_int, [P, P, P]),
+    'ssdk_ssd_loss_forward_backward': (c_int, [P, P, P, P, P, P, c_i64, c_i64, c_int, c_double, c_double, P, P, P, P, P]),
+    'ssdk_count_matches': (c_int, [P, P, c_i64, P]),
     'ssdk_ssd_loss_backward': (c_int, [P, P, P, P, P, P, c_i64, c_i64, c_int, c_double, c_double, P, P, P, P]),
     'ssdk_ssd_targets_and_loss': (c_int, [P, P, P, P, P, P, P, c_int, c_i64, c_int, c_int, c_double, c_double,
                                           c_double, c_double, P, P, P, P, P, P]),
     'ssdk_ssd_targets_and_loss_host': (c_int, [P, P, P, P, P, P, P, c_int, c_i64, c_int, c_int, c_double, c_double,
                                                c_double, c_double, P, P]),
     'ssdk_postprocess': (c_int, [P, P, P, P, c_int, c_int, c_i64, c_int, c_double, c_double, c_int, P, P, P, P, P]),
+    'ssdk_detect': (c_int, [P, P, P, P, c_int, c_int, c_i64, c_int, c_double, c_double, c_int, P, c_double, P, P, P, P]),
     'ssdk_postprocess_host': (c_int, [P, P, P, P, c_int, c_int, c_i64, c_int, c_double, c_double, c_int, P, P, P, P]),
 }
 

@@ -22,6 +22,8 @@
 //     shuffle reduction per row, the reference's 1-(1-p) rounding reproduced per element.
 //   * sums are carried per thread in double across tiles, reduced warp -> CTA, written as per-CTA partials and
 //     combined in a fixed order by a second kernel: deterministic, no float atomics.
+#include <stdlib.h>
+
 #include "stream.cuh"
 
 // ---------------------------------------------------------------------------------------------- per-element math
@@ -405,6 +407,7 @@ int ssdk_ssd_loss(ssdk_ctx* ctx, const float* logits, const float* codes, const 
     // tile = 8 consumer warps x rpw rows; rpw is a multiple of 4 (so rpw*C*4 and rpw*4 bytes are multiples of 16)
     // and at most 32 (one lane per row); about 24 KB per stage
     int rpw = (int)(24576 / (32 * (long long)C)) / 4 * 4;
+    if (const char* e = getenv("SSDK_LOSS_RPW")) rpw = atoi(e);          // tuning knob (rows per warp, multiple of 4)
     if (rpw < 4) rpw = 4;
     if (rpw > 32) rpw = 32;
     const int rows = rpw * LOSS_CONSUMER_WARPS;
@@ -417,12 +420,16 @@ int ssdk_ssd_loss(ssdk_ctx* ctx, const float* logits, const float* codes, const 
                  "ssdk_ssd_loss: num_classes %d too large for the fused kernel (limit about 780); use ssdk_focal_loss", C);
     if (L.stage_bytes < 12 * 1024) L.stages = 4;
     else if (L.stage_bytes < 20 * 1024) L.stages = 3;
+    if (const char* e = getenv("SSDK_LOSS_STAGES")) L.stages = (unsigned)atoi(e);   // tuning knob (2..4)
+    if (L.stages < 2) L.stages = 2;
+    if (L.stages > LOSS_MAX_STAGES) L.stages = LOSS_MAX_STAGES;
     const size_t smem = 128 + (size_t)L.stages * L.stage_bytes;
 
     const long long ntiles = (NA + rows - 1) / rows;
     int per_sm = (int)((227 * 1024) / (smem + 1024 + 2048));   // + reserved + static shared memory
     if (per_sm < 1) per_sm = 1;
     if (per_sm > 5) per_sm = 5;
+    if (const char* e = getenv("SSDK_LOSS_CTAS")) per_sm = atoi(e);             // tuning knob (CTAs per SM)
     long long grid = (long long)ctx->num_sms * per_sm;
     if (grid > ntiles) grid = ntiles;
 

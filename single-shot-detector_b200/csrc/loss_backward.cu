@@ -43,17 +43,47 @@ __device__ __forceinline__ float focal_positive_grad(float x, float gamma) {
     return mod * (gamma * p * logp - q);
 }
 
+// value and d/dx of the negative-class term (both without the (1-alpha) factor): shares e, r, softplus
+template <int GAMMA_MODE>
+__device__ __forceinline__ float focal_negative_both(float x, float gamma, float& value) {
+    const float e = ex2_approx(-fabsf(x) * 1.4426950408889634f);
+    const float r = rcp_approx(1.0f + e);
+    const float er = e * r;
+    const float p = (x >= 0.0f) ? r : er;
+    const float q = (x >= 0.0f) ? er : r;
+    const float sp = fmaxf(x, 0.0f) + log1p_unit(e);
+    const float mod = (GAMMA_MODE == 0) ? p * p : powf(p, gamma);
+    value = mod * sp;
+    return mod * fmaf(gamma * q, sp, p);
+}
+
+// value of the positive-class term without the alpha factor: losses.py:36-41 with targets == 1
+template <int GAMMA_MODE>
+__device__ __forceinline__ float focal_positive_value(float x, float gamma) {
+    const float nlpt = (fmaxf(x, 0.0f) - x) + log1pf(expf(-fabsf(x)));
+    const float q = 1.0f / (1.0f + expf(x));
+    const float mod = (GAMMA_MODE == 0) ? q * q : powf(q, gamma);
+    return mod * nlpt;
+}
+
+__device__ __forceinline__ float smooth_l1_value(float p, float t) {
+    const float d = fabsf(p - t);
+    return d < 1.0f ? 0.5f * d * d : d - 0.5f;
+}
+
 __device__ __forceinline__ float smooth_l1_grad(float p, float t) {
     const float d = p - t;
     return (fabsf(d) < 1.0f) ? d : ((d > 0.0f) ? 1.0f : ((d < 0.0f) ? -1.0f : 0.0f));
 }
 
-template <int GAMMA_MODE>
+// WITH_LOSS: the same pass also accumulates the un-normalised loss sums (forward + backward in one read of the logits);
+// `norm_count` then is the matched count obtained BEFORE the pass (ssdk_count_matches, all-reduced on several GPUs).
+template <int GAMMA_MODE, bool WITH_LOSS>
 __global__ void __launch_bounds__(LOSS_THREADS) ssd_loss_backward_kernel(
     const float* __restrict__ logits, const float4* __restrict__ codes, const float4* __restrict__ reg_t,
     const int* __restrict__ cls_t, const int* __restrict__ matches, long long NA, int C, int rpw, float gamma, float alpha,
-    const double* __restrict__ sums, const float* __restrict__ upstream, LossSmemLayout L, float* __restrict__ grad_logits,
-    float4* __restrict__ grad_codes) {
+    const double* __restrict__ norm_count, const float* __restrict__ upstream, LossSmemLayout L, float* __restrict__ grad_logits,
+    float4* __restrict__ grad_codes, double* __restrict__ partials, unsigned* __restrict__ ticket, double* __restrict__ out_sums) {
     extern __shared__ __align__(128) unsigned char smem[];
     unsigned long long* full = (unsigned long long*)smem;                 // [stages]  producer -> consumers
     unsigned long long* empty = full + LOSS_MAX_STAGES;                   // [stages]  consumers -> producer
@@ -107,7 +137,8 @@ __global__ void __launch_bounds__(LOSS_THREADS) ssd_loss_backward_kernel(
     }
 
     // =============================================================================== consumer warps
-    const double norm = fmax(sums[2], 1.0);                              // ssd.py:123 (global count)
+    const double norm = fmax(*norm_count, 1.0);                          // ssd.py:123 (global count)
+    double acc_cls = 0.0, acc_loc = 0.0, acc_cnt = 0.0;                  // WITH_LOSS: un-normalised sums of this thread
     const float u_loc = upstream ? upstream[0] : 1.0f, u_cls = upstream ? upstream[1] : 1.0f;
     const float k_loc = (float)((double)u_loc / norm);
     const float k_neg = (float)((double)u_cls * (1.0 - (double)alpha) / norm);
@@ -139,42 +170,68 @@ __global__ void __launch_bounds__(LOSS_THREADS) ssd_loss_backward_kernel(
                 const float4 p = codes[n0 + lane], t = reg_t[n0 + lane];
                 g = make_float4(k_loc * smooth_l1_grad(p.x, t.x), k_loc * smooth_l1_grad(p.y, t.y),
                                 k_loc * smooth_l1_grad(p.z, t.z), k_loc * smooth_l1_grad(p.w, t.w));
+                if (WITH_LOSS) {
+                    acc_loc += (double)(smooth_l1_value(p.x, t.x) + smooth_l1_value(p.y, t.y) + smooth_l1_value(p.z, t.z) +
+                                        smooth_l1_value(p.w, t.w));
+                    acc_cnt += 1.0;
+                }
             }
             grad_codes[n0 + lane] = g;
         }
-        // ---- positive-class logits are read before the flat pass overwrites them
+        // ---- patches, as in the forward kernel: the positive-class logit of a matched row is read and replaced by -inf,
+        //      an ignored row (weight 0, ssd.py:103) is replaced by -inf entirely; the negative form maps -inf to value 0
+        //      and gradient 0, so the flat pass needs no per-element target
         const bool special = __any_sync(0xffffffffu, m != -1);
         int tc = -1;
         float xpos = 0.0f;
-        if (special && row_lane && m >= -1) {
-            tc = s_c[lane] - 1;
-            if (tc >= 0 && tc < C) xpos = s_x[lane * C + tc];
-            else tc = -1;
-        }
-        __syncwarp();
-        // ---- flat pass, in place: every element as a negative
-        float4* x4 = (float4*)s_x;
-#pragma unroll 2
-        for (int i = lane; i < n4; i += 32) {
-            float4 v = x4[i];
-            v.x = k_neg * focal_negative_grad<GAMMA_MODE>(v.x, gamma);
-            v.y = k_neg * focal_negative_grad<GAMMA_MODE>(v.y, gamma);
-            v.z = k_neg * focal_negative_grad<GAMMA_MODE>(v.z, gamma);
-            v.w = k_neg * focal_negative_grad<GAMMA_MODE>(v.w, gamma);
-            x4[i] = v;
-        }
-        // ---- fix-ups: the positive class of matched rows, ignored rows (weight 0, ssd.py:103)
         if (special) {
-            __syncwarp();
             if (row_lane) {
                 float* x = s_x + lane * C;
                 if (m < -1) {
-                    for (int c = 0; c < C; ++c) x[c] = 0.0f;
-                } else if (tc >= 0) {
-                    x[tc] = k_pos * focal_positive_grad<GAMMA_MODE>(xpos, gamma);
+                    for (int c = 0; c < C; ++c) x[c] = -INFINITY;
+                } else {
+                    tc = s_c[lane] - 1;
+                    if (tc >= 0 && tc < C) { xpos = x[tc]; x[tc] = -INFINITY; }
+                    else tc = -1;
                 }
             }
+            __syncwarp();
         }
+        // ---- flat pass, in place: every element as a negative
+        float4* x4 = (float4*)s_x;
+        float tile_neg = 0.0f, tile_fix = 0.0f;       // WITH_LOSS: sum of negative-form values; corrections for special rows
+        if (WITH_LOSS) {
+#pragma unroll 2
+            for (int i = lane; i < n4; i += 32) {
+                float4 v = x4[i];
+                float f0, f1, f2, f3;
+                v.x = k_neg * focal_negative_both<GAMMA_MODE>(v.x, gamma, f0);
+                v.y = k_neg * focal_negative_both<GAMMA_MODE>(v.y, gamma, f1);
+                v.z = k_neg * focal_negative_both<GAMMA_MODE>(v.z, gamma, f2);
+                v.w = k_neg * focal_negative_both<GAMMA_MODE>(v.w, gamma, f3);
+                tile_neg += (f0 + f1) + (f2 + f3);
+                x4[i] = v;
+            }
+        } else {
+#pragma unroll 2
+            for (int i = lane; i < n4; i += 32) {
+                float4 v = x4[i];
+                v.x = k_neg * focal_negative_grad<GAMMA_MODE>(v.x, gamma);
+                v.y = k_neg * focal_negative_grad<GAMMA_MODE>(v.y, gamma);
+                v.z = k_neg * focal_negative_grad<GAMMA_MODE>(v.z, gamma);
+                v.w = k_neg * focal_negative_grad<GAMMA_MODE>(v.w, gamma);
+                x4[i] = v;
+            }
+        }
+        // ---- the positive class of matched rows
+        if (special) {
+            __syncwarp();
+            if (row_lane && tc >= 0) {
+                s_x[lane * C + tc] = k_pos * focal_positive_grad<GAMMA_MODE>(xpos, gamma);
+                if (WITH_LOSS) tile_fix = alpha * focal_positive_value<GAMMA_MODE>(xpos, gamma);
+            }
+        }
+        if (WITH_LOSS) acc_cls += (double)fmaf(1.0f - alpha, tile_neg, tile_fix);
         // ---- hand the finished run to the TMA engine; release the PREVIOUS stage once its store has read shared memory
         fence_proxy_async();
         __syncwarp();
@@ -205,23 +262,72 @@ __global__ void __launch_bounds__(LOSS_THREADS) ssd_loss_backward_kernel(
         if (++s == L.stages) { s = 0; st = stage0; parity ^= 1u; }
     }
     if (lane == 0) bulk_wait0();                                          // stores must be complete before the CTA exits
+    if (!WITH_LOSS) return;
+
+    // ---- loss sums: warp -> CTA partial -> the last CTA adds the partials in a fixed order (as ssd_loss_kernel)
+    __shared__ double s_red[LOSS_CONSUMER_WARPS][3];
+    __shared__ double s_fin[64][3];
+    __shared__ int s_last;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        acc_cls += __shfl_xor_sync(0xffffffffu, acc_cls, o);
+        acc_loc += __shfl_xor_sync(0xffffffffu, acc_loc, o);
+        acc_cnt += __shfl_xor_sync(0xffffffffu, acc_cnt, o);
+    }
+    if (lane == 0) { s_red[warp][0] = acc_loc; s_red[warp][1] = acc_cls; s_red[warp][2] = acc_cnt; }
+    asm volatile("bar.sync 1, %0;" ::"n"(LOSS_CONSUMER_WARPS * 32) : "memory");
+    if (tid < 3) {
+        double t = 0.0;
+#pragma unroll
+        for (int w = 0; w < LOSS_CONSUMER_WARPS; ++w) t += s_red[w][tid];
+        partials[(size_t)blockIdx.x * 3 + tid] = t;
+        __threadfence();
+    }
+    asm volatile("bar.sync 1, %0;" ::"n"(LOSS_CONSUMER_WARPS * 32) : "memory");
+    if (tid == 0) s_last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+    asm volatile("bar.sync 1, %0;" ::"n"(LOSS_CONSUMER_WARPS * 32) : "memory");
+    if (!s_last) return;
+    __threadfence();
+    if (tid < 64) {
+        double t[3] = {0.0, 0.0, 0.0};
+        for (int i = tid; i < (int)gridDim.x; i += 64)
+            for (int j = 0; j < 3; ++j) t[j] += __ldcg(&partials[(size_t)i * 3 + j]);
+        for (int j = 0; j < 3; ++j) s_fin[tid][j] = t[j];
+    }
+    asm volatile("bar.sync 1, %0;" ::"n"(LOSS_CONSUMER_WARPS * 32) : "memory");
+    for (int o = 32; o > 0; o >>= 1) {
+        if (tid < o)
+            for (int j = 0; j < 3; ++j) s_fin[tid][j] += s_fin[tid + o][j];
+        asm volatile("bar.sync 1, %0;" ::"n"(LOSS_CONSUMER_WARPS * 32) : "memory");
+    }
+    if (tid < 3) out_sums[tid] = s_fin[0][tid];
+    if (tid == 0) *ticket = 0u;
+}
+
+// number of matched anchors (matches >= 0) of this shard, as a double: the loss normaliser's input when it is needed
+// BEFORE the loss pass (fused forward + backward); ssd.py:89,121-122
+__global__ void __launch_bounds__(256) count_matches_kernel(const int* __restrict__ matches, long long n, double* __restrict__ out) {
+    __shared__ int s_cnt[8];
+    int c = 0;
+    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += (long long)gridDim.x * 256) c += matches[i] >= 0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    if ((threadIdx.x & 31) == 0) s_cnt[threadIdx.x >> 5] = c;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int t = 0;
+        for (int w = 0; w < 8; ++w) t += s_cnt[w];
+        if (t) atomicAdd(out, (double)t);          // integers: exact and order independent
+    }
 }
 
 static bool aligned16(const void* p) { return ((uintptr_t)p & 15) == 0; }
 
-extern "C" int ssdk_ssd_loss_backward(ssdk_ctx* ctx, const float* logits, const float* codes, const float* reg_targets,
-                                      const int32_t* cls_targets, const int32_t* matches, int64_t B, int64_t A, int C,
-                                      double gamma, double alpha, const double* sums, const float* upstream,
-                                      float* grad_logits, float* grad_codes) {
-    SSDK_TRY(ssdk_ctx_enter(ctx));
-    SSDK_REQUIRE(B >= 0 && A >= 0 && C > 0, SSDK_ERR_ARG, "ssdk_ssd_loss_backward: bad sizes");
+static int launch_backward(ssdk_ctx* ctx, bool with_loss, const float* logits, const float* codes, const float* reg_targets,
+                           const int32_t* cls_targets, const int32_t* matches, int64_t B, int64_t A, int C, double gamma,
+                           double alpha, const double* norm_count, const float* upstream, float* grad_logits, float* grad_codes,
+                           double* out_sums) {
     const long long NA = (long long)B * A;
-    if (NA == 0) return SSDK_OK;
-    SSDK_REQUIRE(logits && codes && reg_targets && cls_targets && matches && sums && grad_logits && grad_codes, SSDK_ERR_ARG,
-                 "ssdk_ssd_loss_backward: null pointer");
-    SSDK_REQUIRE(aligned16(logits) && aligned16(codes) && aligned16(reg_targets) && aligned16(cls_targets) && aligned16(matches) &&
-                     aligned16(grad_logits) && aligned16(grad_codes),
-                 SSDK_ERR_SHAPE, "ssdk_ssd_loss_backward: tensors must be 16-byte aligned");
     // same tile geometry as the forward kernel; three stages because a stage is released one tile late
     int rpw = (int)(24576 / (32 * (long long)C)) / 4 * 4;
     if (rpw < 4) rpw = 4;
@@ -232,28 +338,93 @@ extern "C" int ssdk_ssd_loss_backward(ssdk_ctx* ctx, const float* logits, const 
     L.meta_bytes = (unsigned)rows * 4;
     L.stage_bytes = L.tile_bytes + 2 * L.meta_bytes;
     L.stages = 3;
-    SSDK_REQUIRE(128 + 3 * (size_t)L.stage_bytes <= 220 * 1024, SSDK_ERR_SHAPE,
+    SSDK_REQUIRE(128 + 3 * (size_t)L.stage_bytes <= 216 * 1024, SSDK_ERR_SHAPE,
                  "ssdk_ssd_loss_backward: num_classes %d too large for the fused kernel (limit about 570)", C);
     if (L.stage_bytes < 12 * 1024) L.stages = 4;
     const size_t smem = 128 + (size_t)L.stages * L.stage_bytes;
     const long long ntiles = (NA + rows - 1) / rows;
-    int per_sm = (int)((227 * 1024) / (smem + 1024 + 256));
+    int per_sm = (int)((227 * 1024) / (smem + 1024 + 2048));
     if (per_sm < 1) per_sm = 1;
     if (per_sm > 4) per_sm = 4;
     long long grid = (long long)ctx->num_sms * per_sm;
     if (grid > ntiles) grid = ntiles;
-    if (gamma == 2.0) {
-        SSDK_TRY(ssdk_set_max_smem(ctx, (const void*)ssd_loss_backward_kernel<0>, (int)smem));
-        SSDK_KERNEL(ctx, SSDK_K_LOSS_BACKWARD,
-                    ssd_loss_backward_kernel<0><<<(int)grid, LOSS_THREADS, smem, ctx->stream>>>(
-                        logits, (const float4*)codes, (const float4*)reg_targets, cls_targets, matches, NA, C, rpw, (float)gamma,
-                        (float)alpha, sums, upstream, L, grad_logits, (float4*)grad_codes));
-    } else {
-        SSDK_TRY(ssdk_set_max_smem(ctx, (const void*)ssd_loss_backward_kernel<1>, (int)smem));
-        SSDK_KERNEL(ctx, SSDK_K_LOSS_BACKWARD,
-                    ssd_loss_backward_kernel<1><<<(int)grid, LOSS_THREADS, smem, ctx->stream>>>(
-                        logits, (const float4*)codes, (const float4*)reg_targets, cls_targets, matches, NA, C, rpw, (float)gamma,
-                        (float)alpha, sums, upstream, L, grad_logits, (float4*)grad_codes));
+    double* partials = nullptr;
+    unsigned* ticket = nullptr;
+    if (with_loss) {
+        const size_t part_bytes = 16 + (size_t)ctx->num_sms * 8 * 3 * sizeof(double);
+        if (ctx->ws_partials.cap < part_bytes) {
+            SSDK_TRY(ssdk_ensure(ctx, &ctx->ws_partials, part_bytes));
+            SSDK_CHECK_CUDA(cudaMemsetAsync(ctx->ws_partials.p, 0, 16, ctx->stream));
+        }
+        ticket = (unsigned*)ctx->ws_partials.p;
+        partials = (double*)((char*)ctx->ws_partials.p + 16);
     }
+#define SSDK_LAUNCH_BW(GM, WL)                                                                                              \
+    do {                                                                                                                    \
+        SSDK_TRY(ssdk_set_max_smem(ctx, (const void*)ssd_loss_backward_kernel<GM, WL>, (int)smem));                         \
+        SSDK_KERNEL(ctx, SSDK_K_LOSS_BACKWARD,                                                                              \
+                    ssd_loss_backward_kernel<GM, WL><<<(int)grid, LOSS_THREADS, smem, ctx->stream>>>(                       \
+                        logits, (const float4*)codes, (const float4*)reg_targets, cls_targets, matches, NA, C, rpw, (float)gamma, \
+                        (float)alpha, norm_count, upstream, L, grad_logits, (float4*)grad_codes, partials, ticket, out_sums)); \
+    } while (0)
+    const bool g2 = (gamma == 2.0);
+    if (g2 && !with_loss) SSDK_LAUNCH_BW(0, false);
+    else if (g2) SSDK_LAUNCH_BW(0, true);
+    else if (!with_loss) SSDK_LAUNCH_BW(1, false);
+    else SSDK_LAUNCH_BW(1, true);
+#undef SSDK_LAUNCH_BW
     return SSDK_OK;
 }
+
+static int check_backward_args(const char* who, const float* logits, const float* codes, const float* reg_targets,
+                               const int32_t* cls_targets, const int32_t* matches, const void* norm, const float* grad_logits,
+                               const float* grad_codes) {
+    SSDK_REQUIRE(logits && codes && reg_targets && cls_targets && matches && norm && grad_logits && grad_codes, SSDK_ERR_ARG,
+                 "%s: null pointer", who);
+    SSDK_REQUIRE(aligned16(logits) && aligned16(codes) && aligned16(reg_targets) && aligned16(cls_targets) && aligned16(matches) &&
+                     aligned16(grad_logits) && aligned16(grad_codes),
+                 SSDK_ERR_SHAPE, "%s: tensors must be 16-byte aligned", who);
+    return SSDK_OK;
+}
+
+extern "C" {
+
+int ssdk_ssd_loss_backward(ssdk_ctx* ctx, const float* logits, const float* codes, const float* reg_targets,
+                           const int32_t* cls_targets, const int32_t* matches, int64_t B, int64_t A, int C, double gamma,
+                           double alpha, const double* sums, const float* upstream, float* grad_logits, float* grad_codes) {
+    SSDK_TRY(ssdk_ctx_enter(ctx));
+    SSDK_REQUIRE(B >= 0 && A >= 0 && C > 0, SSDK_ERR_ARG, "ssdk_ssd_loss_backward: bad sizes");
+    if ((long long)B * A == 0) return SSDK_OK;
+    SSDK_TRY(check_backward_args("ssdk_ssd_loss_backward", logits, codes, reg_targets, cls_targets, matches, sums, grad_logits, grad_codes));
+    return launch_backward(ctx, false, logits, codes, reg_targets, cls_targets, matches, B, A, C, gamma, alpha, sums + 2, upstream,
+                           grad_logits, grad_codes, nullptr);
+}
+
+int ssdk_ssd_loss_forward_backward(ssdk_ctx* ctx, const float* logits, const float* codes, const float* reg_targets,
+                                   const int32_t* cls_targets, const int32_t* matches, int64_t B, int64_t A, int C,
+                                   double gamma, double alpha, const double* num_matches, const float* upstream,
+                                   double* out_sums, float* grad_logits, float* grad_codes) {
+    SSDK_TRY(ssdk_ctx_enter(ctx));
+    SSDK_REQUIRE(B >= 0 && A >= 0 && C > 0 && out_sums, SSDK_ERR_ARG, "ssdk_ssd_loss_forward_backward: bad arguments");
+    if ((long long)B * A == 0) {
+        SSDK_CHECK_CUDA(cudaMemsetAsync(out_sums, 0, 3 * sizeof(double), ctx->stream));
+        return SSDK_OK;
+    }
+    SSDK_TRY(check_backward_args("ssdk_ssd_loss_forward_backward", logits, codes, reg_targets, cls_targets, matches, num_matches,
+                                 grad_logits, grad_codes));
+    return launch_backward(ctx, true, logits, codes, reg_targets, cls_targets, matches, B, A, C, gamma, alpha, num_matches, upstream,
+                           grad_logits, grad_codes, out_sums);
+}
+
+int ssdk_count_matches(ssdk_ctx* ctx, const int32_t* matches, int64_t n, double* out_count) {
+    SSDK_TRY(ssdk_ctx_enter(ctx));
+    SSDK_REQUIRE(n >= 0 && out_count && (n == 0 || matches), SSDK_ERR_ARG, "ssdk_count_matches: bad arguments");
+    SSDK_CHECK_CUDA(cudaMemsetAsync(out_count, 0, sizeof(double), ctx->stream));
+    if (n == 0) return SSDK_OK;
+    long long blocks = (n + 256 * 8 - 1) / (256 * 8);
+    if (blocks > ctx->num_sms * 8) blocks = ctx->num_sms * 8;
+    SSDK_KERNEL(ctx, SSDK_K_OTHER, count_matches_kernel<<<(int)blocks, 256, 0, ctx->stream>>>(matches, n, out_count));
+    return SSDK_OK;
+}
+
+}  // extern "C"

@@ -489,10 +489,23 @@ __global__ void __launch_bounds__(256) pack_kernel(const float4* __restrict__ se
                                                    const int* __restrict__ seg_anchor, const int* __restrict__ seg_kept,
                                                    int C, int K, float4* __restrict__ out_boxes, float* __restrict__ out_scores,
                                                    int* __restrict__ out_classes, int* __restrict__ out_num,
-                                                   int* __restrict__ out_anchor) {
-    extern __shared__ int s_off[];   // [C+1] exclusive prefix sums of the per-class kept counts
+                                                   int* __restrict__ out_anchor, const float4* __restrict__ box_scaler,
+                                                   float final_thr) {
+    extern __shared__ int s_off[];   // [C+1] exclusive prefix sums of the per-class kept counts, then [C] the counts
+    int* kept = s_off + C + 1;
     const int b = blockIdx.y;
-    const int* kept = seg_kept + (size_t)b * C;
+    // Post-path consumers folded in (model.py:67-68, inference/detector.py:54-58): boxes /= box_scaler[b], and a final
+    // `scores > final_thr` filter.  Inside a class the kept scores are descending, so the survivors of that filter are a
+    // prefix of every class segment and the class-major order is preserved, exactly as the reference's boolean mask does.
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        int k = seg_kept[(size_t)b * C + c];
+        if (final_thr > -INFINITY) {
+            const float* sc = seg_score + ((size_t)b * C + c) * K;
+            while (k > 0 && !(sc[k - 1] > final_thr)) --k;
+        }
+        kept[c] = k;
+    }
+    __syncthreads();
     if (threadIdx.x < 32) {
         const int lane = threadIdx.x;
         const int per = (C + 31) / 32;
@@ -526,7 +539,12 @@ __global__ void __launch_bounds__(256) pack_kernel(const float4* __restrict__ se
         if (j < kept[c]) {                                            // selected entries, class-major (nms.py:42-44)
             const size_t src = ((size_t)b * C + c) * K + j;
             const int dst = s_off[c] + j;
-            ob[dst] = seg_box[src];
+            float4 bx = seg_box[src];
+            if (box_scaler) {
+                const float4 sc4 = box_scaler[b];
+                bx = make_float4(f_div(bx.x, sc4.x), f_div(bx.y, sc4.y), f_div(bx.z, sc4.z), f_div(bx.w, sc4.w));
+            }
+            ob[dst] = bx;
             os[dst] = seg_score[src];
             oc[dst] = c;
             if (oa) oa[dst] = seg_anchor[src];
@@ -549,10 +567,11 @@ static int bits_for(long long n) {   // bits needed to represent values in [0, n
 
 static bool aligned16(const void* p) { return ((uintptr_t)p & 15) == 0; }
 
-extern "C" int ssdk_postprocess(ssdk_ctx* ctx, const float* codes, const float* anchors, const float* scores, int flags,
-                                int B, int64_t A, int C, double score_threshold, double iou_threshold, int K,
-                                float* out_boxes, float* out_scores, int32_t* out_classes, int32_t* out_num,
-                                int32_t* out_anchor_idx) {
+static int postprocess_impl(ssdk_ctx* ctx, const float* codes, const float* anchors, const float* scores, int flags,
+                            int B, int64_t A, int C, double score_threshold, double iou_threshold, int K,
+                            const float* box_scaler, double final_score_threshold,
+                            float* out_boxes, float* out_scores, int32_t* out_classes, int32_t* out_num,
+                            int32_t* out_anchor_idx) {
     SSDK_TRY(ssdk_ctx_enter(ctx));
     SSDK_REQUIRE(B >= 0 && A >= 0 && C > 0 && K > 0, SSDK_ERR_ARG, "ssdk_postprocess: bad sizes (B=%d A=%lld C=%d K=%d)", B,
                  (long long)A, C, K);
@@ -677,8 +696,25 @@ extern "C" int ssdk_postprocess(ssdk_ctx* ctx, const float* codes, const float* 
     }
     // 4. pack
     SSDK_KERNEL(ctx, SSDK_K_PACK,
-                pack_kernel<<<dim3(ceil_div_i((long long)C * K, PACK_SLOTS_PER_BLOCK), B), 256, (size_t)(C + 1) * sizeof(int), ctx->stream>>>(seg_box, seg_score, seg_anchor, seg_kept, C, K,
-                                                                                   (float4*)out_boxes, out_scores, out_classes,
-                                                                                   out_num, out_anchor_idx));
+                pack_kernel<<<dim3(ceil_div_i((long long)C * K, PACK_SLOTS_PER_BLOCK), B), 256, (size_t)(2 * C + 1) * sizeof(int), ctx->stream>>>(
+                    seg_box, seg_score, seg_anchor, seg_kept, C, K, (float4*)out_boxes, out_scores, out_classes, out_num,
+                    out_anchor_idx, (const float4*)box_scaler, (float)final_score_threshold));
     return SSDK_OK;
+}
+
+extern "C" int ssdk_postprocess(ssdk_ctx* ctx, const float* codes, const float* anchors, const float* scores, int flags,
+                                int B, int64_t A, int C, double score_threshold, double iou_threshold, int K,
+                                float* out_boxes, float* out_scores, int32_t* out_classes, int32_t* out_num,
+                                int32_t* out_anchor_idx) {
+    return postprocess_impl(ctx, codes, anchors, scores, flags, B, A, C, score_threshold, iou_threshold, K, nullptr,
+                            -INFINITY, out_boxes, out_scores, out_classes, out_num, out_anchor_idx);
+}
+
+extern "C" int ssdk_detect(ssdk_ctx* ctx, const float* codes, const float* anchors, const float* scores, int flags, int B,
+                           int64_t A, int C, double score_threshold, double iou_threshold, int K, const float* box_scaler,
+                           double final_score_threshold, float* out_boxes, float* out_scores, int32_t* out_classes,
+                           int32_t* out_num) {
+    SSDK_REQUIRE(box_scaler == nullptr || aligned16(box_scaler), SSDK_ERR_SHAPE, "ssdk_detect: box_scaler must be 16-byte aligned");
+    return postprocess_impl(ctx, codes, anchors, scores, flags, B, A, C, score_threshold, iou_threshold, K, box_scaler,
+                            final_score_threshold, out_boxes, out_scores, out_classes, out_num, nullptr);
 }

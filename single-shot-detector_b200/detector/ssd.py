@@ -106,16 +106,29 @@ class SSD:
         return sums, losses
 
     # ------------------------------------------------------------------ inference (ssd.py:42-69)
-    def get_predictions(self, score_threshold=0.05, iou_threshold=0.5, max_boxes_per_class=20, out=None):
+    def get_predictions(self, score_threshold=0.05, iou_threshold=0.5, max_boxes_per_class=20, out=None,
+                        box_scaler=None, final_score_threshold=None):
         """Returns {'boxes' [B,N,4], 'labels' [B,N] int, 'scores' [B,N], 'num_boxes' [B]}, N = C * max_boxes_per_class.
-        The sigmoid of ssd.py:60 is fused into the score-threshold pass."""
+        The sigmoid of ssd.py:60 is fused into the score-threshold pass.  Optional extensions fold in the two consumers
+        that follow in the reference: `box_scaler` [B,4] (boxes /= box_scaler, model.py:67-68) and
+        `final_score_threshold` (keep score > it, order preserved, inference/detector.py:54-58)."""
         if self._host_mode():
+            assert box_scaler is None and final_score_threshold is None, 'extensions need device tensors' 
             return self._get_predictions_host(score_threshold, iou_threshold, max_boxes_per_class, out)
         boxes, scores, classes, num = batch_multiclass_non_max_suppression(
             self.raw_predictions['encoded_boxes'], self.anchors, self.raw_predictions['class_predictions'],
             score_threshold=score_threshold, iou_threshold=iou_threshold,
-            max_boxes_per_class=max_boxes_per_class, scores_are_logits=True)
+            max_boxes_per_class=max_boxes_per_class, scores_are_logits=True,
+            box_scaler=box_scaler, final_score_threshold=final_score_threshold)
         return {'boxes': boxes, 'labels': classes, 'scores': scores, 'num_boxes': num}
+
+    def detect(self, score_threshold=0.1, box_scaler=None, nms_score_threshold=0.05, iou_threshold=0.5, max_boxes_per_class=20):
+        """What inference/detector.py:36-60 returns for a batch of one image: (boxes [N,4], labels [N], scores [N]) with
+        scores > score_threshold, in the exported graph's order (class-major, score-descending)."""
+        p = self.get_predictions(nms_score_threshold, iou_threshold, max_boxes_per_class, box_scaler=box_scaler,
+                                 final_score_threshold=score_threshold)
+        n = int(p['num_boxes'][0])
+        return p['boxes'][0, :n], p['labels'][0, :n], p['scores'][0, :n]
 
     # ------------------------------------------------------------------ training (ssd.py:71-133)
     def loss_sums(self, groundtruth, params, per_anchor=False, keep_targets=False):
@@ -209,11 +222,53 @@ class SSD:
         self._call_bw = (call, up)
         return {'class_predictions': g_logits, 'encoded_boxes': g_codes}
 
-    def loss_with_gradients(self, groundtruth, params, upstream=None):
-        """One training step of the hot path without autograd: (losses, gradients) = forward (targets + losses, sums
-        all-reduced when `process_group` is set) followed by loss_backward(upstream)."""
-        losses = self._loss_forward(groundtruth, params, keep_targets=True)
-        return losses, self.loss_backward(upstream)
+    def loss_with_gradients(self, groundtruth, params, upstream=None, fused=True):
+        """One training step of the hot path without autograd: (losses, gradients).
+        fused=True (default): targets -> matched count (all-reduced when `process_group` is set) -> ONE pass over the
+        logits that produces the loss sums and both gradients (ssdk_ssd_loss_forward_backward) -> sums all-reduced for the
+        reported losses.  fused=False: forward pass, then loss_backward (two reads of the logits)."""
+        if not fused:
+            losses = self._loss_forward(groundtruth, params, keep_targets=True)
+            return losses, self.loss_backward(upstream)
+        from . import ssd as this_module
+        lib = _lib.load()
+        call = Call()
+        logits = call.tensor(self.raw_predictions['class_predictions'], torch.float32)
+        B, A, C = logits.shape
+        codes = call.tensor(self.raw_predictions['encoded_boxes'], torch.float32, (B, A, 4))
+        anchors = call.tensor(self.anchors, torch.float32, (A, 4))
+        gt = call.tensor(groundtruth['boxes'], torch.float32)
+        G = gt.shape[1]
+        labels = call.tensor(groundtruth['labels'], torch.int32, (B, G))
+        num = call.tensor(groundtruth['num_boxes'], torch.int32, (B,))
+        reg, cls_t, matches = call.empty([B, A, 4], torch.float32), call.empty([B, A], torch.int32), call.empty([B, A], torch.int32)
+        count, sums, out = call.empty([1], torch.float64), call.empty([3], torch.float64), call.empty([2], torch.float32)
+        g_logits, g_codes = call.empty([B, A, C], torch.float32), call.empty([B, A, 4], torch.float32)
+        up = None
+        if upstream is not None:
+            up = call.tensor(upstream, torch.float32, (2,)) if isinstance(upstream, torch.Tensor) else \
+                torch.tensor([float(upstream[0]), float(upstream[1])], dtype=torch.float32, device=logits.device)
+        ctx = call.ctx()
+        _lib.check(lib.ssdk_training_targets(ctx, ptr(anchors), A, ptr(gt), ptr(labels), ptr(num), B, G,
+                                             float(this_module.POSITIVES_THRESHOLD), float(this_module.NEGATIVES_THRESHOLD),
+                                             ptr(reg), ptr(cls_t), ptr(matches)))                      # ssd.py:84
+        _lib.check(lib.ssdk_count_matches(ctx, ptr(matches), B * A, ptr(count)))                       # ssd.py:121-122
+        group = None if self.process_group in (None, True) else self.process_group
+        if self.process_group is not None:
+            import torch.distributed as dist
+            dist.all_reduce(count, op=dist.ReduceOp.SUM, group=group)
+        _lib.check(lib.ssdk_ssd_loss_forward_backward(ctx, ptr(logits), ptr(codes), ptr(reg), ptr(cls_t), ptr(matches), B, A, C,
+                                                      float(params['gamma']), float(params['alpha']), ptr(count), ptr(up),
+                                                      ptr(sums), ptr(g_logits), ptr(g_codes)))
+        if self.process_group is not None:
+            dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=group)
+        _lib.check(lib.ssdk_loss_finalize(ctx, ptr(sums), ptr(out)))
+        self.num_matches = sums[2]
+        self._call = call
+        self._saved = dict(logits=logits, codes=codes, sums=sums, gamma=float(params['gamma']), alpha=float(params['alpha']),
+                           reg_targets=reg, cls_targets=cls_t, matches=matches)
+        return ({'localization_loss': out[0], 'classification_loss': out[1]},
+                {'class_predictions': g_logits, 'encoded_boxes': g_codes})
 
     def _create_targets(self, groundtruth):
         """reference ssd.py:165-199: reg_targets [B,A,4], cls_targets [B,A], matches [B,A]."""

@@ -143,3 +143,23 @@ def test_backward_properties_full_size(pkg, syn):
     want = og.ssd_loss_grad(a_np, codes[:1].cpu().numpy(), logits[:1].cpu().numpy(), one, params, C)
     grad_close(g['class_predictions'].cpu().numpy(), want['class_predictions'], 'grad logits (cfg2)')
     grad_close(g['encoded_boxes'].cpu().numpy(), want['encoded_boxes'], 'grad codes (cfg2)', atol=CODES_ATOL / float(want['num_matches']))
+
+
+def test_fused_forward_backward_equals_two_pass(pkg, syn):
+    """ssdk_ssd_loss_forward_backward (one read of the logits) == forward kernel + backward kernel."""
+    for (H, W, C, B, G, kind, gamma) in [(256, 320, 12, 3, 7, 'realistic', 2.0), (200, 333, 7, 2, 5, 'dense', 2.0),
+                                          (128, 160, 91, 2, 5, 'dense', 1.5)]:
+        anchors, gt, logits, codes, gen = make_case(pkg, syn, H, W, C, B, G, seed=41, kind=kind)
+        params = {'gamma': gamma, 'alpha': 0.3}
+        d_gt = {k: cuda(v) for k, v in gt.items()}
+        ssd = pkg.SSD.from_predictions(H, W, {'encoded_boxes': cuda(codes), 'class_predictions': cuda(logits)}, gen, C)
+        l2, g2 = ssd.loss_with_gradients(d_gt, params, upstream=(0.5, 2.0), fused=False)
+        n2 = float(ssd.num_matches)
+        l1, g1 = ssd.loss_with_gradients(d_gt, params, upstream=(0.5, 2.0), fused=True)
+        assert float(ssd.num_matches) == n2
+        # identical per-element arithmetic for the gradients; the loss sums use the general (2-MUFU) negative form here and
+        # the polynomial fast path in the forward kernel: 1e-5 relative, like every loss comparison
+        assert torch.equal(g1['encoded_boxes'], g2['encoded_boxes'])
+        torch.testing.assert_close(g1['class_predictions'], g2['class_predictions'], rtol=1e-6, atol=1e-30)
+        for k in ('localization_loss', 'classification_loss'):
+            assert abs(l1[k].item() - l2[k].item()) <= RTOL * abs(l2[k].item()), (k, l1[k].item(), l2[k].item())

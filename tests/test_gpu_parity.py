@@ -397,3 +397,35 @@ def test_postprocess_edge_cases(pkg, golden):
     sc[0, 6, 1] = float(np.nextafter(np.float32(0.05), np.float32(1)))
     b, s, c, n, a = pkg.batch_multiclass_non_max_suppression(codes[:1], anchors, sc, 0.05, 0.5, 3, return_anchor_indices=True)
     assert n.item() == 1 and a[0, 0].item() == 6 and c[0, 0].item() == 1
+
+
+def test_detect_box_scaler_and_final_threshold(pkg, golden):
+    """ssdk_detect == get_predictions followed by the reference's consumers: boxes /= box_scaler (model.py:67-68) and the
+    host-side `scores > score_threshold` mask of inference/detector.py:54-58 (order preserved)."""
+    from oracle import losses as olosses, nms as onms
+    g = golden('postprocess')
+    codes, anchors, logits = g['codes'], g['anchors'], g['logits']
+    B = codes.shape[0]
+    scaler = np.stack([np.array([1.0, 0.8 + 0.1 * b, 1.0, 0.8 + 0.1 * b], np.float32) for b in range(B)])
+    gen = pkg.AnchorGenerator()
+    H, W = [int(v) for v in g['HW']]
+    ssd = pkg.SSD.from_predictions(H, W, {'encoded_boxes': cuda(codes), 'class_predictions': cuda(logits)}, gen, logits.shape[2])
+    assert np.array_equal(ssd.anchors.cpu().numpy(), anchors)
+    wb, ws, wc, wn = onms.batch_multiclass_non_max_suppression(codes, anchors, olosses.sigmoid(logits), 0.05, 0.5, 10)
+    thr2 = 0.9                                                              # inside every image's kept-score range
+    got = ssd.get_predictions(0.05, 0.5, 10, box_scaler=cuda(scaler), final_score_threshold=thr2)
+    for b in range(B):
+        n = int(wn[b])
+        keep = ws[b, :n] > np.float32(thr2)                                   # detector.py:55
+        n2 = int(keep.sum())
+        assert 0 < n2 and (b == 0 or n2 < n), 'fixture must lose some detections to the final threshold'
+        assert int(got['num_boxes'][b]) == n2
+        assert np.array_equal(got['labels'][b, :n2].cpu().numpy(), wc[b, :n][keep])
+        close(got['scores'][b, :n2].cpu().numpy(), ws[b, :n][keep])
+        close(got['boxes'][b, :n2].cpu().numpy(), (wb[b, :n] / scaler[b][None, :])[keep], atol=1e-7)       # model.py:68
+        assert not got['scores'][b, n2:].any() and not got['boxes'][b, n2:].any() and not got['labels'][b, n2:].any()
+    boxes, labels, scores = pkg.SSD.from_predictions(
+        H, W, {'encoded_boxes': cuda(codes[:1]), 'class_predictions': cuda(logits[:1])}, gen, logits.shape[2]).detect(
+        score_threshold=thr2, box_scaler=cuda(scaler[:1]), nms_score_threshold=0.05, iou_threshold=0.5, max_boxes_per_class=10)
+    n2 = int((ws[0, :int(wn[0])] > np.float32(thr2)).sum())
+    assert boxes.shape == (n2, 4) and labels.shape == (n2,) and scores.shape == (n2,) and bool((scores > thr2).all())
