@@ -401,6 +401,85 @@ def run_ours(args):
     dominant = dict(dominant)
     dominant['share_of_step_kernel_time'] = dominant['avg_launch_ms'] / max(1e-9, sum(step_kernel_ms.values()))
 
+    # ---- head-layout path: the same two sub-paths fed with the per-level tower outputs
+    #      [B, n*C, h, w] / [B, n*4, h, w] (channels_first, as the reference's box predictor emits them) instead of the
+    #      concatenated [B,A,C] / [B,A,4]; plus the cost of reshape_and_concatenate itself, which this path removes
+    head = None
+    try:
+        n_loc = gen.num_anchors_per_location
+        shapes = [(-(-H // s_), -(-W // s_)) for s_ in gen.strides]
+
+        def to_levels(t, D):
+            out_l, off = [], 0
+            for h_, w_ in shapes:
+                cnt = h_ * w_ * n_loc
+                out_l.append(t[:, off:off + cnt].reshape(t.shape[0], h_, w_, n_loc * D).permute(0, 3, 1, 2).contiguous())
+                off += cnt
+            return out_l
+        lv_tlog, lv_tcod, lv_ilog, lv_icod = to_levels(d_tlog, C), to_levels(d_tcod, 4), to_levels(d_ilog, C), to_levels(d_icod, 4)
+        ssd_th = pkg.SSD.from_head_outputs(H, W, lv_tcod, lv_tlog, gen, C)
+        ssd_ih = pkg.SSD.from_head_outputs(H, W, lv_icod, lv_ilog, gen, C)
+        if world > 1:
+            ssd_th.process_group = True
+        up_dev = torch.tensor(UPSTREAM, dtype=torch.float32, device=dev)
+        hl = ssd_th.loss(d_gt, PARAMS)
+        hp = ssd_ih.get_predictions(SCORE_THR, IOU_THR, K_PER_CLASS)
+        head_check = {'localization_loss': float(hl['localization_loss']), 'classification_loss': float(hl['classification_loss']),
+                      'detections_image0': int(hp['num_boxes'][0]),
+                      'detections_identical_to_anchor_major': bool(all(torch.equal(hp[k], pred[k]) for k in ('boxes', 'labels', 'scores', 'num_boxes')))}
+        ms_h_train = timed(lambda: ssd_th.loss(d_gt, PARAMS), args.steps)
+        ms_h_fb = timed(lambda: ssd_th.loss_with_gradients(d_gt, PARAMS, upstream=up_dev), args.steps)
+        ms_h_infer = timed(lambda: ssd_ih.get_predictions(SCORE_THR, IOU_THR, K_PER_CLASS), args.steps)
+        ms_concat_t = timed(lambda: pkg.reshape_and_concatenate(lv_tcod, lv_tlog, C, n_loc, lazy=False), args.steps)
+        ms_concat_i = timed(lambda: pkg.reshape_and_concatenate(lv_icod, lv_ilog, C, n_loc, lazy=False), args.steps)
+        nprof = min(args.steps, 10)
+        lib.set_profiling(True, local_rank)
+        lib.profile_read(local_rank)
+        for _ in range(nprof):
+            ssd_th.loss(d_gt, PARAMS)
+        prof_f = lib.profile_read(local_rank)
+        for _ in range(nprof):
+            ssd_th.loss_with_gradients(d_gt, PARAMS, upstream=up_dev)
+        prof_fb = lib.profile_read(local_rank)
+        for _ in range(nprof):
+            ssd_ih.get_predictions(SCORE_THR, IOU_THR, K_PER_CLASS)
+        prof_i = lib.profile_read(local_rank)
+        lib.set_profiling(False, local_rank)
+
+        def roof_of(p, name, nbytes):
+            tot, cnt = p[name]
+            if cnt == 0:
+                return None
+            avg = tot / cnt
+            ach = nbytes / (avg * 1e-3) / 1e9
+            return {'kernel': name, 'bound': 'hbm', 'achieved': ach, 'peak': peak, 'unit': 'GB/s', 'frac': ach / peak,
+                    'avg_launch_ms': avg, 'algorithmic_bytes_per_launch': nbytes, 'peak_source': peak_src,
+                    'traffic': (ncu_traffic.get(name + '_kernel') or {}).get('dram_bytes_per_launch')}
+        bh_train = 4 * A * C + 4 * A + 40 * A + 20 * G          # logits + matches read by the loss; targets written/read by the matcher side
+        head = {
+            'what': 'same sub-paths on per-level channels_first tower outputs (no reshape_and_concatenate); results checked against the anchor-major path',
+            'check': head_check,
+            'train_ms_per_step': ms_h_train, 'train_images_per_sec': Bt * world / (ms_h_train * 1e-3),
+            'train_fwd_bwd_ms_per_step': ms_h_fb, 'train_fwd_bwd_images_per_sec': Bt * world / (ms_h_fb * 1e-3),
+            'infer_ms_per_step': ms_h_infer, 'infer_images_per_sec': Bi * world / (ms_h_infer * 1e-3),
+            'reshape_and_concatenate_ms': {'train_batch': ms_concat_t, 'infer_batch': ms_concat_i,
+                                           'note': 'cost of the copy the reference makes before the anchor-major path (8AC+32A bytes per image)'},
+            'unfused_train_ms_per_step': ms_concat_t + ms_train, 'unfused_train_fwd_bwd_ms_per_step': ms_concat_t + ms_train_fb,
+            'unfused_infer_ms_per_step': ms_concat_i + ms_infer,
+            'roofline_head_flat_forward': roof_of(prof_f, 'head_flat', 4 * A * C * Bt),
+            'roofline_head_flat_forward_backward': roof_of(prof_fb, 'head_flat', 8 * A * C * Bt),
+            'roofline_head_filter': roof_of(prof_i, 'filter', 4 * A * C * Bi),
+            'kernel_ms': {'forward': {k: v[0] / nprof for k, v in prof_f.items() if v[1]},
+                          'forward_backward': {k: v[0] / nprof for k, v in prof_fb.items() if v[1]},
+                          'infer': {k: v[0] / nprof for k, v in prof_i.items() if v[1]}},
+            'train_frac_of_hbm_roofline': (bh_train * Bt / (ms_h_train * 1e-3) / 1e9) / peak,
+            'infer_frac_of_hbm_roofline': (b_infer * Bi / (ms_h_infer * 1e-3) / 1e9) / peak,
+        }
+        del lv_tlog, lv_tcod, lv_ilog, lv_icod, ssd_th, ssd_ih
+    except Exception as e:                                            # the headline numbers do not depend on this section
+        head = {'error': str(e)[:300]}
+        torch.cuda.synchronize()
+
     # ---- timed region 2 (e2e): the same step through the public API with HOST buffers; every step copies its inputs
     #      from pinned host memory to the device and reads the results back (ssdk_*_host entry points)
     h_raw_t = {'encoded_boxes': h_tcod.numpy(), 'class_predictions': h_tlog.numpy()}
@@ -468,6 +547,7 @@ def run_ours(args):
             'roofline_ssd_loss': roof_loss, 'roofline_filter': roof_filter, 'roofline_ssd_loss_backward': roof_backward,
             'train_fwd_bwd_images_per_sec': Bt * world / (ms_train_fb * 1e-3), 'train_fwd_bwd_ms_per_step': ms_train_fb,
             'train_fwd_bwd_frac_of_hbm_roofline': ((b_train + 8 * A * C // 2 + 16 * A) * Bt / (ms_train_fb * 1e-3) / 1e9) / peak,
+            'head_layout': head,
         },
         'check': check,
     }

@@ -61,8 +61,9 @@ SSDK_API int64_t ssdk_ctx_launch_count(const ssdk_ctx* ctx);
 /* Optional per-kernel timing with CUDA events on the context's stream (for bench.py's roofline line; adds two
  * event records per kernel while enabled).  ssdk_ctx_profile_read synchronises the stream and returns, per kernel
  * id, the accumulated milliseconds and launch counts since the last reset.  Ids: 0 anchors, 1 match,
- * 2 force_match, 3 ssd_loss, 4 loss_reduce, 5 filter, 6 sort, 7 nms, 8 pack, 9 other, 10 ssd_loss_backward. */
-#define SSDK_NUM_KERNEL_IDS 11
+ * 2 force_match, 3 ssd_loss, 4 loss_reduce, 5 filter, 6 sort, 7 nms, 8 pack, 9 other, 10 ssd_loss_backward,
+ * 11 head_flat (flat focal pass over the per-level head tensors), 12 head_rows (matched / ignored anchors), 13 head_concat. */
+#define SSDK_NUM_KERNEL_IDS 14
 SSDK_API int ssdk_ctx_set_profiling(ssdk_ctx* ctx, int enable);
 SSDK_API int ssdk_ctx_profile_read(ssdk_ctx* ctx, double* out_ms, int64_t* out_calls, int n, int reset);
 /* cudaStreamSynchronize on the context's stream (synchronous). */
@@ -216,6 +217,73 @@ SSDK_API int ssdk_postprocess_host(ssdk_ctx* ctx, const float* codes, const floa
                           const float* scores, int flags, int B, int64_t A, int C,
                           double score_threshold, double iou_threshold, int K, float* out_boxes,
                           float* out_scores, int32_t* out_classes, int32_t* out_num);
+
+/* ---- head-layout fusion: detector/box_predictor.py:67-104 (reshape_and_concatenate) ---------- */
+/* The box / class towers emit one tensor per FPN level in the network's data format (channels_first in the reference,
+ * constants.py:9): class_predictions[l] is [B, n*C, h_l, w_l] and encoded_boxes[l] is [B, n*4, h_l, w_l], n =
+ * num_anchors_per_location, channel = anchor_in_cell * C + class (resp. * 4 + coordinate).  The reference transposes,
+ * reshapes and concatenates them into [B,A,C] / [B,A,4] (one full read + write of every logit) before the loss and
+ * before post-processing.  The ssdk_head_* entry points consume the per-level tensors as they are; anchor index
+ * a = level_offset_l + (y * w_l + x) * n + anchor_in_cell, exactly the order of AnchorGenerator (anchor_generator.py:
+ * 99-103) and of reshape_and_concatenate.  SSDK_CHANNELS_LAST describes [B, h_l, w_l, n*C] towers. */
+#define SSDK_MAX_LEVELS 8
+#define SSDK_CHANNELS_LAST 0
+#define SSDK_CHANNELS_FIRST 1
+typedef struct ssdk_head {
+    int32_t num_levels;                 /* 1..SSDK_MAX_LEVELS */
+    int32_t anchors_per_location;       /* n */
+    int32_t data_format;                /* SSDK_CHANNELS_FIRST or SSDK_CHANNELS_LAST */
+    int32_t reserved;
+    int32_t height[SSDK_MAX_LEVELS];    /* h_l */
+    int32_t width[SSDK_MAX_LEVELS];     /* w_l */
+    const float* class_predictions[SSDK_MAX_LEVELS];   /* DEVICE, 16-byte aligned */
+    const float* encoded_boxes[SSDK_MAX_LEVELS];       /* DEVICE, 16-byte aligned */
+} ssdk_head;
+/* Gradient (output) tensors of the same shapes and data format as the head tensors. */
+typedef struct ssdk_head_grads {
+    float* class_predictions[SSDK_MAX_LEVELS];
+    float* encoded_boxes[SSDK_MAX_LEVELS];
+} ssdk_head_grads;
+
+/* reshape_and_concatenate (box_predictor.py:67-104) materialised: out_encoded_boxes [B,A,4] and/or
+ * out_class_predictions [B,A,C] (either may be NULL).  Not needed by the fused entry points below; provided for callers
+ * that want the reference's tensors, and as the un-fused baseline. */
+SSDK_API int ssdk_head_concat(ssdk_ctx* ctx, const ssdk_head* head, int B, int C, float* out_encoded_boxes,
+                     float* out_class_predictions);
+/* ssdk_ssd_loss on the per-level head tensors (no per-anchor outputs).  reg_targets [B,A,4], cls_targets [B,A],
+ * matches [B,A] are in anchor order (as ssdk_training_targets writes them); out_sums as ssdk_ssd_loss. */
+SSDK_API int ssdk_head_ssd_loss(ssdk_ctx* ctx, const ssdk_head* head, const float* reg_targets, const int32_t* cls_targets,
+                       const int32_t* matches, int B, int64_t A, int C, double gamma, double alpha, double* out_sums);
+/* ssdk_ssd_loss_forward_backward on the per-level head tensors: one pass over the logits produces the loss sums and
+ * the gradients, written per level in the head's own layout (every element of `grads` is written).
+ * out_sums may be NULL (backward only).  num_matches, upstream as ssdk_ssd_loss_forward_backward. */
+SSDK_API int ssdk_head_ssd_loss_forward_backward(ssdk_ctx* ctx, const ssdk_head* head, const float* reg_targets,
+                                        const int32_t* cls_targets, const int32_t* matches, int B, int64_t A, int C,
+                                        double gamma, double alpha, const double* num_matches, const float* upstream,
+                                        double* out_sums, const ssdk_head_grads* grads);
+/* ssdk_detect on the per-level head tensors (flags: SSDK_INPUT_LOGITS or SSDK_INPUT_SCORES; boxes are always encoded).
+ * box_scaler may be NULL, final_score_threshold -INFINITY, out_anchor_idx NULL. */
+SSDK_API int ssdk_head_detect(ssdk_ctx* ctx, const ssdk_head* head, const float* anchors, int flags, int B, int64_t A, int C,
+                     double score_threshold, double iou_threshold, int K, const float* box_scaler,
+                     double final_score_threshold, float* out_boxes, float* out_scores, int32_t* out_classes,
+                     int32_t* out_num, int32_t* out_anchor_idx);
+
+/* ---- observability: detector/ssd.py:125-129,135-163 (loss summaries) ------------------------ */
+/* Per-image, per-level statistics behind the reference's TensorBoard summaries, from the per-anchor vectors:
+ *   _add_scalewise_matches_summaries (ssd.py:152-163) / total_mean_matches_per_image (ssd.py:129):
+ *       out_matches[b,l] = number of matched anchors (matches >= 0) of image b on level l; the summaries are the
+ *       means over b of one column, resp. of the row sums.
+ *   _add_scalewise_summaries (ssd.py:135-150), for a per-anchor loss vector `values` [B,A] (all values >= 0):
+ *       k_l = ceil(n_l * top_fraction) (ssd.py:146; 0.20 in the reference), tf.nn.top_k(values[:, level l], k_l,
+ *       sorted=False) selects the k_l biggest values of every image.  The order inside that selection is unspecified
+ *       in TF, so what is exported is what does not depend on it: out_topk_mean[b,l] = mean of the selected values,
+ *       out_topk_kth[b,l] = the smallest selected value (the k_l-th biggest; selected set = values >= it, ties cut).
+ * values / matches may be NULL (the corresponding outputs are then not written and may be NULL too).
+ *   per_level: HOST int32[num_levels] = num_anchors_per_feature_map (anchor_generator.py:65), sum == A.
+ * Outputs are DEVICE float[B, num_levels]. */
+SSDK_API int ssdk_level_summaries(ssdk_ctx* ctx, const float* values, const int32_t* matches, int B, int64_t A,
+                         const int32_t* per_level, int num_levels, double top_fraction, float* out_topk_mean,
+                         float* out_topk_kth, float* out_matches);
 
 #ifdef __cplusplus
 }

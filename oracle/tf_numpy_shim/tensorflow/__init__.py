@@ -175,8 +175,8 @@ def reshape(x, shape):
     return _wrap(np.reshape(_arr(x), _ints(shape)))
 
 
-def transpose(x):
-    return _wrap(np.transpose(_arr(x)))
+def transpose(x, perm=None):
+    return _wrap(np.transpose(_arr(x), perm))
 
 
 def shape(x):

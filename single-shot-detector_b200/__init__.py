@@ -3,6 +3,8 @@
     AnchorGenerator, SSD                       detector/anchor_generator.py, detector/ssd.py
     get_training_targets, match_boxes, ...     detector/training_target_creation.py
     focal_loss, localization_loss              detector/losses.py
+    reshape_and_concatenate                    detector/box_predictor.py:67-104 (a view: SSD consumes the per-level
+                                               tower outputs without the transpose / concat copy)
     iou, encode, decode, batch_multiclass_non_max_suppression, ...   detector/utils
 
 All arithmetic runs in hand-written sm_100a CUDA kernels (csrc/) behind the C ABI of include/ssdk.h.
@@ -12,6 +14,7 @@ The directory name contains a hyphen: import it with importlib.import_module('si
 from . import _lib, config, graph, parallel  # noqa: F401
 from .detector import SSD  # noqa: F401
 from .detector.anchor_generator import AnchorGenerator  # noqa: F401
+from .detector.box_predictor import HeadPredictions, reshape_and_concatenate  # noqa: F401
 from .detector.losses import focal_loss, localization_loss  # noqa: F401
 from .detector.training_target_creation import (batch_training_targets, create_targets,  # noqa: F401
                                                 get_training_targets, match_boxes)

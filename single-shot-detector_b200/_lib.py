@@ -51,7 +51,28 @@ _SIGNATURES = {
     'ssdk_postprocess': (c_int, [P, P, P, P, c_int, c_int, c_i64, c_int, c_double, c_double, c_int, P, P, P, P, P]),
     'ssdk_detect': (c_int, [P, P, P, P, c_int, c_int, c_i64, c_int, c_double, c_double, c_int, P, c_double, P, P, P, P]),
     'ssdk_postprocess_host': (c_int, [P, P, P, P, c_int, c_int, c_i64, c_int, c_double, c_double, c_int, P, P, P, P]),
+    'ssdk_head_concat': (c_int, [P, P, c_int, c_int, P, P]),
+    'ssdk_head_ssd_loss': (c_int, [P, P, P, P, P, c_int, c_i64, c_int, c_double, c_double, P]),
+    'ssdk_head_ssd_loss_forward_backward': (c_int, [P, P, P, P, P, c_int, c_i64, c_int, c_double, c_double, P, P, P, P]),
+    'ssdk_head_detect': (c_int, [P, P, P, c_int, c_int, c_i64, c_int, c_double, c_double, c_int, P, c_double, P, P, P, P, P]),
+    'ssdk_level_summaries': (c_int, [P, P, P, c_int, c_i64, P, c_int, c_double, P, P, P]),
 }
+
+SSDK_MAX_LEVELS = 8
+SSDK_CHANNELS_LAST, SSDK_CHANNELS_FIRST = 0, 1
+
+
+class SsdkHead(ctypes.Structure):
+    """struct ssdk_head of include/ssdk.h: per-level tower outputs (detector/box_predictor.py:67-104)."""
+    _fields_ = [('num_levels', ctypes.c_int32), ('anchors_per_location', ctypes.c_int32), ('data_format', ctypes.c_int32),
+                ('reserved', ctypes.c_int32), ('height', ctypes.c_int32 * SSDK_MAX_LEVELS),
+                ('width', ctypes.c_int32 * SSDK_MAX_LEVELS), ('class_predictions', c_void_p * SSDK_MAX_LEVELS),
+                ('encoded_boxes', c_void_p * SSDK_MAX_LEVELS)]
+
+
+class SsdkHeadGrads(ctypes.Structure):
+    """struct ssdk_head_grads of include/ssdk.h."""
+    _fields_ = [('class_predictions', c_void_p * SSDK_MAX_LEVELS), ('encoded_boxes', c_void_p * SSDK_MAX_LEVELS)]
 
 SSDK_INPUT_SCORES, SSDK_INPUT_LOGITS = 0, 1
 SSDK_BOXES_ENCODED, SSDK_BOXES_DECODED = 0, 2
@@ -106,7 +127,7 @@ def context(device_index):
 
 
 KERNEL_IDS = ['anchors', 'match', 'force_match', 'ssd_loss', 'loss_reduce', 'filter', 'sort', 'nms', 'pack', 'other',
-              'ssd_loss_backward']
+              'ssd_loss_backward', 'head_flat', 'head_rows', 'head_concat']
 
 
 def set_profiling(enable, device_index=0):

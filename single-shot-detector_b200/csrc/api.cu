@@ -141,7 +141,7 @@ int ssdk_ctx_destroy(ssdk_ctx* ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     ssdk_buf* bufs[] = {&ctx->ws_gtbest, &ctx->ws_partials, &ctx->ws_reg, &ctx->ws_cls, &ctx->ws_matches,
-                        &ctx->ws_cand, &ctx->ws_counts, &ctx->ws_seg};
+                        &ctx->ws_cand, &ctx->ws_counts, &ctx->ws_seg, &ctx->ws_head, &ctx->ws_summ};
     for (ssdk_buf* b : bufs) if (b->p) cudaFree(b->p);
     for (ssdk_buf& b : ctx->ws_stage) if (b.p) cudaFree(b.p);
     if (ctx->prof_ev) {
@@ -158,7 +158,7 @@ int64_t ssdk_ctx_workspace_bytes(const ssdk_ctx* ctx) {
     if (!ctx) return 0;
     int64_t t = 0;
     const ssdk_buf* bufs[] = {&ctx->ws_gtbest, &ctx->ws_partials, &ctx->ws_reg, &ctx->ws_cls, &ctx->ws_matches,
-                              &ctx->ws_cand, &ctx->ws_counts, &ctx->ws_seg};
+                              &ctx->ws_cand, &ctx->ws_counts, &ctx->ws_seg, &ctx->ws_head, &ctx->ws_summ};
     for (const ssdk_buf* b : bufs) t += (int64_t)b->cap;
     for (const ssdk_buf& b : ctx->ws_stage) t += (int64_t)b.cap;
     return t;

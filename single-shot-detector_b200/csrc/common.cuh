@@ -18,7 +18,8 @@ struct ssdk_buf {
 // kernel ids for the optional per-kernel event timing (ssdk_ctx_set_profiling)
 enum ssdk_kernel_id {
     SSDK_K_ANCHORS = 0, SSDK_K_MATCH, SSDK_K_FORCE_MATCH, SSDK_K_LOSS, SSDK_K_LOSS_REDUCE, SSDK_K_FILTER,
-    SSDK_K_SORT, SSDK_K_NMS, SSDK_K_PACK, SSDK_K_OTHER, SSDK_K_LOSS_BACKWARD, SSDK_K_COUNT
+    SSDK_K_SORT, SSDK_K_NMS, SSDK_K_PACK, SSDK_K_OTHER, SSDK_K_LOSS_BACKWARD, SSDK_K_HEAD_FLAT, SSDK_K_HEAD_ROWS,
+    SSDK_K_HEAD_CONCAT, SSDK_K_COUNT
 };
 #define SSDK_PROFILE_EVENTS 2048
 
@@ -35,6 +36,8 @@ struct ssdk_ctx {
     ssdk_buf ws_counts;      // postprocess: per-image counters + per-(image,class) segment tables
     ssdk_buf ws_seg;         // postprocess: per-(image,class) kept boxes/scores/anchors
     ssdk_buf ws_stage[8];    // *_host entry points: device staging
+    ssdk_buf ws_head;        // head-layout loss: ticket + per-CTA partials of the flat and the rows kernel
+    ssdk_buf ws_summ;        // level summaries: per-(image, level) scratch
     // profiling: pairs of events around kernels, drained by ssdk_ctx_profile_read
     int profiling = 0;
     int prof_n = 0;
@@ -190,3 +193,38 @@ __device__ __forceinline__ float4 ld_stream_f4(const float4* p) {
 }
 
 static inline int ceil_div_i(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+// ----------------------------------------------------------------------------------------------
+// Head layout (detector/box_predictor.py:67-104): per-level tower outputs consumed without reshape_and_concatenate.
+// Anchor a of image b lives on level l (anchor_off[l] <= a < anchor_off[l+1]) at location loc = (a - anchor_off[l]) / n,
+// anchor-in-cell k = (a - anchor_off[l]) % n; its class-c logit is channel k*C + c, its box coordinate j channel k*4 + j.
+// ----------------------------------------------------------------------------------------------
+struct HeadGeom {
+    int num_levels, per_loc, channels_first, C;
+    int anchor_off[SSDK_MAX_LEVELS + 1];
+    int hw[SSDK_MAX_LEVELS];
+    const float* cls[SSDK_MAX_LEVELS];
+    const float* box[SSDK_MAX_LEVELS];
+};
+
+// Validates an ssdk_head against (B, A, C) and fills the device-side geometry.
+int ssdk_head_geom(const ssdk_head* head, int B, int64_t A, int C, bool need_cls, bool need_box, HeadGeom* out);
+
+__device__ __forceinline__ int head_level_of(const HeadGeom& g, int a) {
+    int l = 0;
+    while (l + 1 < g.num_levels && a >= g.anchor_off[l + 1]) ++l;
+    return l;
+}
+// offset (in floats) of channel ch (of nch per location) at location loc of image b on a level with hw locations
+__device__ __forceinline__ long long head_elem(int channels_first, int b, int nch, int hw, int ch, int loc) {
+    return channels_first ? ((long long)b * nch + ch) * hw + loc : ((long long)b * hw + loc) * nch + ch;
+}
+__device__ __forceinline__ float4 head_load_code(const HeadGeom& g, int b, int a) {
+    const int l = head_level_of(g, a);
+    const int r = a - g.anchor_off[l];
+    const int loc = r / g.per_loc, k = r - loc * g.per_loc;
+    const int hw = g.hw[l];
+    const float* p = g.box[l] + head_elem(g.channels_first, b, g.per_loc * 4, hw, k * 4, loc);
+    if (g.channels_first) return make_float4(__ldg(p), __ldg(p + hw), __ldg(p + 2 * (long long)hw), __ldg(p + 3 * (long long)hw));
+    return __ldg((const float4*)p);
+}

@@ -1,0 +1,519 @@
+// Head-layout fusion: the SSD loss (forward, and forward + backward) computed directly on the per-level tower outputs
+// [B, n*C, h_l, w_l] / [B, n*4, h_l, w_l], i.e. WITHOUT reshape_and_concatenate (detector/box_predictor.py:67-104), which in
+// the reference transposes, reshapes and concatenates every logit into [B,A,C] (one full read + write) right before
+// detector/ssd.py:71-133 consumes it.
+//
+// Why this works without a transpose: with not_ignore weights and one-hot targets (ssd.py:96-109, losses.py:34-50)
+//     sum cls_losses = (1-alpha) * SUM over ALL logits of neg(x)                                   <- layout independent
+//                      + SUM over matched anchors      [ alpha * pos(x_c*) - (1-alpha) * neg(x_c*) ]   <- ~0.5 % of the anchors
+//                      - SUM over ignored anchors, all c [ (1-alpha) * neg(x_c) ]                    <- only when neg_thr < pos_thr
+// with neg(x) = sigmoid(x)^gamma * softplus(x) and pos(x) = (1-sigmoid(x))^gamma * softplus(-x).  So
+//   1. head_flat_kernel streams every level's class tensor as a flat array (128-bit no-allocate loads, register
+//      double-buffering, the same e^3 g(e) fast path as ssd_loss_kernel) and needs neither targets nor geometry; with
+//      WITH_GRAD it also writes k * d neg/dx for every element, in place of the same flat index of the gradient tensor;
+//   2. head_rows_kernel walks matches [B,A] (4 bytes per anchor), and for the few matched / ignored anchors gathers their
+//      logits and box codes through the head geometry: corrections to the sum, smooth-L1, the matched count, and (WITH_GRAD)
+//      the positive-class / ignored-row gradient fix-ups and the box gradients;  the CTA that finishes last adds all
+//      per-CTA partials of both kernels in a fixed order (deterministic, no float atomics).
+// Algorithmic traffic per image: 4AC (+4AC gradients) + 4A (matches) + O(matched) -- the [B,A,C] copy the reference makes
+// (another 8AC) is gone, and so are the 16A + 4A bytes of codes / cls_targets the anchor-major kernel streams.
+//
+// Also here: ssdk_head_concat (reshape_and_concatenate itself, as a tiled transpose) for callers that want the
+// reference's tensors, and as the un-fused baseline in bench.py.
+#include <stdlib.h>
+
+#include "focal_math.cuh"
+
+#define FLAT_THREADS 256
+#define FLAT_U 4                                        // float4 per thread and chunk
+#define FLAT_CHUNK4 (FLAT_THREADS * FLAT_U)             // float4 per chunk (16 KB)
+
+struct FlatSegs {
+    int n;
+    const float* src[SSDK_MAX_LEVELS];
+    float* dst[SSDK_MAX_LEVELS];                        // WITH_GRAD: gradient tensors, same flat indexing
+    long long count[SSDK_MAX_LEVELS];                   // floats per level (B * n*C * h*w)
+    long long chunk0[SSDK_MAX_LEVELS + 1];              // prefix sums of the per-level chunk counts
+};
+
+struct HeadGradPtrs {
+    float* cls[SSDK_MAX_LEVELS];
+    float* box[SSDK_MAX_LEVELS];
+};
+
+// ---------------------------------------------------------------------------------------------- 1. flat pass
+struct FlatChunk {
+    float4 v[FLAT_U];
+    long long i4;        // index of v[0] (in float4) for this thread
+    int lvl;
+};
+
+template <int GAMMA_MODE, bool WITH_GRAD>
+__global__ void __launch_bounds__(FLAT_THREADS) head_flat_kernel(const FlatSegs S, float gamma, float alpha,
+                                                                  const double* __restrict__ norm_count,
+                                                                  const float* __restrict__ upstream,
+                                                                  double* __restrict__ partials /*[grid]*/) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const long long total = S.chunk0[S.n];
+    const float4 ninf4 = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+    float k_neg = 0.0f;
+    if (WITH_GRAD) {
+        const double norm = fmax(*norm_count, 1.0);                       // ssd.py:123 (global count)
+        const float u_cls = upstream ? upstream[1] : 1.0f;
+        k_neg = (float)((double)u_cls * (1.0 - (double)alpha) / norm);
+    }
+    double acc = 0.0;
+
+    int cursor = 0;                                                       // level of the most recently loaded chunk
+    auto load = [&](FlatChunk& ck, long long g) {
+        while (g >= S.chunk0[cursor + 1]) ++cursor;
+        ck.lvl = cursor;
+        const long long n4 = S.count[cursor] >> 2;
+        const float4* src4 = (const float4*)S.src[cursor];
+        ck.i4 = (g - S.chunk0[cursor]) * FLAT_CHUNK4 + tid;
+#pragma unroll
+        for (int u = 0; u < FLAT_U; ++u) {
+            const long long i = ck.i4 + u * FLAT_THREADS;
+            ck.v[u] = (i < n4) ? ld_stream_f4(src4 + i) : ninf4;
+        }
+    };
+    auto compute = [&](FlatChunk& ck, long long g) {
+        float s;
+        if (WITH_GRAD) {
+            const long long n4 = S.count[ck.lvl] >> 2;
+            float4* dst4 = (float4*)S.dst[ck.lvl];
+            float t = 0.0f;
+#pragma unroll
+            for (int u = 0; u < FLAT_U; ++u) {
+                float4 v = ck.v[u];
+                float f0, f1, f2, f3;
+                v.x = k_neg * focal_negative_both<GAMMA_MODE>(v.x, gamma, f0);
+                v.y = k_neg * focal_negative_both<GAMMA_MODE>(v.y, gamma, f1);
+                v.z = k_neg * focal_negative_both<GAMMA_MODE>(v.z, gamma, f2);
+                v.w = k_neg * focal_negative_both<GAMMA_MODE>(v.w, gamma, f3);
+                t += (f0 + f1) + (f2 + f3);
+                const long long i = ck.i4 + u * FLAT_THREADS;
+                if (i < n4) dst4[i] = v;
+            }
+            s = t;
+        } else {
+            bool general = (GAMMA_MODE != 0);
+            if (GAMMA_MODE == 0) {
+                f32x2 a4[4] = {0ull, 0ull, 0ull, 0ull};
+                unsigned allneg = 0x80000000u;
+#pragma unroll
+                for (int u = 0; u < FLAT_U; u += 2) focal_fast8(ck.v[u], ck.v[u + 1], a4, allneg);
+                float s0, s1;
+                unpack2(add2(add2(a4[0], a4[1]), add2(a4[2], a4[3])), s0, s1);
+                s = s0 + s1;
+                general = (allneg >> 31) == 0u;                           // some logit >= +0: redo these with the general form
+            }
+            if (general) {
+                f32x2 a01 = 0ull, a23 = 0ull;
+#pragma unroll
+                for (int u = 0; u < FLAT_U; ++u) {
+                    a01 = focal_negative2<GAMMA_MODE>(ck.v[u].x, ck.v[u].y, gamma, a01);
+                    a23 = focal_negative2<GAMMA_MODE>(ck.v[u].z, ck.v[u].w, gamma, a23);
+                }
+                float s0, s1;
+                unpack2(add2(a01, a23), s0, s1);
+                s = s0 + s1;
+            }
+        }
+        // the (< 4) floats of a level beyond its last float4, handled with the level's last chunk
+        if (g + 1 == S.chunk0[ck.lvl + 1]) {
+            const long long n = S.count[ck.lvl];
+            const int tail = (int)(n & 3);
+            if (tid < tail) {
+                const long long e = (n & ~3ll) + tid;
+                const float x = S.src[ck.lvl][e];
+                if (WITH_GRAD) {
+                    float f;
+                    S.dst[ck.lvl][e] = k_neg * focal_negative_both<GAMMA_MODE>(x, gamma, f);
+                    s += f;
+                } else {
+                    s += focal_negative<GAMMA_MODE>(x, gamma);
+                }
+            }
+        }
+        acc += (double)s;
+    };
+
+    // register double-buffering: the loads of the next chunk are in flight while the current one is evaluated
+    {
+        FlatChunk ca, cb;
+        long long g = blockIdx.x;
+        const long long step = gridDim.x;
+        if (g < total) {
+            load(ca, g);
+            while (true) {
+                const long long gb = g + step;
+                const bool has_b = gb < total;
+                if (has_b) load(cb, gb);
+                compute(ca, g);
+                if (!has_b) break;
+                g = gb + step;
+                const bool has_a = g < total;
+                if (has_a) load(ca, g);
+                compute(cb, gb);
+                if (!has_a) break;
+            }
+        }
+    }
+
+    __shared__ double s_red[FLAT_THREADS / 32];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) s_red[warp] = acc;
+    __syncthreads();
+    if (tid == 0) {
+        double t = 0.0;
+#pragma unroll
+        for (int w = 0; w < FLAT_THREADS / 32; ++w) t += s_red[w];
+        partials[blockIdx.x] = t;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------- 2. matched / ignored anchors
+#define ROWS_THREADS 256
+template <int GAMMA_MODE, bool WITH_GRAD>
+__global__ void __launch_bounds__(ROWS_THREADS) head_rows_kernel(
+    const HeadGeom G, const HeadGradPtrs GR, const float4* __restrict__ reg_t, const int* __restrict__ cls_t,
+    const int* __restrict__ matches, int A, long long NA, float gamma, float alpha, const double* __restrict__ norm_count,
+    const float* __restrict__ upstream, const double* __restrict__ flat_partials, int n_flat,
+    double* __restrict__ partials /*[grid][3]*/, unsigned* __restrict__ ticket, double* __restrict__ out_sums /*[3] or NULL*/) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int C = G.C, n = G.per_loc, cf = G.channels_first;
+    const float one_minus_alpha = 1.0f - alpha;
+    float k_loc = 0.0f, k_pos = 0.0f;
+    if (WITH_GRAD) {
+        const double norm = fmax(*norm_count, 1.0);
+        const float u_loc = upstream ? upstream[0] : 1.0f, u_cls = upstream ? upstream[1] : 1.0f;
+        k_loc = (float)((double)u_loc / norm);
+        k_pos = (float)((double)u_cls * (double)alpha / norm);
+    }
+    double acc_loc = 0.0, acc_fix = 0.0, acc_cnt = 0.0;
+
+    const long long stride = (long long)gridDim.x * ROWS_THREADS;
+    for (long long i0 = (long long)blockIdx.x * ROWS_THREADS; i0 < NA; i0 += stride) {
+        const long long i = i0 + tid;
+        const int m = (i < NA) ? __ldg(matches + i) : -1;
+        int b = 0, l = 0, loc = 0, k = 0;
+        if (m != -1) {                                                   // matched or ignored: locate the anchor in the head
+            b = (int)(i / A);
+            const int a = (int)(i - (long long)b * A);
+            l = head_level_of(G, a);
+            const int r = a - G.anchor_off[l];
+            loc = r / n;
+            k = r - loc * n;
+        }
+        if (m >= 0) {
+            const int hw = G.hw[l];
+            // ---- localisation loss (ssd.py:117, losses.py:4-19) + matched count (ssd.py:121-122)
+            const long long e0 = head_elem(cf, b, n * 4, hw, k * 4, loc);
+            const long long es = cf ? hw : 1;
+            const float* pb = G.box[l] + e0;
+            const float4 p = make_float4(__ldg(pb), __ldg(pb + es), __ldg(pb + 2 * es), __ldg(pb + 3 * es));
+            const float4 t = __ldg(reg_t + i);
+            acc_loc += (double)smooth_l1_4(p, t);
+            acc_cnt += 1.0;
+            if (WITH_GRAD) {
+                float* gb = GR.box[l] + e0;
+                gb[0] = k_loc * smooth_l1_grad(p.x, t.x);
+                gb[es] = k_loc * smooth_l1_grad(p.y, t.y);
+                gb[2 * es] = k_loc * smooth_l1_grad(p.z, t.z);
+                gb[3 * es] = k_loc * smooth_l1_grad(p.w, t.w);
+            }
+            // ---- the positive class: its logit was summed as a negative by the flat pass
+            const int tc = __ldg(cls_t + i) - 1;                         // one_hot(cls, C+1)[1:] (ssd.py:96-100)
+            if (tc >= 0 && tc < C) {
+                const long long e = head_elem(cf, b, n * C, hw, k * C + tc, loc);
+                const float x = __ldg(G.cls[l] + e);
+                acc_fix += (double)(alpha * focal_positive<GAMMA_MODE>(x, gamma)) -
+                           (double)(one_minus_alpha * focal_negative<GAMMA_MODE>(x, gamma));
+                if (WITH_GRAD) GR.cls[l][e] = k_pos * focal_positive_grad<GAMMA_MODE>(x, gamma);
+            }
+        }
+        // ---- ignored anchors (matches == -2: weight 0, ssd.py:103): every class was summed by the flat pass; the warp
+        //      removes them together, lanes over classes
+        unsigned ign = __ballot_sync(0xffffffffu, m < -1);
+        while (ign) {
+            const int src = __ffs(ign) - 1;
+            ign &= ign - 1;
+            const int sb = __shfl_sync(0xffffffffu, b, src), sl = __shfl_sync(0xffffffffu, l, src);
+            const int sloc = __shfl_sync(0xffffffffu, loc, src), sk = __shfl_sync(0xffffffffu, k, src);
+            const int hw = G.hw[sl];
+            float sub = 0.0f;
+            for (int c = lane; c < C; c += 32) {
+                const long long e = head_elem(cf, sb, n * C, hw, sk * C + c, sloc);
+                sub += focal_negative<GAMMA_MODE>(__ldg(G.cls[sl] + e), gamma);
+                if (WITH_GRAD) GR.cls[sl][e] = 0.0f;
+            }
+            acc_fix -= (double)(one_minus_alpha * sub);
+        }
+    }
+
+    // ---- CTA reduction (fixed order) -> partials[blockIdx.x]; the last CTA combines everything
+    __shared__ double s_red[ROWS_THREADS / 32][3];
+    __shared__ double s_fin[64][4];
+    __shared__ int s_last;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        acc_loc += __shfl_xor_sync(0xffffffffu, acc_loc, o);
+        acc_fix += __shfl_xor_sync(0xffffffffu, acc_fix, o);
+        acc_cnt += __shfl_xor_sync(0xffffffffu, acc_cnt, o);
+    }
+    if (lane == 0) { s_red[warp][0] = acc_loc; s_red[warp][1] = acc_fix; s_red[warp][2] = acc_cnt; }
+    __syncthreads();
+    if (out_sums == nullptr) return;
+    if (tid < 3) {
+        double t = 0.0;
+#pragma unroll
+        for (int w = 0; w < ROWS_THREADS / 32; ++w) t += s_red[w][tid];
+        partials[(size_t)blockIdx.x * 3 + tid] = t;
+        __threadfence();
+    }
+    __syncthreads();
+    if (tid == 0) s_last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    if (tid < 64) {
+        double t[4] = {0.0, 0.0, 0.0, 0.0};
+        for (int i = tid; i < (int)gridDim.x; i += 64)
+            for (int j = 0; j < 3; ++j) t[j] += __ldcg(&partials[(size_t)i * 3 + j]);
+        for (int i = tid; i < n_flat; i += 64) t[3] += __ldcg(&flat_partials[i]);
+        for (int j = 0; j < 4; ++j) s_fin[tid][j] = t[j];
+    }
+    __syncthreads();
+    for (int o = 32; o > 0; o >>= 1) {
+        if (tid < o)
+            for (int j = 0; j < 4; ++j) s_fin[tid][j] += s_fin[tid + o][j];
+        __syncthreads();
+    }
+    if (tid == 0) {
+        out_sums[0] = s_fin[0][0];                                                   // sum loc_losses
+        out_sums[1] = (double)one_minus_alpha * s_fin[0][3] + s_fin[0][1];           // sum cls_losses
+        out_sums[2] = s_fin[0][2];                                                   // num_matches
+        *ticket = 0u;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------- reshape_and_concatenate
+// channels_first level [B, CH, hw] -> out[b, (off + loc) * CH/n ... ]: for one image the level is a [CH, hw] matrix whose
+// transpose [hw, CH] is the level's contiguous block of the [A, C] (or [A, 4]) output.  32x32 tiles through shared memory.
+__global__ void __launch_bounds__(256) head_transpose_kernel(const float* __restrict__ in, float* __restrict__ out, int CH, int hw,
+                                                             long long out_image_stride, long long out_level_off) {
+    __shared__ float tile[32][33];
+    const int b = blockIdx.z;
+    const float* src = in + (size_t)b * CH * hw;
+    float* dst = out + (size_t)b * out_image_stride + out_level_off;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;             // 32 x 8
+    const int loc0 = blockIdx.x * 32, ch0 = blockIdx.y * 32;
+#pragma unroll
+    for (int j = 0; j < 32; j += 8) {
+        const int ch = ch0 + ty + j, loc = loc0 + tx;
+        if (ch < CH && loc < hw) tile[ty + j][tx] = src[(size_t)ch * hw + loc];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < 32; j += 8) {
+        const int loc = loc0 + ty + j, ch = ch0 + tx;
+        if (ch < CH && loc < hw) dst[(size_t)loc * CH + ch] = tile[tx][ty + j];
+    }
+}
+
+// channels_last level [B, hw*CH] -> the level's block of every image: a strided copy
+__global__ void __launch_bounds__(256) head_copy_kernel(const float* __restrict__ in, float* __restrict__ out, long long per_image,
+                                                        long long out_image_stride, long long out_level_off) {
+    const int b = blockIdx.y;
+    const float* src = in + (size_t)b * per_image;
+    float* dst = out + (size_t)b * out_image_stride + out_level_off;
+    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < per_image; i += (long long)gridDim.x * 256) dst[i] = src[i];
+}
+
+// ---------------------------------------------------------------------------------------------- host side
+static bool aligned16(const void* p) { return ((uintptr_t)p & 15) == 0; }
+
+int ssdk_head_geom(const ssdk_head* head, int B, int64_t A, int C, bool need_cls, bool need_box, HeadGeom* out) {
+    SSDK_REQUIRE(head != nullptr, SSDK_ERR_ARG, "ssdk_head: null head descriptor");
+    SSDK_REQUIRE(head->num_levels >= 1 && head->num_levels <= SSDK_MAX_LEVELS, SSDK_ERR_ARG, "ssdk_head: num_levels %d not in [1,%d]",
+                 head->num_levels, SSDK_MAX_LEVELS);
+    SSDK_REQUIRE(head->anchors_per_location >= 1, SSDK_ERR_ARG, "ssdk_head: anchors_per_location %d", head->anchors_per_location);
+    SSDK_REQUIRE(head->data_format == SSDK_CHANNELS_FIRST || head->data_format == SSDK_CHANNELS_LAST, SSDK_ERR_ARG,
+                 "ssdk_head: data_format %d", head->data_format);
+    SSDK_REQUIRE(B >= 0 && A >= 0 && C > 0, SSDK_ERR_ARG, "ssdk_head: bad sizes (B=%d A=%lld C=%d)", B, (long long)A, C);
+    SSDK_REQUIRE(A < (1ll << 31), SSDK_ERR_SHAPE, "ssdk_head: A must be < 2^31");
+    HeadGeom g;
+    g.num_levels = head->num_levels;
+    g.per_loc = head->anchors_per_location;
+    g.channels_first = head->data_format == SSDK_CHANNELS_FIRST;
+    g.C = C;
+    long long off = 0;
+    for (int l = 0; l < SSDK_MAX_LEVELS; ++l) {
+        g.anchor_off[l] = (int)off;
+        g.hw[l] = 0; g.cls[l] = nullptr; g.box[l] = nullptr;
+        if (l >= head->num_levels) continue;
+        SSDK_REQUIRE(head->height[l] >= 0 && head->width[l] >= 0, SSDK_ERR_ARG, "ssdk_head: level %d has negative size", l);
+        const long long hw = (long long)head->height[l] * head->width[l];
+        SSDK_REQUIRE(hw * g.per_loc * (long long)(C > 4 ? C : 4) < (1ll << 31), SSDK_ERR_SHAPE, "ssdk_head: level %d too large", l);
+        g.hw[l] = (int)hw;
+        g.cls[l] = head->class_predictions[l];
+        g.box[l] = head->encoded_boxes[l];
+        if (hw > 0 && B > 0) {
+            SSDK_REQUIRE(!need_cls || g.cls[l], SSDK_ERR_ARG, "ssdk_head: class_predictions[%d] is NULL", l);
+            SSDK_REQUIRE(!need_box || g.box[l], SSDK_ERR_ARG, "ssdk_head: encoded_boxes[%d] is NULL", l);
+            SSDK_REQUIRE(aligned16(g.cls[l]) && aligned16(g.box[l]), SSDK_ERR_SHAPE, "ssdk_head: level %d tensors must be 16-byte aligned", l);
+        }
+        off += hw * g.per_loc;
+    }
+    for (int l = head->num_levels; l <= SSDK_MAX_LEVELS; ++l) g.anchor_off[l] = (int)off;
+    SSDK_REQUIRE(off == A, SSDK_ERR_SHAPE, "ssdk_head: levels hold %lld anchors, expected A = %lld", off, (long long)A);
+    *out = g;
+    return SSDK_OK;
+}
+
+static int head_loss_impl(ssdk_ctx* ctx, const ssdk_head* head, const float* reg_targets, const int32_t* cls_targets,
+                          const int32_t* matches, int B, int64_t A, int C, double gamma, double alpha, const double* num_matches,
+                          const float* upstream, double* out_sums, const ssdk_head_grads* grads, bool with_grad) {
+    SSDK_TRY(ssdk_ctx_enter(ctx));
+    HeadGeom G;
+    SSDK_TRY(ssdk_head_geom(head, B, A, C, true, true, &G));
+    const long long NA = (long long)B * A;
+    if (NA == 0) {
+        if (out_sums) SSDK_CHECK_CUDA(cudaMemsetAsync(out_sums, 0, 3 * sizeof(double), ctx->stream));
+        return SSDK_OK;
+    }
+    SSDK_REQUIRE(reg_targets && cls_targets && matches, SSDK_ERR_ARG, "ssdk_head_ssd_loss: null target pointer");
+    SSDK_REQUIRE(aligned16(reg_targets), SSDK_ERR_SHAPE, "ssdk_head_ssd_loss: reg_targets must be 16-byte aligned");
+    SSDK_REQUIRE(!with_grad || (grads && num_matches), SSDK_ERR_ARG, "ssdk_head_ssd_loss_forward_backward: null grads / num_matches");
+    SSDK_REQUIRE(with_grad || out_sums, SSDK_ERR_ARG, "ssdk_head_ssd_loss: out_sums is NULL");
+
+    FlatSegs S;
+    HeadGradPtrs GR;
+    S.n = G.num_levels;
+    long long chunks = 0;
+    for (int l = 0; l < SSDK_MAX_LEVELS; ++l) {
+        S.src[l] = G.cls[l];
+        S.dst[l] = nullptr;
+        GR.cls[l] = nullptr; GR.box[l] = nullptr;
+        S.count[l] = (long long)B * G.per_loc * C * G.hw[l];
+        S.chunk0[l] = chunks;
+        if (l < G.num_levels) {
+            chunks += (S.count[l] + 4 * FLAT_CHUNK4 - 1) / (4 * FLAT_CHUNK4);
+            if (with_grad && S.count[l] > 0) {
+                GR.cls[l] = grads->class_predictions[l];
+                GR.box[l] = grads->encoded_boxes[l];
+                SSDK_REQUIRE(GR.cls[l] && GR.box[l], SSDK_ERR_ARG, "ssdk_head_ssd_loss_forward_backward: grads of level %d are NULL", l);
+                SSDK_REQUIRE(aligned16(GR.cls[l]) && aligned16(GR.box[l]), SSDK_ERR_SHAPE,
+                             "ssdk_head_ssd_loss_forward_backward: grads of level %d must be 16-byte aligned", l);
+                S.dst[l] = GR.cls[l];
+                // box gradients are zero except for the matched anchors, which head_rows_kernel scatters
+                SSDK_CHECK_CUDA(cudaMemsetAsync(GR.box[l], 0, (size_t)B * G.per_loc * 4 * G.hw[l] * sizeof(float), ctx->stream));
+            }
+        }
+    }
+    for (int l = G.num_levels; l <= SSDK_MAX_LEVELS; ++l) S.chunk0[l] = chunks;
+
+    // persistent-style grid: exactly the number of co-resident CTAs (a larger grid would add a partial second wave)
+    static int occ_cache[4] = {0, 0, 0, 0};
+    const int variant = (gamma == 2.0 ? 0 : 2) + (with_grad ? 1 : 0);
+    if (occ_cache[variant] == 0) {
+        const void* fn = variant == 0 ? (const void*)head_flat_kernel<0, false> : variant == 1 ? (const void*)head_flat_kernel<0, true>
+                       : variant == 2 ? (const void*)head_flat_kernel<1, false> : (const void*)head_flat_kernel<1, true>;
+        int occ = 0;
+        SSDK_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, FLAT_THREADS, 0));
+        occ_cache[variant] = occ > 0 ? occ : 1;
+    }
+    int per_sm = occ_cache[variant];
+    if (const char* e = getenv("SSDK_HEAD_CTAS")) per_sm = atoi(e);             // tuning knob (CTAs per SM)
+    if (per_sm < 1) per_sm = 1;
+    if (per_sm > 8) per_sm = 8;
+    long long grid_flat = (long long)ctx->num_sms * per_sm;
+    if (grid_flat > chunks) grid_flat = chunks;
+    if (grid_flat < 1) grid_flat = 1;
+    long long grid_rows = (NA + ROWS_THREADS - 1) / ROWS_THREADS;
+    if (grid_rows > (long long)ctx->num_sms * 8) grid_rows = (long long)ctx->num_sms * 8;
+
+    const size_t ws_bytes = 16 + (size_t)ctx->num_sms * 8 * 4 * sizeof(double);
+    if (ctx->ws_head.cap < ws_bytes) {
+        SSDK_TRY(ssdk_ensure(ctx, &ctx->ws_head, ws_bytes));
+        SSDK_CHECK_CUDA(cudaMemsetAsync(ctx->ws_head.p, 0, 16, ctx->stream));
+    }
+    unsigned* ticket = (unsigned*)ctx->ws_head.p;
+    double* flat_partials = (double*)((char*)ctx->ws_head.p + 16);
+    double* rows_partials = flat_partials + (size_t)ctx->num_sms * 8;
+
+    const float gf = (float)gamma, af = (float)alpha;
+    const bool g2 = (gamma == 2.0);
+#define SSDK_LAUNCH_HEAD(GM, WG)                                                                                              \
+    do {                                                                                                                      \
+        SSDK_KERNEL(ctx, SSDK_K_HEAD_FLAT,                                                                                    \
+                    head_flat_kernel<GM, WG><<<(int)grid_flat, FLAT_THREADS, 0, ctx->stream>>>(S, gf, af, num_matches, upstream, \
+                                                                                              flat_partials));                 \
+        SSDK_KERNEL(ctx, SSDK_K_HEAD_ROWS,                                                                                    \
+                    head_rows_kernel<GM, WG><<<(int)grid_rows, ROWS_THREADS, 0, ctx->stream>>>(                               \
+                        G, GR, (const float4*)reg_targets, cls_targets, matches, (int)A, NA, gf, af, num_matches, upstream,   \
+                        flat_partials, (int)grid_flat, rows_partials, ticket, out_sums));                                     \
+    } while (0)
+    if (g2 && !with_grad) SSDK_LAUNCH_HEAD(0, false);
+    else if (g2) SSDK_LAUNCH_HEAD(0, true);
+    else if (!with_grad) SSDK_LAUNCH_HEAD(1, false);
+    else SSDK_LAUNCH_HEAD(1, true);
+#undef SSDK_LAUNCH_HEAD
+    return SSDK_OK;
+}
+
+extern "C" {
+
+int ssdk_head_ssd_loss(ssdk_ctx* ctx, const ssdk_head* head, const float* reg_targets, const int32_t* cls_targets,
+                       const int32_t* matches, int B, int64_t A, int C, double gamma, double alpha, double* out_sums) {
+    return head_loss_impl(ctx, head, reg_targets, cls_targets, matches, B, A, C, gamma, alpha, nullptr, nullptr, out_sums, nullptr,
+                          false);
+}
+
+int ssdk_head_ssd_loss_forward_backward(ssdk_ctx* ctx, const ssdk_head* head, const float* reg_targets,
+                                        const int32_t* cls_targets, const int32_t* matches, int B, int64_t A, int C,
+                                        double gamma, double alpha, const double* num_matches, const float* upstream,
+                                        double* out_sums, const ssdk_head_grads* grads) {
+    return head_loss_impl(ctx, head, reg_targets, cls_targets, matches, B, A, C, gamma, alpha, num_matches, upstream, out_sums,
+                          grads, true);
+}
+
+int ssdk_head_concat(ssdk_ctx* ctx, const ssdk_head* head, int B, int C, float* out_encoded_boxes, float* out_class_predictions) {
+    SSDK_TRY(ssdk_ctx_enter(ctx));
+    SSDK_REQUIRE(head != nullptr, SSDK_ERR_ARG, "ssdk_head_concat: null head descriptor");
+    long long A = 0;
+    for (int l = 0; l < head->num_levels && l < SSDK_MAX_LEVELS; ++l)
+        A += (long long)head->height[l] * head->width[l] * head->anchors_per_location;
+    HeadGeom G;
+    SSDK_TRY(ssdk_head_geom(head, B, A, C, out_class_predictions != nullptr, out_encoded_boxes != nullptr, &G));
+    if (B == 0 || A == 0) return SSDK_OK;
+    SSDK_REQUIRE(B <= 65535, SSDK_ERR_SHAPE, "ssdk_head_concat: batch %d > 65535", B);
+    for (int which = 0; which < 2; ++which) {
+        float* out = which ? out_class_predictions : out_encoded_boxes;
+        if (!out) continue;
+        const int D = which ? C : 4;                                      // values per anchor
+        for (int l = 0; l < G.num_levels; ++l) {
+            const int hw = G.hw[l];
+            if (hw == 0) continue;
+            const float* in = which ? G.cls[l] : G.box[l];
+            const int CH = G.per_loc * D;
+            const long long level_off = (long long)G.anchor_off[l] * D;
+            if (G.channels_first) {
+                const dim3 grid(ceil_div_i(hw, 32), ceil_div_i(CH, 32), B);
+                SSDK_KERNEL(ctx, SSDK_K_HEAD_CONCAT,
+                            head_transpose_kernel<<<grid, 256, 0, ctx->stream>>>(in, out, CH, hw, A * D, level_off));
+            } else {
+                const long long per_image = (long long)hw * CH;
+                long long gx = (per_image + 256 * 8 - 1) / (256 * 8);
+                if (gx > 4096) gx = 4096;
+                SSDK_KERNEL(ctx, SSDK_K_HEAD_CONCAT,
+                            head_copy_kernel<<<dim3((unsigned)gx, B), 256, 0, ctx->stream>>>(in, out, per_image, A * D, level_off));
+            }
+        }
+    }
+    return SSDK_OK;
+}
+
+}  // extern "C"

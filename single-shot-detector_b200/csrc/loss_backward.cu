@@ -18,63 +18,7 @@
 // the producer one tile later, once that store has finished reading shared memory.  Algorithmic traffic: 4AC read +
 // 4AC written (+ 48A for codes / targets / grad_codes): the kernel is HBM-bound, the math (2 MUFU + ~20 FMA-class ops
 // per element) fits under the 8-bytes-per-element budget.
-#include "stream.cuh"
-
-// d/dx of the negative-class term, without the (1-alpha) * u/N factor
-template <int GAMMA_MODE>
-__device__ __forceinline__ float focal_negative_grad(float x, float gamma) {
-    const float e = ex2_approx(-fabsf(x) * 1.4426950408889634f);
-    const float r = rcp_approx(1.0f + e);
-    const float er = e * r;
-    const float p = (x >= 0.0f) ? r : er;                    // sigmoid(x)
-    const float q = (x >= 0.0f) ? er : r;                    // 1 - sigmoid(x)
-    const float sp = fmaxf(x, 0.0f) + log1p_unit(e);         // softplus(x)
-    if (GAMMA_MODE == 0) return p * p * fmaf(2.0f * q, sp, p);
-    return powf(p, gamma) * fmaf(gamma * q, sp, p);
-}
-
-// d/dx of the positive-class term, without the alpha * u/N factor (at most one per anchor row: libm)
-template <int GAMMA_MODE>
-__device__ __forceinline__ float focal_positive_grad(float x, float gamma) {
-    const float p = 1.0f / (1.0f + expf(-x));
-    const float q = 1.0f / (1.0f + expf(x));                 // 1 - p without cancellation
-    const float logp = -(fmaxf(-x, 0.0f) + log1pf(expf(-fabsf(x))));
-    const float mod = (GAMMA_MODE == 0) ? q * q : powf(q, gamma);
-    return mod * (gamma * p * logp - q);
-}
-
-// value and d/dx of the negative-class term (both without the (1-alpha) factor): shares e, r, softplus
-template <int GAMMA_MODE>
-__device__ __forceinline__ float focal_negative_both(float x, float gamma, float& value) {
-    const float e = ex2_approx(-fabsf(x) * 1.4426950408889634f);
-    const float r = rcp_approx(1.0f + e);
-    const float er = e * r;
-    const float p = (x >= 0.0f) ? r : er;
-    const float q = (x >= 0.0f) ? er : r;
-    const float sp = fmaxf(x, 0.0f) + log1p_unit(e);
-    const float mod = (GAMMA_MODE == 0) ? p * p : powf(p, gamma);
-    value = mod * sp;
-    return mod * fmaf(gamma * q, sp, p);
-}
-
-// value of the positive-class term without the alpha factor: losses.py:36-41 with targets == 1
-template <int GAMMA_MODE>
-__device__ __forceinline__ float focal_positive_value(float x, float gamma) {
-    const float nlpt = (fmaxf(x, 0.0f) - x) + log1pf(expf(-fabsf(x)));
-    const float q = 1.0f / (1.0f + expf(x));
-    const float mod = (GAMMA_MODE == 0) ? q * q : powf(q, gamma);
-    return mod * nlpt;
-}
-
-__device__ __forceinline__ float smooth_l1_value(float p, float t) {
-    const float d = fabsf(p - t);
-    return d < 1.0f ? 0.5f * d * d : d - 0.5f;
-}
-
-__device__ __forceinline__ float smooth_l1_grad(float p, float t) {
-    const float d = p - t;
-    return (fabsf(d) < 1.0f) ? d : ((d > 0.0f) ? 1.0f : ((d < 0.0f) ? -1.0f : 0.0f));
-}
+#include "focal_math.cuh"
 
 // WITH_LOSS: the same pass also accumulates the un-normalised loss sums (forward + backward in one read of the logits);
 // `norm_count` then is the matched count obtained BEFORE the pass (ssdk_count_matches, all-reduced on several GPUs).

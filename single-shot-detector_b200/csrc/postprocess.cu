@@ -21,6 +21,7 @@
 //                         matrix is built in parallel and walked greedily by one thread; stops at K.
 //   4. pack_kernel        class-major concatenation, zero padding to C*K and num_boxes (nms.py:83-93).
 #include <cooperative_groups.h>
+#include <string.h>
 
 #include "common.cuh"
 
@@ -151,6 +152,114 @@ __global__ void __launch_bounds__(FILTER_THREADS) filter_kernel(
     }
 }
 
+// Same scan over the per-level head tensors (head-layout fusion, see head.cu): every level's class tensor
+// [B, n*C, h, w] (or [B, h, w, n*C]) is streamed as ONE flat array; only a candidate pays for the index arithmetic that
+// recovers (image, anchor, class) from its flat position.  A 1-D grid walks 4096-float chunks of all levels.
+#define HFILTER_CHUNK4 (FILTER_THREADS * FILTER_UNROLL)
+struct HeadFilterSegs {
+    long long chunk0[SSDK_MAX_LEVELS + 1];   // prefix sums of the per-level chunk counts
+    long long count[SSDK_MAX_LEVELS];        // floats per level
+};
+
+__device__ __forceinline__ void head_decompose(const HeadGeom& G, int l, long long e, int& b, int& a, int& c) {
+    const int hw = G.hw[l], n = G.per_loc, C = G.C;
+    const long long per_image = (long long)n * C * hw;
+    b = (int)(e / per_image);
+    const int r = (int)(e - (long long)b * per_image);
+    int loc, q;
+    if (G.channels_first) { q = r / hw; loc = r - q * hw; }
+    else { loc = r / (n * C); q = r - loc * (n * C); }
+    const int k = q / C;
+    c = q - k * C;
+    a = G.anchor_off[l] + loc * n + k;
+}
+
+template <bool IS_LOGITS>
+__global__ void __launch_bounds__(FILTER_THREADS) head_filter_kernel(const HeadGeom G, const HeadFilterSegs S, float thr, float x_lo,
+                                                                    KeyFormat fmt, unsigned long long* __restrict__ cand,
+                                                                    long long cap, int* __restrict__ counts) {
+    const int lane = threadIdx.x & 31;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    const long long total = S.chunk0[G.num_levels];
+    int l = 0;
+    for (long long g = blockIdx.x; g < total; g += gridDim.x) {
+        while (g >= S.chunk0[l + 1]) ++l;
+        const long long n = S.count[l], n4 = n >> 2;
+        const float4* body = (const float4*)G.cls[l];
+        const long long i0 = (g - S.chunk0[l]) * HFILTER_CHUNK4;
+        float4 v[FILTER_UNROLL];
+        bool inb[FILTER_UNROLL];
+#pragma unroll
+        for (int u = 0; u < FILTER_UNROLL; ++u) {
+            const long long i = i0 + u * FILTER_THREADS + threadIdx.x;
+            inb[u] = i < n4;
+            v[u] = inb[u] ? ld_stream_f4(body + i) : make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+        }
+#pragma unroll
+        for (int u = 0; u < FILTER_UNROLL; ++u) {
+            const float lim = IS_LOGITS ? x_lo : thr;
+            const float mx = fmaxf(fmaxf(v[u].x, v[u].y), fmaxf(v[u].z, v[u].w));
+            const bool maybe = inb[u] && (mx > lim);
+            if (!__any_sync(0xffffffffu, maybe)) continue;            // warp-uniform fast path
+            const float vals[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+            const long long e0 = (i0 + u * FILTER_THREADS + threadIdx.x) << 2;
+            // the warp's 128 consecutive floats normally belong to one image: one aggregated atomic per warp
+            const long long per_image = (long long)G.per_loc * G.C * G.hw[l];
+            const long long w0 = (i0 + u * FILTER_THREADS + (threadIdx.x & ~31)) << 2;
+            const int b_first = (int)(w0 / per_image);
+            const bool one_image = (w0 + 127) / per_image == b_first;
+            float sc[4];
+            unsigned bal[4];
+            bool hit[4];
+            int totalhits = 0;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                hit[j] = maybe && is_candidate<IS_LOGITS>(vals[j], thr, x_lo, &sc[j]);
+                bal[j] = __ballot_sync(0xffffffffu, hit[j]);
+                totalhits += __popc(bal[j]);
+            }
+            if (totalhits == 0) continue;
+            if (one_image) {
+                int basepos = 0;
+                if (lane == 0) basepos = atomicAdd(counts + b_first, totalhits);
+                basepos = __shfl_sync(0xffffffffu, basepos, 0);
+                int run = 0;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    if (hit[j]) {
+                        int b, a, c;
+                        head_decompose(G, l, e0 + j, b, a, c);
+                        const long long pos = (long long)basepos + run + __popc(bal[j] & lt_mask);
+                        if (pos < cap) cand[(size_t)b * cap + pos] = make_key(c, sc[j], a, fmt);
+                    }
+                    run += __popc(bal[j]);
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    if (hit[j]) {
+                        int b, a, c;
+                        head_decompose(G, l, e0 + j, b, a, c);
+                        const int pos = atomicAdd(counts + b, 1);
+                        if (pos < cap) cand[(size_t)b * cap + pos] = make_key(c, sc[j], a, fmt);
+                    }
+                }
+            }
+        }
+        // the (< 4) floats of a level beyond its last float4, with the level's last chunk
+        if (g + 1 == S.chunk0[l + 1] && threadIdx.x < (int)(n & 3)) {
+            const long long e = (n & ~3ll) + threadIdx.x;
+            float s;
+            if (is_candidate<IS_LOGITS>(G.cls[l][e], thr, x_lo, &s)) {
+                int b, a, c;
+                head_decompose(G, l, e, b, a, c);
+                const int pos = atomicAdd(counts + b, 1);
+                if (pos < cap) cand[(size_t)b * cap + pos] = make_key(c, s, a, fmt);
+            }
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------------------------- 2. sort
 __device__ __forceinline__ void mark_segments(const unsigned long long* keys, long long i, long long n, KeyFormat fmt,
                                               int* seg_start, int* seg_end) {
@@ -238,6 +347,16 @@ __global__ void __launch_bounds__(SORT_THREADS) sort_kernel(unsigned long long* 
 }
 
 // ---------------------------------------------------------------------------------------------- 3. NMS
+// Where the four box codes of (image b, anchor a) live: the anchor-major tensor [B,A,4], or the per-level head tensors.
+struct CodeView {
+    const float4* flat;      // [B,A,4] or nullptr (then `head` is used)
+    HeadGeom head;
+};
+__device__ __forceinline__ float4 load_code(const CodeView& cv, int b, long long A, int a) {
+    if (cv.flat) return cv.flat[(size_t)b * A + a];
+    return head_load_code(cv.head, b, a);
+}
+
 struct NmsBox {          // corners min/max-normalised as NonMaxSuppressionV3 does; area <= 0 never suppresses
     float ymin, xmin, ymax, xmax;
 };
@@ -272,7 +391,7 @@ __device__ __forceinline__ bool nms_exact(const NmsBox a, float area_a, const Nm
 template <bool DECODED>
 __global__ void __launch_bounds__(NMS_SMALL_WARPS * 32) nms_small_kernel(
     const unsigned long long* __restrict__ cand, long long cap, KeyFormat fmt, const int* __restrict__ seg_start,
-    const int* __restrict__ seg_end, const float4* __restrict__ codes, const float4* __restrict__ anchors, long long A,
+    const int* __restrict__ seg_end, const CodeView codes, const float4* __restrict__ anchors, long long A,
     long long nseg, int C, int K, float iou_thr, float4* __restrict__ seg_box, float* __restrict__ seg_score,
     int* __restrict__ seg_anchor, int* __restrict__ seg_kept, int* __restrict__ heavy_queue, int* __restrict__ heavy_count) {
     __shared__ NmsBox s_tile[NMS_SMALL_WARPS][32];
@@ -302,8 +421,8 @@ __global__ void __launch_bounds__(NMS_SMALL_WARPS * 32) nms_small_kernel(
         const unsigned long long key = cand[(size_t)b * cap + start + lane];
         a = key_anchor(key, fmt);
         score = key_score(key, fmt);
-        if (DECODED) raw = codes[(size_t)b * A + a];
-        else raw = box_clip01(box_decode(codes[(size_t)b * A + a], anchors[a]));            // nms.py:76-77
+        raw = load_code(codes, b, A, a);
+        if (!DECODED) raw = box_clip01(box_decode(raw, anchors[a]));                         // nms.py:76-77
         box.ymin = fminf(raw.x, raw.z); box.xmin = fminf(raw.y, raw.w);
         box.ymax = fmaxf(raw.x, raw.z); box.xmax = fmaxf(raw.y, raw.w);
         area = f_mul(f_sub(box.ymax, box.ymin), f_sub(box.xmax, box.xmin));
@@ -351,7 +470,7 @@ __global__ void __launch_bounds__(NMS_SMALL_WARPS * 32) nms_small_kernel(
 template <bool DECODED>
 __global__ void __launch_bounds__(NMS_THREADS) nms_kernel(
     const unsigned long long* __restrict__ cand, long long cap, KeyFormat fmt, const int* __restrict__ seg_start,
-    const int* __restrict__ seg_end, const float4* __restrict__ codes, const float4* __restrict__ anchors, long long A,
+    const int* __restrict__ seg_end, const CodeView codes, const float4* __restrict__ anchors, long long A,
     long long nseg, int C, int K, float iou_thr, float4* __restrict__ seg_box, float* __restrict__ seg_score,
     int* __restrict__ seg_anchor, int* __restrict__ seg_kept, const int* __restrict__ heavy_queue,
     const int* __restrict__ heavy_count) {
@@ -386,7 +505,7 @@ __global__ void __launch_bounds__(NMS_THREADS) nms_kernel(
             if (i < n) {
                 nkey = keys[i];
                 const int na = key_anchor(nkey, fmt);
-                ncode = codes[(size_t)b * A + na];
+                ncode = load_code(codes, b, A, na);
                 if (!DECODED) nanc = anchors[na];
             }
         };
@@ -567,7 +686,7 @@ static int bits_for(long long n) {   // bits needed to represent values in [0, n
 
 static bool aligned16(const void* p) { return ((uintptr_t)p & 15) == 0; }
 
-static int postprocess_impl(ssdk_ctx* ctx, const float* codes, const float* anchors, const float* scores, int flags,
+static int postprocess_impl(ssdk_ctx* ctx, const HeadGeom* head, const float* codes, const float* anchors, const float* scores, int flags,
                             int B, int64_t A, int C, double score_threshold, double iou_threshold, int K,
                             const float* box_scaler, double final_score_threshold,
                             float* out_boxes, float* out_scores, int32_t* out_classes, int32_t* out_num,
@@ -580,7 +699,9 @@ static int postprocess_impl(ssdk_ctx* ctx, const float* codes, const float* anch
     SSDK_REQUIRE(out_boxes && out_scores && out_classes && out_num, SSDK_ERR_ARG, "ssdk_postprocess: null output");
     const bool decoded = (flags & SSDK_BOXES_DECODED) != 0;
     const bool is_logits = (flags & SSDK_INPUT_LOGITS) != 0;
-    SSDK_REQUIRE(A == 0 || (codes && scores && (decoded || anchors)), SSDK_ERR_ARG, "ssdk_postprocess: null input");
+    SSDK_REQUIRE(A == 0 || head || (codes && scores), SSDK_ERR_ARG, "ssdk_postprocess: null input");
+    SSDK_REQUIRE(A == 0 || decoded || anchors, SSDK_ERR_ARG, "ssdk_postprocess: null anchors");
+    SSDK_REQUIRE(!(head && decoded), SSDK_ERR_ARG, "ssdk_head_detect: head tensors hold encoded boxes");
     SSDK_REQUIRE(aligned16(codes) && aligned16(anchors) && aligned16(out_boxes), SSDK_ERR_SHAPE,
                  "ssdk_postprocess: box arrays must be 16-byte aligned");
     SSDK_REQUIRE(((uintptr_t)scores & 3) == 0, SSDK_ERR_SHAPE, "ssdk_postprocess: scores must be 4-byte aligned");
@@ -627,16 +748,35 @@ static int postprocess_impl(ssdk_ctx* ctx, const float* codes, const float* anch
                 x_lo = (float)(lg - 1e-3 * (1.0 + fabs(lg)));
             }
         }
-        long long chunks = (per_image / 4 + FILTER_THREADS * FILTER_UNROLL - 1) / (FILTER_THREADS * FILTER_UNROLL);
-        long long gx = ((long long)ctx->num_sms * 16 + B - 1) / B;
-        if (gx > chunks) gx = chunks;
-        if (gx < 1) gx = 1;
-        const dim3 fgrid((unsigned)gx, B);
-        SSDK_KERNEL(ctx, SSDK_K_FILTER,
-            if (is_logits)
-                filter_kernel<true><<<fgrid, FILTER_THREADS, 0, ctx->stream>>>(scores, per_image, C, thr, x_lo, fmt, cand, cap, counts);
-            else
-                filter_kernel<false><<<fgrid, FILTER_THREADS, 0, ctx->stream>>>(scores, per_image, C, thr, x_lo, fmt, cand, cap, counts));
+        if (head) {
+            HeadFilterSegs S;
+            long long nchunks = 0;
+            for (int l = 0; l < SSDK_MAX_LEVELS; ++l) {
+                S.chunk0[l] = nchunks;
+                S.count[l] = (long long)B * head->per_loc * C * head->hw[l];
+                if (l < head->num_levels) nchunks += (S.count[l] + 4 * HFILTER_CHUNK4 - 1) / (4 * HFILTER_CHUNK4);
+            }
+            S.chunk0[SSDK_MAX_LEVELS] = nchunks;
+            long long gx = (long long)ctx->num_sms * 16;
+            if (gx > nchunks) gx = nchunks;
+            if (gx < 1) gx = 1;
+            SSDK_KERNEL(ctx, SSDK_K_FILTER,
+                if (is_logits)
+                    head_filter_kernel<true><<<(unsigned)gx, FILTER_THREADS, 0, ctx->stream>>>(*head, S, thr, x_lo, fmt, cand, cap, counts);
+                else
+                    head_filter_kernel<false><<<(unsigned)gx, FILTER_THREADS, 0, ctx->stream>>>(*head, S, thr, x_lo, fmt, cand, cap, counts));
+        } else {
+            long long chunks = (per_image / 4 + FILTER_THREADS * FILTER_UNROLL - 1) / (FILTER_THREADS * FILTER_UNROLL);
+            long long gx = ((long long)ctx->num_sms * 16 + B - 1) / B;
+            if (gx > chunks) gx = chunks;
+            if (gx < 1) gx = 1;
+            const dim3 fgrid((unsigned)gx, B);
+            SSDK_KERNEL(ctx, SSDK_K_FILTER,
+                if (is_logits)
+                    filter_kernel<true><<<fgrid, FILTER_THREADS, 0, ctx->stream>>>(scores, per_image, C, thr, x_lo, fmt, cand, cap, counts);
+                else
+                    filter_kernel<false><<<fgrid, FILTER_THREADS, 0, ctx->stream>>>(scores, per_image, C, thr, x_lo, fmt, cand, cap, counts));
+        }
 
         // 2. sort (+ segment table)
         const size_t sort_smem = (size_t)SORT_SMEM_KEYS * sizeof(unsigned long long);
@@ -669,7 +809,10 @@ static int postprocess_impl(ssdk_ctx* ctx, const float* codes, const float* anch
         const int sgrid_nms = ceil_div_i(nseg, NMS_SMALL_WARPS);
         long long hgrid = (long long)ctx->num_sms * 4;
         if (hgrid > nseg) hgrid = nseg;
-        const float4* c4 = (const float4*)codes;
+        CodeView c4;
+        c4.flat = head ? nullptr : (const float4*)codes;
+        if (head) c4.head = *head;
+        else memset(&c4.head, 0, sizeof(c4.head));
         const float4* a4 = (const float4*)anchors;
         const float iou_f = (float)iou_threshold;
         const int nms_slot = ctx->profiling ? ssdk_prof_begin(ctx, SSDK_K_NMS) : -1;
@@ -706,7 +849,7 @@ extern "C" int ssdk_postprocess(ssdk_ctx* ctx, const float* codes, const float* 
                                 int B, int64_t A, int C, double score_threshold, double iou_threshold, int K,
                                 float* out_boxes, float* out_scores, int32_t* out_classes, int32_t* out_num,
                                 int32_t* out_anchor_idx) {
-    return postprocess_impl(ctx, codes, anchors, scores, flags, B, A, C, score_threshold, iou_threshold, K, nullptr,
+    return postprocess_impl(ctx, nullptr, codes, anchors, scores, flags, B, A, C, score_threshold, iou_threshold, K, nullptr,
                             -INFINITY, out_boxes, out_scores, out_classes, out_num, out_anchor_idx);
 }
 
@@ -715,6 +858,17 @@ extern "C" int ssdk_detect(ssdk_ctx* ctx, const float* codes, const float* ancho
                            double final_score_threshold, float* out_boxes, float* out_scores, int32_t* out_classes,
                            int32_t* out_num) {
     SSDK_REQUIRE(box_scaler == nullptr || aligned16(box_scaler), SSDK_ERR_SHAPE, "ssdk_detect: box_scaler must be 16-byte aligned");
-    return postprocess_impl(ctx, codes, anchors, scores, flags, B, A, C, score_threshold, iou_threshold, K, box_scaler,
+    return postprocess_impl(ctx, nullptr, codes, anchors, scores, flags, B, A, C, score_threshold, iou_threshold, K, box_scaler,
                             final_score_threshold, out_boxes, out_scores, out_classes, out_num, nullptr);
+}
+
+extern "C" int ssdk_head_detect(ssdk_ctx* ctx, const ssdk_head* head, const float* anchors, int flags, int B, int64_t A, int C,
+                                double score_threshold, double iou_threshold, int K, const float* box_scaler,
+                                double final_score_threshold, float* out_boxes, float* out_scores, int32_t* out_classes,
+                                int32_t* out_num, int32_t* out_anchor_idx) {
+    SSDK_REQUIRE(box_scaler == nullptr || aligned16(box_scaler), SSDK_ERR_SHAPE, "ssdk_head_detect: box_scaler must be 16-byte aligned");
+    HeadGeom G;
+    SSDK_TRY(ssdk_head_geom(head, B, A, C, true, true, &G));
+    return postprocess_impl(ctx, &G, nullptr, anchors, nullptr, flags & SSDK_INPUT_LOGITS, B, A, C, score_threshold, iou_threshold, K,
+                            box_scaler, final_score_threshold, out_boxes, out_scores, out_classes, out_num, out_anchor_idx);
 }

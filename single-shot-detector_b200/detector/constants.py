@@ -4,6 +4,9 @@
 MIN_LEVEL = 3
 DIVISOR = 128                                   # constants.py:7
 
+# layout of the per-level tower outputs consumed by box_predictor.reshape_and_concatenate (constants.py:9)
+DATA_FORMAT = 'channels_first'
+
 EPSILON = 1e-8                                  # constants.py:12 (compiled into the kernels as SSDK_EPS)
 SCALE_FACTORS = [10.0, 10.0, 5.0, 5.0]          # constants.py:15 (compiled into box_encode / box_decode)
 

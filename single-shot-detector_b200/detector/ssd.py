@@ -1,11 +1,14 @@
 """SSD head with the reference's interface (detector/ssd.py): anchors + raw predictions in, losses or
 detections out.  The network (feature extractor, box predictor) is NOT part of this package: any callables
 producing `encoded_boxes` [B,A,4] and `class_predictions` [B,A,C] (layout of box_predictor.py:67-104) plug in."""
+import ctypes
+
 import numpy as np
 import torch
 
 from .. import _lib
 from .._tensors import Call, ptr
+from .box_predictor import HeadPredictions
 from .constants import MIN_LEVEL, NEGATIVES_THRESHOLD, POSITIVES_THRESHOLD  # noqa: F401
 from .training_target_creation import batch_training_targets
 from .utils.nms import batch_multiclass_non_max_suppression
@@ -34,6 +37,24 @@ class _SSDLossFunction(torch.autograd.Function):
         return grads['class_predictions'], grads['encoded_boxes'], None, None, None
 
 
+class _SSDHeadLossFunction(torch.autograd.Function):
+    """SSD.loss on per-level head tensors as a differentiable torch op (gradients per level, in the head's layout)."""
+
+    @staticmethod
+    def forward(ctx, head, groundtruth, params, *levels):
+        losses = head._loss_forward(groundtruth, params, keep_targets=True)
+        ctx.head = head
+        ctx.saved = head._saved
+        return torch.stack([losses['localization_loss'], losses['classification_loss']])
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        head = ctx.head
+        head._saved = ctx.saved
+        grads = head.loss_backward(grad_out.contiguous())
+        return (None, None, None) + tuple(grads['class_predictions']) + tuple(grads['encoded_boxes'])
+
+
 class SSD:
     def __init__(self, images, feature_extractor, anchor_generator, box_predictor, num_classes):
         """Same arguments as the reference (ssd.py:10-40).  `images`: [B, H, W, 3] tensor (only its shape is
@@ -42,8 +63,11 @@ class SSD:
         image_features = feature_extractor(images)
         image_height, image_width = int(images.shape[1]), int(images.shape[2])           # ssd.py:28-29
         self.raw_predictions = box_predictor(image_features)                               # ssd.py:37
-        device = self.raw_predictions['class_predictions'].device \
-            if isinstance(self.raw_predictions['class_predictions'], torch.Tensor) else None
+        if isinstance(self.raw_predictions, HeadPredictions):          # per-level tower outputs, consumed as they are
+            device = self.raw_predictions.device
+        else:
+            device = self.raw_predictions['class_predictions'].device \
+                if isinstance(self.raw_predictions['class_predictions'], torch.Tensor) else None
         self.anchors = anchor_generator(image_height, image_width,
                                         device=device if device is not None and device.type == 'cuda' else None)  # ssd.py:31
         self.num_anchors_per_feature_map = anchor_generator.num_anchors_per_feature_map   # ssd.py:35
@@ -57,8 +81,30 @@ class SSD:
         fake_images = _ShapeOnly(shape)
         return cls(fake_images, lambda x: None, anchor_generator, lambda f: raw_predictions, num_classes)
 
+    @classmethod
+    def from_head_outputs(cls, image_height, image_width, encoded_boxes_levels, class_predictions_levels, anchor_generator,
+                          num_classes, data_format=None):
+        """Head-layout fusion: the per-level tower outputs ([B, n*4, h_i, w_i] / [B, n*C, h_i, w_i] for 'channels_first')
+        are consumed directly; reshape_and_concatenate (box_predictor.py:67-104) never runs."""
+        head = HeadPredictions(encoded_boxes_levels, class_predictions_levels, num_classes,
+                               anchor_generator.num_anchors_per_location, data_format)
+        fake_images = _ShapeOnly((head.batch_size, int(image_height), int(image_width), 3))
+        return cls(fake_images, lambda x: None, anchor_generator, lambda f: head, num_classes)
+
+    def _head(self):
+        """The HeadPredictions view when the box predictor returned one (and the shapes agree with the anchors)."""
+        h = self.raw_predictions
+        if not isinstance(h, HeadPredictions):
+            return None
+        if h.num_anchors != int(self.anchors.shape[0]) or h.num_classes != int(self.num_classes):
+            raise ValueError('head outputs hold %d anchors x %d classes, the anchor generator made %d anchors, num_classes=%d'
+                             % (h.num_anchors, h.num_classes, int(self.anchors.shape[0]), int(self.num_classes)))
+        return h
+
     # ------------------------------------------------------------------ host (NumPy) buffers
     def _host_mode(self):
+        if isinstance(self.raw_predictions, HeadPredictions):
+            return False
         return isinstance(self.raw_predictions['class_predictions'], np.ndarray)
 
     def _host_args(self):
@@ -115,12 +161,38 @@ class SSD:
         if self._host_mode():
             assert box_scaler is None and final_score_threshold is None, 'extensions need device tensors' 
             return self._get_predictions_host(score_threshold, iou_threshold, max_boxes_per_class, out)
+        head = self._head()
+        if head is not None:
+            return self._get_predictions_head(head, score_threshold, iou_threshold, max_boxes_per_class, box_scaler,
+                                              final_score_threshold)
         boxes, scores, classes, num = batch_multiclass_non_max_suppression(
             self.raw_predictions['encoded_boxes'], self.anchors, self.raw_predictions['class_predictions'],
             score_threshold=score_threshold, iou_threshold=iou_threshold,
             max_boxes_per_class=max_boxes_per_class, scores_are_logits=True,
             box_scaler=box_scaler, final_score_threshold=final_score_threshold)
         return {'boxes': boxes, 'labels': classes, 'scores': scores, 'num_boxes': num}
+
+    def _get_predictions_head(self, head, score_threshold, iou_threshold, max_boxes_per_class, box_scaler=None,
+                              final_score_threshold=None, return_anchor_indices=False):
+        """get_predictions straight from the per-level tower outputs (ssdk_head_detect): the threshold scan streams every
+        level's class tensor in place, the NMS stages gather the few box codes they need through the head geometry."""
+        call = Call(head.device)
+        B, A, C, K = head.batch_size, head.num_anchors, head.num_classes, int(max_boxes_per_class)
+        anchors = call.tensor(self.anchors, torch.float32, (A, 4))
+        boxes, scores = call.empty([B, C * K, 4], torch.float32), call.empty([B, C * K], torch.float32)
+        classes, num = call.empty([B, C * K], torch.int32), call.empty([B], torch.int32)
+        aidx = call.empty([B, C * K], torch.int32) if return_anchor_indices else None
+        sc = None if box_scaler is None else call.tensor(box_scaler, torch.float32, (B, 4))
+        thr2 = float('-inf') if final_score_threshold is None else float(final_score_threshold)
+        d = head.descriptor()
+        _lib.check(_lib.load().ssdk_head_detect(
+            call.ctx(), ctypes.byref(d), ptr(anchors), _lib.SSDK_INPUT_LOGITS, B, A, C, float(score_threshold),
+            float(iou_threshold), K, ptr(sc), thr2, ptr(boxes), ptr(scores), ptr(classes), ptr(num), ptr(aidx)))
+        self._call_pp = call
+        out = {'boxes': boxes, 'labels': classes, 'scores': scores, 'num_boxes': num}
+        if return_anchor_indices:
+            out['anchor_indices'] = aidx
+        return out
 
     def detect(self, score_threshold=0.1, box_scaler=None, nms_score_threshold=0.05, iou_threshold=0.5, max_boxes_per_class=20):
         """What inference/detector.py:36-60 returns for a batch of one image: (boxes [N,4], labels [N], scores [N]) with
@@ -135,6 +207,9 @@ class SSD:
         """Un-normalised shard sums: float64 CUDA tensor [3] = (sum loc_losses, sum cls_losses, num_matches).
         With per_anchor=True also returns the tensors the reference's summaries consume (ssd.py:125-129)."""
         from . import ssd as this_module      # thresholds are module constants, as in ssd.py:187-188
+        head = self._head()
+        if head is not None and not per_anchor:
+            return self._loss_sums_head(head, groundtruth, params, keep_targets)
         call = Call()
         logits = call.tensor(self.raw_predictions['class_predictions'], torch.float32)
         B, A, C = logits.shape
@@ -163,6 +238,43 @@ class SSD:
                                **{k: extra[k] for k in ('reg_targets', 'cls_targets', 'matches')})
         return (sums, extra) if per_anchor else sums
 
+    def _targets_into(self, call, groundtruth, B, A):
+        """ssd.py:84 for a batch: (reg_targets, cls_targets, matches) as fresh tensors of `call`."""
+        from . import ssd as this_module
+        anchors = call.tensor(self.anchors, torch.float32, (A, 4))
+        gt = call.tensor(groundtruth['boxes'], torch.float32)
+        G = gt.shape[1]
+        labels = call.tensor(groundtruth['labels'], torch.int32, (B, G))
+        num = call.tensor(groundtruth['num_boxes'], torch.int32, (B,))
+        reg, cls_t, matches = call.empty([B, A, 4], torch.float32), call.empty([B, A], torch.int32), call.empty([B, A], torch.int32)
+        _lib.check(_lib.load().ssdk_training_targets(
+            call.ctx(), ptr(anchors), A, ptr(gt), ptr(labels), ptr(num), B, G, float(this_module.POSITIVES_THRESHOLD),
+            float(this_module.NEGATIVES_THRESHOLD), ptr(reg), ptr(cls_t), ptr(matches)))
+        return reg, cls_t, matches
+
+    def _loss_sums_head(self, head, groundtruth, params, keep_targets):
+        """loss_sums on the per-level tower outputs: targets (ssd.py:84), then ssdk_head_ssd_loss."""
+        call = Call(head.device)
+        B, A, C = head.batch_size, head.num_anchors, head.num_classes
+        reg, cls_t, matches = self._targets_into(call, groundtruth, B, A)
+        sums = call.empty([3], torch.float64)
+        d = head.descriptor()
+        _lib.check(_lib.load().ssdk_head_ssd_loss(call.ctx(), ctypes.byref(d), ptr(reg), ptr(cls_t), ptr(matches), B, A, C,
+                                                  float(params['gamma']), float(params['alpha']), ptr(sums)))
+        self._call = call
+        if keep_targets:
+            self._saved = dict(head=head, sums=sums, gamma=float(params['gamma']), alpha=float(params['alpha']),
+                               reg_targets=reg, cls_targets=cls_t, matches=matches)
+        return sums
+
+    def _head_grads(self, call, head):
+        g_cls = [call.empty(list(t.shape), torch.float32) for t in head.class_predictions_levels]
+        g_box = [call.empty(list(t.shape), torch.float32) for t in head.encoded_boxes_levels]
+        gd = _lib.SsdkHeadGrads()
+        for l in range(len(g_cls)):
+            gd.class_predictions[l], gd.encoded_boxes[l] = g_cls[l].data_ptr(), g_box[l].data_ptr()
+        return g_cls, g_box, gd
+
     def loss(self, groundtruth, params):
         """Returns {'localization_loss', 'classification_loss'}: two float32 scalars (0-d CUDA tensors), each
         sum / max(num_matches, 1) (ssd.py:121-133).  When `self.process_group` is set the three sums are
@@ -178,6 +290,13 @@ class SSD:
                 losses = np.array([sums[0] / norm, sums[1] / norm], np.float32)
             self.num_matches = sums[2]
             return {'localization_loss': losses[0], 'classification_loss': losses[1]}
+        head = self._head()
+        if head is not None:
+            levels = head.class_predictions_levels + head.encoded_boxes_levels
+            if torch.is_grad_enabled() and any(t.requires_grad for t in levels):
+                out = _SSDHeadLossFunction.apply(self, groundtruth, params, *levels)          # differentiable (model.py:115-118)
+                return {'localization_loss': out[0], 'classification_loss': out[1]}
+            return self._loss_forward(groundtruth, params, keep_targets=False)
         logits_in, codes_in = self.raw_predictions['class_predictions'], self.raw_predictions['encoded_boxes']
         if torch.is_grad_enabled() and isinstance(logits_in, torch.Tensor) and (logits_in.requires_grad or codes_in.requires_grad):
             out = _SSDLossFunction.apply(logits_in, codes_in, self, groundtruth, params)      # differentiable (model.py:115-118)
@@ -207,6 +326,21 @@ class SSD:
         sv = getattr(self, '_saved', None)
         if sv is None:
             raise RuntimeError('loss_backward() needs a preceding loss_with_gradients() or differentiable loss() call')
+        if 'head' in sv:
+            head = sv['head']
+            call = Call(head.device)
+            up = None
+            if upstream is not None:
+                up = call.tensor(upstream, torch.float32, (2,)) if isinstance(upstream, torch.Tensor) else \
+                    torch.tensor([float(upstream[0]), float(upstream[1])], dtype=torch.float32, device=head.device)
+            g_cls, g_box, gd = self._head_grads(call, head)
+            d = head.descriptor()
+            _lib.check(_lib.load().ssdk_head_ssd_loss_forward_backward(
+                call.ctx(), ctypes.byref(d), ptr(sv['reg_targets']), ptr(sv['cls_targets']), ptr(sv['matches']),
+                head.batch_size, head.num_anchors, head.num_classes, sv['gamma'], sv['alpha'], sv['sums'].data_ptr() + 16,
+                ptr(up), None, ctypes.byref(gd)))
+            self._call_bw = (call, up)
+            return {'class_predictions': g_cls, 'encoded_boxes': g_box}
         logits, codes = sv['logits'], sv['codes']
         B, A, C = logits.shape
         call = Call(logits.device)
@@ -230,6 +364,9 @@ class SSD:
         if not fused:
             losses = self._loss_forward(groundtruth, params, keep_targets=True)
             return losses, self.loss_backward(upstream)
+        head = self._head()
+        if head is not None:
+            return self._loss_with_gradients_head(head, groundtruth, params, upstream)
         from . import ssd as this_module
         lib = _lib.load()
         call = Call()
@@ -269,6 +406,71 @@ class SSD:
                            reg_targets=reg, cls_targets=cls_t, matches=matches)
         return ({'localization_loss': out[0], 'classification_loss': out[1]},
                 {'class_predictions': g_logits, 'encoded_boxes': g_codes})
+
+    def _loss_with_gradients_head(self, head, groundtruth, params, upstream):
+        """Fused training step on the per-level tower outputs: targets -> count (all-reduced) -> ONE pass over every level's
+        logits that yields the loss sums and the gradients in the head's own layout (ssdk_head_ssd_loss_forward_backward)."""
+        lib = _lib.load()
+        call = Call(head.device)
+        B, A, C = head.batch_size, head.num_anchors, head.num_classes
+        reg, cls_t, matches = self._targets_into(call, groundtruth, B, A)
+        count, sums, out = call.empty([1], torch.float64), call.empty([3], torch.float64), call.empty([2], torch.float32)
+        g_cls, g_box, gd = self._head_grads(call, head)
+        up = None
+        if upstream is not None:
+            up = call.tensor(upstream, torch.float32, (2,)) if isinstance(upstream, torch.Tensor) else \
+                torch.tensor([float(upstream[0]), float(upstream[1])], dtype=torch.float32, device=head.device)
+        ctx = call.ctx()
+        _lib.check(lib.ssdk_count_matches(ctx, ptr(matches), B * A, ptr(count)))                       # ssd.py:121-122
+        group = None if self.process_group in (None, True) else self.process_group
+        if self.process_group is not None:
+            import torch.distributed as dist
+            dist.all_reduce(count, op=dist.ReduceOp.SUM, group=group)
+        d = head.descriptor()
+        _lib.check(lib.ssdk_head_ssd_loss_forward_backward(
+            ctx, ctypes.byref(d), ptr(reg), ptr(cls_t), ptr(matches), B, A, C, float(params['gamma']), float(params['alpha']),
+            ptr(count), ptr(up), ptr(sums), ctypes.byref(gd)))
+        if self.process_group is not None:
+            dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=group)
+        _lib.check(lib.ssdk_loss_finalize(ctx, ptr(sums), ptr(out)))
+        self.num_matches = sums[2]
+        self._call = call
+        self._saved = dict(head=head, sums=sums, gamma=float(params['gamma']), alpha=float(params['alpha']),
+                           reg_targets=reg, cls_targets=cls_t, matches=matches)
+        return ({'localization_loss': out[0], 'classification_loss': out[1]},
+                {'class_predictions': g_cls, 'encoded_boxes': g_box})
+
+    def level_summaries(self, cls_losses=None, loc_losses=None, matches=None, top_fraction=0.20):
+        """The quantities behind the reference's loss summaries (ssd.py:125-129,135-163), from the per-anchor vectors that
+        `loss_sums(..., per_anchor=True)` returns.  For each given loss vector [B,A]: per image and FPN level the mean of the
+        ceil(top_fraction * n_level) biggest values ('topk_mean', [B,L]) and the smallest of them ('topk_kth'), plus
+        'histogram_mean' [L] = the mean of the vector the reference histograms (tf.reduce_mean(biggest_values, axis=0));
+        for `matches`: 'matches' [B,L], 'mean_matches_per_image_on_level' [L] and 'total_mean_matches_per_image'."""
+        out = {}
+        per_level = np.asarray(self.num_anchors_per_feature_map, np.int32)
+        L = len(per_level)
+        lib = _lib.load()
+        for name, v in (('classification_losses', cls_losses), ('localization_losses', loc_losses)):
+            if v is None:
+                continue
+            call = Call()
+            t = call.tensor(v, torch.float32)
+            B, A = t.shape
+            mean, kth = call.empty([B, L], torch.float32), call.empty([B, L], torch.float32)
+            _lib.check(lib.ssdk_level_summaries(call.ctx(), ptr(t), None, B, A, per_level.ctypes.data, L, float(top_fraction),
+                                                ptr(mean), ptr(kth), None))
+            out[name] = {'topk_mean': mean, 'topk_kth': kth, 'histogram_mean': mean.mean(dim=0)}
+        if matches is not None:
+            call = Call()
+            m = call.tensor(matches, torch.int32)
+            B, A = m.shape
+            cnt = call.empty([B, L], torch.float32)
+            _lib.check(lib.ssdk_level_summaries(call.ctx(), None, ptr(m), B, A, per_level.ctypes.data, L, float(top_fraction),
+                                                None, None, ptr(cnt)))
+            out['matches'] = cnt
+            out['mean_matches_per_image_on_level'] = cnt.mean(dim=0)                                # ssd.py:157-161
+            out['total_mean_matches_per_image'] = cnt.sum(dim=1).mean()                              # ssd.py:129
+        return out
 
     def _create_targets(self, groundtruth):
         """reference ssd.py:165-199: reg_targets [B,A,4], cls_targets [B,A], matches [B,A]."""

@@ -24,6 +24,7 @@ import tensorflow as tf  # noqa: E402  (the shim)
 assert 'tf_numpy_shim' in tf.__file__
 from detector import SSD  # noqa: E402  (reference code)
 from detector.anchor_generator import AnchorGenerator  # noqa: E402
+from detector.box_predictor import reshape_and_concatenate  # noqa: E402
 from detector.losses import focal_loss, localization_loss  # noqa: E402
 from detector.training_target_creation import create_targets, get_training_targets, match_boxes  # noqa: E402
 from detector.utils import area, batch_decode, batch_multiclass_non_max_suppression, encode, intersection, iou  # noqa: E402
@@ -247,7 +248,42 @@ def golden_postprocess():
     save('postprocess', **out)
 
 
+# ---------------------------------------------------------------- head layout (reshape_and_concatenate)
+def head_inputs(seed, B, C, n, shapes):
+    """Seeded channels_first tower outputs; regenerated identically by the tests (never stored for the big case)."""
+    rng = np.random.default_rng(seed)
+    boxes = [rng.standard_normal([B, n * 4, h, w]).astype(np.float32) for h, w in shapes]
+    classes = [rng.standard_normal([B, n * C, h, w]).astype(np.float32) for h, w in shapes]
+    return boxes, classes
+
+
+def golden_head():
+    out = {}
+    # tiny case, stored in full
+    B, C, n, shapes = 2, 3, 2, [(3, 4), (2, 2), (1, 1)]
+    boxes, classes = head_inputs(21, B, C, n, shapes)
+    r = reshape_and_concatenate([T(b) for b in boxes], [T(c) for c in classes], C, n)
+    out['tiny/params'] = np.array([B, C, n])
+    out['tiny/shapes'] = np.array(shapes)
+    for i in range(len(shapes)):
+        out['tiny/boxes%d' % i] = boxes[i]
+        out['tiny/classes%d' % i] = classes[i]
+    out['tiny/encoded_boxes'] = N(r['encoded_boxes'])
+    out['tiny/class_predictions'] = N(r['class_predictions'])
+    # the geometry of the 'losses' fixture (256x320, 6 anchors per location, 7 classes), hashes only
+    B, C, n, shapes = 3, 7, 6, [(32, 40), (16, 20), (8, 10), (4, 5), (2, 3)]
+    boxes, classes = head_inputs(22, B, C, n, shapes)
+    r = reshape_and_concatenate([T(b) for b in boxes], [T(c) for c in classes], C, n)
+    out['big/params'] = np.array([B, C, n])
+    out['big/shapes'] = np.array(shapes)
+    out['big/encoded_boxes_sha256'] = np.array(sha(N(r['encoded_boxes'])))
+    out['big/class_predictions_sha256'] = np.array(sha(N(r['class_predictions'])))
+    out['big/class_predictions_head'] = N(r['class_predictions'])[:, :40]
+    save('head', **out)
+
+
 if __name__ == '__main__':
+    golden_head()
     golden_anchors()
     golden_box_utils()
     golden_matching()

@@ -53,6 +53,22 @@ def test_header_is_plain_c():
     assert r.returncode == 0, r.stderr
 
 
+def test_ctypes_structs_match_the_c_layout(tmp_path):
+    """ssdk_head / ssdk_head_grads are passed by pointer: the ctypes mirrors must have the C compiler's layout."""
+    lib_mod = load_pkg('_lib')
+    src = ('#include <stdio.h>\n#include <stddef.h>\n#include "ssdk.h"\nint main(void) { printf("%zu %zu %zu %zu %zu %d\\n", '
+           'sizeof(ssdk_head), offsetof(ssdk_head, height), offsetof(ssdk_head, class_predictions), '
+           'offsetof(ssdk_head, encoded_boxes), sizeof(ssdk_head_grads), SSDK_MAX_LEVELS); return 0; }\n')
+    exe = str(tmp_path / 'layout')
+    r = subprocess.run(['gcc', '-std=c99', '-I', os.path.join(ROOT, 'include'), '-x', 'c', '-', '-o', exe], input=src, text=True,
+                       capture_output=True)
+    assert r.returncode == 0, r.stderr
+    got = [int(v) for v in subprocess.run([exe], capture_output=True, text=True).stdout.split()]
+    H, G = lib_mod.SsdkHead, lib_mod.SsdkHeadGrads
+    assert got == [ctypes.sizeof(H), H.height.offset, H.class_predictions.offset, H.encoded_boxes.offset, ctypes.sizeof(G),
+                   lib_mod.SSDK_MAX_LEVELS]
+
+
 def test_host_only_entry_points_and_error_reporting():
     """ssdk_num_anchors is pure shape arithmetic (anchor_generator.py:59-62) and needs no GPU; a compute entry point
     without a device must fail loudly with a message, never fall back."""
@@ -107,6 +123,7 @@ REFERENCE_SURFACE = {
     'multiclass_non_max_suppression': (['boxes', 'scores', 'score_threshold', 'iou_threshold', 'max_boxes_per_class'], {}),
     'batch_multiclass_non_max_suppression': (['encoded_boxes', 'anchors', 'scores', 'score_threshold', 'iou_threshold',
                                               'max_boxes_per_class'], {}),
+    'reshape_and_concatenate': (['encoded_boxes', 'class_predictions', 'num_classes', 'num_anchors_per_location'], {}),
 }
 
 

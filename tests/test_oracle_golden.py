@@ -222,3 +222,50 @@ def test_gradient_oracle_matches_finite_differences(syn, gamma, alpha):
             cp[b, a, k] += h; cm[b, a, k] -= h
             fd = (total(x64, cp) - total(x64, cm)) / (2 * h)
             assert abs(fd - g['encoded_boxes'][b, a, k]) <= 1e-6 * abs(fd) + 3e-10
+
+
+# ---------------------------------------------------------------- head layout (box_predictor.py:67-104)
+def _head_inputs(seed, B, C, n, shapes):
+    """Same generator as tests/golden/make_golden.py::head_inputs."""
+    rng = np.random.default_rng(seed)
+    boxes = [rng.standard_normal([B, n * 4, h, w]).astype(np.float32) for h, w in shapes]
+    classes = [rng.standard_normal([B, n * C, h, w]).astype(np.float32) for h, w in shapes]
+    return boxes, classes
+
+
+def test_reshape_and_concatenate_matches_the_reference(golden):
+    from oracle import box_predictor as obp
+    g = golden('head')
+    B, C, n = [int(v) for v in g['tiny/params']]
+    shapes = [tuple(int(v) for v in s) for s in g['tiny/shapes']]
+    boxes = [g['tiny/boxes%d' % i] for i in range(len(shapes))]
+    classes = [g['tiny/classes%d' % i] for i in range(len(shapes))]
+    r = obp.reshape_and_concatenate(boxes, classes, C, n)
+    assert np.array_equal(r['encoded_boxes'], g['tiny/encoded_boxes'])
+    assert np.array_equal(r['class_predictions'], g['tiny/class_predictions'])
+    B, C, n = [int(v) for v in g['big/params']]
+    shapes = [tuple(int(v) for v in s) for s in g['big/shapes']]
+    boxes, classes = _head_inputs(22, B, C, n, shapes)
+    r = obp.reshape_and_concatenate(boxes, classes, C, n)
+    assert hashlib.sha256(r['encoded_boxes'].tobytes()).hexdigest() == str(g['big/encoded_boxes_sha256'])
+    assert hashlib.sha256(r['class_predictions'].tobytes()).hexdigest() == str(g['big/class_predictions_sha256'])
+    assert np.array_equal(r['class_predictions'][:, :40], g['big/class_predictions_head'])
+    # the inverse used to manufacture tower-shaped inputs, both data formats
+    for fmt in ('channels_first', 'channels_last'):
+        lv_b = obp.split_to_levels(r['encoded_boxes'], shapes, n, fmt)
+        lv_c = obp.split_to_levels(r['class_predictions'], shapes, n, fmt)
+        back = obp.reshape_and_concatenate(lv_b, lv_c, C, n, fmt)
+        assert np.array_equal(back['encoded_boxes'], r['encoded_boxes'])
+        assert np.array_equal(back['class_predictions'], r['class_predictions'])
+    assert all(np.array_equal(a, b) for a, b in zip(obp.split_to_levels(r['class_predictions'], shapes, n), classes))
+    assert obp.level_shapes(896, 1344, [8, 16, 32, 64, 128])[-1] == (7, 11)          # 1344/128 = 10.5 -> ceil
+
+
+def test_summary_oracle_known_answers():
+    from oracle import box_predictor as obp
+    v = np.array([[5, 1, 4, 2, 3, 9, 8, 7, 6, 0, 10, 11]], np.float32)
+    mean, kth, hist = obp.top_fraction_summaries(v, [10, 2], top_fraction=0.20)      # k = ceil(2.0) = 2, ceil(0.4) = 1
+    assert mean.tolist() == [[8.5, 11.0]] and kth.tolist() == [[8.0, 11.0]] and hist.tolist() == [8.5, 11.0]
+    m = np.array([[0, -1, 3, -2, -1, 2], [-1, -1, -1, 1, -2, -1]], np.int32)
+    per, lvl, total = obp.matches_summaries(m, [4, 2])
+    assert per.tolist() == [[2.0, 1.0], [1.0, 0.0]] and lvl.tolist() == [1.5, 0.5] and float(total) == 2.0
