@@ -29,11 +29,12 @@
 #define FLAT_CHUNK4 (FLAT_THREADS * FLAT_U)             // float4 per chunk (16 KB)
 
 struct FlatSegs {
-    int n;
+    int n;                                              // class-tensor segments [0, n); WITH_GRAD: zero-fill segments [n, 2n)
+    int nseg;                                           // n or 2n
     const float* src[SSDK_MAX_LEVELS];
-    float* dst[SSDK_MAX_LEVELS];                        // WITH_GRAD: gradient tensors, same flat indexing
-    long long count[SSDK_MAX_LEVELS];                   // floats per level (B * n*C * h*w)
-    long long chunk0[SSDK_MAX_LEVELS + 1];              // prefix sums of the per-level chunk counts
+    float* dst[2 * SSDK_MAX_LEVELS];                    // WITH_GRAD: [0,n) class gradients (same flat indexing), [n,2n) box gradients
+    long long count[2 * SSDK_MAX_LEVELS];               // floats per segment (B * n*C * h*w, resp. B * n*4 * h*w)
+    long long chunk0[2 * SSDK_MAX_LEVELS + 1];          // prefix sums of the per-segment chunk counts
 };
 
 struct HeadGradPtrs {
@@ -54,7 +55,7 @@ __global__ void __launch_bounds__(FLAT_THREADS) head_flat_kernel(const FlatSegs 
                                                                   const float* __restrict__ upstream,
                                                                   double* __restrict__ partials /*[grid]*/) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const long long total = S.chunk0[S.n];
+    const long long total = S.chunk0[S.nseg];
     const float4 ninf4 = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
     float k_neg = 0.0f;
     if (WITH_GRAD) {
@@ -68,9 +69,10 @@ __global__ void __launch_bounds__(FLAT_THREADS) head_flat_kernel(const FlatSegs 
     auto load = [&](FlatChunk& ck, long long g) {
         while (g >= S.chunk0[cursor + 1]) ++cursor;
         ck.lvl = cursor;
+        ck.i4 = (g - S.chunk0[cursor]) * FLAT_CHUNK4 + tid;
+        if (WITH_GRAD && cursor >= S.n) return;                           // zero-fill segment: nothing to read
         const long long n4 = S.count[cursor] >> 2;
         const float4* src4 = (const float4*)S.src[cursor];
-        ck.i4 = (g - S.chunk0[cursor]) * FLAT_CHUNK4 + tid;
 #pragma unroll
         for (int u = 0; u < FLAT_U; ++u) {
             const long long i = ck.i4 + u * FLAT_THREADS;
@@ -79,6 +81,18 @@ __global__ void __launch_bounds__(FLAT_THREADS) head_flat_kernel(const FlatSegs 
     };
     auto compute = [&](FlatChunk& ck, long long g) {
         float s;
+        if (WITH_GRAD && ck.lvl >= S.n) {
+            // box gradients: zero everywhere, head_rows_kernel then scatters the matched anchors' values
+            const long long n = S.count[ck.lvl], n4 = n >> 2;
+            float4* dst4 = (float4*)S.dst[ck.lvl];
+#pragma unroll
+            for (int u = 0; u < FLAT_U; ++u) {
+                const long long i = ck.i4 + u * FLAT_THREADS;
+                if (i < n4) dst4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            if (g + 1 == S.chunk0[ck.lvl + 1] && tid < (int)(n & 3)) S.dst[ck.lvl][(n & ~3ll) + tid] = 0.0f;
+            return;
+        }
         if (WITH_GRAD) {
             const long long n4 = S.count[ck.lvl] >> 2;
             float4* dst4 = (float4*)S.dst[ck.lvl];
@@ -194,68 +208,87 @@ __global__ void __launch_bounds__(ROWS_THREADS) head_rows_kernel(
     }
     double acc_loc = 0.0, acc_fix = 0.0, acc_cnt = 0.0;
 
+    // four consecutive anchors per thread and iteration (one 128-bit load of `matches`); background anchors (-1, the
+    // overwhelming majority) cost nothing more
+    const long long ngroups = (NA + 3) >> 2;
     const long long stride = (long long)gridDim.x * ROWS_THREADS;
-    for (long long i0 = (long long)blockIdx.x * ROWS_THREADS; i0 < NA; i0 += stride) {
-        const long long i = i0 + tid;
-        const int m = (i < NA) ? __ldg(matches + i) : -1;
-        int b = 0, l = 0, loc = 0, k = 0;
-        if (m != -1) {                                                   // matched or ignored: locate the anchor in the head
-            b = (int)(i / A);
-            const int a = (int)(i - (long long)b * A);
-            l = head_level_of(G, a);
-            const int r = a - G.anchor_off[l];
-            loc = r / n;
-            k = r - loc * n;
-        }
-        if (m >= 0) {
-            const int hw = G.hw[l];
-            // ---- localisation loss (ssd.py:117, losses.py:4-19) + matched count (ssd.py:121-122)
-            const long long e0 = head_elem(cf, b, n * 4, hw, k * 4, loc);
-            const long long es = cf ? hw : 1;
-            const float* pb = G.box[l] + e0;
-            const float4 p = make_float4(__ldg(pb), __ldg(pb + es), __ldg(pb + 2 * es), __ldg(pb + 3 * es));
-            const float4 t = __ldg(reg_t + i);
-            acc_loc += (double)smooth_l1_4(p, t);
-            acc_cnt += 1.0;
-            if (WITH_GRAD) {
-                float* gb = GR.box[l] + e0;
-                gb[0] = k_loc * smooth_l1_grad(p.x, t.x);
-                gb[es] = k_loc * smooth_l1_grad(p.y, t.y);
-                gb[2 * es] = k_loc * smooth_l1_grad(p.z, t.z);
-                gb[3 * es] = k_loc * smooth_l1_grad(p.w, t.w);
-            }
-            // ---- the positive class: its logit was summed as a negative by the flat pass
-            const int tc = __ldg(cls_t + i) - 1;                         // one_hot(cls, C+1)[1:] (ssd.py:96-100)
-            if (tc >= 0 && tc < C) {
-                const long long e = head_elem(cf, b, n * C, hw, k * C + tc, loc);
-                const float x = __ldg(G.cls[l] + e);
-                acc_fix += (double)(alpha * focal_positive<GAMMA_MODE>(x, gamma)) -
-                           (double)(one_minus_alpha * focal_negative<GAMMA_MODE>(x, gamma));
-                if (WITH_GRAD) GR.cls[l][e] = k_pos * focal_positive_grad<GAMMA_MODE>(x, gamma);
+    for (long long q0 = (long long)blockIdx.x * ROWS_THREADS; q0 < ngroups; q0 += stride) {
+        const long long q = q0 + tid;
+        int mm[4] = {-1, -1, -1, -1};
+        if (q < ngroups) {
+            if ((q << 2) + 3 < NA) {
+                const int4 v = __ldg((const int4*)matches + q);
+                mm[0] = v.x; mm[1] = v.y; mm[2] = v.z; mm[3] = v.w;
+            } else {
+                for (int j = 0; j < 4; ++j)
+                    if ((q << 2) + j < NA) mm[j] = __ldg(matches + (q << 2) + j);
             }
         }
-        // ---- ignored anchors (matches == -2: weight 0, ssd.py:103): every class was summed by the flat pass; the warp
-        //      removes them together, lanes over classes
-        unsigned ign = __ballot_sync(0xffffffffu, m < -1);
-        while (ign) {
-            const int src = __ffs(ign) - 1;
-            ign &= ign - 1;
-            const int sb = __shfl_sync(0xffffffffu, b, src), sl = __shfl_sync(0xffffffffu, l, src);
-            const int sloc = __shfl_sync(0xffffffffu, loc, src), sk = __shfl_sync(0xffffffffu, k, src);
-            const int hw = G.hw[sl];
-            float sub = 0.0f;
-            for (int c = lane; c < C; c += 32) {
-                const long long e = head_elem(cf, sb, n * C, hw, sk * C + c, sloc);
-                sub += focal_negative<GAMMA_MODE>(__ldg(G.cls[sl] + e), gamma);
-                if (WITH_GRAD) GR.cls[sl][e] = 0.0f;
+        const bool any_special = (mm[0] & mm[1] & mm[2] & mm[3]) != -1;
+        if (!__any_sync(0xffffffffu, any_special)) continue;             // warp-uniform: 128 background anchors
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int m = mm[j];
+            const long long i = (q << 2) + j;
+            int b = 0, l = 0, loc = 0, k = 0;
+            if (m != -1) {                                               // matched or ignored: locate the anchor in the head
+                b = (int)(i / A);
+                const int a = (int)(i - (long long)b * A);
+                l = head_level_of(G, a);
+                const int r = a - G.anchor_off[l];
+                loc = r / n;
+                k = r - loc * n;
             }
-            acc_fix -= (double)(one_minus_alpha * sub);
+            if (m >= 0) {
+                const int hw = G.hw[l];
+                // ---- localisation loss (ssd.py:117, losses.py:4-19) + matched count (ssd.py:121-122)
+                const long long e0 = head_elem(cf, b, n * 4, hw, k * 4, loc);
+                const long long es = cf ? hw : 1;
+                const float* pb = G.box[l] + e0;
+                const float4 p = make_float4(__ldg(pb), __ldg(pb + es), __ldg(pb + 2 * es), __ldg(pb + 3 * es));
+                const float4 t = __ldg(reg_t + i);
+                acc_loc += (double)smooth_l1_4(p, t);
+                acc_cnt += 1.0;
+                if (WITH_GRAD) {
+                    float* gb = GR.box[l] + e0;
+                    gb[0] = k_loc * smooth_l1_grad(p.x, t.x);
+                    gb[es] = k_loc * smooth_l1_grad(p.y, t.y);
+                    gb[2 * es] = k_loc * smooth_l1_grad(p.z, t.z);
+                    gb[3 * es] = k_loc * smooth_l1_grad(p.w, t.w);
+                }
+                // ---- the positive class: its logit was summed as a negative by the flat pass
+                const int tc = __ldg(cls_t + i) - 1;                     // one_hot(cls, C+1)[1:] (ssd.py:96-100)
+                if (tc >= 0 && tc < C) {
+                    const long long e = head_elem(cf, b, n * C, hw, k * C + tc, loc);
+                    const float x = __ldg(G.cls[l] + e);
+                    acc_fix += (double)(alpha * focal_positive<GAMMA_MODE>(x, gamma)) -
+                               (double)(one_minus_alpha * focal_negative<GAMMA_MODE>(x, gamma));
+                    if (WITH_GRAD) GR.cls[l][e] = k_pos * focal_positive_grad<GAMMA_MODE>(x, gamma);
+                }
+            }
+            // ---- ignored anchors (matches == -2: weight 0, ssd.py:103): every class was summed by the flat pass; the
+            //      warp removes them together, lanes over classes
+            unsigned ign = __ballot_sync(0xffffffffu, m < -1);
+            while (ign) {
+                const int src = __ffs(ign) - 1;
+                ign &= ign - 1;
+                const int sb = __shfl_sync(0xffffffffu, b, src), sl = __shfl_sync(0xffffffffu, l, src);
+                const int sloc = __shfl_sync(0xffffffffu, loc, src), sk = __shfl_sync(0xffffffffu, k, src);
+                const int hw = G.hw[sl];
+                float sub = 0.0f;
+                for (int c = lane; c < C; c += 32) {
+                    const long long e = head_elem(cf, sb, n * C, hw, sk * C + c, sloc);
+                    sub += focal_negative<GAMMA_MODE>(__ldg(G.cls[sl] + e), gamma);
+                    if (WITH_GRAD) GR.cls[sl][e] = 0.0f;
+                }
+                acc_fix -= (double)(one_minus_alpha * sub);
+            }
         }
     }
 
     // ---- CTA reduction (fixed order) -> partials[blockIdx.x]; the last CTA combines everything
     __shared__ double s_red[ROWS_THREADS / 32][3];
-    __shared__ double s_fin[64][4];
+    __shared__ double s_fin[ROWS_THREADS][4];
     __shared__ int s_last;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
@@ -278,15 +311,20 @@ __global__ void __launch_bounds__(ROWS_THREADS) head_rows_kernel(
     __syncthreads();
     if (!s_last) return;
     __threadfence();
-    if (tid < 64) {
+    {
+        // every thread owns the partials tid, tid + 256, ... of both kernels: a fixed assignment and a fixed tree below, so the
+        // result does not depend on which CTA happens to be last
         double t[4] = {0.0, 0.0, 0.0, 0.0};
-        for (int i = tid; i < (int)gridDim.x; i += 64)
-            for (int j = 0; j < 3; ++j) t[j] += __ldcg(&partials[(size_t)i * 3 + j]);
-        for (int i = tid; i < n_flat; i += 64) t[3] += __ldcg(&flat_partials[i]);
+        for (int i = tid; i < (int)gridDim.x; i += ROWS_THREADS) {
+            const double p0 = __ldcg(&partials[(size_t)i * 3 + 0]), p1 = __ldcg(&partials[(size_t)i * 3 + 1]),
+                         p2 = __ldcg(&partials[(size_t)i * 3 + 2]);
+            t[0] += p0; t[1] += p1; t[2] += p2;
+        }
+        for (int i = tid; i < n_flat; i += ROWS_THREADS) t[3] += __ldcg(&flat_partials[i]);
         for (int j = 0; j < 4; ++j) s_fin[tid][j] = t[j];
     }
     __syncthreads();
-    for (int o = 32; o > 0; o >>= 1) {
+    for (int o = ROWS_THREADS / 2; o > 0; o >>= 1) {
         if (tid < o)
             for (int j = 0; j < 4; ++j) s_fin[tid][j] += s_fin[tid + o][j];
         __syncthreads();
@@ -389,31 +427,30 @@ static int head_loss_impl(ssdk_ctx* ctx, const ssdk_head* head, const float* reg
     SSDK_REQUIRE(!with_grad || (grads && num_matches), SSDK_ERR_ARG, "ssdk_head_ssd_loss_forward_backward: null grads / num_matches");
     SSDK_REQUIRE(with_grad || out_sums, SSDK_ERR_ARG, "ssdk_head_ssd_loss: out_sums is NULL");
 
+    SSDK_REQUIRE(aligned16(matches), SSDK_ERR_SHAPE, "ssdk_head_ssd_loss: matches must be 16-byte aligned");
     FlatSegs S;
     HeadGradPtrs GR;
-    S.n = G.num_levels;
+    const int nl = G.num_levels;
+    S.n = nl;
+    S.nseg = with_grad ? 2 * nl : nl;
     long long chunks = 0;
-    for (int l = 0; l < SSDK_MAX_LEVELS; ++l) {
-        S.src[l] = G.cls[l];
-        S.dst[l] = nullptr;
-        GR.cls[l] = nullptr; GR.box[l] = nullptr;
-        S.count[l] = (long long)B * G.per_loc * C * G.hw[l];
-        S.chunk0[l] = chunks;
-        if (l < G.num_levels) {
-            chunks += (S.count[l] + 4 * FLAT_CHUNK4 - 1) / (4 * FLAT_CHUNK4);
-            if (with_grad && S.count[l] > 0) {
-                GR.cls[l] = grads->class_predictions[l];
-                GR.box[l] = grads->encoded_boxes[l];
-                SSDK_REQUIRE(GR.cls[l] && GR.box[l], SSDK_ERR_ARG, "ssdk_head_ssd_loss_forward_backward: grads of level %d are NULL", l);
-                SSDK_REQUIRE(aligned16(GR.cls[l]) && aligned16(GR.box[l]), SSDK_ERR_SHAPE,
-                             "ssdk_head_ssd_loss_forward_backward: grads of level %d must be 16-byte aligned", l);
-                S.dst[l] = GR.cls[l];
-                // box gradients are zero except for the matched anchors, which head_rows_kernel scatters
-                SSDK_CHECK_CUDA(cudaMemsetAsync(GR.box[l], 0, (size_t)B * G.per_loc * 4 * G.hw[l] * sizeof(float), ctx->stream));
-            }
-        }
+    for (int l = 0; l < SSDK_MAX_LEVELS; ++l) { S.src[l] = nullptr; GR.cls[l] = nullptr; GR.box[l] = nullptr; }
+    for (int sg = 0; sg < 2 * SSDK_MAX_LEVELS; ++sg) { S.dst[sg] = nullptr; S.count[sg] = 0; }
+    for (int sg = 0; sg < S.nseg; ++sg) {
+        const int l = sg < nl ? sg : sg - nl;
+        S.chunk0[sg] = chunks;
+        S.count[sg] = (long long)B * G.per_loc * (sg < nl ? C : 4) * G.hw[l];
+        chunks += (S.count[sg] + 4 * FLAT_CHUNK4 - 1) / (4 * FLAT_CHUNK4);
+        if (sg < nl) S.src[l] = G.cls[l];
+        if (with_grad && S.count[sg] > 0) {
+            float* gp = sg < nl ? grads->class_predictions[l] : grads->encoded_boxes[l];
+            SSDK_REQUIRE(gp != nullptr, SSDK_ERR_ARG, "ssdk_head_ssd_loss_forward_backward: grads of level %d are NULL", l);
+            SSDK_REQUIRE(aligned16(gp), SSDK_ERR_SHAPE, "ssdk_head_ssd_loss_forward_backward: grads of level %d must be 16-byte aligned", l);
+            S.dst[sg] = gp;
+            if (sg < nl) GR.cls[l] = gp; else GR.box[l] = gp;            // box gradients: zero-filled by the flat kernel,
+        }                                                                // matched anchors scattered by head_rows_kernel
     }
-    for (int l = G.num_levels; l <= SSDK_MAX_LEVELS; ++l) S.chunk0[l] = chunks;
+    for (int sg = S.nseg; sg <= 2 * SSDK_MAX_LEVELS; ++sg) S.chunk0[sg] = chunks;
 
     // persistent-style grid: exactly the number of co-resident CTAs (a larger grid would add a partial second wave)
     static int occ_cache[4] = {0, 0, 0, 0};
@@ -432,8 +469,8 @@ static int head_loss_impl(ssdk_ctx* ctx, const ssdk_head* head, const float* reg
     long long grid_flat = (long long)ctx->num_sms * per_sm;
     if (grid_flat > chunks) grid_flat = chunks;
     if (grid_flat < 1) grid_flat = 1;
-    long long grid_rows = (NA + ROWS_THREADS - 1) / ROWS_THREADS;
-    if (grid_rows > (long long)ctx->num_sms * 8) grid_rows = (long long)ctx->num_sms * 8;
+    long long grid_rows = (NA + 4 * ROWS_THREADS - 1) / (4 * ROWS_THREADS);
+    if (grid_rows > (long long)ctx->num_sms * 4) grid_rows = (long long)ctx->num_sms * 4;
 
     const size_t ws_bytes = 16 + (size_t)ctx->num_sms * 8 * 4 * sizeof(double);
     if (ctx->ws_head.cap < ws_bytes) {
