@@ -208,8 +208,13 @@ __global__ void __launch_bounds__(ROWS_THREADS) head_rows_kernel(
     }
     double acc_loc = 0.0, acc_fix = 0.0, acc_cnt = 0.0;
 
-    // four consecutive anchors per thread and iteration (one 128-bit load of `matches`); background anchors (-1, the
-    // overwhelming majority) cost nothing more
+    // Each warp scans 128 consecutive anchors per iteration (one 128-bit load of `matches` per lane).  Background anchors
+    // (-1, the overwhelming majority) cost nothing more.  The others -- matched anchors come in clusters around a box -- are
+    // compacted into a per-warp queue and then handled ONE PER LANE, so that their dependent gathers (cls_target -> logit)
+    // are in flight together instead of one after the other in the lane that happened to own four of them.
+    __shared__ int s_queue[ROWS_THREADS / 32][128];
+    int* queue = s_queue[warp];
+    const unsigned lt_mask = (1u << lane) - 1u;
     const long long ngroups = (NA + 3) >> 2;
     const long long stride = (long long)gridDim.x * ROWS_THREADS;
     for (long long q0 = (long long)blockIdx.x * ROWS_THREADS; q0 < ngroups; q0 += stride) {
@@ -226,25 +231,30 @@ __global__ void __launch_bounds__(ROWS_THREADS) head_rows_kernel(
         }
         const bool any_special = (mm[0] & mm[1] & mm[2] & mm[3]) != -1;
         if (!__any_sync(0xffffffffu, any_special)) continue;             // warp-uniform: 128 background anchors
+        int total = 0;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            const int m = mm[j];
-            const long long i = (q << 2) + j;
-            int b = 0, l = 0, loc = 0, k = 0;
-            if (m != -1) {                                               // matched or ignored: locate the anchor in the head
-                b = (int)(i / A);
-                const int a = (int)(i - (long long)b * A);
-                l = head_level_of(G, a);
-                const int r = a - G.anchor_off[l];
-                loc = r / n;
-                k = r - loc * n;
-            }
+            const unsigned bal = __ballot_sync(0xffffffffu, mm[j] != -1);
+            if (mm[j] != -1) queue[total + __popc(bal & lt_mask)] = lane * 4 + j;
+            total += __popc(bal);
+        }
+        __syncwarp();
+        const long long warp_base = (q0 + (tid & ~31)) << 2;             // first anchor of this warp's 128
+        for (int r = lane; r < total; r += 32) {
+            const long long i = warp_base + queue[r];
+            const int m = __ldg(matches + i);                            // L1 hit
+            const int b = (int)(i / A);
+            const int a = (int)(i - (long long)b * A);
+            const int l = head_level_of(G, a);
+            const int rr = a - G.anchor_off[l];
+            const int loc = rr / n, k = rr - loc * n;
+            const int hw = G.hw[l];
             if (m >= 0) {
-                const int hw = G.hw[l];
                 // ---- localisation loss (ssd.py:117, losses.py:4-19) + matched count (ssd.py:121-122)
                 const long long e0 = head_elem(cf, b, n * 4, hw, k * 4, loc);
                 const long long es = cf ? hw : 1;
                 const float* pb = G.box[l] + e0;
+                const int tc = __ldg(cls_t + i) - 1;                     // one_hot(cls, C+1)[1:] (ssd.py:96-100)
                 const float4 p = make_float4(__ldg(pb), __ldg(pb + es), __ldg(pb + 2 * es), __ldg(pb + 3 * es));
                 const float4 t = __ldg(reg_t + i);
                 acc_loc += (double)smooth_l1_4(p, t);
@@ -257,7 +267,6 @@ __global__ void __launch_bounds__(ROWS_THREADS) head_rows_kernel(
                     gb[3 * es] = k_loc * smooth_l1_grad(p.w, t.w);
                 }
                 // ---- the positive class: its logit was summed as a negative by the flat pass
-                const int tc = __ldg(cls_t + i) - 1;                     // one_hot(cls, C+1)[1:] (ssd.py:96-100)
                 if (tc >= 0 && tc < C) {
                     const long long e = head_elem(cf, b, n * C, hw, k * C + tc, loc);
                     const float x = __ldg(G.cls[l] + e);
@@ -265,25 +274,24 @@ __global__ void __launch_bounds__(ROWS_THREADS) head_rows_kernel(
                                (double)(one_minus_alpha * focal_negative<GAMMA_MODE>(x, gamma));
                     if (WITH_GRAD) GR.cls[l][e] = k_pos * focal_positive_grad<GAMMA_MODE>(x, gamma);
                 }
-            }
-            // ---- ignored anchors (matches == -2: weight 0, ssd.py:103): every class was summed by the flat pass; the
-            //      warp removes them together, lanes over classes
-            unsigned ign = __ballot_sync(0xffffffffu, m < -1);
-            while (ign) {
-                const int src = __ffs(ign) - 1;
-                ign &= ign - 1;
-                const int sb = __shfl_sync(0xffffffffu, b, src), sl = __shfl_sync(0xffffffffu, l, src);
-                const int sloc = __shfl_sync(0xffffffffu, loc, src), sk = __shfl_sync(0xffffffffu, k, src);
-                const int hw = G.hw[sl];
+            } else {
+                // ---- ignored anchor (matches == -2: weight 0, ssd.py:103): every class was summed by the flat pass.  The
+                //      C gathers of a lane are independent; neighbouring lanes hold neighbouring locations (coalesced for
+                //      channels_first planes)
+                const long long e0 = head_elem(cf, b, n * C, hw, k * C, loc);
+                const long long es = cf ? hw : 1;
+                const float* px = G.cls[l] + e0;
                 float sub = 0.0f;
-                for (int c = lane; c < C; c += 32) {
-                    const long long e = head_elem(cf, sb, n * C, hw, sk * C + c, sloc);
-                    sub += focal_negative<GAMMA_MODE>(__ldg(G.cls[sl] + e), gamma);
-                    if (WITH_GRAD) GR.cls[sl][e] = 0.0f;
+#pragma unroll 4
+                for (int c = 0; c < C; ++c) sub += focal_negative<GAMMA_MODE>(__ldg(px + c * es), gamma);
+                if (WITH_GRAD) {
+                    float* gx = GR.cls[l] + e0;
+                    for (int c = 0; c < C; ++c) gx[c * es] = 0.0f;
                 }
                 acc_fix -= (double)(one_minus_alpha * sub);
             }
         }
+        __syncwarp();                                                    // the queue is rewritten by the next iteration
     }
 
     // ---- CTA reduction (fixed order) -> partials[blockIdx.x]; the last CTA combines everything
