@@ -4,33 +4,32 @@
 // (external C++ kernel called at nms.py:33; semantics restated in oracle/nms.py).
 //
 // Pipeline (all on the context's stream, no host synchronisation):
-//   1. filter_kernel      streams the [B,A,C] scores (or logits) once with 128-bit no-allocate loads and appends
-//                         a packed 64-bit key per (anchor, class) with score > threshold to the image's
-//                         candidate list (one warp-aggregated atomic per warp).  This is the HBM-bound kernel.
-//                         key = class | ~order(score) | anchor  ->  ascending u64 order == class ascending,
-//                         score descending, anchor index ascending.
+//   1. filter_kernel      streams the [B,A,C] scores (or logits) once with 128-bit no-allocate loads and appends a
+//                         packed 64-bit key per (anchor, class) with score > threshold to the candidate list of its
+//                         (image, class) SEGMENT (a fixed region of A keys -- a class cannot have more candidates than
+//                         anchors -- and one atomic counter per segment).  This is the HBM-bound kernel.
+//                         key = class | ~order(score) | anchor  ->  ascending u64 order == score descending, anchor
+//                         index ascending inside a segment.
 //                         The reference's `is_confident` anchor pre-filter (nms.py:71-74, '>=') only removes
 //                         anchors that have no candidate at all (candidates need '>'), so it cannot change any
 //                         output and is not materialised.
-//   2. sort_kernel        one CTA per image sorts the keys in shared memory (bitonic); images with more candidates
-//                         than fit fall back to a multi-CTA bitonic sort in global memory.  Also records the
-//                         [start, end) of every class segment.
-//   3. nms_kernel         one CTA per (image, class): candidates are taken 64 at a time in sorted order (four threads
-//                         per candidate), decoded (box_utils.py:114-142) and clipped (nms.py:77) on the fly, tested
-//                         against the boxes kept so far (shared memory); inside the chunk a 64x64 suppression bit
-//                         matrix is built in parallel and walked greedily by one thread; stops at K.
+//   2. nms_small_kernel   one WARP per segment with at most 32 candidates (the vast majority): the keys are sorted with a
+//                         shuffle bitonic network, decoded (box_utils.py:114-142) and clipped (nms.py:77), a 32x32
+//                         suppression bit matrix is built and walked greedily.  Larger segments are queued.
+//   3. nms_kernel         one CTA per queued segment: bitonic sort of the segment's keys (shared memory up to 4096 keys,
+//                         in place in global memory beyond), then candidates are taken 64 at a time in sorted order (eight
+//                         threads per candidate), tested against the boxes kept so far (shared memory) and against the
+//                         chunk's earlier candidates (64x64 bit matrix); the greedy order is resolved with ballots; stops at K.
 //   4. pack_kernel        class-major concatenation, zero padding to C*K and num_boxes (nms.py:83-93).
-#include <cooperative_groups.h>
+// There is no separate sort pass and nothing of the size of a whole image is ever sorted: the filter buckets by class,
+// each segment is sorted by the warp / CTA that runs its NMS.
 #include <string.h>
 
 #include "common.cuh"
 
-namespace cg = cooperative_groups;
-
 #define FILTER_THREADS 256
 #define FILTER_UNROLL 4
-#define SORT_THREADS 1024
-#define SORT_SMEM_KEYS 16384          // 128 KB of keys
+#define NMS_SORT_SMEM_KEYS 4096       // heavy segments up to this many keys are sorted in shared memory (32 KB)
 #define NMS_THREADS 512
 #define NMS_CH 64                    // candidates per chunk
 #define NMS_TPC (NMS_THREADS / NMS_CH)  // threads per candidate (a power of two <= 32)
@@ -74,13 +73,17 @@ __device__ __forceinline__ bool is_candidate(float v, float thr, float x_lo, flo
 template <bool IS_LOGITS>
 __global__ void __launch_bounds__(FILTER_THREADS) filter_kernel(
     const float* __restrict__ scores, long long per_image /*A*C*/, int C, float thr, float x_lo, KeyFormat fmt,
-    unsigned long long* __restrict__ cand, long long cap, int* __restrict__ counts) {
+    unsigned long long* __restrict__ cand, long long capc /*keys per segment = A*/, int* __restrict__ seg_count /*[B*C]*/) {
     const int b = blockIdx.y;
     const float* base = scores + (size_t)b * per_image;
-    unsigned long long* out = cand + (size_t)b * cap;
-    int* count = counts + b;
+    const long long seg0 = (long long)b * C;                            // first segment of this image
     const int lane = threadIdx.x & 31;
-    const unsigned lt_mask = (1u << lane) - 1u;
+    // a candidate of class c takes the next slot of segment (b, c)
+    auto emit = [&](long long e, float s) {
+        const int a = (int)(e / C), c = (int)(e - (long long)a * C);
+        const int pos = atomicAdd(seg_count + seg0 + c, 1);
+        cand[(size_t)(seg0 + c) * capc + pos] = make_key(c, s, a, fmt);
+    };
 
     // peel to 16-byte alignment: head scalars | body float4 | tail scalars
     const unsigned mis = (unsigned)(((uintptr_t)base >> 2) & 3);
@@ -97,11 +100,7 @@ __global__ void __launch_bounds__(FILTER_THREADS) filter_kernel(
         else if (lane - head < per_image - tail0) e = tail0 + (lane - head);
         if (e >= 0) {
             float s;
-            if (is_candidate<IS_LOGITS>(base[e], thr, x_lo, &s)) {
-                const int a = (int)(e / C), c = (int)(e - (long long)a * C);
-                const int pos = atomicAdd(count, 1);
-                if (pos < cap) out[pos] = make_key(c, s, a, fmt);
-            }
+            if (is_candidate<IS_LOGITS>(base[e], thr, x_lo, &s)) emit(e, s);
         }
     }
 
@@ -120,33 +119,13 @@ __global__ void __launch_bounds__(FILTER_THREADS) filter_kernel(
             const float lim = IS_LOGITS ? x_lo : thr;
             const float mx = fmaxf(fmaxf(v[u].x, v[u].y), fmaxf(v[u].z, v[u].w));
             const bool maybe = inb[u] && (mx > lim);
-            if (!__any_sync(0xffffffffu, maybe)) continue;            // warp-uniform fast path
+            if (!maybe) continue;
             const float vals[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
-            float sc[4];
-            unsigned bal[4];
-            bool hit[4];
-            int total = 0;
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                hit[j] = maybe && is_candidate<IS_LOGITS>(vals[j], thr, x_lo, &sc[j]);
-                bal[j] = __ballot_sync(0xffffffffu, hit[j]);
-                total += __popc(bal[j]);
-            }
-            if (total == 0) continue;
-            int basepos = 0;
-            if (lane == 0) basepos = atomicAdd(count, total);          // one atomic per warp
-            basepos = __shfl_sync(0xffffffffu, basepos, 0);
             const long long e0 = head + ((i0 + u * FILTER_THREADS + threadIdx.x) << 2);
-            int run = 0;
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-                if (hit[j]) {
-                    const long long e = e0 + j;
-                    const int a = (int)(e / C), c = (int)(e - (long long)a * C);
-                    const long long pos = (long long)basepos + run + __popc(bal[j] & lt_mask);
-                    if (pos < cap) out[pos] = make_key(c, sc[j], a, fmt);
-                }
-                run += __popc(bal[j]);
+                float sc;
+                if (is_candidate<IS_LOGITS>(vals[j], thr, x_lo, &sc)) emit(e0 + j, sc);
             }
         }
     }
@@ -177,10 +156,11 @@ __device__ __forceinline__ void head_decompose(const HeadGeom& G, int l, long lo
 template <bool IS_LOGITS>
 __global__ void __launch_bounds__(FILTER_THREADS) head_filter_kernel(const HeadGeom G, const HeadFilterSegs S, float thr, float x_lo,
                                                                     KeyFormat fmt, unsigned long long* __restrict__ cand,
-                                                                    long long cap, int* __restrict__ counts) {
+                                                                    long long capc, int* __restrict__ seg_count) {
     const int lane = threadIdx.x & 31;
     const unsigned lt_mask = (1u << lane) - 1u;
     const long long total = S.chunk0[G.num_levels];
+    const int C = G.C;
     int l = 0;
     for (long long g = blockIdx.x; g < total; g += gridDim.x) {
         while (g >= S.chunk0[l + 1]) ++l;
@@ -203,25 +183,31 @@ __global__ void __launch_bounds__(FILTER_THREADS) head_filter_kernel(const HeadG
             if (!__any_sync(0xffffffffu, maybe)) continue;            // warp-uniform fast path
             const float vals[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
             const long long e0 = (i0 + u * FILTER_THREADS + threadIdx.x) << 2;
-            // the warp's 128 consecutive floats normally belong to one image: one aggregated atomic per warp
-            const long long per_image = (long long)G.per_loc * G.C * G.hw[l];
-            const long long w0 = (i0 + u * FILTER_THREADS + (threadIdx.x & ~31)) << 2;
-            const int b_first = (int)(w0 / per_image);
-            const bool one_image = (w0 + 127) / per_image == b_first;
-            float sc[4];
-            unsigned bal[4];
-            bool hit[4];
-            int totalhits = 0;
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                hit[j] = maybe && is_candidate<IS_LOGITS>(vals[j], thr, x_lo, &sc[j]);
-                bal[j] = __ballot_sync(0xffffffffu, hit[j]);
-                totalhits += __popc(bal[j]);
+            // channels_first: the warp's 128 consecutive floats normally lie in ONE plane (image, anchor-in-cell, class), i.e.
+            // in one segment: a single aggregated atomic per warp, even when every element is a candidate
+            bool one_seg = false;
+            int wb = 0, wc = 0;
+            if (G.channels_first) {
+                const long long w0 = (i0 + u * FILTER_THREADS + (threadIdx.x & ~31)) << 2;
+                const long long hw = G.hw[l];
+                const long long plane = w0 / hw;
+                one_seg = (w0 + 127) / hw == plane;
+                wb = (int)(plane / ((long long)G.per_loc * C));
+                wc = (int)(plane % C);
             }
-            if (totalhits == 0) continue;
-            if (one_image) {
+            float sc[4];
+            bool hit[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) hit[j] = maybe && is_candidate<IS_LOGITS>(vals[j], thr, x_lo, &sc[j]);
+            if (one_seg) {
+                unsigned bal[4];
+                int totalhits = 0;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) { bal[j] = __ballot_sync(0xffffffffu, hit[j]); totalhits += __popc(bal[j]); }
+                if (totalhits == 0) continue;
+                const long long seg = (long long)wb * C + wc;
                 int basepos = 0;
-                if (lane == 0) basepos = atomicAdd(counts + b_first, totalhits);
+                if (lane == 0) basepos = atomicAdd(seg_count + seg, totalhits);
                 basepos = __shfl_sync(0xffffffffu, basepos, 0);
                 int run = 0;
 #pragma unroll
@@ -229,8 +215,7 @@ __global__ void __launch_bounds__(FILTER_THREADS) head_filter_kernel(const HeadG
                     if (hit[j]) {
                         int b, a, c;
                         head_decompose(G, l, e0 + j, b, a, c);
-                        const long long pos = (long long)basepos + run + __popc(bal[j] & lt_mask);
-                        if (pos < cap) cand[(size_t)b * cap + pos] = make_key(c, sc[j], a, fmt);
+                        cand[(size_t)seg * capc + basepos + run + __popc(bal[j] & lt_mask)] = make_key(c, sc[j], a, fmt);
                     }
                     run += __popc(bal[j]);
                 }
@@ -240,8 +225,9 @@ __global__ void __launch_bounds__(FILTER_THREADS) head_filter_kernel(const HeadG
                     if (hit[j]) {
                         int b, a, c;
                         head_decompose(G, l, e0 + j, b, a, c);
-                        const int pos = atomicAdd(counts + b, 1);
-                        if (pos < cap) cand[(size_t)b * cap + pos] = make_key(c, sc[j], a, fmt);
+                        const long long seg = (long long)b * C + c;
+                        const int pos = atomicAdd(seg_count + seg, 1);
+                        cand[(size_t)seg * capc + pos] = make_key(c, sc[j], a, fmt);
                     }
                 }
             }
@@ -253,97 +239,60 @@ __global__ void __launch_bounds__(FILTER_THREADS) head_filter_kernel(const HeadG
             if (is_candidate<IS_LOGITS>(G.cls[l][e], thr, x_lo, &s)) {
                 int b, a, c;
                 head_decompose(G, l, e, b, a, c);
-                const int pos = atomicAdd(counts + b, 1);
-                if (pos < cap) cand[(size_t)b * cap + pos] = make_key(c, s, a, fmt);
+                const long long seg = (long long)b * C + c;
+                const int pos = atomicAdd(seg_count + seg, 1);
+                cand[(size_t)seg * capc + pos] = make_key(c, s, a, fmt);
             }
         }
     }
 }
 
-// ---------------------------------------------------------------------------------------------- 2. sort
-__device__ __forceinline__ void mark_segments(const unsigned long long* keys, long long i, long long n, KeyFormat fmt,
-                                              int* seg_start, int* seg_end) {
-    const int c = key_class(keys[i], fmt);
-    if (i == 0 || key_class(keys[i - 1], fmt) != c) seg_start[c] = (int)i;
-    if (i == n - 1 || key_class(keys[i + 1], fmt) != c) seg_end[c] = (int)(i + 1);
+// ---------------------------------------------------------------------------------------------- 2. sorting helpers
+// 32 keys, one per lane, ascending (bitonic network on shuffles; ~0 pads sort last).
+__device__ __forceinline__ unsigned long long warp_sort_keys(unsigned long long key, int lane) {
+#pragma unroll
+    for (int k = 2; k <= 32; k <<= 1) {
+#pragma unroll
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            const unsigned long long other = __shfl_xor_sync(0xffffffffu, key, j);
+            const bool up = (lane & k) == 0;                // k == 32: every lane ascending
+            const bool lower = (lane & j) == 0;
+            const unsigned long long lo = key < other ? key : other, hi = key < other ? other : key;
+            key = (lower == up) ? lo : hi;
+        }
+    }
+    return key;
 }
 
-// grid (nblk, B).  Images with n <= SORT_SMEM_KEYS: block 0 sorts in shared memory, the other blocks leave.
-// Larger images: all nblk blocks run a bitonic network on the global list (padded to a power of two with ~0 keys),
-// separated by a per-image software barrier (the launch is cooperative when nblk > 1, so blocks are co-resident).
-__global__ void __launch_bounds__(SORT_THREADS) sort_kernel(unsigned long long* __restrict__ cand, long long cap,
-                                                            const int* __restrict__ counts, KeyFormat fmt, int C,
-                                                            int* __restrict__ seg_start, int* __restrict__ seg_end,
-                                                            unsigned* __restrict__ barriers) {
-    extern __shared__ __align__(16) unsigned long long s_keys[];
-    const int b = blockIdx.y;
-    unsigned long long* keys = cand + (size_t)b * cap;
-    long long n = counts[b];
-    if (n > cap) n = cap;
-    int* sstart = seg_start + (size_t)b * C;
-    int* send = seg_end + (size_t)b * C;
-    if (n == 0) return;
-
-    if (n <= SORT_SMEM_KEYS) {
-        if (blockIdx.x != 0) return;
-        int P = 1;
-        while (P < n) P <<= 1;
-        for (int i = threadIdx.x; i < P; i += SORT_THREADS) s_keys[i] = (i < n) ? keys[i] : ~0ull;
+// CTA-wide bitonic sort of keys[0, n) (shared or global memory), ascending, for ANY n: the network is the all-ascending
+// formulation (first step of a merge compares i with its mirror image, the others i with i + j); positions >= n behave as
+// +infinity, never move, and their compare-exchanges are simply skipped.
+__device__ void cta_sort_keys(unsigned long long* keys, int n, int tid, int nthreads) {
+    int P = 1, logP = 0;
+    while (P < n) { P <<= 1; ++logP; }
+    for (int lk = 1; lk <= logP; ++lk) {
+        const int k = 1 << lk, half = k >> 1;
+        for (int t = tid; t < (P >> 1); t += nthreads) {
+            const int blk = t >> (lk - 1), o = t & (half - 1);
+            const int i = (blk << lk) + o, l = (blk << lk) + (k - 1 - o);
+            if (l < n) {
+                const unsigned long long x = keys[i], y = keys[l];
+                if (x > y) { keys[i] = y; keys[l] = x; }
+            }
+        }
         __syncthreads();
-        for (int k = 2; k <= P; k <<= 1) {
-            for (int j = k >> 1; j > 0; j >>= 1) {
-                for (int t = threadIdx.x; t < (P >> 1); t += SORT_THREADS) {
-                    const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));   // lower index of the pair
-                    const int l = i | j;
-                    const unsigned long long x = s_keys[i], y = s_keys[l];
-                    const bool up = (i & k) == 0;
-                    if ((x > y) == up) { s_keys[i] = y; s_keys[l] = x; }
+        for (int j = half >> 1; j > 0; j >>= 1) {
+            for (int t = tid; t < (P >> 1); t += nthreads) {
+                const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+                const int l = i | j;
+                if (l < n) {
+                    const unsigned long long x = keys[i], y = keys[l];
+                    if (x > y) { keys[i] = y; keys[l] = x; }
                 }
-                __syncthreads();
-            }
-        }
-        for (int i = threadIdx.x; i < n; i += SORT_THREADS) {
-            keys[i] = s_keys[i];
-            mark_segments(s_keys, i, n, fmt, sstart, send);
-        }
-        return;
-    }
-
-    // ---- large image: global bitonic sort shared by the nblk blocks of this image
-    long long P = 1;
-    while (P < n) P <<= 1;                      // P <= cap (cap is a power of two)
-    const long long gsize = (long long)gridDim.x * SORT_THREADS;
-    const long long gtid = (long long)blockIdx.x * SORT_THREADS + threadIdx.x;
-    unsigned* bar = barriers + b;
-    unsigned epoch = 0;
-    auto image_barrier = [&]() {
-        __syncthreads();
-        if (gridDim.x > 1) {
-            ++epoch;
-            if (threadIdx.x == 0) {
-                __threadfence();
-                atomicAdd(bar, 1u);
-                while (atomicAdd(bar, 0u) < epoch * gridDim.x) __nanosleep(64);
-                __threadfence();
             }
             __syncthreads();
         }
-    };
-    for (long long i = n + gtid; i < P; i += gsize) keys[i] = ~0ull;
-    image_barrier();
-    for (long long k = 2; k <= P; k <<= 1) {
-        for (long long j = k >> 1; j > 0; j >>= 1) {
-            for (long long t = gtid; t < (P >> 1); t += gsize) {
-                const long long i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
-                const long long l = i | j;
-                const unsigned long long x = keys[i], y = keys[l];
-                const bool up = (i & k) == 0;
-                if ((x > y) == up) { keys[i] = y; keys[l] = x; }
-            }
-            image_barrier();
-        }
     }
-    for (long long i = gtid; i < n; i += gsize) mark_segments(keys, i, n, fmt, sstart, send);
 }
 
 // ---------------------------------------------------------------------------------------------- 3. NMS
@@ -390,8 +339,8 @@ __device__ __forceinline__ bool nms_exact(const NmsBox a, float area_a, const Nm
 #define NMS_SMALL_WARPS 8
 template <bool DECODED>
 __global__ void __launch_bounds__(NMS_SMALL_WARPS * 32) nms_small_kernel(
-    const unsigned long long* __restrict__ cand, long long cap, KeyFormat fmt, const int* __restrict__ seg_start,
-    const int* __restrict__ seg_end, const CodeView codes, const float4* __restrict__ anchors, long long A,
+    const unsigned long long* __restrict__ cand, long long capc, KeyFormat fmt, const int* __restrict__ seg_count,
+    const CodeView codes, const float4* __restrict__ anchors, long long A,
     long long nseg, int C, int K, float iou_thr, float4* __restrict__ seg_box, float* __restrict__ seg_score,
     int* __restrict__ seg_anchor, int* __restrict__ seg_kept, int* __restrict__ heavy_queue, int* __restrict__ heavy_count) {
     __shared__ NmsBox s_tile[NMS_SMALL_WARPS][32];
@@ -399,8 +348,7 @@ __global__ void __launch_bounds__(NMS_SMALL_WARPS * 32) nms_small_kernel(
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const long long seg = (long long)blockIdx.x * NMS_SMALL_WARPS + warp;
     if (seg >= nseg) return;
-    const int start = seg_start[seg];
-    const int n = seg_end[seg] - start;
+    const int n = seg_count[seg];
     if (n <= 0) {
         if (lane == 0) seg_kept[seg] = 0;
         return;
@@ -417,8 +365,9 @@ __global__ void __launch_bounds__(NMS_SMALL_WARPS * 32) nms_small_kernel(
     float4 raw = make_float4(0.f, 0.f, 0.f, 0.f);
     float area = 0.f, score = 0.f;
     int a = 0;
+    // the segment's keys arrive in arbitrary order: sort them (score descending, anchor ascending)
+    const unsigned long long key = warp_sort_keys(alive ? cand[(size_t)seg * capc + lane] : ~0ull, lane);
     if (alive) {
-        const unsigned long long key = cand[(size_t)b * cap + start + lane];
         a = key_anchor(key, fmt);
         score = key_score(key, fmt);
         raw = load_code(codes, b, A, a);
@@ -469,8 +418,8 @@ __global__ void __launch_bounds__(NMS_SMALL_WARPS * 32) nms_small_kernel(
 //   (d) kept candidates append themselves (rank by popcount) to the kept list and to the segment's output.
 template <bool DECODED>
 __global__ void __launch_bounds__(NMS_THREADS) nms_kernel(
-    const unsigned long long* __restrict__ cand, long long cap, KeyFormat fmt, const int* __restrict__ seg_start,
-    const int* __restrict__ seg_end, const CodeView codes, const float4* __restrict__ anchors, long long A,
+    unsigned long long* __restrict__ cand, long long capc, KeyFormat fmt, const int* __restrict__ seg_count,
+    const CodeView codes, const float4* __restrict__ anchors, long long A,
     long long nseg, int C, int K, float iou_thr, float4* __restrict__ seg_box, float* __restrict__ seg_score,
     int* __restrict__ seg_anchor, int* __restrict__ seg_kept, const int* __restrict__ heavy_queue,
     const int* __restrict__ heavy_count) {
@@ -481,20 +430,31 @@ __global__ void __launch_bounds__(NMS_THREADS) nms_kernel(
     __shared__ unsigned s_alive32[2][2];               // [chunk parity][word]: survivors of (a), set with atomicOr
     __shared__ unsigned long long s_keep;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    NmsBox* s_kept = (NmsBox*)nms_smem;                 // [K]
-    float* s_kept_area = (float*)(s_kept + K);          // [K]
+    unsigned long long* s_sort = (unsigned long long*)nms_smem;     // [NMS_SORT_SMEM_KEYS]
+    NmsBox* s_kept = (NmsBox*)(s_sort + NMS_SORT_SMEM_KEYS);        // [K]
+    float* s_kept_area = (float*)(s_kept + K);                      // [K]
     const float band = fabsf(iou_thr) * 3.814697265625e-06f;
     const int c = tid / NMS_TPC, q = tid % NMS_TPC;    // candidate slot in the chunk, position among its threads
     const int nheavy = *heavy_count;
     for (int item = blockIdx.x; item < nheavy; item += gridDim.x) {
         const long long seg = heavy_queue[item];
-        const int start = seg_start[seg];
-        const int n = seg_end[seg] - start;
+        const int n = seg_count[seg];
         const int b = (int)(seg / C);
-        const unsigned long long* keys = cand + (size_t)b * cap + start;
+        unsigned long long* keys = cand + (size_t)seg * capc;
         const size_t obase = (size_t)seg * K;
         int kept = 0;
         if (tid < 4) s_alive32[tid >> 1][tid & 1] = 0u;
+        // ---- sort the segment (score descending, anchor ascending): in shared memory when it fits, else in place
+        const unsigned long long* sorted = keys;
+        if (n <= NMS_SORT_SMEM_KEYS) {
+            for (int i = tid; i < n; i += NMS_THREADS) s_sort[i] = keys[i];
+            __syncthreads();
+            cta_sort_keys(s_sort, n, tid, NMS_THREADS);
+            sorted = s_sort;                                   // stays valid until the next queued segment
+        } else {
+            __syncthreads();
+            cta_sort_keys(keys, n, tid, NMS_THREADS);
+        }
         __syncthreads();
 
         // the candidate of the NEXT chunk (key -> code -> anchor: dependent global loads) is fetched while the current
@@ -503,7 +463,7 @@ __global__ void __launch_bounds__(NMS_THREADS) nms_kernel(
         float4 ncode = make_float4(0.f, 0.f, 0.f, 0.f), nanc = make_float4(0.f, 0.f, 0.f, 0.f);
         auto fetch = [&](int i) {
             if (i < n) {
-                nkey = keys[i];
+                nkey = sorted[i];
                 const int na = key_anchor(nkey, fmt);
                 ncode = load_code(codes, b, A, na);
                 if (!DECODED) nanc = anchors[na];
@@ -707,7 +667,7 @@ static int postprocess_impl(ssdk_ctx* ctx, const HeadGeom* head, const float* co
     SSDK_REQUIRE(((uintptr_t)scores & 3) == 0, SSDK_ERR_SHAPE, "ssdk_postprocess: scores must be 4-byte aligned");
     const long long per_image = (long long)A * C;
     SSDK_REQUIRE(per_image < (1ll << 31), SSDK_ERR_SHAPE, "ssdk_postprocess: A*C must be < 2^31");
-    SSDK_REQUIRE((size_t)K * 20 <= 180 * 1024, SSDK_ERR_SHAPE,
+    SSDK_REQUIRE((size_t)K * 20 <= 160 * 1024, SSDK_ERR_SHAPE,
                  "ssdk_postprocess: max_boxes_per_class %d too large", K);
     KeyFormat fmt;
     fmt.abits = bits_for(A > 1 ? A : 2);
@@ -715,27 +675,26 @@ static int postprocess_impl(ssdk_ctx* ctx, const HeadGeom* head, const float* co
     SSDK_REQUIRE(fmt.cshift + bits_for(C > 1 ? C : 2) <= 64, SSDK_ERR_SHAPE, "ssdk_postprocess: A=%lld x C=%d does not fit the key",
                  (long long)A, C);
 
-    // workspace: candidate keys (worst case: every (anchor, class) is a candidate; power of two per image for the
-    // bitonic fallback), counters + segment tables (zeroed every call), per-segment NMS results
-    long long cap = 1024;
-    while (cap < per_image) cap <<= 1;
-    SSDK_TRY(ssdk_ensure(ctx, &ctx->ws_cand, (size_t)B * cap * sizeof(unsigned long long)));
-    const size_t n_int = (size_t)B * 2 + 4 * (size_t)B * C + 4;        // counts[B], barriers[B], start, end, kept, heavy queue + its count
+    // workspace: one candidate region of A keys per (image, class) segment (a class cannot have more candidates than
+    // anchors, so the regions cannot overflow; only the filled prefixes are ever touched), one counter per segment
+    // (zeroed every call), per-segment NMS results
+    const long long capc = A > 0 ? A : 1;
+    const long long nseg = (long long)B * C;
+    SSDK_TRY(ssdk_ensure(ctx, &ctx->ws_cand, (size_t)nseg * capc * sizeof(unsigned long long)));
+    const size_t n_int = 4 + 3 * (size_t)nseg;                         // heavy count (+pad), seg_count, seg_kept, heavy queue
     SSDK_TRY(ssdk_ensure(ctx, &ctx->ws_counts, n_int * sizeof(int)));
-    const size_t seg_elems = (size_t)B * C * K;
+    const size_t seg_elems = (size_t)nseg * K;
     SSDK_TRY(ssdk_ensure(ctx, &ctx->ws_seg, seg_elems * (sizeof(float4) + sizeof(float) + sizeof(int))));
     unsigned long long* cand = (unsigned long long*)ctx->ws_cand.p;
-    int* counts = (int*)ctx->ws_counts.p;
-    unsigned* barriers = (unsigned*)(counts + B);
-    int* seg_start = counts + 2 * (size_t)B;
-    int* seg_end = seg_start + (size_t)B * C;
-    int* seg_kept = seg_end + (size_t)B * C;
-    int* heavy_queue = seg_kept + (size_t)B * C;
-    int* heavy_count = heavy_queue + (size_t)B * C;
+    int* heavy_count = (int*)ctx->ws_counts.p;
+    int* seg_count = heavy_count + 4;
+    int* seg_kept = seg_count + nseg;
+    int* heavy_queue = seg_kept + nseg;
     float4* seg_box = (float4*)ctx->ws_seg.p;
     float* seg_score = (float*)(seg_box + seg_elems);
     int* seg_anchor = (int*)(seg_score + seg_elems);
-    SSDK_CHECK_CUDA(cudaMemsetAsync(counts, 0, n_int * sizeof(int), ctx->stream));
+    SSDK_CHECK_CUDA(cudaMemsetAsync(heavy_count, 0, (4 + (size_t)nseg) * sizeof(int), ctx->stream));
+    if (per_image == 0) SSDK_CHECK_CUDA(cudaMemsetAsync(seg_kept, 0, (size_t)nseg * sizeof(int), ctx->stream));
 
     const float thr = (float)score_threshold;
     if (per_image > 0) {
@@ -762,9 +721,9 @@ static int postprocess_impl(ssdk_ctx* ctx, const HeadGeom* head, const float* co
             if (gx < 1) gx = 1;
             SSDK_KERNEL(ctx, SSDK_K_FILTER,
                 if (is_logits)
-                    head_filter_kernel<true><<<(unsigned)gx, FILTER_THREADS, 0, ctx->stream>>>(*head, S, thr, x_lo, fmt, cand, cap, counts);
+                    head_filter_kernel<true><<<(unsigned)gx, FILTER_THREADS, 0, ctx->stream>>>(*head, S, thr, x_lo, fmt, cand, capc, seg_count);
                 else
-                    head_filter_kernel<false><<<(unsigned)gx, FILTER_THREADS, 0, ctx->stream>>>(*head, S, thr, x_lo, fmt, cand, cap, counts));
+                    head_filter_kernel<false><<<(unsigned)gx, FILTER_THREADS, 0, ctx->stream>>>(*head, S, thr, x_lo, fmt, cand, capc, seg_count));
         } else {
             long long chunks = (per_image / 4 + FILTER_THREADS * FILTER_UNROLL - 1) / (FILTER_THREADS * FILTER_UNROLL);
             long long gx = ((long long)ctx->num_sms * 16 + B - 1) / B;
@@ -773,39 +732,14 @@ static int postprocess_impl(ssdk_ctx* ctx, const HeadGeom* head, const float* co
             const dim3 fgrid((unsigned)gx, B);
             SSDK_KERNEL(ctx, SSDK_K_FILTER,
                 if (is_logits)
-                    filter_kernel<true><<<fgrid, FILTER_THREADS, 0, ctx->stream>>>(scores, per_image, C, thr, x_lo, fmt, cand, cap, counts);
+                    filter_kernel<true><<<fgrid, FILTER_THREADS, 0, ctx->stream>>>(scores, per_image, C, thr, x_lo, fmt, cand, capc, seg_count);
                 else
-                    filter_kernel<false><<<fgrid, FILTER_THREADS, 0, ctx->stream>>>(scores, per_image, C, thr, x_lo, fmt, cand, cap, counts));
+                    filter_kernel<false><<<fgrid, FILTER_THREADS, 0, ctx->stream>>>(scores, per_image, C, thr, x_lo, fmt, cand, capc, seg_count));
         }
 
-        // 2. sort (+ segment table)
-        const size_t sort_smem = (size_t)SORT_SMEM_KEYS * sizeof(unsigned long long);
-        SSDK_TRY(ssdk_set_max_smem(ctx, (const void*)sort_kernel, (int)sort_smem));
-        int nblk = 1;
-        if (per_image > SORT_SMEM_KEYS) {
-            if (ctx->sort_occupancy == 0)
-                SSDK_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->sort_occupancy, sort_kernel, SORT_THREADS, sort_smem));
-            const int occ = ctx->sort_occupancy;
-            nblk = (ctx->num_sms * (occ > 0 ? occ : 1)) / B;
-            if (nblk < 1) nblk = 1;
-            if (nblk > 64) nblk = 64;
-        }
-        const dim3 sgrid(nblk, B);
-        if (nblk > 1) {
-            void* args[] = {(void*)&cand, (void*)&cap, (void*)&counts, (void*)&fmt, (void*)&C,
-                            (void*)&seg_start, (void*)&seg_end, (void*)&barriers};
-            SSDK_KERNEL(ctx, SSDK_K_SORT,
-                        SSDK_CHECK_CUDA(cudaLaunchCooperativeKernel((void*)sort_kernel, sgrid, dim3(SORT_THREADS), args, sort_smem,
-                                                                    ctx->stream)));
-        } else {
-            SSDK_KERNEL(ctx, SSDK_K_SORT,
-                        sort_kernel<<<sgrid, SORT_THREADS, sort_smem, ctx->stream>>>(cand, cap, counts, fmt, C, seg_start, seg_end,
-                                                                                   barriers));
-        }
-
-        // 3. NMS: one warp per small segment (<= 32 candidates), then one CTA per queued large segment
-        const size_t nms_smem = (size_t)K * (sizeof(NmsBox) + sizeof(float));
-        const long long nseg = (long long)B * C;
+        // 2.-3. NMS: one warp per small segment (<= 32 candidates, sorted with shuffles), then one CTA per queued large
+        //       segment (sorted by the CTA)
+        const size_t nms_smem = (size_t)NMS_SORT_SMEM_KEYS * sizeof(unsigned long long) + (size_t)K * (sizeof(NmsBox) + sizeof(float));
         const int sgrid_nms = ceil_div_i(nseg, NMS_SMALL_WARPS);
         long long hgrid = (long long)ctx->num_sms * 4;
         if (hgrid > nseg) hgrid = nseg;
@@ -819,18 +753,18 @@ static int postprocess_impl(ssdk_ctx* ctx, const HeadGeom* head, const float* co
         if (decoded) {
             SSDK_TRY(ssdk_set_max_smem(ctx, (const void*)nms_kernel<true>, (int)nms_smem));
             nms_small_kernel<true><<<sgrid_nms, NMS_SMALL_WARPS * 32, 0, ctx->stream>>>(
-                cand, cap, fmt, seg_start, seg_end, c4, a4, A, nseg, C, K, iou_f, seg_box, seg_score, seg_anchor, seg_kept,
+                cand, capc, fmt, seg_count, c4, a4, A, nseg, C, K, iou_f, seg_box, seg_score, seg_anchor, seg_kept,
                 heavy_queue, heavy_count);
             nms_kernel<true><<<(int)hgrid, NMS_THREADS, nms_smem, ctx->stream>>>(
-                cand, cap, fmt, seg_start, seg_end, c4, a4, A, nseg, C, K, iou_f, seg_box, seg_score, seg_anchor, seg_kept,
+                cand, capc, fmt, seg_count, c4, a4, A, nseg, C, K, iou_f, seg_box, seg_score, seg_anchor, seg_kept,
                 heavy_queue, heavy_count);
         } else {
             SSDK_TRY(ssdk_set_max_smem(ctx, (const void*)nms_kernel<false>, (int)nms_smem));
             nms_small_kernel<false><<<sgrid_nms, NMS_SMALL_WARPS * 32, 0, ctx->stream>>>(
-                cand, cap, fmt, seg_start, seg_end, c4, a4, A, nseg, C, K, iou_f, seg_box, seg_score, seg_anchor, seg_kept,
+                cand, capc, fmt, seg_count, c4, a4, A, nseg, C, K, iou_f, seg_box, seg_score, seg_anchor, seg_kept,
                 heavy_queue, heavy_count);
             nms_kernel<false><<<(int)hgrid, NMS_THREADS, nms_smem, ctx->stream>>>(
-                cand, cap, fmt, seg_start, seg_end, c4, a4, A, nseg, C, K, iou_f, seg_box, seg_score, seg_anchor, seg_kept,
+                cand, capc, fmt, seg_count, c4, a4, A, nseg, C, K, iou_f, seg_box, seg_score, seg_anchor, seg_kept,
                 heavy_queue, heavy_count);
         }
         if (nms_slot >= 0) ssdk_prof_end(ctx, nms_slot);
