@@ -70,34 +70,44 @@ __device__ __forceinline__ bool is_candidate(float v, float thr, float x_lo, flo
     return v > thr;                                                  // NonMaxSuppressionV3: strict '>'
 }
 
-template <bool IS_LOGITS>
-__global__ void __launch_bounds__(FILTER_THREADS) filter_kernel(
-    const float* __restrict__ scores, long long per_image /*A*C*/, int C, float thr, float x_lo, KeyFormat fmt,
-    unsigned long long* __restrict__ cand, long long capc /*keys per segment = A*/, int* __restrict__ seg_count /*[B*C]*/) {
-    const int b = blockIdx.y;
-    const float* base = scores + (size_t)b * per_image;
-    const long long seg0 = (long long)b * C;                            // first segment of this image
+// A candidate takes the next slot of its (image, class) segment.  The lanes that arrive here together and target the same
+// segment (the normal case when a channels_first plane is scanned: 128 consecutive floats share image and class) share one
+// atomic; otherwise one atomic per candidate -- candidates are rare unless the scores are dense.
+__device__ __forceinline__ void append_key(unsigned long long* __restrict__ cand, long long capc, int* __restrict__ seg_count,
+                                           long long seg, unsigned long long key) {
+    const unsigned m = __activemask();
     const int lane = threadIdx.x & 31;
-    // a candidate of class c takes the next slot of segment (b, c)
-    auto emit = [&](long long e, float s) {
-        const int a = (int)(e / C), c = (int)(e - (long long)a * C);
-        const int pos = atomicAdd(seg_count + seg0 + c, 1);
-        cand[(size_t)(seg0 + c) * capc + pos] = make_key(c, s, a, fmt);
-    };
+    const int leader = __ffs(m) - 1;
+    const long long seg_l = __shfl_sync(m, seg, leader);
+    int pos;
+    if (__all_sync(m, seg == seg_l)) {
+        int first = 0;
+        if (lane == leader) first = atomicAdd(seg_count + seg, __popc(m));
+        pos = __shfl_sync(m, first, leader) + __popc(m & ((1u << lane) - 1u));
+    } else {
+        pos = atomicAdd(seg_count + seg, 1);
+    }
+    cand[(size_t)seg * capc + pos] = key;
+}
 
+// The streaming scan shared by both layouts: `count` floats at `base` are read once with 128-bit no-allocate loads;
+// emit(e, score) is called for every element e with score > threshold.
+template <bool IS_LOGITS, typename Emit>
+__device__ __forceinline__ void scan_candidates(const float* __restrict__ base, long long count, float thr, float x_lo, Emit emit) {
+    const int lane = threadIdx.x & 31;
     // peel to 16-byte alignment: head scalars | body float4 | tail scalars
     const unsigned mis = (unsigned)(((uintptr_t)base >> 2) & 3);
     long long head = mis ? (4 - mis) : 0;
-    if (head > per_image) head = per_image;
-    const long long nbody4 = (per_image - head) >> 2;
+    if (head > count) head = count;
+    const long long nbody4 = (count - head) >> 2;
     const long long tail0 = head + (nbody4 << 2);
     const float4* body = (const float4*)(base + head);
 
     if (blockIdx.x == 0 && threadIdx.x < 32) {
-        // head + tail elements (< 8 in total), one lane each, plain atomics
+        // head + tail elements (< 8 in total), one lane each
         long long e = -1;
         if (lane < head) e = lane;
-        else if (lane - head < per_image - tail0) e = tail0 + (lane - head);
+        else if (lane - head < count - tail0) e = tail0 + (lane - head);
         if (e >= 0) {
             float s;
             if (is_candidate<IS_LOGITS>(base[e], thr, x_lo, &s)) emit(e, s);
@@ -118,133 +128,65 @@ __global__ void __launch_bounds__(FILTER_THREADS) filter_kernel(
         for (int u = 0; u < FILTER_UNROLL; ++u) {
             const float lim = IS_LOGITS ? x_lo : thr;
             const float mx = fmaxf(fmaxf(v[u].x, v[u].y), fmaxf(v[u].z, v[u].w));
-            const bool maybe = inb[u] && (mx > lim);
-            if (!maybe) continue;
-            const float vals[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+            if (!(inb[u] && (mx > lim))) continue;
             const long long e0 = head + ((i0 + u * FILTER_THREADS + threadIdx.x) << 2);
-#pragma unroll
+#pragma unroll 1
             for (int j = 0; j < 4; ++j) {
+                const float x = j == 0 ? v[u].x : (j == 1 ? v[u].y : (j == 2 ? v[u].z : v[u].w));
                 float sc;
-                if (is_candidate<IS_LOGITS>(vals[j], thr, x_lo, &sc)) emit(e0 + j, sc);
+                if (is_candidate<IS_LOGITS>(x, thr, x_lo, &sc)) emit(e0 + j, sc);
             }
         }
     }
 }
 
-// Same scan over the per-level head tensors (head-layout fusion, see head.cu): every level's class tensor
-// [B, n*C, h, w] (or [B, h, w, n*C]) is streamed as ONE flat array; only a candidate pays for the index arithmetic that
-// recovers (image, anchor, class) from its flat position.  A 1-D grid walks 4096-float chunks of all levels.
-#define HFILTER_CHUNK4 (FILTER_THREADS * FILTER_UNROLL)
-struct HeadFilterSegs {
-    long long chunk0[SSDK_MAX_LEVELS + 1];   // prefix sums of the per-level chunk counts
-    long long count[SSDK_MAX_LEVELS];        // floats per level
-};
+// anchor-major layout: grid (gx, B), image blockIdx.y is the [A,C] array scanned
+template <bool IS_LOGITS>
+__global__ void __launch_bounds__(FILTER_THREADS) filter_kernel(
+    const float* __restrict__ scores, long long per_image /*A*C*/, int C, float thr, float x_lo, KeyFormat fmt,
+    unsigned long long* __restrict__ cand, long long capc /*keys per segment = A*/, int* __restrict__ seg_count /*[B*C]*/) {
+    const int b = blockIdx.y;
+    const long long seg0 = (long long)b * C;                            // first segment of this image
+    auto emit = [&](long long e, float s) {
+        const int a = (int)(e / C), c = (int)(e - (long long)a * C);
+        append_key(cand, capc, seg_count, seg0 + c, make_key(c, s, a, fmt));
+    };
+    scan_candidates<IS_LOGITS>(scores + (size_t)b * per_image, per_image, thr, x_lo, emit);
+}
 
-__device__ __forceinline__ void head_decompose(const HeadGeom& G, int l, long long e, int& b, int& a, int& c) {
-    const int hw = G.hw[l], n = G.per_loc, C = G.C;
+// Head layout (head-layout fusion, see head.cu): grid (gx, num_levels); level blockIdx.y's class tensor [B, n*C, h, w] (or
+// [B, h, w, n*C]) is scanned as ONE flat array; only a candidate pays for the index arithmetic that recovers
+// (image, anchor, class) from its flat position.
+struct LevelGeom {        // one level of a HeadGeom, by value
+    int hw, per_loc, C, channels_first, anchor_off;
+};
+__device__ __forceinline__ void head_decompose(const LevelGeom g, long long e, int& b, int& a, int& c) {
+    const int hw = g.hw, n = g.per_loc, C = g.C;
     const long long per_image = (long long)n * C * hw;
     b = (int)(e / per_image);
     const int r = (int)(e - (long long)b * per_image);
     int loc, q;
-    if (G.channels_first) { q = r / hw; loc = r - q * hw; }
+    if (g.channels_first) { q = r / hw; loc = r - q * hw; }
     else { loc = r / (n * C); q = r - loc * (n * C); }
     const int k = q / C;
     c = q - k * C;
-    a = G.anchor_off[l] + loc * n + k;
+    a = g.anchor_off + loc * n + k;
 }
 
 template <bool IS_LOGITS>
-__global__ void __launch_bounds__(FILTER_THREADS) head_filter_kernel(const HeadGeom G, const HeadFilterSegs S, float thr, float x_lo,
-                                                                    KeyFormat fmt, unsigned long long* __restrict__ cand,
-                                                                    long long capc, int* __restrict__ seg_count) {
-    const int lane = threadIdx.x & 31;
-    const unsigned lt_mask = (1u << lane) - 1u;
-    const long long total = S.chunk0[G.num_levels];
-    const int C = G.C;
-    int l = 0;
-    for (long long g = blockIdx.x; g < total; g += gridDim.x) {
-        while (g >= S.chunk0[l + 1]) ++l;
-        const long long n = S.count[l], n4 = n >> 2;
-        const float4* body = (const float4*)G.cls[l];
-        const long long i0 = (g - S.chunk0[l]) * HFILTER_CHUNK4;
-        float4 v[FILTER_UNROLL];
-        bool inb[FILTER_UNROLL];
-#pragma unroll
-        for (int u = 0; u < FILTER_UNROLL; ++u) {
-            const long long i = i0 + u * FILTER_THREADS + threadIdx.x;
-            inb[u] = i < n4;
-            v[u] = inb[u] ? ld_stream_f4(body + i) : make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
-        }
-#pragma unroll
-        for (int u = 0; u < FILTER_UNROLL; ++u) {
-            const float lim = IS_LOGITS ? x_lo : thr;
-            const float mx = fmaxf(fmaxf(v[u].x, v[u].y), fmaxf(v[u].z, v[u].w));
-            const bool maybe = inb[u] && (mx > lim);
-            if (!__any_sync(0xffffffffu, maybe)) continue;            // warp-uniform fast path
-            const float vals[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
-            const long long e0 = (i0 + u * FILTER_THREADS + threadIdx.x) << 2;
-            // channels_first: the warp's 128 consecutive floats normally lie in ONE plane (image, anchor-in-cell, class), i.e.
-            // in one segment: a single aggregated atomic per warp, even when every element is a candidate
-            bool one_seg = false;
-            int wb = 0, wc = 0;
-            if (G.channels_first) {
-                const long long w0 = (i0 + u * FILTER_THREADS + (threadIdx.x & ~31)) << 2;
-                const long long hw = G.hw[l];
-                const long long plane = w0 / hw;
-                one_seg = (w0 + 127) / hw == plane;
-                wb = (int)(plane / ((long long)G.per_loc * C));
-                wc = (int)(plane % C);
-            }
-            float sc[4];
-            bool hit[4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) hit[j] = maybe && is_candidate<IS_LOGITS>(vals[j], thr, x_lo, &sc[j]);
-            if (one_seg) {
-                unsigned bal[4];
-                int totalhits = 0;
-#pragma unroll
-                for (int j = 0; j < 4; ++j) { bal[j] = __ballot_sync(0xffffffffu, hit[j]); totalhits += __popc(bal[j]); }
-                if (totalhits == 0) continue;
-                const long long seg = (long long)wb * C + wc;
-                int basepos = 0;
-                if (lane == 0) basepos = atomicAdd(seg_count + seg, totalhits);
-                basepos = __shfl_sync(0xffffffffu, basepos, 0);
-                int run = 0;
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    if (hit[j]) {
-                        int b, a, c;
-                        head_decompose(G, l, e0 + j, b, a, c);
-                        cand[(size_t)seg * capc + basepos + run + __popc(bal[j] & lt_mask)] = make_key(c, sc[j], a, fmt);
-                    }
-                    run += __popc(bal[j]);
-                }
-            } else {
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    if (hit[j]) {
-                        int b, a, c;
-                        head_decompose(G, l, e0 + j, b, a, c);
-                        const long long seg = (long long)b * C + c;
-                        const int pos = atomicAdd(seg_count + seg, 1);
-                        cand[(size_t)seg * capc + pos] = make_key(c, sc[j], a, fmt);
-                    }
-                }
-            }
-        }
-        // the (< 4) floats of a level beyond its last float4, with the level's last chunk
-        if (g + 1 == S.chunk0[l + 1] && threadIdx.x < (int)(n & 3)) {
-            const long long e = (n & ~3ll) + threadIdx.x;
-            float s;
-            if (is_candidate<IS_LOGITS>(G.cls[l][e], thr, x_lo, &s)) {
-                int b, a, c;
-                head_decompose(G, l, e, b, a, c);
-                const long long seg = (long long)b * C + c;
-                const int pos = atomicAdd(seg_count + seg, 1);
-                cand[(size_t)seg * capc + pos] = make_key(c, s, a, fmt);
-            }
-        }
-    }
+__global__ void __launch_bounds__(FILTER_THREADS) head_filter_kernel(const HeadGeom G, int B, float thr, float x_lo, KeyFormat fmt,
+                                                                    unsigned long long* __restrict__ cand, long long capc,
+                                                                    int* __restrict__ seg_count) {
+    const int l = blockIdx.y;
+    LevelGeom g;
+    g.hw = G.hw[l]; g.per_loc = G.per_loc; g.C = G.C; g.channels_first = G.channels_first; g.anchor_off = G.anchor_off[l];
+    const long long count = (long long)B * g.per_loc * g.C * g.hw;
+    auto emit = [&](long long e, float s) {
+        int b, a, c;
+        head_decompose(g, e, b, a, c);
+        append_key(cand, capc, seg_count, (long long)b * g.C + c, make_key(c, s, a, fmt));
+    };
+    scan_candidates<IS_LOGITS>(G.cls[l], count, thr, x_lo, emit);
 }
 
 // ---------------------------------------------------------------------------------------------- 2. sorting helpers
@@ -708,22 +650,21 @@ static int postprocess_impl(ssdk_ctx* ctx, const HeadGeom* head, const float* co
             }
         }
         if (head) {
-            HeadFilterSegs S;
-            long long nchunks = 0;
-            for (int l = 0; l < SSDK_MAX_LEVELS; ++l) {
-                S.chunk0[l] = nchunks;
-                S.count[l] = (long long)B * head->per_loc * C * head->hw[l];
-                if (l < head->num_levels) nchunks += (S.count[l] + 4 * HFILTER_CHUNK4 - 1) / (4 * HFILTER_CHUNK4);
+            long long most = 0;                                           // floats of the largest level
+            for (int l = 0; l < head->num_levels; ++l) {
+                const long long cnt = (long long)B * head->per_loc * C * head->hw[l];
+                if (cnt > most) most = cnt;
             }
-            S.chunk0[SSDK_MAX_LEVELS] = nchunks;
+            long long chunks = (most / 4 + FILTER_THREADS * FILTER_UNROLL - 1) / (FILTER_THREADS * FILTER_UNROLL);
             long long gx = (long long)ctx->num_sms * 16;
-            if (gx > nchunks) gx = nchunks;
+            if (gx > chunks) gx = chunks;
             if (gx < 1) gx = 1;
+            const dim3 hgrid_f((unsigned)gx, head->num_levels);
             SSDK_KERNEL(ctx, SSDK_K_FILTER,
                 if (is_logits)
-                    head_filter_kernel<true><<<(unsigned)gx, FILTER_THREADS, 0, ctx->stream>>>(*head, S, thr, x_lo, fmt, cand, capc, seg_count);
+                    head_filter_kernel<true><<<hgrid_f, FILTER_THREADS, 0, ctx->stream>>>(*head, B, thr, x_lo, fmt, cand, capc, seg_count);
                 else
-                    head_filter_kernel<false><<<(unsigned)gx, FILTER_THREADS, 0, ctx->stream>>>(*head, S, thr, x_lo, fmt, cand, capc, seg_count));
+                    head_filter_kernel<false><<<hgrid_f, FILTER_THREADS, 0, ctx->stream>>>(*head, B, thr, x_lo, fmt, cand, capc, seg_count));
         } else {
             long long chunks = (per_image / 4 + FILTER_THREADS * FILTER_UNROLL - 1) / (FILTER_THREADS * FILTER_UNROLL);
             long long gx = ((long long)ctx->num_sms * 16 + B - 1) / B;
