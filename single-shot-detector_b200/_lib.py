@@ -9,7 +9,7 @@ import os
 import threading
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'lib', 'libssdk.so')
+LIB_PATH = os.environ.get('SSDK_LIB') or os.path.join(_HERE, 'lib', 'libssdk.so')   # SSDK_LIB: an alternative build (tuning experiments)
 
 c_int, c_i64, c_double, c_void_p = ctypes.c_int, ctypes.c_int64, ctypes.c_double, ctypes.c_void_p
 P = c_void_p  # every tensor argument is passed as a raw address
