@@ -210,33 +210,124 @@ __device__ __forceinline__ unsigned long long warp_sort_keys(unsigned long long 
 
 // CTA-wide bitonic sort of keys[0, n) (shared or global memory), ascending, for ANY n: the network is the all-ascending
 // formulation (first step of a merge compares i with its mirror image, the others i with i + j); positions >= n behave as
-// +infinity, never move, and their compare-exchanges are simply skipped.
-__device__ void cta_sort_keys(unsigned long long* keys, int n, int tid, int nthreads) {
+// +infinity, never move, and their compare-exchanges are simply skipped.  Four independent pairs per thread are loaded
+// before any is written back, so that a sort in global memory (L2) has several loads in flight per thread.
+template <int SORT_ILP>
+__device__ __forceinline__ void sort_step(unsigned long long* keys, int n, int halfP, int tid, int nthreads, int lk, int j /*0: flip step*/) {
+    const int k = 1 << lk, half = k >> 1;
+    for (int t0 = tid; t0 < halfP; t0 += nthreads * SORT_ILP) {
+        int ii[SORT_ILP], ll[SORT_ILP];
+        unsigned long long x[SORT_ILP], y[SORT_ILP];
+#pragma unroll
+        for (int u = 0; u < SORT_ILP; ++u) {
+            const int t = t0 + u * nthreads;
+            if (j == 0) {
+                const int blk = t >> (lk - 1), o = t & (half - 1);
+                ii[u] = (blk << lk) + o;
+                ll[u] = (blk << lk) + (k - 1 - o);
+            } else {
+                ii[u] = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+                ll[u] = ii[u] | j;
+            }
+            if (t >= halfP || ll[u] >= n) ll[u] = -1;
+            if (ll[u] >= 0) { x[u] = keys[ii[u]]; y[u] = keys[ll[u]]; }
+        }
+#pragma unroll
+        for (int u = 0; u < SORT_ILP; ++u)
+            if (ll[u] >= 0 && x[u] > y[u]) { keys[ii[u]] = y[u]; keys[ll[u]] = x[u]; }
+    }
+}
+template <int SORT_ILP>
+__device__ __forceinline__ void cta_sort_keys(unsigned long long* keys, int n, int tid, int nthreads) {
     int P = 1, logP = 0;
     while (P < n) { P <<= 1; ++logP; }
     for (int lk = 1; lk <= logP; ++lk) {
-        const int k = 1 << lk, half = k >> 1;
-        for (int t = tid; t < (P >> 1); t += nthreads) {
-            const int blk = t >> (lk - 1), o = t & (half - 1);
-            const int i = (blk << lk) + o, l = (blk << lk) + (k - 1 - o);
-            if (l < n) {
-                const unsigned long long x = keys[i], y = keys[l];
-                if (x > y) { keys[i] = y; keys[l] = x; }
-            }
-        }
+        sort_step<SORT_ILP>(keys, n, P >> 1, tid, nthreads, lk, 0);
         __syncthreads();
-        for (int j = half >> 1; j > 0; j >>= 1) {
-            for (int t = tid; t < (P >> 1); t += nthreads) {
-                const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
-                const int l = i | j;
-                if (l < n) {
-                    const unsigned long long x = keys[i], y = keys[l];
-                    if (x > y) { keys[i] = y; keys[l] = x; }
-                }
-            }
+        for (int j = 1 << (lk - 2 >= 0 ? lk - 2 : 0); lk >= 2 && j > 0; j >>= 1) {
+            sort_step<SORT_ILP>(keys, n, P >> 1, tid, nthreads, lk, j);
             __syncthreads();
         }
     }
+}
+
+// Best-first selection for a large segment: copies the smallest keys of keys[0, n) -- at least `want` of them (or all n),
+// at most `cap` -- into out[] (unsorted) and returns their number.  Radix select on the key bits below `top_bit` (the bits
+// above are the class, identical inside a segment), 8 bits per pass from the top; a pass is a scan of the whole segment
+// (L2 resident) with 8 loads in flight per thread.  Stops as soon as the bucket boundary gives a count in [want, cap].
+#define SEL_ILP 4
+__device__ __forceinline__ int select_best_keys(const unsigned long long* __restrict__ keys, int n, unsigned long long* out, int want, int cap,
+                                int top_bit, unsigned long long class_prefix, int tid, int nthreads, unsigned* s_hist /*[256]*/,
+                                unsigned long long* s_u64 /*[2]*/, int* s_int /*[4]*/) {
+    int hi = top_bit;                           // bits [0, hi) are still undecided inside the boundary bucket
+    unsigned long long prefix = class_prefix;   // decided high bits of the boundary bucket
+    int below = 0;                              // keys known to be smaller than every key of the boundary bucket
+    unsigned long long T = ~0ull;               // final threshold: select keys < T
+    while (true) {
+        const int bits = hi < 8 ? hi : 8, shift = hi - bits;
+        for (int i = tid; i < 256; i += nthreads) s_hist[i] = 0u;
+        __syncthreads();
+        for (int base = 0; base < n; base += nthreads * SEL_ILP) {      // uniform trip count: the lanes vote below
+            unsigned long long k[SEL_ILP];
+#pragma unroll
+            for (int u = 0; u < SEL_ILP; ++u) { const int i = base + tid + u * nthreads; k[u] = i < n ? keys[i] : 0ull; }
+#pragma unroll
+            for (int u = 0; u < SEL_ILP; ++u) {
+                const int i = base + tid + u * nthreads;
+                const bool in = i < n && (k[u] >> hi) == (prefix >> hi);
+                const unsigned digit = in ? ((unsigned)(k[u] >> shift) & ((1u << bits) - 1u)) : 0xFFFFFFFFu;
+                // lanes with the same digit share one shared-memory atomic (the leading score bits take few distinct values)
+                const unsigned same = __match_any_sync(0xffffffffu, digit);
+                if (in && (threadIdx.x & 31) == __ffs(same) - 1) atomicAdd(&s_hist[digit], (unsigned)__popc(same));
+            }
+        }
+        __syncthreads();
+        if (tid == 0) {
+            int lo = below, b = 0;
+            const int nb = 1 << bits;
+            for (; b < nb - 1; ++b) {
+                if (lo + (int)s_hist[b] >= want) break;
+                lo += (int)s_hist[b];
+            }
+            const int upto = lo + (int)s_hist[b];                  // keys < prefix | (b+1) << shift
+            if (upto <= cap || shift == 0) {                        // shift == 0: buckets hold single keys (keys are unique)
+                s_int[0] = 1;
+                s_u64[0] = (b == nb - 1 && shift + bits >= 64) ? ~0ull : (prefix | ((unsigned long long)(b + 1) << shift));
+                if (b == nb - 1) s_u64[0] = ((prefix >> hi) + 1ull) << hi;     // whole boundary bucket: next prefix
+            } else {
+                s_int[0] = 0;
+                s_int[1] = lo;
+                s_u64[0] = prefix | ((unsigned long long)b << shift);
+            }
+        }
+        __syncthreads();
+        const int done = s_int[0];
+        if (done) { T = s_u64[0]; break; }
+        below = s_int[1];
+        prefix = s_u64[0];
+        hi = shift;
+        __syncthreads();
+    }
+    // compaction (order does not matter: the caller sorts)
+    if (tid == 0) s_int[2] = 0;
+    __syncthreads();
+    for (int i0 = tid; i0 < n; i0 += nthreads * SEL_ILP) {
+        unsigned long long k[SEL_ILP];
+#pragma unroll
+        for (int u = 0; u < SEL_ILP; ++u) { const int i = i0 + u * nthreads; k[u] = i < n ? keys[i] : ~0ull; }
+#pragma unroll
+        for (int u = 0; u < SEL_ILP; ++u) {
+            const int i = i0 + u * nthreads;
+            if (i < n && k[u] < T) {
+                const int pos = atomicAdd(&s_int[2], 1);
+                if (pos < cap) out[pos] = k[u];
+            }
+        }
+    }
+    __syncthreads();
+    const int m = s_int[2];
+    __syncthreads();
+    return m < cap ? m : cap;
 }
 
 // ---------------------------------------------------------------------------------------------- 3. NMS
@@ -297,8 +388,11 @@ __global__ void __launch_bounds__(NMS_SMALL_WARPS * 32) nms_small_kernel(
         if (lane == 0) seg_kept[seg] = 0;
         return;
     }
-    if (n > 32) {
-        if (lane == 0) heavy_queue[atomicAdd(heavy_count, 1)] = (int)seg;
+    if (n > 32) {                                      // heavy_count[0] / [1]: the two queues (heavy | large), nseg entries each
+        if (lane == 0) {
+            const int large = n > NMS_SORT_SMEM_KEYS ? 1 : 0;
+            heavy_queue[(size_t)large * nseg + atomicAdd(heavy_count + large, 1)] = (int)seg;
+        }
         return;
     }
     const int b = (int)(seg / C);
@@ -360,7 +454,9 @@ __global__ void __launch_bounds__(NMS_SMALL_WARPS * 32) nms_small_kernel(
 //       known to be kept, and kept as soon as all of them are known to be removed; every round decides at least the first
 //       undecided candidate, in practice a handful of rounds of ballots decide all 64;  the result is cut at K;
 //   (d) kept candidates append themselves (rank by popcount) to the kept list and to the segment's output.
-template <bool DECODED>
+// LARGE = false: queued segments with 33..NMS_SORT_SMEM_KEYS candidates (sorted in shared memory); LARGE = true: the separate
+// queue of larger segments (dense scores), which need the select / in-place sort machinery and many more registers.
+template <bool DECODED, bool LARGE>
 __global__ void __launch_bounds__(NMS_THREADS) nms_kernel(
     unsigned long long* __restrict__ cand, long long capc, KeyFormat fmt, const int* __restrict__ seg_count,
     const CodeView codes, const float4* __restrict__ anchors, long long A,
@@ -373,6 +469,9 @@ __global__ void __launch_bounds__(NMS_THREADS) nms_kernel(
     __shared__ unsigned long long s_col[NMS_CH];
     __shared__ unsigned s_alive32[2][2];               // [chunk parity][word]: survivors of (a), set with atomicOr
     __shared__ unsigned long long s_keep;
+    __shared__ unsigned s_hist[256];                   // select_best_keys scratch
+    __shared__ unsigned long long s_sel64[2];
+    __shared__ int s_sel32[4];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     unsigned long long* s_sort = (unsigned long long*)nms_smem;     // [NMS_SORT_SMEM_KEYS]
     NmsBox* s_kept = (NmsBox*)(s_sort + NMS_SORT_SMEM_KEYS);        // [K]
@@ -387,18 +486,28 @@ __global__ void __launch_bounds__(NMS_THREADS) nms_kernel(
         unsigned long long* keys = cand + (size_t)seg * capc;
         const size_t obase = (size_t)seg * K;
         int kept = 0;
-        if (tid < 4) s_alive32[tid >> 1][tid & 1] = 0u;
-        // ---- sort the segment (score descending, anchor ascending): in shared memory when it fits, else in place
-        const unsigned long long* sorted = keys;
-        if (n <= NMS_SORT_SMEM_KEYS) {
+        // ---- sort the segment (score descending, anchor ascending).  Up to NMS_SORT_SMEM_KEYS keys: in shared memory.
+        //      Larger segments (dense scores): attempt 0 selects the best <= NMS_SORT_SMEM_KEYS keys with a radix select and
+        //      sorts only those -- greedy NMS truncated at K normally finishes inside them; if it does not (kept < K with
+        //      candidates left) attempt 1 sorts the whole segment in place and starts over.
+      for (int attempt = 0;; ++attempt) {
+        const unsigned long long* sorted = s_sort;
+        int navail = n;
+        __syncthreads();
+        if (!LARGE) {
             for (int i = tid; i < n; i += NMS_THREADS) s_sort[i] = keys[i];
             __syncthreads();
-            cta_sort_keys(s_sort, n, tid, NMS_THREADS);
-            sorted = s_sort;                                   // stays valid until the next queued segment
+            cta_sort_keys<1>(s_sort, n, tid, NMS_THREADS);
+        } else if (attempt == 0) {
+            navail = select_best_keys(keys, n, s_sort, NMS_SORT_SMEM_KEYS / 2, NMS_SORT_SMEM_KEYS, fmt.cshift,
+                                      (unsigned long long)(seg % C) << fmt.cshift, tid, NMS_THREADS, s_hist, s_sel64, s_sel32);
+            cta_sort_keys<1>(s_sort, navail, tid, NMS_THREADS);
         } else {
-            __syncthreads();
-            cta_sort_keys(keys, n, tid, NMS_THREADS);
+            cta_sort_keys<4>(keys, n, tid, NMS_THREADS);
+            sorted = keys;
         }
+        kept = 0;
+        if (tid < 4) s_alive32[tid >> 1][tid & 1] = 0u;
         __syncthreads();
 
         // the candidate of the NEXT chunk (key -> code -> anchor: dependent global loads) is fetched while the current
@@ -406,7 +515,7 @@ __global__ void __launch_bounds__(NMS_THREADS) nms_kernel(
         unsigned long long nkey = 0ull;
         float4 ncode = make_float4(0.f, 0.f, 0.f, 0.f), nanc = make_float4(0.f, 0.f, 0.f, 0.f);
         auto fetch = [&](int i) {
-            if (i < n) {
+            if (i < navail) {
                 nkey = sorted[i];
                 const int na = key_anchor(nkey, fmt);
                 ncode = load_code(codes, b, A, na);
@@ -415,9 +524,9 @@ __global__ void __launch_bounds__(NMS_THREADS) nms_kernel(
         };
         fetch(c);
         int parity = 0;
-        for (int base = 0; base < n && kept < K; base += NMS_CH, parity ^= 1) {
+        for (int base = 0; base < navail && kept < K; base += NMS_CH, parity ^= 1) {
             const int i = base + c;
-            bool alive = i < n;
+            bool alive = i < navail;
             NmsBox box = {0.f, 0.f, 0.f, 0.f};
             float4 raw = make_float4(0.f, 0.f, 0.f, 0.f);
             float area = 0.f, score = 0.f;
@@ -501,6 +610,8 @@ __global__ void __launch_bounds__(NMS_THREADS) nms_kernel(
             kept += __popcll(keep);
             __syncthreads();
         }
+        if (!LARGE || navail == n || kept >= K) break;          // uniform over the CTA; otherwise: full sort and start over
+      }
         if (tid == 0) seg_kept[seg] = kept;
         __syncthreads();
     }
@@ -625,7 +736,7 @@ static int postprocess_impl(ssdk_ctx* ctx, const HeadGeom* head, const float* co
     const long long capc = A > 0 ? A : 1;
     const long long nseg = (long long)B * C;
     SSDK_TRY(ssdk_ensure(ctx, &ctx->ws_cand, (size_t)nseg * capc * sizeof(unsigned long long)));
-    const size_t n_int = 4 + 3 * (size_t)nseg;                         // heavy count (+pad), seg_count, seg_kept, heavy queue
+    const size_t n_int = 4 + 4 * (size_t)nseg;                         // queue counts (+pad), seg_count, seg_kept, heavy queue, large queue
     SSDK_TRY(ssdk_ensure(ctx, &ctx->ws_counts, n_int * sizeof(int)));
     const size_t seg_elems = (size_t)nseg * K;
     SSDK_TRY(ssdk_ensure(ctx, &ctx->ws_seg, seg_elems * (sizeof(float4) + sizeof(float) + sizeof(int))));
@@ -693,23 +804,30 @@ static int postprocess_impl(ssdk_ctx* ctx, const HeadGeom* head, const float* co
         const float4* a4 = (const float4*)anchors;
         const float iou_f = (float)iou_threshold;
         const int nms_slot = ctx->profiling ? ssdk_prof_begin(ctx, SSDK_K_NMS) : -1;
-        if (decoded) {
-            SSDK_TRY(ssdk_set_max_smem(ctx, (const void*)nms_kernel<true>, (int)nms_smem));
-            nms_small_kernel<true><<<sgrid_nms, NMS_SMALL_WARPS * 32, 0, ctx->stream>>>(
-                cand, capc, fmt, seg_count, c4, a4, A, nseg, C, K, iou_f, seg_box, seg_score, seg_anchor, seg_kept,
-                heavy_queue, heavy_count);
-            nms_kernel<true><<<(int)hgrid, NMS_THREADS, nms_smem, ctx->stream>>>(
-                cand, capc, fmt, seg_count, c4, a4, A, nseg, C, K, iou_f, seg_box, seg_score, seg_anchor, seg_kept,
-                heavy_queue, heavy_count);
-        } else {
-            SSDK_TRY(ssdk_set_max_smem(ctx, (const void*)nms_kernel<false>, (int)nms_smem));
-            nms_small_kernel<false><<<sgrid_nms, NMS_SMALL_WARPS * 32, 0, ctx->stream>>>(
-                cand, capc, fmt, seg_count, c4, a4, A, nseg, C, K, iou_f, seg_box, seg_score, seg_anchor, seg_kept,
-                heavy_queue, heavy_count);
-            nms_kernel<false><<<(int)hgrid, NMS_THREADS, nms_smem, ctx->stream>>>(
-                cand, capc, fmt, seg_count, c4, a4, A, nseg, C, K, iou_f, seg_box, seg_score, seg_anchor, seg_kept,
-                heavy_queue, heavy_count);
-        }
+        // segments with more than NMS_SORT_SMEM_KEYS candidates can only exist when A is that large
+        const bool may_be_large = A > NMS_SORT_SMEM_KEYS;
+        long long lgrid = (long long)ctx->num_sms;
+        if (lgrid > nseg) lgrid = nseg;
+#define SSDK_LAUNCH_NMS(DEC)                                                                                                  \
+        do {                                                                                                                  \
+            SSDK_TRY(ssdk_set_max_smem(ctx, (const void*)nms_kernel<DEC, false>, (int)nms_smem));                            \
+            nms_small_kernel<DEC><<<sgrid_nms, NMS_SMALL_WARPS * 32, 0, ctx->stream>>>(                                      \
+                cand, capc, fmt, seg_count, c4, a4, A, nseg, C, K, iou_f, seg_box, seg_score, seg_anchor, seg_kept, heavy_queue, \
+                heavy_count);                                                                                                 \
+            nms_kernel<DEC, false><<<(int)hgrid, NMS_THREADS, nms_smem, ctx->stream>>>(                                      \
+                cand, capc, fmt, seg_count, c4, a4, A, nseg, C, K, iou_f, seg_box, seg_score, seg_anchor, seg_kept, heavy_queue, \
+                heavy_count);                                                                                                 \
+            if (may_be_large) {                                                                                               \
+                SSDK_TRY(ssdk_set_max_smem(ctx, (const void*)nms_kernel<DEC, true>, (int)nms_smem));                         \
+                nms_kernel<DEC, true><<<(int)lgrid, NMS_THREADS, nms_smem, ctx->stream>>>(                                   \
+                    cand, capc, fmt, seg_count, c4, a4, A, nseg, C, K, iou_f, seg_box, seg_score, seg_anchor, seg_kept,       \
+                    heavy_queue + nseg, heavy_count + 1);                                                                     \
+                ctx->launches++;                                                                                              \
+            }                                                                                                                 \
+        } while (0)
+        if (decoded) SSDK_LAUNCH_NMS(true);
+        else SSDK_LAUNCH_NMS(false);
+#undef SSDK_LAUNCH_NMS
         if (nms_slot >= 0) ssdk_prof_end(ctx, nms_slot);
         ctx->launches++;
         SSDK_CHECK_LAUNCH(ctx);
