@@ -43,6 +43,7 @@ def parse():
     ap.add_argument('--e2e-steps', type=int, default=0, help='steps of the host-buffer (e2e) loop; 0 = min(steps, 10)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-graph', action='store_true', help='time eager launches instead of CUDA-graph replays')
+    ap.add_argument('--nccl-allreduce', action='store_true', help='N>1: all-reduce the loss sums with NCCL instead of the peer-memory kernel')
     ap.add_argument('--cpu-sample', type=int, default=2, help='cpu_baseline sample: this many train images + 2x infer images')
     return ap.parse_args()
 
@@ -212,7 +213,7 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
-def workload_config(syn, sample=None):
+def workload_config(syn, sample=None, all_reduce=None):
     tc, ic = syn.CONFIGS[TRAIN_CFG], syn.CONFIGS[INFER_CFG]
     cfg = {
         'workload': 'per step and GPU: SSD.loss (targets + focal/smooth-L1) on cfg2 batch %d  +  SSD.get_predictions '
@@ -225,6 +226,8 @@ def workload_config(syn, sample=None):
     }
     if sample:
         cfg['sample'] = sample
+    if all_reduce:
+        cfg['all_reduce'] = all_reduce
     return cfg
 
 
@@ -281,8 +284,12 @@ def run_ours(args):
     raw_i = {'encoded_boxes': d_icod, 'class_predictions': d_ilog}
     ssd_t = pkg.SSD.from_predictions(H, W, raw_t, gen, C)
     ssd_i = pkg.SSD.from_predictions(H, W, raw_i, gen, C)
+    peer = False
     if world > 1:
         ssd_t.process_group = True
+        if not args.nccl_allreduce:
+            peer = bool(pkg.parallel.connect_peers())          # NVLink peer-memory all-reduce (csrc/comm.cu); NCCL if it cannot connect
+        ssd_t.peer_all_reduce = peer
 
     def step_resident():
         losses = ssd_t.loss(d_gt, PARAMS)
@@ -360,6 +367,11 @@ def run_ours(args):
     ms_infer = timed(lambda: ssd_i.get_predictions(SCORE_THR, IOU_THR, K_PER_CLASS), args.steps)
     # forward + backward of the training side: targets, losses, all-reduce, gradients w.r.t. both heads
     ms_train_fb = timed(lambda: ssd_t.loss_with_gradients(d_gt, PARAMS, upstream=UPSTREAM), args.steps)
+    ms_train_nccl = None
+    if world > 1 and peer:                       # the same training sub-path with the library collective, for comparison
+        ssd_t.peer_all_reduce = False
+        ms_train_nccl = timed(lambda: ssd_t.loss(d_gt, PARAMS), args.steps)
+        ssd_t.peer_all_reduce = True
 
     # ---- per-kernel durations (library-side CUDA events on the launching stream) for the roofline object
     lib.set_profiling(True, local_rank)
@@ -421,6 +433,7 @@ def run_ours(args):
         ssd_ih = pkg.SSD.from_head_outputs(H, W, lv_icod, lv_ilog, gen, C)
         if world > 1:
             ssd_th.process_group = True
+            ssd_th.peer_all_reduce = peer
         up_dev = torch.tensor(UPSTREAM, dtype=torch.float32, device=dev)
         hl = ssd_th.loss(d_gt, PARAMS)
         hp = ssd_ih.get_predictions(SCORE_THR, IOU_THR, K_PER_CLASS)
@@ -532,7 +545,8 @@ def run_ours(args):
         'metric': 'images_per_sec_target_assign_focal_loss_and_decode_nms_896x640',
         'value': value, 'unit': 'images/s', 'n_gpus': world, 'steps': args.steps, 'warmup': max(args.warmup, 3),
         'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
-        'dtype': 'f32', 'data': 'synthetic', 'config': workload_config(syn),
+        'dtype': 'f32', 'data': 'synthetic', 'config': workload_config(syn, all_reduce=(
+            None if world == 1 else ('NVLink peer-memory kernel fused with the loss finalisation (csrc/comm.cu)' if peer else 'NCCL'))),
         'clocks': clocks, 'e2e': e2e, 'gpu_launches': int(launches), 'launch_mode': mode,
         'roofline': dominant,
         'cpu_baseline': cpu,
@@ -548,6 +562,7 @@ def run_ours(args):
             'train_fwd_bwd_images_per_sec': Bt * world / (ms_train_fb * 1e-3), 'train_fwd_bwd_ms_per_step': ms_train_fb,
             'train_fwd_bwd_frac_of_hbm_roofline': ((b_train + 8 * A * C // 2 + 16 * A) * Bt / (ms_train_fb * 1e-3) / 1e9) / peak,
             'head_layout': head,
+            'train_ms_per_step_with_nccl_all_reduce': ms_train_nccl,
         },
         'check': check,
     }

@@ -62,8 +62,9 @@ SSDK_API int64_t ssdk_ctx_launch_count(const ssdk_ctx* ctx);
  * event records per kernel while enabled).  ssdk_ctx_profile_read synchronises the stream and returns, per kernel
  * id, the accumulated milliseconds and launch counts since the last reset.  Ids: 0 anchors, 1 match,
  * 2 force_match, 3 ssd_loss, 4 loss_reduce, 5 filter, 6 sort, 7 nms, 8 pack, 9 other, 10 ssd_loss_backward,
- * 11 head_flat (flat focal pass over the per-level head tensors), 12 head_rows (matched / ignored anchors), 13 head_concat. */
-#define SSDK_NUM_KERNEL_IDS 14
+ * 11 head_flat (flat focal pass over the per-level head tensors), 12 head_rows (matched / ignored anchors), 13 head_concat,
+ * 14 comm (peer-memory all-reduce). */
+#define SSDK_NUM_KERNEL_IDS 15
 SSDK_API int ssdk_ctx_set_profiling(ssdk_ctx* ctx, int enable);
 SSDK_API int ssdk_ctx_profile_read(ssdk_ctx* ctx, double* out_ms, int64_t* out_calls, int n, int reset);
 /* cudaStreamSynchronize on the context's stream (synchronous). */
@@ -267,6 +268,30 @@ SSDK_API int ssdk_head_detect(ssdk_ctx* ctx, const ssdk_head* head, const float*
                      double score_threshold, double iou_threshold, int K, const float* box_scaler,
                      double final_score_threshold, float* out_boxes, float* out_scores, int32_t* out_classes,
                      int32_t* out_num, int32_t* out_anchor_idx);
+
+/* ---- multi-GPU: the one exchange of the path, over NVLink peer memory ------------------------ */
+/* Images are sharded over the GPUs of one box, one process per GPU; the only coupling is the loss normaliser and the loss
+ * sums (detector/ssd.py:121-123,131-133): an all-reduce(sum) of three doubles.  These entry points do it with peer-memory
+ * stores inside one small kernel (see csrc/comm.cu) instead of a library collective; torch.distributed / NCCL remains the
+ * plumbing that carries the 64-byte handles (and the fallback when peers cannot map each other's memory).
+ *   ssdk_comm_local_handle : allocates this context's mailbox and returns its CUDA IPC handle (HOST buffer, 64 bytes).
+ *   ssdk_comm_connect      : `handles` = HOST world*64 bytes, handle of rank r at offset 64*r (all-gathered by the caller).
+ *                            Maps every peer's mailbox; SSDK_ERR_NCCL if a peer cannot be mapped (not the same box / no P2P).
+ *   ssdk_comm_all_reduce_sum : values (DEVICE double[n], n <= 8) summed over all ranks IN PLACE, in rank order (bit-identical
+ *                            on every rank); asynchronous on the context's stream, CUDA-graph capturable.  A collective:
+ *                            every rank must issue the same sequence of ssdk_comm_* exchanges.
+ *   ssdk_comm_loss_finalize : all-reduce of sums[3] (in place) fused with ssdk_loss_finalize, one launch.
+ *   ssdk_comm_error        : synchronises and reports the exchange number at which a peer failed to show up within ~15 s
+ *                            (0 = no error; the affected outputs are NaN).
+ *   ssdk_comm_world        : number of connected ranks, 0 when not connected. */
+#define SSDK_COMM_HANDLE_BYTES 64
+SSDK_API int ssdk_comm_local_handle(ssdk_ctx* ctx, void* out_handle);
+SSDK_API int ssdk_comm_connect(ssdk_ctx* ctx, int rank, int world, const void* handles);
+SSDK_API int ssdk_comm_world(const ssdk_ctx* ctx);
+SSDK_API int ssdk_comm_all_reduce_sum(ssdk_ctx* ctx, double* values, int n);
+SSDK_API int ssdk_comm_loss_finalize(ssdk_ctx* ctx, double* sums, float* out_losses);
+SSDK_API int ssdk_comm_error(ssdk_ctx* ctx, int64_t* out_epoch_of_timeout);
+SSDK_API int ssdk_comm_disconnect(ssdk_ctx* ctx);
 
 /* ---- observability: detector/ssd.py:125-129,135-163 (loss summaries) ------------------------ */
 /* Per-image, per-level statistics behind the reference's TensorBoard summaries, from the per-anchor vectors:

@@ -56,6 +56,13 @@ _SIGNATURES = {
     'ssdk_head_ssd_loss_forward_backward': (c_int, [P, P, P, P, P, c_int, c_i64, c_int, c_double, c_double, P, P, P, P]),
     'ssdk_head_detect': (c_int, [P, P, P, c_int, c_int, c_i64, c_int, c_double, c_double, c_int, P, c_double, P, P, P, P, P]),
     'ssdk_level_summaries': (c_int, [P, P, P, c_int, c_i64, P, c_int, c_double, P, P, P]),
+    'ssdk_comm_local_handle': (c_int, [P, P]),
+    'ssdk_comm_connect': (c_int, [P, c_int, c_int, P]),
+    'ssdk_comm_world': (c_int, [P]),
+    'ssdk_comm_all_reduce_sum': (c_int, [P, P, c_int]),
+    'ssdk_comm_loss_finalize': (c_int, [P, P, P]),
+    'ssdk_comm_error': (c_int, [P, ctypes.POINTER(c_i64)]),
+    'ssdk_comm_disconnect': (c_int, [P]),
 }
 
 SSDK_MAX_LEVELS = 8
@@ -127,7 +134,7 @@ def context(device_index):
 
 
 KERNEL_IDS = ['anchors', 'match', 'force_match', 'ssd_loss', 'loss_reduce', 'filter', 'sort', 'nms', 'pack', 'other',
-              'ssd_loss_backward', 'head_flat', 'head_rows', 'head_concat']
+              'ssd_loss_backward', 'head_flat', 'head_rows', 'head_concat', 'comm']
 
 
 def set_profiling(enable, device_index=0):

@@ -138,6 +138,7 @@ int ssdk_ctx_set_stream(ssdk_ctx* ctx, void* stream) {
 
 int ssdk_ctx_destroy(ssdk_ctx* ctx) {
     if (!ctx) return SSDK_OK;
+    ssdk_comm_disconnect(ctx);
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     ssdk_buf* bufs[] = {&ctx->ws_gtbest, &ctx->ws_partials, &ctx->ws_reg, &ctx->ws_cls, &ctx->ws_matches,

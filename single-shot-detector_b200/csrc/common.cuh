@@ -19,7 +19,7 @@ struct ssdk_buf {
 enum ssdk_kernel_id {
     SSDK_K_ANCHORS = 0, SSDK_K_MATCH, SSDK_K_FORCE_MATCH, SSDK_K_LOSS, SSDK_K_LOSS_REDUCE, SSDK_K_FILTER,
     SSDK_K_SORT, SSDK_K_NMS, SSDK_K_PACK, SSDK_K_OTHER, SSDK_K_LOSS_BACKWARD, SSDK_K_HEAD_FLAT, SSDK_K_HEAD_ROWS,
-    SSDK_K_HEAD_CONCAT, SSDK_K_COUNT
+    SSDK_K_HEAD_CONCAT, SSDK_K_COMM, SSDK_K_COUNT
 };
 #define SSDK_PROFILE_EVENTS 2048
 
@@ -47,6 +47,7 @@ struct ssdk_ctx {
     long long prof_calls[SSDK_K_COUNT] = {0};
     int sort_occupancy = 0;
     cudaStream_t copy_stream = nullptr;
+    void* comm = nullptr;    // peer-memory communicator (comm.cu), NULL until ssdk_comm_local_handle
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
 };
 

@@ -72,6 +72,8 @@ class SSD:
                                         device=device if device is not None and device.type == 'cuda' else None)  # ssd.py:31
         self.num_anchors_per_feature_map = anchor_generator.num_anchors_per_feature_map   # ssd.py:35
         self.process_group = None      # set to a torch.distributed group (or True for WORLD) to all-reduce the sums
+        self.peer_all_reduce = False   # True (after parallel.connect_peers() returned True): the all-reduce of the loss sums
+                                       # runs as a peer-memory NVLink kernel fused with the finalisation instead of NCCL
         self._anchors_host = None
 
     @classmethod
@@ -305,17 +307,34 @@ class SSD:
 
     def _loss_forward(self, groundtruth, params, keep_targets):
         sums = self.loss_sums(groundtruth, params, keep_targets=keep_targets)
-        if self.process_group is not None:
-            import torch.distributed as dist
-            dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=None if self.process_group is True else self.process_group)
         call = self._call
         out = call.empty([2], torch.float32)
-        _lib.check(_lib.load().ssdk_loss_finalize(call.ctx(), ptr(sums), ptr(out)))
+        self._reduce_and_finalize(call.ctx(), sums, out)
         self.num_matches = sums[2]
         if call.numpy_mode:
             o = out.cpu().numpy()
             return {'localization_loss': o[0], 'classification_loss': o[1]}
         return {'localization_loss': out[0], 'classification_loss': out[1]}
+
+    def _reduce_and_finalize(self, ctx, sums, out):
+        """ssd.py:121-133 across the image shards: all-reduce(sum) of (sum loc, sum cls, num_matches), then the two ratios."""
+        lib = _lib.load()
+        if self.process_group is not None and self.peer_all_reduce:
+            _lib.check(lib.ssdk_comm_loss_finalize(ctx, ptr(sums), ptr(out)))           # one kernel: NVLink exchange + finalize
+            return
+        if self.process_group is not None:
+            import torch.distributed as dist
+            dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=None if self.process_group is True else self.process_group)
+        _lib.check(lib.ssdk_loss_finalize(ctx, ptr(sums), ptr(out)))
+
+    def _reduce_count(self, ctx, count):
+        if self.process_group is None:
+            return
+        if self.peer_all_reduce:
+            _lib.check(_lib.load().ssdk_comm_all_reduce_sum(ctx, ptr(count), 1))
+            return
+        import torch.distributed as dist
+        dist.all_reduce(count, op=dist.ReduceOp.SUM, group=None if self.process_group is True else self.process_group)
 
     def loss_backward(self, upstream=None):
         """Gradients of  upstream[0] * localization_loss + upstream[1] * classification_loss  w.r.t. the head outputs,
@@ -390,16 +409,11 @@ class SSD:
                                              float(this_module.POSITIVES_THRESHOLD), float(this_module.NEGATIVES_THRESHOLD),
                                              ptr(reg), ptr(cls_t), ptr(matches)))                      # ssd.py:84
         _lib.check(lib.ssdk_count_matches(ctx, ptr(matches), B * A, ptr(count)))                       # ssd.py:121-122
-        group = None if self.process_group in (None, True) else self.process_group
-        if self.process_group is not None:
-            import torch.distributed as dist
-            dist.all_reduce(count, op=dist.ReduceOp.SUM, group=group)
+        self._reduce_count(ctx, count)
         _lib.check(lib.ssdk_ssd_loss_forward_backward(ctx, ptr(logits), ptr(codes), ptr(reg), ptr(cls_t), ptr(matches), B, A, C,
                                                       float(params['gamma']), float(params['alpha']), ptr(count), ptr(up),
                                                       ptr(sums), ptr(g_logits), ptr(g_codes)))
-        if self.process_group is not None:
-            dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=group)
-        _lib.check(lib.ssdk_loss_finalize(ctx, ptr(sums), ptr(out)))
+        self._reduce_and_finalize(ctx, sums, out)
         self.num_matches = sums[2]
         self._call = call
         self._saved = dict(logits=logits, codes=codes, sums=sums, gamma=float(params['gamma']), alpha=float(params['alpha']),
@@ -422,17 +436,12 @@ class SSD:
                 torch.tensor([float(upstream[0]), float(upstream[1])], dtype=torch.float32, device=head.device)
         ctx = call.ctx()
         _lib.check(lib.ssdk_count_matches(ctx, ptr(matches), B * A, ptr(count)))                       # ssd.py:121-122
-        group = None if self.process_group in (None, True) else self.process_group
-        if self.process_group is not None:
-            import torch.distributed as dist
-            dist.all_reduce(count, op=dist.ReduceOp.SUM, group=group)
+        self._reduce_count(ctx, count)
         d = head.descriptor()
         _lib.check(lib.ssdk_head_ssd_loss_forward_backward(
             ctx, ctypes.byref(d), ptr(reg), ptr(cls_t), ptr(matches), B, A, C, float(params['gamma']), float(params['alpha']),
             ptr(count), ptr(up), ptr(sums), ctypes.byref(gd)))
-        if self.process_group is not None:
-            dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=group)
-        _lib.check(lib.ssdk_loss_finalize(ctx, ptr(sums), ptr(out)))
+        self._reduce_and_finalize(ctx, sums, out)
         self.num_matches = sums[2]
         self._call = call
         self._saved = dict(head=head, sums=sums, gamma=float(params['gamma']), alpha=float(params['alpha']),

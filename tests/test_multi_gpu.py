@@ -1,6 +1,7 @@
-"""N>1 on real GPUs (skipped unless the box has >= 2): images sharded over 2 ranks, one NCCL all-reduce of
-(sum loc, sum cls, num_matches); every rank must return the full-batch losses of the oracle, and the sharded
-`matches` / detections must equal the single-GPU ones bit for bit."""
+"""N>1 on real GPUs (skipped unless the box has >= 2): images sharded over 2 ranks, one all-reduce of
+(sum loc, sum cls, num_matches) -- through NCCL and through the hand-written NVLink peer-memory kernel (csrc/comm.cu);
+every rank must return the full-batch losses of the oracle, both ways, and the sharded `matches` / detections must
+equal the single-GPU ones bit for bit."""
 import json
 import os
 import socket
@@ -40,7 +41,34 @@ sgt = {{k: cuda(v) for k, v in pkg.parallel.shard_groundtruth(gt, rank, world).i
 res = ssd.loss(sgt, dict(gamma=2.0, alpha=0.25))
 _, _, matches = ssd._create_targets(sgt)
 pred = ssd.get_predictions(0.05, 0.5, 10)
-out = dict(rank=rank, lo=lo, hi=hi, loc=float(res['localization_loss']), cls=float(res['classification_loss']),
+# ---- the same exchange through the peer-memory kernel: plain all-reduce (many epochs, both parity slots), fused
+#      finalisation, fused forward + backward, and CUDA-graph replay
+peer = pkg.parallel.connect_peers()
+peer_out = dict(connected=bool(peer))
+if peer:
+    vals = []
+    for it in range(5):
+        t = torch.tensor([rank + 1.0 + it, 10.0 * (rank + 1), 0.5, -2.0 * rank], dtype=torch.float64, device='cuda')
+        pkg.parallel.peer_all_reduce_sum(t)
+        vals.append(t.cpu().numpy().tolist())
+    ssd.peer_all_reduce = True
+    res_p = ssd.loss(sgt, dict(gamma=2.0, alpha=0.25))
+    l_fb, g_fb = ssd.loss_with_gradients(sgt, dict(gamma=2.0, alpha=0.25))
+    ssd.peer_all_reduce = False
+    l_nc, g_nc = ssd.loss_with_gradients(sgt, dict(gamma=2.0, alpha=0.25))
+    ssd.peer_all_reduce = True
+    step = pkg.graph.capture(lambda: ssd.loss(sgt, dict(gamma=2.0, alpha=0.25)))
+    replays = []
+    for _ in range(4):
+        r = step.replay()
+        replays.append([float(r['localization_loss']), float(r['classification_loss'])])
+    peer_out.update(vals=vals, loc=float(res_p['localization_loss']), cls=float(res_p['classification_loss']),
+                    fb=[float(l_fb['localization_loss']), float(l_fb['classification_loss'])],
+                    fb_nccl=[float(l_nc['localization_loss']), float(l_nc['classification_loss'])],
+                    grads_equal=bool(torch.equal(g_fb['class_predictions'], g_nc['class_predictions'])
+                                     and torch.equal(g_fb['encoded_boxes'], g_nc['encoded_boxes'])),
+                    replays=replays, error=pkg.parallel.peer_error())
+out = dict(rank=rank, peer=peer_out, lo=lo, hi=hi, loc=float(res['localization_loss']), cls=float(res['classification_loss']),
            num_matches=float(ssd.num_matches), matches=matches.cpu().numpy().tolist(),
            num_boxes=pred['num_boxes'].cpu().numpy().tolist(), labels=pred['labels'].cpu().numpy().tolist())
 json.dump(out, open(os.path.join({out_dir!r}, 'result_%d.json' % rank), 'w'))
@@ -89,6 +117,17 @@ def test_two_gpu_sharded_equals_single(tmp_path):
         assert abs(r['loc'] - float(full['localization_loss'])) <= 1e-5 * abs(float(full['localization_loss']))
         assert abs(r['cls'] - float(full['classification_loss'])) <= 1e-5 * abs(float(full['classification_loss']))
     assert r0['loc'] == r1['loc'] and r0['cls'] == r1['cls']
+    # the NVLink peer-memory all-reduce: same values on both ranks, equal to the NCCL results
+    assert r0['peer']['connected'] and r1['peer']['connected'], 'peer mailboxes could not be mapped on a 2-GPU box'
+    for it in range(5):
+        want_vals = [(1.0 + it) + (2.0 + it), 30.0, 1.0, -2.0]
+        assert r0['peer']['vals'][it] == want_vals and r1['peer']['vals'][it] == want_vals
+    for r in (r0, r1):
+        p = r['peer']
+        assert p['error'] == 0
+        assert (p['loc'], p['cls']) == (r['loc'], r['cls'])               # sums are added in rank order on every rank
+        assert p['fb'] == p['fb_nccl'] and p['grads_equal']
+        assert all(rep == [p['loc'], p['cls']] for rep in p['replays'])
     got = np.concatenate([np.array(r0['matches'], np.int32), np.array(r1['matches'], np.int32)])
     assert np.array_equal(got, full['matches'])                           # bit-exact across the shard boundary
     want = onms.batch_multiclass_non_max_suppression(codes, anchors, olosses.sigmoid(logits), 0.05, 0.5, 10)
