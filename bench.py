@@ -459,7 +459,7 @@ def run_ours(args):
         prof_i = lib.profile_read(local_rank)
         lib.set_profiling(False, local_rank)
 
-        def roof_of(p, name, nbytes):
+        def roof_of(p, name, nbytes, traffic_key=None):
             tot, cnt = p[name]
             if cnt == 0:
                 return None
@@ -467,7 +467,7 @@ def run_ours(args):
             ach = nbytes / (avg * 1e-3) / 1e9
             return {'kernel': name, 'bound': 'hbm', 'achieved': ach, 'peak': peak, 'unit': 'GB/s', 'frac': ach / peak,
                     'avg_launch_ms': avg, 'algorithmic_bytes_per_launch': nbytes, 'peak_source': peak_src,
-                    'traffic': (ncu_traffic.get(name + '_kernel') or {}).get('dram_bytes_per_launch')}
+                    'traffic': (ncu_traffic.get(traffic_key or (name + '_kernel')) or {}).get('dram_bytes_per_launch')}
         bh_train = 4 * A * C + 4 * A + 40 * A + 20 * G          # logits + matches read by the loss; targets written/read by the matcher side
         head = {
             'what': 'same sub-paths on per-level channels_first tower outputs (no reshape_and_concatenate); results checked against the anchor-major path',
@@ -479,8 +479,8 @@ def run_ours(args):
                                            'note': 'cost of the copy the reference makes before the anchor-major path (8AC+32A bytes per image)'},
             'unfused_train_ms_per_step': ms_concat_t + ms_train, 'unfused_train_fwd_bwd_ms_per_step': ms_concat_t + ms_train_fb,
             'unfused_infer_ms_per_step': ms_concat_i + ms_infer,
-            'roofline_head_flat_forward': roof_of(prof_f, 'head_flat', 4 * A * C * Bt),
-            'roofline_head_flat_forward_backward': roof_of(prof_fb, 'head_flat', 8 * A * C * Bt),
+            'roofline_head_flat_forward': roof_of(prof_f, 'head_flat', 4 * A * C * Bt, 'head_flat_forward_kernel'),
+            'roofline_head_flat_forward_backward': roof_of(prof_fb, 'head_flat', 8 * A * C * Bt, 'head_flat_forward_backward_kernel'),
             'roofline_head_filter': roof_of(prof_i, 'filter', 4 * A * C * Bi),
             'kernel_ms': {'forward': {k: v[0] / nprof for k, v in prof_f.items() if v[1]},
                           'forward_backward': {k: v[0] / nprof for k, v in prof_fb.items() if v[1]},

@@ -17,9 +17,9 @@ if [ "$MODE" = "full" ]; then
   timeout 600 python bench.py --impl reference --steps 2 --warmup 1 > $OUT/${TAG}_bench_ref.json 2> $OUT/${TAG}_bench_ref.err; echo "ref exit $?"
   cat $OUT/${TAG}_bench_ref.json
   timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/${TAG}_launches.csv \
-      python bench.py --steps 3 --warmup 3 --no-cpu-baseline --e2e-steps 1 > $OUT/${TAG}_ncu_bench.log 2>&1
+      python bench.py --steps 3 --warmup 3 --no-cpu-baseline --e2e-steps 1 --no-graph > $OUT/${TAG}_ncu_bench.log 2>&1
   timeout 900 ncu --set full --clock-control none --import-source on \
-      -k regex:'ssd_loss_kernel|filter_kernel|nms_kernel|match_kernel|sort_kernel' -s 10 -c 5 -f -o $OUT/${TAG}_prof \
-      python bench.py --steps 2 --warmup 3 --no-cpu-baseline --e2e-steps 1 > $OUT/${TAG}_ncu_full.log 2>&1
+      -k regex:'ssd_loss_kernel|ssd_loss_backward_kernel|filter_kernel|nms_kernel|nms_small_kernel|match_kernel|pack_kernel|head_flat_kernel|head_rows_kernel' \
+      -s 40 -c 40 -f -o $OUT/${TAG}_prof python bench.py --steps 2 --warmup 3 --no-cpu-baseline --e2e-steps 1 --no-graph > $OUT/${TAG}_ncu_full.log 2>&1
   ls -la $OUT
 fi
