@@ -43,6 +43,7 @@ def parse():
     ap.add_argument('--e2e-steps', type=int, default=0, help='steps of the host-buffer (e2e) loop; 0 = min(steps, 10)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-graph', action='store_true', help='time eager launches instead of CUDA-graph replays')
+    ap.add_argument('--no-overlap', action='store_true', help='headline: replay the two sub-paths back to back on one stream')
     ap.add_argument('--nccl-allreduce', action='store_true', help='N>1: all-reduce the loss sums with NCCL instead of the peer-memory kernel')
     ap.add_argument('--cpu-sample', type=int, default=2, help='cpu_baseline sample: this many train images + 2x infer images')
     return ap.parse_args()
@@ -223,6 +224,8 @@ def workload_config(syn, sample=None, all_reduce=None):
         'logits': 'train: N(-4.595,1) prior-bias init; infer: N(-7,1) background + N(1.5,1.5) on anchors with IoU>=0.4 to a GT',
         'l2': 'inputs per step (0.62 GB + 1.24 GB of logits) exceed the 126 MB L2; no flush needed',
         'parallelism': 'image-sharded, one all-reduce of 3 doubles per step',
+        'launch': 'one CUDA graph per step; the training-side and the inference-side sub-path are independent and are issued on '
+                  'two streams inside it (breakdown.sequential_graph_* = the same graph on one stream)',
     }
     if sample:
         cfg['sample'] = sample
@@ -332,17 +335,37 @@ def run_ours(args):
     #      identical kernels and inputs, one launch per step, so the host cannot starve the GPU
     mode = 'eager'
     ms_per_step = eager_ms_per_step
+    ms_sequential_graph = None
     if not args.no_graph:
         try:
             captured = pkg.graph.capture(step_resident, warmup=2)
             for _ in range(3):
                 captured.replay()
             ms_graph, win, out = timed_loop(captured.replay, args.steps)
-            ms_per_step = ms_graph / args.steps
+            ms_per_step = ms_sequential_graph = ms_graph / args.steps
             launches = captured.launches_per_replay * args.steps
             mode = 'cuda_graph'
         except Exception as e:                                       # keep the eager number, say why
             mode = 'eager (graph capture failed: %s)' % str(e)[:200]
+            torch.cuda.synchronize()
+    # ---- timed region 1c: the same step with its two independent sub-paths on two streams inside the graph (same
+    #      kernels, same inputs, same results): matching / sorting / NMS / packing hide behind the two HBM-bound passes
+    if mode == 'cuda_graph' and not args.no_overlap:
+        try:
+            step_overlapped = pkg.graph.concurrent(lambda: ssd_t.loss(d_gt, PARAMS),
+                                                   lambda: ssd_i.get_predictions(SCORE_THR, IOU_THR, K_PER_CLASS))
+            captured_o = pkg.graph.capture(step_overlapped, warmup=2)
+            for _ in range(3):
+                captured_o.replay()
+            ms_o, win_o, out_o = timed_loop(captured_o.replay, args.steps)
+            same = (float(out_o[0]['localization_loss']) == float(out[0]['localization_loss'])
+                    and float(out_o[0]['classification_loss']) == float(out[0]['classification_loss'])
+                    and all(torch.equal(out_o[1][k], out[1][k]) for k in ('boxes', 'labels', 'scores', 'num_boxes')))
+            if same and ms_o / args.steps < ms_per_step:
+                ms_per_step, win, out = ms_o / args.steps, win_o, out_o
+                launches = captured_o.launches_per_replay * args.steps
+                mode = 'cuda_graph, sub-paths on two streams'
+        except Exception:
             torch.cuda.synchronize()
     if sampler:
         sampler.window(*win)
@@ -552,6 +575,8 @@ def run_ours(args):
         'cpu_baseline': cpu,
         'breakdown': {
             'eager_ms_per_step': eager_ms_per_step, 'eager_images_per_sec': (Bt + Bi) * world / (eager_ms_per_step * 1e-3),
+            'sequential_graph_ms_per_step': ms_sequential_graph,
+            'sequential_graph_images_per_sec': None if not ms_sequential_graph else (Bt + Bi) * world / (ms_sequential_graph * 1e-3),
             'train_images_per_sec': Bt * world / (ms_train * 1e-3), 'train_ms_per_step': ms_train,
             'train_frac_of_hbm_roofline': (b_train * Bt / (ms_train * 1e-3) / 1e9) / peak,
             'infer_images_per_sec': Bi * world / (ms_infer * 1e-3), 'infer_ms_per_step': ms_infer,

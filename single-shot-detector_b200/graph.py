@@ -26,6 +26,29 @@ class CapturedStep:
         return self.outputs
 
 
+def concurrent(*fns, device=None):
+    """Returns a function that runs the independent `fns` on one side stream each, forked from and joined to the current
+    stream.  Inside `capture` this becomes parallel branches of the CUDA graph, so the ALU- / latency-bound kernels of one
+    sub-path (matching, sorting, NMS, packing) hide behind the HBM-bound kernels of another (the loss pass, the score scan).
+    The library keeps separate workspace for the training-side and the inference-side sub-paths, so `SSD.loss` and
+    `SSD.get_predictions` may overlap; two calls of the SAME sub-path must not."""
+    dev = torch.device('cuda', torch.cuda.current_device()) if device is None else torch.device(device)
+    streams = [torch.cuda.Stream(device=dev) for _ in fns]
+
+    def run():
+        cur = torch.cuda.current_stream(dev)
+        outs = []
+        for st in streams:
+            st.wait_stream(cur)
+        for st, fn in zip(streams, fns):
+            with torch.cuda.stream(st):
+                outs.append(fn())
+        for st in streams:
+            cur.wait_stream(st)
+        return tuple(outs)
+    return run
+
+
 def capture(fn, warmup=2, device=None):
     """Run `fn` `warmup` times eagerly on a side stream (grows the workspace, initialises NCCL), then capture one call."""
     if not torch.cuda.is_available():
