@@ -117,6 +117,14 @@ SSDK_API int ssdk_training_targets(ssdk_ctx* ctx, const float* anchors, int64_t 
                           double positives_threshold, double negatives_threshold,
                           float* out_reg, int32_t* out_cls, int32_t* out_matches);
 
+/* ssdk_training_targets that also delivers the number of matched anchors of this shard (matches >= 0; ssd.py:89,121-122)
+ * in out_count (DEVICE double[1]) -- the loss normaliser's input, needed BEFORE the fused forward + backward pass; counted
+ * inside the matching kernel, so no extra pass over `matches` (ssdk_count_matches) is needed. */
+SSDK_API int ssdk_training_targets_count(ssdk_ctx* ctx, const float* anchors, int64_t A, const float* gt_boxes,
+                                const int32_t* gt_labels, const int32_t* num_boxes, int B, int Gmax,
+                                double positives_threshold, double negatives_threshold, float* out_reg,
+                                int32_t* out_cls, int32_t* out_matches, double* out_count);
+
 /* ---- losses: detector/losses.py ----------------------------------------------------------- */
 /* localization_loss (:4-19): predictions/targets [B,A,4], weights [B,A] -> out [B,A]. */
 SSDK_API int ssdk_localization_loss(ssdk_ctx* ctx, const float* predictions, const float* targets,

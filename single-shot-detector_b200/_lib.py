@@ -37,6 +37,7 @@ _SIGNATURES = {
     'ssdk_match_boxes': (c_int, [P, P, c_i64, P, P, c_int, c_int, c_double, c_double, c_int, P]),
     'ssdk_create_targets': (c_int, [P, P, c_i64, P, P, c_int, c_int, P, P, P]),
     'ssdk_training_targets': (c_int, [P, P, c_i64, P, P, P, c_int, c_int, c_double, c_double, P, P, P]),
+    'ssdk_training_targets_count': (c_int, [P, P, c_i64, P, P, P, c_int, c_int, c_double, c_double, P, P, P, P]),
     'ssdk_localization_loss': (c_int, [P, P, P, P, c_i64, c_i64, P]),
     'ssdk_focal_loss': (c_int, [P, P, P, P, c_i64, c_i64, c_int, c_double, c_double, P]),
     'ssdk_ssd_loss': (c_int, [P, P, P, P, P, P, c_i64, c_i64, c_int, c_double, c_double, P, P, P]),

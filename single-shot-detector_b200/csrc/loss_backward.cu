@@ -331,6 +331,15 @@ static int check_backward_args(const char* who, const float* logits, const float
     return SSDK_OK;
 }
 
+// adds the number of entries >= 0 to *out_count (which the caller has zeroed)
+int ssdk_count_impl(ssdk_ctx* ctx, const int32_t* matches, int64_t n, double* out_count) {
+    if (n == 0) return SSDK_OK;
+    long long blocks = (n + 256 * 8 - 1) / (256 * 8);
+    if (blocks > ctx->num_sms * 8) blocks = ctx->num_sms * 8;
+    SSDK_KERNEL(ctx, SSDK_K_OTHER, count_matches_kernel<<<(int)blocks, 256, 0, ctx->stream>>>(matches, n, out_count));
+    return SSDK_OK;
+}
+
 extern "C" {
 
 int ssdk_ssd_loss_backward(ssdk_ctx* ctx, const float* logits, const float* codes, const float* reg_targets,
@@ -364,11 +373,7 @@ int ssdk_count_matches(ssdk_ctx* ctx, const int32_t* matches, int64_t n, double*
     SSDK_TRY(ssdk_ctx_enter(ctx));
     SSDK_REQUIRE(n >= 0 && out_count && (n == 0 || matches), SSDK_ERR_ARG, "ssdk_count_matches: bad arguments");
     SSDK_CHECK_CUDA(cudaMemsetAsync(out_count, 0, sizeof(double), ctx->stream));
-    if (n == 0) return SSDK_OK;
-    long long blocks = (n + 256 * 8 - 1) / (256 * 8);
-    if (blocks > ctx->num_sms * 8) blocks = ctx->num_sms * 8;
-    SSDK_KERNEL(ctx, SSDK_K_OTHER, count_matches_kernel<<<(int)blocks, 256, 0, ctx->stream>>>(matches, n, out_count));
-    return SSDK_OK;
+    return ssdk_count_impl(ctx, matches, n, out_count);
 }
 
 }  // extern "C"

@@ -30,7 +30,7 @@ template <bool WRITE_TARGETS>
 __device__ __forceinline__ void force_match_image(
     int b, int N, int* s_fid, unsigned char* s_ok, const float4* __restrict__ anchors, int A,
     const float4* __restrict__ gt_boxes, const int* __restrict__ gt_labels, int Gmax,
-    const unsigned long long* gt_best, int* matches, float4* reg, int* cls) {
+    const unsigned long long* gt_best, int* matches, float4* reg, int* cls, int* s_new_matched = nullptr) {
     for (int g = threadIdx.x; g < N; g += blockDim.x) {
         const unsigned long long key = __ldcg(&gt_best[(size_t)b * Gmax + g]);
         // key == 0: the whole IoU row is 0 -> argmax is anchor 0, value 0
@@ -49,6 +49,7 @@ __device__ __forceinline__ void force_match_image(
         }
         if (first && any_ok) {
             const size_t o = (size_t)b * A + a;
+            if (s_new_matched && __ldcg(&matches[o]) < 0) atomicAdd(s_new_matched, 1);   // a forced match of a so far unmatched anchor
             matches[o] = g;
             if (WRITE_TARGETS) {
                 reg[o] = box_encode(gt_boxes[(size_t)b * Gmax + g], anchors[a]);
@@ -64,6 +65,8 @@ __global__ void __launch_bounds__(MATCH_THREADS) match_kernel(
     const int* __restrict__ num_boxes, int Gmax, float pos_thr, float neg_thr, int same_thr,
     unsigned long long* __restrict__ gt_best /*[B,Gmax], zeroed; may be NULL (no forced matching)*/,
     int* __restrict__ tickets /*[B], zeroed; non-NULL: the last CTA of an image applies the forced matches (Gmax <= GT_CHUNK)*/,
+    int* __restrict__ img_count /*[B], zeroed; with out_count: matched anchors per image before forced matching*/,
+    double* __restrict__ out_count /*zeroed or NULL: + number of matched anchors (ssd.py:89,121-122), added once per image*/,
     int* __restrict__ matches, float4* __restrict__ reg, int* __restrict__ cls) {
     __shared__ float4 s_box[GT_CHUNK];
     __shared__ float s_area[GT_CHUNK];
@@ -96,6 +99,7 @@ __global__ void __launch_bounds__(MATCH_THREADS) match_kernel(
         __syncthreads();
     }
 
+    int my_matched = 0;
     for (int chunk = blockIdx.x; chunk < nchunks; chunk += gridDim.x) {
         const int a = chunk * MATCH_THREADS + threadIdx.x;
         const bool valid = a < A;
@@ -166,6 +170,7 @@ __global__ void __launch_bounds__(MATCH_THREADS) match_kernel(
             const int m = (N > 0) ? threshold_match(best_g, best_v, pos_thr, neg_thr, same_thr != 0) : -1;   // :24-37
             const size_t o = (size_t)b * A + a;
             matches[o] = m;
+            my_matched += (m >= 0);
             if (WRITE_TARGETS) {                                               // create_targets :133-176
                 if (m >= 0) {
                     reg[o] = box_encode(gtb[m], anc);
@@ -184,15 +189,30 @@ __global__ void __launch_bounds__(MATCH_THREADS) match_kernel(
     if (tickets && N > 0) {
         // Fused forced matching: every CTA publishes its writes and takes a ticket; the CTA that draws the last ticket
         // of the image sees all threshold results and all per-GT maxima, and overrides the forced anchors.
-        __shared__ int s_last;
+        __shared__ int s_last, s_cnt;
+        if (threadIdx.x == 0) s_cnt = 0;
+        __syncthreads();
+        if (out_count) {                                              // this CTA's matched anchors -> the image's counter
+            my_matched = __reduce_add_sync(0xffffffffu, my_matched);
+            if (lane == 0 && my_matched) atomicAdd(&s_cnt, my_matched);
+            __syncthreads();
+            if (threadIdx.x == 0 && s_cnt) atomicAdd(&img_count[b], s_cnt);
+        }
         __threadfence();
         __syncthreads();
-        if (threadIdx.x == 0) s_last = (atomicAdd(&tickets[b], 1) == (int)gridDim.x - 1);
+        if (threadIdx.x == 0) { s_last = (atomicAdd(&tickets[b], 1) == (int)gridDim.x - 1); s_cnt = 0; }
         __syncthreads();
         if (s_last) {
             __threadfence();
             force_match_image<WRITE_TARGETS>(b, N, (int*)s_area, (unsigned char*)s_box, anchors, A, gt_boxes, gt_labels, Gmax,
-                                             gt_best, matches, reg, cls);
+                                             gt_best, matches, reg, cls, out_count ? &s_cnt : nullptr);
+            if (out_count) {
+                __syncthreads();
+                if (threadIdx.x == 0) {
+                    const int total = __ldcg(&img_count[b]) + s_cnt;
+                    if (total) atomicAdd(out_count, (double)total);      // integers: exact and order independent
+                }
+            }
         }
     }
 }
@@ -231,15 +251,18 @@ __global__ void __launch_bounds__(256) create_targets_kernel(
 
 static bool aligned16(const void* p) { return ((uintptr_t)p & 15) == 0; }
 
+int ssdk_count_impl(ssdk_ctx* ctx, const int32_t* matches, int64_t n, double* out_count);
+
 int ssdk_match_impl(ssdk_ctx* ctx, const float* anchors, int64_t A, const float* gt_boxes, const int32_t* gt_labels,
                     const int32_t* num_boxes, int B, int Gmax, double pos_thr, double neg_thr, int force,
-                    float* out_reg, int32_t* out_cls, int32_t* out_matches) {
+                    float* out_reg, int32_t* out_cls, int32_t* out_matches, double* out_count = nullptr) {
     SSDK_TRY(ssdk_ctx_enter(ctx));
     SSDK_REQUIRE(pos_thr >= neg_thr, SSDK_ERR_ARG,
                  "positives_threshold (%g) must be >= negatives_threshold (%g)", pos_thr, neg_thr);  // :86
     SSDK_REQUIRE(B >= 0 && A >= 0 && Gmax >= 0, SSDK_ERR_ARG, "match: negative size");
     SSDK_REQUIRE(A < (1ll << 31) && B <= 65535, SSDK_ERR_SHAPE, "match: A must be < 2^31 and B <= 65535");
     SSDK_REQUIRE(Gmax <= 4096, SSDK_ERR_SHAPE, "match: at most 4096 ground-truth boxes per image (got %d)", Gmax);
+    if (out_count) SSDK_CHECK_CUDA(cudaMemsetAsync(out_count, 0, sizeof(double), ctx->stream));
     if (B == 0 || A == 0) return SSDK_OK;
     SSDK_REQUIRE(anchors && out_matches && (Gmax == 0 || gt_boxes), SSDK_ERR_ARG, "match: null pointer");
     const bool targets = out_reg != nullptr || out_cls != nullptr;
@@ -248,13 +271,20 @@ int ssdk_match_impl(ssdk_ctx* ctx, const float* anchors, int64_t A, const float*
                  "match: box arrays must be 16-byte aligned");
     unsigned long long* best = nullptr;
     int* tickets = nullptr;
+    int* img_count = nullptr;
     if (force && Gmax > 0) {
-        const size_t bytes = (size_t)B * Gmax * sizeof(unsigned long long) + (size_t)B * sizeof(int);   // keys + tickets
+        const size_t bytes = (size_t)B * Gmax * sizeof(unsigned long long) + 2 * (size_t)B * sizeof(int);   // keys + tickets + counts
         SSDK_TRY(ssdk_ensure(ctx, &ctx->ws_gtbest, bytes));
         best = (unsigned long long*)ctx->ws_gtbest.p;
-        if (Gmax <= GT_CHUNK) tickets = (int*)(best + (size_t)B * Gmax);
+        if (Gmax <= GT_CHUNK) {
+            tickets = (int*)(best + (size_t)B * Gmax);
+            img_count = tickets + B;
+        }
         SSDK_CHECK_CUDA(cudaMemsetAsync(best, 0, bytes, ctx->stream));
     }
+    // the matched count is folded into the kernel when the forced matches are (one CTA per image sees the final state);
+    // otherwise a separate pass over `matches` counts afterwards
+    double* fused_count = tickets ? out_count : nullptr;
     // about six resident CTAs per SM in total; each CTA walks ceil(nchunks / grid.x) chunks of its image
     const int nchunks = ceil_div_i(A, MATCH_THREADS);
     int gx = (ctx->num_sms * 6 + B - 1) / B;
@@ -266,11 +296,11 @@ int ssdk_match_impl(ssdk_ctx* ctx, const float* anchors, int64_t A, const float*
         if (targets)
             match_kernel<true><<<grid, MATCH_THREADS, 0, ctx->stream>>>(
                 (const float4*)anchors, (int)A, (const float4*)gt_boxes, gt_labels, num_boxes, Gmax, (float)pos_thr,
-                (float)neg_thr, same, best, tickets, out_matches, (float4*)out_reg, out_cls);
+                (float)neg_thr, same, best, tickets, img_count, fused_count, out_matches, (float4*)out_reg, out_cls);
         else
             match_kernel<false><<<grid, MATCH_THREADS, 0, ctx->stream>>>(
                 (const float4*)anchors, (int)A, (const float4*)gt_boxes, gt_labels, num_boxes, Gmax, (float)pos_thr,
-                (float)neg_thr, same, best, tickets, out_matches, nullptr, nullptr));
+                (float)neg_thr, same, best, tickets, img_count, fused_count, out_matches, nullptr, nullptr));
     if (best && !tickets) {
         const size_t smem = (size_t)Gmax * 5 + 16;
         SSDK_KERNEL(ctx, SSDK_K_FORCE_MATCH,
@@ -283,10 +313,19 @@ int ssdk_match_impl(ssdk_ctx* ctx, const float* anchors, int64_t A, const float*
                                                                         gt_labels, num_boxes, Gmax, best, out_matches, nullptr,
                                                                         nullptr));
     }
+    if (out_count && !fused_count) SSDK_TRY(ssdk_count_impl(ctx, out_matches, (int64_t)B * A, out_count));
     return SSDK_OK;
 }
 
 extern "C" {
+
+int ssdk_training_targets_count(ssdk_ctx* ctx, const float* anchors, int64_t A, const float* gt_boxes, const int32_t* gt_labels,
+                                const int32_t* num_boxes, int B, int Gmax, double pos_thr, double neg_thr, float* out_reg,
+                                int32_t* out_cls, int32_t* out_matches, double* out_count) {
+    SSDK_REQUIRE(out_reg && out_cls && out_count, SSDK_ERR_ARG, "ssdk_training_targets_count: out_reg/out_cls/out_count are required");
+    return ssdk_match_impl(ctx, anchors, A, gt_boxes, gt_labels, num_boxes, B, Gmax, pos_thr, neg_thr, 1, out_reg, out_cls,
+                           out_matches, out_count);
+}
 
 int ssdk_match_boxes(ssdk_ctx* ctx, const float* anchors, int64_t A, const float* gt_boxes, const int32_t* num_boxes,
                      int B, int Gmax, double pos_thr, double neg_thr, int force, int32_t* out_matches) {

@@ -4,7 +4,7 @@
 
 int ssdk_match_impl(ssdk_ctx* ctx, const float* anchors, int64_t A, const float* gt_boxes, const int32_t* gt_labels,
                     const int32_t* num_boxes, int B, int Gmax, double pos_thr, double neg_thr, int force,
-                    float* out_reg, int32_t* out_cls, int32_t* out_matches);
+                    float* out_reg, int32_t* out_cls, int32_t* out_matches, double* out_count = nullptr);
 
 template <typename T>
 static int stage_h2d(ssdk_ctx* ctx, int slot, const T* host, size_t count, T** dev) {

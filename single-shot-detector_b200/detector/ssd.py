@@ -240,8 +240,9 @@ class SSD:
                                **{k: extra[k] for k in ('reg_targets', 'cls_targets', 'matches')})
         return (sums, extra) if per_anchor else sums
 
-    def _targets_into(self, call, groundtruth, B, A):
-        """ssd.py:84 for a batch: (reg_targets, cls_targets, matches) as fresh tensors of `call`."""
+    def _targets_into(self, call, groundtruth, B, A, count=None):
+        """ssd.py:84 for a batch: (reg_targets, cls_targets, matches) as fresh tensors of `call`; `count` (float64 [1]), when
+        given, receives the number of matched anchors (ssd.py:121-122), counted inside the matching kernel."""
         from . import ssd as this_module
         anchors = call.tensor(self.anchors, torch.float32, (A, 4))
         gt = call.tensor(groundtruth['boxes'], torch.float32)
@@ -249,6 +250,11 @@ class SSD:
         labels = call.tensor(groundtruth['labels'], torch.int32, (B, G))
         num = call.tensor(groundtruth['num_boxes'], torch.int32, (B,))
         reg, cls_t, matches = call.empty([B, A, 4], torch.float32), call.empty([B, A], torch.int32), call.empty([B, A], torch.int32)
+        if count is not None:
+            _lib.check(_lib.load().ssdk_training_targets_count(
+                call.ctx(), ptr(anchors), A, ptr(gt), ptr(labels), ptr(num), B, G, float(this_module.POSITIVES_THRESHOLD),
+                float(this_module.NEGATIVES_THRESHOLD), ptr(reg), ptr(cls_t), ptr(matches), ptr(count)))
+            return reg, cls_t, matches
         _lib.check(_lib.load().ssdk_training_targets(
             call.ctx(), ptr(anchors), A, ptr(gt), ptr(labels), ptr(num), B, G, float(this_module.POSITIVES_THRESHOLD),
             float(this_module.NEGATIVES_THRESHOLD), ptr(reg), ptr(cls_t), ptr(matches)))
@@ -405,10 +411,9 @@ class SSD:
             up = call.tensor(upstream, torch.float32, (2,)) if isinstance(upstream, torch.Tensor) else \
                 torch.tensor([float(upstream[0]), float(upstream[1])], dtype=torch.float32, device=logits.device)
         ctx = call.ctx()
-        _lib.check(lib.ssdk_training_targets(ctx, ptr(anchors), A, ptr(gt), ptr(labels), ptr(num), B, G,
-                                             float(this_module.POSITIVES_THRESHOLD), float(this_module.NEGATIVES_THRESHOLD),
-                                             ptr(reg), ptr(cls_t), ptr(matches)))                      # ssd.py:84
-        _lib.check(lib.ssdk_count_matches(ctx, ptr(matches), B * A, ptr(count)))                       # ssd.py:121-122
+        _lib.check(lib.ssdk_training_targets_count(ctx, ptr(anchors), A, ptr(gt), ptr(labels), ptr(num), B, G,
+                                                   float(this_module.POSITIVES_THRESHOLD), float(this_module.NEGATIVES_THRESHOLD),
+                                                   ptr(reg), ptr(cls_t), ptr(matches), ptr(count)))    # ssd.py:84 and :121-122
         self._reduce_count(ctx, count)
         _lib.check(lib.ssdk_ssd_loss_forward_backward(ctx, ptr(logits), ptr(codes), ptr(reg), ptr(cls_t), ptr(matches), B, A, C,
                                                       float(params['gamma']), float(params['alpha']), ptr(count), ptr(up),
@@ -427,15 +432,14 @@ class SSD:
         lib = _lib.load()
         call = Call(head.device)
         B, A, C = head.batch_size, head.num_anchors, head.num_classes
-        reg, cls_t, matches = self._targets_into(call, groundtruth, B, A)
         count, sums, out = call.empty([1], torch.float64), call.empty([3], torch.float64), call.empty([2], torch.float32)
+        reg, cls_t, matches = self._targets_into(call, groundtruth, B, A, count=count)             # ssd.py:84 and :121-122
         g_cls, g_box, gd = self._head_grads(call, head)
         up = None
         if upstream is not None:
             up = call.tensor(upstream, torch.float32, (2,)) if isinstance(upstream, torch.Tensor) else \
                 torch.tensor([float(upstream[0]), float(upstream[1])], dtype=torch.float32, device=head.device)
         ctx = call.ctx()
-        _lib.check(lib.ssdk_count_matches(ctx, ptr(matches), B * A, ptr(count)))                       # ssd.py:121-122
         self._reduce_count(ctx, count)
         d = head.descriptor()
         _lib.check(lib.ssdk_head_ssd_loss_forward_backward(

@@ -429,3 +429,31 @@ def test_detect_box_scaler_and_final_threshold(pkg, golden):
         score_threshold=thr2, box_scaler=cuda(scaler[:1]), nms_score_threshold=0.05, iou_threshold=0.5, max_boxes_per_class=10)
     n2 = int((ws[0, :int(wn[0])] > np.float32(thr2)).sum())
     assert boxes.shape == (n2, 4) and labels.shape == (n2,) and scores.shape == (n2,) and bool((scores > thr2).all())
+
+
+@pytest.mark.parametrize('case', MATCH_CASES)
+@pytest.mark.parametrize('tag', list(THR))
+def test_matched_count_from_the_matching_kernel(pkg, golden, case, tag):
+    """ssdk_training_targets_count: the count produced inside the matching kernel (incl. forced matches that turn a
+    background / ignored anchor into a match, and the quirk case) == (matches >= 0).sum() of the reference's matches."""
+    import ctypes
+    g = golden('matching')
+    anchors, gt, labels = g['anchors'], g[case + '/gt'], g[case + '/labels']
+    pt, nt = THR[tag]
+    A, N = anchors.shape[0], gt.shape[0]
+    B, Gmax = 3, max(N, 1) + 2                                        # the same image three times, padded ground truth
+    boxes = np.zeros([B, Gmax, 4], np.float32); boxes[:, :N] = gt
+    labs = np.zeros([B, Gmax], np.int32); labs[:, :N] = labels
+    num = np.array([N, 0, N], np.int32)                               # the middle image has no boxes
+    d = {k: cuda(v) for k, v in dict(a=anchors, b=boxes, l=labs, n=num).items()}
+    reg = torch.empty([B, A, 4], device='cuda'); cls = torch.empty([B, A], dtype=torch.int32, device='cuda')
+    mat = torch.empty([B, A], dtype=torch.int32, device='cuda'); cnt = torch.full([1], -1.0, dtype=torch.float64, device='cuda')
+    lib = pkg._lib.load()
+    ctx = pkg._lib.context(0)
+    pkg._lib.check(lib.ssdk_ctx_set_stream(ctx, torch.cuda.current_stream().cuda_stream))
+    pkg._lib.check(lib.ssdk_training_targets_count(ctx, d['a'].data_ptr(), A, d['b'].data_ptr(), d['l'].data_ptr(), d['n'].data_ptr(),
+                                                   B, Gmax, pt, nt, reg.data_ptr(), cls.data_ptr(), mat.data_ptr(), cnt.data_ptr()))
+    want = g['%s/%s/matches' % (case, tag)]
+    m = mat.cpu().numpy()
+    assert np.array_equal(m[0], want) and np.array_equal(m[2], want) and (m[1] == -1).all()
+    assert cnt.item() == 2.0 * float((want >= 0).sum())
