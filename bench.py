@@ -375,13 +375,15 @@ def run_ours(args):
              'detections_image0': int(pred['num_boxes'][0])}
 
     # ---- sub-path timings (same resident inputs), each its own event-timed loop
+    eager_fallbacks = []
     def timed(fn, n):
         """ms per call of one sub-path, launched the same way as the headline number (graph replay when available)."""
         run = fn
-        if mode == 'cuda_graph':
+        if mode.startswith('cuda_graph'):
             try:
                 run = pkg.graph.capture(fn, warmup=2).replay
-            except Exception:
+            except Exception as e:
+                eager_fallbacks.append(str(e)[:120])
                 torch.cuda.synchronize()
         for _ in range(3):
             run()
@@ -587,6 +589,7 @@ def run_ours(args):
             'train_fwd_bwd_images_per_sec': Bt * world / (ms_train_fb * 1e-3), 'train_fwd_bwd_ms_per_step': ms_train_fb,
             'train_fwd_bwd_frac_of_hbm_roofline': ((b_train + 8 * A * C // 2 + 16 * A) * Bt / (ms_train_fb * 1e-3) / 1e9) / peak,
             'head_layout': head,
+            'sub_path_timings_that_fell_back_to_eager_launches': eager_fallbacks,
             'train_ms_per_step_with_nccl_all_reduce': ms_train_nccl,
         },
         'check': check,
