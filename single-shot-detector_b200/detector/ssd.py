@@ -14,6 +14,21 @@ from .training_target_creation import batch_training_targets
 from .utils.nms import batch_multiclass_non_max_suppression
 
 
+_UPSTREAM_CACHE = {}
+
+
+def _upstream_tensor(call, upstream, device):
+    """(w_loc, w_cls) as a float32 CUDA tensor [2].  Python pairs are uploaded once per (values, device) and cached, so that a
+    training step with constant loss weights (model.py:86-87) issues no host-to-device copy and can be captured in a CUDA graph."""
+    if isinstance(upstream, torch.Tensor):
+        return call.tensor(upstream, torch.float32, (2,))
+    key = (float(upstream[0]), float(upstream[1]), str(device))
+    t = _UPSTREAM_CACHE.get(key)
+    if t is None:
+        t = _UPSTREAM_CACHE[key] = torch.tensor(key[:2], dtype=torch.float32, device=device)
+    return t
+
+
 class _ShapeOnly:
     def __init__(self, shape):
         self.shape = shape
@@ -356,8 +371,7 @@ class SSD:
             call = Call(head.device)
             up = None
             if upstream is not None:
-                up = call.tensor(upstream, torch.float32, (2,)) if isinstance(upstream, torch.Tensor) else \
-                    torch.tensor([float(upstream[0]), float(upstream[1])], dtype=torch.float32, device=head.device)
+                up = _upstream_tensor(call, upstream, head.device)
             g_cls, g_box, gd = self._head_grads(call, head)
             d = head.descriptor()
             _lib.check(_lib.load().ssdk_head_ssd_loss_forward_backward(
@@ -371,8 +385,7 @@ class SSD:
         call = Call(logits.device)
         up = None
         if upstream is not None:
-            up = call.tensor(upstream, torch.float32, (2,)) if isinstance(upstream, torch.Tensor) else \
-                torch.tensor([float(upstream[0]), float(upstream[1])], dtype=torch.float32, device=logits.device)
+            up = _upstream_tensor(call, upstream, logits.device)
         g_logits = call.empty([B, A, C], torch.float32)
         g_codes = call.empty([B, A, 4], torch.float32)
         _lib.check(_lib.load().ssdk_ssd_loss_backward(
@@ -408,8 +421,7 @@ class SSD:
         g_logits, g_codes = call.empty([B, A, C], torch.float32), call.empty([B, A, 4], torch.float32)
         up = None
         if upstream is not None:
-            up = call.tensor(upstream, torch.float32, (2,)) if isinstance(upstream, torch.Tensor) else \
-                torch.tensor([float(upstream[0]), float(upstream[1])], dtype=torch.float32, device=logits.device)
+            up = _upstream_tensor(call, upstream, logits.device)
         ctx = call.ctx()
         _lib.check(lib.ssdk_training_targets_count(ctx, ptr(anchors), A, ptr(gt), ptr(labels), ptr(num), B, G,
                                                    float(this_module.POSITIVES_THRESHOLD), float(this_module.NEGATIVES_THRESHOLD),
@@ -437,8 +449,7 @@ class SSD:
         g_cls, g_box, gd = self._head_grads(call, head)
         up = None
         if upstream is not None:
-            up = call.tensor(upstream, torch.float32, (2,)) if isinstance(upstream, torch.Tensor) else \
-                torch.tensor([float(upstream[0]), float(upstream[1])], dtype=torch.float32, device=head.device)
+            up = _upstream_tensor(call, upstream, head.device)
         ctx = call.ctx()
         self._reduce_count(ctx, count)
         d = head.descriptor()
