@@ -178,7 +178,9 @@ SSDK_API int ssdk_loss_finalize(ssdk_ctx* ctx, const double* sums, float* out_lo
 
 /* Whole training-side hot path for a batch of images resident in HBM:
  * targets (ssd.py:84) + losses (ssd.py:89-133).  Any of out_reg/out_cls/out_matches may be NULL,
- * in which case context workspace is used for them. */
+ * in which case context workspace is used for them.  Without per-anchor outputs (out_cls_losses == out_loc_losses == NULL)
+ * the loss is computed as a flat pass over the logits plus corrections for the matched / ignored anchors, and the matcher
+ * runs on the context's side stream concurrently with the flat pass (joined before the corrections). */
 SSDK_API int ssdk_ssd_targets_and_loss(ssdk_ctx* ctx, const float* anchors, const float* logits,
                               const float* codes, const float* gt_boxes, const int32_t* gt_labels,
                               const int32_t* num_boxes, int B, int64_t A, int C, int Gmax,
@@ -263,6 +265,13 @@ SSDK_API int ssdk_head_concat(ssdk_ctx* ctx, const ssdk_head* head, int B, int C
  * matches [B,A] are in anchor order (as ssdk_training_targets writes them); out_sums as ssdk_ssd_loss. */
 SSDK_API int ssdk_head_ssd_loss(ssdk_ctx* ctx, const ssdk_head* head, const float* reg_targets, const int32_t* cls_targets,
                        const int32_t* matches, int B, int64_t A, int C, double gamma, double alpha, double* out_sums);
+/* ssdk_ssd_targets_and_loss on the per-level head tensors: target assignment (ssd.py:84) + losses (ssd.py:89-133).  The flat
+ * pass over the logits needs no targets, so the matcher runs on the context's side stream concurrently with it (ALU-bound
+ * matching hidden behind the HBM-bound stream); any of out_reg / out_cls / out_matches may be NULL (workspace is used). */
+SSDK_API int ssdk_head_ssd_targets_and_loss(ssdk_ctx* ctx, const ssdk_head* head, const float* anchors, const float* gt_boxes,
+                                   const int32_t* gt_labels, const int32_t* num_boxes, int B, int64_t A, int C, int Gmax,
+                                   double positives_threshold, double negatives_threshold, double gamma, double alpha,
+                                   double* out_sums, float* out_reg, int32_t* out_cls, int32_t* out_matches);
 /* ssdk_ssd_loss_forward_backward on the per-level head tensors: one pass over the logits produces the loss sums and
  * the gradients, written per level in the head's own layout (every element of `grads` is written).
  * out_sums may be NULL (backward only).  num_matches, upstream as ssdk_ssd_loss_forward_backward. */

@@ -54,6 +54,7 @@ _SIGNATURES = {
     'ssdk_postprocess_host': (c_int, [P, P, P, P, c_int, c_int, c_i64, c_int, c_double, c_double, c_int, P, P, P, P]),
     'ssdk_head_concat': (c_int, [P, P, c_int, c_int, P, P]),
     'ssdk_head_ssd_loss': (c_int, [P, P, P, P, P, c_int, c_i64, c_int, c_double, c_double, P]),
+    'ssdk_head_ssd_targets_and_loss': (c_int, [P, P, P, P, P, P, c_int, c_i64, c_int, c_int, c_double, c_double, c_double, c_double, P, P, P, P]),
     'ssdk_head_ssd_loss_forward_backward': (c_int, [P, P, P, P, P, c_int, c_i64, c_int, c_double, c_double, P, P, P, P]),
     'ssdk_head_detect': (c_int, [P, P, P, c_int, c_int, c_i64, c_int, c_double, c_double, c_int, P, c_double, P, P, P, P, P]),
     'ssdk_level_summaries': (c_int, [P, P, P, c_int, c_i64, P, c_int, c_double, P, P, P]),

@@ -419,12 +419,10 @@ int ssdk_head_geom(const ssdk_head* head, int B, int64_t A, int C, bool need_cls
     return SSDK_OK;
 }
 
-static int head_loss_impl(ssdk_ctx* ctx, const ssdk_head* head, const float* reg_targets, const int32_t* cls_targets,
-                          const int32_t* matches, int B, int64_t A, int C, double gamma, double alpha, const double* num_matches,
-                          const float* upstream, double* out_sums, const ssdk_head_grads* grads, bool with_grad) {
-    SSDK_TRY(ssdk_ctx_enter(ctx));
-    HeadGeom G;
-    SSDK_TRY(ssdk_head_geom(head, B, A, C, true, true, &G));
+// phases: 1 = the flat pass (needs no targets), 2 = the matched / ignored anchors + final reduction, 3 = both
+int ssdk_head_loss_core(ssdk_ctx* ctx, const HeadGeom& G, const float* reg_targets, const int32_t* cls_targets,
+                        const int32_t* matches, int B, int64_t A, int C, double gamma, double alpha, const double* num_matches,
+                        const float* upstream, double* out_sums, const ssdk_head_grads* grads, bool with_grad, int phases) {
     const long long NA = (long long)B * A;
     if (NA == 0) {
         if (out_sums) SSDK_CHECK_CUDA(cudaMemsetAsync(out_sums, 0, 3 * sizeof(double), ctx->stream));
@@ -493,13 +491,15 @@ static int head_loss_impl(ssdk_ctx* ctx, const ssdk_head* head, const float* reg
     const bool g2 = (gamma == 2.0);
 #define SSDK_LAUNCH_HEAD(GM, WG)                                                                                              \
     do {                                                                                                                      \
-        SSDK_KERNEL(ctx, SSDK_K_HEAD_FLAT,                                                                                    \
-                    head_flat_kernel<GM, WG><<<(int)grid_flat, FLAT_THREADS, 0, ctx->stream>>>(S, gf, af, num_matches, upstream, \
-                                                                                              flat_partials));                 \
-        SSDK_KERNEL(ctx, SSDK_K_HEAD_ROWS,                                                                                    \
-                    head_rows_kernel<GM, WG><<<(int)grid_rows, ROWS_THREADS, 0, ctx->stream>>>(                               \
-                        G, GR, (const float4*)reg_targets, cls_targets, matches, (int)A, NA, gf, af, num_matches, upstream,   \
-                        flat_partials, (int)grid_flat, rows_partials, ticket, out_sums));                                     \
+        if (phases & 1)                                                                                                       \
+            SSDK_KERNEL(ctx, SSDK_K_HEAD_FLAT,                                                                                \
+                        head_flat_kernel<GM, WG><<<(int)grid_flat, FLAT_THREADS, 0, ctx->stream>>>(S, gf, af, num_matches,    \
+                                                                                                  upstream, flat_partials)); \
+        if (phases & 2)                                                                                                       \
+            SSDK_KERNEL(ctx, SSDK_K_HEAD_ROWS,                                                                                \
+                        head_rows_kernel<GM, WG><<<(int)grid_rows, ROWS_THREADS, 0, ctx->stream>>>(                           \
+                            G, GR, (const float4*)reg_targets, cls_targets, matches, (int)A, NA, gf, af, num_matches, upstream, \
+                            flat_partials, (int)grid_flat, rows_partials, ticket, out_sums));                                 \
     } while (0)
     if (g2 && !with_grad) SSDK_LAUNCH_HEAD(0, false);
     else if (g2) SSDK_LAUNCH_HEAD(0, true);
@@ -509,7 +509,79 @@ static int head_loss_impl(ssdk_ctx* ctx, const ssdk_head* head, const float* reg
     return SSDK_OK;
 }
 
+static int head_loss_impl(ssdk_ctx* ctx, const ssdk_head* head, const float* reg_targets, const int32_t* cls_targets,
+                          const int32_t* matches, int B, int64_t A, int C, double gamma, double alpha, const double* num_matches,
+                          const float* upstream, double* out_sums, const ssdk_head_grads* grads, bool with_grad) {
+    SSDK_TRY(ssdk_ctx_enter(ctx));
+    HeadGeom G;
+    SSDK_TRY(ssdk_head_geom(head, B, A, C, true, true, &G));
+    return ssdk_head_loss_core(ctx, G, reg_targets, cls_targets, matches, B, A, C, gamma, alpha, num_matches, upstream, out_sums,
+                               grads, with_grad, 3);
+}
+
+// HeadGeom of the anchor-major tensors [B,A,C] / [B,A,4]: one channels_last "level" with one anchor per location
+HeadGeom ssdk_flat_geom(const float* logits, const float* codes, int64_t A, int C) {
+    HeadGeom g;
+    g.num_levels = 1; g.per_loc = 1; g.channels_first = 0; g.C = C;
+    for (int l = 0; l < SSDK_MAX_LEVELS; ++l) { g.anchor_off[l] = l ? (int)A : 0; g.hw[l] = 0; g.cls[l] = nullptr; g.box[l] = nullptr; }
+    g.anchor_off[SSDK_MAX_LEVELS] = (int)A;
+    g.hw[0] = (int)A; g.cls[0] = logits; g.box[0] = codes;
+    return g;
+}
+
+int ssdk_match_impl(ssdk_ctx* ctx, const float* anchors, int64_t A, const float* gt_boxes, const int32_t* gt_labels,
+                    const int32_t* num_boxes, int B, int Gmax, double pos_thr, double neg_thr, int force,
+                    float* out_reg, int32_t* out_cls, int32_t* out_matches, double* out_count = nullptr);
+
+// Forward loss of a batch with target assignment: the flat pass needs no targets, so the (ALU-bound) matcher runs on the
+// context's side stream WHILE the (HBM-bound) flat pass streams the logits; the rows kernel joins both.
+int ssdk_targets_and_loss_overlapped(ssdk_ctx* ctx, const HeadGeom& G, const float* anchors, const float* gt_boxes,
+                                     const int32_t* gt_labels, const int32_t* num_boxes, int B, int64_t A, int C, int Gmax,
+                                     double pos_thr, double neg_thr, double gamma, double alpha, double* out_sums, float* out_reg,
+                                     int32_t* out_cls, int32_t* out_matches) {
+    const size_t NA = (size_t)B * (size_t)A;
+    if (!out_reg) { SSDK_TRY(ssdk_ensure(ctx, &ctx->ws_reg, NA * 16 + 16)); out_reg = (float*)ctx->ws_reg.p; }
+    if (!out_cls) { SSDK_TRY(ssdk_ensure(ctx, &ctx->ws_cls, NA * 4 + 16)); out_cls = (int32_t*)ctx->ws_cls.p; }
+    if (!out_matches) { SSDK_TRY(ssdk_ensure(ctx, &ctx->ws_matches, NA * 4 + 16)); out_matches = (int32_t*)ctx->ws_matches.p; }
+    SSDK_REQUIRE(out_sums != nullptr, SSDK_ERR_ARG, "targets_and_loss: out_sums is NULL");
+    if (NA == 0) {
+        SSDK_CHECK_CUDA(cudaMemsetAsync(out_sums, 0, 3 * sizeof(double), ctx->stream));
+        return SSDK_OK;
+    }
+    cudaStream_t main_stream = ctx->stream, side = ctx->copy_stream;
+    // fork: everything already queued on the main stream (e.g. the producer of the logits / ground truth) precedes the matcher
+    SSDK_CHECK_CUDA(cudaEventRecord(ctx->ev[0], main_stream));
+    SSDK_CHECK_CUDA(cudaStreamWaitEvent(side, ctx->ev[0], 0));
+    ctx->stream = side;
+    int st = ssdk_match_impl(ctx, anchors, A, gt_boxes, gt_labels, num_boxes, B, Gmax, pos_thr, neg_thr, 1, out_reg, out_cls,
+                             out_matches);                                                    // ssd.py:84
+    ctx->stream = main_stream;
+    if (st == SSDK_OK) {
+        st = cudaEventRecord(ctx->ev[1], side) == cudaSuccess ? SSDK_OK : SSDK_ERR_CUDA;
+        if (st != SSDK_OK) ssdk_set_error("cudaEventRecord failed on the side stream");
+    }
+    if (st == SSDK_OK)
+        st = ssdk_head_loss_core(ctx, G, out_reg, out_cls, out_matches, B, A, C, gamma, alpha, nullptr, nullptr, out_sums, nullptr,
+                                 false, 1);                                                   // flat pass, concurrently
+    // join (also on the error paths, so that a stream capture in progress is never left forked)
+    cudaStreamWaitEvent(main_stream, ctx->ev[1], 0);
+    SSDK_TRY(st);
+    return ssdk_head_loss_core(ctx, G, out_reg, out_cls, out_matches, B, A, C, gamma, alpha, nullptr, nullptr, out_sums, nullptr,
+                               false, 2);                                                     // ssd.py:89-133
+}
+
 extern "C" {
+
+int ssdk_head_ssd_targets_and_loss(ssdk_ctx* ctx, const ssdk_head* head, const float* anchors, const float* gt_boxes,
+                                   const int32_t* gt_labels, const int32_t* num_boxes, int B, int64_t A, int C, int Gmax,
+                                   double positives_threshold, double negatives_threshold, double gamma, double alpha,
+                                   double* out_sums, float* out_reg, int32_t* out_cls, int32_t* out_matches) {
+    SSDK_TRY(ssdk_ctx_enter(ctx));
+    HeadGeom G;
+    SSDK_TRY(ssdk_head_geom(head, B, A, C, true, true, &G));
+    return ssdk_targets_and_loss_overlapped(ctx, G, anchors, gt_boxes, gt_labels, num_boxes, B, A, C, Gmax, positives_threshold,
+                                            negatives_threshold, gamma, alpha, out_sums, out_reg, out_cls, out_matches);
+}
 
 int ssdk_head_ssd_loss(ssdk_ctx* ctx, const ssdk_head* head, const float* reg_targets, const int32_t* cls_targets,
                        const int32_t* matches, int B, int64_t A, int C, double gamma, double alpha, double* out_sums) {

@@ -6,6 +6,13 @@ int ssdk_match_impl(ssdk_ctx* ctx, const float* anchors, int64_t A, const float*
                     const int32_t* num_boxes, int B, int Gmax, double pos_thr, double neg_thr, int force,
                     float* out_reg, int32_t* out_cls, int32_t* out_matches, double* out_count = nullptr);
 
+struct HeadGeom;
+HeadGeom ssdk_flat_geom(const float* logits, const float* codes, int64_t A, int C);
+int ssdk_targets_and_loss_overlapped(ssdk_ctx* ctx, const HeadGeom& G, const float* anchors, const float* gt_boxes,
+                                     const int32_t* gt_labels, const int32_t* num_boxes, int B, int64_t A, int C, int Gmax,
+                                     double pos_thr, double neg_thr, double gamma, double alpha, double* out_sums, float* out_reg,
+                                     int32_t* out_cls, int32_t* out_matches);
+
 template <typename T>
 static int stage_h2d(ssdk_ctx* ctx, int slot, const T* host, size_t count, T** dev) {
     *dev = nullptr;
@@ -25,6 +32,14 @@ int ssdk_ssd_targets_and_loss(ssdk_ctx* ctx, const float* anchors, const float* 
                               float* out_loc_losses) {
     SSDK_TRY(ssdk_ctx_enter(ctx));
     SSDK_REQUIRE(B >= 0 && A >= 0, SSDK_ERR_ARG, "ssdk_ssd_targets_and_loss: bad sizes");
+    if (!out_cls_losses && !out_loc_losses && C > 0 && A < (1ll << 31) && logits && codes && (((uintptr_t)logits | (uintptr_t)codes) & 15) == 0 &&
+        (long long)A * (C > 4 ? C : 4) < (1ll << 31)) {
+        // no per-anchor outputs wanted: flat pass + matched-anchor corrections (csrc/head.cu), with the matcher running on the
+        // side stream behind the flat pass.  The anchor-major tensors are a one-level channels_last head.
+        const HeadGeom G = ssdk_flat_geom(logits, codes, A, C);
+        return ssdk_targets_and_loss_overlapped(ctx, G, anchors, gt_boxes, gt_labels, num_boxes, B, A, C, Gmax, pos_thr, neg_thr,
+                                                gamma, alpha, out_sums, out_reg, out_cls, out_matches);
+    }
     const size_t NA = (size_t)B * (size_t)A;
     if (!out_reg) { SSDK_TRY(ssdk_ensure(ctx, &ctx->ws_reg, NA * 16 + 16)); out_reg = (float*)ctx->ws_reg.p; }
     if (!out_cls) { SSDK_TRY(ssdk_ensure(ctx, &ctx->ws_cls, NA * 4 + 16)); out_cls = (int32_t*)ctx->ws_cls.p; }

@@ -277,13 +277,22 @@ class SSD:
 
     def _loss_sums_head(self, head, groundtruth, params, keep_targets):
         """loss_sums on the per-level tower outputs: targets (ssd.py:84), then ssdk_head_ssd_loss."""
+        from . import ssd as this_module
         call = Call(head.device)
         B, A, C = head.batch_size, head.num_anchors, head.num_classes
-        reg, cls_t, matches = self._targets_into(call, groundtruth, B, A)
+        anchors = call.tensor(self.anchors, torch.float32, (A, 4))
+        gt = call.tensor(groundtruth['boxes'], torch.float32)
+        G = gt.shape[1]
+        labels = call.tensor(groundtruth['labels'], torch.int32, (B, G))
+        num = call.tensor(groundtruth['num_boxes'], torch.int32, (B,))
+        reg, cls_t, matches = call.empty([B, A, 4], torch.float32), call.empty([B, A], torch.int32), call.empty([B, A], torch.int32)
         sums = call.empty([3], torch.float64)
         d = head.descriptor()
-        _lib.check(_lib.load().ssdk_head_ssd_loss(call.ctx(), ctypes.byref(d), ptr(reg), ptr(cls_t), ptr(matches), B, A, C,
-                                                  float(params['gamma']), float(params['alpha']), ptr(sums)))
+        # targets (ssd.py:84) + losses (ssd.py:89-133); the matcher runs on the library's side stream behind the flat pass
+        _lib.check(_lib.load().ssdk_head_ssd_targets_and_loss(
+            call.ctx(), ctypes.byref(d), ptr(anchors), ptr(gt), ptr(labels), ptr(num), B, A, C, G,
+            float(this_module.POSITIVES_THRESHOLD), float(this_module.NEGATIVES_THRESHOLD), float(params['gamma']),
+            float(params['alpha']), ptr(sums), ptr(reg), ptr(cls_t), ptr(matches)))
         self._call = call
         if keep_targets:
             self._saved = dict(head=head, sums=sums, gamma=float(params['gamma']), alpha=float(params['alpha']),
