@@ -53,6 +53,12 @@ SSDK_API const char* ssdk_last_error(void);
 /* stream: a cudaStream_t (NULL = legacy default stream).  Creates the context on `device`. */
 SSDK_API int ssdk_ctx_create(int device, void* stream, ssdk_ctx** out);
 SSDK_API int ssdk_ctx_set_stream(ssdk_ctx* ctx, void* stream);
+/* Options.  SSDK_OPT_OVERLAP_MATCHER (default 1): ssdk_ssd_targets_and_loss / ssdk_head_ssd_targets_and_loss run the
+ * (ALU-bound) matcher on the context's side stream concurrently with the (HBM-bound) flat pass over the logits.  Set it to
+ * 0 when the caller already keeps the GPU busy with other work on a second stream (e.g. the inference-side sub-path): the
+ * extra contention then costs more than the overlap gains. */
+#define SSDK_OPT_OVERLAP_MATCHER 1
+SSDK_API int ssdk_ctx_set_option(ssdk_ctx* ctx, int option, int value);
 SSDK_API int ssdk_ctx_destroy(ssdk_ctx* ctx);
 /* Bytes of private workspace currently held (grows on demand, never shrinks). */
 SSDK_API int64_t ssdk_ctx_workspace_bytes(const ssdk_ctx* ctx);

@@ -20,6 +20,7 @@ _SIGNATURES = {
     'ssdk_last_error': (ctypes.c_char_p, []),
     'ssdk_ctx_create': (c_int, [c_int, P, ctypes.POINTER(P)]),
     'ssdk_ctx_set_stream': (c_int, [P, P]),
+    'ssdk_ctx_set_option': (c_int, [P, c_int, c_int]),
     'ssdk_ctx_destroy': (c_int, [P]),
     'ssdk_ctx_workspace_bytes': (c_i64, [P]),
     'ssdk_ctx_launch_count': (c_i64, [P]),
@@ -150,6 +151,13 @@ def profile_read(device_index=0, reset=True):
     calls = (c_i64 * n)()
     check(load().ssdk_ctx_profile_read(context(device_index), ctypes.cast(ms, P), ctypes.cast(calls, P), n, 1 if reset else 0))
     return {k: (ms[i], int(calls[i])) for i, k in enumerate(KERNEL_IDS)}
+
+
+SSDK_OPT_OVERLAP_MATCHER = 1
+
+
+def set_option(option, value, device_index=0):
+    check(load().ssdk_ctx_set_option(context(device_index), int(option), int(value)))
 
 
 def launch_count(device_index=0):

@@ -130,6 +130,14 @@ int ssdk_ctx_create(int device, void* stream, ssdk_ctx** out) {
     return SSDK_OK;
 }
 
+int ssdk_ctx_set_option(ssdk_ctx* ctx, int option, int value) {
+    SSDK_REQUIRE(ctx != nullptr, SSDK_ERR_ARG, "null context");
+    switch (option) {
+        case SSDK_OPT_OVERLAP_MATCHER: ctx->overlap_matcher = value ? 1 : 0; return SSDK_OK;
+        default: ssdk_set_error("ssdk_ctx_set_option: unknown option %d", option); return SSDK_ERR_ARG;
+    }
+}
+
 int ssdk_ctx_set_stream(ssdk_ctx* ctx, void* stream) {
     SSDK_REQUIRE(ctx != nullptr, SSDK_ERR_ARG, "null context");
     ctx->stream = (cudaStream_t)stream;

@@ -47,6 +47,7 @@ struct ssdk_ctx {
     long long prof_calls[SSDK_K_COUNT] = {0};
     int sort_occupancy = 0;
     cudaStream_t copy_stream = nullptr;
+    int overlap_matcher = 1; // SSDK_OPT_OVERLAP_MATCHER
     void* comm = nullptr;    // peer-memory communicator (comm.cu), NULL until ssdk_comm_local_handle
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
 };

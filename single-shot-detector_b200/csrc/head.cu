@@ -548,6 +548,13 @@ int ssdk_targets_and_loss_overlapped(ssdk_ctx* ctx, const HeadGeom& G, const flo
         SSDK_CHECK_CUDA(cudaMemsetAsync(out_sums, 0, 3 * sizeof(double), ctx->stream));
         return SSDK_OK;
     }
+    const char* ov = getenv("SSDK_OVERLAP_MATCH");                  // "0" / SSDK_OPT_OVERLAP_MATCHER = 0: matcher on the caller's stream
+    if ((ov && ov[0] == '0') || !ctx->overlap_matcher) {
+        SSDK_TRY(ssdk_match_impl(ctx, anchors, A, gt_boxes, gt_labels, num_boxes, B, Gmax, pos_thr, neg_thr, 1, out_reg, out_cls,
+                                 out_matches));
+        return ssdk_head_loss_core(ctx, G, out_reg, out_cls, out_matches, B, A, C, gamma, alpha, nullptr, nullptr, out_sums, nullptr,
+                                   false, 3);
+    }
     cudaStream_t main_stream = ctx->stream, side = ctx->copy_stream;
     // fork: everything already queued on the main stream (e.g. the producer of the logits / ground truth) precedes the matcher
     SSDK_CHECK_CUDA(cudaEventRecord(ctx->ev[0], main_stream));

@@ -40,9 +40,14 @@ def concurrent(*fns, device=None):
         outs = []
         for st in streams:
             st.wait_stream(cur)
-        for st, fn in zip(streams, fns):
-            with torch.cuda.stream(st):
-                outs.append(fn())
+        # the caller provides the concurrency here: the library's own matcher / flat-pass overlap would only add contention
+        _lib.set_option(_lib.SSDK_OPT_OVERLAP_MATCHER, 0, dev.index)
+        try:
+            for st, fn in zip(streams, fns):
+                with torch.cuda.stream(st):
+                    outs.append(fn())
+        finally:
+            _lib.set_option(_lib.SSDK_OPT_OVERLAP_MATCHER, 1, dev.index)
         for st in streams:
             cur.wait_stream(st)
         return tuple(outs)
