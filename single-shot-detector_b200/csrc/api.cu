@@ -126,6 +126,13 @@ int ssdk_ctx_create(int device, void* stream, ssdk_ctx** out) {
     c->num_sms = prop.multiProcessorCount;
     SSDK_CHECK_CUDA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
     for (int i = 0; i < 4; ++i) SSDK_CHECK_CUDA(cudaEventCreateWithFlags(&c->ev[i], cudaEventDisableTiming));
+    if (cudaHostAlloc((void**)&c->hint_host, 2 * sizeof(int), cudaHostAllocMapped) == cudaSuccess) {
+        c->hint_host[0] = c->hint_host[1] = 0;
+        if (cudaHostGetDevicePointer((void**)&c->hint_dev, c->hint_host, 0) != cudaSuccess) c->hint_dev = nullptr;
+    } else {
+        cudaGetLastError();
+        c->hint_host = nullptr;
+    }
     *out = c;
     return SSDK_OK;
 }
@@ -157,6 +164,7 @@ int ssdk_ctx_destroy(ssdk_ctx* ctx) {
         for (int i = 0; i < 2 * SSDK_PROFILE_EVENTS; ++i) cudaEventDestroy(ctx->prof_ev[i]);
         delete[] ctx->prof_ev;
     }
+    if (ctx->hint_host) cudaFreeHost(ctx->hint_host);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     for (int i = 0; i < 4; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
     delete ctx;

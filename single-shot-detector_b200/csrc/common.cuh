@@ -48,6 +48,8 @@ struct ssdk_ctx {
     int sort_occupancy = 0;
     cudaStream_t copy_stream = nullptr;
     int overlap_matcher = 1; // SSDK_OPT_OVERLAP_MATCHER
+    int* hint_host = nullptr; // mapped pinned int[2]: [0] = large segments met by the last post-processing call (density hint)
+    int* hint_dev = nullptr;  // device alias of hint_host
     void* comm = nullptr;    // peer-memory communicator (comm.cu), NULL until ssdk_comm_local_handle
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
 };

@@ -457,3 +457,38 @@ def test_matched_count_from_the_matching_kernel(pkg, golden, case, tag):
     m = mat.cpu().numpy()
     assert np.array_equal(m[0], want) and np.array_equal(m[2], want) and (m[1] == -1).all()
     assert cnt.item() == 2.0 * float((want >= 0).sum())
+
+
+@pytest.mark.parametrize('kind', ['dense', 'realistic'])
+def test_dense_filter_kernel_equals_the_sparse_one(pkg, kind, monkeypatch):
+    """The CTA-aggregated candidate append used for dense scores (chosen by a hint from the previous call, or forced with
+    SSDK_FILTER_DENSE) must produce exactly the detections of the per-candidate append, for any input."""
+    from oracle import losses as olosses, nms as onms
+    from oracle.anchor_generator import AnchorGenerator as OracleGen
+    syn = load_pkg('synthetic')
+    H, W, C, B, K = 200, 333, 7, 3, 12
+    anchors = OracleGen(scale_multipliers=[1.0, 1.4142])(H, W)
+    A = anchors.shape[0]
+    gt = syn.make_groundtruth(55, B, 8, H, W, C)
+    logits = syn.make_logits(kind, 55, B, A, C, anchors, gt) if kind == 'realistic' else syn.make_logits(kind, 55, B, A, C)
+    logits = logits[:, :, :C].copy()
+    codes = (syn.make_codes(55, B, A) * np.float32(0.5)).astype(np.float32)
+    gen = pkg.AnchorGenerator(scale_multipliers=[1.0, 1.4142])
+    # an odd image stride (A*C*4 bytes not a multiple of 16) exercises the unaligned head / tail of every image
+    ssd = pkg.SSD.from_predictions(H, W, {'encoded_boxes': cuda(codes), 'class_predictions': cuda(logits)}, gen, C)
+    monkeypatch.setenv('SSDK_FILTER_DENSE', '0')
+    sparse = ssd.get_predictions(0.05, 0.5, K)
+    monkeypatch.setenv('SSDK_FILTER_DENSE', '1')
+    dense = ssd.get_predictions(0.05, 0.5, K)
+    monkeypatch.delenv('SSDK_FILTER_DENSE')
+    hinted = ssd.get_predictions(0.05, 0.5, K)          # whichever kernel the hint selects
+    for k in ('boxes', 'labels', 'scores', 'num_boxes'):
+        assert torch.equal(sparse[k], dense[k]) and torch.equal(sparse[k], hinted[k]), k
+    want = onms.batch_multiclass_non_max_suppression(codes, anchors, olosses.sigmoid(logits), 0.05, 0.5, K)
+    assert np.array_equal(dense['num_boxes'].cpu().numpy(), want[3]) and want[3].sum() > 0
+    assert np.array_equal(dense['labels'].cpu().numpy(), want[2])
+    close(dense['boxes'].cpu().numpy(), want[0], atol=1e-7)
+    # scores given as probabilities (batch_multiclass_non_max_suppression) through the dense kernel
+    monkeypatch.setenv('SSDK_FILTER_DENSE', '1')
+    b, s, c, n = pkg.batch_multiclass_non_max_suppression(cuda(codes), cuda(anchors), cuda(olosses.sigmoid(logits)), 0.05, 0.5, K)
+    assert np.array_equal(n.cpu().numpy(), want[3]) and np.array_equal(c.cpu().numpy(), want[2])
