@@ -20,6 +20,6 @@ if [ "$MODE" = "full" ]; then
       python bench.py --steps 3 --warmup 3 --no-cpu-baseline --e2e-steps 1 --no-graph > $OUT/${TAG}_ncu_bench.log 2>&1
   timeout 900 ncu --set full --clock-control none --import-source on \
       -k regex:'ssd_loss_kernel|ssd_loss_backward_kernel|filter_kernel|nms_kernel|nms_small_kernel|match_kernel|pack_kernel|head_flat_kernel|head_rows_kernel' \
-      -s 40 -c 40 -f -o $OUT/${TAG}_prof python bench.py --steps 2 --warmup 3 --no-cpu-baseline --e2e-steps 1 --no-graph > $OUT/${TAG}_ncu_full.log 2>&1
+      -s 60 -c 36 -f -o $OUT/${TAG}_prof python bench.py --steps 2 --warmup 3 --no-cpu-baseline --e2e-steps 1 --no-graph > $OUT/${TAG}_ncu_full.log 2>&1
   ls -la $OUT
 fi
