@@ -378,7 +378,10 @@ __device__ __forceinline__ int select_best_keys(const unsigned long long* __rest
             if (upto <= cap || shift == 0) {                        // shift == 0: buckets hold single keys (keys are unique)
                 s_int[0] = 1;
                 s_u64[0] = (b == nb - 1 && shift + bits >= 64) ? ~0ull : (prefix | ((unsigned long long)(b + 1) << shift));
-                if (b == nb - 1) s_u64[0] = ((prefix >> hi) + 1ull) << hi;     // whole boundary bucket: next prefix
+                if (b == nb - 1) {                                          // whole boundary bucket: threshold = next prefix
+                    const unsigned long long next = ((prefix >> hi) + 1ull) << hi;
+                    s_u64[0] = next > prefix ? next : ~0ull;                     // (wrap-around: nothing lies above)
+                }
             } else {
                 s_int[0] = 0;
                 s_int[1] = lo;
