@@ -492,3 +492,70 @@ def test_dense_filter_kernel_equals_the_sparse_one(pkg, kind, monkeypatch):
     monkeypatch.setenv('SSDK_FILTER_DENSE', '1')
     b, s, c, n = pkg.batch_multiclass_non_max_suppression(cuda(codes), cuda(anchors), cuda(olosses.sigmoid(logits)), 0.05, 0.5, K)
     assert np.array_equal(n.cpu().numpy(), want[3]) and np.array_equal(c.cpu().numpy(), want[2])
+
+
+# ------------------------------------------------------------------------------------------------ sharding / launching
+def test_cfg4_batch_256_sharded_like_8_ranks(pkg):
+    """BASELINE.json configs[3]: batch 256 at 640x896 split into 8 image shards of 32 (what 8 ranks hold).  Per-shard sums add
+    up to the full-batch sums (count exactly, losses to 1e-9), and a shard's fused forward+backward step, given the GLOBAL
+    matched count, produces exactly the full batch's gradients for its images (normaliser = global count, ssd.py:121-123)."""
+    syn = load_pkg('synthetic')
+    cfg = syn.CONFIGS[4]
+    H, W, C, B, G = cfg['H'], cfg['W'], cfg['C'], cfg['B'], cfg['G']
+    assert B == 256
+    gen = pkg.AnchorGenerator(scale_multipliers=cfg['scale_multipliers'])
+    A = gen.count(H, W)[0]
+    gt = {k: cuda(v) for k, v in syn.make_groundtruth(4, B, G, H, W, C).items()}
+    g = torch.Generator(device='cuda').manual_seed(4)
+    logits = torch.randn([B, A, C], device='cuda', generator=g) - 4.595
+    codes = torch.randn([B, A, 4], device='cuda', generator=g)
+    params = {'gamma': 2.0, 'alpha': 0.25}
+    full = pkg.SSD.from_predictions(H, W, {'encoded_boxes': codes, 'class_predictions': logits}, gen, C)
+    full_sums = full.loss_sums(gt, params).cpu().numpy()
+    _, full_grads = full.loss_with_gradients(gt, params)
+    total = np.zeros(3)
+    for r in range(8):
+        lo, hi = pkg.parallel.shard_range(B, r, 8)
+        assert (lo, hi) == (32 * r, 32 * r + 32)
+        shard = pkg.SSD.from_predictions(H, W, {'encoded_boxes': codes[lo:hi], 'class_predictions': logits[lo:hi]}, gen, C)
+        sgt = {k: v[lo:hi] for k, v in gt.items()}
+        total += shard.loss_sums(sgt, params).cpu().numpy()
+        if r in (0, 5):
+            shard.process_group = True                                  # stand-in for the all-reduce: the global count
+            shard._reduce_count = lambda ctx, count: count.fill_(float(full_sums[2]))
+            shard._reduce_and_finalize = lambda ctx, sums, out: None
+            _, grads = shard.loss_with_gradients(sgt, params)
+            assert torch.equal(grads['class_predictions'], full_grads['class_predictions'][lo:hi])
+            assert torch.equal(grads['encoded_boxes'], full_grads['encoded_boxes'][lo:hi])
+    assert total[2] == full_sums[2] and total[2] > 0
+    close(total[:2], full_sums[:2], rtol=1e-9)
+
+
+def test_concurrent_subpaths_and_options(pkg, golden):
+    """graph.concurrent: the training-side and the inference-side sub-path on two streams (eager and as parallel branches of a
+    captured graph) give exactly the results of the sequential calls; SSDK_OPT_OVERLAP_MATCHER does not change results."""
+    g = golden('losses')
+    H, W = [int(v) for v in g['HW']]
+    C = int(g['C'])
+    gen = pkg.AnchorGenerator(scale_multipliers=[1.0, 1.4142])
+    raw = {'encoded_boxes': cuda(g['codes']), 'class_predictions': cuda(g['logits'])}
+    ssd = pkg.SSD.from_predictions(H, W, raw, gen, C)
+    gt = {'boxes': cuda(g['gt_boxes']), 'labels': cuda(g['gt_labels']), 'num_boxes': cuda(g['num_boxes'])}
+    params = {'gamma': 2.0, 'alpha': 0.25}
+    want_l, want_p = ssd.loss(gt, params), ssd.get_predictions(0.05, 0.5, 10)
+    pkg._lib.set_option(pkg._lib.SSDK_OPT_OVERLAP_MATCHER, 0)
+    l0 = ssd.loss(gt, params)
+    pkg._lib.set_option(pkg._lib.SSDK_OPT_OVERLAP_MATCHER, 1)
+    assert float(l0['classification_loss']) == float(want_l['classification_loss'])
+    assert float(l0['localization_loss']) == float(want_l['localization_loss'])
+    both = pkg.graph.concurrent(lambda: ssd.loss(gt, params), lambda: ssd.get_predictions(0.05, 0.5, 10))
+    for run in (both, pkg.graph.capture(both).replay):
+        for _ in range(3):
+            l, p = run()
+            torch.cuda.synchronize()
+            assert float(l['classification_loss']) == float(want_l['classification_loss'])
+            assert float(l['localization_loss']) == float(want_l['localization_loss'])
+            for k in ('boxes', 'labels', 'scores', 'num_boxes'):
+                assert torch.equal(p[k], want_p[k]), k
+    with pytest.raises(ValueError):
+        pkg._lib.set_option(99, 1)
