@@ -534,6 +534,31 @@ def run_ours(args):
         head = {'error': str(e)[:300]}
         torch.cuda.synchronize()
 
+    # ---- BASELINE.json configs[0] (the reference's own CPU-runnable case: config_mobilenet anchor set, one 640x640 image,
+    #      20 GT boxes, matching + focal loss) and single-image inference latency (inference/detector.py serves one image)
+    small = None
+    try:
+        c1 = syn.CONFIGS[1]
+        gen1 = pkg.AnchorGenerator(scale_multipliers=c1['scale_multipliers'])
+        anc1 = gen1(c1['H'], c1['W'], device=dev)
+        A1, C1 = anc1.shape[0], c1['C']
+        gt1 = syn.make_groundtruth(1, 1, c1['G'], c1['H'], c1['W'], C1)
+        log1 = syn.make_logits('train', 1, 1, A1, C1)
+        cod1 = syn.make_codes(1, 1, A1)
+        ssd1 = pkg.SSD.from_predictions(c1['H'], c1['W'], {'encoded_boxes': torch.from_numpy(cod1).to(dev),
+                                                           'class_predictions': torch.from_numpy(log1).to(dev)}, gen1, C1)
+        d_gt1 = {k: torch.from_numpy(v).to(dev) for k, v in gt1.items()}
+        ms_cfg1 = timed(lambda: ssd1.loss(d_gt1, PARAMS), args.steps)
+        l1 = ssd1.loss(d_gt1, PARAMS)
+        ssd_b1 = pkg.SSD.from_predictions(H, W, {'encoded_boxes': d_icod[:1].contiguous(), 'class_predictions': d_ilog[:1].contiguous()}, gen, C)
+        ms_b1 = timed(lambda: ssd_b1.get_predictions(SCORE_THR, IOU_THR, K_PER_CLASS), args.steps)
+        small = {'cfg1_train_one_image_640x640_ms': ms_cfg1, 'cfg1_anchors': int(A1), 'cfg1_classes': int(C1),
+                 'cfg1_check': {'localization_loss': float(l1['localization_loss']), 'classification_loss': float(l1['classification_loss'])},
+                 'infer_latency_one_image_640x896_ms': ms_b1, '_inputs': (anc1.cpu().numpy(), cod1, log1, gt1, C1)}
+    except Exception as e:
+        small = {'error': str(e)[:300]}
+        torch.cuda.synchronize()
+
     # ---- timed region 2 (e2e): the same step through the public API with HOST buffers; every step copies its inputs
     #      from pinned host memory to the device and reads the results back (ssdk_*_host entry points)
     h_raw_t = {'encoded_boxes': h_tcod.numpy(), 'class_predictions': h_tlog.numpy()}
@@ -582,6 +607,14 @@ def run_ours(args):
                'sample': '2 steps x (%d train + %d infer images) of the same workload, oracle port (NumPy f32 op-for-op + C '
                          'NonMaxSuppressionV3), one image per thread-pool task' % (n_t, n_i)}
 
+    if small and '_inputs' in small:
+        anc1_np, cod1, log1, gt1, C1 = small.pop('_inputs')
+        if world == 1 and not args.no_cpu_baseline:            # the same single image through the CPU port
+            from oracle import ssd as ossd
+            t0 = time.perf_counter()
+            o1 = ossd.loss(anc1_np, cod1, log1, gt1, PARAMS, C1)
+            small['cfg1_cpu_port_ms'] = (time.perf_counter() - t0) * 1e3
+            small['cfg1_cpu_port_check'] = {'localization_loss': float(o1['localization_loss']), 'classification_loss': float(o1['classification_loss'])}
     line = {
         'metric': 'images_per_sec_target_assign_focal_loss_and_decode_nms_896x640',
         'value': value, 'unit': 'images/s', 'n_gpus': world, 'steps': args.steps, 'warmup': max(args.warmup, 3),
@@ -606,6 +639,7 @@ def run_ours(args):
             'train_fwd_bwd_images_per_sec': Bt * world / (ms_train_fb * 1e-3), 'train_fwd_bwd_ms_per_step': ms_train_fb,
             'train_fwd_bwd_frac_of_hbm_roofline': ((b_train + 8 * A * C // 2 + 16 * A) * Bt / (ms_train_fb * 1e-3) / 1e9) / peak,
             'head_layout': head,
+            'small_cases': small,
             'sub_path_timings_that_fell_back_to_eager_launches': eager_fallbacks,
             'train_ms_per_step_with_nccl_all_reduce': ms_train_nccl,
         },

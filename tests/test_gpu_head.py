@@ -314,3 +314,39 @@ def test_level_summaries(pkg, syn):
     r = ssd.level_summaries(cls_losses=const, loc_losses=torch.zeros_like(const))
     assert (r['classification_losses']['topk_mean'] == 0.25).all() and (r['classification_losses']['topk_kth'] == 0.25).all()
     assert (r['localization_losses']['topk_mean'] == 0).all()
+
+
+def test_head_c_abi_argument_errors(pkg):
+    """The C entry points reject malformed head descriptors with a status and a message (no crash, no fallback)."""
+    import ctypes
+    lib_mod = pkg._lib
+    lib = lib_mod.load()
+    ctx = lib_mod.context(0)
+    x = torch.zeros([1, 2 * 3, 2, 2], device='cuda')
+    bx = torch.zeros([1, 2 * 4, 2, 2], device='cuda')
+    sums = torch.zeros(3, dtype=torch.float64, device='cuda')
+    reg = torch.zeros([1, 8, 4], device='cuda'); cls = torch.zeros([1, 8], dtype=torch.int32, device='cuda')
+    mat = torch.full([1, 8], -1, dtype=torch.int32, device='cuda')
+
+    def desc(levels=1, n=2, fmt=1, h=2, w=2, cp=None, bp=None):
+        d = lib_mod.SsdkHead()
+        d.num_levels, d.anchors_per_location, d.data_format = levels, n, fmt
+        d.height[0], d.width[0] = h, w
+        d.class_predictions[0] = x.data_ptr() if cp is None else cp
+        d.encoded_boxes[0] = bx.data_ptr() if bp is None else bp
+        return d
+
+    def call(d, A=8, C=3):
+        return lib.ssdk_head_ssd_loss(ctx, ctypes.byref(d), reg.data_ptr(), cls.data_ptr(), mat.data_ptr(), 1, A, C, 2.0, 0.25,
+                                      sums.data_ptr())
+    assert call(desc()) == 0
+    torch.cuda.synchronize()
+    assert sums[2].item() == 0 and sums[0].item() == 0 and abs(sums[1].item() - 0.75 * 24 * 0.25 * np.log(2.0)) < 1e-6
+    for bad, code in ((desc(levels=0), -1), (desc(levels=9), -1), (desc(n=0), -1), (desc(fmt=7), -1), (desc(h=3), -2),
+                      (desc(cp=x.data_ptr() + 4), -2), (desc(cp=0), -1)):
+        assert call(bad) == code, lib.ssdk_last_error()
+        assert lib.ssdk_last_error()
+    assert call(desc(), A=9) == -2 and b'anchors' in lib.ssdk_last_error()
+    assert lib.ssdk_head_ssd_loss(ctx, None, reg.data_ptr(), cls.data_ptr(), mat.data_ptr(), 1, 8, 3, 2.0, 0.25, sums.data_ptr()) == -1
+    assert lib.ssdk_head_detect(ctx, ctypes.byref(desc()), None, 1, 1, 8, 3, 0.05, 0.5, 10, None, float('-inf'), None, None, None, None,
+                                None) == -1

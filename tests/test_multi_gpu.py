@@ -62,6 +62,17 @@ if peer:
     for _ in range(4):
         r = step.replay()
         replays.append([float(r['localization_loss']), float(r['classification_loss'])])
+    # head layout (per-level tower outputs) on the sharded batch, with the peer all-reduce
+    from oracle import box_predictor as obp
+    shapes = obp.level_shapes(H, W, gen.strides)
+    n_loc = gen.num_anchors_per_location
+    hssd = pkg.SSD.from_head_outputs(H, W, [cuda(t) for t in obp.split_to_levels(codes[lo:hi], shapes, n_loc)],
+                                     [cuda(t) for t in obp.split_to_levels(logits[lo:hi], shapes, n_loc)], gen, C)
+    hssd.process_group, hssd.peer_all_reduce = True, True
+    res_h = hssd.loss(sgt, dict(gamma=2.0, alpha=0.25))
+    l_hfb, _ = hssd.loss_with_gradients(sgt, dict(gamma=2.0, alpha=0.25))
+    peer_out.update(head=[float(res_h['localization_loss']), float(res_h['classification_loss'])],
+                    head_fb=[float(l_hfb['localization_loss']), float(l_hfb['classification_loss'])])
     peer_out.update(vals=vals, loc=float(res_p['localization_loss']), cls=float(res_p['classification_loss']),
                     fb=[float(l_fb['localization_loss']), float(l_fb['classification_loss'])],
                     fb_nccl=[float(l_nc['localization_loss']), float(l_nc['classification_loss'])],
@@ -128,6 +139,10 @@ def test_two_gpu_sharded_equals_single(tmp_path):
         assert (p['loc'], p['cls']) == (r['loc'], r['cls'])               # sums are added in rank order on every rank
         assert p['fb'] == p['fb_nccl'] and p['grads_equal']
         assert all(rep == [p['loc'], p['cls']] for rep in p['replays'])
+        for got in (p['head'], p['head_fb']):                             # head-layout path on the shards: the global losses
+            assert abs(got[0] - float(full['localization_loss'])) <= 1e-5 * abs(float(full['localization_loss']))
+            assert abs(got[1] - float(full['classification_loss'])) <= 1e-5 * abs(float(full['classification_loss']))
+    assert r0['peer']['head'] == r1['peer']['head'] and r0['peer']['head_fb'] == r1['peer']['head_fb']
     got = np.concatenate([np.array(r0['matches'], np.int32), np.array(r1['matches'], np.int32)])
     assert np.array_equal(got, full['matches'])                           # bit-exact across the shard boundary
     want = onms.batch_multiclass_non_max_suppression(codes, anchors, olosses.sigmoid(logits), 0.05, 0.5, 10)
