@@ -192,6 +192,7 @@ __global__ void __launch_bounds__(FLAT_THREADS) head_flat_kernel(const FlatSegs 
 
 // ---------------------------------------------------------------------------------------------- 2. matched / ignored anchors
 #define ROWS_THREADS 256
+#define ROWS_G 2                                          // 128-bit loads of `matches` in flight per lane
 template <int GAMMA_MODE, bool WITH_GRAD>
 __global__ void __launch_bounds__(ROWS_THREADS) head_rows_kernel(
     const HeadGeom G, const HeadGradPtrs GR, const float4* __restrict__ reg_t, const int* __restrict__ cls_t,
@@ -214,34 +215,45 @@ __global__ void __launch_bounds__(ROWS_THREADS) head_rows_kernel(
     // (-1, the overwhelming majority) cost nothing more.  The others -- matched anchors come in clusters around a box -- are
     // compacted into a per-warp queue and then handled ONE PER LANE, so that their dependent gathers (cls_target -> logit)
     // are in flight together instead of one after the other in the lane that happened to own four of them.
-    __shared__ int s_queue[ROWS_THREADS / 32][128];
+    __shared__ int s_queue[ROWS_THREADS / 32][128 * ROWS_G];
     int* queue = s_queue[warp];
     const unsigned lt_mask = (1u << lane) - 1u;
     const long long ngroups = (NA + 3) >> 2;
-    const long long stride = (long long)gridDim.x * ROWS_THREADS;
-    for (long long q0 = (long long)blockIdx.x * ROWS_THREADS; q0 < ngroups; q0 += stride) {
-        const long long q = q0 + tid;
-        int mm[4] = {-1, -1, -1, -1};
-        if (q < ngroups) {
-            if ((q << 2) + 3 < NA) {
-                const int4 v = __ldg((const int4*)matches + q);
-                mm[0] = v.x; mm[1] = v.y; mm[2] = v.z; mm[3] = v.w;
-            } else {
-                for (int j = 0; j < 4; ++j)
-                    if ((q << 2) + j < NA) mm[j] = __ldg(matches + (q << 2) + j);
+    const long long stride = (long long)gridDim.x * ROWS_THREADS * ROWS_G;
+    for (long long q0 = (long long)blockIdx.x * ROWS_THREADS * ROWS_G; q0 < ngroups; q0 += stride) {
+        // ROWS_G 128-bit loads of `matches` per lane, all issued before any is looked at; group u of the warp covers the 128
+        // anchors starting at (q0 + u * ROWS_THREADS + warp * 32) * 4
+        int mm[ROWS_G][4];
+#pragma unroll
+        for (int u = 0; u < ROWS_G; ++u) {
+            const long long q = q0 + u * ROWS_THREADS + tid;
+            mm[u][0] = mm[u][1] = mm[u][2] = mm[u][3] = -1;
+            if (q < ngroups) {
+                if ((q << 2) + 3 < NA) {
+                    const int4 v = __ldg((const int4*)matches + q);
+                    mm[u][0] = v.x; mm[u][1] = v.y; mm[u][2] = v.z; mm[u][3] = v.w;
+                } else {
+                    for (int j = 0; j < 4; ++j)
+                        if ((q << 2) + j < NA) mm[u][j] = __ldg(matches + (q << 2) + j);
+                }
             }
         }
-        const bool any_special = (mm[0] & mm[1] & mm[2] & mm[3]) != -1;
-        if (!__any_sync(0xffffffffu, any_special)) continue;             // warp-uniform: 128 background anchors
+        bool any_special = false;
+#pragma unroll
+        for (int u = 0; u < ROWS_G; ++u) any_special |= (mm[u][0] & mm[u][1] & mm[u][2] & mm[u][3]) != -1;
+        if (!__any_sync(0xffffffffu, any_special)) continue;             // warp-uniform: only background anchors
         int total = 0;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const unsigned bal = __ballot_sync(0xffffffffu, mm[j] != -1);
-            if (mm[j] != -1) queue[total + __popc(bal & lt_mask)] = lane * 4 + j;
-            total += __popc(bal);
+        for (int u = 0; u < ROWS_G; ++u) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const unsigned bal = __ballot_sync(0xffffffffu, mm[u][j] != -1);
+                if (mm[u][j] != -1) queue[total + __popc(bal & lt_mask)] = u * (ROWS_THREADS * 4) + lane * 4 + j;
+                total += __popc(bal);
+            }
         }
         __syncwarp();
-        const long long warp_base = (q0 + (tid & ~31)) << 2;             // first anchor of this warp's 128
+        const long long warp_base = (q0 + (tid & ~31)) << 2;             // first anchor of this warp's group 0
         for (int r = lane; r < total; r += 32) {
             const long long i = warp_base + queue[r];
             const int m = __ldg(matches + i);                            // L1 hit
@@ -477,8 +489,8 @@ int ssdk_head_loss_core(ssdk_ctx* ctx, const HeadGeom& G, const float* reg_targe
     long long grid_flat = (long long)ctx->num_sms * per_sm;
     if (grid_flat > chunks) grid_flat = chunks;
     if (grid_flat < 1) grid_flat = 1;
-    long long grid_rows = (NA + 4 * ROWS_THREADS - 1) / (4 * ROWS_THREADS);
-    if (grid_rows > (long long)ctx->num_sms * 4) grid_rows = (long long)ctx->num_sms * 4;
+    long long grid_rows = (NA + 4 * ROWS_THREADS * ROWS_G - 1) / (4 * ROWS_THREADS * ROWS_G);
+    if (grid_rows > (long long)ctx->num_sms * 8) grid_rows = (long long)ctx->num_sms * 8;
 
     const size_t ws_bytes = 16 + (size_t)ctx->num_sms * 8 * 4 * sizeof(double);
     if (ctx->ws_head.cap < ws_bytes) {
