@@ -12,9 +12,6 @@
 #include "common.cuh"
 
 #define MATCH_THREADS 256
-#ifndef SKIP_HOPELESS
-#define SKIP_HOPELESS 1
-#endif
 #define GT_CHUNK 512
 
 // matches value from the thresholds: training_target_creation.py:92-100
@@ -77,7 +74,6 @@ __global__ void __launch_bounds__(MATCH_THREADS) match_kernel(
 
     const int b = blockIdx.y;
     const int lane = threadIdx.x & 31;
-    const float neg_margin = neg_thr * 0.99999618530273437500f;          // neg_thr * (1 - 2^-18)
     const int N = num_boxes ? min(max(num_boxes[b], 0), Gmax) : Gmax;
     const float4* gtb = gt_boxes + (size_t)b * Gmax;
     const int nchunks = (A + MATCH_THREADS - 1) / MATCH_THREADS;
@@ -148,20 +144,9 @@ __global__ void __launch_bounds__(MATCH_THREADS) match_kernel(
                     const float4 gb = s_box[t];
                     // iou(groundtruth_boxes, anchors): box_utils.py:14-27.  inter == 0 -> 0 / (union + eps) == 0 exactly.
                     const float inter = box_intersection(gb, anc);
-                    const float area_g = s_area[t];
-                    // The exact value only matters if it can reach the negatives threshold (per-anchor outcome, :92-100) or
-                    // the GT's best IoU so far (per-GT argmax, :112).  IoU <= inter / max(area): a pair with
-                    // inter < min(neg_thr, best_t) * max(area) * (1 - 2^-18) is strictly below both (the margin covers the
-                    // roundings of union, + eps and the division) and is treated as IoU 0, which changes neither result.
-                    bool need = valid && inter > 0.0f;
-                    if (SKIP_HOPELESS && need) {
-                        const float best_t = gt_best ? __uint_as_float((unsigned)(s_best[t] >> 32)) : 1.0f;
-                        need = !(inter < fminf(neg_margin, best_t * 0.99999618530273437500f) * fmaxf(area_a, area_g));
-                    }
-                    if (SKIP_HOPELESS && !__any_sync(0xffffffffu, need)) continue;
                     float v = 0.0f;
-                    if (need) {
-                        const float uni = f_sub(f_add(area_g, area_a), inter);
+                    if (valid && inter > 0.0f) {
+                        const float uni = f_sub(f_add(s_area[t], area_a), inter);
                         v = fminf(fmaxf(f_div(inter, f_add(uni, SSDK_EPS)), 0.0f), 1.0f);
                     }
                     if (v > best_v) { best_v = v; best_g = g0 + t; }           // :90-91 (first max over GT)
