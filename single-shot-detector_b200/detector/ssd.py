@@ -403,17 +403,41 @@ class SSD:
         self._call_bw = (call, up)
         return {'class_predictions': g_logits, 'encoded_boxes': g_codes}
 
-    def loss_with_gradients(self, groundtruth, params, upstream=None, fused=True):
+    @staticmethod
+    def assign_targets(anchors, groundtruth, positives_threshold=None, negatives_threshold=None):
+        """Target assignment of a batch (ssd.py:84 / :165-199) WITHOUT the head outputs: it needs only the anchors and the
+        ground truth, so a training loop can issue it on a side stream while the network's forward pass is still running and
+        take it off the critical path.  Returns {'reg_targets' [B,A,4], 'cls_targets' [B,A], 'matches' [B,A], 'count'
+        (float64 [1]: matched anchors of this shard)} for `loss_with_gradients(..., targets=...)`."""
+        from . import ssd as this_module
+        pos = this_module.POSITIVES_THRESHOLD if positives_threshold is None else positives_threshold
+        neg = this_module.NEGATIVES_THRESHOLD if negatives_threshold is None else negatives_threshold
+        call = Call()
+        a = call.tensor(anchors, torch.float32, (-1, 4))
+        A = a.shape[0]
+        gt = call.tensor(groundtruth['boxes'], torch.float32)
+        B, G = gt.shape[0], gt.shape[1]
+        labels = call.tensor(groundtruth['labels'], torch.int32, (B, G))
+        num = call.tensor(groundtruth['num_boxes'], torch.int32, (B,))
+        reg, cls_t, matches = call.empty([B, A, 4], torch.float32), call.empty([B, A], torch.int32), call.empty([B, A], torch.int32)
+        count = call.empty([1], torch.float64)
+        _lib.check(_lib.load().ssdk_training_targets_count(call.ctx(), ptr(a), A, ptr(gt), ptr(labels), ptr(num), B, G, float(pos),
+                                                           float(neg), ptr(reg), ptr(cls_t), ptr(matches), ptr(count)))
+        return {'reg_targets': reg, 'cls_targets': cls_t, 'matches': matches, 'count': count}
+
+    def loss_with_gradients(self, groundtruth, params, upstream=None, fused=True, targets=None):
         """One training step of the hot path without autograd: (losses, gradients).
         fused=True (default): targets -> matched count (all-reduced when `process_group` is set) -> ONE pass over the
         logits that produces the loss sums and both gradients (ssdk_ssd_loss_forward_backward) -> sums all-reduced for the
-        reported losses.  fused=False: forward pass, then loss_backward (two reads of the logits)."""
+        reported losses.  fused=False: forward pass, then loss_backward (two reads of the logits).
+        targets: the dict returned by `SSD.assign_targets` (computed earlier, e.g. during the network's forward pass); the
+        step then consists of the streaming pass alone.  `groundtruth` is not read in that case."""
         if not fused:
             losses = self._loss_forward(groundtruth, params, keep_targets=True)
             return losses, self.loss_backward(upstream)
         head = self._head()
         if head is not None:
-            return self._loss_with_gradients_head(head, groundtruth, params, upstream)
+            return self._loss_with_gradients_head(head, groundtruth, params, upstream, targets)
         from . import ssd as this_module
         lib = _lib.load()
         call = Call()
@@ -421,20 +445,26 @@ class SSD:
         B, A, C = logits.shape
         codes = call.tensor(self.raw_predictions['encoded_boxes'], torch.float32, (B, A, 4))
         anchors = call.tensor(self.anchors, torch.float32, (A, 4))
-        gt = call.tensor(groundtruth['boxes'], torch.float32)
-        G = gt.shape[1]
-        labels = call.tensor(groundtruth['labels'], torch.int32, (B, G))
-        num = call.tensor(groundtruth['num_boxes'], torch.int32, (B,))
-        reg, cls_t, matches = call.empty([B, A, 4], torch.float32), call.empty([B, A], torch.int32), call.empty([B, A], torch.int32)
-        count, sums, out = call.empty([1], torch.float64), call.empty([3], torch.float64), call.empty([2], torch.float32)
+        sums, out = call.empty([3], torch.float64), call.empty([2], torch.float32)
         g_logits, g_codes = call.empty([B, A, C], torch.float32), call.empty([B, A, 4], torch.float32)
         up = None
         if upstream is not None:
             up = _upstream_tensor(call, upstream, logits.device)
         ctx = call.ctx()
-        _lib.check(lib.ssdk_training_targets_count(ctx, ptr(anchors), A, ptr(gt), ptr(labels), ptr(num), B, G,
-                                                   float(this_module.POSITIVES_THRESHOLD), float(this_module.NEGATIVES_THRESHOLD),
-                                                   ptr(reg), ptr(cls_t), ptr(matches), ptr(count)))    # ssd.py:84 and :121-122
+        if targets is not None:
+            reg, cls_t, matches = self._given_targets(call, targets, B, A)
+            count = call.empty([1], torch.float64)
+            count.copy_(targets['count'].reshape(1))                 # the all-reduce below works on a private copy
+        else:
+            gt = call.tensor(groundtruth['boxes'], torch.float32)
+            G = gt.shape[1]
+            labels = call.tensor(groundtruth['labels'], torch.int32, (B, G))
+            num = call.tensor(groundtruth['num_boxes'], torch.int32, (B,))
+            reg, cls_t, matches = call.empty([B, A, 4], torch.float32), call.empty([B, A], torch.int32), call.empty([B, A], torch.int32)
+            count = call.empty([1], torch.float64)
+            _lib.check(lib.ssdk_training_targets_count(ctx, ptr(anchors), A, ptr(gt), ptr(labels), ptr(num), B, G,
+                                                       float(this_module.POSITIVES_THRESHOLD), float(this_module.NEGATIVES_THRESHOLD),
+                                                       ptr(reg), ptr(cls_t), ptr(matches), ptr(count)))    # ssd.py:84 and :121-122
         self._reduce_count(ctx, count)
         _lib.check(lib.ssdk_ssd_loss_forward_backward(ctx, ptr(logits), ptr(codes), ptr(reg), ptr(cls_t), ptr(matches), B, A, C,
                                                       float(params['gamma']), float(params['alpha']), ptr(count), ptr(up),
@@ -447,14 +477,25 @@ class SSD:
         return ({'localization_loss': out[0], 'classification_loss': out[1]},
                 {'class_predictions': g_logits, 'encoded_boxes': g_codes})
 
-    def _loss_with_gradients_head(self, head, groundtruth, params, upstream):
+    @staticmethod
+    def _given_targets(call, targets, B, A):
+        reg = call.tensor(targets['reg_targets'], torch.float32, (B, A, 4))
+        cls_t = call.tensor(targets['cls_targets'], torch.int32, (B, A))
+        matches = call.tensor(targets['matches'], torch.int32, (B, A))
+        return reg, cls_t, matches
+
+    def _loss_with_gradients_head(self, head, groundtruth, params, upstream, targets=None):
         """Fused training step on the per-level tower outputs: targets -> count (all-reduced) -> ONE pass over every level's
         logits that yields the loss sums and the gradients in the head's own layout (ssdk_head_ssd_loss_forward_backward)."""
         lib = _lib.load()
         call = Call(head.device)
         B, A, C = head.batch_size, head.num_anchors, head.num_classes
         count, sums, out = call.empty([1], torch.float64), call.empty([3], torch.float64), call.empty([2], torch.float32)
-        reg, cls_t, matches = self._targets_into(call, groundtruth, B, A, count=count)             # ssd.py:84 and :121-122
+        if targets is not None:
+            reg, cls_t, matches = self._given_targets(call, targets, B, A)
+            count.copy_(targets['count'].reshape(1))
+        else:
+            reg, cls_t, matches = self._targets_into(call, groundtruth, B, A, count=count)         # ssd.py:84 and :121-122
         g_cls, g_box, gd = self._head_grads(call, head)
         up = None
         if upstream is not None:

@@ -163,3 +163,31 @@ def test_fused_forward_backward_equals_two_pass(pkg, syn):
         torch.testing.assert_close(g1['class_predictions'], g2['class_predictions'], rtol=1e-6, atol=1e-30)
         for k in ('localization_loss', 'classification_loss'):
             assert abs(l1[k].item() - l2[k].item()) <= RTOL * abs(l2[k].item()), (k, l1[k].item(), l2[k].item())
+
+
+def test_precomputed_targets_step_equals_the_full_step(pkg, syn):
+    """SSD.assign_targets (anchors + ground truth only, e.g. issued on a side stream during the network's forward pass) followed by
+    loss_with_gradients(targets=...) == the step that assigns targets itself, for both layouts."""
+    from oracle import box_predictor as obp
+    H, W, C, B, G = 256, 320, 9, 3, 7
+    anchors, gt, logits, codes, gen = make_case(pkg, syn, H, W, C, B, G, seed=23)
+    dgt = {k: cuda(v) for k, v in gt.items()}
+    params = {'gamma': 2.0, 'alpha': 0.25}
+    ssd = pkg.SSD.from_predictions(H, W, {'encoded_boxes': cuda(codes), 'class_predictions': cuda(logits)}, gen, C)
+    side = torch.cuda.Stream()
+    with torch.cuda.stream(side):
+        targets = pkg.SSD.assign_targets(ssd.anchors, dgt)
+    torch.cuda.current_stream().wait_stream(side)
+    assert float(targets['count']) == float((targets['matches'] >= 0).sum())
+    l0, g0 = ssd.loss_with_gradients(dgt, params, upstream=(0.7, 1.3))
+    l1, g1 = ssd.loss_with_gradients(None, params, upstream=(0.7, 1.3), targets=targets)
+    assert float(l0['localization_loss']) == float(l1['localization_loss']) and float(l0['classification_loss']) == float(l1['classification_loss'])
+    assert torch.equal(g0['class_predictions'], g1['class_predictions']) and torch.equal(g0['encoded_boxes'], g1['encoded_boxes'])
+    shapes = obp.level_shapes(H, W, gen.strides)
+    n = gen.num_anchors_per_location
+    head = pkg.SSD.from_head_outputs(H, W, [cuda(t) for t in obp.split_to_levels(codes, shapes, n)],
+                                     [cuda(t) for t in obp.split_to_levels(logits, shapes, n)], gen, C)
+    h0, hg0 = head.loss_with_gradients(dgt, params)
+    h1, hg1 = head.loss_with_gradients(None, params, targets=targets)
+    assert float(h0['classification_loss']) == float(h1['classification_loss'])
+    assert all(torch.equal(a, b) for a, b in zip(hg0['class_predictions'], hg1['class_predictions']))
