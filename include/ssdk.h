@@ -292,6 +292,28 @@ SSDK_API int ssdk_head_detect(ssdk_ctx* ctx, const ssdk_head* head, const float*
                      double final_score_threshold, float* out_boxes, float* out_scores, int32_t* out_classes,
                      int32_t* out_num, int32_t* out_anchor_idx);
 
+/* ---- ground-truth side of the random-crop augmentation: detector/input_pipeline/random_image_crop.py --- */
+/* The box arithmetic that follows the choice of a crop window (the window itself comes from TensorFlow's
+ * sample_distorted_bounding_box; JPEG decoding and the sampler are input-pipeline work and out of scope).  Boxes are
+ * DEVICE float[.,4], 16-byte aligned; kept indices are ascending (tf.where + tf.gather order); outputs are caller-owned. */
+/* ioa (:190-209): out[i,j] = clip(intersection(boxes1_i, boxes2_j) / (area(boxes2_j) + 1e-8), 0, 1); not symmetric. */
+SSDK_API int ssdk_ioa(ssdk_ctx* ctx, const float* boxes1, int64_t n, const float* boxes2, int64_t m, float* out /*[n,m]*/);
+/* change_coordinate_frame (:162-187): window DEVICE float[4]; out[i] = clip((box - origin) / size, 0, 1). */
+SSDK_API int ssdk_change_coordinate_frame(ssdk_ctx* ctx, const float* boxes, int64_t n, const float* window, float* out);
+/* prune_completely_outside_window (:102-131): out_boxes float[n,4] / out_indices int[n] hold the out_num[0] kept boxes
+ * (not clipped) first, zero / -1 padding after. */
+SSDK_API int ssdk_prune_completely_outside_window(ssdk_ctx* ctx, const float* boxes, int64_t n, const float* window,
+                                         float* out_boxes, int32_t* out_indices, int32_t* out_num);
+/* prune_non_overlapping_boxes (:134-159): keeps boxes1_i with max_j ioa(boxes2_j, boxes1_i) >= min_overlap. */
+SSDK_API int ssdk_prune_non_overlapping_boxes(ssdk_ctx* ctx, const float* boxes1, int64_t n, const float* boxes2, int64_t m,
+                                     double min_overlap, float* out_boxes, int32_t* out_indices, int32_t* out_num);
+/* randomly_crop_image's box part (:86-99) for a batch in the pipeline's padded format: boxes [B,Gmax,4], num_boxes [B]
+ * (NULL = Gmax each), windows [B,4] -> per image: prune outside, prune ioa(window, box) < overlap_thresh, move to the
+ * window's frame; out_boxes [B,Gmax,4] zero padded, out_keep_indices int[B,Gmax] (-1 padded; indexes the image's input
+ * boxes, use it to gather the labels, :36), out_num int[B]. */
+SSDK_API int ssdk_crop_boxes(ssdk_ctx* ctx, const float* boxes, const int32_t* num_boxes, const float* windows, int B, int Gmax,
+                    double overlap_thresh, float* out_boxes, int32_t* out_keep_indices, int32_t* out_num);
+
 /* ---- multi-GPU: the one exchange of the path, over NVLink peer memory ------------------------ */
 /* Images are sharded over the GPUs of one box, one process per GPU; the only coupling is the loss normaliser and the loss
  * sums (detector/ssd.py:121-123,131-133): an all-reduce(sum) of three doubles.  These entry points do it with peer-memory

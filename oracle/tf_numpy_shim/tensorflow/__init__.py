@@ -120,6 +120,7 @@ greater = _binary(np.greater)
 greater_equal = _binary(np.greater_equal)
 less = _binary(np.less)
 equal = _binary(np.equal)
+less_equal = _binary(np.less_equal)
 add = _binary(np.add)
 
 
@@ -244,6 +245,14 @@ def one_hot(indices, depth, dtype=np.float32, axis=-1):
     if axis not in (-1, out.ndim - 1):
         out = np.moveaxis(out, -1, axis)
     return _wrap(out)
+
+
+def logical_not(x):
+    return _wrap(np.logical_not(np.asarray(_arr(x))))
+
+
+def reduce_any(x, axis=None):
+    return _wrap(np.any(np.asarray(_arr(x)), axis=axis))
 
 
 def where(condition, x=None, y=None):

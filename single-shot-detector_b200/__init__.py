@@ -15,6 +15,8 @@ from . import _lib, config, graph, parallel  # noqa: F401
 from .detector import SSD  # noqa: F401
 from .detector.anchor_generator import AnchorGenerator  # noqa: F401
 from .detector.box_predictor import HeadPredictions, reshape_and_concatenate  # noqa: F401
+from .detector.input_pipeline import (change_coordinate_frame, crop_boxes, ioa, prune_completely_outside_window,  # noqa: F401
+                                      prune_non_overlapping_boxes)
 from .detector.losses import focal_loss, localization_loss  # noqa: F401
 from .detector.training_target_creation import (batch_training_targets, create_targets,  # noqa: F401
                                                 get_training_targets, match_boxes)

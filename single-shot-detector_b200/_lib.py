@@ -59,6 +59,11 @@ _SIGNATURES = {
     'ssdk_head_ssd_loss_forward_backward': (c_int, [P, P, P, P, P, c_int, c_i64, c_int, c_double, c_double, P, P, P, P]),
     'ssdk_head_detect': (c_int, [P, P, P, c_int, c_int, c_i64, c_int, c_double, c_double, c_int, P, c_double, P, P, P, P, P]),
     'ssdk_level_summaries': (c_int, [P, P, P, c_int, c_i64, P, c_int, c_double, P, P, P]),
+    'ssdk_ioa': (c_int, [P, P, c_i64, P, c_i64, P]),
+    'ssdk_change_coordinate_frame': (c_int, [P, P, c_i64, P, P]),
+    'ssdk_prune_completely_outside_window': (c_int, [P, P, c_i64, P, P, P, P]),
+    'ssdk_prune_non_overlapping_boxes': (c_int, [P, P, c_i64, P, c_i64, c_double, P, P, P]),
+    'ssdk_crop_boxes': (c_int, [P, P, P, P, c_int, c_int, c_double, P, P, P]),
     'ssdk_comm_local_handle': (c_int, [P, P]),
     'ssdk_comm_connect': (c_int, [P, c_int, c_int, P]),
     'ssdk_comm_world': (c_int, [P]),

@@ -282,7 +282,42 @@ def golden_head():
     save('head', **out)
 
 
+# ---------------------------------------------------------------- random-crop box ops (input_pipeline/random_image_crop.py)
+def golden_crop():
+    import importlib.util
+    # the file is loaded by path: detector/input_pipeline/__init__.py pulls in the tf.data pipeline, which the shim does not cover
+    spec = importlib.util.spec_from_file_location('ref_random_image_crop', '/root/reference/detector/input_pipeline/random_image_crop.py')
+    ric = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ric)
+    rng = np.random.default_rng(31)
+    out = {}
+    for case in range(6):
+        n = [12, 40, 1, 7, 25, 3][case]
+        boxes = syn.make_gt_boxes(rng, n, 480, 640)
+        c = rng.uniform(0.2, 0.8, 2)
+        hw = rng.uniform(0.15, 0.6, 2)
+        window = np.clip(np.array([c[0] - hw[0], c[1] - hw[1], c[0] + hw[0], c[1] + hw[1]]), 0, 1).astype(np.float32)
+        if case == 3:
+            window = np.array([0.0, 0.0, 1.0, 1.0], np.float32)
+        thr = [0.3, 0.3, 0.3, 0.3, 0.6, 0.05][case]
+        pre = 'c%d/' % case
+        out[pre + 'boxes'], out[pre + 'window'], out[pre + 'thr'] = boxes, window, np.float32(thr)
+        b1, i1 = ric.prune_completely_outside_window(T(boxes), T(window))
+        out[pre + 'outside_boxes'], out[pre + 'outside_idx'] = N(b1).reshape(-1, 4), N(i1).reshape(-1)
+        b2, i2 = ric.prune_non_overlapping_boxes(b1, tf.expand_dims(T(window), 0), min_overlap=thr)
+        out[pre + 'overlap_boxes'], out[pre + 'overlap_idx'] = N(b2).reshape(-1, 4), N(i2).reshape(-1)
+        out[pre + 'changed'] = N(ric.change_coordinate_frame(b2, T(window))).reshape(-1, 4)
+        out[pre + 'keep'] = N(tf.gather(i1, i2)).reshape(-1)
+        others = syn.make_gt_boxes(rng, 5, 480, 640)
+        out[pre + 'others'] = others
+        out[pre + 'ioa'] = N(ric.ioa(T(others), T(boxes)))
+        b3, i3 = ric.prune_non_overlapping_boxes(T(boxes), T(others), min_overlap=0.25)
+        out[pre + 'multi_boxes'], out[pre + 'multi_idx'] = N(b3).reshape(-1, 4), N(i3).reshape(-1)
+    save('crop', **out)
+
+
 if __name__ == '__main__':
+    golden_crop()
     golden_head()
     golden_anchors()
     golden_box_utils()

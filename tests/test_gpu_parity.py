@@ -559,3 +559,51 @@ def test_concurrent_subpaths_and_options(pkg, golden):
                 assert torch.equal(p[k], want_p[k]), k
     with pytest.raises(ValueError):
         pkg._lib.set_option(99, 1)
+
+
+# ------------------------------------------------------------------------------------------------ random-crop box ops
+def test_crop_box_ops_golden(pkg, golden):
+    """input_pipeline/random_image_crop.py:86-209 on the GPU vs the reference's own functions (golden fixture): kept index
+    sets bit-exact, boxes bit-exact (only IEEE subtract / divide / clip are involved)."""
+    g = golden('crop')
+    Gmax = 48
+    batch_boxes = np.zeros([6, Gmax, 4], np.float32)
+    num = np.zeros([6], np.int32)
+    windows = np.zeros([6, 4], np.float32)
+    for case in range(6):
+        pre = 'c%d/' % case
+        boxes, window, thr = g[pre + 'boxes'], g[pre + 'window'], float(g[pre + 'thr'])
+        b1, i1 = pkg.prune_completely_outside_window(cuda(boxes), cuda(window))
+        assert np.array_equal(b1.cpu().numpy(), g[pre + 'outside_boxes']) and np.array_equal(i1.cpu().numpy(), g[pre + 'outside_idx'])
+        b2, i2 = pkg.prune_non_overlapping_boxes(b1, cuda(window[None]), thr)
+        assert np.array_equal(b2.cpu().numpy(), g[pre + 'overlap_boxes']) and np.array_equal(i2.cpu().numpy(), g[pre + 'overlap_idx'])
+        assert np.array_equal(pkg.change_coordinate_frame(b2, cuda(window)).cpu().numpy(), g[pre + 'changed'])
+        assert np.array_equal(pkg.ioa(cuda(g[pre + 'others']), cuda(boxes)).cpu().numpy(), g[pre + 'ioa'])
+        b3, i3 = pkg.prune_non_overlapping_boxes(cuda(boxes), cuda(g[pre + 'others']), 0.25)
+        assert np.array_equal(b3.cpu().numpy(), g[pre + 'multi_boxes']) and np.array_equal(i3.cpu().numpy(), g[pre + 'multi_idx'])
+        # NumPy in -> NumPy out, as everywhere in the mirror
+        b4, i4 = pkg.prune_completely_outside_window(boxes, window)
+        assert isinstance(b4, np.ndarray) and np.array_equal(i4, g[pre + 'outside_idx'])
+        if thr == 0.3:
+            batch_boxes[case, :boxes.shape[0]] = boxes
+            num[case] = boxes.shape[0]
+            windows[case] = window
+    ob, oi, on = pkg.crop_boxes(cuda(batch_boxes), cuda(num), cuda(windows), overlap_thresh=0.3)
+    ob, oi, on = ob.cpu().numpy(), oi.cpu().numpy(), on.cpu().numpy()
+    for case in range(6):
+        pre = 'c%d/' % case
+        if float(g[pre + 'thr']) != 0.3:
+            assert on[case] == 0 and (oi[case] == -1).all() and (ob[case] == 0).all()       # empty image slots
+            continue
+        k = len(g[pre + 'keep'])
+        assert on[case] == k and np.array_equal(oi[case, :k], g[pre + 'keep']) and (oi[case, k:] == -1).all()
+        assert np.array_equal(ob[case, :k], g[pre + 'changed']) and (ob[case, k:] == 0).all()
+    # more boxes than one pass of the CTA (ordered compaction across passes)
+    rng = np.random.default_rng(3)
+    many = np.concatenate([load_pkg('synthetic').make_gt_boxes(rng, 700, 480, 640)])
+    from oracle import random_image_crop as oric
+    w = np.array([0.25, 0.2, 0.8, 0.9], np.float32)
+    want_b, want_i = oric.crop_boxes(many, w, 0.3)
+    ob, oi, on = pkg.crop_boxes(cuda(many[None]), None, cuda(w[None]), 0.3)
+    k = int(on[0])
+    assert k == len(want_i) and np.array_equal(oi[0, :k].cpu().numpy(), want_i) and np.array_equal(ob[0, :k].cpu().numpy(), want_b)

@@ -124,6 +124,10 @@ REFERENCE_SURFACE = {
     'batch_multiclass_non_max_suppression': (['encoded_boxes', 'anchors', 'scores', 'score_threshold', 'iou_threshold',
                                               'max_boxes_per_class'], {}),
     'reshape_and_concatenate': (['encoded_boxes', 'class_predictions', 'num_classes', 'num_anchors_per_location'], {}),
+    'ioa': (['boxes1', 'boxes2'], {}),
+    'prune_completely_outside_window': (['boxes', 'window'], {}),
+    'prune_non_overlapping_boxes': (['boxes1', 'boxes2', 'min_overlap'], {}),
+    'change_coordinate_frame': (['boxes', 'window'], {}),
 }
 
 

@@ -269,3 +269,23 @@ def test_summary_oracle_known_answers():
     m = np.array([[0, -1, 3, -2, -1, 2], [-1, -1, -1, 1, -2, -1]], np.int32)
     per, lvl, total = obp.matches_summaries(m, [4, 2])
     assert per.tolist() == [[2.0, 1.0], [1.0, 0.0]] and lvl.tolist() == [1.5, 0.5] and float(total) == 2.0
+
+
+# ---------------------------------------------------------------- random-crop box ops (input_pipeline/random_image_crop.py)
+def test_crop_box_ops_match_the_reference(golden):
+    from oracle import random_image_crop as oric
+    g = golden('crop')
+    for case in range(6):
+        pre = 'c%d/' % case
+        boxes, window, thr = g[pre + 'boxes'], g[pre + 'window'], float(g[pre + 'thr'])
+        b1, i1 = oric.prune_completely_outside_window(boxes, window)
+        assert np.array_equal(b1, g[pre + 'outside_boxes']) and np.array_equal(i1, g[pre + 'outside_idx'])
+        b2, i2 = oric.prune_non_overlapping_boxes(b1, window[None], thr)
+        assert np.array_equal(b2, g[pre + 'overlap_boxes']) and np.array_equal(i2, g[pre + 'overlap_idx'])
+        assert np.array_equal(oric.change_coordinate_frame(b2, window), g[pre + 'changed'])
+        cb, keep = oric.crop_boxes(boxes, window, thr)
+        assert np.array_equal(cb, g[pre + 'changed']) and np.array_equal(keep, g[pre + 'keep'])
+        assert np.array_equal(oric.ioa(g[pre + 'others'], boxes), g[pre + 'ioa'])
+        b3, i3 = oric.prune_non_overlapping_boxes(boxes, g[pre + 'others'], 0.25)
+        assert np.array_equal(b3, g[pre + 'multi_boxes']) and np.array_equal(i3, g[pre + 'multi_idx'])
+    assert sum(len(g['c%d/keep' % c]) for c in range(6)) > 10 and len(g['c3/keep']) == 7      # full-image window keeps everything
