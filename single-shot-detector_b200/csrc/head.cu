@@ -21,10 +21,8 @@
 // Also here: ssdk_head_concat (reshape_and_concatenate itself, as a tiled transpose) for callers that want the
 // reference's tensors, and as the un-fused baseline in bench.py.
 #include <stdlib.h>
-#include <string.h>
 
 #include "focal_math.cuh"
-#include "matcher.cuh"
 
 // plain stores: st.global.cs (evict-first) was measured and changes nothing (0.2751 vs 0.2725 ms for the fused step)
 #define HEAD_STORE(p, v) (*(p) = (v))
@@ -53,22 +51,13 @@ struct FlatChunk {
     int lvl;
 };
 
-// WITH_MATCH (forward only): the work list also holds the target assignment of the batch, one 256-anchor chunk of one image
-// per item, interleaved evenly with the streaming chunks.  The flat pass needs no targets, so the ALU-bound matching of some
-// CTAs runs under the HBM-bound streaming of the others on the same SM -- one persistent kernel instead of two kernels that
-// fight for the register file.
-template <int GAMMA_MODE, bool WITH_GRAD, bool WITH_MATCH>
-__global__ void __launch_bounds__(FLAT_THREADS, 4) head_flat_kernel(const FlatSegs S, float gamma, float alpha,
+template <int GAMMA_MODE, bool WITH_GRAD>
+__global__ void __launch_bounds__(FLAT_THREADS) head_flat_kernel(const FlatSegs S, float gamma, float alpha,
                                                                   const double* __restrict__ norm_count,
                                                                   const float* __restrict__ upstream,
-                                                                  double* __restrict__ partials /*[grid]*/, const MatchJob J) {
-    extern __shared__ __align__(16) unsigned char s_match[];             // WITH_MATCH: GT staging of match_chunk
+                                                                  double* __restrict__ partials /*[grid]*/) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const long long flat_total = S.chunk0[S.nseg];
-    const long long n_match = WITH_MATCH ? J.nchunks : 0;
-    const long long total = flat_total + n_match;
-    // position p of the interleaved list -> number of matching items before it (they are spread evenly)
-    auto match_before = [&](long long p) { return WITH_MATCH ? (p * n_match) / total : 0ll; };
+    const long long total = S.chunk0[S.nseg];
     const float4 ninf4 = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
     float k_neg = 0.0f;
     if (WITH_GRAD) {
@@ -79,10 +68,7 @@ __global__ void __launch_bounds__(FLAT_THREADS, 4) head_flat_kernel(const FlatSe
     double acc = 0.0;
 
     int cursor = 0;                                                       // level of the most recently loaded chunk
-    auto load = [&](FlatChunk& ck, long long p) {
-        const long long mb = match_before(p);
-        if (WITH_MATCH && match_before(p + 1) > mb) { ck.lvl = -1; return; }    // a matching item: nothing to prefetch
-        const long long g = p - mb;
+    auto load = [&](FlatChunk& ck, long long g) {
         while (g >= S.chunk0[cursor + 1]) ++cursor;
         ck.lvl = cursor;
         ck.i4 = (g - S.chunk0[cursor]) * FLAT_CHUNK4 + tid;
@@ -95,15 +81,7 @@ __global__ void __launch_bounds__(FLAT_THREADS, 4) head_flat_kernel(const FlatSe
             ck.v[u] = (i < n4) ? ld_stream_f4(src4 + i) : ninf4;
         }
     };
-    auto compute = [&](FlatChunk& ck, long long p) {
-        if (WITH_MATCH && ck.lvl < 0) {
-            float4* s_box = (float4*)s_match;
-            float* s_area = (float*)(s_box + GT_CHUNK);
-            unsigned long long* s_best = (unsigned long long*)(s_area + GT_CHUNK);
-            match_chunk(J, match_before(p), s_box, s_area, s_best, (int*)(s_best + GT_CHUNK));
-            return;
-        }
-        const long long g = p - match_before(p);
+    auto compute = [&](FlatChunk& ck, long long g) {
         float s;
         if (WITH_GRAD && ck.lvl >= S.n) {
             // box gradients: zero everywhere, head_rows_kernel then scatters the matched anchors' values
@@ -458,8 +436,7 @@ int ssdk_head_geom(const ssdk_head* head, int B, int64_t A, int C, bool need_cls
 // phases: 1 = the flat pass (needs no targets), 2 = the matched / ignored anchors + final reduction, 3 = both
 int ssdk_head_loss_core(ssdk_ctx* ctx, const HeadGeom& G, const float* reg_targets, const int32_t* cls_targets,
                         const int32_t* matches, int B, int64_t A, int C, double gamma, double alpha, const double* num_matches,
-                        const float* upstream, double* out_sums, const ssdk_head_grads* grads, bool with_grad, int phases,
-                        const MatchJob* job /*= nullptr: phase 1 also runs this target assignment (forward only)*/) {
+                        const float* upstream, double* out_sums, const ssdk_head_grads* grads, bool with_grad, int phases) {
     const long long NA = (long long)B * A;
     if (NA == 0) {
         if (out_sums) SSDK_CHECK_CUDA(cudaMemsetAsync(out_sums, 0, 3 * sizeof(double), ctx->stream));
@@ -496,27 +473,21 @@ int ssdk_head_loss_core(ssdk_ctx* ctx, const HeadGeom& G, const float* reg_targe
     for (int sg = S.nseg; sg <= 2 * SSDK_MAX_LEVELS; ++sg) S.chunk0[sg] = chunks;
 
     // persistent-style grid: exactly the number of co-resident CTAs (a larger grid would add a partial second wave)
-    const bool with_match = job != nullptr && !with_grad && (phases & 1);
-    const size_t match_smem = with_match ? (size_t)GT_CHUNK * (sizeof(float4) + sizeof(float) + sizeof(unsigned long long)) + 16 : 0;
-    static int occ_cache[6] = {0, 0, 0, 0, 0, 0};
-    const int variant = with_match ? (gamma == 2.0 ? 4 : 5) : (gamma == 2.0 ? 0 : 2) + (with_grad ? 1 : 0);
+    static int occ_cache[4] = {0, 0, 0, 0};
+    const int variant = (gamma == 2.0 ? 0 : 2) + (with_grad ? 1 : 0);
     if (occ_cache[variant] == 0) {
-        const void* fn = variant == 0 ? (const void*)head_flat_kernel<0, false, false> : variant == 1 ? (const void*)head_flat_kernel<0, true, false>
-                       : variant == 2 ? (const void*)head_flat_kernel<1, false, false> : variant == 3 ? (const void*)head_flat_kernel<1, true, false>
-                       : variant == 4 ? (const void*)head_flat_kernel<0, false, true> : (const void*)head_flat_kernel<1, false, true>;
+        const void* fn = variant == 0 ? (const void*)head_flat_kernel<0, false> : variant == 1 ? (const void*)head_flat_kernel<0, true>
+                       : variant == 2 ? (const void*)head_flat_kernel<1, false> : (const void*)head_flat_kernel<1, true>;
         int occ = 0;
-        SSDK_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, FLAT_THREADS, match_smem));
+        SSDK_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, FLAT_THREADS, 0));
         occ_cache[variant] = occ > 0 ? occ : 1;
     }
-    MatchJob J;
-    memset(&J, 0, sizeof(J));
-    if (with_match) J = *job;
     int per_sm = occ_cache[variant];
     if (const char* e = getenv("SSDK_HEAD_CTAS")) per_sm = atoi(e);             // tuning knob (CTAs per SM)
     if (per_sm < 1) per_sm = 1;
     if (per_sm > 8) per_sm = 8;
     long long grid_flat = (long long)ctx->num_sms * per_sm;
-    if (grid_flat > chunks + J.nchunks) grid_flat = chunks + J.nchunks;
+    if (grid_flat > chunks) grid_flat = chunks;
     if (grid_flat < 1) grid_flat = 1;
     long long grid_rows = (NA + 4 * ROWS_THREADS * ROWS_G - 1) / (4 * ROWS_THREADS * ROWS_G);
     if (grid_rows > (long long)ctx->num_sms * 8) grid_rows = (long long)ctx->num_sms * 8;
@@ -534,14 +505,10 @@ int ssdk_head_loss_core(ssdk_ctx* ctx, const HeadGeom& G, const float* reg_targe
     const bool g2 = (gamma == 2.0);
 #define SSDK_LAUNCH_HEAD(GM, WG)                                                                                              \
     do {                                                                                                                      \
-        if ((phases & 1) && with_match)                                                                                       \
+        if (phases & 1)                                                                                                       \
             SSDK_KERNEL(ctx, SSDK_K_HEAD_FLAT,                                                                                \
-                        head_flat_kernel<GM, false, true><<<(int)grid_flat, FLAT_THREADS, match_smem, ctx->stream>>>(        \
-                            S, gf, af, num_matches, upstream, flat_partials, J));                                             \
-        else if (phases & 1)                                                                                                  \
-            SSDK_KERNEL(ctx, SSDK_K_HEAD_FLAT,                                                                                \
-                        head_flat_kernel<GM, WG, false><<<(int)grid_flat, FLAT_THREADS, 0, ctx->stream>>>(S, gf, af, num_matches, \
-                                                                                                         upstream, flat_partials, J)); \
+                        head_flat_kernel<GM, WG><<<(int)grid_flat, FLAT_THREADS, 0, ctx->stream>>>(S, gf, af, num_matches,    \
+                                                                                                  upstream, flat_partials)); \
         if (phases & 2)                                                                                                       \
             SSDK_KERNEL(ctx, SSDK_K_HEAD_ROWS,                                                                                \
                         head_rows_kernel<GM, WG><<<(int)grid_rows, ROWS_THREADS, 0, ctx->stream>>>(                           \
@@ -563,7 +530,7 @@ static int head_loss_impl(ssdk_ctx* ctx, const ssdk_head* head, const float* reg
     HeadGeom G;
     SSDK_TRY(ssdk_head_geom(head, B, A, C, true, true, &G));
     return ssdk_head_loss_core(ctx, G, reg_targets, cls_targets, matches, B, A, C, gamma, alpha, num_matches, upstream, out_sums,
-                               grads, with_grad, 3, nullptr);
+                               grads, with_grad, 3);
 }
 
 // HeadGeom of the anchor-major tensors [B,A,C] / [B,A,4]: one channels_last "level" with one anchor per location
@@ -600,29 +567,7 @@ int ssdk_targets_and_loss_overlapped(ssdk_ctx* ctx, const HeadGeom& G, const flo
         SSDK_TRY(ssdk_match_impl(ctx, anchors, A, gt_boxes, gt_labels, num_boxes, B, Gmax, pos_thr, neg_thr, 1, out_reg, out_cls,
                                  out_matches));
         return ssdk_head_loss_core(ctx, G, out_reg, out_cls, out_matches, B, A, C, gamma, alpha, nullptr, nullptr, out_sums, nullptr,
-                                   false, 3, nullptr);
-    }
-    if (Gmax > 0 && Gmax <= GT_CHUNK && A < (1ll << 31) && !(getenv("SSDK_FUSED_MATCH") && getenv("SSDK_FUSED_MATCH")[0] == '0')) {
-        // one persistent kernel: the matching chunks are interleaved with the streaming chunks of the flat pass
-        SSDK_REQUIRE(anchors && gt_boxes && gt_labels, SSDK_ERR_ARG, "targets_and_loss: null pointer");
-        SSDK_REQUIRE(aligned16(anchors) && aligned16(gt_boxes) && aligned16(out_reg), SSDK_ERR_SHAPE,
-                     "targets_and_loss: box arrays must be 16-byte aligned");
-        SSDK_REQUIRE(pos_thr >= neg_thr, SSDK_ERR_ARG, "positives_threshold (%g) must be >= negatives_threshold (%g)", pos_thr, neg_thr);
-        const size_t bytes = (size_t)B * Gmax * sizeof(unsigned long long) + 2 * (size_t)B * sizeof(int);
-        SSDK_TRY(ssdk_ensure(ctx, &ctx->ws_gtbest, bytes));
-        SSDK_CHECK_CUDA(cudaMemsetAsync(ctx->ws_gtbest.p, 0, bytes, ctx->stream));
-        MatchJob J;
-        J.anchors = (const float4*)anchors; J.gt_boxes = (const float4*)gt_boxes; J.gt_labels = gt_labels; J.num_boxes = num_boxes;
-        J.gt_best = (unsigned long long*)ctx->ws_gtbest.p;
-        J.tickets = (int*)(J.gt_best + (size_t)B * Gmax);
-        J.matches = out_matches; J.reg = (float4*)out_reg; J.cls = out_cls;
-        J.A = (int)A; J.Gmax = Gmax; J.chunks_per_image = ceil_div_i(A, MATCH_THREADS);
-        J.pos_thr = (float)pos_thr; J.neg_thr = (float)neg_thr; J.same_thr = (pos_thr == neg_thr) ? 1 : 0;
-        J.nchunks = (long long)B * J.chunks_per_image;
-        SSDK_TRY(ssdk_head_loss_core(ctx, G, out_reg, out_cls, out_matches, B, A, C, gamma, alpha, nullptr, nullptr, out_sums, nullptr,
-                                     false, 1, &J));
-        return ssdk_head_loss_core(ctx, G, out_reg, out_cls, out_matches, B, A, C, gamma, alpha, nullptr, nullptr, out_sums, nullptr,
-                                   false, 2, nullptr);
+                                   false, 3);
     }
     cudaStream_t main_stream = ctx->stream, side = ctx->copy_stream;
     // fork: everything already queued on the main stream (e.g. the producer of the logits / ground truth) precedes the matcher
@@ -638,12 +583,12 @@ int ssdk_targets_and_loss_overlapped(ssdk_ctx* ctx, const HeadGeom& G, const flo
     }
     if (st == SSDK_OK)
         st = ssdk_head_loss_core(ctx, G, out_reg, out_cls, out_matches, B, A, C, gamma, alpha, nullptr, nullptr, out_sums, nullptr,
-                                 false, 1, nullptr);                                          // flat pass, concurrently
+                                 false, 1);                                                   // flat pass, concurrently
     // join (also on the error paths, so that a stream capture in progress is never left forked)
     cudaStreamWaitEvent(main_stream, ctx->ev[1], 0);
     SSDK_TRY(st);
     return ssdk_head_loss_core(ctx, G, out_reg, out_cls, out_matches, B, A, C, gamma, alpha, nullptr, nullptr, out_sums, nullptr,
-                               false, 2, nullptr);                                            // ssd.py:89-133
+                               false, 2);                                                     // ssd.py:89-133
 }
 
 extern "C" {

@@ -9,7 +9,55 @@
 // order is the float order) -> shared-memory atomicMax -> one global atomicMax per (CTA, GT) on the packed key
 //     key = iou_bits << 32 | (0xFFFFFFFF - anchor_index)      (ties -> LOWEST anchor index, as tf.argmax axis=1).
 // A second, tiny kernel applies the forced matches, including the reference's row-id quirk (:117).
-#include "matcher.cuh"
+#include "common.cuh"
+
+#define MATCH_THREADS 256
+#define GT_CHUNK 512
+
+// matches value from the thresholds: training_target_creation.py:92-100
+__device__ __forceinline__ int threshold_match(int best_g, float best_v, float pos_thr, float neg_thr, bool same_thr) {
+    if (best_v >= pos_thr) return best_g;
+    if (same_thr) return -1;
+    return (neg_thr > best_v) ? -1 : -2;
+}
+
+
+// Forced matches: training_target_creation.py:105-126.  For GT g: fid[g] = first anchor with the row maximum,
+// ok[g] = (row maximum >= 0.1).  Anchor a is overridden iff some ok GT picked it; the value written is the
+// LOWEST GT index among all GTs that picked a, ok or not (argmax over the unmasked one-hot, :117).
+// Runs in one CTA per image: either force_match_kernel or the last match_kernel CTA of the image.
+template <bool WRITE_TARGETS>
+__device__ __forceinline__ void force_match_image(
+    int b, int N, int* s_fid, unsigned char* s_ok, const float4* __restrict__ anchors, int A,
+    const float4* __restrict__ gt_boxes, const int* __restrict__ gt_labels, int Gmax,
+    const unsigned long long* gt_best, int* matches, float4* reg, int* cls, int* s_new_matched = nullptr) {
+    for (int g = threadIdx.x; g < N; g += blockDim.x) {
+        const unsigned long long key = __ldcg(&gt_best[(size_t)b * Gmax + g]);
+        // key == 0: the whole IoU row is 0 -> argmax is anchor 0, value 0
+        s_fid[g] = key ? (int)(0xFFFFFFFFu - (unsigned)(key & 0xFFFFFFFFull)) : 0;
+        s_ok[g] = __uint_as_float((unsigned)(key >> 32)) >= 0.1f;
+    }
+    __syncthreads();
+    for (int g = threadIdx.x; g < N; g += blockDim.x) {
+        const int a = s_fid[g];
+        bool first = true, any_ok = false;
+        for (int h = 0; h < N; ++h) {
+            if (s_fid[h] == a) {
+                if (h < g) first = false;
+                any_ok |= (s_ok[h] != 0);
+            }
+        }
+        if (first && any_ok) {
+            const size_t o = (size_t)b * A + a;
+            if (s_new_matched && __ldcg(&matches[o]) < 0) atomicAdd(s_new_matched, 1);   // a forced match of a so far unmatched anchor
+            matches[o] = g;
+            if (WRITE_TARGETS) {
+                reg[o] = box_encode(gt_boxes[(size_t)b * Gmax + g], anchors[a]);
+                cls[o] = gt_labels[(size_t)b * Gmax + g] + 1;
+            }
+        }
+    }
+}
 
 template <bool WRITE_TARGETS>
 __global__ void __launch_bounds__(MATCH_THREADS) match_kernel(
