@@ -27,7 +27,9 @@
 // plain stores: st.global.cs (evict-first) was measured and changes nothing (0.2751 vs 0.2725 ms for the fused step)
 #define HEAD_STORE(p, v) (*(p) = (v))
 #define FLAT_THREADS 256
-#define FLAT_U 4                                        // float4 per thread and chunk
+#ifndef FLAT_U
+#define FLAT_U 4                                        // float4 per thread and chunk (2: 0.166 ms, 8: 0.160 ms, 4: 0.148 ms forward)
+#endif
 #define FLAT_CHUNK4 (FLAT_THREADS * FLAT_U)             // float4 per chunk (16 KB)
 
 struct FlatSegs {
