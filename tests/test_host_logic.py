@@ -204,6 +204,7 @@ from oracle import ssd as ossd                                  # the checker st
 from oracle.anchor_generator import AnchorGenerator as OracleGen
 rank, world = int(os.environ['RANK']), int(os.environ['WORLD_SIZE'])
 dist.init_process_group('gloo', rank=rank, world_size=world)
+assert par.connect_peers() is False                # no GPUs here: the NVLink peer exchange is unavailable, NCCL/gloo stays in use
 H, W, C, B, G = 128, 160, 5, 5, 4
 anchors = OracleGen()(H, W); A = anchors.shape[0]
 gt = syn.make_groundtruth(77, B, G, H, W, C, vary_count=True)
