@@ -45,7 +45,6 @@ struct ssdk_ctx {
     int prof_id[SSDK_PROFILE_EVENTS];
     double prof_ms[SSDK_K_COUNT] = {0};
     long long prof_calls[SSDK_K_COUNT] = {0};
-    int sort_occupancy = 0;
     cudaStream_t copy_stream = nullptr;
     int overlap_matcher = 1; // SSDK_OPT_OVERLAP_MATCHER
     int* hint_host = nullptr; // mapped pinned int[2]: [0] = large segments met by the last post-processing call (density hint)
