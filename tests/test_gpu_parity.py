@@ -436,7 +436,6 @@ def test_detect_box_scaler_and_final_threshold(pkg, golden):
 def test_matched_count_from_the_matching_kernel(pkg, golden, case, tag):
     """ssdk_training_targets_count: the count produced inside the matching kernel (incl. forced matches that turn a
     background / ignored anchor into a match, and the quirk case) == (matches >= 0).sum() of the reference's matches."""
-    import ctypes
     g = golden('matching')
     anchors, gt, labels = g['anchors'], g[case + '/gt'], g[case + '/labels']
     pt, nt = THR[tag]
