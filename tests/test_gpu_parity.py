@@ -606,3 +606,15 @@ def test_crop_box_ops_golden(pkg, golden):
     ob, oi, on = pkg.crop_boxes(cuda(many[None]), None, cuda(w[None]), 0.3)
     k = int(on[0])
     assert k == len(want_i) and np.array_equal(oi[0, :k].cpu().numpy(), want_i) and np.array_equal(ob[0, :k].cpu().numpy(), want_b)
+
+
+def test_plain_c_program_end_to_end(pkg, tmp_path):
+    """examples/c_abi_example.c through the C ABI alone: anchors + target assignment + error reporting from plain C."""
+    import subprocess
+    from test_host_logic import build_c_example
+    r = subprocess.run([build_c_example(tmp_path)], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert r.stdout.strip().endswith('ok') and 'matched anchors' in r.stdout and 'expected error' in r.stdout
+    gen = pkg.AnchorGenerator(scale_multipliers=[1.0, 2 ** (1 / 3), 2 ** (2 / 3)])
+    first = gen(640, 896)[0].cpu().numpy()
+    assert ('first anchor [%.6f %.6f %.6f %.6f]' % tuple(first)) in r.stdout

@@ -69,6 +69,27 @@ def test_ctypes_structs_match_the_c_layout(tmp_path):
                    lib_mod.SSDK_MAX_LEVELS]
 
 
+def build_c_example(tmp_path):
+    """examples/c_abi_example.c: a plain-C (gcc -std=c99) user of the library -- no C++, torch or Python on the boundary."""
+    lib_dir = os.path.dirname(load_pkg('_lib').LIB_PATH)
+    exe = str(tmp_path / 'ssdk_example')
+    r = subprocess.run(['gcc', '-std=c99', '-Wall', '-Werror', '-I', os.path.join(ROOT, 'include'), '-I', '/usr/local/cuda/include',
+                        os.path.join(ROOT, 'examples', 'c_abi_example.c'), '-L', lib_dir, '-lssdk', '-L', '/usr/local/cuda/lib64',
+                        '-lcudart', '-lm', '-Wl,-rpath,' + lib_dir, '-o', exe], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    return exe
+
+
+def test_plain_c_program_links_and_runs_the_host_part(tmp_path):
+    import torch
+    exe = build_c_example(tmp_path)
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert 'anchors: 107415 (per level 80640 20160 5040 1260 315)' in r.stdout
+    if not torch.cuda.is_available():
+        assert 'no CPU fallback' in r.stdout                            # refuses, loudly, to compute without a GPU
+
+
 def test_host_only_entry_points_and_error_reporting():
     """ssdk_num_anchors is pure shape arithmetic (anchor_generator.py:59-62) and needs no GPU; a compute entry point
     without a device must fail loudly with a message, never fall back."""
