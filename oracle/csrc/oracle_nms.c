@@ -3,9 +3,10 @@
  * TensorFlow 1.12's NonMaxSuppressionV3 CPU kernel, the one piece of the
  * reference's hot path whose algorithm lives outside /root/reference
  * (called at reference detector/utils/nms.py:33, pinned only by
- * "tensorflow 1.12" in README.md:22).  PARITY UNPINNED: no reference-side
- * golden vector exists for this op; semantics restated from the published
- * kernel (tensorflow/core/kernels/non_max_suppression_op.cc):
+ * "tensorflow 1.12" in README.md:22).  Pinned to TensorFlow's own unit-test
+ * vectors (tests/golden/tf_nms_vectors.py <- non_max_suppression_op_test.cc);
+ * semantics restated from the published kernel
+ * (tensorflow/core/kernels/non_max_suppression_op.cc):
  *   - candidates are the boxes with score > score_threshold (strict);
  *   - they are visited in descending score order (equal scores: lower index
  *     first -- TF 1.12's heap order is unspecified, TF>=2 uses this rule);

@@ -4,7 +4,9 @@ Follows reference detector/utils/nms.py: multiclass_non_max_suppression :6-45,
 batch_multiclass_non_max_suppression :48-102.  tf.image.non_max_suppression
 (TF 1.12 NonMaxSuppressionV3, external C++) is restated in
 non_max_suppression_v3 below and, for speed, in oracle/csrc/oracle_nms.c.
-PARITY UNPINNED for that op."""
+That op is pinned to TensorFlow's own published unit-test vectors
+(tests/golden/tf_nms_vectors.py, restating non_max_suppression_op_test.cc) and cross-checked
+against torchvision.ops.nms on random boxes (tests/test_oracle_golden.py)."""
 import ctypes
 import os
 
@@ -58,6 +60,8 @@ def non_max_suppression_v3(boxes, scores, max_output_size, iou_threshold, score_
     boxes = np.ascontiguousarray(boxes, dtype=np.float32).reshape(-1, 4)
     scores = np.ascontiguousarray(scores, dtype=np.float32)
     n = boxes.shape[0]
+    if not (0.0 <= float(iou_threshold) <= 1.0):        # OP_REQUIRES of the TF kernel
+        raise ValueError('iou_threshold must be in [0, 1]')
     if use_c:
         out = np.zeros([max(int(max_output_size), 1)], dtype=np.int32)
         k = _lib().oracle_nms_v3(

@@ -800,6 +800,9 @@ static int postprocess_impl(ssdk_ctx* ctx, const HeadGeom* head, const float* co
     SSDK_REQUIRE(B >= 0 && A >= 0 && C > 0 && K > 0, SSDK_ERR_ARG, "ssdk_postprocess: bad sizes (B=%d A=%lld C=%d K=%d)", B,
                  (long long)A, C, K);
     SSDK_REQUIRE(B <= 65535, SSDK_ERR_SHAPE, "ssdk_postprocess: batch %d > 65535", B);
+    // OP_REQUIRES of TensorFlow's NonMaxSuppressionV3 kernel (the op behind detector/utils/nms.py:33)
+    SSDK_REQUIRE(iou_threshold >= 0.0 && iou_threshold <= 1.0, SSDK_ERR_ARG, "ssdk_postprocess: iou_threshold must be in [0, 1] (got %g)",
+                 iou_threshold);
     if (B == 0) return SSDK_OK;
     SSDK_REQUIRE(out_boxes && out_scores && out_classes && out_num, SSDK_ERR_ARG, "ssdk_postprocess: null output");
     const bool decoded = (flags & SSDK_BOXES_DECODED) != 0;

@@ -32,16 +32,20 @@ def _postprocess(call, codes, anchors, scores, flags, score_threshold, iou_thres
     return boxes, out_scores, classes, num
 
 
-def multiclass_non_max_suppression(boxes, scores, score_threshold, iou_threshold, max_boxes_per_class):
+def multiclass_non_max_suppression(boxes, scores, score_threshold, iou_threshold, max_boxes_per_class, return_indices=False):
     """reference :6-45.  boxes [N,4] (already decoded), scores [N,C] ->
-    selected_boxes [N',4], selected_scores [N'], selected_classes [N'] (class-major, score-descending)."""
+    selected_boxes [N',4], selected_scores [N'], selected_classes [N'] (class-major, score-descending).
+    return_indices=True appends the selected row indices [N'] (what tf.image.non_max_suppression returns per class, :33)."""
     call = Call()
     s = call.tensor(scores, torch.float32)
     N, C = s.shape
     b = call.tensor(boxes, torch.float32, (1, N, 4))
-    ob, os_, oc, on = _postprocess(call, b, None, s.reshape(1, N, C), _lib.SSDK_INPUT_SCORES | _lib.SSDK_BOXES_DECODED,
-                                   score_threshold, iou_threshold, max_boxes_per_class)
+    out = _postprocess(call, b, None, s.reshape(1, N, C), _lib.SSDK_INPUT_SCORES | _lib.SSDK_BOXES_DECODED,
+                       score_threshold, iou_threshold, max_boxes_per_class, return_anchor_indices=return_indices)
+    ob, os_, oc, on = out[:4]
     n = int(on[0].item())          # N' is data dependent: one host read, as tf.shape() would need
+    if return_indices:
+        return call.result(ob[0, :n], os_[0, :n], oc[0, :n], out[4][0, :n])
     return call.result(ob[0, :n], os_[0, :n], oc[0, :n])
 
 

@@ -319,6 +319,33 @@ def test_multiclass_nms_single_image(pkg, golden):
     assert np.array_equal(sb.cpu().numpy(), ob)
 
 
+def test_nms_v3_tensorflow_published_vectors(pkg):
+    """The CUDA NMS against TensorFlow's own NonMaxSuppressionV3 unit-test vectors (tests/golden/tf_nms_vectors.py), through the
+    reference's call site for that op: multiclass_non_max_suppression with one class (detector/utils/nms.py:31-40)."""
+    import importlib.util, os
+    spec = importlib.util.spec_from_file_location('tf_nms_vectors', os.path.join(os.path.dirname(__file__), 'golden', 'tf_nms_vectors.py'))
+    tfv = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(tfv)
+    seen = 0
+    for name, boxes, scores, k, iou, thr, want in tfv.cases():
+        sb, ss, sc, si = pkg.multiclass_non_max_suppression(cuda(boxes).reshape(-1, 4), cuda(scores).reshape(-1, 1), thr, iou, k,
+                                                            return_indices=True)
+        assert np.array_equal(si.cpu().numpy(), want), (name, si.cpu().numpy(), want)
+        assert np.array_equal(sb.cpu().numpy(), boxes[want]) and np.array_equal(ss.cpu().numpy(), scores[want]), name
+        assert not sc.any()
+        # and with the case embedded as class 1 of 3 (classes 0 and 2 empty), twice in a batch of decoded boxes
+        if len(scores):
+            dense = np.zeros([len(scores), 3], np.float32)
+            dense[:, 1] = scores
+            sb3, ss3, sc3, si3 = pkg.multiclass_non_max_suppression(cuda(boxes), cuda(dense), thr, iou, k, return_indices=True)
+            assert np.array_equal(si3.cpu().numpy(), want) and (sc3.cpu().numpy() == 1).all(), name
+        seen += 1
+    assert seen == 8
+    b, s, k, iou, thr = tfv.INVALID_IOU_THRESHOLD                       # "iou_threshold must be in [0, 1]"
+    with pytest.raises(ValueError):
+        pkg.multiclass_non_max_suppression(cuda(np.asarray(b, np.float32)), cuda(np.asarray(s, np.float32)).reshape(-1, 1), thr, iou, k)
+
+
 @pytest.mark.parametrize('cfg_id,B,kind,K', [(3, 2, 'realistic', 100), (3, 1, 'dense', 100), (5, 1, 'dense', 100),
                                             (1, 1, 'dense', 5)])
 def test_postprocess_full_size(pkg, cfg_id, B, kind, K):

@@ -151,6 +151,34 @@ def test_get_predictions(golden):
     assert np.array_equal(losses.sigmoid(g['logits']), g['scores'])
 
 
+def _tf_vectors():
+    import importlib.util, os
+    spec = importlib.util.spec_from_file_location('tf_nms_vectors', os.path.join(os.path.dirname(__file__), 'golden', 'tf_nms_vectors.py'))
+    m = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(m)
+    return m
+
+
+@pytest.mark.parametrize('use_c', [True, False])
+def test_nms_v3_tensorflow_published_vectors(use_c):
+    """NonMaxSuppressionV3 (called at reference detector/utils/nms.py:33) pinned to TensorFlow's own unit-test vectors
+    (tests/golden/tf_nms_vectors.py restates non_max_suppression_op_test.cc)."""
+    tfv = _tf_vectors()
+    seen = 0
+    for name, boxes, scores, k, iou, thr, want in tfv.cases():
+        got = nms.non_max_suppression_v3(boxes, scores, k, iou, thr, use_c=use_c)
+        assert np.array_equal(got, want), (name, got, want)
+        # the same case through the reference's call site (nms.py:31-44): one class
+        sb, ss, sc, si = nms.multiclass_non_max_suppression(boxes, scores.reshape(-1, 1), thr, iou, k, use_c=use_c,
+                                                            return_indices=True)
+        assert np.array_equal(si, want) and np.array_equal(sb, boxes[want]) and np.array_equal(ss, scores[want]), name
+        seen += 1
+    assert seen == 8
+    b, s, k, iou, thr = tfv.INVALID_IOU_THRESHOLD
+    with pytest.raises(ValueError):
+        nms.non_max_suppression_v3(np.asarray(b, np.float32), np.asarray(s, np.float32), k, iou, thr, use_c=use_c)
+
+
 def test_nms_restatement_vs_torchvision():
     """Independent cross-check of the NonMaxSuppressionV3 restatement (kept sets)."""
     torch = pytest.importorskip('torch')
