@@ -53,11 +53,16 @@ SSDK_API const char* ssdk_last_error(void);
 /* stream: a cudaStream_t (NULL = legacy default stream).  Creates the context on `device`. */
 SSDK_API int ssdk_ctx_create(int device, void* stream, ssdk_ctx** out);
 SSDK_API int ssdk_ctx_set_stream(ssdk_ctx* ctx, void* stream);
-/* Options.  SSDK_OPT_OVERLAP_MATCHER (default 1): ssdk_ssd_targets_and_loss / ssdk_head_ssd_targets_and_loss run the
- * (ALU-bound) matcher on the context's side stream concurrently with the (HBM-bound) flat pass over the logits.  Set it to
- * 0 when the caller already keeps the GPU busy with other work on a second stream (e.g. the inference-side sub-path): the
- * extra contention then costs more than the overlap gains. */
-#define SSDK_OPT_OVERLAP_MATCHER 1
+/* Options of the fused training step (ssdk_ssd_loss_step, ssdk_ssd_targets_and_loss and their ssdk_head_* forms; see
+ * csrc/train_step.cu): one persistent kernel whose CTAs take roles -- `SSDK_OPT_MATCH_CTAS_PER_SM` CTAs per SM (default 2, 1..4)
+ * start with the ALU-bound target assignment while the others stream the logits, and join the streaming afterwards for
+ * `SSDK_OPT_MATCH_FLAT_SHARE_PCT` percent (default 50, 0..100) of a streaming CTA's share of the chunks.
+ * SSDK_OPT_FUSED_TRAIN_STEP = 0 runs the same computation as separate launches (matcher, flat pass, matched-anchor pass,
+ * finalisation) -- for comparison; results agree to rounding of the double sums.  The same knobs are read once at context
+ * creation from SSDK_MATCH_CTAS / SSDK_MATCH_FLAT_SHARE (values are clamped to their valid ranges). */
+#define SSDK_OPT_FUSED_TRAIN_STEP 1
+#define SSDK_OPT_MATCH_CTAS_PER_SM 2
+#define SSDK_OPT_MATCH_FLAT_SHARE_PCT 3
 SSDK_API int ssdk_ctx_set_option(ssdk_ctx* ctx, int option, int value);
 SSDK_API int ssdk_ctx_destroy(ssdk_ctx* ctx);
 /* Bytes of private workspace currently held (grows on demand, never shrinks). */
@@ -70,10 +75,16 @@ SSDK_API int64_t ssdk_ctx_launch_count(const ssdk_ctx* ctx);
  * 2 force_match, 3 ssd_loss, 4 loss_reduce (unused), 5 filter, 6 sort (unused: segments are sorted inside the NMS kernels),
  * 7 nms, 8 pack, 9 other, 10 ssd_loss_backward,
  * 11 head_flat (flat focal pass over the per-level head tensors), 12 head_rows (matched / ignored anchors), 13 head_concat,
- * 14 comm (peer-memory all-reduce). */
-#define SSDK_NUM_KERNEL_IDS 15
+ * 14 comm (peer-memory all-reduce), 15 train_step (the fused training step), 16 nms_rounds (dense / overflowing segments). */
+#define SSDK_NUM_KERNEL_IDS 17
 SSDK_API int ssdk_ctx_set_profiling(ssdk_ctx* ctx, int enable);
 SSDK_API int ssdk_ctx_profile_read(ssdk_ctx* ctx, double* out_ms, int64_t* out_calls, int n, int reset);
+/* Sticky asynchronous error word of the context (synchronises the stream first): 0, or the code of a condition a kernel met
+ * that no status return could report.  SSDK_ASYNC_ROUNDS_TIMEOUT: the dense-segment stage of the post-processing
+ * (nms_rounds_kernel, a persistent grid with grid-wide barriers) gave up after ~10 s because part of its grid was never
+ * scheduled (the GPU was oversubscribed by other work for that long); the detections of that call are incomplete. */
+#define SSDK_ASYNC_ROUNDS_TIMEOUT 1
+SSDK_API int ssdk_ctx_async_error(ssdk_ctx* ctx, int* out_code);
 /* cudaStreamSynchronize on the context's stream (synchronous). */
 SSDK_API int ssdk_ctx_synchronize(ssdk_ctx* ctx);
 
@@ -186,8 +197,8 @@ SSDK_API int ssdk_loss_finalize(ssdk_ctx* ctx, const double* sums, float* out_lo
 /* Whole training-side hot path for a batch of images resident in HBM:
  * targets (ssd.py:84) + losses (ssd.py:89-133).  Any of out_reg/out_cls/out_matches may be NULL,
  * in which case context workspace is used for them.  Without per-anchor outputs (out_cls_losses == out_loc_losses == NULL)
- * the loss is computed as a flat pass over the logits plus corrections for the matched / ignored anchors, and the matcher
- * runs on the context's side stream concurrently with the flat pass (joined before the corrections). */
+ * the loss is computed as a flat pass over the logits plus corrections for the matched / ignored anchors, by the fused
+ * training-step kernel (one launch: matching CTAs and streaming CTAs side by side). */
 SSDK_API int ssdk_ssd_targets_and_loss(ssdk_ctx* ctx, const float* anchors, const float* logits,
                               const float* codes, const float* gt_boxes, const int32_t* gt_labels,
                               const int32_t* num_boxes, int B, int64_t A, int C, int Gmax,
@@ -195,6 +206,17 @@ SSDK_API int ssdk_ssd_targets_and_loss(ssdk_ctx* ctx, const float* anchors, cons
                               double gamma, double alpha, double* out_sums, float* out_reg,
                               int32_t* out_cls, int32_t* out_matches, float* out_cls_losses,
                               float* out_loc_losses);
+/* SSD.loss (detector/ssd.py:71-133) for a batch in ONE launch: ssdk_ssd_targets_and_loss without per-anchor outputs, plus the
+ * normalisation -- out_losses: DEVICE float[2] = { localization_loss, classification_loss } = sums / max(num_matches, 1)
+ * (ssd.py:121-133).  flags & SSDK_STEP_ALL_REDUCE (the context must be connected, ssdk_comm_connect): the three sums are
+ * all-reduced over the image shards of all ranks by the kernel's last CTA (NVLink peer memory), out_sums then holds the
+ * GLOBAL sums and out_losses the global losses on every rank; a collective like ssdk_comm_all_reduce_sum. */
+#define SSDK_STEP_ALL_REDUCE 1
+SSDK_API int ssdk_ssd_loss_step(ssdk_ctx* ctx, const float* anchors, const float* logits, const float* codes,
+                       const float* gt_boxes, const int32_t* gt_labels, const int32_t* num_boxes, int B, int64_t A, int C,
+                       int Gmax, double positives_threshold, double negatives_threshold, double gamma, double alpha,
+                       int flags, double* out_sums, float* out_losses, float* out_reg, int32_t* out_cls,
+                       int32_t* out_matches);
 /* Same call with HOST buffers (synchronous): copies inputs H2D, runs, copies
  * out_sums (double[3]) and out_losses (float[2], normalised with the LOCAL count) back. */
 SSDK_API int ssdk_ssd_targets_and_loss_host(ssdk_ctx* ctx, const float* anchors, const float* logits,
@@ -273,12 +295,17 @@ SSDK_API int ssdk_head_concat(ssdk_ctx* ctx, const ssdk_head* head, int B, int C
 SSDK_API int ssdk_head_ssd_loss(ssdk_ctx* ctx, const ssdk_head* head, const float* reg_targets, const int32_t* cls_targets,
                        const int32_t* matches, int B, int64_t A, int C, double gamma, double alpha, double* out_sums);
 /* ssdk_ssd_targets_and_loss on the per-level head tensors: target assignment (ssd.py:84) + losses (ssd.py:89-133).  The flat
- * pass over the logits needs no targets, so the matcher runs on the context's side stream concurrently with it (ALU-bound
- * matching hidden behind the HBM-bound stream); any of out_reg / out_cls / out_matches may be NULL (workspace is used). */
+ * pass over the logits needs no targets, so the matching runs inside the same kernel, on CTAs of its own (ALU-bound matching in
+ * the issue slots the HBM-bound stream leaves idle); any of out_reg / out_cls / out_matches may be NULL (workspace is used). */
 SSDK_API int ssdk_head_ssd_targets_and_loss(ssdk_ctx* ctx, const ssdk_head* head, const float* anchors, const float* gt_boxes,
                                    const int32_t* gt_labels, const int32_t* num_boxes, int B, int64_t A, int C, int Gmax,
                                    double positives_threshold, double negatives_threshold, double gamma, double alpha,
                                    double* out_sums, float* out_reg, int32_t* out_cls, int32_t* out_matches);
+/* ssdk_ssd_loss_step on the per-level head tensors. */
+SSDK_API int ssdk_head_ssd_loss_step(ssdk_ctx* ctx, const ssdk_head* head, const float* anchors, const float* gt_boxes,
+                            const int32_t* gt_labels, const int32_t* num_boxes, int B, int64_t A, int C, int Gmax,
+                            double positives_threshold, double negatives_threshold, double gamma, double alpha, int flags,
+                            double* out_sums, float* out_losses, float* out_reg, int32_t* out_cls, int32_t* out_matches);
 /* ssdk_ssd_loss_forward_backward on the per-level head tensors: one pass over the logits produces the loss sums and
  * the gradients, written per level in the head's own layout (every element of `grads` is written).
  * out_sums may be NULL (backward only).  num_matches, upstream as ssdk_ssd_loss_forward_backward. */

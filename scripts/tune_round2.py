@@ -1,0 +1,194 @@
+"""Round-2 tuning sweep (run on the GPU box): graph-replay timings of
+  * the fused training step (ssdk_ssd_loss_step) on cfg2 over its two knobs (matcher CTAs per SM, matcher CTAs' share of the
+    streaming) and against the un-fused launch sequence,
+  * the stand-alone flat pass (targets given),
+  * the inference sub-path on cfg3, and the dense post-processing / training step of the stress configuration (cfg5).
+Prints one JSON object.   python scripts/tune_round2.py [--quick]"""
+import argparse
+import importlib
+import json
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+pkg = importlib.import_module('single-shot-detector_b200')
+syn = importlib.import_module('single-shot-detector_b200.synthetic')
+L = pkg._lib
+
+ap = argparse.ArgumentParser()
+ap.add_argument('--quick', action='store_true')
+ap.add_argument('--reps', type=int, default=40)
+args = ap.parse_args()
+params = {'gamma': 2.0, 'alpha': 0.25}
+peak = 6448.4
+try:
+    peak = float(json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))['hbm_gbs'])
+except Exception:
+    pass
+
+
+def timeit(fn, reps=None, graph=True):
+    reps = reps or args.reps
+    run = fn
+    cap = None
+    if graph:
+        cap = pkg.graph.capture(fn, warmup=2)
+        run = cap.replay
+    for _ in range(3):
+        run()
+    torch.cuda.synchronize()
+    best = 1e9
+    for _ in range(3):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            run()
+        e1.record()
+        torch.cuda.synchronize()
+        best = min(best, e0.elapsed_time(e1) / reps)
+    if cap is not None:
+        cap.release()
+    return best
+
+
+out = {'peak_hbm_gbs': peak, 'lib': os.environ.get('SSDK_LIB', 'default')}
+
+# ---------------------------------------------------------------- cfg2: training side
+cfg = syn.CONFIGS[2]
+H, W, C, B, G = cfg['H'], cfg['W'], cfg['C'], cfg['B'], cfg['G']
+gen = pkg.AnchorGenerator(scale_multipliers=cfg['scale_multipliers'])
+anchors = gen(H, W)
+A = anchors.shape[0]
+gt = {k: torch.from_numpy(v).cuda() for k, v in syn.make_groundtruth(2, B, G, H, W, C).items()}
+g = torch.Generator(device='cuda').manual_seed(2)
+logits = torch.randn([B, A, C], device='cuda', generator=g) - 4.595
+codes = torch.randn([B, A, 4], device='cuda', generator=g)
+ssd = pkg.SSD.from_predictions(H, W, {'encoded_boxes': codes, 'class_predictions': logits}, gen, C)
+b_train = (4 * A * C + 56 * A + 20 * G) * B
+b_flat = 4 * A * C * B
+
+
+def frac(nbytes, ms):
+    return nbytes / (ms * 1e-3) / 1e9 / peak
+
+
+ref = ssd.loss(gt, params)
+out['cfg2_check'] = {k: float(v) for k, v in ref.items()}
+ms = timeit(lambda: ssd.loss(gt, params))
+out['train_fused_default'] = {'ms': ms, 'frac_of_roofline': frac(b_train, ms)}
+sweep = {}
+for ctas in ([1, 2, 3] if not args.quick else [2]):
+    for share in ([0, 25, 50, 75, 100] if not args.quick else [50]):
+        L.set_option(L.SSDK_OPT_MATCH_CTAS_PER_SM, ctas)
+        L.set_option(L.SSDK_OPT_MATCH_FLAT_SHARE_PCT, share)
+        ms = timeit(lambda: ssd.loss(gt, params))
+        sweep['ctas%d_share%d' % (ctas, share)] = round(ms, 5)
+L.set_option(L.SSDK_OPT_MATCH_CTAS_PER_SM, 2)
+L.set_option(L.SSDK_OPT_MATCH_FLAT_SHARE_PCT, 50)
+out['train_fused_sweep_ms'] = sweep
+best = min(sweep, key=sweep.get)
+out['train_fused_best'] = {'knobs': best, 'ms': sweep[best], 'frac_of_roofline': frac(b_train, sweep[best])}
+L.set_option(L.SSDK_OPT_FUSED_TRAIN_STEP, 0)
+ms = timeit(lambda: ssd.loss(gt, params))
+L.set_option(L.SSDK_OPT_FUSED_TRAIN_STEP, 1)
+out['train_unfused'] = {'ms': ms, 'frac_of_roofline': frac(b_train, ms)}
+
+# stand-alone flat pass + matched-anchor pass (targets given), kernels timed by the library's events
+tg = pkg.SSD.assign_targets(anchors, gt)
+lib = L.load()
+ctx = L.context(0)
+sums = torch.zeros([3], dtype=torch.float64, device='cuda')
+
+
+def loss_given_targets():
+    L.check(lib.ssdk_ctx_set_stream(ctx, torch.cuda.current_stream().cuda_stream))
+    d = pkg.HeadPredictions([codes.reshape(B, A, 1, 4)], [logits.reshape(B, A, 1, C)], C, 1, 'channels_last').descriptor()
+    import ctypes
+    L.check(lib.ssdk_head_ssd_loss(ctx, ctypes.byref(d), tg['reg_targets'].data_ptr(), tg['cls_targets'].data_ptr(),
+                                   tg['matches'].data_ptr(), B, A, C, 2.0, 0.25, sums.data_ptr()))
+
+
+try:
+    loss_given_targets()
+    L.set_profiling(True)
+    L.profile_read()
+    for _ in range(20):
+        loss_given_targets()
+    prof = L.profile_read()
+    L.set_profiling(False)
+    ms_flat = prof['head_flat'][0] / max(1, prof['head_flat'][1])
+    out['flat_pass_alone'] = {'ms': ms_flat, 'frac_of_roofline': frac(b_flat, ms_flat), 'rows_ms': prof['head_rows'][0] / max(1, prof['head_rows'][1])}
+except Exception as e:          # the descriptor helper may differ: not essential
+    out['flat_pass_alone'] = {'error': str(e)[:200]}
+    L.set_profiling(False)
+
+ms = timeit(lambda: ssd.loss_with_gradients(gt, params, upstream=(1.0, 1.0)))
+out['train_fwd_bwd'] = {'ms': ms, 'frac_of_roofline': frac((8 * A * C + 72 * A + 20 * G) * B, ms)}
+ms = timeit(lambda: pkg.SSD.assign_targets(anchors, gt))
+out['matcher_alone_ms'] = ms
+
+# ---------------------------------------------------------------- cfg3: inference side
+Bi = syn.CONFIGS[3]['B']
+ilog = torch.randn([Bi, A, C], device='cuda', generator=g) - 7.0
+igt = syn.make_groundtruth(3, Bi, G, H, W, C)
+# plant object-like logits near the ground truth (same recipe as synthetic.make_logits('realistic'), on the device)
+import numpy as np
+anc_np = anchors.cpu().numpy()
+for b in range(Bi):
+    sim = syn._pair_iou(igt['boxes'][b], anc_np)
+    for gi in range(G):
+        idx = torch.from_numpy(np.nonzero(sim[gi] >= 0.4)[0]).cuda()
+        ilog[b, idx, int(igt['labels'][b, gi])] = 1.5 + 1.5 * torch.randn([idx.numel()], device='cuda', generator=g)
+icod = torch.randn([Bi, A, 4], device='cuda', generator=g)
+issd = pkg.SSD.from_predictions(H, W, {'encoded_boxes': icod, 'class_predictions': ilog}, gen, C)
+p = issd.get_predictions(0.05, 0.5, 100)
+ms = timeit(lambda: issd.get_predictions(0.05, 0.5, 100))
+b_inf = (4 * A * C + 32 * A + 24 * C * 100 + 4) * Bi
+out['infer'] = {'ms': ms, 'frac_of_roofline': frac(b_inf, ms), 'detections_image0': int(p['num_boxes'][0]),
+                'workspace_MB': L.workspace_bytes() / 1e6}
+L.set_profiling(True)
+L.profile_read()
+for _ in range(10):
+    issd.get_predictions(0.05, 0.5, 100)
+prof = L.profile_read()
+L.set_profiling(False)
+out['infer_kernels_ms'] = {k: v[0] / 10 for k, v in prof.items() if v[1]}
+both = pkg.graph.concurrent(lambda: ssd.loss(gt, params), lambda: issd.get_predictions(0.05, 0.5, 100))
+ms = timeit(both)
+out['step_two_streams'] = {'ms': ms, 'images_per_s': (B + Bi) / (ms * 1e-3)}
+ms = timeit(lambda: (ssd.loss(gt, params), issd.get_predictions(0.05, 0.5, 100)))
+out['step_one_stream'] = {'ms': ms, 'images_per_s': (B + Bi) / (ms * 1e-3)}
+del ilog, icod, issd, logits, codes, ssd
+torch.cuda.empty_cache()
+
+# ---------------------------------------------------------------- cfg5: stress
+cfg = syn.CONFIGS[5]
+H, W, C, B, G = cfg['H'], cfg['W'], cfg['C'], cfg['B'], cfg['G']
+gen5 = pkg.AnchorGenerator(scale_multipliers=cfg['scale_multipliers'])
+anc5 = gen5(H, W)
+A = anc5.shape[0]
+gt5 = {k: torch.from_numpy(v).cuda() for k, v in syn.make_groundtruth(5, B, G, H, W, C).items()}
+g5 = torch.Generator(device='cuda').manual_seed(5)
+log5 = torch.randn([B, A, C], device='cuda', generator=g5) * 1.5 - 2.0
+cod5 = torch.randn([B, A, 4], device='cuda', generator=g5)
+s5 = pkg.SSD.from_predictions(H, W, {'encoded_boxes': cod5, 'class_predictions': log5}, gen5, C)
+p5 = s5.get_predictions(0.05, 0.5, 100)
+ms_pp = timeit(lambda: s5.get_predictions(0.05, 0.5, 100), reps=10)
+L.set_profiling(True)
+L.profile_read()
+for _ in range(5):
+    s5.get_predictions(0.05, 0.5, 100)
+prof = L.profile_read()
+L.set_profiling(False)
+ms_t = timeit(lambda: s5.loss(gt5, params), reps=10)
+ms_fb = timeit(lambda: s5.loss_with_gradients(gt5, params), reps=10)
+ms_m = timeit(lambda: pkg.SSD.assign_targets(anc5, gt5), reps=10)
+out['stress'] = {'postprocess_dense_ms': ms_pp, 'postprocess_kernels_ms': {k: v[0] / 5 for k, v in prof.items() if v[1]},
+                 'postprocess_frac_of_roofline': frac((4 * A * C + 32 * A + 24 * C * 100 + 4) * B, ms_pp),
+                 'detections_image0': int(p5['num_boxes'][0]), 'async_error': L.async_error(),
+                 'train_forward_ms': ms_t, 'train_forward_backward_ms': ms_fb, 'matcher_alone_ms': ms_m,
+                 'matcher_iou_pairs_per_s': B * G * A / (ms_m * 1e-3)}
+print(json.dumps(out))

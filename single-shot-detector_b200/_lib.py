@@ -25,6 +25,7 @@ _SIGNATURES = {
     'ssdk_ctx_workspace_bytes': (c_i64, [P]),
     'ssdk_ctx_launch_count': (c_i64, [P]),
     'ssdk_ctx_synchronize': (c_int, [P]),
+    'ssdk_ctx_async_error': (c_int, [P, ctypes.POINTER(c_int)]),
     'ssdk_ctx_set_profiling': (c_int, [P, c_int]),
     'ssdk_ctx_profile_read': (c_int, [P, P, P, c_int, c_int]),
     'ssdk_num_anchors': (c_int, [c_int, c_int, P, c_int, c_int, ctypes.POINTER(c_i64), P]),
@@ -48,6 +49,10 @@ _SIGNATURES = {
     'ssdk_ssd_loss_backward': (c_int, [P, P, P, P, P, P, c_i64, c_i64, c_int, c_double, c_double, P, P, P, P]),
     'ssdk_ssd_targets_and_loss': (c_int, [P, P, P, P, P, P, P, c_int, c_i64, c_int, c_int, c_double, c_double,
                                           c_double, c_double, P, P, P, P, P, P]),
+    'ssdk_ssd_loss_step': (c_int, [P, P, P, P, P, P, P, c_int, c_i64, c_int, c_int, c_double, c_double, c_double, c_double,
+                                   c_int, P, P, P, P, P]),
+    'ssdk_head_ssd_loss_step': (c_int, [P, P, P, P, P, P, c_int, c_i64, c_int, c_int, c_double, c_double, c_double, c_double,
+                                        c_int, P, P, P, P, P]),
     'ssdk_ssd_targets_and_loss_host': (c_int, [P, P, P, P, P, P, P, c_int, c_i64, c_int, c_int, c_double, c_double,
                                                c_double, c_double, P, P]),
     'ssdk_postprocess': (c_int, [P, P, P, P, c_int, c_int, c_i64, c_int, c_double, c_double, c_int, P, P, P, P, P]),
@@ -142,7 +147,7 @@ def context(device_index):
 
 
 KERNEL_IDS = ['anchors', 'match', 'force_match', 'ssd_loss', 'loss_reduce', 'filter', 'sort', 'nms', 'pack', 'other',
-              'ssd_loss_backward', 'head_flat', 'head_rows', 'head_concat', 'comm']
+              'ssd_loss_backward', 'head_flat', 'head_rows', 'head_concat', 'comm', 'train_step', 'nms_rounds']
 
 
 def set_profiling(enable, device_index=0):
@@ -158,7 +163,16 @@ def profile_read(device_index=0, reset=True):
     return {k: (ms[i], int(calls[i])) for i, k in enumerate(KERNEL_IDS)}
 
 
-SSDK_OPT_OVERLAP_MATCHER = 1
+SSDK_OPT_FUSED_TRAIN_STEP, SSDK_OPT_MATCH_CTAS_PER_SM, SSDK_OPT_MATCH_FLAT_SHARE_PCT = 1, 2, 3
+SSDK_STEP_ALL_REDUCE = 1
+SSDK_ASYNC_ROUNDS_TIMEOUT = 1
+
+
+def async_error(device_index=0):
+    """Sticky asynchronous error word of the context (0 = none); synchronises its stream."""
+    e = c_int(0)
+    check(load().ssdk_ctx_async_error(context(device_index), ctypes.byref(e)))
+    return int(e.value)
 
 
 def set_option(option, value, device_index=0):

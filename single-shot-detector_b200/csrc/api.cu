@@ -1,6 +1,7 @@
 // Context, error reporting and workspace management of libssdk.
 #include "common.cuh"
 
+#include <stdlib.h>
 #include <string.h>
 
 static thread_local char g_err[512] = "";
@@ -76,6 +77,18 @@ int ssdk_prof_begin(ssdk_ctx* ctx, int id) {
 
 void ssdk_prof_end(ssdk_ctx* ctx, int slot) { cudaEventRecord(ctx->prof_ev[2 * slot + 1], ctx->stream); }
 
+// integer knob from the environment: unset -> dflt; otherwise clamped to [lo, hi] and rounded down to a multiple of `mult`
+static int env_int(const char* name, int dflt, int lo, int hi, int mult) {
+    const char* e = getenv(name);
+    if (!e || !*e) return dflt;
+    long v = strtol(e, nullptr, 10);
+    if (v < lo) v = lo;
+    if (v > hi) v = hi;
+    v -= v % mult;
+    if (v < lo) v = lo;
+    return (int)v;
+}
+
 extern "C" {
 
 int ssdk_ctx_set_profiling(ssdk_ctx* ctx, int enable) {
@@ -124,15 +137,16 @@ int ssdk_ctx_create(int device, void* stream, ssdk_ctx** out) {
     c->device = device;
     c->stream = (cudaStream_t)stream;
     c->num_sms = prop.multiProcessorCount;
-    SSDK_CHECK_CUDA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
     for (int i = 0; i < 4; ++i) SSDK_CHECK_CUDA(cudaEventCreateWithFlags(&c->ev[i], cudaEventDisableTiming));
-    if (cudaHostAlloc((void**)&c->hint_host, 2 * sizeof(int), cudaHostAllocMapped) == cudaSuccess) {
-        c->hint_host[0] = c->hint_host[1] = 0;
-        if (cudaHostGetDevicePointer((void**)&c->hint_dev, c->hint_host, 0) != cudaSuccess) c->hint_dev = nullptr;
-    } else {
-        cudaGetLastError();
-        c->hint_host = nullptr;
-    }
+    SSDK_CHECK_CUDA(cudaMalloc((void**)&c->dev_err, 16));
+    SSDK_CHECK_CUDA(cudaMemset(c->dev_err, 0, 16));
+    // tuning knobs: read once, forced into their valid ranges (an out-of-range value cannot reach a kernel)
+    c->tune_head_ctas = env_int("SSDK_HEAD_CTAS", 0, 1, 8, 1);            // CTAs per SM of the stand-alone flat pass
+    c->tune_loss_rpw = env_int("SSDK_LOSS_RPW", 0, 4, 32, 4);             // rows per warp of ssd_loss_kernel: a multiple of 4 (16-byte TMA tiles)
+    c->tune_loss_stages = env_int("SSDK_LOSS_STAGES", 0, 2, 4, 1);        // TMA ring depth
+    c->tune_loss_ctas = env_int("SSDK_LOSS_CTAS", 0, 1, 8, 1);            // the partials buffer holds num_sms * 8 CTAs
+    c->match_ctas_per_sm = env_int("SSDK_MATCH_CTAS", 2, 1, 4, 1);
+    c->match_flat_share_pct = env_int("SSDK_MATCH_FLAT_SHARE", 50, 0, 100, 1);
     *out = c;
     return SSDK_OK;
 }
@@ -140,7 +154,15 @@ int ssdk_ctx_create(int device, void* stream, ssdk_ctx** out) {
 int ssdk_ctx_set_option(ssdk_ctx* ctx, int option, int value) {
     SSDK_REQUIRE(ctx != nullptr, SSDK_ERR_ARG, "null context");
     switch (option) {
-        case SSDK_OPT_OVERLAP_MATCHER: ctx->overlap_matcher = value ? 1 : 0; return SSDK_OK;
+        case SSDK_OPT_FUSED_TRAIN_STEP: ctx->fused_train_step = value ? 1 : 0; return SSDK_OK;
+        case SSDK_OPT_MATCH_CTAS_PER_SM:
+            SSDK_REQUIRE(value >= 1 && value <= 4, SSDK_ERR_ARG, "SSDK_OPT_MATCH_CTAS_PER_SM must be in [1,4] (got %d)", value);
+            ctx->match_ctas_per_sm = value;
+            return SSDK_OK;
+        case SSDK_OPT_MATCH_FLAT_SHARE_PCT:
+            SSDK_REQUIRE(value >= 0 && value <= 100, SSDK_ERR_ARG, "SSDK_OPT_MATCH_FLAT_SHARE_PCT must be in [0,100] (got %d)", value);
+            ctx->match_flat_share_pct = value;
+            return SSDK_OK;
         default: ssdk_set_error("ssdk_ctx_set_option: unknown option %d", option); return SSDK_ERR_ARG;
     }
 }
@@ -157,16 +179,15 @@ int ssdk_ctx_destroy(ssdk_ctx* ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     ssdk_buf* bufs[] = {&ctx->ws_gtbest, &ctx->ws_partials, &ctx->ws_reg, &ctx->ws_cls, &ctx->ws_matches,
-                        &ctx->ws_cand, &ctx->ws_counts, &ctx->ws_seg, &ctx->ws_head, &ctx->ws_summ};
+                        &ctx->ws_cand, &ctx->ws_counts, &ctx->ws_seg, &ctx->ws_head, &ctx->ws_summ, &ctx->ws_train};
     for (ssdk_buf* b : bufs) if (b->p) cudaFree(b->p);
     for (ssdk_buf& b : ctx->ws_stage) if (b.p) cudaFree(b.p);
     if (ctx->prof_ev) {
         for (int i = 0; i < 2 * SSDK_PROFILE_EVENTS; ++i) cudaEventDestroy(ctx->prof_ev[i]);
         delete[] ctx->prof_ev;
     }
-    if (ctx->hint_host) cudaFreeHost(ctx->hint_host);
-    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     for (int i = 0; i < 4; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
+    if (ctx->dev_err) cudaFree(ctx->dev_err);
     delete ctx;
     return SSDK_OK;
 }
@@ -175,13 +196,21 @@ int64_t ssdk_ctx_workspace_bytes(const ssdk_ctx* ctx) {
     if (!ctx) return 0;
     int64_t t = 0;
     const ssdk_buf* bufs[] = {&ctx->ws_gtbest, &ctx->ws_partials, &ctx->ws_reg, &ctx->ws_cls, &ctx->ws_matches,
-                              &ctx->ws_cand, &ctx->ws_counts, &ctx->ws_seg, &ctx->ws_head, &ctx->ws_summ};
+                              &ctx->ws_cand, &ctx->ws_counts, &ctx->ws_seg, &ctx->ws_head, &ctx->ws_summ, &ctx->ws_train};
     for (const ssdk_buf* b : bufs) t += (int64_t)b->cap;
     for (const ssdk_buf& b : ctx->ws_stage) t += (int64_t)b.cap;
     return t;
 }
 
 int64_t ssdk_ctx_launch_count(const ssdk_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int ssdk_ctx_async_error(ssdk_ctx* ctx, int* out_code) {
+    SSDK_TRY(ssdk_ctx_enter(ctx));
+    SSDK_REQUIRE(out_code != nullptr, SSDK_ERR_ARG, "ssdk_ctx_async_error: out_code is NULL");
+    SSDK_CHECK_CUDA(cudaStreamSynchronize(ctx->stream));
+    SSDK_CHECK_CUDA(cudaMemcpy(out_code, ctx->dev_err, sizeof(int), cudaMemcpyDeviceToHost));
+    return SSDK_OK;
+}
 
 int ssdk_ctx_synchronize(ssdk_ctx* ctx) {
     SSDK_TRY(ssdk_ctx_enter(ctx));

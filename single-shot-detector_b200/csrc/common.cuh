@@ -19,7 +19,7 @@ struct ssdk_buf {
 enum ssdk_kernel_id {
     SSDK_K_ANCHORS = 0, SSDK_K_MATCH, SSDK_K_FORCE_MATCH, SSDK_K_LOSS, SSDK_K_LOSS_REDUCE, SSDK_K_FILTER,
     SSDK_K_SORT, SSDK_K_NMS, SSDK_K_PACK, SSDK_K_OTHER, SSDK_K_LOSS_BACKWARD, SSDK_K_HEAD_FLAT, SSDK_K_HEAD_ROWS,
-    SSDK_K_HEAD_CONCAT, SSDK_K_COMM, SSDK_K_COUNT
+    SSDK_K_HEAD_CONCAT, SSDK_K_COMM, SSDK_K_TRAIN_STEP, SSDK_K_NMS_ROUNDS, SSDK_K_COUNT
 };
 #define SSDK_PROFILE_EVENTS 2048
 
@@ -45,10 +45,13 @@ struct ssdk_ctx {
     int prof_id[SSDK_PROFILE_EVENTS];
     double prof_ms[SSDK_K_COUNT] = {0};
     long long prof_calls[SSDK_K_COUNT] = {0};
-    cudaStream_t copy_stream = nullptr;
-    int overlap_matcher = 1; // SSDK_OPT_OVERLAP_MATCHER
-    int* hint_host = nullptr; // mapped pinned int[2]: [0] = large segments met by the last post-processing call (density hint)
-    int* hint_dev = nullptr;  // device alias of hint_host
+    ssdk_buf ws_train;       // fused training step: per-CTA partials | ticket, forced-match deltas, per-image tickets, per-GT keys (zero between launches)
+    int fused_train_step = 1;      // SSDK_OPT_FUSED_TRAIN_STEP
+    int match_ctas_per_sm = 2;     // SSDK_OPT_MATCH_CTAS_PER_SM
+    int match_flat_share_pct = 50; // SSDK_OPT_MATCH_FLAT_SHARE_PCT
+    // tuning knobs, read from the environment ONCE (ssdk_ctx_create) and validated there; 0 = automatic
+    int tune_head_ctas = 0, tune_loss_rpw = 0, tune_loss_stages = 0, tune_loss_ctas = 0;
+    int* dev_err = nullptr;  // device int: sticky asynchronous error raised by a kernel (ssdk_ctx_async_error)
     void* comm = nullptr;    // peer-memory communicator (comm.cu), NULL until ssdk_comm_local_handle
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
 };

@@ -1,0 +1,78 @@
+// The flat pass over the class logits, shared by head_flat_kernel (head.cu) and the fused training-step kernel
+// (train_step.cu): every level's class tensor is streamed as one flat array of 16 KB chunks (FLAT_THREADS x FLAT_U 128-bit
+// no-allocate loads), each element is summed as if it were a negative (detector/losses.py:22-50 with targets == 0), and the
+// few matched / ignored anchors are corrected elsewhere.  See head.cu for why this is layout independent.
+#pragma once
+#include "focal_math.cuh"
+
+#define FLAT_THREADS 256
+#ifndef FLAT_U
+#define FLAT_U 4                                        // float4 per thread and chunk (2: 0.166 ms, 8: 0.160 ms, 4: 0.148 ms forward)
+#endif
+#define FLAT_CHUNK4 (FLAT_THREADS * FLAT_U)             // float4 per chunk (16 KB)
+
+struct FlatSegs {
+    int n;                                              // class-tensor segments [0, n); WITH_GRAD: zero-fill segments [n, 2n)
+    int nseg;                                           // n or 2n
+    const float* src[SSDK_MAX_LEVELS];
+    float* dst[2 * SSDK_MAX_LEVELS];                    // WITH_GRAD: [0,n) class gradients (same flat indexing), [n,2n) box gradients
+    long long count[2 * SSDK_MAX_LEVELS];               // floats per segment (B * n*C * h*w, resp. B * n*4 * h*w)
+    long long chunk0[2 * SSDK_MAX_LEVELS + 1];          // prefix sums of the per-segment chunk counts
+};
+
+struct FlatChunk {
+    float4 v[FLAT_U];
+    long long i4;        // index of v[0] (in float4) for this thread
+    int lvl;
+};
+
+// Loads chunk g (global chunk index over all segments) for this thread; `cursor` is the segment of the previously loaded
+// chunk (chunks are visited in ascending order by a CTA).
+__device__ __forceinline__ void flat_load(const FlatSegs& S, FlatChunk& ck, long long g, int& cursor, int tid) {
+    while (g >= S.chunk0[cursor + 1]) ++cursor;
+    ck.lvl = cursor;
+    ck.i4 = (g - S.chunk0[cursor]) * FLAT_CHUNK4 + tid;
+    const long long n4 = S.count[cursor] >> 2;
+    const float4* src4 = (const float4*)S.src[cursor];
+    const float4 ninf4 = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+#pragma unroll
+    for (int u = 0; u < FLAT_U; ++u) {
+        const long long i = ck.i4 + u * FLAT_THREADS;
+        ck.v[u] = (i < n4) ? ld_stream_f4(src4 + i) : ninf4;
+    }
+}
+
+// Sum over this thread's FLAT_U float4 of the negative-class focal term (without the (1-alpha) factor), forward only.
+template <int GAMMA_MODE>
+__device__ __forceinline__ float flat_value(const FlatSegs& S, const FlatChunk& ck, long long g, float gamma, int tid) {
+    float s;
+    bool general = (GAMMA_MODE != 0);
+    if (GAMMA_MODE == 0) {
+        f32x2 a4[4] = {0ull, 0ull, 0ull, 0ull};
+        float mx = -INFINITY;
+#pragma unroll
+        for (int u = 0; u < FLAT_U; u += 2) focal_half8(ck.v[u], ck.v[u + 1], a4, mx);
+        float s0, s1;
+        unpack2(add2(add2(a4[0], a4[1]), add2(a4[2], a4[3])), s0, s1);
+        s = s0 + s1;
+        general = mx > FOCAL_HALF_MAX_X;                    // some logit > -ln 2: redo these 16 with the general form
+    }
+    if (general) {
+        f32x2 a01 = 0ull, a23 = 0ull;
+#pragma unroll
+        for (int u = 0; u < FLAT_U; ++u) {
+            a01 = focal_negative2<GAMMA_MODE>(ck.v[u].x, ck.v[u].y, gamma, a01);
+            a23 = focal_negative2<GAMMA_MODE>(ck.v[u].z, ck.v[u].w, gamma, a23);
+        }
+        float s0, s1;
+        unpack2(add2(a01, a23), s0, s1);
+        s = s0 + s1;
+    }
+    // the (< 4) floats of a level beyond its last float4, handled with the level's last chunk
+    if (g + 1 == S.chunk0[ck.lvl + 1]) {
+        const long long n = S.count[ck.lvl];
+        const int tail = (int)(n & 3);
+        if (tid < tail) s += focal_negative<GAMMA_MODE>(S.src[ck.lvl][(n & ~3ll) + tid], gamma);
+    }
+    return s;
+}

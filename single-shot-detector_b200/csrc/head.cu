@@ -22,24 +22,10 @@
 // reference's tensors, and as the un-fused baseline in bench.py.
 #include <stdlib.h>
 
-#include "focal_math.cuh"
+#include "flat.cuh"
 
 // plain stores: st.global.cs (evict-first) was measured and changes nothing (0.2751 vs 0.2725 ms for the fused step)
 #define HEAD_STORE(p, v) (*(p) = (v))
-#define FLAT_THREADS 256
-#ifndef FLAT_U
-#define FLAT_U 4                                        // float4 per thread and chunk (2: 0.166 ms, 8: 0.160 ms, 4: 0.148 ms forward)
-#endif
-#define FLAT_CHUNK4 (FLAT_THREADS * FLAT_U)             // float4 per chunk (16 KB)
-
-struct FlatSegs {
-    int n;                                              // class-tensor segments [0, n); WITH_GRAD: zero-fill segments [n, 2n)
-    int nseg;                                           // n or 2n
-    const float* src[SSDK_MAX_LEVELS];
-    float* dst[2 * SSDK_MAX_LEVELS];                    // WITH_GRAD: [0,n) class gradients (same flat indexing), [n,2n) box gradients
-    long long count[2 * SSDK_MAX_LEVELS];               // floats per segment (B * n*C * h*w, resp. B * n*4 * h*w)
-    long long chunk0[2 * SSDK_MAX_LEVELS + 1];          // prefix sums of the per-segment chunk counts
-};
 
 struct HeadGradPtrs {
     float* cls[SSDK_MAX_LEVELS];
@@ -47,12 +33,6 @@ struct HeadGradPtrs {
 };
 
 // ---------------------------------------------------------------------------------------------- 1. flat pass
-struct FlatChunk {
-    float4 v[FLAT_U];
-    long long i4;        // index of v[0] (in float4) for this thread
-    int lvl;
-};
-
 template <int GAMMA_MODE, bool WITH_GRAD>
 __global__ void __launch_bounds__(FLAT_THREADS) head_flat_kernel(const FlatSegs S, float gamma, float alpha,
                                                                   const double* __restrict__ norm_count,
@@ -60,7 +40,6 @@ __global__ void __launch_bounds__(FLAT_THREADS) head_flat_kernel(const FlatSegs 
                                                                   double* __restrict__ partials /*[grid]*/) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const long long total = S.chunk0[S.nseg];
-    const float4 ninf4 = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
     float k_neg = 0.0f;
     if (WITH_GRAD) {
         const double norm = fmax(*norm_count, 1.0);                       // ssd.py:123 (global count)
@@ -71,21 +50,22 @@ __global__ void __launch_bounds__(FLAT_THREADS) head_flat_kernel(const FlatSegs 
 
     int cursor = 0;                                                       // level of the most recently loaded chunk
     auto load = [&](FlatChunk& ck, long long g) {
-        while (g >= S.chunk0[cursor + 1]) ++cursor;
-        ck.lvl = cursor;
-        ck.i4 = (g - S.chunk0[cursor]) * FLAT_CHUNK4 + tid;
-        if (WITH_GRAD && cursor >= S.n) return;                           // zero-fill segment: nothing to read
-        const long long n4 = S.count[cursor] >> 2;
-        const float4* src4 = (const float4*)S.src[cursor];
-#pragma unroll
-        for (int u = 0; u < FLAT_U; ++u) {
-            const long long i = ck.i4 + u * FLAT_THREADS;
-            ck.v[u] = (i < n4) ? ld_stream_f4(src4 + i) : ninf4;
+        if (WITH_GRAD) {
+            while (g >= S.chunk0[cursor + 1]) ++cursor;
+            if (cursor >= S.n) {                                          // zero-fill segment: nothing to read
+                ck.lvl = cursor;
+                ck.i4 = (g - S.chunk0[cursor]) * FLAT_CHUNK4 + tid;
+                return;
+            }
         }
+        flat_load(S, ck, g, cursor, tid);
     };
     auto compute = [&](FlatChunk& ck, long long g) {
-        float s;
-        if (WITH_GRAD && ck.lvl >= S.n) {
+        if (!WITH_GRAD) {
+            acc += (double)flat_value<GAMMA_MODE>(S, ck, g, gamma, tid);
+            return;
+        }
+        if (ck.lvl >= S.n) {
             // box gradients: zero everywhere, head_rows_kernel then scatters the matched anchors' values
             const long long n = S.count[ck.lvl], n4 = n >> 2;
             float4* dst4 = (float4*)S.dst[ck.lvl];
@@ -97,46 +77,20 @@ __global__ void __launch_bounds__(FLAT_THREADS) head_flat_kernel(const FlatSegs 
             if (g + 1 == S.chunk0[ck.lvl + 1] && tid < (int)(n & 3)) S.dst[ck.lvl][(n & ~3ll) + tid] = 0.0f;
             return;
         }
-        if (WITH_GRAD) {
-            const long long n4 = S.count[ck.lvl] >> 2;
-            float4* dst4 = (float4*)S.dst[ck.lvl];
-            float t = 0.0f;
+        const long long n4 = S.count[ck.lvl] >> 2;
+        float4* dst4 = (float4*)S.dst[ck.lvl];
+        float s = 0.0f;
 #pragma unroll
-            for (int u = 0; u < FLAT_U; ++u) {
-                float4 v = ck.v[u];
-                float f0, f1, f2, f3;
-                v.x = k_neg * focal_negative_both<GAMMA_MODE>(v.x, gamma, f0);
-                v.y = k_neg * focal_negative_both<GAMMA_MODE>(v.y, gamma, f1);
-                v.z = k_neg * focal_negative_both<GAMMA_MODE>(v.z, gamma, f2);
-                v.w = k_neg * focal_negative_both<GAMMA_MODE>(v.w, gamma, f3);
-                t += (f0 + f1) + (f2 + f3);
-                const long long i = ck.i4 + u * FLAT_THREADS;
-                if (i < n4) HEAD_STORE(dst4 + i, v);
-            }
-            s = t;
-        } else {
-            bool general = (GAMMA_MODE != 0);
-            if (GAMMA_MODE == 0) {
-                f32x2 a4[4] = {0ull, 0ull, 0ull, 0ull};
-                unsigned allneg = 0x80000000u;
-#pragma unroll
-                for (int u = 0; u < FLAT_U; u += 2) focal_fast8(ck.v[u], ck.v[u + 1], a4, allneg);
-                float s0, s1;
-                unpack2(add2(add2(a4[0], a4[1]), add2(a4[2], a4[3])), s0, s1);
-                s = s0 + s1;
-                general = (allneg >> 31) == 0u;                           // some logit >= +0: redo these with the general form
-            }
-            if (general) {
-                f32x2 a01 = 0ull, a23 = 0ull;
-#pragma unroll
-                for (int u = 0; u < FLAT_U; ++u) {
-                    a01 = focal_negative2<GAMMA_MODE>(ck.v[u].x, ck.v[u].y, gamma, a01);
-                    a23 = focal_negative2<GAMMA_MODE>(ck.v[u].z, ck.v[u].w, gamma, a23);
-                }
-                float s0, s1;
-                unpack2(add2(a01, a23), s0, s1);
-                s = s0 + s1;
-            }
+        for (int u = 0; u < FLAT_U; ++u) {
+            float4 v = ck.v[u];
+            float f0, f1, f2, f3;
+            v.x = k_neg * focal_negative_both<GAMMA_MODE>(v.x, gamma, f0);
+            v.y = k_neg * focal_negative_both<GAMMA_MODE>(v.y, gamma, f1);
+            v.z = k_neg * focal_negative_both<GAMMA_MODE>(v.z, gamma, f2);
+            v.w = k_neg * focal_negative_both<GAMMA_MODE>(v.w, gamma, f3);
+            s += (f0 + f1) + (f2 + f3);
+            const long long i = ck.i4 + u * FLAT_THREADS;
+            if (i < n4) HEAD_STORE(dst4 + i, v);
         }
         // the (< 4) floats of a level beyond its last float4, handled with the level's last chunk
         if (g + 1 == S.chunk0[ck.lvl + 1]) {
@@ -144,14 +98,9 @@ __global__ void __launch_bounds__(FLAT_THREADS) head_flat_kernel(const FlatSegs 
             const int tail = (int)(n & 3);
             if (tid < tail) {
                 const long long e = (n & ~3ll) + tid;
-                const float x = S.src[ck.lvl][e];
-                if (WITH_GRAD) {
-                    float f;
-                    S.dst[ck.lvl][e] = k_neg * focal_negative_both<GAMMA_MODE>(x, gamma, f);
-                    s += f;
-                } else {
-                    s += focal_negative<GAMMA_MODE>(x, gamma);
-                }
+                float f;
+                S.dst[ck.lvl][e] = k_neg * focal_negative_both<GAMMA_MODE>(S.src[ck.lvl][e], gamma, f);
+                s += f;
             }
         }
         acc += (double)s;
@@ -163,9 +112,9 @@ __global__ void __launch_bounds__(FLAT_THREADS) head_flat_kernel(const FlatSegs 
         long long g = blockIdx.x;
         const long long step = gridDim.x;
         if (!WITH_GRAD) {
-            // forward: no register double-buffering -- 40 registers instead of 58 give six resident CTAs per SM instead of
-            // four; the extra warps hide the load latency just as well (0.1504 vs 0.1600 ms for the forward sub-path) and leave
-            // the co-running matcher more issue slots.  The read+write pass below does need the prefetch (0.2728 vs 0.2862 ms).
+            // forward: no register double-buffering -- fewer registers give six resident CTAs per SM instead of four; the
+            // extra warps hide the load latency just as well (0.1504 vs 0.1600 ms for the forward sub-path).  The read+write
+            // pass below does need the prefetch (0.2728 vs 0.2862 ms).
             for (; g < total; g += step) {
                 load(ca, g);
                 compute(ca, g);
@@ -443,6 +392,25 @@ int ssdk_head_geom(const ssdk_head* head, int B, int64_t A, int C, bool need_cls
     return SSDK_OK;
 }
 
+// The class tensors of all levels as the chunk list of the flat pass (forward: segments [0, num_levels)).
+void ssdk_flat_segments(const HeadGeom& G, int B, int C, FlatSegs* out) {
+    FlatSegs S;
+    const int nl = G.num_levels;
+    S.n = nl;
+    S.nseg = nl;
+    long long chunks = 0;
+    for (int l = 0; l < SSDK_MAX_LEVELS; ++l) S.src[l] = nullptr;
+    for (int sg = 0; sg < 2 * SSDK_MAX_LEVELS; ++sg) { S.dst[sg] = nullptr; S.count[sg] = 0; }
+    for (int sg = 0; sg < nl; ++sg) {
+        S.chunk0[sg] = chunks;
+        S.count[sg] = (long long)B * G.per_loc * C * G.hw[sg];
+        chunks += (S.count[sg] + 4 * FLAT_CHUNK4 - 1) / (4 * FLAT_CHUNK4);
+        S.src[sg] = G.cls[sg];
+    }
+    for (int sg = nl; sg <= 2 * SSDK_MAX_LEVELS; ++sg) S.chunk0[sg] = chunks;
+    *out = S;
+}
+
 // phases: 1 = the flat pass (needs no targets), 2 = the matched / ignored anchors + final reduction, 3 = both
 int ssdk_head_loss_core(ssdk_ctx* ctx, const HeadGeom& G, const float* reg_targets, const int32_t* cls_targets,
                         const int32_t* matches, int B, int64_t A, int C, double gamma, double alpha, const double* num_matches,
@@ -461,26 +429,30 @@ int ssdk_head_loss_core(ssdk_ctx* ctx, const HeadGeom& G, const float* reg_targe
     FlatSegs S;
     HeadGradPtrs GR;
     const int nl = G.num_levels;
-    S.n = nl;
-    S.nseg = with_grad ? 2 * nl : nl;
-    long long chunks = 0;
-    for (int l = 0; l < SSDK_MAX_LEVELS; ++l) { S.src[l] = nullptr; GR.cls[l] = nullptr; GR.box[l] = nullptr; }
-    for (int sg = 0; sg < 2 * SSDK_MAX_LEVELS; ++sg) { S.dst[sg] = nullptr; S.count[sg] = 0; }
-    for (int sg = 0; sg < S.nseg; ++sg) {
-        const int l = sg < nl ? sg : sg - nl;
-        S.chunk0[sg] = chunks;
-        S.count[sg] = (long long)B * G.per_loc * (sg < nl ? C : 4) * G.hw[l];
-        chunks += (S.count[sg] + 4 * FLAT_CHUNK4 - 1) / (4 * FLAT_CHUNK4);
-        if (sg < nl) S.src[l] = G.cls[l];
-        if (with_grad && S.count[sg] > 0) {
-            float* gp = sg < nl ? grads->class_predictions[l] : grads->encoded_boxes[l];
-            SSDK_REQUIRE(gp != nullptr, SSDK_ERR_ARG, "ssdk_head_ssd_loss_forward_backward: grads of level %d are NULL", l);
-            SSDK_REQUIRE(aligned16(gp), SSDK_ERR_SHAPE, "ssdk_head_ssd_loss_forward_backward: grads of level %d must be 16-byte aligned", l);
-            S.dst[sg] = gp;
-            if (sg < nl) GR.cls[l] = gp; else GR.box[l] = gp;            // box gradients: zero-filled by the flat kernel,
-        }                                                                // matched anchors scattered by head_rows_kernel
+    ssdk_flat_segments(G, B, C, &S);
+    for (int l = 0; l < SSDK_MAX_LEVELS; ++l) { GR.cls[l] = nullptr; GR.box[l] = nullptr; }
+    if (with_grad) {
+        // zero-fill segments [n, 2n) for the box gradients, appended to the chunk list
+        long long chunks_g = S.chunk0[nl];
+        S.nseg = 2 * nl;
+        for (int sg = 0; sg < S.nseg; ++sg) {
+            const int l = sg < nl ? sg : sg - nl;
+            if (sg >= nl) {
+                S.chunk0[sg] = chunks_g;
+                S.count[sg] = (long long)B * G.per_loc * 4 * G.hw[l];
+                chunks_g += (S.count[sg] + 4 * FLAT_CHUNK4 - 1) / (4 * FLAT_CHUNK4);
+            }
+            if (S.count[sg] > 0) {
+                float* gp = sg < nl ? grads->class_predictions[l] : grads->encoded_boxes[l];
+                SSDK_REQUIRE(gp != nullptr, SSDK_ERR_ARG, "ssdk_head_ssd_loss_forward_backward: grads of level %d are NULL", l);
+                SSDK_REQUIRE(aligned16(gp), SSDK_ERR_SHAPE, "ssdk_head_ssd_loss_forward_backward: grads of level %d must be 16-byte aligned", l);
+                S.dst[sg] = gp;
+                if (sg < nl) GR.cls[l] = gp; else GR.box[l] = gp;        // box gradients: zero-filled by the flat kernel,
+            }                                                            // matched anchors scattered by head_rows_kernel
+        }
+        for (int sg = S.nseg; sg <= 2 * SSDK_MAX_LEVELS; ++sg) S.chunk0[sg] = chunks_g;
     }
-    for (int sg = S.nseg; sg <= 2 * SSDK_MAX_LEVELS; ++sg) S.chunk0[sg] = chunks;
+    const long long chunks = S.chunk0[S.nseg];
 
     // persistent-style grid: exactly the number of co-resident CTAs (a larger grid would add a partial second wave)
     static int occ_cache[4] = {0, 0, 0, 0};
@@ -493,7 +465,7 @@ int ssdk_head_loss_core(ssdk_ctx* ctx, const HeadGeom& G, const float* reg_targe
         occ_cache[variant] = occ > 0 ? occ : 1;
     }
     int per_sm = occ_cache[variant];
-    if (const char* e = getenv("SSDK_HEAD_CTAS")) per_sm = atoi(e);             // tuning knob (CTAs per SM)
+    if (ctx->tune_head_ctas) per_sm = ctx->tune_head_ctas;                       // SSDK_HEAD_CTAS (validated at context creation)
     if (per_sm < 1) per_sm = 1;
     if (per_sm > 8) per_sm = 8;
     long long grid_flat = (long long)ctx->num_sms * per_sm;
@@ -553,53 +525,10 @@ HeadGeom ssdk_flat_geom(const float* logits, const float* codes, int64_t A, int 
     return g;
 }
 
-int ssdk_match_impl(ssdk_ctx* ctx, const float* anchors, int64_t A, const float* gt_boxes, const int32_t* gt_labels,
-                    const int32_t* num_boxes, int B, int Gmax, double pos_thr, double neg_thr, int force,
-                    float* out_reg, int32_t* out_cls, int32_t* out_matches, double* out_count = nullptr);
-
-// Forward loss of a batch with target assignment: the flat pass needs no targets, so the (ALU-bound) matcher runs on the
-// context's side stream WHILE the (HBM-bound) flat pass streams the logits; the rows kernel joins both.
-int ssdk_targets_and_loss_overlapped(ssdk_ctx* ctx, const HeadGeom& G, const float* anchors, const float* gt_boxes,
-                                     const int32_t* gt_labels, const int32_t* num_boxes, int B, int64_t A, int C, int Gmax,
-                                     double pos_thr, double neg_thr, double gamma, double alpha, double* out_sums, float* out_reg,
-                                     int32_t* out_cls, int32_t* out_matches) {
-    const size_t NA = (size_t)B * (size_t)A;
-    if (!out_reg) { SSDK_TRY(ssdk_ensure(ctx, &ctx->ws_reg, NA * 16 + 16)); out_reg = (float*)ctx->ws_reg.p; }
-    if (!out_cls) { SSDK_TRY(ssdk_ensure(ctx, &ctx->ws_cls, NA * 4 + 16)); out_cls = (int32_t*)ctx->ws_cls.p; }
-    if (!out_matches) { SSDK_TRY(ssdk_ensure(ctx, &ctx->ws_matches, NA * 4 + 16)); out_matches = (int32_t*)ctx->ws_matches.p; }
-    SSDK_REQUIRE(out_sums != nullptr, SSDK_ERR_ARG, "targets_and_loss: out_sums is NULL");
-    if (NA == 0) {
-        SSDK_CHECK_CUDA(cudaMemsetAsync(out_sums, 0, 3 * sizeof(double), ctx->stream));
-        return SSDK_OK;
-    }
-    const char* ov = getenv("SSDK_OVERLAP_MATCH");                  // "0" / SSDK_OPT_OVERLAP_MATCHER = 0: matcher on the caller's stream
-    if ((ov && ov[0] == '0') || !ctx->overlap_matcher) {
-        SSDK_TRY(ssdk_match_impl(ctx, anchors, A, gt_boxes, gt_labels, num_boxes, B, Gmax, pos_thr, neg_thr, 1, out_reg, out_cls,
-                                 out_matches));
-        return ssdk_head_loss_core(ctx, G, out_reg, out_cls, out_matches, B, A, C, gamma, alpha, nullptr, nullptr, out_sums, nullptr,
-                                   false, 3);
-    }
-    cudaStream_t main_stream = ctx->stream, side = ctx->copy_stream;
-    // fork: everything already queued on the main stream (e.g. the producer of the logits / ground truth) precedes the matcher
-    SSDK_CHECK_CUDA(cudaEventRecord(ctx->ev[0], main_stream));
-    SSDK_CHECK_CUDA(cudaStreamWaitEvent(side, ctx->ev[0], 0));
-    ctx->stream = side;
-    int st = ssdk_match_impl(ctx, anchors, A, gt_boxes, gt_labels, num_boxes, B, Gmax, pos_thr, neg_thr, 1, out_reg, out_cls,
-                             out_matches);                                                    // ssd.py:84
-    ctx->stream = main_stream;
-    if (st == SSDK_OK) {
-        st = cudaEventRecord(ctx->ev[1], side) == cudaSuccess ? SSDK_OK : SSDK_ERR_CUDA;
-        if (st != SSDK_OK) ssdk_set_error("cudaEventRecord failed on the side stream");
-    }
-    if (st == SSDK_OK)
-        st = ssdk_head_loss_core(ctx, G, out_reg, out_cls, out_matches, B, A, C, gamma, alpha, nullptr, nullptr, out_sums, nullptr,
-                                 false, 1);                                                   // flat pass, concurrently
-    // join (also on the error paths, so that a stream capture in progress is never left forked)
-    cudaStreamWaitEvent(main_stream, ctx->ev[1], 0);
-    SSDK_TRY(st);
-    return ssdk_head_loss_core(ctx, G, out_reg, out_cls, out_matches, B, A, C, gamma, alpha, nullptr, nullptr, out_sums, nullptr,
-                               false, 2);                                                     // ssd.py:89-133
-}
+int ssdk_train_step_impl(ssdk_ctx* ctx, const HeadGeom& G, const float* anchors, const float* gt_boxes, const int32_t* gt_labels,
+                         const int32_t* num_boxes, int B, int64_t A, int C, int Gmax, double pos_thr, double neg_thr, double gamma,
+                         double alpha, int flags, double* out_sums, float* out_losses, float* out_reg, int32_t* out_cls,
+                         int32_t* out_matches);
 
 extern "C" {
 
@@ -610,8 +539,19 @@ int ssdk_head_ssd_targets_and_loss(ssdk_ctx* ctx, const ssdk_head* head, const f
     SSDK_TRY(ssdk_ctx_enter(ctx));
     HeadGeom G;
     SSDK_TRY(ssdk_head_geom(head, B, A, C, true, true, &G));
-    return ssdk_targets_and_loss_overlapped(ctx, G, anchors, gt_boxes, gt_labels, num_boxes, B, A, C, Gmax, positives_threshold,
-                                            negatives_threshold, gamma, alpha, out_sums, out_reg, out_cls, out_matches);
+    return ssdk_train_step_impl(ctx, G, anchors, gt_boxes, gt_labels, num_boxes, B, A, C, Gmax, positives_threshold, negatives_threshold,
+                                gamma, alpha, 0, out_sums, nullptr, out_reg, out_cls, out_matches);
+}
+
+int ssdk_head_ssd_loss_step(ssdk_ctx* ctx, const ssdk_head* head, const float* anchors, const float* gt_boxes,
+                            const int32_t* gt_labels, const int32_t* num_boxes, int B, int64_t A, int C, int Gmax,
+                            double positives_threshold, double negatives_threshold, double gamma, double alpha, int flags,
+                            double* out_sums, float* out_losses, float* out_reg, int32_t* out_cls, int32_t* out_matches) {
+    SSDK_TRY(ssdk_ctx_enter(ctx));
+    HeadGeom G;
+    SSDK_TRY(ssdk_head_geom(head, B, A, C, true, true, &G));
+    return ssdk_train_step_impl(ctx, G, anchors, gt_boxes, gt_labels, num_boxes, B, A, C, Gmax, positives_threshold, negatives_threshold,
+                                gamma, alpha, flags, out_sums, out_losses, out_reg, out_cls, out_matches);
 }
 
 int ssdk_head_ssd_loss(ssdk_ctx* ctx, const ssdk_head* head, const float* reg_targets, const int32_t* cls_targets,

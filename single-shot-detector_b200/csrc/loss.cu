@@ -304,7 +304,7 @@ int ssdk_ssd_loss(ssdk_ctx* ctx, const float* logits, const float* codes, const 
     // tile = 8 consumer warps x rpw rows; rpw is a multiple of 4 (so rpw*C*4 and rpw*4 bytes are multiples of 16)
     // and at most 32 (one lane per row); about 24 KB per stage
     int rpw = (int)(24576 / (32 * (long long)C)) / 4 * 4;
-    if (const char* e = getenv("SSDK_LOSS_RPW")) rpw = atoi(e);          // tuning knob (rows per warp, multiple of 4)
+    if (ctx->tune_loss_rpw) rpw = ctx->tune_loss_rpw;                    // SSDK_LOSS_RPW (a multiple of 4 in [4,32], validated at context creation)
     if (rpw < 4) rpw = 4;
     if (rpw > 32) rpw = 32;
     const int rows = rpw * LOSS_CONSUMER_WARPS;
@@ -317,16 +317,18 @@ int ssdk_ssd_loss(ssdk_ctx* ctx, const float* logits, const float* codes, const 
                  "ssdk_ssd_loss: num_classes %d too large for the fused kernel (limit about 780); use ssdk_focal_loss", C);
     if (L.stage_bytes < 12 * 1024) L.stages = 4;
     else if (L.stage_bytes < 20 * 1024) L.stages = 3;
-    if (const char* e = getenv("SSDK_LOSS_STAGES")) L.stages = (unsigned)atoi(e);   // tuning knob (2..4)
+    if (ctx->tune_loss_stages) L.stages = (unsigned)ctx->tune_loss_stages;         // SSDK_LOSS_STAGES (2..4)
     if (L.stages < 2) L.stages = 2;
     if (L.stages > LOSS_MAX_STAGES) L.stages = LOSS_MAX_STAGES;
+    while (L.stages > 2 && 128 + (size_t)L.stages * L.stage_bytes > 223 * 1024) --L.stages;   // whatever the knob says, the ring must fit
     const size_t smem = 128 + (size_t)L.stages * L.stage_bytes;
 
     const long long ntiles = (NA + rows - 1) / rows;
     int per_sm = (int)((227 * 1024) / (smem + 1024 + 2048));   // + reserved + static shared memory
     if (per_sm < 1) per_sm = 1;
     if (per_sm > 5) per_sm = 5;
-    if (const char* e = getenv("SSDK_LOSS_CTAS")) per_sm = atoi(e);             // tuning knob (CTAs per SM)
+    if (ctx->tune_loss_ctas) per_sm = ctx->tune_loss_ctas;                       // SSDK_LOSS_CTAS (1..8: the partials buffer holds num_sms * 8 CTAs)
+    while (per_sm > 1 && per_sm * (smem + 3072) > 227 * 1024) --per_sm;          // resident CTAs the shared memory allows
     long long grid = (long long)ctx->num_sms * per_sm;
     if (grid > ntiles) grid = ntiles;
 

@@ -8,10 +8,16 @@ int ssdk_match_impl(ssdk_ctx* ctx, const float* anchors, int64_t A, const float*
 
 struct HeadGeom;
 HeadGeom ssdk_flat_geom(const float* logits, const float* codes, int64_t A, int C);
-int ssdk_targets_and_loss_overlapped(ssdk_ctx* ctx, const HeadGeom& G, const float* anchors, const float* gt_boxes,
-                                     const int32_t* gt_labels, const int32_t* num_boxes, int B, int64_t A, int C, int Gmax,
-                                     double pos_thr, double neg_thr, double gamma, double alpha, double* out_sums, float* out_reg,
-                                     int32_t* out_cls, int32_t* out_matches);
+int ssdk_train_step_impl(ssdk_ctx* ctx, const HeadGeom& G, const float* anchors, const float* gt_boxes, const int32_t* gt_labels,
+                         const int32_t* num_boxes, int B, int64_t A, int C, int Gmax, double pos_thr, double neg_thr, double gamma,
+                         double alpha, int flags, double* out_sums, float* out_losses, float* out_reg, int32_t* out_cls,
+                         int32_t* out_matches);
+
+// the anchor-major tensors qualify for the flat pass (one channels_last "level", 16-byte aligned, sizes within the geometry's ints)
+static bool flat_path_ok(const float* logits, const float* codes, int64_t A, int C) {
+    return C > 0 && A < (1ll << 31) && logits && codes && (((uintptr_t)logits | (uintptr_t)codes) & 15) == 0 &&
+           (long long)A * (C > 4 ? C : 4) < (1ll << 31);
+}
 
 template <typename T>
 static int stage_h2d(ssdk_ctx* ctx, int slot, const T* host, size_t count, T** dev) {
@@ -32,13 +38,12 @@ int ssdk_ssd_targets_and_loss(ssdk_ctx* ctx, const float* anchors, const float* 
                               float* out_loc_losses) {
     SSDK_TRY(ssdk_ctx_enter(ctx));
     SSDK_REQUIRE(B >= 0 && A >= 0, SSDK_ERR_ARG, "ssdk_ssd_targets_and_loss: bad sizes");
-    if (!out_cls_losses && !out_loc_losses && C > 0 && A < (1ll << 31) && logits && codes && (((uintptr_t)logits | (uintptr_t)codes) & 15) == 0 &&
-        (long long)A * (C > 4 ? C : 4) < (1ll << 31)) {
-        // no per-anchor outputs wanted: flat pass + matched-anchor corrections (csrc/head.cu), with the matcher running on the
-        // side stream behind the flat pass.  The anchor-major tensors are a one-level channels_last head.
+    if (!out_cls_losses && !out_loc_losses && flat_path_ok(logits, codes, A, C)) {
+        // no per-anchor outputs wanted: the fused training step (csrc/train_step.cu) -- matching, the flat pass over the logits and
+        // the matched-anchor corrections in one launch.  The anchor-major tensors are just a one-level channels_last head.
         const HeadGeom G = ssdk_flat_geom(logits, codes, A, C);
-        return ssdk_targets_and_loss_overlapped(ctx, G, anchors, gt_boxes, gt_labels, num_boxes, B, A, C, Gmax, pos_thr, neg_thr,
-                                                gamma, alpha, out_sums, out_reg, out_cls, out_matches);
+        return ssdk_train_step_impl(ctx, G, anchors, gt_boxes, gt_labels, num_boxes, B, A, C, Gmax, pos_thr, neg_thr, gamma, alpha, 0,
+                                    out_sums, nullptr, out_reg, out_cls, out_matches);
     }
     const size_t NA = (size_t)B * (size_t)A;
     if (!out_reg) { SSDK_TRY(ssdk_ensure(ctx, &ctx->ws_reg, NA * 16 + 16)); out_reg = (float*)ctx->ws_reg.p; }
@@ -48,6 +53,25 @@ int ssdk_ssd_targets_and_loss(ssdk_ctx* ctx, const float* anchors, const float* 
                              out_matches));                                                   // ssd.py:84
     return ssdk_ssd_loss(ctx, logits, codes, out_reg, out_cls, out_matches, B, A, C, gamma, alpha, out_sums, out_cls_losses,
                          out_loc_losses);                                                     // ssd.py:89-133
+}
+
+int ssdk_ssd_loss_step(ssdk_ctx* ctx, const float* anchors, const float* logits, const float* codes, const float* gt_boxes,
+                       const int32_t* gt_labels, const int32_t* num_boxes, int B, int64_t A, int C, int Gmax, double pos_thr,
+                       double neg_thr, double gamma, double alpha, int flags, double* out_sums, float* out_losses, float* out_reg,
+                       int32_t* out_cls, int32_t* out_matches) {
+    SSDK_TRY(ssdk_ctx_enter(ctx));
+    SSDK_REQUIRE(B >= 0 && A >= 0 && C > 0, SSDK_ERR_ARG, "ssdk_ssd_loss_step: bad sizes");
+    SSDK_REQUIRE(out_sums && out_losses, SSDK_ERR_ARG, "ssdk_ssd_loss_step: out_sums / out_losses are required");
+    if (flat_path_ok(logits, codes, A, C)) {
+        const HeadGeom G = ssdk_flat_geom(logits, codes, A, C);
+        return ssdk_train_step_impl(ctx, G, anchors, gt_boxes, gt_labels, num_boxes, B, A, C, Gmax, pos_thr, neg_thr, gamma, alpha, flags,
+                                    out_sums, out_losses, out_reg, out_cls, out_matches);
+    }
+    // unaligned or oversized tensors: the row-tiled kernel, then the exchange / finalisation as separate launches
+    SSDK_TRY(ssdk_ssd_targets_and_loss(ctx, anchors, logits, codes, gt_boxes, gt_labels, num_boxes, B, A, C, Gmax, pos_thr, neg_thr, gamma,
+                                       alpha, out_sums, out_reg, out_cls, out_matches, nullptr, nullptr));
+    if (flags & SSDK_STEP_ALL_REDUCE) return ssdk_comm_loss_finalize(ctx, out_sums, out_losses);
+    return ssdk_loss_finalize(ctx, out_sums, out_losses);
 }
 
 int ssdk_ssd_targets_and_loss_host(ssdk_ctx* ctx, const float* anchors, const float* logits, const float* codes,
@@ -68,9 +92,8 @@ int ssdk_ssd_targets_and_loss_host(ssdk_ctx* ctx, const float* anchors, const fl
     SSDK_TRY(stage_h2d(ctx, 4, gt_labels, (size_t)B * Gmax, &d_labels));
     SSDK_TRY(stage_h2d(ctx, 5, num_boxes, (size_t)(num_boxes ? B : 0), &d_num));
     SSDK_TRY(stage_h2d(ctx, 6, (const double*)nullptr, 4, &d_out));   // double[3] sums + float[2] losses
-    SSDK_TRY(ssdk_ssd_targets_and_loss(ctx, d_anchors, d_logits, d_codes, d_gt, d_labels, d_num, B, A, C, Gmax, pos_thr, neg_thr,
-                                       gamma, alpha, d_out, nullptr, nullptr, nullptr, nullptr, nullptr));
-    SSDK_TRY(ssdk_loss_finalize(ctx, d_out, (float*)(d_out + 3)));
+    SSDK_TRY(ssdk_ssd_loss_step(ctx, d_anchors, d_logits, d_codes, d_gt, d_labels, d_num, B, A, C, Gmax, pos_thr, neg_thr, gamma, alpha, 0,
+                                d_out, (float*)(d_out + 3), nullptr, nullptr, nullptr));
     double h[4];
     SSDK_CHECK_CUDA(cudaMemcpyAsync(h, d_out, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
     SSDK_CHECK_CUDA(cudaStreamSynchronize(ctx->stream));

@@ -1,13 +1,14 @@
 // Inference post-processing: score threshold -> per-(image, class) candidate lists -> sort -> greedy NMS -> pack.
 // Replaces detector/utils/nms.py:48-102 (batch_multiclass_non_max_suppression), :6-45
 // (multiclass_non_max_suppression), the sigmoid of detector/ssd.py:60 and TensorFlow 1.12's NonMaxSuppressionV3
-// (external C++ kernel called at nms.py:33; semantics restated in oracle/nms.py).
+// (external C++ kernel called at nms.py:33; semantics restated in oracle/nms.py and pinned to TensorFlow's own unit-test
+// vectors, tests/golden/tf_nms_vectors.py).
 //
-// Pipeline (all on the context's stream, no host synchronisation):
+// Pipeline (all on the context's stream, no host synchronisation, the same launches whatever the data):
 //   1. filter_kernel      streams the [B,A,C] scores (or logits) once with 128-bit no-allocate loads and appends a
 //                         packed 64-bit key per (anchor, class) with score > threshold to the candidate list of its
-//                         (image, class) SEGMENT (a fixed region of A keys -- a class cannot have more candidates than
-//                         anchors -- and one atomic counter per segment).  This is the HBM-bound kernel.
+//                         (image, class) SEGMENT: a BOUNDED region of SEG_CAP keys and one atomic counter per segment.
+//                         This is the HBM-bound kernel.
 //                         key = class | ~order(score) | anchor  ->  ascending u64 order == score descending, anchor
 //                         index ascending inside a segment.
 //                         The reference's `is_confident` anchor pre-filter (nms.py:71-74, '>=') only removes
@@ -16,13 +17,25 @@
 //   2. nms_small_kernel   one WARP per segment with at most 32 candidates (the vast majority): the keys are sorted with a
 //                         shuffle bitonic network, decoded (box_utils.py:114-142) and clipped (nms.py:77), a 32x32
 //                         suppression bit matrix is built and walked greedily.  Larger segments are queued.
-//   3. nms_kernel         one CTA per queued segment: bitonic sort of the segment's keys (shared memory up to 4096 keys,
-//                         in place in global memory beyond), then candidates are taken 64 at a time in sorted order (eight
-//                         threads per candidate), tested against the boxes kept so far (shared memory) and against the
-//                         chunk's earlier candidates (64x64 bit matrix); the greedy order is resolved with ballots; stops at K.
-//   4. pack_kernel        class-major concatenation, zero padding to C*K and num_boxes (nms.py:83-93).
+//   3. nms_kernel         one CTA per queued segment that fits its region: bitonic sort of the keys in shared memory, then
+//                         candidates are taken 64 at a time in sorted order (eight threads per candidate), tested against the
+//                         boxes kept so far (shared memory) and against the chunk's earlier candidates (64x64 bit matrix);
+//                         the greedy order is resolved with ballots; stops at K.
+//   4. nms_rounds_kernel  segments with MORE candidates than a region holds (dense scores) -- the region's content is then
+//                         an arbitrary subset and is discarded.  One persistent grid works in rounds separated by grid-wide
+//                         barriers: a streaming pass histograms the not yet processed keys of every such segment over its
+//                         current key range, a planning step picks the best-scored prefix of bins that fits a region
+//                         (or narrows the range when a single bin is too big: a radix select over streaming passes), a
+//                         second streaming pass collects exactly those keys, and the segment's greedy NMS CONTINUES over
+//                         them with the boxes kept so far; repeat until K boxes are kept or no candidate is left.  Greedy
+//                         NMS truncated at K normally ends inside the first ~1000 keys, i.e. after one round; the rounds
+//                         make the result exact for ANY input with bounded memory.  Exits at once when no segment
+//                         overflowed (the normal, sparse case).
+//   5. pack_kernel        class-major concatenation, zero padding to C*K and num_boxes (nms.py:83-93).
 // There is no separate sort pass and nothing of the size of a whole image is ever sorted: the filter buckets by class,
-// each segment is sorted by the warp / CTA that runs its NMS.
+// each segment is sorted by the warp / CTA that runs its NMS.  Workspace: 32 KB per segment (0.08 of the logits at 90 classes
+// and 107k anchors), independent of the number of anchors.
+#include <math.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -30,25 +43,31 @@
 
 #define FILTER_THREADS 256
 #define FILTER_UNROLL 4
-#define NMS_SORT_SMEM_KEYS 4096       // heavy segments up to this many keys are sorted in shared memory (32 KB)
+#define SEG_CAP 4096                 // keys per (image, class) region == keys a CTA sorts in shared memory (32 KB)
 #define NMS_THREADS 512
 #define NMS_CH 64                    // candidates per chunk
 #define NMS_TPC (NMS_THREADS / NMS_CH)  // threads per candidate (a power of two <= 32)
+#define ROUND_NB 64                  // histogram bins per round
+#define ROUND_WANT 1024              // a round collects at least this many keys (if that many are left) and at most SEG_CAP
+#define ROUND_SMEM_MAX_C 320         // classes up to which the rounds keep their per-class tables / histograms in shared memory
 
 struct KeyFormat {
     int abits;       // bits for the anchor index
     int cshift;      // 32 + abits
 };
 
-__device__ __forceinline__ unsigned order_desc(float s) {
-    unsigned u = __float_as_uint(s);
+__host__ __device__ __forceinline__ unsigned order_desc_bits(unsigned u) {
     u = (u & 0x80000000u) ? ~u : (u | 0x80000000u);   // ascending total order of floats
     return ~u;                                        // descending
 }
-__device__ __forceinline__ float key_score(unsigned long long key, KeyFormat f) {
-    unsigned u = ~(unsigned)((key >> f.abits) & 0xFFFFFFFFull);
+__device__ __forceinline__ unsigned order_desc(float s) { return order_desc_bits(__float_as_uint(s)); }
+__device__ __forceinline__ float score_of_order(unsigned o) {
+    unsigned u = ~o;
     u = (u & 0x80000000u) ? (u & 0x7FFFFFFFu) : ~u;
     return __uint_as_float(u);
+}
+__device__ __forceinline__ float key_score(unsigned long long key, KeyFormat f) {
+    return score_of_order((unsigned)((key >> f.abits) & 0xFFFFFFFFull));
 }
 __device__ __forceinline__ int key_anchor(unsigned long long key, KeyFormat f) {
     return (int)(key & ((1ull << f.abits) - 1ull));
@@ -73,9 +92,13 @@ __device__ __forceinline__ bool is_candidate(float v, float thr, float x_lo, flo
 
 // A candidate takes the next slot of its (image, class) segment.  The lanes that arrive here together and target the same
 // segment (the normal case when a channels_first plane is scanned: 128 consecutive floats share image and class) share one
-// atomic; otherwise one atomic per candidate -- candidates are rare unless the scores are dense.
-__device__ __forceinline__ void append_key(unsigned long long* __restrict__ cand, long long capc, int* __restrict__ seg_count,
-                                           long long seg, unsigned long long key) {
+// atomic; otherwise one atomic per candidate -- candidates are rare unless the scores are dense.  The counter keeps counting
+// past the region's capacity (that is how an overflow is seen), but once it is PAST the capacity nothing more is added:
+// nms_rounds_kernel re-derives such a segment from the scores, and with dense scores these atomics would otherwise all hit
+// the same few counters (13.5 ms per 8 images at the stress configuration, measured in round 1).
+__device__ __forceinline__ void append_key(unsigned long long* __restrict__ cand, int* __restrict__ seg_count, long long seg,
+                                           unsigned long long key) {
+    if (__ldcg(seg_count + seg) > SEG_CAP) return;
     const unsigned m = __activemask();
     const int lane = threadIdx.x & 31;
     const int leader = __ffs(m) - 1;
@@ -88,7 +111,7 @@ __device__ __forceinline__ void append_key(unsigned long long* __restrict__ cand
     } else {
         pos = atomicAdd(seg_count + seg, 1);
     }
-    cand[(size_t)seg * capc + pos] = key;
+    if (pos < SEG_CAP) cand[(size_t)seg * SEG_CAP + pos] = key;
 }
 
 // The streaming scan shared by both layouts: `count` floats at `base` are read once with 128-bit no-allocate loads;
@@ -147,98 +170,14 @@ __device__ __forceinline__ void scan_candidates(const float* __restrict__ base, 
 template <bool IS_LOGITS>
 __global__ void __launch_bounds__(FILTER_THREADS) filter_kernel(
     const float* __restrict__ scores, long long per_image /*A*C*/, int C, float thr, float x_lo, KeyFormat fmt,
-    unsigned long long* __restrict__ cand, long long capc /*keys per segment = A*/, int* __restrict__ seg_count /*[B*C]*/) {
+    unsigned long long* __restrict__ cand, int* __restrict__ seg_count /*[B*C]*/) {
     const int b = blockIdx.y;
     const long long seg0 = (long long)b * C;                            // first segment of this image
     auto emit = [&](long long e, float s) {
         const int a = (int)(e / C), c = (int)(e - (long long)a * C);
-        append_key(cand, capc, seg_count, seg0 + c, make_key(c, s, a, fmt));
+        append_key(cand, seg_count, seg0 + c, make_key(c, s, a, fmt));
     };
     scan_candidates<IS_LOGITS>(scores + (size_t)b * per_image, per_image, thr, x_lo, emit);
-}
-
-// Dense scores (a large fraction of all (anchor, class) pairs above the threshold; BASELINE.json's stress config): one
-// global atomic per candidate would mean tens of millions of atomics on B*C counters.  Here a CTA works on tiles of 4096
-// consecutive elements (every class occurs 4096/C times in a tile): candidates take a rank from a shared-memory histogram,
-// one global atomic per class and tile reserves the slots, then the keys are written.  Chosen by the host when the previous
-// call on this context met segments with more than NMS_SORT_SMEM_KEYS candidates (a hint: both kernels are correct for any
-// input).  grid (gx, B), dynamic shared memory 2*C ints.
-#define FD_U 4
-template <bool IS_LOGITS>
-__global__ void __launch_bounds__(FILTER_THREADS) filter_dense_kernel(
-    const float* __restrict__ scores, long long per_image /*A*C*/, int C, float thr, float x_lo, KeyFormat fmt,
-    unsigned long long* __restrict__ cand, long long capc, int* __restrict__ seg_count) {
-    extern __shared__ int s_dense[];
-    int* s_hist = s_dense;
-    int* s_base = s_dense + C;
-    const int b = blockIdx.y, tid = threadIdx.x;
-    const float* base = scores + (size_t)b * per_image;
-    const long long seg0 = (long long)b * C;
-    for (int c = tid; c < C; c += FILTER_THREADS) s_hist[c] = 0;
-    __syncthreads();
-    const unsigned mis = (unsigned)(((uintptr_t)base >> 2) & 3);
-    long long head = mis ? (4 - mis) : 0;
-    if (head > per_image) head = per_image;
-    const long long nbody4 = (per_image - head) >> 2;
-    const long long tail0 = head + (nbody4 << 2);
-    const float4* body = (const float4*)(base + head);
-    if (blockIdx.x == 0 && tid < 32) {                                  // the (< 8) unaligned head / tail elements
-        long long e = -1;
-        if (tid < head) e = tid;
-        else if (tid - head < per_image - tail0) e = tail0 + (tid - head);
-        float s;
-        if (e >= 0 && is_candidate<IS_LOGITS>(base[e], thr, x_lo, &s)) {
-            const int a = (int)(e / C), c = (int)(e - (long long)a * C);
-            cand[(size_t)(seg0 + c) * capc + atomicAdd(seg_count + seg0 + c, 1)] = make_key(c, s, a, fmt);
-        }
-    }
-    const long long ntiles = (nbody4 + FILTER_THREADS * FD_U - 1) / (FILTER_THREADS * FD_U);
-    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        float sc[4 * FD_U];
-        unsigned short rk[4 * FD_U];
-        unsigned hit = 0u;
-        // phase 1: candidates take their rank inside (tile, class)
-#pragma unroll
-        for (int u = 0; u < FD_U; ++u) {
-            const long long i4 = tile * (FILTER_THREADS * FD_U) + u * FILTER_THREADS + tid;
-            const float4 v = i4 < nbody4 ? ld_stream_f4(body + i4) : make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
-            const float vals[4] = {v.x, v.y, v.z, v.w};
-            const unsigned e0 = (unsigned)(head + (i4 << 2));
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                if (is_candidate<IS_LOGITS>(vals[j], thr, x_lo, &sc[u * 4 + j])) {
-                    const unsigned e = e0 + j, a = e / (unsigned)C, c = e - a * (unsigned)C;
-                    rk[u * 4 + j] = (unsigned short)atomicAdd(&s_hist[c], 1);
-                    hit |= 1u << (u * 4 + j);
-                }
-            }
-        }
-        __syncthreads();
-        // phase 2: one global atomic per class reserves the tile's slots
-        for (int c = tid; c < C; c += FILTER_THREADS) {
-            const int h = s_hist[c];
-            if (h) {
-                s_base[c] = atomicAdd(seg_count + seg0 + c, h);
-                s_hist[c] = 0;
-            }
-        }
-        __syncthreads();
-        // phase 3: write the keys
-#pragma unroll
-        for (int u = 0; u < FD_U; ++u) {
-            const long long i4 = tile * (FILTER_THREADS * FD_U) + u * FILTER_THREADS + tid;
-            const unsigned e0 = (unsigned)(head + (i4 << 2));
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                if ((hit >> (u * 4 + j)) & 1u) {
-                    const unsigned e = e0 + j, a = e / (unsigned)C, c = e - a * (unsigned)C;
-                    cand[(size_t)(seg0 + c) * capc + s_base[c] + rk[u * 4 + j]] = make_key((int)c, sc[u * 4 + j], (int)a, fmt);
-                }
-            }
-        }
-        // no barrier here: the next tile's phase 2 (the only writer of s_base) comes after its phase-1 barrier, which every
-        // thread reaches only after this phase 3
-    }
 }
 
 // Head layout (head-layout fusion, see head.cu): grid (gx, num_levels); level blockIdx.y's class tensor [B, n*C, h, w] (or
@@ -247,11 +186,14 @@ __global__ void __launch_bounds__(FILTER_THREADS) filter_dense_kernel(
 struct LevelGeom {        // one level of a HeadGeom, by value
     int hw, per_loc, C, channels_first, anchor_off;
 };
-__device__ __forceinline__ void head_decompose(const LevelGeom g, long long e, int& b, int& a, int& c) {
+__device__ __forceinline__ LevelGeom level_geom(const HeadGeom& G, int l) {
+    LevelGeom g;
+    g.hw = G.hw[l]; g.per_loc = G.per_loc; g.C = G.C; g.channels_first = G.channels_first; g.anchor_off = G.anchor_off[l];
+    return g;
+}
+// element r of ONE image's block of a level -> (anchor, class)
+__device__ __forceinline__ void level_decompose(const LevelGeom g, int r, int& a, int& c) {
     const int hw = g.hw, n = g.per_loc, C = g.C;
-    const long long per_image = (long long)n * C * hw;
-    b = (int)(e / per_image);
-    const int r = (int)(e - (long long)b * per_image);
     int loc, q;
     if (g.channels_first) { q = r / hw; loc = r - q * hw; }
     else { loc = r / (n * C); q = r - loc * (n * C); }
@@ -259,19 +201,23 @@ __device__ __forceinline__ void head_decompose(const LevelGeom g, long long e, i
     c = q - k * C;
     a = g.anchor_off + loc * n + k;
 }
+__device__ __forceinline__ void head_decompose(const LevelGeom g, long long e, int& b, int& a, int& c) {
+    const long long per_image = (long long)g.per_loc * g.C * g.hw;
+    b = (int)(e / per_image);
+    level_decompose(g, (int)(e - (long long)b * per_image), a, c);
+}
 
 template <bool IS_LOGITS>
 __global__ void __launch_bounds__(FILTER_THREADS) head_filter_kernel(const HeadGeom G, int B, float thr, float x_lo, KeyFormat fmt,
-                                                                    unsigned long long* __restrict__ cand, long long capc,
+                                                                    unsigned long long* __restrict__ cand,
                                                                     int* __restrict__ seg_count) {
     const int l = blockIdx.y;
-    LevelGeom g;
-    g.hw = G.hw[l]; g.per_loc = G.per_loc; g.C = G.C; g.channels_first = G.channels_first; g.anchor_off = G.anchor_off[l];
+    const LevelGeom g = level_geom(G, l);
     const long long count = (long long)B * g.per_loc * g.C * g.hw;
     auto emit = [&](long long e, float s) {
         int b, a, c;
         head_decompose(g, e, b, a, c);
-        append_key(cand, capc, seg_count, (long long)b * g.C + c, make_key(c, s, a, fmt));
+        append_key(cand, seg_count, (long long)b * g.C + c, make_key(c, s, a, fmt));
     };
     scan_candidates<IS_LOGITS>(G.cls[l], count, thr, x_lo, emit);
 }
@@ -293,129 +239,38 @@ __device__ __forceinline__ unsigned long long warp_sort_keys(unsigned long long 
     return key;
 }
 
-// CTA-wide bitonic sort of keys[0, n) (shared or global memory), ascending, for ANY n: the network is the all-ascending
-// formulation (first step of a merge compares i with its mirror image, the others i with i + j); positions >= n behave as
-// +infinity, never move, and their compare-exchanges are simply skipped.  Four independent pairs per thread are loaded
-// before any is written back, so that a sort in global memory (L2) has several loads in flight per thread.
-template <int SORT_ILP>
+// CTA-wide bitonic sort of keys[0, n) in shared memory, ascending, for ANY n: the network is the all-ascending formulation
+// (first step of a merge compares i with its mirror image, the others i with i + j); positions >= n behave as +infinity,
+// never move, and their compare-exchanges are simply skipped.
 __device__ __forceinline__ void sort_step(unsigned long long* keys, int n, int halfP, int tid, int nthreads, int lk, int j /*0: flip step*/) {
     const int k = 1 << lk, half = k >> 1;
-    for (int t0 = tid; t0 < halfP; t0 += nthreads * SORT_ILP) {
-        int ii[SORT_ILP], ll[SORT_ILP];
-        unsigned long long x[SORT_ILP], y[SORT_ILP];
-#pragma unroll
-        for (int u = 0; u < SORT_ILP; ++u) {
-            const int t = t0 + u * nthreads;
-            if (j == 0) {
-                const int blk = t >> (lk - 1), o = t & (half - 1);
-                ii[u] = (blk << lk) + o;
-                ll[u] = (blk << lk) + (k - 1 - o);
-            } else {
-                ii[u] = ((t & ~(j - 1)) << 1) | (t & (j - 1));
-                ll[u] = ii[u] | j;
-            }
-            if (t >= halfP || ll[u] >= n) ll[u] = -1;
-            if (ll[u] >= 0) { x[u] = keys[ii[u]]; y[u] = keys[ll[u]]; }
+    for (int t = tid; t < halfP; t += nthreads) {
+        int ii, ll;
+        if (j == 0) {
+            const int blk = t >> (lk - 1), o = t & (half - 1);
+            ii = (blk << lk) + o;
+            ll = (blk << lk) + (k - 1 - o);
+        } else {
+            ii = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+            ll = ii | j;
         }
-#pragma unroll
-        for (int u = 0; u < SORT_ILP; ++u)
-            if (ll[u] >= 0 && x[u] > y[u]) { keys[ii[u]] = y[u]; keys[ll[u]] = x[u]; }
+        if (ll < n) {
+            const unsigned long long x = keys[ii], y = keys[ll];
+            if (x > y) { keys[ii] = y; keys[ll] = x; }
+        }
     }
 }
-template <int SORT_ILP>
 __device__ __forceinline__ void cta_sort_keys(unsigned long long* keys, int n, int tid, int nthreads) {
     int P = 1, logP = 0;
     while (P < n) { P <<= 1; ++logP; }
     for (int lk = 1; lk <= logP; ++lk) {
-        sort_step<SORT_ILP>(keys, n, P >> 1, tid, nthreads, lk, 0);
+        sort_step(keys, n, P >> 1, tid, nthreads, lk, 0);
         __syncthreads();
         for (int j = 1 << (lk - 2 >= 0 ? lk - 2 : 0); lk >= 2 && j > 0; j >>= 1) {
-            sort_step<SORT_ILP>(keys, n, P >> 1, tid, nthreads, lk, j);
+            sort_step(keys, n, P >> 1, tid, nthreads, lk, j);
             __syncthreads();
         }
     }
-}
-
-// Best-first selection for a large segment: copies the smallest keys of keys[0, n) -- at least `want` of them (or all n),
-// at most `cap` -- into out[] (unsorted) and returns their number.  Radix select on the key bits below `top_bit` (the bits
-// above are the class, identical inside a segment), 8 bits per pass from the top; a pass is a scan of the whole segment
-// (L2 resident) with 8 loads in flight per thread.  Stops as soon as the bucket boundary gives a count in [want, cap].
-#define SEL_ILP 4
-__device__ __forceinline__ int select_best_keys(const unsigned long long* __restrict__ keys, int n, unsigned long long* out, int want, int cap,
-                                int top_bit, unsigned long long class_prefix, int tid, int nthreads, unsigned* s_hist /*[256]*/,
-                                unsigned long long* s_u64 /*[2]*/, int* s_int /*[4]*/) {
-    int hi = top_bit;                           // bits [0, hi) are still undecided inside the boundary bucket
-    unsigned long long prefix = class_prefix;   // decided high bits of the boundary bucket
-    int below = 0;                              // keys known to be smaller than every key of the boundary bucket
-    unsigned long long T = ~0ull;               // final threshold: select keys < T
-    while (true) {
-        const int bits = hi < 8 ? hi : 8, shift = hi - bits;
-        for (int i = tid; i < 256; i += nthreads) s_hist[i] = 0u;
-        __syncthreads();
-        for (int base = 0; base < n; base += nthreads * SEL_ILP) {      // uniform trip count: the lanes vote below
-            unsigned long long k[SEL_ILP];
-#pragma unroll
-            for (int u = 0; u < SEL_ILP; ++u) { const int i = base + tid + u * nthreads; k[u] = i < n ? keys[i] : 0ull; }
-#pragma unroll
-            for (int u = 0; u < SEL_ILP; ++u) {
-                const int i = base + tid + u * nthreads;
-                const bool in = i < n && (k[u] >> hi) == (prefix >> hi);
-                const unsigned digit = in ? ((unsigned)(k[u] >> shift) & ((1u << bits) - 1u)) : 0xFFFFFFFFu;
-                // lanes with the same digit share one shared-memory atomic (the leading score bits take few distinct values)
-                const unsigned same = __match_any_sync(0xffffffffu, digit);
-                if (in && (threadIdx.x & 31) == __ffs(same) - 1) atomicAdd(&s_hist[digit], (unsigned)__popc(same));
-            }
-        }
-        __syncthreads();
-        if (tid == 0) {
-            int lo = below, b = 0;
-            const int nb = 1 << bits;
-            for (; b < nb - 1; ++b) {
-                if (lo + (int)s_hist[b] >= want) break;
-                lo += (int)s_hist[b];
-            }
-            const int upto = lo + (int)s_hist[b];                  // keys < prefix | (b+1) << shift
-            if (upto <= cap || shift == 0) {                        // shift == 0: buckets hold single keys (keys are unique)
-                s_int[0] = 1;
-                s_u64[0] = (b == nb - 1 && shift + bits >= 64) ? ~0ull : (prefix | ((unsigned long long)(b + 1) << shift));
-                if (b == nb - 1) {                                          // whole boundary bucket: threshold = next prefix
-                    const unsigned long long next = ((prefix >> hi) + 1ull) << hi;
-                    s_u64[0] = next > prefix ? next : ~0ull;                     // (wrap-around: nothing lies above)
-                }
-            } else {
-                s_int[0] = 0;
-                s_int[1] = lo;
-                s_u64[0] = prefix | ((unsigned long long)b << shift);
-            }
-        }
-        __syncthreads();
-        const int done = s_int[0];
-        if (done) { T = s_u64[0]; break; }
-        below = s_int[1];
-        prefix = s_u64[0];
-        hi = shift;
-        __syncthreads();
-    }
-    // compaction (order does not matter: the caller sorts)
-    if (tid == 0) s_int[2] = 0;
-    __syncthreads();
-    for (int i0 = tid; i0 < n; i0 += nthreads * SEL_ILP) {
-        unsigned long long k[SEL_ILP];
-#pragma unroll
-        for (int u = 0; u < SEL_ILP; ++u) { const int i = i0 + u * nthreads; k[u] = i < n ? keys[i] : ~0ull; }
-#pragma unroll
-        for (int u = 0; u < SEL_ILP; ++u) {
-            const int i = i0 + u * nthreads;
-            if (i < n && k[u] < T) {
-                const int pos = atomicAdd(&s_int[2], 1);
-                if (pos < cap) out[pos] = k[u];
-            }
-        }
-    }
-    __syncthreads();
-    const int m = s_int[2];
-    __syncthreads();
-    return m < cap ? m : cap;
 }
 
 // ---------------------------------------------------------------------------------------------- 3. NMS
@@ -432,6 +287,13 @@ __device__ __forceinline__ float4 load_code(const CodeView& cv, int b, long long
 struct NmsBox {          // corners min/max-normalised as NonMaxSuppressionV3 does; area <= 0 never suppresses
     float ymin, xmin, ymax, xmax;
 };
+__device__ __forceinline__ NmsBox nms_box_of(const float4 raw, float& area) {
+    NmsBox box;
+    box.ymin = fminf(raw.x, raw.z); box.xmin = fminf(raw.y, raw.w);
+    box.ymax = fmaxf(raw.x, raw.z); box.xmax = fmaxf(raw.y, raw.w);
+    area = f_mul(f_sub(box.ymax, box.ymin), f_sub(box.xmax, box.xmin));
+    return box;
+}
 
 // IoU(a, b) > thr with the exact float32 semantics of  inter / (area_a + area_b - inter) > thr  (IEEE divide).
 // nms_fast decides without the division whenever |inter - thr*union| > 2^-18 * |thr| * union (both roundings
@@ -456,16 +318,21 @@ __device__ __forceinline__ bool nms_exact(const NmsBox a, float area_a, const Nm
     return f_div(inter, f_sub(f_add(area_a, area_b), inter)) > thr;
 }
 
+// header ints of the counter workspace (zeroed every call)
+enum { H_HEAVY = 0, H_PEND, H_BAR, H_ERR, H_NIMG_C, H_NHIST0, H_NHIST1, H_NIMG_H0, H_NIMG_H1, H_WORDS = 16 };
+
 // Segments with at most 32 candidates (the vast majority: background classes) are resolved by ONE WARP each, one
 // candidate per lane: decode, a 32x32 suppression bit matrix (one column per lane), a greedy walk with shuffles.
-// Larger segments are pushed to a queue for nms_kernel, which spends a whole CTA on each of them.
+// Larger segments are pushed to a queue: `heavy` (fits its region: nms_kernel spends a whole CTA on each) or `pending`
+// (overflowed its region: nms_rounds_kernel).
 #define NMS_SMALL_WARPS 8
 template <bool DECODED>
 __global__ void __launch_bounds__(NMS_SMALL_WARPS * 32) nms_small_kernel(
-    const unsigned long long* __restrict__ cand, long long capc, KeyFormat fmt, const int* __restrict__ seg_count,
+    const unsigned long long* __restrict__ cand, KeyFormat fmt, const int* __restrict__ seg_count,
     const CodeView codes, const float4* __restrict__ anchors, long long A,
     long long nseg, int C, int K, float iou_thr, float4* __restrict__ seg_box, float* __restrict__ seg_score,
-    int* __restrict__ seg_anchor, int* __restrict__ seg_kept, int* __restrict__ heavy_queue, int* __restrict__ heavy_count) {
+    int* __restrict__ seg_anchor, int* __restrict__ seg_kept, int* __restrict__ heavy_queue, int* __restrict__ pend_queue,
+    int* __restrict__ hdr) {
     __shared__ NmsBox s_tile[NMS_SMALL_WARPS][32];
     __shared__ float s_tile_area[NMS_SMALL_WARPS][32];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -476,10 +343,10 @@ __global__ void __launch_bounds__(NMS_SMALL_WARPS * 32) nms_small_kernel(
         if (lane == 0) seg_kept[seg] = 0;
         return;
     }
-    if (n > 32) {                                      // heavy_count[0] / [1]: the two queues (heavy | large), nseg entries each
+    if (n > 32) {
         if (lane == 0) {
-            const int large = n > NMS_SORT_SMEM_KEYS ? 1 : 0;
-            heavy_queue[(size_t)large * nseg + atomicAdd(heavy_count + large, 1)] = (int)seg;
+            if (n > SEG_CAP) pend_queue[atomicAdd(hdr + H_PEND, 1)] = (int)seg;
+            else heavy_queue[atomicAdd(hdr + H_HEAVY, 1)] = (int)seg;
         }
         return;
     }
@@ -492,15 +359,13 @@ __global__ void __launch_bounds__(NMS_SMALL_WARPS * 32) nms_small_kernel(
     float area = 0.f, score = 0.f;
     int a = 0;
     // the segment's keys arrive in arbitrary order: sort them (score descending, anchor ascending)
-    const unsigned long long key = warp_sort_keys(alive ? cand[(size_t)seg * capc + lane] : ~0ull, lane);
+    const unsigned long long key = warp_sort_keys(alive ? cand[(size_t)seg * SEG_CAP + lane] : ~0ull, lane);
     if (alive) {
         a = key_anchor(key, fmt);
         score = key_score(key, fmt);
         raw = load_code(codes, b, A, a);
         if (!DECODED) raw = box_clip01(box_decode(raw, anchors[a]));                         // nms.py:76-77
-        box.ymin = fminf(raw.x, raw.z); box.xmin = fminf(raw.y, raw.w);
-        box.ymax = fmaxf(raw.x, raw.z); box.xmax = fmaxf(raw.y, raw.w);
-        area = f_mul(f_sub(box.ymax, box.ymin), f_sub(box.xmax, box.xmin));
+        box = nms_box_of(raw, area);
     }
     s_tile[warp][lane] = box;
     s_tile_area[warp][lane] = area;
@@ -533,191 +398,519 @@ __global__ void __launch_bounds__(NMS_SMALL_WARPS * 32) nms_small_kernel(
     if (lane == 0) seg_kept[seg] = __popc(keep);
 }
 
-// One CTA per queued (image, class) segment, NMS_CH candidates per chunk in sorted order, NMS_TPC threads per candidate:
-//   (a) every candidate is decoded + clipped and tested against the boxes kept from earlier chunks (shared memory);
-//       the threads of a candidate split the kept list and OR their verdicts with shuffles;
+// Greedy NMS of ONE segment over `navail` keys sorted ascending (score descending), by a whole CTA, NMS_CH candidates per
+// chunk in sorted order, NMS_TPC threads per candidate; CONTINUES a list of `kept` boxes already in sh.kept (0 for a fresh
+// segment):
+//   (a) every candidate is decoded + clipped and tested against the boxes kept so far (shared memory); the threads of a
+//       candidate split the kept list and OR their verdicts with shuffles;
 //   (b) column c of the chunk's suppression bit matrix (bit t set <=> t < c, t survived (a), IoU(t, c) > threshold) is
 //       built the same way, the threads splitting t;
 //   (c) warp 0 resolves the greedy order WITHOUT walking it: a candidate is removed as soon as one of its suppressors is
 //       known to be kept, and kept as soon as all of them are known to be removed; every round decides at least the first
 //       undecided candidate, in practice a handful of rounds of ballots decide all 64;  the result is cut at K;
 //   (d) kept candidates append themselves (rank by popcount) to the kept list and to the segment's output.
-// LARGE = false: queued segments with 33..NMS_SORT_SMEM_KEYS candidates (sorted in shared memory); LARGE = true: the separate
-// queue of larger segments (dense scores), which need the select / in-place sort machinery and many more registers.
-template <bool DECODED, bool LARGE>
-__global__ void __launch_bounds__(NMS_THREADS) nms_kernel(
-    unsigned long long* __restrict__ cand, long long capc, KeyFormat fmt, const int* __restrict__ seg_count,
-    const CodeView codes, const float4* __restrict__ anchors, long long A,
-    long long nseg, int C, int K, float iou_thr, float4* __restrict__ seg_box, float* __restrict__ seg_score,
-    int* __restrict__ seg_anchor, int* __restrict__ seg_kept, const int* __restrict__ heavy_queue,
-    const int* __restrict__ heavy_count) {
-    extern __shared__ __align__(16) unsigned char nms_smem[];
-    __shared__ NmsBox s_tile[NMS_CH];
-    __shared__ float s_tile_area[NMS_CH];
-    __shared__ unsigned long long s_col[NMS_CH];
-    __shared__ unsigned s_alive32[2][2];               // [chunk parity][word]: survivors of (a), set with atomicOr
-    __shared__ unsigned long long s_keep;
-    __shared__ unsigned s_hist[256];                   // select_best_keys scratch
-    __shared__ unsigned long long s_sel64[2];
-    __shared__ int s_sel32[4];
+// Returns the new number of kept boxes (CTA-uniform).
+struct NmsShared {
+    NmsBox tile[NMS_CH];
+    float tile_area[NMS_CH];
+    unsigned long long col[NMS_CH];
+    unsigned alive32[2][2];                // [chunk parity][word]: survivors of (a), set with atomicOr
+    unsigned long long keep;
+};
+struct NmsSegArgs {
+    KeyFormat fmt;
+    CodeView codes;
+    const float4* anchors;
+    long long A;
+    int C, K;
+    float iou_thr;
+    float4* seg_box; float* seg_score; int* seg_anchor;
+};
+
+template <bool DECODED>
+__device__ __forceinline__ int nms_sorted_segment(const NmsSegArgs& N, NmsShared& sh, NmsBox* s_kept, float* s_kept_area,
+                                                  const unsigned long long* sorted, int navail, long long seg, int kept) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    unsigned long long* s_sort = (unsigned long long*)nms_smem;     // [NMS_SORT_SMEM_KEYS]
-    NmsBox* s_kept = (NmsBox*)(s_sort + NMS_SORT_SMEM_KEYS);        // [K]
-    float* s_kept_area = (float*)(s_kept + K);                      // [K]
-    const float band = fabsf(iou_thr) * 3.814697265625e-06f;
     const int c = tid / NMS_TPC, q = tid % NMS_TPC;    // candidate slot in the chunk, position among its threads
-    const int nheavy = *heavy_count;
+    const int b = (int)(seg / N.C), K = N.K;
+    const size_t obase = (size_t)seg * K;
+    const float iou_thr = N.iou_thr, band = fabsf(iou_thr) * 3.814697265625e-06f;
+    if (tid < 4) sh.alive32[tid >> 1][tid & 1] = 0u;
+    __syncthreads();
+    // the candidate of the NEXT chunk (key -> code -> anchor: dependent global loads) is fetched while the current
+    // chunk is processed
+    unsigned long long nkey = 0ull;
+    float4 ncode = make_float4(0.f, 0.f, 0.f, 0.f), nanc = make_float4(0.f, 0.f, 0.f, 0.f);
+    auto fetch = [&](int i) {
+        if (i < navail) {
+            nkey = sorted[i];
+            const int na = key_anchor(nkey, N.fmt);
+            ncode = load_code(N.codes, b, N.A, na);
+            if (!DECODED) nanc = N.anchors[na];
+        }
+    };
+    fetch(c);
+    int parity = 0;
+    for (int base = 0; base < navail && kept < K; base += NMS_CH, parity ^= 1) {
+        const int i = base + c;
+        bool alive = i < navail;
+        NmsBox box = {0.f, 0.f, 0.f, 0.f};
+        float4 raw = make_float4(0.f, 0.f, 0.f, 0.f);
+        float area = 0.f, score = 0.f;
+        int a = 0;
+        if (alive) {
+            a = key_anchor(nkey, N.fmt);
+            score = key_score(nkey, N.fmt);
+            if (DECODED) raw = ncode;
+            else raw = box_clip01(box_decode(ncode, nanc));                              // nms.py:76-77
+            box = nms_box_of(raw, area);
+        }
+        fetch(i + NMS_CH);
+        // (a) against the boxes kept so far
+        int hit = 0;
+        if (alive) {
+            for (int j = q; j < kept; j += NMS_TPC) {
+                bool y, am;
+                nms_fast(box, area, s_kept[j], s_kept_area[j], iou_thr, band, y, am);
+                if (am) y = nms_exact(box, area, s_kept[j], s_kept_area[j], iou_thr); // rare: within 2^-18 of the threshold
+                hit |= y ? 1 : 0;
+            }
+        }
+#pragma unroll
+        for (int o = 1; o < NMS_TPC; o <<= 1) hit |= __shfl_xor_sync(0xffffffffu, hit, o);
+        alive = alive && !hit;
+        if (q == 0) {
+            sh.tile[c] = box;
+            sh.tile_area[c] = area;
+            if (alive) atomicOr(&sh.alive32[parity][c >> 5], 1u << (c & 31));
+        }
+        if (tid < 2) sh.alive32[parity ^ 1][tid] = 0u;      // the buffer of the next chunk (last read two barriers ago)
+        __syncthreads();
+        const unsigned long long alive_mask = ((unsigned long long)sh.alive32[parity][1] << 32) | sh.alive32[parity][0];
+        // (b) column of the chunk's suppression matrix
+        unsigned long long col = 0ull;
+        if (alive && (alive_mask & (alive_mask - 1ull))) {               // at least two survivors in the chunk
+            for (int t = q; t < c; t += NMS_TPC) {
+                if ((alive_mask >> t) & 1ull) {
+                    bool y, am;
+                    nms_fast(box, area, sh.tile[t], sh.tile_area[t], iou_thr, band, y, am);
+                    if (am) y = nms_exact(box, area, sh.tile[t], sh.tile_area[t], iou_thr);
+                    if (y) col |= 1ull << t;
+                }
+            }
+        }
+#pragma unroll
+        for (int o = 1; o < NMS_TPC; o <<= 1) col |= __shfl_xor_sync(0xffffffffu, col, o);
+        if (q == 0) sh.col[c] = col;
+        __syncthreads();
+        // (c) greedy order by resolution rounds (warp 0: lane l owns candidates l and l + 32)
+        if (warp == 0) {
+            const unsigned long long col_lo = sh.col[lane], col_hi = sh.col[lane + 32];
+            unsigned long long keep = 0ull, gone = ~alive_mask, und = alive_mask;
+            while (und) {
+                int st_lo = 0, st_hi = 0;                                // 1 = kept, 2 = removed
+                if ((und >> lane) & 1ull) st_lo = (col_lo & keep) ? 2 : ((col_lo & ~gone) == 0ull ? 1 : 0);
+                if ((und >> (lane + 32)) & 1ull) st_hi = (col_hi & keep) ? 2 : ((col_hi & ~gone) == 0ull ? 1 : 0);
+                const unsigned long long k_new = ((unsigned long long)__ballot_sync(0xffffffffu, st_hi == 1) << 32) | __ballot_sync(0xffffffffu, st_lo == 1);
+                const unsigned long long g_new = ((unsigned long long)__ballot_sync(0xffffffffu, st_hi == 2) << 32) | __ballot_sync(0xffffffffu, st_lo == 2);
+                keep |= k_new;
+                gone |= g_new;
+                und &= ~(k_new | g_new);
+            }
+            int extra = __popcll(keep) - (K - kept);                      // at most K in total: drop the lowest-scored
+            while (extra > 0) { keep &= ~(1ull << (63 - __clzll((long long)keep))); --extra; }
+            if (lane == 0) sh.keep = keep;
+        }
+        __syncthreads();
+        const unsigned long long keep = sh.keep;
+        // (d) append the kept candidates in score order
+        if (q == 0 && ((keep >> c) & 1ull)) {
+            const int pos = kept + __popcll(keep & ((1ull << c) - 1ull));
+            s_kept[pos] = box;
+            s_kept_area[pos] = area;
+            N.seg_box[obase + pos] = raw;
+            N.seg_score[obase + pos] = score;
+            N.seg_anchor[obase + pos] = a;
+        }
+        kept += __popcll(keep);
+        __syncthreads();
+    }
+    return kept;
+}
+
+// One CTA per queued (image, class) segment with 33..SEG_CAP candidates: sort in shared memory, then nms_sorted_segment.
+template <bool DECODED>
+__global__ void __launch_bounds__(NMS_THREADS) nms_kernel(const unsigned long long* __restrict__ cand, const int* __restrict__ seg_count,
+                                                          const NmsSegArgs N, int* __restrict__ seg_kept,
+                                                          const int* __restrict__ heavy_queue, const int* __restrict__ hdr) {
+    extern __shared__ __align__(16) unsigned char nms_smem[];
+    __shared__ NmsShared sh;
+    const int tid = threadIdx.x;
+    unsigned long long* s_sort = (unsigned long long*)nms_smem;     // [SEG_CAP]
+    NmsBox* s_kept = (NmsBox*)(s_sort + SEG_CAP);                   // [K]
+    float* s_kept_area = (float*)(s_kept + N.K);                    // [K]
+    const int nheavy = hdr[H_HEAVY];
     for (int item = blockIdx.x; item < nheavy; item += gridDim.x) {
         const long long seg = heavy_queue[item];
-        const int n = seg_count[seg];
-        const int b = (int)(seg / C);
-        unsigned long long* keys = cand + (size_t)seg * capc;
-        const size_t obase = (size_t)seg * K;
-        int kept = 0;
-        // ---- sort the segment (score descending, anchor ascending).  Up to NMS_SORT_SMEM_KEYS keys: in shared memory.
-        //      Larger segments (dense scores): attempt 0 selects the best <= NMS_SORT_SMEM_KEYS keys with a radix select and
-        //      sorts only those -- greedy NMS truncated at K normally finishes inside them; if it does not (kept < K with
-        //      candidates left) attempt 1 sorts the whole segment in place and starts over.
-      for (int attempt = 0;; ++attempt) {
-        const unsigned long long* sorted = s_sort;
-        int navail = n;
+        const int n = min(seg_count[seg], SEG_CAP);
+        const unsigned long long* keys = cand + (size_t)seg * SEG_CAP;
         __syncthreads();
-        if (!LARGE) {
-            for (int i = tid; i < n; i += NMS_THREADS) s_sort[i] = keys[i];
-            __syncthreads();
-            cta_sort_keys<1>(s_sort, n, tid, NMS_THREADS);
-        } else if (attempt == 0) {
-            navail = select_best_keys(keys, n, s_sort, NMS_SORT_SMEM_KEYS / 2, NMS_SORT_SMEM_KEYS, fmt.cshift,
-                                      (unsigned long long)(seg % C) << fmt.cshift, tid, NMS_THREADS, s_hist, s_sel64, s_sel32);
-            cta_sort_keys<1>(s_sort, navail, tid, NMS_THREADS);
-        } else {
-            cta_sort_keys<4>(keys, n, tid, NMS_THREADS);
-            sorted = keys;
-        }
-        kept = 0;
-        if (tid < 4) s_alive32[tid >> 1][tid & 1] = 0u;
+        for (int i = tid; i < n; i += NMS_THREADS) s_sort[i] = keys[i];
         __syncthreads();
-
-        // the candidate of the NEXT chunk (key -> code -> anchor: dependent global loads) is fetched while the current
-        // chunk is processed
-        unsigned long long nkey = 0ull;
-        float4 ncode = make_float4(0.f, 0.f, 0.f, 0.f), nanc = make_float4(0.f, 0.f, 0.f, 0.f);
-        auto fetch = [&](int i) {
-            if (i < navail) {
-                nkey = sorted[i];
-                const int na = key_anchor(nkey, fmt);
-                ncode = load_code(codes, b, A, na);
-                if (!DECODED) nanc = anchors[na];
-            }
-        };
-        fetch(c);
-        int parity = 0;
-        for (int base = 0; base < navail && kept < K; base += NMS_CH, parity ^= 1) {
-            const int i = base + c;
-            bool alive = i < navail;
-            NmsBox box = {0.f, 0.f, 0.f, 0.f};
-            float4 raw = make_float4(0.f, 0.f, 0.f, 0.f);
-            float area = 0.f, score = 0.f;
-            int a = 0;
-            if (alive) {
-                a = key_anchor(nkey, fmt);
-                score = key_score(nkey, fmt);
-                if (DECODED) raw = ncode;
-                else raw = box_clip01(box_decode(ncode, nanc));                              // nms.py:76-77
-                box.ymin = fminf(raw.x, raw.z); box.xmin = fminf(raw.y, raw.w);
-                box.ymax = fmaxf(raw.x, raw.z); box.xmax = fmaxf(raw.y, raw.w);
-                area = f_mul(f_sub(box.ymax, box.ymin), f_sub(box.xmax, box.xmin));
-            }
-            fetch(i + NMS_CH);
-            // (a) against the boxes kept from earlier chunks
-            int hit = 0;
-            if (alive) {
-                for (int j = q; j < kept; j += NMS_TPC) {
-                    bool y, am;
-                    nms_fast(box, area, s_kept[j], s_kept_area[j], iou_thr, band, y, am);
-                    if (am) y = nms_exact(box, area, s_kept[j], s_kept_area[j], iou_thr); // rare: within 2^-18 of the threshold
-                    hit |= y ? 1 : 0;
-                }
-            }
-#pragma unroll
-            for (int o = 1; o < NMS_TPC; o <<= 1) hit |= __shfl_xor_sync(0xffffffffu, hit, o);
-            alive = alive && !hit;
-            if (q == 0) {
-                s_tile[c] = box;
-                s_tile_area[c] = area;
-                if (alive) atomicOr(&s_alive32[parity][c >> 5], 1u << (c & 31));
-            }
-            if (tid < 2) s_alive32[parity ^ 1][tid] = 0u;      // the buffer of the next chunk (last read two barriers ago)
-            __syncthreads();
-            const unsigned long long alive_mask = ((unsigned long long)s_alive32[parity][1] << 32) | s_alive32[parity][0];
-            // (b) column of the chunk's suppression matrix
-            unsigned long long col = 0ull;
-            if (alive && (alive_mask & (alive_mask - 1ull))) {               // at least two survivors in the chunk
-                for (int t = q; t < c; t += NMS_TPC) {
-                    if ((alive_mask >> t) & 1ull) {
-                        bool y, am;
-                        nms_fast(box, area, s_tile[t], s_tile_area[t], iou_thr, band, y, am);
-                        if (am) y = nms_exact(box, area, s_tile[t], s_tile_area[t], iou_thr);
-                        if (y) col |= 1ull << t;
-                    }
-                }
-            }
-#pragma unroll
-            for (int o = 1; o < NMS_TPC; o <<= 1) col |= __shfl_xor_sync(0xffffffffu, col, o);
-            if (q == 0) s_col[c] = col;
-            __syncthreads();
-            // (c) greedy order by resolution rounds (warp 0: lane l owns candidates l and l + 32)
-            if (warp == 0) {
-                const unsigned long long col_lo = s_col[lane], col_hi = s_col[lane + 32];
-                unsigned long long keep = 0ull, gone = ~alive_mask, und = alive_mask;
-                while (und) {
-                    int st_lo = 0, st_hi = 0;                                // 1 = kept, 2 = removed
-                    if ((und >> lane) & 1ull) st_lo = (col_lo & keep) ? 2 : ((col_lo & ~gone) == 0ull ? 1 : 0);
-                    if ((und >> (lane + 32)) & 1ull) st_hi = (col_hi & keep) ? 2 : ((col_hi & ~gone) == 0ull ? 1 : 0);
-                    const unsigned long long k_new = ((unsigned long long)__ballot_sync(0xffffffffu, st_hi == 1) << 32) | __ballot_sync(0xffffffffu, st_lo == 1);
-                    const unsigned long long g_new = ((unsigned long long)__ballot_sync(0xffffffffu, st_hi == 2) << 32) | __ballot_sync(0xffffffffu, st_lo == 2);
-                    keep |= k_new;
-                    gone |= g_new;
-                    und &= ~(k_new | g_new);
-                }
-                int extra = __popcll(keep) - (K - kept);                      // at most K in total: drop the lowest-scored
-                while (extra > 0) { keep &= ~(1ull << (63 - __clzll((long long)keep))); --extra; }
-                if (lane == 0) s_keep = keep;
-            }
-            __syncthreads();
-            const unsigned long long keep = s_keep;
-            // (d) append the kept candidates in score order
-            if (q == 0 && ((keep >> c) & 1ull)) {
-                const int pos = kept + __popcll(keep & ((1ull << c) - 1ull));
-                s_kept[pos] = box;
-                s_kept_area[pos] = area;
-                seg_box[obase + pos] = raw;
-                seg_score[obase + pos] = score;
-                seg_anchor[obase + pos] = a;
-            }
-            kept += __popcll(keep);
-            __syncthreads();
-        }
-        if (!LARGE || navail == n || kept >= K) break;          // uniform over the CTA; otherwise: full sort and start over
-      }
+        cta_sort_keys(s_sort, n, tid, NMS_THREADS);                 // score descending, anchor ascending
+        const int kept = nms_sorted_segment<DECODED>(N, sh, s_kept, s_kept_area, s_sort, n, seg, 0);
         if (tid == 0) seg_kept[seg] = kept;
-        __syncthreads();
     }
 }
 
-// ---------------------------------------------------------------------------------------------- 4. pack
+// ---------------------------------------------------------------------------------------------- 4. rounds (overflowing segments)
+// State of a pending segment, in k-space: k = key without its class bits = order(score) << abits | anchor; every candidate has
+// k < k_thr; smaller k = better.  lo: every key < lo has been through the segment's NMS.  [dlo, dhi): the key range the
+// current histogram resolves (bin = (k - dlo) >> sh; keys in [lo, dlo) count into bin 0, keys >= dhi are not looked at, their
+// number is `beyond`).  mid: the round collects the keys in [lo, mid).
+enum { ST_HIST = 1, ST_COLLECT = 2, ST_DONE = 3 };
+struct RoundState {
+    int* hdr;                      // H_* words
+    int* pend_queue;               // [nseg]
+    int* st; int* sh; int* fill; int* rem; int* beyond;              // [nseg]
+    unsigned long long* lo; unsigned long long* mid; unsigned long long* dlo; unsigned long long* dhi;   // [nseg]
+    unsigned* hist;                // [nseg][ROUND_NB]
+    int* stamp_h; int* stamp_c;    // [B]: image listed for the histogram / collect pass of round number = stamp
+    int* list_h;                   // [2][B]
+    int* list_c;                   // [B]
+    unsigned long long k_thr, dlo0;
+    int* err;                      // the context's sticky asynchronous-error word
+};
+
+__device__ __forceinline__ int ceil_log2_per_bin(unsigned long long width) {   // smallest s with ROUND_NB << s >= width
+    const unsigned long long per = (width + ROUND_NB - 1) / ROUND_NB;
+    return per <= 1ull ? 0 : 64 - __clzll((long long)(per - 1ull));
+}
+
+// all CTAs of the (co-resident) grid; `epoch` counts the barriers passed.  Gives up after ~10 s (a CTA that was never scheduled).
+__device__ __forceinline__ bool grid_barrier(int* hdr, int& epoch) {
+    __shared__ int s_ok;
+    ++epoch;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        atomicAdd(hdr + H_BAR, 1);
+        const int target = epoch * (int)gridDim.x;
+        const long long t0 = clock64();
+        int ok = 1;
+        while (*((volatile int*)(hdr + H_BAR)) < target) {
+            if (*((volatile int*)(hdr + H_ERR)) || clock64() - t0 > 20000000000ll) { atomicExch(hdr + H_ERR, 1); ok = 0; break; }
+            __nanosleep(64);
+        }
+        __threadfence();
+        s_ok = ok;
+    }
+    __syncthreads();
+    return s_ok != 0;
+}
+
+// CTA-cooperative streaming scan of `count` floats at `base` (peeled to 16-byte alignment); emit(r, v) for every element with
+// v > lim (r = element index inside the block)
+template <typename Emit>
+__device__ __forceinline__ void cta_scan(const float* __restrict__ base, int count, float lim, Emit emit) {
+    const int tid = threadIdx.x;
+    const unsigned mis = (unsigned)(((uintptr_t)base >> 2) & 3);
+    int head = mis ? (int)(4 - mis) : 0;
+    if (head > count) head = count;
+    const int nbody4 = (count - head) >> 2;
+    const int tail0 = head + (nbody4 << 2);
+    const float4* body = (const float4*)(base + head);
+    if (tid < 32) {
+        int r = -1;
+        if (tid < head) r = tid;
+        else if (tid - head < count - tail0) r = tail0 + (tid - head);
+        if (r >= 0 && base[r] > lim) emit(r, base[r]);
+    }
+    for (int i0 = 0; i0 < nbody4; i0 += NMS_THREADS * FILTER_UNROLL) {
+        float4 v[FILTER_UNROLL];
+#pragma unroll
+        for (int u = 0; u < FILTER_UNROLL; ++u) {
+            const int i = i0 + u * NMS_THREADS + tid;
+            v[u] = i < nbody4 ? ld_stream_f4(body + i) : make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+        }
+#pragma unroll
+        for (int u = 0; u < FILTER_UNROLL; ++u) {
+            const int r0 = head + ((i0 + u * NMS_THREADS + tid) << 2);
+            const float vals[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                if (vals[j] > lim) emit(r0 + j, vals[j]);
+        }
+    }
+}
+
+// per-class tables of one image during a streaming pass (shared memory when C <= ROUND_SMEM_MAX_C, else read from global)
+struct ClassTables {
+    unsigned char* st;             // [C]
+    unsigned char* shift;          // [C]
+    float* vmin;                   // [C]   collect pass: conservative lower bound of the value (logit or score) of a key < mid
+    unsigned long long* lo;        // [C]
+    unsigned long long* a;         // [C]   histogram pass: dlo;  collect pass: mid
+    unsigned long long* b;         // [C]   histogram pass: dhi
+    unsigned* hist;                // [C][ROUND_NB]
+};
+
+template <bool DECODED, bool IS_LOGITS>
+__global__ void __launch_bounds__(NMS_THREADS) nms_rounds_kernel(const HeadGeom G, int B, float thr, float x_lo, unsigned long long* __restrict__ cand,
+                                                                 const NmsSegArgs N, int* __restrict__ seg_kept, const RoundState R) {
+    extern __shared__ __align__(16) unsigned char nms_smem[];
+    __shared__ NmsShared sh;
+    const int npend = R.hdr[H_PEND];
+    if (npend == 0) return;                                          // the normal case: no segment overflowed its region
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int C = N.C, K = N.K;
+    const KeyFormat fmt = N.fmt;
+    const int grid = (int)gridDim.x, cta = (int)blockIdx.x;
+    unsigned long long* s_sort = (unsigned long long*)nms_smem;     // [SEG_CAP]
+    NmsBox* s_kept = (NmsBox*)(s_sort + SEG_CAP);                   // [K]
+    float* s_kept_area = (float*)(s_kept + K);                      // [K]
+    const bool tables_in_smem = C <= ROUND_SMEM_MAX_C;
+    ClassTables T;
+    {
+        unsigned char* p = (unsigned char*)(s_kept_area + K);
+        p = (unsigned char*)(((uintptr_t)p + 15) & ~(uintptr_t)15);
+        T.lo = (unsigned long long*)p; p += (size_t)C * 8;
+        T.a = (unsigned long long*)p; p += (size_t)C * 8;
+        T.b = (unsigned long long*)p; p += (size_t)C * 8;
+        T.hist = (unsigned*)p; p += (size_t)C * ROUND_NB * 4;
+        T.vmin = (float*)p; p += (size_t)C * 4;
+        T.st = p; p += C;
+        T.shift = p;
+    }
+    const unsigned long long kmask = (1ull << fmt.cshift) - 1ull;
+    int epoch = 0;
+
+    // ---- init: every pending segment starts with a histogram over [dlo0, k_thr)
+    for (int p = cta * NMS_THREADS + tid; p < npend; p += grid * NMS_THREADS) {
+        const int seg = R.pend_queue[p];
+        R.st[seg] = ST_HIST; R.lo[seg] = 0ull; R.dlo[seg] = R.dlo0; R.dhi[seg] = R.k_thr;
+        R.sh[seg] = ceil_log2_per_bin(R.k_thr - R.dlo0);
+        R.beyond[seg] = 0; R.rem[seg] = 0; R.fill[seg] = 0;
+        seg_kept[seg] = 0;
+        for (int j = 0; j < ROUND_NB; ++j) R.hist[(size_t)seg * ROUND_NB + j] = 0u;
+        const int b = seg / C;
+        if (atomicExch(R.stamp_h + b, 1) != 1) R.list_h[atomicAdd(R.hdr + H_NIMG_H0 + 1, 1) * 1 + B] = b;   // list of round 1 lives in list_h[1]
+    }
+    if (!grid_barrier(R.hdr, epoch)) { if (tid == 0) *R.err = SSDK_ASYNC_ROUNDS_TIMEOUT; return; }
+
+    // streaming decomposition of one pass: unit u -> (image list[u / group], slice u % group of every level's block)
+    auto for_units = [&](const int* list, int n_img, auto&& per_unit) {
+        const int group = n_img >= grid ? 1 : grid / n_img;
+        const long long units = (long long)n_img * group;
+        for (long long u = cta; u < units; u += grid) per_unit(list[u / group], (int)(u % group), group);
+    };
+    auto load_tables = [&](int b, int want_state) {
+        // per-class view of image b's segments for this pass; returns through T (shared memory) when it fits
+        for (int c = tid; c < C; c += NMS_THREADS) {
+            const int seg = b * C + c;
+            const int st = R.st[seg];
+            T.st[c] = (unsigned char)(st == want_state ? 1 : 0);
+            if (st != want_state) continue;
+            T.lo[c] = R.lo[seg];
+            if (want_state == ST_HIST) {
+                T.a[c] = R.dlo[seg]; T.b[c] = R.dhi[seg]; T.shift[c] = (unsigned char)R.sh[seg];
+            } else {
+                const unsigned long long mid = R.mid[seg];
+                T.a[c] = mid;
+                // values of keys < mid: their order word is <= mid's, i.e. their score is >= score_of_order(mid >> abits)
+                float vmin = -INFINITY;
+                const unsigned long long om = mid >> fmt.abits;
+                if (om <= 0xFFFFFFFFull) {
+                    const float s_mid = score_of_order((unsigned)om);
+                    if (!IS_LOGITS) vmin = s_mid;
+                    else if (s_mid >= 1.0f) vmin = 15.0f;                // sigmoid rounds to 1 only above 16.6
+                    else if (s_mid > 0.0f) {
+                        const float lg = logf(s_mid / (1.0f - s_mid));
+                        vmin = lg - 1e-3f * (1.0f + fabsf(lg));
+                    }
+                }
+                T.vmin[c] = vmin;
+            }
+        }
+        if (want_state == ST_HIST)
+            for (int i = tid; i < C * ROUND_NB; i += NMS_THREADS) T.hist[i] = 0u;
+        __syncthreads();
+    };
+
+    for (int round = 1;; ++round) {
+        const int par = round & 1;
+        const int n_img_h = R.hdr[H_NIMG_H0 + par];
+        const int n_hist = round == 1 ? npend : R.hdr[H_NHIST0 + par];
+        if (n_hist == 0) break;                                      // uniform: written before the last barrier
+        if (cta == 0 && tid == 0) {                                  // counters the NEXT round reads, and this round's collect list
+            R.hdr[H_NIMG_H0 + (par ^ 1)] = 0;
+            R.hdr[H_NHIST0 + (par ^ 1)] = 0;
+            R.hdr[H_NIMG_C] = 0;
+        }
+        // ---- (1) histogram pass
+        for_units(R.list_h + (size_t)par * B, n_img_h, [&](int b, int slice, int group) {
+            if (tables_in_smem) load_tables(b, ST_HIST);
+            for (int l = 0; l < G.num_levels; ++l) {
+                const LevelGeom g = level_geom(G, l);
+                const int blk = g.per_loc * g.C * g.hw;
+                const int r0 = (int)((long long)blk * slice / group), r1 = (int)((long long)blk * (slice + 1) / group);
+                const float* base = G.cls[l] + (size_t)b * blk;
+                cta_scan(base + r0, r1 - r0, IS_LOGITS ? x_lo : thr, [&](int r, float v) {
+                    int a, c;
+                    level_decompose(g, r0 + r, a, c);
+                    const int seg = b * C + c;
+                    if (tables_in_smem ? !T.st[c] : (R.st[seg] != ST_HIST)) return;
+                    float s;
+                    if (!is_candidate<IS_LOGITS>(v, thr, x_lo, &s)) return;
+                    const unsigned long long k = ((unsigned long long)order_desc(s) << fmt.abits) | (unsigned long long)a;
+                    const unsigned long long lo = tables_in_smem ? T.lo[c] : R.lo[seg];
+                    const unsigned long long dlo = tables_in_smem ? T.a[c] : R.dlo[seg];
+                    const unsigned long long dhi = tables_in_smem ? T.b[c] : R.dhi[seg];
+                    if (k < lo || k >= dhi) return;
+                    const int shf = tables_in_smem ? (int)T.shift[c] : R.sh[seg];
+                    unsigned long long bin = k <= dlo ? 0ull : ((k - dlo) >> shf);
+                    if (bin > ROUND_NB - 1) bin = ROUND_NB - 1;
+                    if (tables_in_smem) atomicAdd(&T.hist[c * ROUND_NB + (int)bin], 1u);
+                    else atomicAdd(&R.hist[(size_t)seg * ROUND_NB + (int)bin], 1u);
+                });
+            }
+            if (tables_in_smem) {
+                __syncthreads();
+                for (int i = tid; i < C * ROUND_NB; i += NMS_THREADS) {
+                    const unsigned h = T.hist[i];
+                    if (h) atomicAdd(&R.hist[(size_t)b * C * ROUND_NB + i], h);
+                }
+                __syncthreads();
+            }
+        });
+        if (!grid_barrier(R.hdr, epoch)) { if (tid == 0) *R.err = SSDK_ASYNC_ROUNDS_TIMEOUT; return; }
+
+        // ---- (2) plan: one thread per pending segment
+        for (int p = cta * NMS_THREADS + tid; p < npend; p += grid * NMS_THREADS) {
+            const int seg = R.pend_queue[p];
+            if (R.st[seg] != ST_HIST) continue;
+            unsigned* h = R.hist + (size_t)seg * ROUND_NB;
+            long long total = 0;
+            int f = -1;
+            for (int j = 0; j < ROUND_NB; ++j) {
+                total += h[j];
+                if (f < 0 && h[j]) f = j;
+            }
+            const unsigned long long lo = R.lo[seg], dlo = R.dlo[seg], dhi = R.dhi[seg];
+            const int shf = R.sh[seg], b = seg / C;
+            const long long beyond = R.beyond[seg];
+            if (f < 0) {
+                // nothing left inside the range
+                if (beyond == 0) R.st[seg] = ST_DONE;
+                else {                                              // (cannot happen after a refinement, whose bin is not empty; kept for safety)
+                    R.lo[seg] = dhi; R.dlo[seg] = dhi; R.dhi[seg] = R.k_thr; R.sh[seg] = ceil_log2_per_bin(R.k_thr - dhi); R.beyond[seg] = 0;
+                    atomicAdd(R.hdr + H_NHIST0 + (par ^ 1), 1);
+                    if (atomicExch(R.stamp_h + b, round + 1) != round + 1) R.list_h[(size_t)(par ^ 1) * B + atomicAdd(R.hdr + H_NIMG_H0 + (par ^ 1), 1)] = b;
+                }
+            } else if ((long long)h[f] > SEG_CAP) {
+                // the best non-empty bin alone does not fit a region: narrow the range to that bin (the bins before it are empty)
+                const unsigned long long nlo = f == 0 ? lo : dlo + ((unsigned long long)f << shf);
+                unsigned long long nhi = f == ROUND_NB - 1 ? dhi : dlo + ((unsigned long long)(f + 1) << shf);
+                if (nhi > dhi) nhi = dhi;
+                R.lo[seg] = nlo; R.dlo[seg] = nlo; R.dhi[seg] = nhi; R.sh[seg] = ceil_log2_per_bin(nhi - nlo);
+                R.beyond[seg] = (int)(beyond + total - (long long)h[f]);
+                atomicAdd(R.hdr + H_NHIST0 + (par ^ 1), 1);
+                if (atomicExch(R.stamp_h + b, round + 1) != round + 1) R.list_h[(size_t)(par ^ 1) * B + atomicAdd(R.hdr + H_NIMG_H0 + (par ^ 1), 1)] = b;
+            } else {
+                long long cum = 0;
+                int j = f;
+                for (; j < ROUND_NB; ++j) {
+                    if (cum + (long long)h[j] > SEG_CAP) break;
+                    cum += h[j];
+                    if (cum >= ROUND_WANT) { ++j; break; }
+                }
+                unsigned long long mid = j >= ROUND_NB ? dhi : dlo + ((unsigned long long)j << shf);
+                if (mid > dhi) mid = dhi;
+                R.mid[seg] = mid;
+                R.rem[seg] = (int)(total - cum + beyond);
+                R.fill[seg] = 0;
+                R.st[seg] = ST_COLLECT;
+                if (atomicExch(R.stamp_c + b, round) != round) R.list_c[atomicAdd(R.hdr + H_NIMG_C, 1)] = b;
+            }
+            for (int j = 0; j < ROUND_NB; ++j) h[j] = 0u;
+        }
+        if (!grid_barrier(R.hdr, epoch)) { if (tid == 0) *R.err = SSDK_ASYNC_ROUNDS_TIMEOUT; return; }
+
+        // ---- (3) collect pass: the keys in [lo, mid) of every collecting segment -> its region
+        const int n_img_c = R.hdr[H_NIMG_C];
+        for_units(R.list_c, n_img_c, [&](int b, int slice, int group) {
+            if (tables_in_smem) load_tables(b, ST_COLLECT);
+            for (int l = 0; l < G.num_levels; ++l) {
+                const LevelGeom g = level_geom(G, l);
+                const int blk = g.per_loc * g.C * g.hw;
+                const int r0 = (int)((long long)blk * slice / group), r1 = (int)((long long)blk * (slice + 1) / group);
+                const float* base = G.cls[l] + (size_t)b * blk;
+                cta_scan(base + r0, r1 - r0, IS_LOGITS ? x_lo : thr, [&](int r, float v) {
+                    int a, c;
+                    level_decompose(g, r0 + r, a, c);
+                    const int seg = b * C + c;
+                    if (tables_in_smem) {
+                        if (!T.st[c] || v < T.vmin[c]) return;
+                    } else if (R.st[seg] != ST_COLLECT) return;
+                    float s;
+                    if (!is_candidate<IS_LOGITS>(v, thr, x_lo, &s)) return;
+                    const unsigned long long k = ((unsigned long long)order_desc(s) << fmt.abits) | (unsigned long long)a;
+                    const unsigned long long lo = tables_in_smem ? T.lo[c] : R.lo[seg];
+                    const unsigned long long mid = tables_in_smem ? T.a[c] : R.mid[seg];
+                    if (k < lo || k >= mid) return;
+                    const int pos = atomicAdd(R.fill + seg, 1);
+                    if (pos < SEG_CAP) cand[(size_t)seg * SEG_CAP + pos] = ((unsigned long long)c << fmt.cshift) | k;
+                });
+            }
+            __syncthreads();
+        });
+        if (!grid_barrier(R.hdr, epoch)) { if (tid == 0) *R.err = SSDK_ASYNC_ROUNDS_TIMEOUT; return; }
+
+        // ---- (4) the segments' NMS continues over the collected keys
+        for (int p = cta; p < npend; p += grid) {
+            const int seg = R.pend_queue[p];
+            if (R.st[seg] != ST_COLLECT) continue;                   // CTA-uniform
+            const int n = min(R.fill[seg], SEG_CAP);
+            int kept = seg_kept[seg];
+            __syncthreads();
+            for (int i = tid; i < n; i += NMS_THREADS) s_sort[i] = cand[(size_t)seg * SEG_CAP + i] & kmask;
+            for (int i = tid; i < kept; i += NMS_THREADS) {          // the boxes kept in earlier rounds
+                float area;
+                s_kept[i] = nms_box_of(N.seg_box[(size_t)seg * K + i], area);
+                s_kept_area[i] = area;
+            }
+            __syncthreads();
+            cta_sort_keys(s_sort, n, tid, NMS_THREADS);
+            kept = nms_sorted_segment<DECODED>(N, sh, s_kept, s_kept_area, s_sort, n, seg, kept);
+            if (tid == 0) {
+                seg_kept[seg] = kept;
+                const unsigned long long mid = R.mid[seg];
+                if (kept >= K || R.rem[seg] <= 0 || mid >= R.k_thr) R.st[seg] = ST_DONE;
+                else {
+                    const int b = seg / C;
+                    R.st[seg] = ST_HIST;
+                    R.lo[seg] = mid; R.dlo[seg] = mid; R.dhi[seg] = R.k_thr; R.sh[seg] = ceil_log2_per_bin(R.k_thr - mid); R.beyond[seg] = 0;
+                    atomicAdd(R.hdr + H_NHIST0 + (par ^ 1), 1);
+                    if (atomicExch(R.stamp_h + b, round + 1) != round + 1) R.list_h[(size_t)(par ^ 1) * B + atomicAdd(R.hdr + H_NIMG_H0 + (par ^ 1), 1)] = b;
+                }
+            }
+        }
+        if (!grid_barrier(R.hdr, epoch)) { if (tid == 0) *R.err = SSDK_ASYNC_ROUNDS_TIMEOUT; return; }
+        (void)lane;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------- 5. pack
 #define PACK_SLOTS_PER_BLOCK 1024
 __global__ void __launch_bounds__(256) pack_kernel(const float4* __restrict__ seg_box, const float* __restrict__ seg_score,
                                                    const int* __restrict__ seg_anchor, const int* __restrict__ seg_kept,
                                                    int C, int K, float4* __restrict__ out_boxes, float* __restrict__ out_scores,
                                                    int* __restrict__ out_classes, int* __restrict__ out_num,
                                                    int* __restrict__ out_anchor, const float4* __restrict__ box_scaler,
-                                                   float final_thr, const int* __restrict__ large_count, int* hint_out) {
+                                                   float final_thr) {
     extern __shared__ int s_off[];   // [C+1] exclusive prefix sums of the per-class kept counts, then [C] the counts
     int* kept = s_off + C + 1;
     const int b = blockIdx.y;
-    // density hint for the NEXT call: number of segments that needed the large-segment path, posted to mapped host memory
-    if (hint_out && blockIdx.x == 0 && b == 0 && threadIdx.x == 0) *hint_out = *large_count;
     // Post-path consumers folded in (model.py:67-68, inference/detector.py:54-58): boxes /= box_scaler[b], and a final
     // `scores > final_thr` filter.  Inside a class the kept scores are descending, so the survivors of that filter are a
     // prefix of every class segment and the class-major order is preserved, exactly as the reference's boolean mask does.
@@ -791,6 +984,14 @@ static int bits_for(long long n) {   // bits needed to represent values in [0, n
 
 static bool aligned16(const void* p) { return ((uintptr_t)p & 15) == 0; }
 
+HeadGeom ssdk_flat_geom(const float* logits, const float* codes, int64_t A, int C);
+
+static unsigned order_of_float(float s) {
+    unsigned u;
+    memcpy(&u, &s, 4);
+    return order_desc_bits(u);
+}
+
 static int postprocess_impl(ssdk_ctx* ctx, const HeadGeom* head, const float* codes, const float* anchors, const float* scores, int flags,
                             int B, int64_t A, int C, double score_threshold, double iou_threshold, int K,
                             const float* box_scaler, double final_score_threshold,
@@ -815,33 +1016,36 @@ static int postprocess_impl(ssdk_ctx* ctx, const HeadGeom* head, const float* co
     SSDK_REQUIRE(((uintptr_t)scores & 3) == 0, SSDK_ERR_SHAPE, "ssdk_postprocess: scores must be 4-byte aligned");
     const long long per_image = (long long)A * C;
     SSDK_REQUIRE(per_image < (1ll << 31), SSDK_ERR_SHAPE, "ssdk_postprocess: A*C must be < 2^31");
-    SSDK_REQUIRE((size_t)K * 20 <= 160 * 1024, SSDK_ERR_SHAPE,
-                 "ssdk_postprocess: max_boxes_per_class %d too large", K);
+    SSDK_REQUIRE((size_t)K * 20 <= 96 * 1024, SSDK_ERR_SHAPE, "ssdk_postprocess: max_boxes_per_class %d too large", K);
     KeyFormat fmt;
     fmt.abits = bits_for(A > 1 ? A : 2);
     fmt.cshift = 32 + fmt.abits;
     SSDK_REQUIRE(fmt.cshift + bits_for(C > 1 ? C : 2) <= 64, SSDK_ERR_SHAPE, "ssdk_postprocess: A=%lld x C=%d does not fit the key",
                  (long long)A, C);
-
-    // workspace: one candidate region of A keys per (image, class) segment (a class cannot have more candidates than
-    // anchors, so the regions cannot overflow; only the filled prefixes are ever touched), one counter per segment
-    // (zeroed every call), per-segment NMS results
-    const long long capc = A > 0 ? A : 1;
     const long long nseg = (long long)B * C;
-    SSDK_TRY(ssdk_ensure(ctx, &ctx->ws_cand, (size_t)nseg * capc * sizeof(unsigned long long)));
-    const size_t n_int = 4 + 4 * (size_t)nseg;                         // queue counts (+pad), seg_count, seg_kept, heavy queue, large queue
-    SSDK_TRY(ssdk_ensure(ctx, &ctx->ws_counts, n_int * sizeof(int)));
+    SSDK_REQUIRE(nseg < (1ll << 31), SSDK_ERR_SHAPE, "ssdk_postprocess: B*C must be < 2^31");
+
+    // workspace: one BOUNDED candidate region of min(A, SEG_CAP) keys per (image, class) segment, one counter per segment
+    // (zeroed every call), the queues, the per-segment NMS results, and the state of the rounds (dense segments)
+    const bool may_overflow = A > SEG_CAP;                               // a segment can only overflow when there are that many anchors
+    SSDK_TRY(ssdk_ensure(ctx, &ctx->ws_cand, (size_t)nseg * SEG_CAP * sizeof(unsigned long long)));
+    const size_t n_int = H_WORDS + 4 * (size_t)nseg + (may_overflow ? 5 * (size_t)nseg + 5 * (size_t)B + 4 : 0);
+    const size_t n_u64 = may_overflow ? 4 * (size_t)nseg : 0;
+    const size_t n_hist = may_overflow ? (size_t)nseg * ROUND_NB : 0;
+    SSDK_TRY(ssdk_ensure(ctx, &ctx->ws_counts, 16 + n_u64 * 8 + (n_int + n_hist) * 4));
     const size_t seg_elems = (size_t)nseg * K;
     SSDK_TRY(ssdk_ensure(ctx, &ctx->ws_seg, seg_elems * (sizeof(float4) + sizeof(float) + sizeof(int))));
     unsigned long long* cand = (unsigned long long*)ctx->ws_cand.p;
-    int* heavy_count = (int*)ctx->ws_counts.p;
-    int* seg_count = heavy_count + 4;
+    unsigned long long* w64 = (unsigned long long*)ctx->ws_counts.p;
+    int* hdr = (int*)(w64 + n_u64);
+    int* seg_count = hdr + H_WORDS;
     int* seg_kept = seg_count + nseg;
     int* heavy_queue = seg_kept + nseg;
+    int* pend_queue = heavy_queue + nseg;
     float4* seg_box = (float4*)ctx->ws_seg.p;
     float* seg_score = (float*)(seg_box + seg_elems);
     int* seg_anchor = (int*)(seg_score + seg_elems);
-    SSDK_CHECK_CUDA(cudaMemsetAsync(heavy_count, 0, (4 + (size_t)nseg) * sizeof(int), ctx->stream));
+    SSDK_CHECK_CUDA(cudaMemsetAsync(hdr, 0, (H_WORDS + (size_t)nseg) * sizeof(int), ctx->stream));
     if (per_image == 0) SSDK_CHECK_CUDA(cudaMemsetAsync(seg_kept, 0, (size_t)nseg * sizeof(int), ctx->stream));
 
     const float thr = (float)score_threshold;
@@ -867,67 +1071,42 @@ static int postprocess_impl(ssdk_ctx* ctx, const HeadGeom* head, const float* co
             if (gx < 1) gx = 1;
             const dim3 hgrid_f((unsigned)gx, head->num_levels);
             SSDK_KERNEL(ctx, SSDK_K_FILTER,
-                if (is_logits)
-                    head_filter_kernel<true><<<hgrid_f, FILTER_THREADS, 0, ctx->stream>>>(*head, B, thr, x_lo, fmt, cand, capc, seg_count);
-                else
-                    head_filter_kernel<false><<<hgrid_f, FILTER_THREADS, 0, ctx->stream>>>(*head, B, thr, x_lo, fmt, cand, capc, seg_count));
+                if (is_logits) head_filter_kernel<true><<<hgrid_f, FILTER_THREADS, 0, ctx->stream>>>(*head, B, thr, x_lo, fmt, cand, seg_count);
+                else head_filter_kernel<false><<<hgrid_f, FILTER_THREADS, 0, ctx->stream>>>(*head, B, thr, x_lo, fmt, cand, seg_count));
         } else {
             long long chunks = (per_image / 4 + FILTER_THREADS * FILTER_UNROLL - 1) / (FILTER_THREADS * FILTER_UNROLL);
             long long gx = ((long long)ctx->num_sms * 16 + B - 1) / B;
             if (gx > chunks) gx = chunks;
             if (gx < 1) gx = 1;
             const dim3 fgrid((unsigned)gx, B);
-            // dense scores last time on this context (hint posted by pack_kernel; stale or missing is fine, both kernels are
-            // correct for any input): CTA-aggregated append
-            const bool dense = ctx->hint_host && ((volatile int*)ctx->hint_host)[0] > 0 && C <= 4096 && per_image < (1ll << 31) - 8;
-            if (getenv("SSDK_FILTER_DENSE") ? atoi(getenv("SSDK_FILTER_DENSE")) != 0 : dense) {
-                const size_t dsmem = 2 * (size_t)C * sizeof(int);
-                SSDK_KERNEL(ctx, SSDK_K_FILTER,
-                    if (is_logits)
-                        filter_dense_kernel<true><<<fgrid, FILTER_THREADS, dsmem, ctx->stream>>>(scores, per_image, C, thr, x_lo, fmt, cand, capc, seg_count);
-                    else
-                        filter_dense_kernel<false><<<fgrid, FILTER_THREADS, dsmem, ctx->stream>>>(scores, per_image, C, thr, x_lo, fmt, cand, capc, seg_count));
-            } else
             SSDK_KERNEL(ctx, SSDK_K_FILTER,
-                if (is_logits)
-                    filter_kernel<true><<<fgrid, FILTER_THREADS, 0, ctx->stream>>>(scores, per_image, C, thr, x_lo, fmt, cand, capc, seg_count);
-                else
-                    filter_kernel<false><<<fgrid, FILTER_THREADS, 0, ctx->stream>>>(scores, per_image, C, thr, x_lo, fmt, cand, capc, seg_count));
+                if (is_logits) filter_kernel<true><<<fgrid, FILTER_THREADS, 0, ctx->stream>>>(scores, per_image, C, thr, x_lo, fmt, cand, seg_count);
+                else filter_kernel<false><<<fgrid, FILTER_THREADS, 0, ctx->stream>>>(scores, per_image, C, thr, x_lo, fmt, cand, seg_count));
         }
 
-        // 2.-3. NMS: one warp per small segment (<= 32 candidates, sorted with shuffles), then one CTA per queued large
+        // 2.-3. NMS: one warp per small segment (<= 32 candidates, sorted with shuffles), then one CTA per queued heavy
         //       segment (sorted by the CTA)
-        const size_t nms_smem = (size_t)NMS_SORT_SMEM_KEYS * sizeof(unsigned long long) + (size_t)K * (sizeof(NmsBox) + sizeof(float));
+        const size_t nms_smem = (size_t)SEG_CAP * sizeof(unsigned long long) + (size_t)K * (sizeof(NmsBox) + sizeof(float));
         const int sgrid_nms = ceil_div_i(nseg, NMS_SMALL_WARPS);
         long long hgrid = (long long)ctx->num_sms * 4;
         if (hgrid > nseg) hgrid = nseg;
-        CodeView c4;
-        c4.flat = head ? nullptr : (const float4*)codes;
-        if (head) c4.head = *head;
-        else memset(&c4.head, 0, sizeof(c4.head));
-        const float4* a4 = (const float4*)anchors;
-        const float iou_f = (float)iou_threshold;
+        NmsSegArgs N;
+        memset(&N, 0, sizeof(N));
+        N.fmt = fmt;
+        N.codes.flat = head ? nullptr : (const float4*)codes;
+        if (head) N.codes.head = *head;
+        N.anchors = (const float4*)anchors;
+        N.A = A; N.C = C; N.K = K;
+        N.iou_thr = (float)iou_threshold;
+        N.seg_box = seg_box; N.seg_score = seg_score; N.seg_anchor = seg_anchor;
         const int nms_slot = ctx->profiling ? ssdk_prof_begin(ctx, SSDK_K_NMS) : -1;
-        // segments with more than NMS_SORT_SMEM_KEYS candidates can only exist when A is that large
-        const bool may_be_large = A > NMS_SORT_SMEM_KEYS;
-        long long lgrid = (long long)ctx->num_sms;
-        if (lgrid > nseg) lgrid = nseg;
 #define SSDK_LAUNCH_NMS(DEC)                                                                                                  \
         do {                                                                                                                  \
-            SSDK_TRY(ssdk_set_max_smem(ctx, (const void*)nms_kernel<DEC, false>, (int)nms_smem));                            \
+            SSDK_TRY(ssdk_set_max_smem(ctx, (const void*)nms_kernel<DEC>, (int)nms_smem));                                   \
             nms_small_kernel<DEC><<<sgrid_nms, NMS_SMALL_WARPS * 32, 0, ctx->stream>>>(                                      \
-                cand, capc, fmt, seg_count, c4, a4, A, nseg, C, K, iou_f, seg_box, seg_score, seg_anchor, seg_kept, heavy_queue, \
-                heavy_count);                                                                                                 \
-            nms_kernel<DEC, false><<<(int)hgrid, NMS_THREADS, nms_smem, ctx->stream>>>(                                      \
-                cand, capc, fmt, seg_count, c4, a4, A, nseg, C, K, iou_f, seg_box, seg_score, seg_anchor, seg_kept, heavy_queue, \
-                heavy_count);                                                                                                 \
-            if (may_be_large) {                                                                                               \
-                SSDK_TRY(ssdk_set_max_smem(ctx, (const void*)nms_kernel<DEC, true>, (int)nms_smem));                         \
-                nms_kernel<DEC, true><<<(int)lgrid, NMS_THREADS, nms_smem, ctx->stream>>>(                                   \
-                    cand, capc, fmt, seg_count, c4, a4, A, nseg, C, K, iou_f, seg_box, seg_score, seg_anchor, seg_kept,       \
-                    heavy_queue + nseg, heavy_count + 1);                                                                     \
-                ctx->launches++;                                                                                              \
-            }                                                                                                                 \
+                cand, fmt, seg_count, N.codes, N.anchors, A, nseg, C, K, N.iou_thr, seg_box, seg_score, seg_anchor, seg_kept,  \
+                heavy_queue, pend_queue, hdr);                                                                                \
+            nms_kernel<DEC><<<(int)hgrid, NMS_THREADS, nms_smem, ctx->stream>>>(cand, seg_count, N, seg_kept, heavy_queue, hdr); \
         } while (0)
         if (decoded) SSDK_LAUNCH_NMS(true);
         else SSDK_LAUNCH_NMS(false);
@@ -935,13 +1114,54 @@ static int postprocess_impl(ssdk_ctx* ctx, const HeadGeom* head, const float* co
         if (nms_slot >= 0) ssdk_prof_end(ctx, nms_slot);
         ctx->launches++;
         SSDK_CHECK_LAUNCH(ctx);
+
+        // 4. rounds: segments that overflowed their region (dense scores); exits at once when there is none
+        if (may_overflow) {
+            RoundState R;
+            memset(&R, 0, sizeof(R));
+            R.hdr = hdr;
+            R.pend_queue = pend_queue;
+            int* ip = pend_queue + nseg;
+            R.st = ip; ip += nseg;
+            R.sh = ip; ip += nseg;
+            R.fill = ip; ip += nseg;
+            R.rem = ip; ip += nseg;
+            R.beyond = ip; ip += nseg;
+            R.stamp_h = ip; ip += B;
+            R.stamp_c = ip; ip += B;
+            R.list_h = ip; ip += 2 * (size_t)B;
+            R.list_c = ip; ip += B;
+            R.hist = (unsigned*)(((uintptr_t)ip + 15) & ~(uintptr_t)15);
+            R.lo = w64; R.mid = w64 + nseg; R.dlo = w64 + 2 * nseg; R.dhi = w64 + 3 * nseg;
+            SSDK_CHECK_CUDA(cudaMemsetAsync(R.stamp_h, 0, 2 * (size_t)B * sizeof(int), ctx->stream));
+            const unsigned o_thr = order_of_float(thr), o_one = order_of_float(1.0f);
+            R.k_thr = (unsigned long long)o_thr << fmt.abits;            // candidates: score > thr <=> order word < o_thr
+            R.err = ctx->dev_err;
+            R.dlo0 = o_one < o_thr ? ((unsigned long long)o_one << fmt.abits) : 0ull;   // scores are normally <= 1: resolve [1.0, thr)
+            const HeadGeom G = head ? *head : ssdk_flat_geom(scores, codes, A, C);
+            const bool tables = C <= ROUND_SMEM_MAX_C;
+            size_t rsmem = nms_smem + 16;
+            if (tables) rsmem += (size_t)C * (3 * 8 + ROUND_NB * 4 + 4 + 2) + 16;
+            const void* fn = decoded ? (is_logits ? (const void*)nms_rounds_kernel<true, true> : (const void*)nms_rounds_kernel<true, false>)
+                                     : (is_logits ? (const void*)nms_rounds_kernel<false, true> : (const void*)nms_rounds_kernel<false, false>);
+            SSDK_TRY(ssdk_set_max_smem(ctx, fn, (int)rsmem));
+            int occ = 0;
+            SSDK_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, NMS_THREADS, rsmem));
+            SSDK_REQUIRE(occ >= 1, SSDK_ERR_SHAPE, "ssdk_postprocess: %d classes x %d boxes per class do not fit the dense-segment kernel", C, K);
+            if (occ > 2) occ = 2;
+            const int rgrid = ctx->num_sms * occ;                        // all CTAs must be co-resident (grid-wide barriers)
+            SSDK_KERNEL(ctx, SSDK_K_NMS_ROUNDS,
+                if (decoded && is_logits) nms_rounds_kernel<true, true><<<rgrid, NMS_THREADS, rsmem, ctx->stream>>>(G, B, thr, x_lo, cand, N, seg_kept, R);
+                else if (decoded) nms_rounds_kernel<true, false><<<rgrid, NMS_THREADS, rsmem, ctx->stream>>>(G, B, thr, x_lo, cand, N, seg_kept, R);
+                else if (is_logits) nms_rounds_kernel<false, true><<<rgrid, NMS_THREADS, rsmem, ctx->stream>>>(G, B, thr, x_lo, cand, N, seg_kept, R);
+                else nms_rounds_kernel<false, false><<<rgrid, NMS_THREADS, rsmem, ctx->stream>>>(G, B, thr, x_lo, cand, N, seg_kept, R));
+        }
     }
-    // 4. pack
+    // 5. pack
     SSDK_KERNEL(ctx, SSDK_K_PACK,
                 pack_kernel<<<dim3(ceil_div_i((long long)C * K, PACK_SLOTS_PER_BLOCK), B), 256, (size_t)(2 * C + 1) * sizeof(int), ctx->stream>>>(
                     seg_box, seg_score, seg_anchor, seg_kept, C, K, (float4*)out_boxes, out_scores, out_classes, out_num,
-                    out_anchor_idx, (const float4*)box_scaler, (float)final_score_threshold, heavy_count + 1,
-                    (per_image > 0 && !head) ? ctx->hint_dev : nullptr));
+                    out_anchor_idx, (const float4*)box_scaler, (float)final_score_threshold));
     return SSDK_OK;
 }
 

@@ -336,15 +336,62 @@ class SSD:
         return self._loss_forward(groundtruth, params, keep_targets=False)
 
     def _loss_forward(self, groundtruth, params, keep_targets):
-        sums = self.loss_sums(groundtruth, params, keep_targets=keep_targets)
-        call = self._call
-        out = call.empty([2], torch.float32)
-        self._reduce_and_finalize(call.ctx(), sums, out)
+        """ssd.py:71-133 in ONE launch (ssdk_ssd_loss_step: matching, flat pass, matched-anchor corrections, the exchange between
+        the image shards over NVLink peer memory, normalisation) whenever no library collective is needed; with NCCL as the
+        collective: sums -> all-reduce -> ssdk_loss_finalize."""
+        if self.process_group is not None and not self.peer_all_reduce:
+            sums = self.loss_sums(groundtruth, params, keep_targets=keep_targets)
+            call = self._call
+            out = call.empty([2], torch.float32)
+            self._reduce_and_finalize(call.ctx(), sums, out)
+        else:
+            sums, out = self._loss_step(groundtruth, params, keep_targets)
+            call = self._call
         self.num_matches = sums[2]
         if call.numpy_mode:
             o = out.cpu().numpy()
             return {'localization_loss': o[0], 'classification_loss': o[1]}
         return {'localization_loss': out[0], 'classification_loss': out[1]}
+
+    def _loss_step(self, groundtruth, params, keep_targets):
+        from . import ssd as this_module      # thresholds are module constants, as in ssd.py:187-188
+        lib = _lib.load()
+        flags = _lib.SSDK_STEP_ALL_REDUCE if (self.process_group is not None and self.peer_all_reduce) else 0
+        head = self._head()
+        call = Call(head.device) if head is not None else Call()
+        if head is not None:
+            B, A, C = head.batch_size, head.num_anchors, head.num_classes
+        else:
+            logits = call.tensor(self.raw_predictions['class_predictions'], torch.float32)
+            B, A, C = logits.shape
+            codes = call.tensor(self.raw_predictions['encoded_boxes'], torch.float32, (B, A, 4))
+        anchors = call.tensor(self.anchors, torch.float32, (A, 4))
+        gt = call.tensor(groundtruth['boxes'], torch.float32)
+        G = gt.shape[1]
+        labels = call.tensor(groundtruth['labels'], torch.int32, (B, G))
+        num = call.tensor(groundtruth['num_boxes'], torch.int32, (B,))
+        sums, out = call.empty([3], torch.float64), call.empty([2], torch.float32)
+        reg = cls_t = matches = None
+        if keep_targets:
+            reg, cls_t, matches = call.empty([B, A, 4], torch.float32), call.empty([B, A], torch.int32), call.empty([B, A], torch.int32)
+        thr = (float(this_module.POSITIVES_THRESHOLD), float(this_module.NEGATIVES_THRESHOLD))
+        if head is not None:
+            d = head.descriptor()
+            _lib.check(lib.ssdk_head_ssd_loss_step(
+                call.ctx(), ctypes.byref(d), ptr(anchors), ptr(gt), ptr(labels), ptr(num), B, A, C, G, thr[0], thr[1],
+                float(params['gamma']), float(params['alpha']), flags, ptr(sums), ptr(out), ptr(reg), ptr(cls_t), ptr(matches)))
+            if keep_targets:
+                self._saved = dict(head=head, sums=sums, gamma=float(params['gamma']), alpha=float(params['alpha']),
+                                   reg_targets=reg, cls_targets=cls_t, matches=matches)
+        else:
+            _lib.check(lib.ssdk_ssd_loss_step(
+                call.ctx(), ptr(anchors), ptr(logits), ptr(codes), ptr(gt), ptr(labels), ptr(num), B, A, C, G, thr[0], thr[1],
+                float(params['gamma']), float(params['alpha']), flags, ptr(sums), ptr(out), ptr(reg), ptr(cls_t), ptr(matches)))
+            if keep_targets:
+                self._saved = dict(logits=logits, codes=codes, sums=sums, gamma=float(params['gamma']), alpha=float(params['alpha']),
+                                   reg_targets=reg, cls_targets=cls_t, matches=matches)
+        self._call = call
+        return sums, out
 
     def _reduce_and_finalize(self, ctx, sums, out):
         """ssd.py:121-133 across the image shards: all-reduce(sum) of (sum loc, sum cls, num_matches), then the two ratios."""

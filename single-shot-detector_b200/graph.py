@@ -22,8 +22,28 @@ class CapturedStep:
         self.launches_per_replay = launches
 
     def replay(self):
+        if self.graph is None:
+            raise _lib.SsdkError('this CapturedStep has been released')
         self.graph.replay()
         return self.outputs
+
+    def release(self):
+        """Destroys the CUDA graph (and the references it holds to communicators, streams and tensors).  Teardown order for
+        multi-GPU programs: synchronize -> release() every CapturedStep -> torch.distributed.destroy_process_group().
+        A captured NCCL all-reduce keeps its communicator busy as long as the graph exists, and destroying the process group
+        first can block for minutes; the library's own peer-memory exchange has no such tie (plain kernels)."""
+        if self.graph is not None:
+            torch.cuda.synchronize()
+            self.graph.reset()
+            self.graph = None
+            self.outputs = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.release()
+        return False
 
 
 def concurrent(*fns, device=None):
@@ -40,14 +60,9 @@ def concurrent(*fns, device=None):
         outs = []
         for st in streams:
             st.wait_stream(cur)
-        # the caller provides the concurrency here: the library's own matcher / flat-pass overlap would only add contention
-        _lib.set_option(_lib.SSDK_OPT_OVERLAP_MATCHER, 0, dev.index)
-        try:
-            for st, fn in zip(streams, fns):
-                with torch.cuda.stream(st):
-                    outs.append(fn())
-        finally:
-            _lib.set_option(_lib.SSDK_OPT_OVERLAP_MATCHER, 1, dev.index)
+        for st, fn in zip(streams, fns):
+            with torch.cuda.stream(st):
+                outs.append(fn())
         for st in streams:
             cur.wait_stream(st)
         return tuple(outs)

@@ -485,39 +485,159 @@ def test_matched_count_from_the_matching_kernel(pkg, golden, case, tag):
     assert cnt.item() == 2.0 * float((want >= 0).sum())
 
 
+def _oracle_multiclass(boxes, scores, thr, iou, K):
+    from oracle import nms as onms
+    return onms.multiclass_non_max_suppression(boxes, scores, thr, iou, K, return_indices=True)
+
+
+@pytest.mark.parametrize('tag', ['p5n5', 'p5n4', 'p7n3'])
+@pytest.mark.parametrize('case', ['random40', 'quirk', 'tiny_ties', 'empty'])
+def test_fused_train_step_writes_the_same_targets(pkg, golden, case, tag):
+    """The fused training step (one launch: matcher CTAs + streaming CTAs, csrc/train_step.cu) materialises reg_targets /
+    cls_targets / matches exactly as the reference's own get_training_targets (golden fixture), counts the matched anchors
+    exactly -- forced matches and the row-id quirk included (their contributions are booked as CHANGES of the sums by the
+    CTA that finishes the image) -- and its losses equal the oracle's and the separate launches'."""
+    from oracle import ssd as ossd
+    g = golden('matching')
+    anchors, gt, labels = g['anchors'], g[case + '/gt'], g[case + '/labels']
+    A, n = anchors.shape[0], gt.shape[0]
+    C, B, Gmax = 80, 3, max(n, 1) + 2
+    pt, nt = THR[tag]
+    gtb = np.zeros([B, Gmax, 4], np.float32); gtb[:, :n] = gt
+    gtl = np.zeros([B, Gmax], np.int32); gtl[:, :n] = labels
+    num = np.array([n, 0, n], np.int32)                                # the middle image has no boxes
+    rng = np.random.default_rng(9)
+    logits = (rng.standard_normal([B, A, C]) * 2 - 3).astype(np.float32)
+    codes = rng.standard_normal([B, A, 4]).astype(np.float32)
+    d = {k: cuda(v) for k, v in dict(a=anchors, x=logits, c=codes, b=gtb, l=gtl, n=num).items()}
+    lib, L = pkg._lib.load(), pkg._lib
+    ctx = L.context(0)
+    L.check(lib.ssdk_ctx_set_stream(ctx, torch.cuda.current_stream().cuda_stream))
+    out = {}
+    for fused in (1, 0):
+        L.set_option(L.SSDK_OPT_FUSED_TRAIN_STEP, fused)
+        reg = torch.full([B, A, 4], 7.0, device='cuda'); cls = torch.full([B, A], 7, dtype=torch.int32, device='cuda')
+        mat = torch.full([B, A], 7, dtype=torch.int32, device='cuda')
+        sums = torch.zeros([3], dtype=torch.float64, device='cuda'); losses = torch.zeros([2], device='cuda')
+        try:
+            for _ in range(2):                                           # twice: the kernel leaves its workspace clean
+                L.check(lib.ssdk_ssd_loss_step(ctx, d['a'].data_ptr(), d['x'].data_ptr(), d['c'].data_ptr(), d['b'].data_ptr(),
+                                               d['l'].data_ptr(), d['n'].data_ptr(), B, A, C, Gmax, pt, nt, 2.0, 0.25, 0,
+                                               sums.data_ptr(), losses.data_ptr(), reg.data_ptr(), cls.data_ptr(), mat.data_ptr()))
+        finally:
+            L.set_option(L.SSDK_OPT_FUSED_TRAIN_STEP, 1)
+        out[fused] = [t.cpu().numpy() for t in (reg, cls, mat, sums, losses)]
+    want = g['%s/%s/matches' % (case, tag)] if n else np.full([A], -1, np.int32)
+    for fused in (1, 0):
+        reg, cls, mat, sums, losses = out[fused]
+        assert np.array_equal(mat[0], want) and np.array_equal(mat[2], want) and (mat[1] == -1).all()
+        assert sums[2] == 2.0 * float((want >= 0).sum())
+        if n:
+            assert np.array_equal(cls[0], g['%s/%s/cls' % (case, tag)]) and np.array_equal(cls[2], cls[0]) and not cls[1].any()
+            close(reg[0], g['%s/%s/reg' % (case, tag)], atol=1e-6)
+            assert np.array_equal(reg[2], reg[0]) and not reg[1].any()
+    for j in range(3):
+        assert np.array_equal(out[1][j], out[0][j])
+    close(out[1][3], out[0][3], rtol=1e-6)
+    close(out[1][4], out[0][4], rtol=1e-6)
+    o = ossd.loss(anchors, codes, logits, {'boxes': gtb, 'labels': gtl, 'num_boxes': num}, {'gamma': 2.0, 'alpha': 0.25}, C,
+                  positives_threshold=pt, negatives_threshold=nt)
+    close(out[1][4][0], o['localization_loss'], atol=1e-12)
+    close(out[1][4][1], o['classification_loss'])
+
+
 @pytest.mark.parametrize('kind', ['dense', 'realistic'])
-def test_dense_filter_kernel_equals_the_sparse_one(pkg, kind, monkeypatch):
-    """The CTA-aggregated candidate append used for dense scores (chosen by a hint from the previous call, or forced with
-    SSDK_FILTER_DENSE) must produce exactly the detections of the per-candidate append, for any input."""
+def test_bounded_candidate_regions_dense_and_sparse(pkg, kind):
+    """Candidate regions hold at most 4096 keys per (image, class).  With dense scores every segment overflows its region and
+    goes through the rounds of nms_rounds_kernel (histogram -> plan -> collect -> NMS continues); results must equal the
+    oracle's, which looks at every candidate.  'realistic': the same inputs sparse -- nothing overflows, same code path as
+    the bench.  An odd image stride (A*C*4 bytes not a multiple of 16) exercises the unaligned head / tail of every image."""
     from oracle import losses as olosses, nms as onms
     from oracle.anchor_generator import AnchorGenerator as OracleGen
     syn = load_pkg('synthetic')
     H, W, C, B, K = 200, 333, 7, 3, 12
     anchors = OracleGen(scale_multipliers=[1.0, 1.4142])(H, W)
     A = anchors.shape[0]
+    assert A > 4096
     gt = syn.make_groundtruth(55, B, 8, H, W, C)
     logits = syn.make_logits(kind, 55, B, A, C, anchors, gt) if kind == 'realistic' else syn.make_logits(kind, 55, B, A, C)
-    logits = logits[:, :, :C].copy()
     codes = (syn.make_codes(55, B, A) * np.float32(0.5)).astype(np.float32)
+    scores = olosses.sigmoid(logits)
+    if kind == 'dense':
+        assert ((scores > 0.05).sum(axis=1) > 4096).all()                # every segment overflows
     gen = pkg.AnchorGenerator(scale_multipliers=[1.0, 1.4142])
-    # an odd image stride (A*C*4 bytes not a multiple of 16) exercises the unaligned head / tail of every image
     ssd = pkg.SSD.from_predictions(H, W, {'encoded_boxes': cuda(codes), 'class_predictions': cuda(logits)}, gen, C)
-    monkeypatch.setenv('SSDK_FILTER_DENSE', '0')
-    sparse = ssd.get_predictions(0.05, 0.5, K)
-    monkeypatch.setenv('SSDK_FILTER_DENSE', '1')
-    dense = ssd.get_predictions(0.05, 0.5, K)
-    monkeypatch.delenv('SSDK_FILTER_DENSE')
-    hinted = ssd.get_predictions(0.05, 0.5, K)          # whichever kernel the hint selects
-    for k in ('boxes', 'labels', 'scores', 'num_boxes'):
-        assert torch.equal(sparse[k], dense[k]) and torch.equal(sparse[k], hinted[k]), k
-    want = onms.batch_multiclass_non_max_suppression(codes, anchors, olosses.sigmoid(logits), 0.05, 0.5, K)
-    assert np.array_equal(dense['num_boxes'].cpu().numpy(), want[3]) and want[3].sum() > 0
-    assert np.array_equal(dense['labels'].cpu().numpy(), want[2])
-    close(dense['boxes'].cpu().numpy(), want[0], atol=1e-7)
-    # scores given as probabilities (batch_multiclass_non_max_suppression) through the dense kernel
-    monkeypatch.setenv('SSDK_FILTER_DENSE', '1')
-    b, s, c, n = pkg.batch_multiclass_non_max_suppression(cuda(codes), cuda(anchors), cuda(olosses.sigmoid(logits)), 0.05, 0.5, K)
+    got = ssd.get_predictions(0.05, 0.5, K)
+    want = onms.batch_multiclass_non_max_suppression(codes, anchors, scores, 0.05, 0.5, K)
+    assert np.array_equal(got['num_boxes'].cpu().numpy(), want[3]) and want[3].sum() > 0
+    assert np.array_equal(got['labels'].cpu().numpy(), want[2])
+    close(got['boxes'].cpu().numpy(), want[0], atol=1e-7)
+    # scores given as probabilities (batch_multiclass_non_max_suppression): kept anchors bit-exact
+    b, s, c, n, a = pkg.batch_multiclass_non_max_suppression(cuda(codes), cuda(anchors), cuda(scores), 0.05, 0.5, K,
+                                                             return_anchor_indices=True)
+    want = onms.batch_multiclass_non_max_suppression(codes, anchors, scores, 0.05, 0.5, K, return_anchor_indices=True)
     assert np.array_equal(n.cpu().numpy(), want[3]) and np.array_equal(c.cpu().numpy(), want[2])
+    assert np.array_equal(a.cpu().numpy(), want[4]) and np.array_equal(s.cpu().numpy(), want[1])
+    # the same images as per-level channels_first tower outputs: identical detections
+    from oracle import box_predictor as obp
+    shapes = obp.level_shapes(H, W, gen.strides)
+    nloc = gen.num_anchors_per_location
+    head = pkg.SSD.from_head_outputs(H, W, [cuda(t) for t in obp.split_to_levels(codes, shapes, nloc)],
+                                     [cuda(t) for t in obp.split_to_levels(logits, shapes, nloc)], gen, C)
+    hgot = head.get_predictions(0.05, 0.5, K)
+    for k in ('boxes', 'labels', 'scores', 'num_boxes'):
+        assert torch.equal(hgot[k], got[k]), k
+    assert pkg._lib.async_error() == 0
+
+
+def test_overflowing_segments_need_every_candidate(pkg):
+    """The cases a top-T shortcut would get wrong: (1) 10,000 candidates of one class that are all the SAME box -- one is kept,
+    every other one must be looked at and suppressed, over several rounds; (2) candidates cycling through 5 disjoint boxes with
+    K = 8 -- exactly the best-scored anchor of each cluster survives; (3) 10,000 candidates with IDENTICAL scores -- the
+    histogram cannot separate them by score, the range is narrowed down to the anchor-index bits (ties go to the lower
+    index, as in TensorFlow's test TestSelectFromTenIdenticalBoxes)."""
+    rng = np.random.default_rng(11)
+    n, K = 10000, 8
+    clusters = np.array([[0.1 * j, 0.1 * j, 0.1 * j + 0.08, 0.1 * j + 0.08] for j in range(5)], np.float32)
+    boxes = np.zeros([n, 4], np.float32)
+    boxes[:] = clusters[np.arange(n) % 5]
+    scores = np.zeros([n, 3], np.float32)
+    scores[:, 0] = rng.permutation(n).astype(np.float32) / n * 0.9 + 0.06          # distinct scores, clusters of 5 boxes
+    same = np.tile(np.array([[0.2, 0.2, 0.6, 0.7]], np.float32), [n, 1])
+    scores[:, 1] = 0.5                                                             # identical scores
+    scores[:, 2] = rng.permutation(n).astype(np.float32) / n * 0.9 + 0.06
+    for bx, name in ((boxes, 'clusters'), (same, 'one box')):
+        sb, ss, sc, si = pkg.multiclass_non_max_suppression(cuda(bx), cuda(scores), 0.05, 0.5, K, return_indices=True)
+        ob, os_, oc, oi = _oracle_multiclass(bx, scores, 0.05, 0.5, K)
+        assert np.array_equal(si.cpu().numpy(), oi), name
+        assert np.array_equal(sc.cpu().numpy(), oc) and np.array_equal(ss.cpu().numpy(), os_) and np.array_equal(sb.cpu().numpy(), ob)
+        if name == 'clusters':
+            assert len(oi) == 15 and list(oi[5:10]) == [0, 1, 2, 3, 4]            # identical scores: lowest indices win
+        else:
+            assert len(oi) == 3 and oi[1] == 0
+    # disjoint boxes, identical scores, more candidates than a region: the K lowest anchor indices
+    grid = np.stack(np.meshgrid(np.arange(100), np.arange(100), indexing='ij'), -1).reshape(-1, 2).astype(np.float32) / 100
+    disjoint = np.concatenate([grid, grid + 0.009], axis=1).astype(np.float32)
+    sb, ss, sc, si = pkg.multiclass_non_max_suppression(cuda(disjoint), cuda(scores[:, 1:2]), 0.05, 0.5, K, return_indices=True)
+    assert list(si.cpu().numpy()) == list(range(K))
+    assert pkg._lib.async_error() == 0
+
+
+def test_candidate_workspace_is_bounded(pkg):
+    """ADVICE / VERDICT item: the candidate arena is 4096 keys per (image, class), independent of the number of anchors --
+    at cfg3's shape (107,415 anchors, 90 classes) less than a quarter of the logits' bytes (it was twice the logits)."""
+    syn = load_pkg('synthetic')
+    cfg = syn.CONFIGS[3]
+    H, W, C, B = cfg['H'], cfg['W'], cfg['C'], 4
+    gen = pkg.AnchorGenerator(scale_multipliers=cfg['scale_multipliers'])
+    anchors = gen(H, W)
+    A = anchors.shape[0]
+    before = pkg._lib.workspace_bytes()
+    logits = torch.full([B, A, C], -9.0, device='cuda')
+    codes = torch.zeros([B, A, 4], device='cuda')
+    pkg.batch_multiclass_non_max_suppression(codes, anchors, logits, 0.05, 0.5, 100, scores_are_logits=True)
+    grown = pkg._lib.workspace_bytes() - before
+    assert grown <= 0.25 * B * A * C * 4, (grown, B * A * C * 4)
 
 
 # ------------------------------------------------------------------------------------------------ sharding / launching
@@ -559,7 +679,8 @@ def test_cfg4_batch_256_sharded_like_8_ranks(pkg):
 
 def test_concurrent_subpaths_and_options(pkg, golden):
     """graph.concurrent: the training-side and the inference-side sub-path on two streams (eager and as parallel branches of a
-    captured graph) give exactly the results of the sequential calls; SSDK_OPT_OVERLAP_MATCHER does not change results."""
+    captured graph) give exactly the results of the sequential calls; the knobs of the fused training step (CTAs that start as
+    matchers, their share of the streaming, fusion off) change the partition of the sums only: same count, losses to 1e-7."""
     g = golden('losses')
     H, W = [int(v) for v in g['HW']]
     C = int(g['C'])
@@ -569,11 +690,25 @@ def test_concurrent_subpaths_and_options(pkg, golden):
     gt = {'boxes': cuda(g['gt_boxes']), 'labels': cuda(g['gt_labels']), 'num_boxes': cuda(g['num_boxes'])}
     params = {'gamma': 2.0, 'alpha': 0.25}
     want_l, want_p = ssd.loss(gt, params), ssd.get_predictions(0.05, 0.5, 10)
-    pkg._lib.set_option(pkg._lib.SSDK_OPT_OVERLAP_MATCHER, 0)
-    l0 = ssd.loss(gt, params)
-    pkg._lib.set_option(pkg._lib.SSDK_OPT_OVERLAP_MATCHER, 1)
-    assert float(l0['classification_loss']) == float(want_l['classification_loss'])
-    assert float(l0['localization_loss']) == float(want_l['localization_loss'])
+    L = pkg._lib
+    want_n = float(ssd.num_matches)
+    try:
+        for opt, val in ((L.SSDK_OPT_FUSED_TRAIN_STEP, 0), (L.SSDK_OPT_MATCH_CTAS_PER_SM, 1), (L.SSDK_OPT_MATCH_CTAS_PER_SM, 4),
+                         (L.SSDK_OPT_MATCH_FLAT_SHARE_PCT, 0), (L.SSDK_OPT_MATCH_FLAT_SHARE_PCT, 100)):
+            L.set_option(opt, val)
+            l0 = ssd.loss(gt, params)
+            assert float(ssd.num_matches) == want_n
+            close(float(l0['classification_loss']), float(want_l['classification_loss']), rtol=1e-7)
+            close(float(l0['localization_loss']), float(want_l['localization_loss']), rtol=1e-7)
+            L.set_option(L.SSDK_OPT_FUSED_TRAIN_STEP, 1)
+            L.set_option(L.SSDK_OPT_MATCH_CTAS_PER_SM, 2)
+            L.set_option(L.SSDK_OPT_MATCH_FLAT_SHARE_PCT, 50)
+        with pytest.raises(ValueError):
+            L.set_option(L.SSDK_OPT_MATCH_CTAS_PER_SM, 9)
+    finally:
+        L.set_option(L.SSDK_OPT_FUSED_TRAIN_STEP, 1)
+        L.set_option(L.SSDK_OPT_MATCH_CTAS_PER_SM, 2)
+        L.set_option(L.SSDK_OPT_MATCH_FLAT_SHARE_PCT, 50)
     both = pkg.graph.concurrent(lambda: ssd.loss(gt, params), lambda: ssd.get_predictions(0.05, 0.5, 10))
     for run in (both, pkg.graph.capture(both).replay):
         for _ in range(3):
