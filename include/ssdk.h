@@ -54,9 +54,10 @@ SSDK_API const char* ssdk_last_error(void);
 SSDK_API int ssdk_ctx_create(int device, void* stream, ssdk_ctx** out);
 SSDK_API int ssdk_ctx_set_stream(ssdk_ctx* ctx, void* stream);
 /* Options of the fused training step (ssdk_ssd_loss_step, ssdk_ssd_targets_and_loss and their ssdk_head_* forms; see
- * csrc/train_step.cu): one persistent kernel whose CTAs take roles -- `SSDK_OPT_MATCH_CTAS_PER_SM` CTAs per SM (default 2, 1..4)
- * start with the ALU-bound target assignment while the others stream the logits, and join the streaming afterwards for
- * `SSDK_OPT_MATCH_FLAT_SHARE_PCT` percent (default 50, 0..100) of a streaming CTA's share of the chunks.
+ * csrc/train_step.cu): one persistent kernel whose CTAs take roles -- `SSDK_OPT_MATCH_CTAS_PER_SM` CTAs per SM (1..7, capped by
+ * the kernel's occupancy) start with the ALU-bound target assignment while the others stream the logits, and join the
+ * streaming afterwards for `SSDK_OPT_MATCH_FLAT_SHARE_PCT` percent (0..100) of a streaming CTA's share of the chunks.  The
+ * defaults (0 and -1) choose both from the number of ground-truth boxes and classes (the ratio of matching to streaming work).
  * SSDK_OPT_FUSED_TRAIN_STEP = 0 runs the same computation as separate launches (matcher, flat pass, matched-anchor pass,
  * finalisation) -- for comparison; results agree to rounding of the double sums.  The same knobs are read once at context
  * creation from SSDK_MATCH_CTAS / SSDK_MATCH_FLAT_SHARE (values are clamped to their valid ranges). */
@@ -85,6 +86,10 @@ SSDK_API int ssdk_ctx_profile_read(ssdk_ctx* ctx, double* out_ms, int64_t* out_c
  * scheduled (the GPU was oversubscribed by other work for that long); the detections of that call are incomplete. */
 #define SSDK_ASYNC_ROUNDS_TIMEOUT 1
 SSDK_API int ssdk_ctx_async_error(ssdk_ctx* ctx, int* out_code);
+/* Diagnostics of the dense-segment stage of the LAST post-processing call (synchronises): out[0] = rounds run (0 = no segment
+ * overflowed its candidate region), out[1..n) = %globaltimer nanoseconds at kernel start, after initialisation, and per round at
+ * its start and after the histogram pass, the planning step, the collect pass and the NMS phase (first rounds only). */
+SSDK_API int ssdk_ctx_round_times(ssdk_ctx* ctx, int64_t* out, int n);
 /* cudaStreamSynchronize on the context's stream (synchronous). */
 SSDK_API int ssdk_ctx_synchronize(ssdk_ctx* ctx);
 
@@ -252,6 +257,29 @@ SSDK_API int ssdk_detect(ssdk_ctx* ctx, const float* codes, const float* anchors
                 int64_t A, int C, double score_threshold, double iou_threshold, int K, const float* box_scaler,
                 double final_score_threshold, float* out_boxes, float* out_scores, int32_t* out_classes,
                 int32_t* out_num);
+/* ssdk_detect plus the rows of the COCO results file that inference/evaluate_on_COCO.ipynb (cell 10) builds from the detector's
+ * output, written by the same pack kernel: for detection i of image b (same order and padding as out_boxes)
+ *     box * [height, width, height, width] (float32)  ->  out_bbox_xywh = [int(xmin), int(ymin), int(xmax - xmin), int(ymax - ymin)]
+ * (Python int(): truncation towards zero), out_category_id = category_ids[class] (the notebook's integer_to_coco_id; NULL =
+ * the class index), out_image_id = image_ids[b] (NULL = b); padding rows are 0 / -1 / -1.
+ *   image_sizes: DEVICE float[B,2] = (height, width) in pixels; out_bbox_xywh: DEVICE int32[B,C*K,4] (16-byte aligned);
+ *   out_category_id, out_image_id: DEVICE int32[B,C*K].  The notebook calls the detector with score_threshold 0.15: pass it
+ *   as final_score_threshold. */
+SSDK_API int ssdk_detect_coco(ssdk_ctx* ctx, const float* codes, const float* anchors, const float* scores, int flags, int B,
+                     int64_t A, int C, double score_threshold, double iou_threshold, int K, const float* box_scaler,
+                     double final_score_threshold, const float* image_sizes, const int32_t* image_ids,
+                     const int32_t* category_ids, float* out_boxes, float* out_scores, int32_t* out_classes,
+                     int32_t* out_num, int32_t* out_bbox_xywh, int32_t* out_category_id, int32_t* out_image_id);
+/* The per-label detection lists the reference's evaluator accumulates (metrics.py:113-123: add_detections appends
+ * get_box(box, image_name, score) to self.detections[label] for every detection of every image, in evaluation order): label-major
+ * packing of the same NMS results.  For label c: out_counts[c] records; record j is out_boxes[c, j] / out_scores[c, j] /
+ * out_image[c, j] (= image_ids[b], NULL = b): image 0's boxes of that class in descending score, then image 1's, ...
+ *   out_boxes DEVICE float[C, B*K, 4] (16-byte aligned), out_scores float[C, B*K], out_image int32[C, B*K], out_counts int32[C];
+ *   entries beyond out_counts[c] are not written. */
+SSDK_API int ssdk_detect_by_label(ssdk_ctx* ctx, const float* codes, const float* anchors, const float* scores, int flags, int B,
+                         int64_t A, int C, double score_threshold, double iou_threshold, int K, const float* box_scaler,
+                         double final_score_threshold, const int32_t* image_ids, float* out_boxes, float* out_scores,
+                         int32_t* out_image, int32_t* out_counts);
 /* Same as ssdk_postprocess with HOST buffers (synchronous). */
 SSDK_API int ssdk_postprocess_host(ssdk_ctx* ctx, const float* codes, const float* anchors,
                           const float* scores, int flags, int B, int64_t A, int C,

@@ -26,6 +26,7 @@ _SIGNATURES = {
     'ssdk_ctx_launch_count': (c_i64, [P]),
     'ssdk_ctx_synchronize': (c_int, [P]),
     'ssdk_ctx_async_error': (c_int, [P, ctypes.POINTER(c_int)]),
+    'ssdk_ctx_round_times': (c_int, [P, P, c_int]),
     'ssdk_ctx_set_profiling': (c_int, [P, c_int]),
     'ssdk_ctx_profile_read': (c_int, [P, P, P, c_int, c_int]),
     'ssdk_num_anchors': (c_int, [c_int, c_int, P, c_int, c_int, ctypes.POINTER(c_i64), P]),
@@ -57,6 +58,8 @@ _SIGNATURES = {
                                                c_double, c_double, P, P]),
     'ssdk_postprocess': (c_int, [P, P, P, P, c_int, c_int, c_i64, c_int, c_double, c_double, c_int, P, P, P, P, P]),
     'ssdk_detect': (c_int, [P, P, P, P, c_int, c_int, c_i64, c_int, c_double, c_double, c_int, P, c_double, P, P, P, P]),
+    'ssdk_detect_coco': (c_int, [P, P, P, P, c_int, c_int, c_i64, c_int, c_double, c_double, c_int, P, c_double, P, P, P, P, P, P, P, P, P, P]),
+    'ssdk_detect_by_label': (c_int, [P, P, P, P, c_int, c_int, c_i64, c_int, c_double, c_double, c_int, P, c_double, P, P, P, P, P]),
     'ssdk_postprocess_host': (c_int, [P, P, P, P, c_int, c_int, c_i64, c_int, c_double, c_double, c_int, P, P, P, P]),
     'ssdk_head_concat': (c_int, [P, P, c_int, c_int, P, P]),
     'ssdk_head_ssd_loss': (c_int, [P, P, P, P, P, c_int, c_i64, c_int, c_double, c_double, P]),
@@ -166,6 +169,13 @@ def profile_read(device_index=0, reset=True):
 SSDK_OPT_FUSED_TRAIN_STEP, SSDK_OPT_MATCH_CTAS_PER_SM, SSDK_OPT_MATCH_FLAT_SHARE_PCT = 1, 2, 3
 SSDK_STEP_ALL_REDUCE = 1
 SSDK_ASYNC_ROUNDS_TIMEOUT = 1
+
+
+def round_times(device_index=0, n=32):
+    """[rounds run, timestamps in ns ...] of the dense-segment stage of the last post-processing call (ssdk_ctx_round_times)."""
+    buf = (c_i64 * n)()
+    check(load().ssdk_ctx_round_times(context(device_index), ctypes.cast(buf, P), n))
+    return [int(v) for v in buf]
 
 
 def async_error(device_index=0):

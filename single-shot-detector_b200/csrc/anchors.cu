@@ -70,7 +70,7 @@ extern "C" int ssdk_num_anchors(int H, int W, const int* strides, int L, int per
 
 extern "C" int ssdk_anchors(ssdk_ctx* ctx, int H, int W, const int* strides, const float* scales,
                             const float* ratios, int L, int per_loc, float* out, float* raw) {
-    SSDK_TRY(ssdk_ctx_enter(ctx));
+    SSDK_ENTER(ctx);
     SSDK_REQUIRE(H > 0 && W > 0 && strides && scales && ratios && out, SSDK_ERR_ARG, "ssdk_anchors: bad arguments");
     SSDK_REQUIRE(L > 0 && L <= SSDK_MAX_LEVELS, SSDK_ERR_SHAPE, "num_levels %d not in [1,%d]", L, SSDK_MAX_LEVELS);
     SSDK_REQUIRE(per_loc > 0 && per_loc <= SSDK_MAX_PER_LOC, SSDK_ERR_SHAPE, "anchors_per_location %d not in [1,%d]",

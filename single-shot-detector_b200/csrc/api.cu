@@ -34,6 +34,29 @@ int ssdk_ensure(ssdk_ctx* ctx, ssdk_buf* b, size_t bytes) {
     return SSDK_OK;
 }
 
+SsdkWsGuard::SsdkWsGuard(ssdk_ctx* c, int g) : ctx(c), group(g) {
+    cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(ctx->stream, &st) != cudaSuccess) { cudaGetLastError(); st = cudaStreamCaptureStatusNone; }
+    capturing = st != cudaStreamCaptureStatusNone;
+    if (capturing) return;
+    if (ctx->ws_valid[group] && ctx->ws_stream[group] != ctx->stream) cudaStreamWaitEvent(ctx->stream, ctx->ws_event[group], 0);
+}
+
+SsdkWsGuard::~SsdkWsGuard() {
+    if (capturing) {
+        ctx->ws_valid[group] = false;               // the last use is inside a graph: nothing an eager call could wait on
+        return;
+    }
+    if (!ctx->ws_event[group] && cudaEventCreateWithFlags(&ctx->ws_event[group], cudaEventDisableTiming) != cudaSuccess) {
+        cudaGetLastError();
+        ctx->ws_event[group] = nullptr;
+        ctx->ws_valid[group] = false;
+        return;
+    }
+    ctx->ws_valid[group] = cudaEventRecord(ctx->ws_event[group], ctx->stream) == cudaSuccess;
+    ctx->ws_stream[group] = ctx->stream;
+}
+
 // Raise a kernel's dynamic shared-memory limit once per (device, kernel) instead of on every launch.  The attribute is
 // a property of the function on the device, not of a context, so the record is process-wide (contexts of other host
 // threads -- e.g. the autograd engine's -- launch the same kernels) and the limit is only ever raised.
@@ -92,7 +115,7 @@ static int env_int(const char* name, int dflt, int lo, int hi, int mult) {
 extern "C" {
 
 int ssdk_ctx_set_profiling(ssdk_ctx* ctx, int enable) {
-    SSDK_TRY(ssdk_ctx_enter(ctx));
+    SSDK_ENTER(ctx);
     if (enable && !ctx->prof_ev) {
         ctx->prof_ev = new cudaEvent_t[2 * SSDK_PROFILE_EVENTS];
         for (int i = 0; i < 2 * SSDK_PROFILE_EVENTS; ++i) SSDK_CHECK_CUDA(cudaEventCreate(&ctx->prof_ev[i]));
@@ -103,7 +126,7 @@ int ssdk_ctx_set_profiling(ssdk_ctx* ctx, int enable) {
 }
 
 int ssdk_ctx_profile_read(ssdk_ctx* ctx, double* out_ms, int64_t* out_calls, int n, int reset) {
-    SSDK_TRY(ssdk_ctx_enter(ctx));
+    SSDK_ENTER(ctx);
     SSDK_TRY(prof_drain(ctx));
     for (int i = 0; i < n && i < SSDK_K_COUNT; ++i) {
         if (out_ms) out_ms[i] = ctx->prof_ms[i];
@@ -128,6 +151,11 @@ int ssdk_ctx_create(int device, void* stream, ssdk_ctx** out) {
         return SSDK_ERR_CUDA;
     }
     SSDK_REQUIRE(device >= 0 && device < count, SSDK_ERR_ARG, "device %d out of range [0,%d)", device, count);
+    struct Restore {                                    // the caller's current device is left as it was
+        int prev = -1;
+        Restore() { if (cudaGetDevice(&prev) != cudaSuccess) prev = -1; }
+        ~Restore() { if (prev >= 0) cudaSetDevice(prev); }
+    } restore;
     SSDK_CHECK_CUDA(cudaSetDevice(device));
     cudaDeviceProp prop;
     SSDK_CHECK_CUDA(cudaGetDeviceProperties(&prop, device));
@@ -145,8 +173,8 @@ int ssdk_ctx_create(int device, void* stream, ssdk_ctx** out) {
     c->tune_loss_rpw = env_int("SSDK_LOSS_RPW", 0, 4, 32, 4);             // rows per warp of ssd_loss_kernel: a multiple of 4 (16-byte TMA tiles)
     c->tune_loss_stages = env_int("SSDK_LOSS_STAGES", 0, 2, 4, 1);        // TMA ring depth
     c->tune_loss_ctas = env_int("SSDK_LOSS_CTAS", 0, 1, 8, 1);            // the partials buffer holds num_sms * 8 CTAs
-    c->match_ctas_per_sm = env_int("SSDK_MATCH_CTAS", 2, 1, 4, 1);
-    c->match_flat_share_pct = env_int("SSDK_MATCH_FLAT_SHARE", 50, 0, 100, 1);
+    c->match_ctas_per_sm = env_int("SSDK_MATCH_CTAS", 0, 0, 7, 1);
+    c->match_flat_share_pct = env_int("SSDK_MATCH_FLAT_SHARE", -1, -1, 100, 1);
     *out = c;
     return SSDK_OK;
 }
@@ -156,11 +184,11 @@ int ssdk_ctx_set_option(ssdk_ctx* ctx, int option, int value) {
     switch (option) {
         case SSDK_OPT_FUSED_TRAIN_STEP: ctx->fused_train_step = value ? 1 : 0; return SSDK_OK;
         case SSDK_OPT_MATCH_CTAS_PER_SM:
-            SSDK_REQUIRE(value >= 1 && value <= 4, SSDK_ERR_ARG, "SSDK_OPT_MATCH_CTAS_PER_SM must be in [1,4] (got %d)", value);
+            SSDK_REQUIRE(value >= 0 && value <= 7, SSDK_ERR_ARG, "SSDK_OPT_MATCH_CTAS_PER_SM must be in [0,7] (got %d)", value);
             ctx->match_ctas_per_sm = value;
             return SSDK_OK;
         case SSDK_OPT_MATCH_FLAT_SHARE_PCT:
-            SSDK_REQUIRE(value >= 0 && value <= 100, SSDK_ERR_ARG, "SSDK_OPT_MATCH_FLAT_SHARE_PCT must be in [0,100] (got %d)", value);
+            SSDK_REQUIRE(value >= -1 && value <= 100, SSDK_ERR_ARG, "SSDK_OPT_MATCH_FLAT_SHARE_PCT must be in [-1,100] (got %d)", value);
             ctx->match_flat_share_pct = value;
             return SSDK_OK;
         default: ssdk_set_error("ssdk_ctx_set_option: unknown option %d", option); return SSDK_ERR_ARG;
@@ -176,6 +204,8 @@ int ssdk_ctx_set_stream(ssdk_ctx* ctx, void* stream) {
 int ssdk_ctx_destroy(ssdk_ctx* ctx) {
     if (!ctx) return SSDK_OK;
     ssdk_comm_disconnect(ctx);
+    int prev_dev = -1;
+    if (cudaGetDevice(&prev_dev) != cudaSuccess) prev_dev = -1;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     ssdk_buf* bufs[] = {&ctx->ws_gtbest, &ctx->ws_partials, &ctx->ws_reg, &ctx->ws_cls, &ctx->ws_matches,
@@ -188,7 +218,10 @@ int ssdk_ctx_destroy(ssdk_ctx* ctx) {
     }
     for (int i = 0; i < 4; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
     if (ctx->dev_err) cudaFree(ctx->dev_err);
+    for (int i = 0; i < 8; ++i) if (ctx->ws_event[i]) cudaEventDestroy(ctx->ws_event[i]);
+    const int own_dev = ctx->device;
     delete ctx;
+    if (prev_dev >= 0 && prev_dev != own_dev) cudaSetDevice(prev_dev);
     return SSDK_OK;
 }
 
@@ -205,7 +238,7 @@ int64_t ssdk_ctx_workspace_bytes(const ssdk_ctx* ctx) {
 int64_t ssdk_ctx_launch_count(const ssdk_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
 int ssdk_ctx_async_error(ssdk_ctx* ctx, int* out_code) {
-    SSDK_TRY(ssdk_ctx_enter(ctx));
+    SSDK_ENTER(ctx);
     SSDK_REQUIRE(out_code != nullptr, SSDK_ERR_ARG, "ssdk_ctx_async_error: out_code is NULL");
     SSDK_CHECK_CUDA(cudaStreamSynchronize(ctx->stream));
     SSDK_CHECK_CUDA(cudaMemcpy(out_code, ctx->dev_err, sizeof(int), cudaMemcpyDeviceToHost));
@@ -213,7 +246,7 @@ int ssdk_ctx_async_error(ssdk_ctx* ctx, int* out_code) {
 }
 
 int ssdk_ctx_synchronize(ssdk_ctx* ctx) {
-    SSDK_TRY(ssdk_ctx_enter(ctx));
+    SSDK_ENTER(ctx);
     SSDK_CHECK_CUDA(cudaStreamSynchronize(ctx->stream));
     return SSDK_OK;
 }

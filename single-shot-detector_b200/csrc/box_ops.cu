@@ -75,7 +75,7 @@ __global__ void __launch_bounds__(256) focal_dense_kernel(const float* __restric
 extern "C" {
 
 int ssdk_area(ssdk_ctx* ctx, const float* boxes, int64_t n, float* out) {
-    SSDK_TRY(ssdk_ctx_enter(ctx));
+    SSDK_ENTER(ctx);
     SSDK_REQUIRE(n >= 0 && (n == 0 || (boxes && out)), SSDK_ERR_ARG, "ssdk_area: bad arguments");
     if (n == 0) return SSDK_OK;
     area_kernel<<<ceil_div_i(n, 256), 256, 0, ctx->stream>>>((const float4*)boxes, n, out);
@@ -84,7 +84,7 @@ int ssdk_area(ssdk_ctx* ctx, const float* boxes, int64_t n, float* out) {
 }
 
 static int pairwise(ssdk_ctx* ctx, bool is_iou, const float* b1, int64_t n, const float* b2, int64_t m, float* out) {
-    SSDK_TRY(ssdk_ctx_enter(ctx));
+    SSDK_ENTER(ctx);
     SSDK_REQUIRE(n >= 0 && m >= 0, SSDK_ERR_ARG, "pairwise: negative size");
     if (n == 0 || m == 0) return SSDK_OK;
     SSDK_REQUIRE(b1 && b2 && out, SSDK_ERR_ARG, "pairwise: null pointer");
@@ -104,7 +104,7 @@ int ssdk_iou(ssdk_ctx* ctx, const float* b1, int64_t n, const float* b2, int64_t
 }
 
 static int coder(ssdk_ctx* ctx, int mode, const float* x, const float* anchors, int64_t n, int64_t A, float* out) {
-    SSDK_TRY(ssdk_ctx_enter(ctx));
+    SSDK_ENTER(ctx);
     SSDK_REQUIRE(n >= 0, SSDK_ERR_ARG, "coder: negative size");
     if (n == 0) return SSDK_OK;
     SSDK_REQUIRE(x && anchors && out, SSDK_ERR_ARG, "coder: null pointer");
@@ -128,7 +128,7 @@ int ssdk_batch_decode(ssdk_ctx* ctx, const float* codes, const float* anchors, i
 }
 
 int ssdk_localization_loss(ssdk_ctx* ctx, const float* p, const float* t, const float* w, int64_t B, int64_t A, float* out) {
-    SSDK_TRY(ssdk_ctx_enter(ctx));
+    SSDK_ENTER(ctx);
     SSDK_REQUIRE(B >= 0 && A >= 0, SSDK_ERR_ARG, "ssdk_localization_loss: negative size");
     const int64_t n = B * A;
     if (n == 0) return SSDK_OK;
@@ -140,7 +140,7 @@ int ssdk_localization_loss(ssdk_ctx* ctx, const float* p, const float* t, const 
 
 int ssdk_focal_loss(ssdk_ctx* ctx, const float* logits, const float* targets, const float* weights, int64_t B,
                     int64_t A, int C, double gamma, double alpha, float* out) {
-    SSDK_TRY(ssdk_ctx_enter(ctx));
+    SSDK_ENTER(ctx);
     SSDK_REQUIRE(B >= 0 && A >= 0 && C > 0, SSDK_ERR_ARG, "ssdk_focal_loss: bad sizes");
     const int64_t n = B * A;
     if (n == 0) return SSDK_OK;

@@ -52,7 +52,7 @@ __global__ void __launch_bounds__(32) comm_finalize_kernel(const CommPeers P, do
 extern "C" {
 
 int ssdk_comm_local_handle(ssdk_ctx* ctx, void* out_handle) {
-    SSDK_TRY(ssdk_ctx_enter(ctx));
+    SSDK_ENTER(ctx);
     SSDK_REQUIRE(out_handle != nullptr, SSDK_ERR_ARG, "ssdk_comm_local_handle: out_handle is NULL");
     static_assert(sizeof(cudaIpcMemHandle_t) == SSDK_COMM_HANDLE_BYTES, "handle size");
     ssdk_comm* c = comm_of(ctx);
@@ -72,7 +72,7 @@ int ssdk_comm_local_handle(ssdk_ctx* ctx, void* out_handle) {
 }
 
 int ssdk_comm_connect(ssdk_ctx* ctx, int rank, int world, const void* handles) {
-    SSDK_TRY(ssdk_ctx_enter(ctx));
+    SSDK_ENTER(ctx);
     ssdk_comm* c = comm_of(ctx);
     SSDK_REQUIRE(c && c->local, SSDK_ERR_ARG, "ssdk_comm_connect: call ssdk_comm_local_handle first");
     SSDK_REQUIRE(world >= 1 && world <= COMM_MAX_WORLD && rank >= 0 && rank < world && handles, SSDK_ERR_ARG,
@@ -111,7 +111,7 @@ int ssdk_comm_world(const ssdk_ctx* ctx) {
 }
 
 int ssdk_comm_all_reduce_sum(ssdk_ctx* ctx, double* values, int n) {
-    SSDK_TRY(ssdk_ctx_enter(ctx));
+    SSDK_ENTER(ctx);
     ssdk_comm* c = comm_of(ctx);
     SSDK_REQUIRE(c && c->connected, SSDK_ERR_ARG, "ssdk_comm_all_reduce_sum: not connected");
     SSDK_REQUIRE(values && n >= 1 && n <= COMM_MAX_VALUES, SSDK_ERR_ARG, "ssdk_comm_all_reduce_sum: n must be in [1,%d]", COMM_MAX_VALUES);
@@ -120,7 +120,7 @@ int ssdk_comm_all_reduce_sum(ssdk_ctx* ctx, double* values, int n) {
 }
 
 int ssdk_comm_loss_finalize(ssdk_ctx* ctx, double* sums, float* out_losses) {
-    SSDK_TRY(ssdk_ctx_enter(ctx));
+    SSDK_ENTER(ctx);
     ssdk_comm* c = comm_of(ctx);
     SSDK_REQUIRE(c && c->connected, SSDK_ERR_ARG, "ssdk_comm_loss_finalize: not connected");
     SSDK_REQUIRE(sums && out_losses, SSDK_ERR_ARG, "ssdk_comm_loss_finalize: null pointer");
@@ -129,7 +129,7 @@ int ssdk_comm_loss_finalize(ssdk_ctx* ctx, double* sums, float* out_losses) {
 }
 
 int ssdk_comm_error(ssdk_ctx* ctx, int64_t* out_epoch_of_timeout) {
-    SSDK_TRY(ssdk_ctx_enter(ctx));
+    SSDK_ENTER(ctx);
     ssdk_comm* c = comm_of(ctx);
     SSDK_REQUIRE(c && c->local && out_epoch_of_timeout, SSDK_ERR_ARG, "ssdk_comm_error: no communicator");
     SSDK_CHECK_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -141,7 +141,7 @@ int ssdk_comm_error(ssdk_ctx* ctx, int64_t* out_epoch_of_timeout) {
 
 int ssdk_comm_disconnect(ssdk_ctx* ctx) {
     if (!ctx || !ctx->comm) return SSDK_OK;
-    cudaSetDevice(ctx->device);
+    SsdkDeviceGuard dev_guard(ctx);
     ssdk_comm* c = comm_of(ctx);
     cudaStreamSynchronize(ctx->stream);
     for (int r = 0; r < COMM_MAX_WORLD; ++r)

@@ -47,13 +47,18 @@ struct ssdk_ctx {
     long long prof_calls[SSDK_K_COUNT] = {0};
     ssdk_buf ws_train;       // fused training step: per-CTA partials | ticket, forced-match deltas, per-image tickets, per-GT keys (zero between launches)
     int fused_train_step = 1;      // SSDK_OPT_FUSED_TRAIN_STEP
-    int match_ctas_per_sm = 2;     // SSDK_OPT_MATCH_CTAS_PER_SM
-    int match_flat_share_pct = 50; // SSDK_OPT_MATCH_FLAT_SHARE_PCT
+    int match_ctas_per_sm = 0;     // SSDK_OPT_MATCH_CTAS_PER_SM (0 = automatic)
+    int match_flat_share_pct = -1; // SSDK_OPT_MATCH_FLAT_SHARE_PCT (-1 = automatic)
     // tuning knobs, read from the environment ONCE (ssdk_ctx_create) and validated there; 0 = automatic
     int tune_head_ctas = 0, tune_loss_rpw = 0, tune_loss_stages = 0, tune_loss_ctas = 0;
+    unsigned long long* round_times = nullptr;   // inside ws_counts: phase timestamps of the last dense-segment rounds (ssdk_ctx_round_times)
     int* dev_err = nullptr;  // device int: sticky asynchronous error raised by a kernel (ssdk_ctx_async_error)
     void* comm = nullptr;    // peer-memory communicator (comm.cu), NULL until ssdk_comm_local_handle
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    // workspace groups (SsdkWsGuard): event recorded after the last use, the stream it was recorded on
+    cudaEvent_t ws_event[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    cudaStream_t ws_stream[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    bool ws_valid[8] = {false, false, false, false, false, false, false, false};
 };
 
 void ssdk_set_error(const char* fmt, ...);
@@ -101,14 +106,55 @@ void ssdk_prof_end(ssdk_ctx* ctx, int slot);
         if (_s != SSDK_OK) return _s;                                                      \
     } while (0)
 
-static inline int ssdk_ctx_enter(ssdk_ctx* ctx) {
-    if (!ctx) {
-        ssdk_set_error("null context");
-        return SSDK_ERR_ARG;
+// Entry guard of every API function: makes the context's device current for the duration of the call and RESTORES the
+// caller's device afterwards (a process that drives several GPUs must not find its current device switched by a library call).
+struct SsdkDeviceGuard {
+    int prev = -1;
+    int status = SSDK_OK;
+    explicit SsdkDeviceGuard(ssdk_ctx* ctx) {
+        if (!ctx) {
+            ssdk_set_error("null context");
+            status = SSDK_ERR_ARG;
+            return;
+        }
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+        if (prev != ctx->device) {
+            const cudaError_t e = cudaSetDevice(ctx->device);
+            if (e != cudaSuccess) {
+                ssdk_set_error("cudaSetDevice(%d) failed: %s", ctx->device, cudaGetErrorString(e));
+                status = SSDK_ERR_CUDA;
+                prev = -1;
+            }
+        } else {
+            prev = -1;                                      // nothing to restore
+        }
     }
-    SSDK_CHECK_CUDA(cudaSetDevice(ctx->device));
-    return SSDK_OK;
-}
+    ~SsdkDeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+    SsdkDeviceGuard(const SsdkDeviceGuard&) = delete;
+    SsdkDeviceGuard& operator=(const SsdkDeviceGuard&) = delete;
+};
+#define SSDK_ENTER(ctx)                  \
+    SsdkDeviceGuard _ssdk_dev_guard(ctx); \
+    SSDK_TRY(_ssdk_dev_guard.status)
+
+// Workspace groups: buffers inside the context that one entry point writes and a later one may reuse.  Work is enqueued on
+// whatever stream the caller set, so two calls on DIFFERENT streams could touch the same buffer concurrently.  Every entry
+// point brackets its use of a group with this guard: on entry the call's stream waits for the group's last use if that
+// was on another stream; on exit the use is recorded.  While a stream is being captured into a CUDA graph no events are
+// exchanged (a captured event cannot be waited on from outside the capture): inside a graph the caller's fork / join
+// (e.g. graph.concurrent) defines the order, and calls that share a group must not be put on parallel branches.
+enum ssdk_ws_group_id { SSDK_WS_TRAIN = 0, SSDK_WS_MATCH, SSDK_WS_LOSS, SSDK_WS_POST, SSDK_WS_STAGE, SSDK_WS_SUMM, SSDK_WS_GROUPS };
+struct SsdkWsGuard {
+    ssdk_ctx* ctx;
+    int group;
+    bool capturing = false;
+    SsdkWsGuard(ssdk_ctx* c, int g);
+    ~SsdkWsGuard();
+    SsdkWsGuard(const SsdkWsGuard&) = delete;
+    SsdkWsGuard& operator=(const SsdkWsGuard&) = delete;
+};
 
 // ----------------------------------------------------------------------------------------------
 // Parity-critical float32 arithmetic.  The reference executes one TF kernel per Python-level op,

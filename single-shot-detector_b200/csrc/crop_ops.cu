@@ -107,7 +107,7 @@ static bool aligned16(const void* p) { return ((uintptr_t)p & 15) == 0; }
 extern "C" {
 
 int ssdk_ioa(ssdk_ctx* ctx, const float* boxes1, int64_t n, const float* boxes2, int64_t m, float* out) {
-    SSDK_TRY(ssdk_ctx_enter(ctx));
+    SSDK_ENTER(ctx);
     SSDK_REQUIRE(n >= 0 && m >= 0, SSDK_ERR_ARG, "ssdk_ioa: negative size");
     if (n == 0 || m == 0) return SSDK_OK;
     SSDK_REQUIRE(boxes1 && boxes2 && out, SSDK_ERR_ARG, "ssdk_ioa: null pointer");
@@ -118,7 +118,7 @@ int ssdk_ioa(ssdk_ctx* ctx, const float* boxes1, int64_t n, const float* boxes2,
 }
 
 int ssdk_change_coordinate_frame(ssdk_ctx* ctx, const float* boxes, int64_t n, const float* window, float* out) {
-    SSDK_TRY(ssdk_ctx_enter(ctx));
+    SSDK_ENTER(ctx);
     SSDK_REQUIRE(n >= 0, SSDK_ERR_ARG, "ssdk_change_coordinate_frame: negative size");
     if (n == 0) return SSDK_OK;
     SSDK_REQUIRE(boxes && window && out, SSDK_ERR_ARG, "ssdk_change_coordinate_frame: null pointer");
@@ -140,7 +140,7 @@ static int prune_check(const char* who, const float* boxes, int64_t n, const flo
 
 int ssdk_prune_completely_outside_window(ssdk_ctx* ctx, const float* boxes, int64_t n, const float* window, float* out_boxes,
                                          int32_t* out_indices, int32_t* out_num) {
-    SSDK_TRY(ssdk_ctx_enter(ctx));
+    SSDK_ENTER(ctx);
     SSDK_TRY(prune_check("ssdk_prune_completely_outside_window", boxes, n, window, out_boxes, out_indices, out_num));
     SSDK_KERNEL(ctx, SSDK_K_OTHER,
                 prune_kernel<0><<<1, CROP_THREADS, 0, ctx->stream>>>((const float4*)boxes, nullptr, (int)n, (const float4*)window, 1, 0.0f,
@@ -150,7 +150,7 @@ int ssdk_prune_completely_outside_window(ssdk_ctx* ctx, const float* boxes, int6
 
 int ssdk_prune_non_overlapping_boxes(ssdk_ctx* ctx, const float* boxes1, int64_t n, const float* boxes2, int64_t m, double min_overlap,
                                      float* out_boxes, int32_t* out_indices, int32_t* out_num) {
-    SSDK_TRY(ssdk_ctx_enter(ctx));
+    SSDK_ENTER(ctx);
     SSDK_TRY(prune_check("ssdk_prune_non_overlapping_boxes", boxes1, n, boxes2, out_boxes, out_indices, out_num));
     SSDK_REQUIRE(m >= 1 && m <= (1 << 20), SSDK_ERR_ARG, "ssdk_prune_non_overlapping_boxes: boxes2 must hold at least one box");
     SSDK_KERNEL(ctx, SSDK_K_OTHER,
@@ -161,7 +161,7 @@ int ssdk_prune_non_overlapping_boxes(ssdk_ctx* ctx, const float* boxes1, int64_t
 
 int ssdk_crop_boxes(ssdk_ctx* ctx, const float* boxes, const int32_t* num_boxes, const float* windows, int B, int Gmax,
                     double overlap_thresh, float* out_boxes, int32_t* out_keep_indices, int32_t* out_num) {
-    SSDK_TRY(ssdk_ctx_enter(ctx));
+    SSDK_ENTER(ctx);
     SSDK_REQUIRE(B >= 0 && Gmax >= 0, SSDK_ERR_ARG, "ssdk_crop_boxes: negative size");
     if (B == 0) return SSDK_OK;
     SSDK_REQUIRE(windows && out_num && (Gmax == 0 || (boxes && out_boxes && out_keep_indices)), SSDK_ERR_ARG, "ssdk_crop_boxes: null pointer");

@@ -416,6 +416,7 @@ int ssdk_head_loss_core(ssdk_ctx* ctx, const HeadGeom& G, const float* reg_targe
                         const int32_t* matches, int B, int64_t A, int C, double gamma, double alpha, const double* num_matches,
                         const float* upstream, double* out_sums, const ssdk_head_grads* grads, bool with_grad, int phases) {
     const long long NA = (long long)B * A;
+    SsdkWsGuard ws_guard(ctx, SSDK_WS_LOSS);
     if (NA == 0) {
         if (out_sums) SSDK_CHECK_CUDA(cudaMemsetAsync(out_sums, 0, 3 * sizeof(double), ctx->stream));
         return SSDK_OK;
@@ -508,7 +509,7 @@ int ssdk_head_loss_core(ssdk_ctx* ctx, const HeadGeom& G, const float* reg_targe
 static int head_loss_impl(ssdk_ctx* ctx, const ssdk_head* head, const float* reg_targets, const int32_t* cls_targets,
                           const int32_t* matches, int B, int64_t A, int C, double gamma, double alpha, const double* num_matches,
                           const float* upstream, double* out_sums, const ssdk_head_grads* grads, bool with_grad) {
-    SSDK_TRY(ssdk_ctx_enter(ctx));
+    SSDK_ENTER(ctx);
     HeadGeom G;
     SSDK_TRY(ssdk_head_geom(head, B, A, C, true, true, &G));
     return ssdk_head_loss_core(ctx, G, reg_targets, cls_targets, matches, B, A, C, gamma, alpha, num_matches, upstream, out_sums,
@@ -536,7 +537,7 @@ int ssdk_head_ssd_targets_and_loss(ssdk_ctx* ctx, const ssdk_head* head, const f
                                    const int32_t* gt_labels, const int32_t* num_boxes, int B, int64_t A, int C, int Gmax,
                                    double positives_threshold, double negatives_threshold, double gamma, double alpha,
                                    double* out_sums, float* out_reg, int32_t* out_cls, int32_t* out_matches) {
-    SSDK_TRY(ssdk_ctx_enter(ctx));
+    SSDK_ENTER(ctx);
     HeadGeom G;
     SSDK_TRY(ssdk_head_geom(head, B, A, C, true, true, &G));
     return ssdk_train_step_impl(ctx, G, anchors, gt_boxes, gt_labels, num_boxes, B, A, C, Gmax, positives_threshold, negatives_threshold,
@@ -547,7 +548,7 @@ int ssdk_head_ssd_loss_step(ssdk_ctx* ctx, const ssdk_head* head, const float* a
                             const int32_t* gt_labels, const int32_t* num_boxes, int B, int64_t A, int C, int Gmax,
                             double positives_threshold, double negatives_threshold, double gamma, double alpha, int flags,
                             double* out_sums, float* out_losses, float* out_reg, int32_t* out_cls, int32_t* out_matches) {
-    SSDK_TRY(ssdk_ctx_enter(ctx));
+    SSDK_ENTER(ctx);
     HeadGeom G;
     SSDK_TRY(ssdk_head_geom(head, B, A, C, true, true, &G));
     return ssdk_train_step_impl(ctx, G, anchors, gt_boxes, gt_labels, num_boxes, B, A, C, Gmax, positives_threshold, negatives_threshold,
@@ -569,7 +570,7 @@ int ssdk_head_ssd_loss_forward_backward(ssdk_ctx* ctx, const ssdk_head* head, co
 }
 
 int ssdk_head_concat(ssdk_ctx* ctx, const ssdk_head* head, int B, int C, float* out_encoded_boxes, float* out_class_predictions) {
-    SSDK_TRY(ssdk_ctx_enter(ctx));
+    SSDK_ENTER(ctx);
     SSDK_REQUIRE(head != nullptr, SSDK_ERR_ARG, "ssdk_head_concat: null head descriptor");
     long long A = 0;
     for (int l = 0; l < head->num_levels && l < SSDK_MAX_LEVELS; ++l)

@@ -289,9 +289,10 @@ extern "C" {
 int ssdk_ssd_loss(ssdk_ctx* ctx, const float* logits, const float* codes, const float* reg_targets,
                   const int32_t* cls_targets, const int32_t* matches, int64_t B, int64_t A, int C, double gamma,
                   double alpha, double* out_sums, float* out_cls_losses, float* out_loc_losses) {
-    SSDK_TRY(ssdk_ctx_enter(ctx));
+    SSDK_ENTER(ctx);
     SSDK_REQUIRE(B >= 0 && A >= 0 && C > 0, SSDK_ERR_ARG, "ssdk_ssd_loss: bad sizes");
     SSDK_REQUIRE(out_sums != nullptr, SSDK_ERR_ARG, "ssdk_ssd_loss: out_sums is NULL");
+    SsdkWsGuard ws_guard(ctx, SSDK_WS_LOSS);
     const long long NA = (long long)B * A;
     if (NA == 0) {
         SSDK_CHECK_CUDA(cudaMemsetAsync(out_sums, 0, 3 * sizeof(double), ctx->stream));
@@ -352,7 +353,7 @@ int ssdk_ssd_loss(ssdk_ctx* ctx, const float* logits, const float* codes, const 
 }
 
 int ssdk_loss_finalize(ssdk_ctx* ctx, const double* sums, float* out_losses) {
-    SSDK_TRY(ssdk_ctx_enter(ctx));
+    SSDK_ENTER(ctx);
     SSDK_REQUIRE(sums && out_losses, SSDK_ERR_ARG, "ssdk_loss_finalize: null pointer");
     SSDK_KERNEL(ctx, SSDK_K_OTHER, loss_finalize_kernel<<<1, 1, 0, ctx->stream>>>(sums, out_losses));
     return SSDK_OK;

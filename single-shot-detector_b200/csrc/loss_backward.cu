@@ -345,7 +345,8 @@ extern "C" {
 int ssdk_ssd_loss_backward(ssdk_ctx* ctx, const float* logits, const float* codes, const float* reg_targets,
                            const int32_t* cls_targets, const int32_t* matches, int64_t B, int64_t A, int C, double gamma,
                            double alpha, const double* sums, const float* upstream, float* grad_logits, float* grad_codes) {
-    SSDK_TRY(ssdk_ctx_enter(ctx));
+    SSDK_ENTER(ctx);
+    SsdkWsGuard ws_guard(ctx, SSDK_WS_LOSS);
     SSDK_REQUIRE(B >= 0 && A >= 0 && C > 0, SSDK_ERR_ARG, "ssdk_ssd_loss_backward: bad sizes");
     if ((long long)B * A == 0) return SSDK_OK;
     SSDK_TRY(check_backward_args("ssdk_ssd_loss_backward", logits, codes, reg_targets, cls_targets, matches, sums, grad_logits, grad_codes));
@@ -357,7 +358,8 @@ int ssdk_ssd_loss_forward_backward(ssdk_ctx* ctx, const float* logits, const flo
                                    const int32_t* cls_targets, const int32_t* matches, int64_t B, int64_t A, int C,
                                    double gamma, double alpha, const double* num_matches, const float* upstream,
                                    double* out_sums, float* grad_logits, float* grad_codes) {
-    SSDK_TRY(ssdk_ctx_enter(ctx));
+    SSDK_ENTER(ctx);
+    SsdkWsGuard ws_guard(ctx, SSDK_WS_LOSS);
     SSDK_REQUIRE(B >= 0 && A >= 0 && C > 0 && out_sums, SSDK_ERR_ARG, "ssdk_ssd_loss_forward_backward: bad arguments");
     if ((long long)B * A == 0) {
         SSDK_CHECK_CUDA(cudaMemsetAsync(out_sums, 0, 3 * sizeof(double), ctx->stream));
@@ -370,7 +372,8 @@ int ssdk_ssd_loss_forward_backward(ssdk_ctx* ctx, const float* logits, const flo
 }
 
 int ssdk_count_matches(ssdk_ctx* ctx, const int32_t* matches, int64_t n, double* out_count) {
-    SSDK_TRY(ssdk_ctx_enter(ctx));
+    SSDK_ENTER(ctx);
+    SsdkWsGuard ws_guard(ctx, SSDK_WS_LOSS);
     SSDK_REQUIRE(n >= 0 && out_count && (n == 0 || matches), SSDK_ERR_ARG, "ssdk_count_matches: bad arguments");
     SSDK_CHECK_CUDA(cudaMemsetAsync(out_count, 0, sizeof(double), ctx->stream));
     return ssdk_count_impl(ctx, matches, n, out_count);

@@ -58,7 +58,8 @@ int ssdk_count_impl(ssdk_ctx* ctx, const int32_t* matches, int64_t n, double* ou
 int ssdk_match_impl(ssdk_ctx* ctx, const float* anchors, int64_t A, const float* gt_boxes, const int32_t* gt_labels,
                     const int32_t* num_boxes, int B, int Gmax, double pos_thr, double neg_thr, int force,
                     float* out_reg, int32_t* out_cls, int32_t* out_matches, double* out_count = nullptr) {
-    SSDK_TRY(ssdk_ctx_enter(ctx));
+    SSDK_ENTER(ctx);
+    SsdkWsGuard ws_guard(ctx, SSDK_WS_MATCH);
     SSDK_REQUIRE(pos_thr >= neg_thr, SSDK_ERR_ARG,
                  "positives_threshold (%g) must be >= negatives_threshold (%g)", pos_thr, neg_thr);  // :86
     SSDK_REQUIRE(B >= 0 && A >= 0 && Gmax >= 0, SSDK_ERR_ARG, "match: negative size");
@@ -145,7 +146,7 @@ int ssdk_training_targets(ssdk_ctx* ctx, const float* anchors, int64_t A, const 
 
 int ssdk_create_targets(ssdk_ctx* ctx, const float* anchors, int64_t A, const float* gt_boxes, const int32_t* gt_labels,
                         int B, int Gmax, const int32_t* matches, float* out_reg, int32_t* out_cls) {
-    SSDK_TRY(ssdk_ctx_enter(ctx));
+    SSDK_ENTER(ctx);
     SSDK_REQUIRE(B >= 0 && A >= 0 && Gmax >= 0 && A < (1ll << 31) && B <= 65535, SSDK_ERR_ARG, "create_targets: bad sizes");
     if (B == 0 || A == 0) return SSDK_OK;
     SSDK_REQUIRE(anchors && matches && out_reg && out_cls && (Gmax == 0 || (gt_boxes && gt_labels)), SSDK_ERR_ARG,

@@ -36,7 +36,8 @@ int ssdk_ssd_targets_and_loss(ssdk_ctx* ctx, const float* anchors, const float* 
                               int C, int Gmax, double pos_thr, double neg_thr, double gamma, double alpha, double* out_sums,
                               float* out_reg, int32_t* out_cls, int32_t* out_matches, float* out_cls_losses,
                               float* out_loc_losses) {
-    SSDK_TRY(ssdk_ctx_enter(ctx));
+    SSDK_ENTER(ctx);
+    SsdkWsGuard ws_guard(ctx, SSDK_WS_TRAIN);
     SSDK_REQUIRE(B >= 0 && A >= 0, SSDK_ERR_ARG, "ssdk_ssd_targets_and_loss: bad sizes");
     if (!out_cls_losses && !out_loc_losses && flat_path_ok(logits, codes, A, C)) {
         // no per-anchor outputs wanted: the fused training step (csrc/train_step.cu) -- matching, the flat pass over the logits and
@@ -59,7 +60,7 @@ int ssdk_ssd_loss_step(ssdk_ctx* ctx, const float* anchors, const float* logits,
                        const int32_t* gt_labels, const int32_t* num_boxes, int B, int64_t A, int C, int Gmax, double pos_thr,
                        double neg_thr, double gamma, double alpha, int flags, double* out_sums, float* out_losses, float* out_reg,
                        int32_t* out_cls, int32_t* out_matches) {
-    SSDK_TRY(ssdk_ctx_enter(ctx));
+    SSDK_ENTER(ctx);
     SSDK_REQUIRE(B >= 0 && A >= 0 && C > 0, SSDK_ERR_ARG, "ssdk_ssd_loss_step: bad sizes");
     SSDK_REQUIRE(out_sums && out_losses, SSDK_ERR_ARG, "ssdk_ssd_loss_step: out_sums / out_losses are required");
     if (flat_path_ok(logits, codes, A, C)) {
@@ -78,7 +79,8 @@ int ssdk_ssd_targets_and_loss_host(ssdk_ctx* ctx, const float* anchors, const fl
                                    const float* gt_boxes, const int32_t* gt_labels, const int32_t* num_boxes, int B, int64_t A,
                                    int C, int Gmax, double pos_thr, double neg_thr, double gamma, double alpha,
                                    double* out_sums, float* out_losses) {
-    SSDK_TRY(ssdk_ctx_enter(ctx));
+    SSDK_ENTER(ctx);
+    SsdkWsGuard ws_guard(ctx, SSDK_WS_STAGE);
     SSDK_REQUIRE(B >= 0 && A >= 0 && C > 0 && Gmax >= 0, SSDK_ERR_ARG, "ssdk_ssd_targets_and_loss_host: bad sizes");
     SSDK_REQUIRE(out_sums || out_losses, SSDK_ERR_ARG, "ssdk_ssd_targets_and_loss_host: no output requested");
     const size_t NA = (size_t)B * (size_t)A;
@@ -105,7 +107,8 @@ int ssdk_ssd_targets_and_loss_host(ssdk_ctx* ctx, const float* anchors, const fl
 int ssdk_postprocess_host(ssdk_ctx* ctx, const float* codes, const float* anchors, const float* scores, int flags, int B,
                           int64_t A, int C, double score_threshold, double iou_threshold, int K, float* out_boxes,
                           float* out_scores, int32_t* out_classes, int32_t* out_num) {
-    SSDK_TRY(ssdk_ctx_enter(ctx));
+    SSDK_ENTER(ctx);
+    SsdkWsGuard ws_guard(ctx, SSDK_WS_STAGE);
     SSDK_REQUIRE(B >= 0 && A >= 0 && C > 0 && K > 0, SSDK_ERR_ARG, "ssdk_postprocess_host: bad sizes");
     SSDK_REQUIRE(out_boxes && out_scores && out_classes && out_num, SSDK_ERR_ARG, "ssdk_postprocess_host: null output");
     const size_t NA = (size_t)B * (size_t)A, M = (size_t)B * C * K;

@@ -93,26 +93,37 @@ __device__ __forceinline__ bool is_candidate(float v, float thr, float x_lo, flo
 // A candidate takes the next slot of its (image, class) segment.  The lanes that arrive here together and target the same
 // segment (the normal case when a channels_first plane is scanned: 128 consecutive floats share image and class) share one
 // atomic; otherwise one atomic per candidate -- candidates are rare unless the scores are dense.  The counter keeps counting
-// past the region's capacity (that is how an overflow is seen), but once it is PAST the capacity nothing more is added:
-// nms_rounds_kernel re-derives such a segment from the scores, and with dense scores these atomics would otherwise all hit
-// the same few counters (13.5 ms per 8 images at the stress configuration, measured in round 1).
+// past the region's capacity (that is how an overflow is seen), but a CTA that has SEEN a segment past its capacity stops
+// adding to it (one bit per segment in shared memory: `sat`, `sat_bits` of them, indexed seg - sat_seg0): nms_rounds_kernel
+// re-derives such a segment from the scores, and with dense scores these atomics would otherwise all hit the same few
+// counters (13.5 ms per 8 images at the stress configuration, measured in round 1; re-reading the counters instead of
+// caching the verdict still took 2.6 ms: 70 M loads of the same twenty cache lines).
 __device__ __forceinline__ void append_key(unsigned long long* __restrict__ cand, int* __restrict__ seg_count, long long seg,
-                                           unsigned long long key) {
-    if (__ldcg(seg_count + seg) > SEG_CAP) return;
+                                           unsigned long long key, unsigned* sat, long long sat_seg0, int sat_bits) {
+    const long long sb = seg - sat_seg0;
+    const bool cached = sb >= 0 && sb < sat_bits;
+    if (cached) {
+        if ((sat[sb >> 5] >> (sb & 31)) & 1u) return;
+    } else if (__ldcg(seg_count + seg) > SEG_CAP) return;
     const unsigned m = __activemask();
     const int lane = threadIdx.x & 31;
     const int leader = __ffs(m) - 1;
     const long long seg_l = __shfl_sync(m, seg, leader);
-    int pos;
+    int pos, n = 1;
     if (__all_sync(m, seg == seg_l)) {
         int first = 0;
-        if (lane == leader) first = atomicAdd(seg_count + seg, __popc(m));
-        pos = __shfl_sync(m, first, leader) + __popc(m & ((1u << lane) - 1u));
+        n = __popc(m);
+        if (lane == leader) first = atomicAdd(seg_count + seg, n);
+        first = __shfl_sync(m, first, leader);
+        pos = first + __popc(m & ((1u << lane) - 1u));
+        if (first + n > SEG_CAP && cached && lane == leader) atomicOr(&sat[sb >> 5], 1u << (sb & 31));
     } else {
         pos = atomicAdd(seg_count + seg, 1);
+        if (pos >= SEG_CAP && cached) atomicOr(&sat[sb >> 5], 1u << (sb & 31));
     }
     if (pos < SEG_CAP) cand[(size_t)seg * SEG_CAP + pos] = key;
 }
+#define FILTER_SAT_WORDS 2048          // 65536 segment bits (8 KB of shared memory) cached per CTA
 
 // The streaming scan shared by both layouts: `count` floats at `base` are read once with 128-bit no-allocate loads;
 // emit(e, score) is called for every element e with score > threshold.
@@ -171,11 +182,15 @@ template <bool IS_LOGITS>
 __global__ void __launch_bounds__(FILTER_THREADS) filter_kernel(
     const float* __restrict__ scores, long long per_image /*A*C*/, int C, float thr, float x_lo, KeyFormat fmt,
     unsigned long long* __restrict__ cand, int* __restrict__ seg_count /*[B*C]*/) {
+    extern __shared__ unsigned s_sat[];                                 // one bit per class of this image: segment seen past its capacity
     const int b = blockIdx.y;
     const long long seg0 = (long long)b * C;                            // first segment of this image
+    const int sat_bits = min(C, FILTER_SAT_WORDS * 32);
+    for (int i = threadIdx.x; i < (sat_bits + 31) / 32; i += FILTER_THREADS) s_sat[i] = 0u;
+    __syncthreads();
     auto emit = [&](long long e, float s) {
         const int a = (int)(e / C), c = (int)(e - (long long)a * C);
-        append_key(cand, seg_count, seg0 + c, make_key(c, s, a, fmt));
+        append_key(cand, seg_count, seg0 + c, make_key(c, s, a, fmt), s_sat, seg0, sat_bits);
     };
     scan_candidates<IS_LOGITS>(scores + (size_t)b * per_image, per_image, thr, x_lo, emit);
 }
@@ -211,13 +226,17 @@ template <bool IS_LOGITS>
 __global__ void __launch_bounds__(FILTER_THREADS) head_filter_kernel(const HeadGeom G, int B, float thr, float x_lo, KeyFormat fmt,
                                                                     unsigned long long* __restrict__ cand,
                                                                     int* __restrict__ seg_count) {
+    extern __shared__ unsigned s_sat[];                                 // one bit per (image, class) segment (the first 65536 of them)
     const int l = blockIdx.y;
     const LevelGeom g = level_geom(G, l);
     const long long count = (long long)B * g.per_loc * g.C * g.hw;
+    const int sat_bits = (int)min((long long)B * g.C, (long long)FILTER_SAT_WORDS * 32);
+    for (int i = threadIdx.x; i < (sat_bits + 31) / 32; i += FILTER_THREADS) s_sat[i] = 0u;
+    __syncthreads();
     auto emit = [&](long long e, float s) {
         int b, a, c;
         head_decompose(g, e, b, a, c);
-        append_key(cand, seg_count, (long long)b * g.C + c, make_key(c, s, a, fmt));
+        append_key(cand, seg_count, (long long)b * g.C + c, make_key(c, s, a, fmt), s_sat, 0, sat_bits);
     };
     scan_candidates<IS_LOGITS>(G.cls[l], count, thr, x_lo, emit);
 }
@@ -580,7 +599,14 @@ struct RoundState {
     int* list_c;                   // [B]
     unsigned long long k_thr, dlo0;
     int* err;                      // the context's sticky asynchronous-error word
+    unsigned long long* times;     // [ROUND_TIMES]: [0] = rounds run, then %globaltimer (ns) at the start and after every phase of the first rounds
 };
+#define ROUND_TIMES 32
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
 
 __device__ __forceinline__ int ceil_log2_per_bin(unsigned long long width) {   // smallest s with ROUND_NB << s >= width
     const unsigned long long per = (width + ROUND_NB - 1) / ROUND_NB;
@@ -661,7 +687,10 @@ __global__ void __launch_bounds__(NMS_THREADS) nms_rounds_kernel(const HeadGeom 
     extern __shared__ __align__(16) unsigned char nms_smem[];
     __shared__ NmsShared sh;
     const int npend = R.hdr[H_PEND];
-    if (npend == 0) return;                                          // the normal case: no segment overflowed its region
+    if (npend == 0) {                                                // the normal case: no segment overflowed its region
+        if (blockIdx.x == 0 && threadIdx.x == 0) R.times[0] = 0ull;
+        return;
+    }
     const int tid = threadIdx.x, lane = tid & 31;
     const int C = N.C, K = N.K;
     const KeyFormat fmt = N.fmt;
@@ -683,7 +712,9 @@ __global__ void __launch_bounds__(NMS_THREADS) nms_rounds_kernel(const HeadGeom 
         T.shift = p;
     }
     const unsigned long long kmask = (1ull << fmt.cshift) - 1ull;
-    int epoch = 0;
+    int epoch = 0, stamp = 1;
+    auto mark = [&]() { if (cta == 0 && tid == 0 && stamp < ROUND_TIMES) R.times[stamp++] = global_timer_ns(); };
+    mark();
 
     // ---- init: every pending segment starts with a histogram over [dlo0, k_thr)
     for (int p = cta * NMS_THREADS + tid; p < npend; p += grid * NMS_THREADS) {
@@ -742,6 +773,8 @@ __global__ void __launch_bounds__(NMS_THREADS) nms_rounds_kernel(const HeadGeom 
         const int n_img_h = R.hdr[H_NIMG_H0 + par];
         const int n_hist = round == 1 ? npend : R.hdr[H_NHIST0 + par];
         if (n_hist == 0) break;                                      // uniform: written before the last barrier
+        if (cta == 0 && tid == 0) R.times[0] = (unsigned long long)round;
+        mark();
         if (cta == 0 && tid == 0) {                                  // counters the NEXT round reads, and this round's collect list
             R.hdr[H_NIMG_H0 + (par ^ 1)] = 0;
             R.hdr[H_NHIST0 + (par ^ 1)] = 0;
@@ -784,6 +817,7 @@ __global__ void __launch_bounds__(NMS_THREADS) nms_rounds_kernel(const HeadGeom 
             }
         });
         if (!grid_barrier(R.hdr, epoch)) { if (tid == 0) *R.err = SSDK_ASYNC_ROUNDS_TIMEOUT; return; }
+        mark();
 
         // ---- (2) plan: one thread per pending segment
         for (int p = cta * NMS_THREADS + tid; p < npend; p += grid * NMS_THREADS) {
@@ -835,6 +869,7 @@ __global__ void __launch_bounds__(NMS_THREADS) nms_rounds_kernel(const HeadGeom 
             for (int j = 0; j < ROUND_NB; ++j) h[j] = 0u;
         }
         if (!grid_barrier(R.hdr, epoch)) { if (tid == 0) *R.err = SSDK_ASYNC_ROUNDS_TIMEOUT; return; }
+        mark();
 
         // ---- (3) collect pass: the keys in [lo, mid) of every collecting segment -> its region
         const int n_img_c = R.hdr[H_NIMG_C];
@@ -865,6 +900,7 @@ __global__ void __launch_bounds__(NMS_THREADS) nms_rounds_kernel(const HeadGeom 
             __syncthreads();
         });
         if (!grid_barrier(R.hdr, epoch)) { if (tid == 0) *R.err = SSDK_ASYNC_ROUNDS_TIMEOUT; return; }
+        mark();
 
         // ---- (4) the segments' NMS continues over the collected keys
         for (int p = cta; p < npend; p += grid) {
@@ -896,18 +932,32 @@ __global__ void __launch_bounds__(NMS_THREADS) nms_rounds_kernel(const HeadGeom 
             }
         }
         if (!grid_barrier(R.hdr, epoch)) { if (tid == 0) *R.err = SSDK_ASYNC_ROUNDS_TIMEOUT; return; }
+        mark();
         (void)lane;
     }
 }
 
 // ---------------------------------------------------------------------------------------------- 5. pack
+// Optional extra outputs of pack_kernel: the rows of the COCO results json that inference/evaluate_on_COCO.ipynb (cell 10) builds
+// from the detector's output: boxes * [height, width, height, width] (float32), then x, y = int(xmin), int(ymin) and
+// w, h = int(xmax - xmin), int(ymax - ymin) (Python int(): truncation towards zero), category_id through the notebook's
+// integer_to_coco_id table, image_id.
+struct PackCoco {
+    const float2* image_sizes;     // [B] (height, width) in pixels; NULL = no COCO outputs
+    const int* image_ids;          // [B] or NULL (then the image's index in the batch)
+    const int* category_ids;       // [C] or NULL (then the class index)
+    int4* out_xywh;                // [B, C*K]
+    int* out_category;             // [B, C*K]
+    int* out_image;                // [B, C*K]
+};
+
 #define PACK_SLOTS_PER_BLOCK 1024
 __global__ void __launch_bounds__(256) pack_kernel(const float4* __restrict__ seg_box, const float* __restrict__ seg_score,
                                                    const int* __restrict__ seg_anchor, const int* __restrict__ seg_kept,
                                                    int C, int K, float4* __restrict__ out_boxes, float* __restrict__ out_scores,
                                                    int* __restrict__ out_classes, int* __restrict__ out_num,
                                                    int* __restrict__ out_anchor, const float4* __restrict__ box_scaler,
-                                                   float final_thr) {
+                                                   float final_thr, const PackCoco coco) {
     extern __shared__ int s_off[];   // [C+1] exclusive prefix sums of the per-class kept counts, then [C] the counts
     int* kept = s_off + C + 1;
     const int b = blockIdx.y;
@@ -965,14 +1015,80 @@ __global__ void __launch_bounds__(256) pack_kernel(const float4* __restrict__ se
             os[dst] = seg_score[src];
             oc[dst] = c;
             if (oa) oa[dst] = seg_anchor[src];
+            if (coco.image_sizes) {
+                const float2 hw = coco.image_sizes[b];
+                const float ymin = f_mul(bx.x, hw.x), xmin = f_mul(bx.y, hw.y), ymax = f_mul(bx.z, hw.x), xmax = f_mul(bx.w, hw.y);
+                coco.out_xywh[b * M + dst] = make_int4((int)xmin, (int)ymin, (int)f_sub(xmax, xmin), (int)f_sub(ymax, ymin));
+                coco.out_category[b * M + dst] = coco.category_ids ? coco.category_ids[c] : c;
+                coco.out_image[b * M + dst] = coco.image_ids ? coco.image_ids[b] : b;
+            }
         }
         if (idx >= total) {                                           // zero padding (nms.py:84-89)
             ob[idx] = make_float4(0.f, 0.f, 0.f, 0.f);
             os[idx] = 0.f;
             oc[idx] = 0;
             if (oa) oa[idx] = -1;
+            if (coco.image_sizes) {
+                coco.out_xywh[b * M + idx] = make_int4(0, 0, 0, 0);
+                coco.out_category[b * M + idx] = -1;
+                coco.out_image[b * M + idx] = -1;
+            }
         }
     }
+}
+
+// Label-major packing: the per-label detection lists the reference's evaluator keeps (metrics.py:113-123, add_detections:
+// `self.detections[label].append(get_box(box, image_name, score))` for every detection of every image in evaluation order).
+// For label c the records are image 0's kept boxes of that class (descending score), then image 1's, ...  One CTA per label;
+// the images' counts are scanned in chunks of 256.  out_* are [C, B*K] (the most a label can have), out_counts [C].
+struct PackByLabel {
+    float4* out_boxes; float* out_scores; int* out_image; int* out_counts;
+    const int* image_ids;          // [B] or NULL
+};
+__global__ void __launch_bounds__(256) pack_by_label_kernel(const float4* __restrict__ seg_box, const float* __restrict__ seg_score,
+                                                            const int* __restrict__ seg_kept, int B, int C, int K,
+                                                            const float4* __restrict__ box_scaler, float final_thr, const PackByLabel P) {
+    __shared__ int s_scan[256];
+    __shared__ int s_base;
+    const int c = blockIdx.x, tid = threadIdx.x;
+    const size_t cap = (size_t)B * K;
+    if (tid == 0) s_base = 0;
+    __syncthreads();
+    for (int b0 = 0; b0 < B; b0 += 256) {
+        const int b = b0 + tid;
+        int k = 0;
+        if (b < B) {
+            k = seg_kept[(size_t)b * C + c];
+            if (final_thr > -INFINITY) {
+                const float* sc = seg_score + ((size_t)b * C + c) * K;
+                while (k > 0 && !(sc[k - 1] > final_thr)) --k;
+            }
+        }
+        s_scan[tid] = k;
+        __syncthreads();
+        for (int o = 1; o < 256; o <<= 1) {                                  // inclusive scan (Hillis-Steele)
+            const int v = tid >= o ? s_scan[tid - o] : 0;
+            __syncthreads();
+            s_scan[tid] += v;
+            __syncthreads();
+        }
+        const int off = s_base + s_scan[tid] - k;
+        for (int j = 0; j < k; ++j) {
+            const size_t src = ((size_t)b * C + c) * K + j;
+            float4 bx = seg_box[src];
+            if (box_scaler) {
+                const float4 sc4 = box_scaler[b];
+                bx = make_float4(f_div(bx.x, sc4.x), f_div(bx.y, sc4.y), f_div(bx.z, sc4.z), f_div(bx.w, sc4.w));
+            }
+            P.out_boxes[(size_t)c * cap + off + j] = bx;
+            P.out_scores[(size_t)c * cap + off + j] = seg_score[src];
+            P.out_image[(size_t)c * cap + off + j] = P.image_ids ? P.image_ids[b] : b;
+        }
+        __syncthreads();
+        if (tid == 255) s_base += s_scan[255];
+        __syncthreads();
+    }
+    if (tid == 0) P.out_counts[c] = s_base;
 }
 
 // ---------------------------------------------------------------------------------------------- host side
@@ -983,6 +1099,12 @@ static int bits_for(long long n) {   // bits needed to represent values in [0, n
 }
 
 static bool aligned16(const void* p) { return ((uintptr_t)p & 15) == 0; }
+
+// shared memory of the filter kernels' saturation cache: one bit per segment, at most FILTER_SAT_WORDS words
+static size_t sat_bytes(long long segments) {
+    const long long bits = segments < (long long)FILTER_SAT_WORDS * 32 ? segments : (long long)FILTER_SAT_WORDS * 32;
+    return (size_t)((bits + 31) / 32) * 4 + 4;
+}
 
 HeadGeom ssdk_flat_geom(const float* logits, const float* codes, int64_t A, int C);
 
@@ -996,8 +1118,9 @@ static int postprocess_impl(ssdk_ctx* ctx, const HeadGeom* head, const float* co
                             int B, int64_t A, int C, double score_threshold, double iou_threshold, int K,
                             const float* box_scaler, double final_score_threshold,
                             float* out_boxes, float* out_scores, int32_t* out_classes, int32_t* out_num,
-                            int32_t* out_anchor_idx) {
-    SSDK_TRY(ssdk_ctx_enter(ctx));
+                            int32_t* out_anchor_idx, const PackCoco* coco = nullptr, const PackByLabel* by_label = nullptr) {
+    SSDK_ENTER(ctx);
+    ctx->round_times = nullptr;
     SSDK_REQUIRE(B >= 0 && A >= 0 && C > 0 && K > 0, SSDK_ERR_ARG, "ssdk_postprocess: bad sizes (B=%d A=%lld C=%d K=%d)", B,
                  (long long)A, C, K);
     SSDK_REQUIRE(B <= 65535, SSDK_ERR_SHAPE, "ssdk_postprocess: batch %d > 65535", B);
@@ -1005,7 +1128,8 @@ static int postprocess_impl(ssdk_ctx* ctx, const HeadGeom* head, const float* co
     SSDK_REQUIRE(iou_threshold >= 0.0 && iou_threshold <= 1.0, SSDK_ERR_ARG, "ssdk_postprocess: iou_threshold must be in [0, 1] (got %g)",
                  iou_threshold);
     if (B == 0) return SSDK_OK;
-    SSDK_REQUIRE(out_boxes && out_scores && out_classes && out_num, SSDK_ERR_ARG, "ssdk_postprocess: null output");
+    SsdkWsGuard ws_guard(ctx, SSDK_WS_POST);
+    SSDK_REQUIRE(by_label || (out_boxes && out_scores && out_classes && out_num), SSDK_ERR_ARG, "ssdk_postprocess: null output");
     const bool decoded = (flags & SSDK_BOXES_DECODED) != 0;
     const bool is_logits = (flags & SSDK_INPUT_LOGITS) != 0;
     SSDK_REQUIRE(A == 0 || head || (codes && scores), SSDK_ERR_ARG, "ssdk_postprocess: null input");
@@ -1029,8 +1153,9 @@ static int postprocess_impl(ssdk_ctx* ctx, const HeadGeom* head, const float* co
     // (zeroed every call), the queues, the per-segment NMS results, and the state of the rounds (dense segments)
     const bool may_overflow = A > SEG_CAP;                               // a segment can only overflow when there are that many anchors
     SSDK_TRY(ssdk_ensure(ctx, &ctx->ws_cand, (size_t)nseg * SEG_CAP * sizeof(unsigned long long)));
-    const size_t n_int = H_WORDS + 4 * (size_t)nseg + (may_overflow ? 5 * (size_t)nseg + 5 * (size_t)B + 4 : 0);
-    const size_t n_u64 = may_overflow ? 4 * (size_t)nseg : 0;
+    const size_t n_stamp = may_overflow ? 2 * (size_t)B : 0;             // zeroed with the header, in the same memset
+    const size_t n_int = H_WORDS + n_stamp + 4 * (size_t)nseg + (may_overflow ? 5 * (size_t)nseg + 3 * (size_t)B + 4 : 0);
+    const size_t n_u64 = may_overflow ? 4 * (size_t)nseg + ROUND_TIMES : 0;
     const size_t n_hist = may_overflow ? (size_t)nseg * ROUND_NB : 0;
     SSDK_TRY(ssdk_ensure(ctx, &ctx->ws_counts, 16 + n_u64 * 8 + (n_int + n_hist) * 4));
     const size_t seg_elems = (size_t)nseg * K;
@@ -1038,14 +1163,14 @@ static int postprocess_impl(ssdk_ctx* ctx, const HeadGeom* head, const float* co
     unsigned long long* cand = (unsigned long long*)ctx->ws_cand.p;
     unsigned long long* w64 = (unsigned long long*)ctx->ws_counts.p;
     int* hdr = (int*)(w64 + n_u64);
-    int* seg_count = hdr + H_WORDS;
+    int* seg_count = hdr + H_WORDS + n_stamp;
     int* seg_kept = seg_count + nseg;
     int* heavy_queue = seg_kept + nseg;
     int* pend_queue = heavy_queue + nseg;
     float4* seg_box = (float4*)ctx->ws_seg.p;
     float* seg_score = (float*)(seg_box + seg_elems);
     int* seg_anchor = (int*)(seg_score + seg_elems);
-    SSDK_CHECK_CUDA(cudaMemsetAsync(hdr, 0, (H_WORDS + (size_t)nseg) * sizeof(int), ctx->stream));
+    SSDK_CHECK_CUDA(cudaMemsetAsync(hdr, 0, (H_WORDS + n_stamp + (size_t)nseg) * sizeof(int), ctx->stream));
     if (per_image == 0) SSDK_CHECK_CUDA(cudaMemsetAsync(seg_kept, 0, (size_t)nseg * sizeof(int), ctx->stream));
 
     const float thr = (float)score_threshold;
@@ -1070,18 +1195,20 @@ static int postprocess_impl(ssdk_ctx* ctx, const HeadGeom* head, const float* co
             if (gx > chunks) gx = chunks;
             if (gx < 1) gx = 1;
             const dim3 hgrid_f((unsigned)gx, head->num_levels);
+            const size_t sat_head = sat_bytes(nseg);
             SSDK_KERNEL(ctx, SSDK_K_FILTER,
-                if (is_logits) head_filter_kernel<true><<<hgrid_f, FILTER_THREADS, 0, ctx->stream>>>(*head, B, thr, x_lo, fmt, cand, seg_count);
-                else head_filter_kernel<false><<<hgrid_f, FILTER_THREADS, 0, ctx->stream>>>(*head, B, thr, x_lo, fmt, cand, seg_count));
+                if (is_logits) head_filter_kernel<true><<<hgrid_f, FILTER_THREADS, sat_head, ctx->stream>>>(*head, B, thr, x_lo, fmt, cand, seg_count);
+                else head_filter_kernel<false><<<hgrid_f, FILTER_THREADS, sat_head, ctx->stream>>>(*head, B, thr, x_lo, fmt, cand, seg_count));
         } else {
             long long chunks = (per_image / 4 + FILTER_THREADS * FILTER_UNROLL - 1) / (FILTER_THREADS * FILTER_UNROLL);
             long long gx = ((long long)ctx->num_sms * 16 + B - 1) / B;
             if (gx > chunks) gx = chunks;
             if (gx < 1) gx = 1;
             const dim3 fgrid((unsigned)gx, B);
+            const size_t sat_img = sat_bytes(C);
             SSDK_KERNEL(ctx, SSDK_K_FILTER,
-                if (is_logits) filter_kernel<true><<<fgrid, FILTER_THREADS, 0, ctx->stream>>>(scores, per_image, C, thr, x_lo, fmt, cand, seg_count);
-                else filter_kernel<false><<<fgrid, FILTER_THREADS, 0, ctx->stream>>>(scores, per_image, C, thr, x_lo, fmt, cand, seg_count));
+                if (is_logits) filter_kernel<true><<<fgrid, FILTER_THREADS, sat_img, ctx->stream>>>(scores, per_image, C, thr, x_lo, fmt, cand, seg_count);
+                else filter_kernel<false><<<fgrid, FILTER_THREADS, sat_img, ctx->stream>>>(scores, per_image, C, thr, x_lo, fmt, cand, seg_count));
         }
 
         // 2.-3. NMS: one warp per small segment (<= 32 candidates, sorted with shuffles), then one CTA per queued heavy
@@ -1127,13 +1254,14 @@ static int postprocess_impl(ssdk_ctx* ctx, const HeadGeom* head, const float* co
             R.fill = ip; ip += nseg;
             R.rem = ip; ip += nseg;
             R.beyond = ip; ip += nseg;
-            R.stamp_h = ip; ip += B;
-            R.stamp_c = ip; ip += B;
+            R.stamp_h = hdr + H_WORDS;
+            R.stamp_c = R.stamp_h + B;
             R.list_h = ip; ip += 2 * (size_t)B;
             R.list_c = ip; ip += B;
             R.hist = (unsigned*)(((uintptr_t)ip + 15) & ~(uintptr_t)15);
             R.lo = w64; R.mid = w64 + nseg; R.dlo = w64 + 2 * nseg; R.dhi = w64 + 3 * nseg;
-            SSDK_CHECK_CUDA(cudaMemsetAsync(R.stamp_h, 0, 2 * (size_t)B * sizeof(int), ctx->stream));
+            R.times = w64 + 4 * nseg;
+            ctx->round_times = R.times;
             const unsigned o_thr = order_of_float(thr), o_one = order_of_float(1.0f);
             R.k_thr = (unsigned long long)o_thr << fmt.abits;            // candidates: score > thr <=> order word < o_thr
             R.err = ctx->dev_err;
@@ -1158,10 +1286,32 @@ static int postprocess_impl(ssdk_ctx* ctx, const HeadGeom* head, const float* co
         }
     }
     // 5. pack
+    if (by_label) {
+        SSDK_KERNEL(ctx, SSDK_K_PACK,
+                    pack_by_label_kernel<<<C, 256, 0, ctx->stream>>>(seg_box, seg_score, seg_kept, B, C, K, (const float4*)box_scaler,
+                                                                     (float)final_score_threshold, *by_label));
+        return SSDK_OK;
+    }
+    PackCoco pc;
+    memset(&pc, 0, sizeof(pc));
+    if (coco) pc = *coco;
     SSDK_KERNEL(ctx, SSDK_K_PACK,
                 pack_kernel<<<dim3(ceil_div_i((long long)C * K, PACK_SLOTS_PER_BLOCK), B), 256, (size_t)(2 * C + 1) * sizeof(int), ctx->stream>>>(
                     seg_box, seg_score, seg_anchor, seg_kept, C, K, (float4*)out_boxes, out_scores, out_classes, out_num,
-                    out_anchor_idx, (const float4*)box_scaler, (float)final_score_threshold));
+                    out_anchor_idx, (const float4*)box_scaler, (float)final_score_threshold, pc));
+    return SSDK_OK;
+}
+
+// Phase timestamps of the dense-segment rounds of the LAST post-processing call on this context (synchronises): out[0] = rounds
+// run (0: no segment overflowed), out[1..] = nanosecond timestamps: kernel start, after init, then per round: start, after the
+// histogram pass, after planning, after the collect pass, after the NMS phase.
+extern "C" int ssdk_ctx_round_times(ssdk_ctx* ctx, int64_t* out, int n) {
+    SSDK_ENTER(ctx);
+    SSDK_REQUIRE(out && n >= 1, SSDK_ERR_ARG, "ssdk_ctx_round_times: bad arguments");
+    for (int i = 0; i < n; ++i) out[i] = 0;
+    if (!ctx->round_times) return SSDK_OK;
+    SSDK_CHECK_CUDA(cudaStreamSynchronize(ctx->stream));
+    SSDK_CHECK_CUDA(cudaMemcpy(out, ctx->round_times, sizeof(int64_t) * (size_t)(n < ROUND_TIMES ? n : ROUND_TIMES), cudaMemcpyDeviceToHost));
     return SSDK_OK;
 }
 
@@ -1191,4 +1341,34 @@ extern "C" int ssdk_head_detect(ssdk_ctx* ctx, const ssdk_head* head, const floa
     SSDK_TRY(ssdk_head_geom(head, B, A, C, true, true, &G));
     return postprocess_impl(ctx, &G, nullptr, anchors, nullptr, flags & SSDK_INPUT_LOGITS, B, A, C, score_threshold, iou_threshold, K,
                             box_scaler, final_score_threshold, out_boxes, out_scores, out_classes, out_num, out_anchor_idx);
+}
+
+extern "C" int ssdk_detect_coco(ssdk_ctx* ctx, const float* codes, const float* anchors, const float* scores, int flags, int B,
+                                int64_t A, int C, double score_threshold, double iou_threshold, int K, const float* box_scaler,
+                                double final_score_threshold, const float* image_sizes, const int32_t* image_ids,
+                                const int32_t* category_ids, float* out_boxes, float* out_scores, int32_t* out_classes,
+                                int32_t* out_num, int32_t* out_bbox_xywh, int32_t* out_category_id, int32_t* out_image_id) {
+    SSDK_REQUIRE(box_scaler == nullptr || aligned16(box_scaler), SSDK_ERR_SHAPE, "ssdk_detect_coco: box_scaler must be 16-byte aligned");
+    SSDK_REQUIRE(image_sizes && out_bbox_xywh && out_category_id && out_image_id, SSDK_ERR_ARG, "ssdk_detect_coco: null pointer");
+    SSDK_REQUIRE(((uintptr_t)image_sizes & 7) == 0 && aligned16(out_bbox_xywh), SSDK_ERR_SHAPE,
+                 "ssdk_detect_coco: image_sizes must be 8-byte aligned, out_bbox_xywh 16-byte aligned");
+    PackCoco pc;
+    pc.image_sizes = (const float2*)image_sizes; pc.image_ids = image_ids; pc.category_ids = category_ids;
+    pc.out_xywh = (int4*)out_bbox_xywh; pc.out_category = out_category_id; pc.out_image = out_image_id;
+    return postprocess_impl(ctx, nullptr, codes, anchors, scores, flags, B, A, C, score_threshold, iou_threshold, K, box_scaler,
+                            final_score_threshold, out_boxes, out_scores, out_classes, out_num, nullptr, &pc, nullptr);
+}
+
+extern "C" int ssdk_detect_by_label(ssdk_ctx* ctx, const float* codes, const float* anchors, const float* scores, int flags, int B,
+                                    int64_t A, int C, double score_threshold, double iou_threshold, int K, const float* box_scaler,
+                                    double final_score_threshold, const int32_t* image_ids, float* out_boxes, float* out_scores,
+                                    int32_t* out_image, int32_t* out_counts) {
+    SSDK_REQUIRE(box_scaler == nullptr || aligned16(box_scaler), SSDK_ERR_SHAPE, "ssdk_detect_by_label: box_scaler must be 16-byte aligned");
+    SSDK_REQUIRE(out_boxes && out_scores && out_image && out_counts, SSDK_ERR_ARG, "ssdk_detect_by_label: null output");
+    SSDK_REQUIRE(aligned16(out_boxes), SSDK_ERR_SHAPE, "ssdk_detect_by_label: out_boxes must be 16-byte aligned");
+    PackByLabel pl;
+    pl.out_boxes = (float4*)out_boxes; pl.out_scores = out_scores; pl.out_image = out_image; pl.out_counts = out_counts;
+    pl.image_ids = image_ids;
+    return postprocess_impl(ctx, nullptr, codes, anchors, scores, flags, B, A, C, score_threshold, iou_threshold, K, box_scaler,
+                            final_score_threshold, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, &pl);
 }

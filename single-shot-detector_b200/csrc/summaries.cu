@@ -103,7 +103,8 @@ __global__ void __launch_bounds__(SUMM_THREADS) level_topk_kernel(const float* _
 extern "C" int ssdk_level_summaries(ssdk_ctx* ctx, const float* values, const int32_t* matches, int B, int64_t A,
                                     const int32_t* per_level, int num_levels, double top_fraction, float* out_topk_mean,
                                     float* out_topk_kth, float* out_matches) {
-    SSDK_TRY(ssdk_ctx_enter(ctx));
+    SSDK_ENTER(ctx);
+    SsdkWsGuard ws_guard(ctx, SSDK_WS_SUMM);
     SSDK_REQUIRE(B >= 0 && A >= 0 && num_levels >= 1 && num_levels <= 64 && per_level, SSDK_ERR_ARG, "ssdk_level_summaries: bad sizes");
     SSDK_REQUIRE(B <= 65535, SSDK_ERR_SHAPE, "ssdk_level_summaries: batch %d > 65535", B);
     SSDK_REQUIRE(top_fraction > 0.0 && top_fraction <= 1.0, SSDK_ERR_ARG, "ssdk_level_summaries: top_fraction %g not in (0,1]", top_fraction);

@@ -285,6 +285,7 @@ int ssdk_train_step_impl(ssdk_ctx* ctx, const HeadGeom& G, const float* anchors,
                          double alpha, int flags, double* out_sums, float* out_losses, float* out_reg, int32_t* out_cls,
                          int32_t* out_matches) {
     const size_t NA = (size_t)B * (size_t)A;
+    SsdkWsGuard ws_guard(ctx, SSDK_WS_TRAIN);
     SSDK_REQUIRE(out_sums != nullptr, SSDK_ERR_ARG, "targets_and_loss: out_sums is NULL");
     SSDK_REQUIRE(pos_thr >= neg_thr, SSDK_ERR_ARG, "positives_threshold (%g) must be >= negatives_threshold (%g)", pos_thr, neg_thr);
     SSDK_REQUIRE(B >= 0 && A >= 0 && Gmax >= 0 && C > 0, SSDK_ERR_ARG, "targets_and_loss: bad sizes");
@@ -343,7 +344,21 @@ int ssdk_train_step_impl(ssdk_ctx* ctx, const HeadGeom& G, const float* anchors,
     if (gx < 1) gx = 1;
     const long long items = (long long)gx * B;
     long long grid = (long long)ctx->num_sms * occ;
-    long long n_match = (long long)ctx->num_sms * ctx->match_ctas_per_sm;
+    // Role split.  Automatic (the options' defaults) from the ratio of the matching work to the streaming work per (image,
+    // anchor), both measured on a B200 with the kernels alone: matching 13.8 ps + 0.494 ps per ground-truth box (23.7 ps at
+    // G = 20, 162 ps at G = 300: ALU-bound), streaming 0.646 ps per class (4C bytes at 0.96 of the HBM peak).  m of the
+    // `occ` resident CTAs per SM start as matchers, m / occ ~ share of the matching in the total work; they finish after
+    // ~0.75 * t_match * occ / m (matching speeds up next to memory-stalled warps) and then stream for the rest of the
+    // kernel: rho = 1 - that / total is their share of the chunk list relative to a streaming CTA's.
+    const double t_match = 13.8 + 0.494 * Gmax, t_flat = 0.646 * C;
+    int m = ctx->match_ctas_per_sm;
+    if (m <= 0) {
+        m = (int)(occ * t_match / (t_match + t_flat) + 0.5);
+        if (m < 1) m = 1;
+        if (m > occ - 1) m = occ - 1;
+    }
+    if (m > occ) m = occ;
+    long long n_match = (long long)ctx->num_sms * m;
     if (n_match > items) n_match = items;
     if (n_match > grid - 1) n_match = grid - 1;
     if (n_match < 1) n_match = 1;
@@ -351,8 +366,14 @@ int ssdk_train_step_impl(ssdk_ctx* ctx, const HeadGeom& G, const float* anchors,
     if (n_flat > chunks) n_flat = chunks;
     if (n_flat < 1) n_flat = 1;
     grid = n_match + n_flat;
-    // share of the streaming given to a matcher CTA, relative to a streaming CTA's: rho; rounds_all = rho * T / (n_flat + rho * n_match)
-    const double rho = ctx->match_flat_share_pct / 100.0;
+    double rho = ctx->match_flat_share_pct / 100.0;
+    if (ctx->match_flat_share_pct < 0) {
+        const double total = 1.2 * (t_match > t_flat ? t_match : t_flat);
+        rho = 1.0 - 0.75 * t_match * occ / m / total;
+        if (rho < 0.0) rho = 0.0;
+        if (rho > 1.0) rho = 1.0;
+    }
+    // rounds in which every CTA takes a chunk: rho * T / (n_flat + rho * n_match)
     T.rounds_all = (long long)(rho * (double)chunks / ((double)n_flat + rho * (double)n_match));
     T.n_match = (int)n_match;
     T.gx = gx;

@@ -85,8 +85,26 @@ class HeadPredictions:
         _lib.check(_lib.load().ssdk_ctx_set_stream(h, torch.cuda.current_stream(dev).cuda_stream))
         return h
 
+    def _materialize_differentiable(self, key):
+        """box_predictor.py:83-102 with torch ops, so that gradients flow back to the towers when user code (auxiliary losses,
+        regularisers) indexes raw_predictions as in the reference."""
+        levels = self.class_predictions_levels if key == 'class_predictions' else self.encoded_boxes_levels
+        D = self.num_classes if key == 'class_predictions' else 4
+        parts = []
+        for t in levels:
+            if self.data_format == 'channels_first':
+                t = t.permute(0, 2, 3, 1)                                           # :84
+            parts.append(t.reshape(self.batch_size, -1, D))                         # :88-97
+        return torch.cat(parts, dim=1)                                              # :101-102
+
     def materialize(self, key):
-        """The reference's concatenated tensor for `key` (box_predictor.py:88-102), computed by ssdk_head_concat."""
+        """The reference's concatenated tensor for `key` (box_predictor.py:88-102): computed by ssdk_head_concat, or -- when a
+        level tensor requires grad -- by differentiable torch ops (the raw kernel's output would be detached from autograd)."""
+        if key not in ('class_predictions', 'encoded_boxes'):
+            raise KeyError(key)
+        levels = self.class_predictions_levels if key == 'class_predictions' else self.encoded_boxes_levels
+        if torch.is_grad_enabled() and any(t.requires_grad for t in levels):
+            return self._materialize_differentiable(key)                            # not cached: tied to the current autograd graph
         if key not in self._cache:
             B, A = self.batch_size, self.num_anchors
             d = self.descriptor()

@@ -11,7 +11,7 @@ from .._tensors import Call, ptr
 from .box_predictor import HeadPredictions
 from .constants import MIN_LEVEL, NEGATIVES_THRESHOLD, POSITIVES_THRESHOLD  # noqa: F401
 from .training_target_creation import batch_training_targets
-from .utils.nms import batch_multiclass_non_max_suppression
+from .utils.nms import batch_coco_detections, batch_detections_by_label, batch_multiclass_non_max_suppression
 
 
 _UPSTREAM_CACHE = {}
@@ -42,11 +42,13 @@ class _SSDLossFunction(torch.autograd.Function):
         losses = head._loss_forward(groundtruth, params, keep_targets=True)
         ctx.head = head
         ctx.saved = head._saved
+        ctx.save_for_backward(logits, codes)          # autograd's version check: an in-place edit before backward() raises
         return torch.stack([losses['localization_loss'], losses['classification_loss']])
 
     @staticmethod
     def backward(ctx, grad_out):
         head = ctx.head
+        _ = ctx.saved_tensors                         # raises if logits / codes were modified in place since forward()
         head._saved = ctx.saved
         grads = head.loss_backward(grad_out.contiguous())
         return grads['class_predictions'], grads['encoded_boxes'], None, None, None
@@ -60,11 +62,13 @@ class _SSDHeadLossFunction(torch.autograd.Function):
         losses = head._loss_forward(groundtruth, params, keep_targets=True)
         ctx.head = head
         ctx.saved = head._saved
+        ctx.save_for_backward(*levels)                # autograd's version check: an in-place edit before backward() raises
         return torch.stack([losses['localization_loss'], losses['classification_loss']])
 
     @staticmethod
     def backward(ctx, grad_out):
         head = ctx.head
+        _ = ctx.saved_tensors                         # raises if a level tensor was modified in place since forward()
         head._saved = ctx.saved
         grads = head.loss_backward(grad_out.contiguous())
         return (None, None, None) + tuple(grads['class_predictions']) + tuple(grads['encoded_boxes'])
@@ -218,6 +222,40 @@ class SSD:
                                  final_score_threshold=score_threshold)
         n = int(p['num_boxes'][0])
         return p['boxes'][0, :n], p['labels'][0, :n], p['scores'][0, :n]
+
+    def _flat_predictions(self):
+        """(encoded_boxes [B,A,4], class_predictions [B,A,C]) -- materialised from the per-level tensors if need be."""
+        raw = self.raw_predictions
+        return raw['encoded_boxes'], raw['class_predictions']
+
+    def detections_by_label(self, score_threshold=0.05, iou_threshold=0.5, max_boxes_per_class=20, box_scaler=None,
+                            final_score_threshold=None, image_ids=None):
+        """What the reference's evaluator accumulates from get_predictions (metrics.py:113-123, add_detections): for every label the
+        list of (image, box, score) records over the images of the batch in order, each image's boxes in descending score.
+        Returns {label: {'image': int [n], 'boxes': [n,4], 'scores': [n]}} (labels without detections are absent)."""
+        codes, logits = self._flat_predictions()
+        boxes, scores, image, counts = batch_detections_by_label(
+            codes, self.anchors, logits, score_threshold, iou_threshold, max_boxes_per_class, scores_are_logits=True,
+            box_scaler=box_scaler, final_score_threshold=final_score_threshold, image_ids=image_ids)
+        cnt = counts.cpu().numpy() if isinstance(counts, torch.Tensor) else counts        # data dependent sizes: one host read
+        return {int(c): {'image': image[c, :n], 'boxes': boxes[c, :n], 'scores': scores[c, :n]} for c, n in enumerate(cnt) if n > 0}
+
+    def coco_results(self, image_sizes, image_ids=None, category_ids=None, score_threshold=0.15, nms_score_threshold=0.05,
+                     iou_threshold=0.5, max_boxes_per_class=20, box_scaler=None):
+        """The `results` list of inference/evaluate_on_COCO.ipynb (cell 10) for a batch: one dict per detection with score >
+        score_threshold -- {"image_id", "category_id", "bbox": [x, y, w, h] (ints, pixels), "score"} -- ready for json.dump.
+        image_sizes [B,2] = (height, width); category_ids [C] = the notebook's integer_to_coco_id."""
+        codes, logits = self._flat_predictions()
+        out = batch_coco_detections(codes, self.anchors, logits, image_sizes, nms_score_threshold, iou_threshold, max_boxes_per_class,
+                                    scores_are_logits=True, box_scaler=box_scaler, final_score_threshold=score_threshold,
+                                    image_ids=image_ids, category_ids=category_ids)
+        _, scores, _, num, xywh, cat, img = [t.cpu().numpy() if isinstance(t, torch.Tensor) else t for t in out]
+        results = []
+        for b in range(len(num)):
+            for i in range(int(num[b])):
+                results.append({'image_id': int(img[b, i]), 'category_id': int(cat[b, i]), 'bbox': [int(v) for v in xywh[b, i]],
+                                'score': float(scores[b, i])})
+        return results
 
     # ------------------------------------------------------------------ training (ssd.py:71-133)
     def loss_sums(self, groundtruth, params, per_anchor=False, keep_targets=False):

@@ -350,3 +350,64 @@ def test_head_c_abi_argument_errors(pkg):
     assert lib.ssdk_head_ssd_loss(ctx, None, reg.data_ptr(), cls.data_ptr(), mat.data_ptr(), 1, 8, 3, 2.0, 0.25, sums.data_ptr()) == -1
     assert lib.ssdk_head_detect(ctx, ctypes.byref(desc()), None, 1, 1, 8, 3, 0.05, 0.5, 10, None, float('-inf'), None, None, None, None,
                                 None) == -1
+
+
+def test_raw_predictions_stay_differentiable_and_inplace_edits_are_caught(pkg, syn):
+    """ADVICE (round 1): user code that indexes raw_predictions as in the reference (auxiliary losses, regularisers) must get
+    gradients back to the towers -- the lazily materialised tensors come from differentiable torch ops when a level requires
+    grad -- and an in-place edit of a head tensor between SSD.loss() and backward() must raise (save_for_backward)."""
+    torch.manual_seed(0)
+    B, C, n = 2, 5, 6
+    lv_cls = [torch.randn([B, n * C, h, w], device='cuda', requires_grad=True) for h, w in ((4, 5), (2, 3))]
+    lv_box = [torch.randn([B, n * 4, h, w], device='cuda', requires_grad=True) for h, w in ((4, 5), (2, 3))]
+    head = pkg.reshape_and_concatenate(lv_box, lv_cls, C, n)
+    cp, eb = head['class_predictions'], head['encoded_boxes']
+    assert cp.requires_grad and eb.requires_grad and cp.shape == (B, (20 + 6) * n, C)
+    (cp.square().sum() + eb.sum()).backward()
+    for t in lv_cls:
+        assert torch.allclose(t.grad, 2 * t.detach())
+    for t in lv_box:
+        assert torch.equal(t.grad, torch.ones_like(t))
+    # same values as the kernel path (no grad): ssdk_head_concat
+    with torch.no_grad():
+        plain = pkg.reshape_and_concatenate([t.detach() for t in lv_box], [t.detach() for t in lv_cls], C, n, lazy=False)
+    assert torch.equal(plain['class_predictions'], cp.detach()) and torch.equal(plain['encoded_boxes'], eb.detach())
+    # in-place edit between forward and backward
+    c = _case(pkg, syn, 64, 96, 4, 2, 3, seed=4)
+    lvl_c = [cuda(t).requires_grad_(True) for t in c['lv_classes']]
+    lvl_b = [cuda(t).requires_grad_(True) for t in c['lv_boxes']]
+    ssd = pkg.SSD.from_head_outputs(c['H'], c['W'], lvl_b, lvl_c, c['gen'], c['C'])
+    dgt = {k: cuda(v) for k, v in c['gt'].items()}
+    res = ssd.loss(dgt, {'gamma': 2.0, 'alpha': 0.25})
+    with torch.no_grad():
+        lvl_c[0].add_(1.0)
+    with pytest.raises(RuntimeError):
+        (res['classification_loss'] + res['localization_loss']).backward()
+
+
+def test_two_streams_share_one_context_safely(pkg, syn):
+    """ADVICE (round 1): the library keeps one context per (thread, device) and re-points its stream per call; workspaces are
+    shared.  A prefetching SSD.assign_targets on a side stream next to SSD.loss() on the main stream (the pattern the docstring
+    recommends), and the same entry point issued from two streams back to back, must give the single-stream results."""
+    c = _case(pkg, syn, 128, 160, 6, 3, 5, seed=6)
+    params = {'gamma': 2.0, 'alpha': 0.25}
+    ssd = _head_ssd(pkg, c)
+    c['dgt'] = {k: cuda(v) for k, v in c['gt'].items()}
+    want = ssd.loss(c['dgt'], params)
+    want_t = pkg.SSD.assign_targets(ssd.anchors, c['dgt'])
+    torch.cuda.synchronize()
+    side, side2 = torch.cuda.Stream(), torch.cuda.Stream()
+    for _ in range(20):
+        with torch.cuda.stream(side):
+            t1 = pkg.SSD.assign_targets(ssd.anchors, c['dgt'])
+        got = ssd.loss(c['dgt'], params)
+        with torch.cuda.stream(side2):
+            t2 = pkg.SSD.assign_targets(ssd.anchors, c['dgt'])
+            got2 = ssd.loss(c['dgt'], params)
+        torch.cuda.synchronize()
+        for t in (t1, t2):
+            assert torch.equal(t['matches'], want_t['matches']) and torch.equal(t['reg_targets'], want_t['reg_targets'])
+            assert t['count'].item() == want_t['count'].item()
+        for g in (got, got2):
+            assert float(g['classification_loss']) == float(want['classification_loss'])
+            assert float(g['localization_loss']) == float(want['localization_loss'])

@@ -693,7 +693,7 @@ def test_concurrent_subpaths_and_options(pkg, golden):
     L = pkg._lib
     want_n = float(ssd.num_matches)
     try:
-        for opt, val in ((L.SSDK_OPT_FUSED_TRAIN_STEP, 0), (L.SSDK_OPT_MATCH_CTAS_PER_SM, 1), (L.SSDK_OPT_MATCH_CTAS_PER_SM, 4),
+        for opt, val in ((L.SSDK_OPT_FUSED_TRAIN_STEP, 0), (L.SSDK_OPT_MATCH_CTAS_PER_SM, 1), (L.SSDK_OPT_MATCH_CTAS_PER_SM, 5),
                          (L.SSDK_OPT_MATCH_FLAT_SHARE_PCT, 0), (L.SSDK_OPT_MATCH_FLAT_SHARE_PCT, 100)):
             L.set_option(opt, val)
             l0 = ssd.loss(gt, params)
@@ -701,14 +701,14 @@ def test_concurrent_subpaths_and_options(pkg, golden):
             close(float(l0['classification_loss']), float(want_l['classification_loss']), rtol=1e-7)
             close(float(l0['localization_loss']), float(want_l['localization_loss']), rtol=1e-7)
             L.set_option(L.SSDK_OPT_FUSED_TRAIN_STEP, 1)
-            L.set_option(L.SSDK_OPT_MATCH_CTAS_PER_SM, 2)
-            L.set_option(L.SSDK_OPT_MATCH_FLAT_SHARE_PCT, 50)
+            L.set_option(L.SSDK_OPT_MATCH_CTAS_PER_SM, 0)
+            L.set_option(L.SSDK_OPT_MATCH_FLAT_SHARE_PCT, -1)
         with pytest.raises(ValueError):
             L.set_option(L.SSDK_OPT_MATCH_CTAS_PER_SM, 9)
     finally:
         L.set_option(L.SSDK_OPT_FUSED_TRAIN_STEP, 1)
-        L.set_option(L.SSDK_OPT_MATCH_CTAS_PER_SM, 2)
-        L.set_option(L.SSDK_OPT_MATCH_FLAT_SHARE_PCT, 50)
+        L.set_option(L.SSDK_OPT_MATCH_CTAS_PER_SM, 0)
+        L.set_option(L.SSDK_OPT_MATCH_FLAT_SHARE_PCT, -1)
     both = pkg.graph.concurrent(lambda: ssd.loss(gt, params), lambda: ssd.get_predictions(0.05, 0.5, 10))
     for run in (both, pkg.graph.capture(both).replay):
         for _ in range(3):
@@ -780,3 +780,89 @@ def test_plain_c_program_end_to_end(pkg, tmp_path):
     gen = pkg.AnchorGenerator(scale_multipliers=[1.0, 2 ** (1 / 3), 2 ** (2 / 3)])
     first = gen(640, 896)[0].cpu().numpy()
     assert ('first anchor [%.6f %.6f %.6f %.6f]' % tuple(first)) in r.stdout
+
+
+# ------------------------------------------------------------------------------------------------ post-path consumers (f3)
+def _add_detections_transcription(num_classes, per_image):
+    """NumPy transcription of the reference evaluator's bookkeeping (metrics.py:103-123): `initialize` makes one list per label,
+    `add_detections(image_name, boxes, labels, scores)` appends get_box(box, image_name, score) to self.detections[label] for
+    every detection, images in evaluation order."""
+    detections = {label: [] for label in range(num_classes)}                       # :103-105
+    for image_name, boxes, labels, scores in per_image:
+        for box, label, score in zip(boxes, labels, scores):                       # :121-123
+            ymin, xmin, ymax, xmax = box                                           # get_box :133-141
+            detections[int(label)].append({'ymin': ymin, 'xmin': xmin, 'ymax': ymax, 'xmax': xmax,
+                                           'image_name': image_name, 'confidence': score})
+    return detections
+
+
+def test_detections_by_label_and_coco_rows(pkg, golden):
+    """the detection formats consumed after get_predictions -- the evaluator's per-label lists
+    (metrics.py:113-123) and the COCO results rows of inference/evaluate_on_COCO.ipynb cell 10 -- come out of pack-kernel variants;
+    checked against NumPy transcriptions fed with the ORACLE's detections."""
+    from oracle import ssd as ossd
+    g = golden('postprocess')
+    H, W = [int(v) for v in g['HW']]
+    C = int(g['C'])
+    codes, logits, anchors = g['codes'], g['logits'], g['anchors']
+    B = codes.shape[0]
+    K, thr_final = 10, 0.15
+    ssd = _ssd(pkg, H, W, [1.0, 1.4142], logits, codes, C)
+    o = ossd.get_predictions(anchors, codes, logits, 0.05, 0.5, K)
+    image_ids = np.array([1000 + 7 * b for b in range(B)], np.int32)
+    # ---- per-label lists
+    per_image = []
+    for b in range(B):
+        n = int(o['num_boxes'][b])
+        per_image.append((int(image_ids[b]), o['boxes'][b, :n], o['labels'][b, :n], o['scores'][b, :n]))
+    want = _add_detections_transcription(C, per_image)
+    got = ssd.detections_by_label(0.05, 0.5, K, image_ids=cuda(image_ids))
+    assert sorted(got.keys()) == [c for c in range(C) if want[c]] and len(got) > 1
+    for c, rec in got.items():
+        w = want[c]
+        assert [int(v) for v in rec['image'].cpu().numpy()] == [r['image_name'] for r in w]
+        close(rec['scores'].cpu().numpy(), np.array([r['confidence'] for r in w], np.float32), atol=1e-9)
+        close(rec['boxes'].cpu().numpy(), np.array([[r['ymin'], r['xmin'], r['ymax'], r['xmax']] for r in w], np.float32), atol=1e-7)
+    # with the final threshold of the exported detector (inference/detector.py:54-58) and a box scaler (model.py:67-68)
+    scaler = np.array([[1.0, 0.8, 1.0, 0.8]] * B, np.float32)
+    got2 = ssd.detections_by_label(0.05, 0.5, K, box_scaler=cuda(scaler), final_score_threshold=thr_final)
+    per_image2 = []
+    for b in range(B):
+        n = int(o['num_boxes'][b])
+        keep = o['scores'][b, :n] > np.float32(thr_final)
+        per_image2.append((b, (o['boxes'][b, :n] / scaler[b])[keep], o['labels'][b, :n][keep], o['scores'][b, :n][keep]))
+    want2 = _add_detections_transcription(C, per_image2)
+    assert sorted(got2.keys()) == [c for c in range(C) if want2[c]]
+    for c, rec in got2.items():
+        assert [int(v) for v in rec['image'].cpu().numpy()] == [r['image_name'] for r in want2[c]]
+        close(rec['boxes'].cpu().numpy(), np.array([[r['ymin'], r['xmin'], r['ymax'], r['xmax']] for r in want2[c]], np.float32), atol=1e-7)
+    # ---- COCO rows: transcription of the notebook's loop body
+    sizes = np.array([[480.0, 640.0], [375.0, 500.0], [600.0, 431.0]], np.float32)[:B] if B <= 3 else np.tile(np.array([[480.0, 640.0]], np.float32), [B, 1])
+    integer_to_coco_id = np.array([3 * c + 1 for c in range(C)], np.int32)
+    rows = ssd.coco_results(cuda(sizes), image_ids=cuda(image_ids), category_ids=cuda(integer_to_coco_id), score_threshold=thr_final,
+                            max_boxes_per_class=K)
+    want_rows = []
+    for b in range(B):
+        n = int(o['num_boxes'][b])
+        keep = o['scores'][b, :n] > np.float32(thr_final)                              # detector(image, score_threshold=0.15)
+        boxes, labels, scores = o['boxes'][b, :n][keep], o['labels'][b, :n][keep], o['scores'][b, :n][keep]
+        height, width = sizes[b]
+        scaler_ = np.array([height, width, height, width], dtype='float32')
+        boxes = boxes * scaler_
+        for i in range(len(boxes)):
+            ymin, xmin, ymax, xmax = boxes[i]
+            x, y = int(xmin), int(ymin)
+            w, h = int(xmax - xmin), int(ymax - ymin)
+            want_rows.append({'image_id': int(image_ids[b]), 'category_id': int(integer_to_coco_id[labels[i]]),
+                              'bbox': [x, y, w, h], 'score': float(scores[i])})
+    assert len(rows) == len(want_rows) and len(rows) > 5
+    mism = 0
+    for r, w in zip(rows, want_rows):
+        assert r['image_id'] == w['image_id'] and r['category_id'] == w['category_id']
+        assert abs(r['score'] - w['score']) <= 1e-6 * abs(w['score'])
+        # decoded boxes agree to 1e-5 relative (exp ulps): an integer truncation may flip when a coordinate sits on a pixel edge
+        mism += sum(1 for u, v in zip(r['bbox'], w['bbox']) if u != v)
+        assert all(abs(u - v) <= 1 for u, v in zip(r['bbox'], w['bbox']))
+    assert mism <= max(1, len(rows) // 50)
+    import json
+    json.dumps(rows)
