@@ -80,14 +80,14 @@ out['cfg2_check'] = {k: float(v) for k, v in ref.items()}
 ms = timeit(lambda: ssd.loss(gt, params))
 out['train_fused_default'] = {'ms': ms, 'frac_of_roofline': frac(b_train, ms)}
 sweep = {}
-for ctas in ([1, 2, 3] if not args.quick else [2]):
-    for share in ([0, 25, 50, 75, 100] if not args.quick else [50]):
+for ctas in ([2, 3] if not args.quick else [2]):
+    for share in ([10, 20, 30, 40, 50, 60] if not args.quick else [50]):
         L.set_option(L.SSDK_OPT_MATCH_CTAS_PER_SM, ctas)
         L.set_option(L.SSDK_OPT_MATCH_FLAT_SHARE_PCT, share)
         ms = timeit(lambda: ssd.loss(gt, params))
         sweep['ctas%d_share%d' % (ctas, share)] = round(ms, 5)
-L.set_option(L.SSDK_OPT_MATCH_CTAS_PER_SM, 2)
-L.set_option(L.SSDK_OPT_MATCH_FLAT_SHARE_PCT, 50)
+L.set_option(L.SSDK_OPT_MATCH_CTAS_PER_SM, 0)
+L.set_option(L.SSDK_OPT_MATCH_FLAT_SHARE_PCT, -1)
 out['train_fused_sweep_ms'] = sweep
 best = min(sweep, key=sweep.get)
 out['train_fused_best'] = {'knobs': best, 'ms': sweep[best], 'frac_of_roofline': frac(b_train, sweep[best])}
@@ -184,11 +184,21 @@ for _ in range(5):
 prof = L.profile_read()
 L.set_profiling(False)
 ms_t = timeit(lambda: s5.loss(gt5, params), reps=10)
+sweep5 = {}
+for ctas in ([3, 4, 5] if not args.quick else []):
+    for share in [0, 25, 50]:
+        L.set_option(L.SSDK_OPT_MATCH_CTAS_PER_SM, ctas)
+        L.set_option(L.SSDK_OPT_MATCH_FLAT_SHARE_PCT, share)
+        sweep5['ctas%d_share%d' % (ctas, share)] = round(timeit(lambda: s5.loss(gt5, params), reps=10), 5)
+L.set_option(L.SSDK_OPT_MATCH_CTAS_PER_SM, 0)
+L.set_option(L.SSDK_OPT_MATCH_FLAT_SHARE_PCT, -1)
+rt = L.round_times()
 ms_fb = timeit(lambda: s5.loss_with_gradients(gt5, params), reps=10)
 ms_m = timeit(lambda: pkg.SSD.assign_targets(anc5, gt5), reps=10)
 out['stress'] = {'postprocess_dense_ms': ms_pp, 'postprocess_kernels_ms': {k: v[0] / 5 for k, v in prof.items() if v[1]},
                  'postprocess_frac_of_roofline': frac((4 * A * C + 32 * A + 24 * C * 100 + 4) * B, ms_pp),
                  'detections_image0': int(p5['num_boxes'][0]), 'async_error': L.async_error(),
-                 'train_forward_ms': ms_t, 'train_forward_backward_ms': ms_fb, 'matcher_alone_ms': ms_m,
+                 'train_forward_sweep_ms': sweep5, 'round_times_ms': [round((rt[i + 1] - rt[i]) * 1e-6, 4) for i in range(1, 8)] if rt[0] else None,
+                 'rounds': rt[0], 'train_forward_ms': ms_t, 'train_forward_backward_ms': ms_fb, 'matcher_alone_ms': ms_m,
                  'matcher_iou_pairs_per_s': B * G * A / (ms_m * 1e-3)}
 print(json.dumps(out))
