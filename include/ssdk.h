@@ -73,7 +73,7 @@ SSDK_API int64_t ssdk_ctx_launch_count(const ssdk_ctx* ctx);
 /* Optional per-kernel timing with CUDA events on the context's stream (for bench.py's roofline line; adds two
  * event records per kernel while enabled).  ssdk_ctx_profile_read synchronises the stream and returns, per kernel
  * id, the accumulated milliseconds and launch counts since the last reset.  Ids: 0 anchors, 1 match,
- * 2 force_match, 3 ssd_loss, 4 loss_reduce (unused), 5 filter, 6 sort (unused: segments are sorted inside the NMS kernels),
+ * 2 force_match, 3 ssd_loss, 4 loss_reduce (unused), 5 filter, 6 filter_dense (images with dense scores, redone with per-tile aggregation),
  * 7 nms, 8 pack, 9 other, 10 ssd_loss_backward,
  * 11 head_flat (flat focal pass over the per-level head tensors), 12 head_rows (matched / ignored anchors), 13 head_concat,
  * 14 comm (peer-memory all-reduce), 15 train_step (the fused training step), 16 nms_rounds (dense / overflowing segments). */

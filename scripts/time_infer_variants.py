@@ -1,0 +1,43 @@
+"""Graph-replay time of the inference sub-path (cfg3) for the library build named by SSDK_LIB; one JSON line."""
+import importlib, json, os, sys
+import numpy as np, torch
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+pkg = importlib.import_module('single-shot-detector_b200')
+syn = importlib.import_module('single-shot-detector_b200.synthetic')
+L = pkg._lib
+cfg = syn.CONFIGS[3]
+H, W, C, B, G = cfg['H'], cfg['W'], cfg['C'], cfg['B'], cfg['G']
+gen = pkg.AnchorGenerator(scale_multipliers=cfg['scale_multipliers'])
+anchors = gen(H, W)
+A = anchors.shape[0]
+g = torch.Generator(device='cuda').manual_seed(2)
+ilog = torch.randn([B, A, C], device='cuda', generator=g) - 7.0
+igt = syn.make_groundtruth(3, B, G, H, W, C)
+anc_np = anchors.cpu().numpy()
+for b in range(B):
+    sim = syn._pair_iou(igt['boxes'][b], anc_np)
+    for gi in range(G):
+        idx = torch.from_numpy(np.nonzero(sim[gi] >= 0.4)[0]).cuda()
+        ilog[b, idx, int(igt['labels'][b, gi])] = 1.5 + 1.5 * torch.randn([idx.numel()], device='cuda', generator=g)
+icod = torch.randn([B, A, 4], device='cuda', generator=g)
+issd = pkg.SSD.from_predictions(H, W, {'encoded_boxes': icod, 'class_predictions': ilog}, gen, C)
+fn = lambda: issd.get_predictions(0.05, 0.5, 100)
+cap = pkg.graph.capture(fn, warmup=3)
+best = 1e9
+for _ in range(5):
+    for _ in range(3):
+        cap.replay()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(50):
+        cap.replay()
+    e1.record(); torch.cuda.synchronize()
+    best = min(best, e0.elapsed_time(e1) / 50)
+L.set_profiling(True); L.profile_read()
+for _ in range(20):
+    fn()
+prof = L.profile_read(); L.set_profiling(False)
+print(json.dumps({'lib': os.environ.get('SSDK_LIB', 'default'), 'infer_graph_ms': round(best, 5),
+                  'kernels_ms': {k: round(v[0] / 20, 5) for k, v in prof.items() if v[1]}, 'launches_per_replay': cap.launches_per_replay}))

@@ -149,7 +149,7 @@ def context(device_index):
     return ctx
 
 
-KERNEL_IDS = ['anchors', 'match', 'force_match', 'ssd_loss', 'loss_reduce', 'filter', 'sort', 'nms', 'pack', 'other',
+KERNEL_IDS = ['anchors', 'match', 'force_match', 'ssd_loss', 'loss_reduce', 'filter', 'filter_dense', 'nms', 'pack', 'other',
               'ssd_loss_backward', 'head_flat', 'head_rows', 'head_concat', 'comm', 'train_step', 'nms_rounds']
 
 

@@ -48,7 +48,7 @@
 #define NMS_CH 64                    // candidates per chunk
 #define NMS_TPC (NMS_THREADS / NMS_CH)  // threads per candidate (a power of two <= 32)
 #define ROUND_NB 64                  // histogram bins per round
-#define ROUND_WANT 1024              // a round collects at least this many keys (if that many are left) and at most SEG_CAP
+#define ROUND_WANT 512               // a round collects at least this many keys (if that many are left) and at most SEG_CAP
 #define ROUND_SMEM_MAX_C 320         // classes up to which the rounds keep their per-class tables / histograms in shared memory
 
 struct KeyFormat {
@@ -125,11 +125,111 @@ __device__ __forceinline__ void append_key(unsigned long long* __restrict__ cand
 }
 #define FILTER_SAT_WORDS 2048          // 65536 segment bits (8 KB of shared memory) cached per CTA
 
+// One level of a HeadGeom by value, and the index arithmetic that recovers (image, anchor, class) from a flat element index.
+// Exact division of 32-bit numerators by a runtime constant: q = mulhi64(n, floor(2^64 / d) + 1) (round-up method: exact for
+// every n < 2^32).  The candidate paths recover (anchor, class) from a flat element index with these; with dense scores
+// every element is a candidate, and a 64-bit hardware-emulated division per element was half of the filter's instructions.
+struct FastDiv {
+    unsigned d;
+    unsigned long long m;
+};
+__host__ __device__ __forceinline__ FastDiv fast_div(unsigned d) {
+    FastDiv f;
+    f.d = d ? d : 1u;
+    f.m = f.d == 1u ? 0ull : (~0ull / f.d) + 1ull;
+    return f;
+}
+__device__ __forceinline__ unsigned div_fast(unsigned n, const FastDiv f) {
+    return f.d == 1u ? n : (unsigned)__umul64hi((unsigned long long)n, f.m);
+}
+
+struct LevelGeom {        // one level of a HeadGeom, by value
+    int hw, per_loc, C, channels_first, anchor_off;
+    FastDiv d_hw, d_nc, d_c, d_img;     // by hw, per_loc * C, C, per_loc * C * hw
+};
+__host__ __device__ __forceinline__ LevelGeom level_geom(const HeadGeom& G, int l) {
+    LevelGeom g;
+    g.hw = G.hw[l]; g.per_loc = G.per_loc; g.C = G.C; g.channels_first = G.channels_first; g.anchor_off = G.anchor_off[l];
+    g.d_hw = fast_div((unsigned)g.hw); g.d_nc = fast_div((unsigned)(g.per_loc * g.C)); g.d_c = fast_div((unsigned)g.C);
+    g.d_img = fast_div((unsigned)(g.per_loc * g.C * g.hw));
+    return g;
+}
+// element r of ONE image's block of a level -> (anchor, class)
+__device__ __forceinline__ void level_decompose(const LevelGeom g, int r, int& a, int& c) {
+    const int hw = g.hw, n = g.per_loc, C = g.C;
+    int loc, q;
+    if (g.channels_first) { q = (int)div_fast((unsigned)r, g.d_hw); loc = r - q * hw; }
+    else { loc = (int)div_fast((unsigned)r, g.d_nc); q = r - loc * (n * C); }
+    const int k = (int)div_fast((unsigned)q, g.d_c);
+    c = q - k * C;
+    a = g.anchor_off + loc * n + k;
+}
+// element e of a level's whole tensor [B, ...] -> (image, anchor, class); the tensor holds < 2^31 elements per image and the
+// image index is found with one 64-bit division only when the tensor itself is larger than 2^32 elements
+__device__ __forceinline__ void head_decompose(const LevelGeom g, long long e, int& b, int& a, int& c) {
+    const long long per_image = (long long)g.per_loc * g.C * g.hw;
+    if (e < (1ll << 32)) b = (int)div_fast((unsigned)e, g.d_img);
+    else b = (int)(e / per_image);
+    level_decompose(g, (int)(e - (long long)b * per_image), a, c);
+}
+
+// Everything a candidate needs to find its segment, by value in shared memory (one copy per CTA).
+#ifndef FILTER_MIN_CTAS
+#define FILTER_MIN_CTAS 4              // at most 64 registers
+#endif
+struct FilterEmit {
+    unsigned long long* cand;
+    int* seg_count;
+    long long seg0;            // anchor-major: first segment of the CTA's image
+    long long sat_seg0;
+    int sat_bits;
+    int C;
+    int head;                  // 1: `g` describes the level scanned (element -> image, anchor, class through head_decompose)
+    KeyFormat fmt;
+    LevelGeom g;
+    float thr, x_lo;
+};
+
+// Four consecutive elements starting at element e0, at least one of which may be a candidate.
+template <bool IS_LOGITS, bool HEAD>
+__device__ __forceinline__ void filter_group(const FilterEmit* __restrict__ E, unsigned* sat, const float4 v, long long e0) {
+    const float vals[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        float sc;
+        if (!is_candidate<IS_LOGITS>(vals[j], E->thr, E->x_lo, &sc)) continue;
+        const long long e = e0 + j;
+        int a, c;
+        long long seg;
+        if (HEAD) {
+            int b;
+            head_decompose(E->g, e, b, a, c);
+            seg = (long long)b * E->C + c;
+        } else {
+            a = (int)((unsigned)e / (unsigned)E->C);                          // per image: e < 2^31
+            c = (int)e - a * E->C;
+            seg = E->seg0 + c;
+        }
+        append_key(E->cand, E->seg_count, seg, make_key(c, sc, a, E->fmt), sat, E->sat_seg0, E->sat_bits);
+    }
+}
+
 // The streaming scan shared by both layouts: `count` floats at `base` are read once with 128-bit no-allocate loads;
-// emit(e, score) is called for every element e with score > threshold.
-template <bool IS_LOGITS, typename Emit>
-__device__ __forceinline__ void scan_candidates(const float* __restrict__ base, long long count, float thr, float x_lo, Emit emit) {
+// every group of four elements whose maximum passes the (cheap) pre-test goes to filter_group.  The candidate code is written
+// fully unrolled and inlined on purpose: the compiler then lays the rare path out of the way of the streaming loop.  Measured
+// on a B200 (cfg3, graph replay of the inference sub-path, profiles/round2_filter_variants.txt): this form 0.228 ms (scan
+// 0.190 ms); the candidate code as an out-of-line function 0.248 ms (0.246 / 0.268 ms when the call forces spills at 48 / 40
+// registers); values parked in shared memory and walked by a rolled loop 0.335 ms; a rolled 4-iteration loop 4.3 vs 6.2 TB/s
+// (round 1).
+// `dense_flag` (anchor-major only): set by the first thread that finds possible candidates in all four of its groups; every
+// thread that comes across a possible candidate afterwards stops its scan -- filter_dense_kernel redoes such an image from
+// scratch.  Both checks sit on the candidate path, the streaming loop itself does not know about them (a flag load and a
+// ballot per iteration cost 15 % of the scan's bandwidth).
+template <bool IS_LOGITS, bool HEAD>
+__device__ __forceinline__ void scan_candidates(const float* __restrict__ base, long long count, const FilterEmit* __restrict__ E,
+                                                unsigned* sat, int* dense_flag) {
     const int lane = threadIdx.x & 31;
+    const float lim = IS_LOGITS ? E->x_lo : E->thr;
     // peel to 16-byte alignment: head scalars | body float4 | tail scalars
     const unsigned mis = (unsigned)(((uintptr_t)base >> 2) & 3);
     long long head = mis ? (4 - mis) : 0;
@@ -143,14 +243,13 @@ __device__ __forceinline__ void scan_candidates(const float* __restrict__ base, 
         long long e = -1;
         if (lane < head) e = lane;
         else if (lane - head < count - tail0) e = tail0 + (lane - head);
-        if (e >= 0) {
-            float s;
-            if (is_candidate<IS_LOGITS>(base[e], thr, x_lo, &s)) emit(e, s);
-        }
+        if (e >= 0 && base[e] > lim)
+            filter_group<IS_LOGITS, HEAD>(E, sat, make_float4(base[e], -INFINITY, -INFINITY, -INFINITY), e);
     }
 
     const long long stride = (long long)gridDim.x * FILTER_THREADS * FILTER_UNROLL;
-    for (long long i0 = (long long)blockIdx.x * FILTER_THREADS * FILTER_UNROLL; i0 < nbody4; i0 += stride) {
+    bool stop = false;
+    for (long long i0 = (long long)blockIdx.x * FILTER_THREADS * FILTER_UNROLL; i0 < nbody4 && !stop; i0 += stride) {
         float4 v[FILTER_UNROLL];
         bool inb[FILTER_UNROLL];
 #pragma unroll
@@ -159,86 +258,197 @@ __device__ __forceinline__ void scan_candidates(const float* __restrict__ base, 
             inb[u] = i < nbody4;
             v[u] = inb[u] ? ld_stream_f4(body + i) : make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
         }
+        bool hit[FILTER_UNROLL];
+#pragma unroll
+        for (int u = 0; u < FILTER_UNROLL; ++u) hit[u] = inb[u] && fmaxf(fmaxf(v[u].x, v[u].y), fmaxf(v[u].z, v[u].w)) > lim;
+        if (!HEAD && dense_flag) {
+            // a thread ALL of whose four groups (4 KB apart) hold a possible candidate sits in a dense image: with 5 % of the
+            // elements above the threshold that happens to 0.1 % of the threads, with 20 % to every tenth -- and with a few
+            // confident anchors per image never (their classes cannot line up in all four 4-class windows).  Checked BEFORE
+            // anything is appended: in a dense image every thread would otherwise start with a burst of contended atomics.
+            bool all = true;
+#pragma unroll
+            for (int u = 0; u < FILTER_UNROLL; ++u) all = all && hit[u];
+            if (all) {
+                *dense_flag = 1;
+                break;
+            }
+        }
 #pragma unroll
         for (int u = 0; u < FILTER_UNROLL; ++u) {
-            const float lim = IS_LOGITS ? x_lo : thr;
-            const float mx = fmaxf(fmaxf(v[u].x, v[u].y), fmaxf(v[u].z, v[u].w));
-            if (!(inb[u] && (mx > lim))) continue;
-            const long long e0 = head + ((i0 + u * FILTER_THREADS + threadIdx.x) << 2);
-            // fully unrolled on purpose: the compiler predicates this rare path; written as a rolled loop it becomes a
-            // branch region per group and the scan loses 30 % of its bandwidth (measured: 4.3 vs 6.2 TB/s)
-            const float vals[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                float sc;
-                if (is_candidate<IS_LOGITS>(vals[j], thr, x_lo, &sc)) emit(e0 + j, sc);
-            }
+            if (!hit[u]) continue;
+            if (!HEAD && dense_flag && __ldcg(dense_flag)) { stop = true; continue; }
+            filter_group<IS_LOGITS, HEAD>(E, sat, v[u], head + ((i0 + u * FILTER_THREADS + threadIdx.x) << 2));
         }
     }
 }
 
 // anchor-major layout: grid (gx, B), image blockIdx.y is the [A,C] array scanned
 template <bool IS_LOGITS>
-__global__ void __launch_bounds__(FILTER_THREADS) filter_kernel(
+__global__ void __launch_bounds__(FILTER_THREADS, FILTER_MIN_CTAS) filter_kernel(
     const float* __restrict__ scores, long long per_image /*A*C*/, int C, float thr, float x_lo, KeyFormat fmt,
-    unsigned long long* __restrict__ cand, int* __restrict__ seg_count /*[B*C]*/) {
+    unsigned long long* __restrict__ cand, int* __restrict__ seg_count /*[B*C]*/, int* __restrict__ img_dense /*[B] or NULL*/) {
     extern __shared__ unsigned s_sat[];                                 // one bit per class of this image: segment seen past its capacity
+    __shared__ FilterEmit s_emit;
     const int b = blockIdx.y;
-    const long long seg0 = (long long)b * C;                            // first segment of this image
     const int sat_bits = min(C, FILTER_SAT_WORDS * 32);
     for (int i = threadIdx.x; i < (sat_bits + 31) / 32; i += FILTER_THREADS) s_sat[i] = 0u;
+    if (threadIdx.x == 0) {
+        FilterEmit e;
+        e.cand = cand; e.seg_count = seg_count; e.seg0 = (long long)b * C; e.sat_seg0 = e.seg0; e.sat_bits = sat_bits;
+        e.C = C; e.head = 0; e.fmt = fmt; e.thr = thr; e.x_lo = x_lo;
+        memset(&e.g, 0, sizeof(e.g));
+        s_emit = e;
+    }
     __syncthreads();
-    auto emit = [&](long long e, float s) {
-        const int a = (int)(e / C), c = (int)(e - (long long)a * C);
-        append_key(cand, seg_count, seg0 + c, make_key(c, s, a, fmt), s_sat, seg0, sat_bits);
-    };
-    scan_candidates<IS_LOGITS>(scores + (size_t)b * per_image, per_image, thr, x_lo, emit);
+    scan_candidates<IS_LOGITS, false>(scores + (size_t)b * per_image, per_image, &s_emit, s_sat, img_dense ? img_dense + b : nullptr);
 }
 
 // Head layout (head-layout fusion, see head.cu): grid (gx, num_levels); level blockIdx.y's class tensor [B, n*C, h, w] (or
 // [B, h, w, n*C]) is scanned as ONE flat array; only a candidate pays for the index arithmetic that recovers
 // (image, anchor, class) from its flat position.
-struct LevelGeom {        // one level of a HeadGeom, by value
-    int hw, per_loc, C, channels_first, anchor_off;
-};
-__device__ __forceinline__ LevelGeom level_geom(const HeadGeom& G, int l) {
-    LevelGeom g;
-    g.hw = G.hw[l]; g.per_loc = G.per_loc; g.C = G.C; g.channels_first = G.channels_first; g.anchor_off = G.anchor_off[l];
-    return g;
-}
-// element r of ONE image's block of a level -> (anchor, class)
-__device__ __forceinline__ void level_decompose(const LevelGeom g, int r, int& a, int& c) {
-    const int hw = g.hw, n = g.per_loc, C = g.C;
-    int loc, q;
-    if (g.channels_first) { q = r / hw; loc = r - q * hw; }
-    else { loc = r / (n * C); q = r - loc * (n * C); }
-    const int k = q / C;
-    c = q - k * C;
-    a = g.anchor_off + loc * n + k;
-}
-__device__ __forceinline__ void head_decompose(const LevelGeom g, long long e, int& b, int& a, int& c) {
-    const long long per_image = (long long)g.per_loc * g.C * g.hw;
-    b = (int)(e / per_image);
-    level_decompose(g, (int)(e - (long long)b * per_image), a, c);
-}
-
 template <bool IS_LOGITS>
-__global__ void __launch_bounds__(FILTER_THREADS) head_filter_kernel(const HeadGeom G, int B, float thr, float x_lo, KeyFormat fmt,
+__global__ void __launch_bounds__(FILTER_THREADS, FILTER_MIN_CTAS) head_filter_kernel(const HeadGeom G, int B, float thr, float x_lo, KeyFormat fmt,
                                                                     unsigned long long* __restrict__ cand,
                                                                     int* __restrict__ seg_count) {
     extern __shared__ unsigned s_sat[];                                 // one bit per (image, class) segment (the first 65536 of them)
+    __shared__ FilterEmit s_emit;
     const int l = blockIdx.y;
     const LevelGeom g = level_geom(G, l);
     const long long count = (long long)B * g.per_loc * g.C * g.hw;
     const int sat_bits = (int)min((long long)B * g.C, (long long)FILTER_SAT_WORDS * 32);
     for (int i = threadIdx.x; i < (sat_bits + 31) / 32; i += FILTER_THREADS) s_sat[i] = 0u;
+    if (threadIdx.x == 0) {
+        FilterEmit e;
+        e.cand = cand; e.seg_count = seg_count; e.seg0 = 0; e.sat_seg0 = 0; e.sat_bits = sat_bits;
+        e.C = g.C; e.head = 1; e.fmt = fmt; e.g = g; e.thr = thr; e.x_lo = x_lo;
+        s_emit = e;
+    }
     __syncthreads();
-    auto emit = [&](long long e, float s) {
-        int b, a, c;
-        head_decompose(g, e, b, a, c);
-        append_key(cand, seg_count, (long long)b * g.C + c, make_key(c, s, a, fmt), s_sat, 0, sat_bits);
-    };
-    scan_candidates<IS_LOGITS>(G.cls[l], count, thr, x_lo, emit);
+    scan_candidates<IS_LOGITS, true>(G.cls[l], count, &s_emit, s_sat, nullptr);
+}
+
+// ---------------------------------------------------------------------------------------------- 1b. dense images
+// An image declared dense by filter_kernel is redone here from scratch (its own counters: seg_count_dense), by the whole
+// grid row of that image; every other CTA exits at once.  A CTA works on tiles of 4096 consecutive elements:
+//   phase 1  every element above the pre-test limit is counted in its class's VALUE histogram (shared memory; FD_NB bins over
+//            [lim, lim + FD_RANGE) of the raw value -- logit or score --, no sigmoid); unless the CTA has seen the class's
+//            segment past its capacity, the exact candidate test follows and a candidate takes a rank inside (tile, class);
+//   phase 2  one global atomic per class and tile reserves the tile's slots (13.5 ms -> 0.5 ms against one atomic per
+//            candidate in round 1: same-address atomics retire at ~8 M/s);
+//   phase 3  the keys are written.
+// At the end the value histograms of the saturated classes are added to the global ones: nms_rounds_kernel uses them to GUESS
+// the value above which a region's worth of the best candidates lies, so that its first round needs no histogram pass of its
+// own; the guess only has to be good, not exact (the collect pass counts).
+#define FD_U 4
+#define FD_NB 32
+#define FD_RANGE 19.0f                 // logits: sigmoid(lim + 19) rounds to 1 for every usual threshold; scores: (thr, 1] is a subset
+__device__ __forceinline__ int value_bin(float v, float lim, float inv_w) {      // bin 0 = the best values
+    const int b = FD_NB - 1 - (int)((v - lim) * inv_w);
+    return b < 0 ? 0 : (b > FD_NB - 1 ? FD_NB - 1 : b);
+}
+template <bool IS_LOGITS>
+__global__ void __launch_bounds__(FILTER_THREADS) filter_dense_kernel(
+    const float* __restrict__ scores, long long per_image /*A*C*/, int C, float thr, float x_lo, KeyFormat fmt,
+    unsigned long long* __restrict__ cand, int* __restrict__ seg_count_dense, const int* __restrict__ img_dense,
+    unsigned* __restrict__ vhist /*[B*C][FD_NB]*/) {
+    extern __shared__ int s_dense[];
+    const int b = blockIdx.y, tid = threadIdx.x;
+    if (!img_dense[b]) return;
+    int* s_cnt = s_dense;                                   // [C]
+    int* s_base = s_dense + C;                              // [C]
+    unsigned* s_satd = (unsigned*)(s_dense + 2 * C);        // [(C + 31) / 32]
+    unsigned* s_vh = s_satd + (C + 31) / 32;                // [C][FD_NB]
+    const float* base = scores + (size_t)b * per_image;
+    const long long seg0 = (long long)b * C;
+    const float lim = IS_LOGITS ? x_lo : thr;
+    const float inv_w = (float)FD_NB / FD_RANGE;
+    const FastDiv dc = fast_div((unsigned)C);
+    for (int c = tid; c < C; c += FILTER_THREADS) s_cnt[c] = 0;
+    for (int i = tid; i < (C + 31) / 32; i += FILTER_THREADS) s_satd[i] = 0u;
+    for (int i = tid; i < C * FD_NB; i += FILTER_THREADS) s_vh[i] = 0u;
+    __syncthreads();
+    const unsigned mis = (unsigned)(((uintptr_t)base >> 2) & 3);
+    long long head = mis ? (4 - mis) : 0;
+    if (head > per_image) head = per_image;
+    const long long nbody4 = (per_image - head) >> 2;
+    const long long tail0 = head + (nbody4 << 2);
+    const float4* body = (const float4*)(base + head);
+    if (blockIdx.x == 0 && tid < 32) {                                  // the (< 8) unaligned head / tail elements
+        long long e = -1;
+        if (tid < head) e = tid;
+        else if (tid - head < per_image - tail0) e = tail0 + (tid - head);
+        float s;
+        if (e >= 0 && base[e] > lim) {
+            const int a = (int)div_fast((unsigned)e, dc), c = (int)e - a * C;
+            atomicAdd(&s_vh[c * FD_NB + value_bin(base[e], lim, inv_w)], 1u);
+            if (is_candidate<IS_LOGITS>(base[e], thr, x_lo, &s)) {
+                const int pos = atomicAdd(seg_count_dense + seg0 + c, 1);
+                if (pos < SEG_CAP) cand[(size_t)(seg0 + c) * SEG_CAP + pos] = make_key(c, s, a, fmt);
+            }
+        }
+    }
+    const long long ntiles = (nbody4 + FILTER_THREADS * FD_U - 1) / (FILTER_THREADS * FD_U);
+    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        float sc[4 * FD_U];
+        unsigned short rk[4 * FD_U];
+        unsigned hit = 0u;
+        // phase 1
+#pragma unroll
+        for (int u = 0; u < FD_U; ++u) {
+            const long long i4 = tile * (FILTER_THREADS * FD_U) + u * FILTER_THREADS + tid;
+            const float4 v = i4 < nbody4 ? ld_stream_f4(body + i4) : make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+            const float vals[4] = {v.x, v.y, v.z, v.w};
+            const unsigned e0 = (unsigned)(head + (i4 << 2));
+            unsigned a = div_fast(e0, dc);
+            int c = (int)(e0 - a * (unsigned)C);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                if (vals[j] > lim) {
+                    atomicAdd(&s_vh[c * FD_NB + value_bin(vals[j], lim, inv_w)], 1u);
+                    if (!((s_satd[c >> 5] >> (c & 31)) & 1u) && is_candidate<IS_LOGITS>(vals[j], thr, x_lo, &sc[u * 4 + j])) {
+                        rk[u * 4 + j] = (unsigned short)atomicAdd(&s_cnt[c], 1);
+                        hit |= 1u << (u * 4 + j);
+                    }
+                }
+                if (++c == C) c = 0;                                    // next element: next class (next anchor at the wrap)
+            }
+        }
+        if (!__syncthreads_or((int)hit)) continue;                      // (every class saturated: the normal case after the first tile)
+        // phase 2: one global atomic per class reserves the tile's slots
+        for (int c = tid; c < C; c += FILTER_THREADS) {
+            const int h = s_cnt[c];
+            if (h) {
+                const int first = atomicAdd(seg_count_dense + seg0 + c, h);
+                s_base[c] = first;
+                s_cnt[c] = 0;
+                if (first + h > SEG_CAP) atomicOr(&s_satd[c >> 5], 1u << (c & 31));
+            }
+        }
+        __syncthreads();
+        // phase 3: write the keys
+#pragma unroll
+        for (int u = 0; u < FD_U; ++u) {
+            const long long i4 = tile * (FILTER_THREADS * FD_U) + u * FILTER_THREADS + tid;
+            const unsigned e0 = (unsigned)(head + (i4 << 2));
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                if ((hit >> (u * 4 + j)) & 1u) {
+                    const unsigned e = e0 + j, a = div_fast(e, dc), c = e - a * (unsigned)C;
+                    const int pos = s_base[c] + rk[u * 4 + j];
+                    if (pos < SEG_CAP) cand[(size_t)(seg0 + c) * SEG_CAP + pos] = make_key((int)c, sc[u * 4 + j], (int)a, fmt);
+                }
+            }
+        }
+        // no barrier here: the next tile's phase 2 (the only writer of s_base) comes after its phase-1 barrier, which every
+        // thread reaches only after this phase 3
+    }
+    __syncthreads();
+    for (int i = tid; i < C * FD_NB; i += FILTER_THREADS) {
+        const int c = i / FD_NB;
+        const unsigned h = s_vh[i];
+        if (h && ((s_satd[c >> 5] >> (c & 31)) & 1u)) atomicAdd(&vhist[(size_t)(seg0 + c) * FD_NB + (i - c * FD_NB)], h);
+    }
 }
 
 // ---------------------------------------------------------------------------------------------- 2. sorting helpers
@@ -340,6 +550,17 @@ __device__ __forceinline__ bool nms_exact(const NmsBox a, float area_a, const Nm
 // header ints of the counter workspace (zeroed every call)
 enum { H_HEAVY = 0, H_PEND, H_BAR, H_ERR, H_NIMG_C, H_NHIST0, H_NHIST1, H_NIMG_H0, H_NIMG_H1, H_WORDS = 16 };
 
+// Candidate count of a segment: from filter_kernel's counters, or from filter_dense_kernel's when the image was redone by it.
+struct SegCounts {
+    const int* sparse;
+    const int* dense;          // NULL when the dense-image path is not in use
+    const int* img_dense;
+};
+__device__ __forceinline__ int seg_candidates(const SegCounts SC, long long seg, int C) {
+    if (SC.dense && SC.img_dense[seg / C]) return SC.dense[seg];
+    return SC.sparse[seg];
+}
+
 // Segments with at most 32 candidates (the vast majority: background classes) are resolved by ONE WARP each, one
 // candidate per lane: decode, a 32x32 suppression bit matrix (one column per lane), a greedy walk with shuffles.
 // Larger segments are pushed to a queue: `heavy` (fits its region: nms_kernel spends a whole CTA on each) or `pending`
@@ -347,7 +568,7 @@ enum { H_HEAVY = 0, H_PEND, H_BAR, H_ERR, H_NIMG_C, H_NHIST0, H_NHIST1, H_NIMG_H
 #define NMS_SMALL_WARPS 8
 template <bool DECODED>
 __global__ void __launch_bounds__(NMS_SMALL_WARPS * 32) nms_small_kernel(
-    const unsigned long long* __restrict__ cand, KeyFormat fmt, const int* __restrict__ seg_count,
+    const unsigned long long* __restrict__ cand, KeyFormat fmt, const SegCounts SC,
     const CodeView codes, const float4* __restrict__ anchors, long long A,
     long long nseg, int C, int K, float iou_thr, float4* __restrict__ seg_box, float* __restrict__ seg_score,
     int* __restrict__ seg_anchor, int* __restrict__ seg_kept, int* __restrict__ heavy_queue, int* __restrict__ pend_queue,
@@ -357,7 +578,7 @@ __global__ void __launch_bounds__(NMS_SMALL_WARPS * 32) nms_small_kernel(
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const long long seg = (long long)blockIdx.x * NMS_SMALL_WARPS + warp;
     if (seg >= nseg) return;
-    const int n = seg_count[seg];
+    const int n = seg_candidates(SC, seg, C);
     if (n <= 0) {
         if (lane == 0) seg_kept[seg] = 0;
         return;
@@ -559,7 +780,7 @@ __device__ __forceinline__ int nms_sorted_segment(const NmsSegArgs& N, NmsShared
 
 // One CTA per queued (image, class) segment with 33..SEG_CAP candidates: sort in shared memory, then nms_sorted_segment.
 template <bool DECODED>
-__global__ void __launch_bounds__(NMS_THREADS) nms_kernel(const unsigned long long* __restrict__ cand, const int* __restrict__ seg_count,
+__global__ void __launch_bounds__(NMS_THREADS) nms_kernel(const unsigned long long* __restrict__ cand, const SegCounts SC,
                                                           const NmsSegArgs N, int* __restrict__ seg_kept,
                                                           const int* __restrict__ heavy_queue, const int* __restrict__ hdr) {
     extern __shared__ __align__(16) unsigned char nms_smem[];
@@ -571,7 +792,7 @@ __global__ void __launch_bounds__(NMS_THREADS) nms_kernel(const unsigned long lo
     const int nheavy = hdr[H_HEAVY];
     for (int item = blockIdx.x; item < nheavy; item += gridDim.x) {
         const long long seg = heavy_queue[item];
-        const int n = min(seg_count[seg], SEG_CAP);
+        const int n = min(seg_candidates(SC, seg, N.C), SEG_CAP);
         const unsigned long long* keys = cand + (size_t)seg * SEG_CAP;
         __syncthreads();
         for (int i = tid; i < n; i += NMS_THREADS) s_sort[i] = keys[i];
@@ -598,6 +819,10 @@ struct RoundState {
     int* list_h;                   // [2][B]
     int* list_c;                   // [B]
     unsigned long long k_thr, dlo0;
+    float* vcut;                   // [nseg]: collect pass: no key < mid has a raw value (logit / score) below this
+    const unsigned* vhist;         // [nseg][FD_NB] value histograms of filter_dense_kernel, or NULL
+    const int* img_dense;          // [B]
+    float vlim, vwidth;            // value-histogram geometry: bin FD_NB - 1 - q holds [vlim + q * vwidth, vlim + (q + 1) * vwidth)
     int* err;                      // the context's sticky asynchronous-error word
     unsigned long long* times;     // [ROUND_TIMES]: [0] = rounds run, then %globaltimer (ns) at the start and after every phase of the first rounds
 };
@@ -606,6 +831,20 @@ __device__ __forceinline__ unsigned long long global_timer_ns() {
     unsigned long long t;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
     return t;
+}
+
+// Lower bound of the raw value of any element whose key is < mid: such keys have an order word <= mid's, i.e. a score >=
+// score_of_order(mid >> abits); for logits the bound goes back through the sigmoid with a margin.
+template <bool IS_LOGITS>
+__device__ __forceinline__ float value_bound_of_key(unsigned long long mid, int abits) {
+    const unsigned long long om = mid >> abits;
+    if (om > 0xFFFFFFFFull) return -INFINITY;
+    const float s_mid = score_of_order((unsigned)om);
+    if (!IS_LOGITS) return s_mid;
+    if (s_mid >= 1.0f) return 15.0f;                                     // sigmoid rounds to 1 only above 16.6
+    if (!(s_mid > 0.0f)) return -INFINITY;
+    const float lg = logf(s_mid / (1.0f - s_mid));
+    return lg - 1e-3f * (1.0f + fabsf(lg));
 }
 
 __device__ __forceinline__ int ceil_log2_per_bin(unsigned long long width) {   // smallest s with ROUND_NB << s >= width
@@ -636,9 +875,10 @@ __device__ __forceinline__ bool grid_barrier(int* hdr, int& epoch) {
 }
 
 // CTA-cooperative streaming scan of `count` floats at `base` (peeled to 16-byte alignment); emit(r, v) for every element with
-// v > lim (r = element index inside the block)
+// v > lim (r = element index inside the block).  Same structure as scan_candidates: values that may matter are parked in the
+// thread's shared-memory slot and walked in a rolled loop, so that `emit` is instantiated twice, not seventeen times.
 template <typename Emit>
-__device__ __forceinline__ void cta_scan(const float* __restrict__ base, int count, float lim, Emit emit) {
+__device__ __forceinline__ void cta_scan(const float* __restrict__ base, int count, float lim, float (*slot)[NMS_THREADS], Emit emit) {
     const int tid = threadIdx.x;
     const unsigned mis = (unsigned)(((uintptr_t)base >> 2) & 3);
     int head = mis ? (int)(4 - mis) : 0;
@@ -659,13 +899,18 @@ __device__ __forceinline__ void cta_scan(const float* __restrict__ base, int cou
             const int i = i0 + u * NMS_THREADS + tid;
             v[u] = i < nbody4 ? ld_stream_f4(body + i) : make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
         }
+        float mx = -INFINITY;
+#pragma unroll
+        for (int u = 0; u < FILTER_UNROLL; ++u) mx = fmaxf(mx, fmaxf(fmaxf(v[u].x, v[u].y), fmaxf(v[u].z, v[u].w)));
+        if (!(mx > lim)) continue;
 #pragma unroll
         for (int u = 0; u < FILTER_UNROLL; ++u) {
-            const int r0 = head + ((i0 + u * NMS_THREADS + tid) << 2);
-            const float vals[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-                if (vals[j] > lim) emit(r0 + j, vals[j]);
+            slot[4 * u + 0][tid] = v[u].x; slot[4 * u + 1][tid] = v[u].y; slot[4 * u + 2][tid] = v[u].z; slot[4 * u + 3][tid] = v[u].w;
+        }
+#pragma unroll 1
+        for (int k = 0; k < 4 * FILTER_UNROLL; ++k) {
+            const float x = slot[k][tid];
+            if (x > lim) emit(head + ((i0 + (k >> 2) * NMS_THREADS + tid) << 2) + (k & 3), x);
         }
     }
 }
@@ -675,6 +920,7 @@ struct ClassTables {
     unsigned char* st;             // [C]
     unsigned char* shift;          // [C]
     float* vmin;                   // [C]   collect pass: conservative lower bound of the value (logit or score) of a key < mid
+    float* vmin_all;               // [1]   collect pass: the smallest vmin over the image's collecting classes
     unsigned long long* lo;        // [C]
     unsigned long long* a;         // [C]   histogram pass: dlo;  collect pass: mid
     unsigned long long* b;         // [C]   histogram pass: dhi
@@ -686,6 +932,7 @@ __global__ void __launch_bounds__(NMS_THREADS) nms_rounds_kernel(const HeadGeom 
                                                                  const NmsSegArgs N, int* __restrict__ seg_kept, const RoundState R) {
     extern __shared__ __align__(16) unsigned char nms_smem[];
     __shared__ NmsShared sh;
+    __shared__ float s_slot[4 * FILTER_UNROLL][NMS_THREADS];
     const int npend = R.hdr[H_PEND];
     if (npend == 0) {                                                // the normal case: no segment overflowed its region
         if (blockIdx.x == 0 && threadIdx.x == 0) R.times[0] = 0ull;
@@ -708,26 +955,60 @@ __global__ void __launch_bounds__(NMS_THREADS) nms_rounds_kernel(const HeadGeom 
         T.b = (unsigned long long*)p; p += (size_t)C * 8;
         T.hist = (unsigned*)p; p += (size_t)C * ROUND_NB * 4;
         T.vmin = (float*)p; p += (size_t)C * 4;
+        T.vmin_all = (float*)p; p += 16;
         T.st = p; p += C;
         T.shift = p;
     }
     const unsigned long long kmask = (1ull << fmt.cshift) - 1ull;
+    const bool flat_geom = G.num_levels == 1 && !G.channels_first && G.per_loc == 1;   // the anchor-major tensor: class = element % C
     int epoch = 0, stamp = 1;
     auto mark = [&]() { if (cta == 0 && tid == 0 && stamp < ROUND_TIMES) R.times[stamp++] = global_timer_ns(); };
     mark();
 
-    // ---- init: every pending segment starts with a histogram over [dlo0, k_thr)
+    // ---- init.  A segment of an image that filter_dense_kernel redid comes with a VALUE histogram: the value above which
+    //      about ROUND_WANT of its best candidates lie is read off it, turned into a key bound `mid` (for logits through the
+    //      sigmoid, 8 ulps up: expf is good to 2 ulps and the division is exact, so no element with a smaller logit can have a
+    //      score above that) and the first round collects [0, mid) right away; the collect pass counts exactly, and a guess that
+    //      turns out too generous falls back to the exact key-space histogram.  Every other segment starts with that histogram
+    //      over [dlo0, k_thr).
     for (int p = cta * NMS_THREADS + tid; p < npend; p += grid * NMS_THREADS) {
         const int seg = R.pend_queue[p];
-        R.st[seg] = ST_HIST; R.lo[seg] = 0ull; R.dlo[seg] = R.dlo0; R.dhi[seg] = R.k_thr;
-        R.sh[seg] = ceil_log2_per_bin(R.k_thr - R.dlo0);
-        R.beyond[seg] = 0; R.rem[seg] = 0; R.fill[seg] = 0;
+        const int b = seg / C;
+        R.lo[seg] = 0ull; R.beyond[seg] = 0; R.rem[seg] = 0; R.fill[seg] = 0;
         seg_kept[seg] = 0;
         for (int j = 0; j < ROUND_NB; ++j) R.hist[(size_t)seg * ROUND_NB + j] = 0u;
-        const int b = seg / C;
-        if (atomicExch(R.stamp_h + b, 1) != 1) R.list_h[atomicAdd(R.hdr + H_NIMG_H0 + 1, 1) * 1 + B] = b;   // list of round 1 lives in list_h[1]
+        bool guessed = false;
+        if (R.vhist && R.img_dense[b]) {
+            const unsigned* vh = R.vhist + (size_t)seg * FD_NB;
+            long long cum = 0;
+            int jb = 0;
+            for (; jb < FD_NB; ++jb) {
+                cum += vh[jb];
+                if (cum >= ROUND_WANT + ROUND_WANT / 4) break;
+            }
+            if (jb < FD_NB - 1 && cum <= SEG_CAP - SEG_CAP / 4) {
+                const float v_cut = R.vlim + (float)(FD_NB - 1 - jb) * R.vwidth;
+                float s_cut = v_cut;
+                if (IS_LOGITS) s_cut = __uint_as_float(__float_as_uint(f_div(1.0f, f_add(1.0f, expf(-v_cut)))) + 8u);
+                if (s_cut < 1.0f && s_cut > thr) {
+                    R.mid[seg] = (unsigned long long)order_desc(s_cut) << fmt.abits;     // keys < mid <=> score > s_cut
+                    R.vcut[seg] = v_cut;
+                    R.rem[seg] = 0x3fffffff;                                             // unknown: assume there is more
+                    R.st[seg] = ST_COLLECT;
+                    if (atomicExch(R.stamp_c + b, 1) != 1) R.list_c[atomicAdd(R.hdr + H_NIMG_C, 1)] = b;
+                    guessed = true;
+                }
+            }
+        }
+        if (!guessed) {
+            R.st[seg] = ST_HIST; R.dlo[seg] = R.dlo0; R.dhi[seg] = R.k_thr;
+            R.sh[seg] = ceil_log2_per_bin(R.k_thr - R.dlo0);
+            atomicAdd(R.hdr + H_NHIST0 + 1, 1);
+            if (atomicExch(R.stamp_h + b, 1) != 1) R.list_h[(size_t)B + atomicAdd(R.hdr + H_NIMG_H0 + 1, 1)] = b;   // round 1: list_h[1]
+        }
     }
     if (!grid_barrier(R.hdr, epoch)) { if (tid == 0) *R.err = SSDK_ASYNC_ROUNDS_TIMEOUT; return; }
+    mark();
 
     // streaming decomposition of one pass: unit u -> (image list[u / group], slice u % group of every level's block)
     auto for_units = [&](const int* list, int n_img, auto&& per_unit) {
@@ -746,39 +1027,34 @@ __global__ void __launch_bounds__(NMS_THREADS) nms_rounds_kernel(const HeadGeom 
             if (want_state == ST_HIST) {
                 T.a[c] = R.dlo[seg]; T.b[c] = R.dhi[seg]; T.shift[c] = (unsigned char)R.sh[seg];
             } else {
-                const unsigned long long mid = R.mid[seg];
-                T.a[c] = mid;
-                // values of keys < mid: their order word is <= mid's, i.e. their score is >= score_of_order(mid >> abits)
-                float vmin = -INFINITY;
-                const unsigned long long om = mid >> fmt.abits;
-                if (om <= 0xFFFFFFFFull) {
-                    const float s_mid = score_of_order((unsigned)om);
-                    if (!IS_LOGITS) vmin = s_mid;
-                    else if (s_mid >= 1.0f) vmin = 15.0f;                // sigmoid rounds to 1 only above 16.6
-                    else if (s_mid > 0.0f) {
-                        const float lg = logf(s_mid / (1.0f - s_mid));
-                        vmin = lg - 1e-3f * (1.0f + fabsf(lg));
-                    }
-                }
-                T.vmin[c] = vmin;
+                T.a[c] = R.mid[seg];
+                T.vmin[c] = R.vcut[seg];
             }
         }
         if (want_state == ST_HIST)
             for (int i = tid; i < C * ROUND_NB; i += NMS_THREADS) T.hist[i] = 0u;
         __syncthreads();
+        if (want_state == ST_COLLECT) {
+            if (tid == 0) {
+                float m = INFINITY;
+                for (int c = 0; c < C; ++c)
+                    if (T.st[c]) m = fminf(m, T.vmin[c]);
+                T.vmin_all[0] = m;
+            }
+            __syncthreads();
+        }
     };
 
     for (int round = 1;; ++round) {
         const int par = round & 1;
         const int n_img_h = R.hdr[H_NIMG_H0 + par];
-        const int n_hist = round == 1 ? npend : R.hdr[H_NHIST0 + par];
-        if (n_hist == 0) break;                                      // uniform: written before the last barrier
+        const int n_hist = R.hdr[H_NHIST0 + par];
+        if (n_hist == 0 && (round > 1 || R.hdr[H_NIMG_C] == 0)) break;   // uniform: written before the last barrier
         if (cta == 0 && tid == 0) R.times[0] = (unsigned long long)round;
         mark();
-        if (cta == 0 && tid == 0) {                                  // counters the NEXT round reads, and this round's collect list
+        if (cta == 0 && tid == 0) {                                  // counters the NEXT round reads
             R.hdr[H_NIMG_H0 + (par ^ 1)] = 0;
             R.hdr[H_NHIST0 + (par ^ 1)] = 0;
-            R.hdr[H_NIMG_C] = 0;
         }
         // ---- (1) histogram pass
         for_units(R.list_h + (size_t)par * B, n_img_h, [&](int b, int slice, int group) {
@@ -788,9 +1064,10 @@ __global__ void __launch_bounds__(NMS_THREADS) nms_rounds_kernel(const HeadGeom 
                 const int blk = g.per_loc * g.C * g.hw;
                 const int r0 = (int)((long long)blk * slice / group), r1 = (int)((long long)blk * (slice + 1) / group);
                 const float* base = G.cls[l] + (size_t)b * blk;
-                cta_scan(base + r0, r1 - r0, IS_LOGITS ? x_lo : thr, [&](int r, float v) {
+                cta_scan(base + r0, r1 - r0, IS_LOGITS ? x_lo : thr, s_slot, [&](int r, float v) {
                     int a, c;
-                    level_decompose(g, r0 + r, a, c);
+                    if (flat_geom) { a = (int)div_fast((unsigned)(r0 + r), g.d_c); c = r0 + r - a * C; }
+                    else level_decompose(g, r0 + r, a, c);
                     const int seg = b * C + c;
                     if (tables_in_smem ? !T.st[c] : (R.st[seg] != ST_HIST)) return;
                     float s;
@@ -819,17 +1096,36 @@ __global__ void __launch_bounds__(NMS_THREADS) nms_rounds_kernel(const HeadGeom 
         if (!grid_barrier(R.hdr, epoch)) { if (tid == 0) *R.err = SSDK_ASYNC_ROUNDS_TIMEOUT; return; }
         mark();
 
-        // ---- (2) plan: one thread per pending segment
-        for (int p = cta * NMS_THREADS + tid; p < npend; p += grid * NMS_THREADS) {
+        // ---- (2) plan: one warp per pending segment (lane l owns bins l and l + 32)
+        static_assert(ROUND_NB == 64, "the planning step maps two bins to every lane");
+        for (int p = cta * (NMS_THREADS / 32) + (tid >> 5); p < npend; p += grid * (NMS_THREADS / 32)) {
             const int seg = R.pend_queue[p];
-            if (R.st[seg] != ST_HIST) continue;
+            if (R.st[seg] != ST_HIST) continue;                      // warp-uniform
             unsigned* h = R.hist + (size_t)seg * ROUND_NB;
-            long long total = 0;
-            int f = -1;
-            for (int j = 0; j < ROUND_NB; ++j) {
-                total += h[j];
-                if (f < 0 && h[j]) f = j;
+            const long long h0 = h[lane], h1 = h[lane + 32];
+            h[lane] = 0u;                                            // zero for the next histogram pass
+            h[lane + 32] = 0u;
+            long long c0 = h0, c1 = h1;                              // inclusive prefix sums over the 64 bins
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const long long v0 = __shfl_up_sync(0xffffffffu, c0, o), v1 = __shfl_up_sync(0xffffffffu, c1, o);
+                if (lane >= o) { c0 += v0; c1 += v1; }
             }
+            const long long sum0 = __shfl_sync(0xffffffffu, c0, 31);
+            c1 += sum0;
+            const long long total = __shfl_sync(0xffffffffu, c1, 31);
+            const unsigned ne0 = __ballot_sync(0xffffffffu, h0 != 0), ne1 = __ballot_sync(0xffffffffu, h1 != 0);
+            const int f = ne0 ? __ffs(ne0) - 1 : (ne1 ? 32 + __ffs(ne1) - 1 : -1);
+            // first bin whose inclusive sum reaches ROUND_WANT / exceeds SEG_CAP
+            const unsigned w0 = __ballot_sync(0xffffffffu, c0 >= ROUND_WANT), w1 = __ballot_sync(0xffffffffu, c1 >= ROUND_WANT);
+            const unsigned x0 = __ballot_sync(0xffffffffu, c0 > SEG_CAP), x1 = __ballot_sync(0xffffffffu, c1 > SEG_CAP);
+            const int j_want = w0 ? __ffs(w0) - 1 : (w1 ? 32 + __ffs(w1) - 1 : ROUND_NB);
+            const int j_cap = x0 ? __ffs(x0) - 1 : (x1 ? 32 + __ffs(x1) - 1 : ROUND_NB);
+            int j = j_want + 1 < j_cap ? j_want + 1 : j_cap;          // bins [f, j) are collected
+            if (j > ROUND_NB) j = ROUND_NB;
+            const long long cum_j = j == 0 ? 0 : (j <= 32 ? __shfl_sync(0xffffffffu, c0, j - 1) : __shfl_sync(0xffffffffu, c1, j - 33));
+            const long long h_f = f < 0 ? 0 : (f < 32 ? __shfl_sync(0xffffffffu, h0, f) : __shfl_sync(0xffffffffu, h1, f - 32));
+            if (lane != 0) continue;
             const unsigned long long lo = R.lo[seg], dlo = R.dlo[seg], dhi = R.dhi[seg];
             const int shf = R.sh[seg], b = seg / C;
             const long long beyond = R.beyond[seg];
@@ -841,32 +1137,25 @@ __global__ void __launch_bounds__(NMS_THREADS) nms_rounds_kernel(const HeadGeom 
                     atomicAdd(R.hdr + H_NHIST0 + (par ^ 1), 1);
                     if (atomicExch(R.stamp_h + b, round + 1) != round + 1) R.list_h[(size_t)(par ^ 1) * B + atomicAdd(R.hdr + H_NIMG_H0 + (par ^ 1), 1)] = b;
                 }
-            } else if ((long long)h[f] > SEG_CAP) {
+            } else if (h_f > SEG_CAP) {
                 // the best non-empty bin alone does not fit a region: narrow the range to that bin (the bins before it are empty)
                 const unsigned long long nlo = f == 0 ? lo : dlo + ((unsigned long long)f << shf);
                 unsigned long long nhi = f == ROUND_NB - 1 ? dhi : dlo + ((unsigned long long)(f + 1) << shf);
                 if (nhi > dhi) nhi = dhi;
                 R.lo[seg] = nlo; R.dlo[seg] = nlo; R.dhi[seg] = nhi; R.sh[seg] = ceil_log2_per_bin(nhi - nlo);
-                R.beyond[seg] = (int)(beyond + total - (long long)h[f]);
+                R.beyond[seg] = (int)(beyond + total - h_f);
                 atomicAdd(R.hdr + H_NHIST0 + (par ^ 1), 1);
                 if (atomicExch(R.stamp_h + b, round + 1) != round + 1) R.list_h[(size_t)(par ^ 1) * B + atomicAdd(R.hdr + H_NIMG_H0 + (par ^ 1), 1)] = b;
             } else {
-                long long cum = 0;
-                int j = f;
-                for (; j < ROUND_NB; ++j) {
-                    if (cum + (long long)h[j] > SEG_CAP) break;
-                    cum += h[j];
-                    if (cum >= ROUND_WANT) { ++j; break; }
-                }
                 unsigned long long mid = j >= ROUND_NB ? dhi : dlo + ((unsigned long long)j << shf);
                 if (mid > dhi) mid = dhi;
                 R.mid[seg] = mid;
-                R.rem[seg] = (int)(total - cum + beyond);
+                R.vcut[seg] = value_bound_of_key<IS_LOGITS>(mid, fmt.abits);
+                R.rem[seg] = (int)(total - cum_j + beyond);
                 R.fill[seg] = 0;
                 R.st[seg] = ST_COLLECT;
                 if (atomicExch(R.stamp_c + b, round) != round) R.list_c[atomicAdd(R.hdr + H_NIMG_C, 1)] = b;
             }
-            for (int j = 0; j < ROUND_NB; ++j) h[j] = 0u;
         }
         if (!grid_barrier(R.hdr, epoch)) { if (tid == 0) *R.err = SSDK_ASYNC_ROUNDS_TIMEOUT; return; }
         mark();
@@ -875,18 +1164,21 @@ __global__ void __launch_bounds__(NMS_THREADS) nms_rounds_kernel(const HeadGeom 
         const int n_img_c = R.hdr[H_NIMG_C];
         for_units(R.list_c, n_img_c, [&](int b, int slice, int group) {
             if (tables_in_smem) load_tables(b, ST_COLLECT);
+            // nothing below the smallest per-class bound can be collected: one compare rejects ~99 % of a dense image
+            const float lim_c = tables_in_smem ? fmaxf(IS_LOGITS ? x_lo : thr, T.vmin_all[0] - 1e-6f * fabsf(T.vmin_all[0])) : (IS_LOGITS ? x_lo : thr);
             for (int l = 0; l < G.num_levels; ++l) {
                 const LevelGeom g = level_geom(G, l);
                 const int blk = g.per_loc * g.C * g.hw;
                 const int r0 = (int)((long long)blk * slice / group), r1 = (int)((long long)blk * (slice + 1) / group);
                 const float* base = G.cls[l] + (size_t)b * blk;
-                cta_scan(base + r0, r1 - r0, IS_LOGITS ? x_lo : thr, [&](int r, float v) {
+                cta_scan(base + r0, r1 - r0, lim_c, s_slot, [&](int r, float v) {
                     int a, c;
-                    level_decompose(g, r0 + r, a, c);
+                    if (flat_geom) { a = (int)div_fast((unsigned)(r0 + r), g.d_c); c = r0 + r - a * C; }
+                    else level_decompose(g, r0 + r, a, c);
                     const int seg = b * C + c;
                     if (tables_in_smem) {
                         if (!T.st[c] || v < T.vmin[c]) return;
-                    } else if (R.st[seg] != ST_COLLECT) return;
+                    } else if (R.st[seg] != ST_COLLECT || v < R.vcut[seg]) return;
                     float s;
                     if (!is_candidate<IS_LOGITS>(v, thr, x_lo, &s)) return;
                     const unsigned long long k = ((unsigned long long)order_desc(s) << fmt.abits) | (unsigned long long)a;
@@ -903,9 +1195,22 @@ __global__ void __launch_bounds__(NMS_THREADS) nms_rounds_kernel(const HeadGeom 
         mark();
 
         // ---- (4) the segments' NMS continues over the collected keys
+        if (cta == 0 && tid == 0) R.hdr[H_NIMG_C] = 0;               // consumed by (3); produced again by the next round's (2)
         for (int p = cta; p < npend; p += grid) {
             const int seg = R.pend_queue[p];
             if (R.st[seg] != ST_COLLECT) continue;                   // CTA-uniform
+            if (R.fill[seg] > SEG_CAP) {
+                // (only after a guessed bound) more keys below `mid` than a region holds: the exact histogram over [lo, mid) decides
+                if (tid == 0) {
+                    const int b = seg / C;
+                    const unsigned long long lo = R.lo[seg], mid = R.mid[seg];
+                    R.st[seg] = ST_HIST;
+                    R.dlo[seg] = lo; R.dhi[seg] = mid; R.sh[seg] = ceil_log2_per_bin(mid - lo); R.beyond[seg] = 1;   // >= 1 key lies beyond
+                    atomicAdd(R.hdr + H_NHIST0 + (par ^ 1), 1);
+                    if (atomicExch(R.stamp_h + b, round + 1) != round + 1) R.list_h[(size_t)(par ^ 1) * B + atomicAdd(R.hdr + H_NIMG_H0 + (par ^ 1), 1)] = b;
+                }
+                continue;
+            }
             const int n = min(R.fill[seg], SEG_CAP);
             int kept = seg_kept[seg];
             __syncthreads();
@@ -933,7 +1238,6 @@ __global__ void __launch_bounds__(NMS_THREADS) nms_rounds_kernel(const HeadGeom 
         }
         if (!grid_barrier(R.hdr, epoch)) { if (tid == 0) *R.err = SSDK_ASYNC_ROUNDS_TIMEOUT; return; }
         mark();
-        (void)lane;
     }
 }
 
@@ -1153,8 +1457,14 @@ static int postprocess_impl(ssdk_ctx* ctx, const HeadGeom* head, const float* co
     // (zeroed every call), the queues, the per-segment NMS results, and the state of the rounds (dense segments)
     const bool may_overflow = A > SEG_CAP;                               // a segment can only overflow when there are that many anchors
     SSDK_TRY(ssdk_ensure(ctx, &ctx->ws_cand, (size_t)nseg * SEG_CAP * sizeof(unsigned long long)));
-    const size_t n_stamp = may_overflow ? 2 * (size_t)B : 0;             // zeroed with the header, in the same memset
-    const size_t n_int = H_WORDS + n_stamp + 4 * (size_t)nseg + (may_overflow ? 5 * (size_t)nseg + 3 * (size_t)B + 4 : 0);
+    // dense images (anchor-major tensors only): redone by filter_dense_kernel with its own counters and value histograms
+    const bool use_dense = may_overflow && !head && C <= 1024;
+    // int words zeroed by ONE memset per call: header | round stamps [2B] | dense-image flags [B] | seg_count [nseg] |
+    // seg_count_dense [nseg] | value histograms [nseg][FD_NB]
+    const size_t n_stamp = may_overflow ? 2 * (size_t)B : 0;
+    const size_t n_dense = use_dense ? (size_t)B + (size_t)nseg + (size_t)nseg * FD_NB : 0;
+    const size_t n_zero = H_WORDS + n_stamp + (size_t)nseg + n_dense;
+    const size_t n_int = n_zero + 3 * (size_t)nseg + (may_overflow ? 6 * (size_t)nseg + 3 * (size_t)B + 4 : 0);
     const size_t n_u64 = may_overflow ? 4 * (size_t)nseg + ROUND_TIMES : 0;
     const size_t n_hist = may_overflow ? (size_t)nseg * ROUND_NB : 0;
     SSDK_TRY(ssdk_ensure(ctx, &ctx->ws_counts, 16 + n_u64 * 8 + (n_int + n_hist) * 4));
@@ -1163,14 +1473,18 @@ static int postprocess_impl(ssdk_ctx* ctx, const HeadGeom* head, const float* co
     unsigned long long* cand = (unsigned long long*)ctx->ws_cand.p;
     unsigned long long* w64 = (unsigned long long*)ctx->ws_counts.p;
     int* hdr = (int*)(w64 + n_u64);
-    int* seg_count = hdr + H_WORDS + n_stamp;
-    int* seg_kept = seg_count + nseg;
+    int* stamps = hdr + H_WORDS;
+    int* img_dense = use_dense ? stamps + n_stamp : nullptr;
+    int* seg_count = stamps + n_stamp + (use_dense ? B : 0);
+    int* seg_count_dense = use_dense ? seg_count + nseg : nullptr;
+    unsigned* vhist = use_dense ? (unsigned*)(seg_count_dense + nseg) : nullptr;
+    int* seg_kept = hdr + n_zero;
     int* heavy_queue = seg_kept + nseg;
     int* pend_queue = heavy_queue + nseg;
     float4* seg_box = (float4*)ctx->ws_seg.p;
     float* seg_score = (float*)(seg_box + seg_elems);
     int* seg_anchor = (int*)(seg_score + seg_elems);
-    SSDK_CHECK_CUDA(cudaMemsetAsync(hdr, 0, (H_WORDS + n_stamp + (size_t)nseg) * sizeof(int), ctx->stream));
+    SSDK_CHECK_CUDA(cudaMemsetAsync(hdr, 0, n_zero * sizeof(int), ctx->stream));
     if (per_image == 0) SSDK_CHECK_CUDA(cudaMemsetAsync(seg_kept, 0, (size_t)nseg * sizeof(int), ctx->stream));
 
     const float thr = (float)score_threshold;
@@ -1207,8 +1521,21 @@ static int postprocess_impl(ssdk_ctx* ctx, const HeadGeom* head, const float* co
             const dim3 fgrid((unsigned)gx, B);
             const size_t sat_img = sat_bytes(C);
             SSDK_KERNEL(ctx, SSDK_K_FILTER,
-                if (is_logits) filter_kernel<true><<<fgrid, FILTER_THREADS, sat_img, ctx->stream>>>(scores, per_image, C, thr, x_lo, fmt, cand, seg_count);
-                else filter_kernel<false><<<fgrid, FILTER_THREADS, sat_img, ctx->stream>>>(scores, per_image, C, thr, x_lo, fmt, cand, seg_count));
+                if (is_logits) filter_kernel<true><<<fgrid, FILTER_THREADS, sat_img, ctx->stream>>>(scores, per_image, C, thr, x_lo, fmt, cand, seg_count, img_dense);
+                else filter_kernel<false><<<fgrid, FILTER_THREADS, sat_img, ctx->stream>>>(scores, per_image, C, thr, x_lo, fmt, cand, seg_count, img_dense));
+            if (use_dense) {
+                // images that filter_kernel found dense are redone with per-tile aggregation; a no-op otherwise (a small
+                // persistent grid: six CTAs per SM in total, each walks its share of the image's tiles)
+                long long dgx = ((long long)ctx->num_sms * 6 + B - 1) / B;
+                if (dgx > chunks) dgx = chunks;
+                if (dgx < 1) dgx = 1;
+                const dim3 dgrid((unsigned)dgx, B);
+                const size_t dsmem = ((size_t)2 * C + (size_t)(C + 31) / 32 + (size_t)C * FD_NB) * sizeof(int);
+                SSDK_TRY(ssdk_set_max_smem(ctx, is_logits ? (const void*)filter_dense_kernel<true> : (const void*)filter_dense_kernel<false>, (int)dsmem));
+                SSDK_KERNEL(ctx, SSDK_K_SORT,
+                    if (is_logits) filter_dense_kernel<true><<<dgrid, FILTER_THREADS, dsmem, ctx->stream>>>(scores, per_image, C, thr, x_lo, fmt, cand, seg_count_dense, img_dense, vhist);
+                    else filter_dense_kernel<false><<<dgrid, FILTER_THREADS, dsmem, ctx->stream>>>(scores, per_image, C, thr, x_lo, fmt, cand, seg_count_dense, img_dense, vhist));
+            }
         }
 
         // 2.-3. NMS: one warp per small segment (<= 32 candidates, sorted with shuffles), then one CTA per queued heavy
@@ -1226,14 +1553,16 @@ static int postprocess_impl(ssdk_ctx* ctx, const HeadGeom* head, const float* co
         N.A = A; N.C = C; N.K = K;
         N.iou_thr = (float)iou_threshold;
         N.seg_box = seg_box; N.seg_score = seg_score; N.seg_anchor = seg_anchor;
+        SegCounts SC;
+        SC.sparse = seg_count; SC.dense = seg_count_dense; SC.img_dense = img_dense;
         const int nms_slot = ctx->profiling ? ssdk_prof_begin(ctx, SSDK_K_NMS) : -1;
 #define SSDK_LAUNCH_NMS(DEC)                                                                                                  \
         do {                                                                                                                  \
             SSDK_TRY(ssdk_set_max_smem(ctx, (const void*)nms_kernel<DEC>, (int)nms_smem));                                   \
             nms_small_kernel<DEC><<<sgrid_nms, NMS_SMALL_WARPS * 32, 0, ctx->stream>>>(                                      \
-                cand, fmt, seg_count, N.codes, N.anchors, A, nseg, C, K, N.iou_thr, seg_box, seg_score, seg_anchor, seg_kept,  \
+                cand, fmt, SC, N.codes, N.anchors, A, nseg, C, K, N.iou_thr, seg_box, seg_score, seg_anchor, seg_kept,        \
                 heavy_queue, pend_queue, hdr);                                                                                \
-            nms_kernel<DEC><<<(int)hgrid, NMS_THREADS, nms_smem, ctx->stream>>>(cand, seg_count, N, seg_kept, heavy_queue, hdr); \
+            nms_kernel<DEC><<<(int)hgrid, NMS_THREADS, nms_smem, ctx->stream>>>(cand, SC, N, seg_kept, heavy_queue, hdr);    \
         } while (0)
         if (decoded) SSDK_LAUNCH_NMS(true);
         else SSDK_LAUNCH_NMS(false);
@@ -1243,7 +1572,11 @@ static int postprocess_impl(ssdk_ctx* ctx, const HeadGeom* head, const float* co
         SSDK_CHECK_LAUNCH(ctx);
 
         // 4. rounds: segments that overflowed their region (dense scores); exits at once when there is none
+#ifdef SSDK_VARIANT_NO_ROUNDS
+        if (false) {
+#else
         if (may_overflow) {
+#endif
             RoundState R;
             memset(&R, 0, sizeof(R));
             R.hdr = hdr;
@@ -1254,7 +1587,12 @@ static int postprocess_impl(ssdk_ctx* ctx, const HeadGeom* head, const float* co
             R.fill = ip; ip += nseg;
             R.rem = ip; ip += nseg;
             R.beyond = ip; ip += nseg;
-            R.stamp_h = hdr + H_WORDS;
+            R.vcut = (float*)ip; ip += nseg;
+            R.vhist = vhist;
+            R.img_dense = img_dense;
+            R.vlim = is_logits ? x_lo : thr;
+            R.vwidth = FD_RANGE / (float)FD_NB;
+            R.stamp_h = stamps;
             R.stamp_c = R.stamp_h + B;
             R.list_h = ip; ip += 2 * (size_t)B;
             R.list_c = ip; ip += B;
@@ -1269,7 +1607,7 @@ static int postprocess_impl(ssdk_ctx* ctx, const HeadGeom* head, const float* co
             const HeadGeom G = head ? *head : ssdk_flat_geom(scores, codes, A, C);
             const bool tables = C <= ROUND_SMEM_MAX_C;
             size_t rsmem = nms_smem + 16;
-            if (tables) rsmem += (size_t)C * (3 * 8 + ROUND_NB * 4 + 4 + 2) + 16;
+            if (tables) rsmem += (size_t)C * (3 * 8 + ROUND_NB * 4 + 4 + 2) + 32;
             const void* fn = decoded ? (is_logits ? (const void*)nms_rounds_kernel<true, true> : (const void*)nms_rounds_kernel<true, false>)
                                      : (is_logits ? (const void*)nms_rounds_kernel<false, true> : (const void*)nms_rounds_kernel<false, false>);
             SSDK_TRY(ssdk_set_max_smem(ctx, fn, (int)rsmem));
