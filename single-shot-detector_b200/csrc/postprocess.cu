@@ -227,7 +227,7 @@ __device__ __forceinline__ void filter_group(const FilterEmit* __restrict__ E, u
 // ballot per iteration cost 15 % of the scan's bandwidth).
 template <bool IS_LOGITS, bool HEAD>
 __device__ __forceinline__ void scan_candidates(const float* __restrict__ base, long long count, const FilterEmit* __restrict__ E,
-                                                unsigned* sat, int* dense_flag) {
+                                                unsigned* sat, int* dense_flag, int* cta_stop) {
     const int lane = threadIdx.x & 31;
     const float lim = IS_LOGITS ? E->x_lo : E->thr;
     // peel to 16-byte alignment: head scalars | body float4 | tail scalars
@@ -270,14 +270,16 @@ __device__ __forceinline__ void scan_candidates(const float* __restrict__ base, 
 #pragma unroll
             for (int u = 0; u < FILTER_UNROLL; ++u) all = all && hit[u];
             if (all) {
-                *dense_flag = 1;
+                // one shared-memory exchange per warp, one global store per CTA (hundreds of thousands of stores to one word
+                // take 0.3 ms by themselves)
+                if ((int)(threadIdx.x & 31) == __ffs(__activemask()) - 1 && atomicExch(cta_stop, 1) == 0) *dense_flag = 1;
                 break;
             }
         }
 #pragma unroll
         for (int u = 0; u < FILTER_UNROLL; ++u) {
             if (!hit[u]) continue;
-            if (!HEAD && dense_flag && __ldcg(dense_flag)) { stop = true; continue; }
+            if (!HEAD && dense_flag && (*(volatile int*)cta_stop || __ldcg(dense_flag))) { stop = true; continue; }
             filter_group<IS_LOGITS, HEAD>(E, sat, v[u], head + ((i0 + u * FILTER_THREADS + threadIdx.x) << 2));
         }
     }
@@ -290,10 +292,12 @@ __global__ void __launch_bounds__(FILTER_THREADS, FILTER_MIN_CTAS) filter_kernel
     unsigned long long* __restrict__ cand, int* __restrict__ seg_count /*[B*C]*/, int* __restrict__ img_dense /*[B] or NULL*/) {
     extern __shared__ unsigned s_sat[];                                 // one bit per class of this image: segment seen past its capacity
     __shared__ FilterEmit s_emit;
+    __shared__ int s_stop;
     const int b = blockIdx.y;
     const int sat_bits = min(C, FILTER_SAT_WORDS * 32);
     for (int i = threadIdx.x; i < (sat_bits + 31) / 32; i += FILTER_THREADS) s_sat[i] = 0u;
     if (threadIdx.x == 0) {
+        s_stop = 0;
         FilterEmit e;
         e.cand = cand; e.seg_count = seg_count; e.seg0 = (long long)b * C; e.sat_seg0 = e.seg0; e.sat_bits = sat_bits;
         e.C = C; e.head = 0; e.fmt = fmt; e.thr = thr; e.x_lo = x_lo;
@@ -301,7 +305,7 @@ __global__ void __launch_bounds__(FILTER_THREADS, FILTER_MIN_CTAS) filter_kernel
         s_emit = e;
     }
     __syncthreads();
-    scan_candidates<IS_LOGITS, false>(scores + (size_t)b * per_image, per_image, &s_emit, s_sat, img_dense ? img_dense + b : nullptr);
+    scan_candidates<IS_LOGITS, false>(scores + (size_t)b * per_image, per_image, &s_emit, s_sat, img_dense ? img_dense + b : nullptr, &s_stop);
 }
 
 // Head layout (head-layout fusion, see head.cu): grid (gx, num_levels); level blockIdx.y's class tensor [B, n*C, h, w] (or
@@ -325,7 +329,7 @@ __global__ void __launch_bounds__(FILTER_THREADS, FILTER_MIN_CTAS) head_filter_k
         s_emit = e;
     }
     __syncthreads();
-    scan_candidates<IS_LOGITS, true>(G.cls[l], count, &s_emit, s_sat, nullptr);
+    scan_candidates<IS_LOGITS, true>(G.cls[l], count, &s_emit, s_sat, nullptr, nullptr);
 }
 
 // ---------------------------------------------------------------------------------------------- 1b. dense images
@@ -915,6 +919,87 @@ __device__ __forceinline__ void cta_scan(const float* __restrict__ base, int cou
     }
 }
 
+// The same scan for a SPARSE survivor set (the collect pass: ~1 % of a dense image lies above the class-independent bound):
+// handling the survivors where they are found means a ~100-instruction path (index arithmetic, sigmoid, 64-bit key compares,
+// the append) executed by one or two lanes of a warp, several times per iteration -- 0.54 ms per pass over the stress
+// configuration.  Here every warp compacts its survivors (value, element index) into a small shared-memory queue and handles
+// 32 of them at a time with all lanes busy.
+#define SCAN_QUEUE 128                 // entries per warp; an iteration adds at most 512, normally < 16
+struct ScanQueueEntry { float v; int r; };
+template <typename Emit>
+__device__ __forceinline__ void cta_scan_compact(const float* __restrict__ base, int count, float lim, ScanQueueEntry* queue /*[SCAN_QUEUE] of this warp*/,
+                                                 Emit emit) {
+    const int tid = threadIdx.x, lane = tid & 31;
+    const unsigned mis = (unsigned)(((uintptr_t)base >> 2) & 3);
+    int head = mis ? (int)(4 - mis) : 0;
+    if (head > count) head = count;
+    const int nbody4 = (count - head) >> 2;
+    const int tail0 = head + (nbody4 << 2);
+    const float4* body = (const float4*)(base + head);
+    if (tid < 32) {
+        int r = -1;
+        if (tid < head) r = tid;
+        else if (tid - head < count - tail0) r = tail0 + (tid - head);
+        if (r >= 0 && base[r] > lim) emit(r, base[r]);
+    }
+    int qn = 0;                                                            // warp-uniform
+    for (int i0 = 0; i0 < nbody4; i0 += NMS_THREADS * FILTER_UNROLL) {      // trip count uniform over the CTA
+        float4 v[FILTER_UNROLL];
+#pragma unroll
+        for (int u = 0; u < FILTER_UNROLL; ++u) {
+            const int i = i0 + u * NMS_THREADS + tid;
+            v[u] = i < nbody4 ? ld_stream_f4(body + i) : make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+        }
+        float mx = -INFINITY;
+#pragma unroll
+        for (int u = 0; u < FILTER_UNROLL; ++u) mx = fmaxf(mx, fmaxf(fmaxf(v[u].x, v[u].y), fmaxf(v[u].z, v[u].w)));
+        if (!__any_sync(0xffffffffu, mx > lim)) continue;
+        const float vals[4 * FILTER_UNROLL] = {v[0].x, v[0].y, v[0].z, v[0].w, v[1].x, v[1].y, v[1].z, v[1].w,
+                                                v[2].x, v[2].y, v[2].z, v[2].w, v[3].x, v[3].y, v[3].z, v[3].w};
+        static_assert(FILTER_UNROLL == 4, "vals[] spells out four float4");
+        int cnt = 0;
+#pragma unroll
+        for (int k = 0; k < 4 * FILTER_UNROLL; ++k) cnt += vals[k] > lim ? 1 : 0;
+        int incl = cnt;                                                    // inclusive prefix sum over the lanes
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        const int total = __shfl_sync(0xffffffffu, incl, 31);
+        if (qn + total > SCAN_QUEUE) {
+            // (never in practice) more survivors than the queue takes: handle this iteration's where they are
+#pragma unroll
+            for (int k = 0; k < 4 * FILTER_UNROLL; ++k)
+                if (vals[k] > lim) emit(head + ((i0 + (k >> 2) * NMS_THREADS + tid) << 2) + (k & 3), vals[k]);
+            continue;
+        }
+        int pos = qn + incl - cnt;
+#pragma unroll
+        for (int k = 0; k < 4 * FILTER_UNROLL; ++k) {
+            if (vals[k] > lim) {
+                queue[pos].v = vals[k];
+                queue[pos].r = head + ((i0 + (k >> 2) * NMS_THREADS + tid) << 2) + (k & 3);
+                ++pos;
+            }
+        }
+        qn += total;
+        __syncwarp();
+        while (qn >= 32) {                                                 // 32 survivors, one per lane
+            const ScanQueueEntry e = queue[qn - 32 + lane];
+            qn -= 32;
+            __syncwarp();
+            emit(e.r, e.v);
+        }
+    }
+    __syncwarp();
+    if (lane < qn) {
+        const ScanQueueEntry e = queue[lane];
+        emit(e.r, e.v);
+    }
+    __syncwarp();
+}
+
 // per-class tables of one image during a streaming pass (shared memory when C <= ROUND_SMEM_MAX_C, else read from global)
 struct ClassTables {
     unsigned char* st;             // [C]
@@ -928,11 +1013,14 @@ struct ClassTables {
 };
 
 template <bool DECODED, bool IS_LOGITS>
-__global__ void __launch_bounds__(NMS_THREADS) nms_rounds_kernel(const HeadGeom G, int B, float thr, float x_lo, unsigned long long* __restrict__ cand,
+__global__ void __launch_bounds__(NMS_THREADS, 2) nms_rounds_kernel(const HeadGeom G, int B, float thr, float x_lo, unsigned long long* __restrict__ cand,
                                                                  const NmsSegArgs N, int* __restrict__ seg_kept, const RoundState R) {
     extern __shared__ __align__(16) unsigned char nms_smem[];
     __shared__ NmsShared sh;
-    __shared__ float s_slot[4 * FILTER_UNROLL][NMS_THREADS];
+    __shared__ union {                                               // never in use at the same time
+        float slot[4 * FILTER_UNROLL][NMS_THREADS];                  // histogram pass (cta_scan)
+        ScanQueueEntry queue[NMS_THREADS / 32][SCAN_QUEUE];          // collect pass (cta_scan_compact)
+    } s_scan;
     const int npend = R.hdr[H_PEND];
     if (npend == 0) {                                                // the normal case: no segment overflowed its region
         if (blockIdx.x == 0 && threadIdx.x == 0) R.times[0] = 0ull;
@@ -971,36 +1059,41 @@ __global__ void __launch_bounds__(NMS_THREADS) nms_rounds_kernel(const HeadGeom 
     //      score above that) and the first round collects [0, mid) right away; the collect pass counts exactly, and a guess that
     //      turns out too generous falls back to the exact key-space histogram.  Every other segment starts with that histogram
     //      over [dlo0, k_thr).
-    for (int p = cta * NMS_THREADS + tid; p < npend; p += grid * NMS_THREADS) {
+    static_assert(FD_NB == 32 && ROUND_NB == 64, "one value-histogram bin and two key-histogram bins per lane");
+    for (int p = cta * (NMS_THREADS / 32) + (tid >> 5); p < npend; p += grid * (NMS_THREADS / 32)) {     // one warp per segment
         const int seg = R.pend_queue[p];
         const int b = seg / C;
-        R.lo[seg] = 0ull; R.beyond[seg] = 0; R.rem[seg] = 0; R.fill[seg] = 0;
-        seg_kept[seg] = 0;
-        for (int j = 0; j < ROUND_NB; ++j) R.hist[(size_t)seg * ROUND_NB + j] = 0u;
+        R.hist[(size_t)seg * ROUND_NB + lane] = 0u;
+        R.hist[(size_t)seg * ROUND_NB + 32 + lane] = 0u;
         bool guessed = false;
+        float v_cut = 0.0f, s_cut = 0.0f;
         if (R.vhist && R.img_dense[b]) {
-            const unsigned* vh = R.vhist + (size_t)seg * FD_NB;
-            long long cum = 0;
-            int jb = 0;
-            for (; jb < FD_NB; ++jb) {
-                cum += vh[jb];
-                if (cum >= ROUND_WANT + ROUND_WANT / 4) break;
+            long long incl = R.vhist[(size_t)seg * FD_NB + lane];            // inclusive prefix sums: bin 0 = the best values
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const long long t = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += t;
             }
+            const unsigned reach = __ballot_sync(0xffffffffu, incl >= ROUND_WANT + ROUND_WANT / 4);
+            const int jb = reach ? __ffs(reach) - 1 : FD_NB;
+            const long long cum = jb < FD_NB ? __shfl_sync(0xffffffffu, incl, jb) : 0;
             if (jb < FD_NB - 1 && cum <= SEG_CAP - SEG_CAP / 4) {
-                const float v_cut = R.vlim + (float)(FD_NB - 1 - jb) * R.vwidth;
-                float s_cut = v_cut;
+                v_cut = R.vlim + (float)(FD_NB - 1 - jb) * R.vwidth;
+                s_cut = v_cut;
                 if (IS_LOGITS) s_cut = __uint_as_float(__float_as_uint(f_div(1.0f, f_add(1.0f, expf(-v_cut)))) + 8u);
-                if (s_cut < 1.0f && s_cut > thr) {
-                    R.mid[seg] = (unsigned long long)order_desc(s_cut) << fmt.abits;     // keys < mid <=> score > s_cut
-                    R.vcut[seg] = v_cut;
-                    R.rem[seg] = 0x3fffffff;                                             // unknown: assume there is more
-                    R.st[seg] = ST_COLLECT;
-                    if (atomicExch(R.stamp_c + b, 1) != 1) R.list_c[atomicAdd(R.hdr + H_NIMG_C, 1)] = b;
-                    guessed = true;
-                }
+                guessed = s_cut < 1.0f && s_cut > thr;
             }
         }
-        if (!guessed) {
+        if (lane != 0) continue;
+        R.lo[seg] = 0ull; R.beyond[seg] = 0; R.rem[seg] = 0; R.fill[seg] = 0;
+        seg_kept[seg] = 0;
+        if (guessed) {
+            R.mid[seg] = (unsigned long long)order_desc(s_cut) << fmt.abits;             // keys < mid <=> score > s_cut
+            R.vcut[seg] = v_cut;
+            R.rem[seg] = 0x3fffffff;                                                     // unknown: assume there is more
+            R.st[seg] = ST_COLLECT;
+            if (atomicExch(R.stamp_c + b, 1) != 1) R.list_c[atomicAdd(R.hdr + H_NIMG_C, 1)] = b;
+        } else {
             R.st[seg] = ST_HIST; R.dlo[seg] = R.dlo0; R.dhi[seg] = R.k_thr;
             R.sh[seg] = ceil_log2_per_bin(R.k_thr - R.dlo0);
             atomicAdd(R.hdr + H_NHIST0 + 1, 1);
@@ -1064,7 +1157,7 @@ __global__ void __launch_bounds__(NMS_THREADS) nms_rounds_kernel(const HeadGeom 
                 const int blk = g.per_loc * g.C * g.hw;
                 const int r0 = (int)((long long)blk * slice / group), r1 = (int)((long long)blk * (slice + 1) / group);
                 const float* base = G.cls[l] + (size_t)b * blk;
-                cta_scan(base + r0, r1 - r0, IS_LOGITS ? x_lo : thr, s_slot, [&](int r, float v) {
+                cta_scan(base + r0, r1 - r0, IS_LOGITS ? x_lo : thr, s_scan.slot, [&](int r, float v) {
                     int a, c;
                     if (flat_geom) { a = (int)div_fast((unsigned)(r0 + r), g.d_c); c = r0 + r - a * C; }
                     else level_decompose(g, r0 + r, a, c);
@@ -1171,7 +1264,7 @@ __global__ void __launch_bounds__(NMS_THREADS) nms_rounds_kernel(const HeadGeom 
                 const int blk = g.per_loc * g.C * g.hw;
                 const int r0 = (int)((long long)blk * slice / group), r1 = (int)((long long)blk * (slice + 1) / group);
                 const float* base = G.cls[l] + (size_t)b * blk;
-                cta_scan(base + r0, r1 - r0, lim_c, s_slot, [&](int r, float v) {
+                cta_scan_compact(base + r0, r1 - r0, lim_c, s_scan.queue[tid >> 5], [&](int r, float v) {
                     int a, c;
                     if (flat_geom) { a = (int)div_fast((unsigned)(r0 + r), g.d_c); c = r0 + r - a * C; }
                     else level_decompose(g, r0 + r, a, c);

@@ -342,7 +342,6 @@ int ssdk_train_step_impl(ssdk_ctx* ctx, const HeadGeom& G, const float* anchors,
     int gx = (ctx->num_sms * 6 + B - 1) / B;                               // matcher work items per image (about 6 per SM in total)
     if (gx > nchunks_img) gx = nchunks_img;
     if (gx < 1) gx = 1;
-    const long long items = (long long)gx * B;
     long long grid = (long long)ctx->num_sms * occ;
     // Role split.  Automatic (the options' defaults) from the ratio of the matching work to the streaming work per (image,
     // anchor), both measured on a B200 with the kernels alone: matching 13.8 ps + 0.494 ps per ground-truth box (23.7 ps at
@@ -359,7 +358,13 @@ int ssdk_train_step_impl(ssdk_ctx* ctx, const HeadGeom& G, const float* anchors,
     }
     if (m > occ) m = occ;
     long long n_match = (long long)ctx->num_sms * m;
-    if (n_match > items) n_match = items;
+    // every matcher CTA should get the same number of work items: prefer an items-per-image count whose total is a multiple
+    // of the matcher CTAs (at 16 images and 296 matcher CTAs: 37 per image = 2 items each, instead of 56 = 3.03)
+    for (int g2 = gx; g2 >= (gx + 1) / 2 && g2 >= 1; --g2) {
+        if (((long long)g2 * B) % n_match == 0) { gx = g2; break; }
+    }
+    const long long items2 = (long long)gx * B;
+    if (n_match > items2) n_match = items2;
     if (n_match > grid - 1) n_match = grid - 1;
     if (n_match < 1) n_match = 1;
     long long n_flat = grid - n_match;

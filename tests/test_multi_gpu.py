@@ -62,6 +62,7 @@ if peer:
     for _ in range(4):
         r = step.replay()
         replays.append([float(r['localization_loss']), float(r['classification_loss'])])
+    step.release()                                   # teardown order: graphs first, then the process group (graph.CapturedStep.release)
     # head layout (per-level tower outputs) on the sharded batch, with the peer all-reduce
     from oracle import box_predictor as obp
     shapes = obp.level_shapes(H, W, gen.strides)
@@ -148,3 +149,23 @@ def test_two_gpu_sharded_equals_single(tmp_path):
     want = onms.batch_multiclass_non_max_suppression(codes, anchors, olosses.sigmoid(logits), 0.05, 0.5, 10)
     assert r0['num_boxes'] + r1['num_boxes'] == want[3].tolist()
     assert np.array_equal(np.array(r0['labels'] + r1['labels'], np.int32), want[2])
+
+
+def test_library_calls_leave_the_current_device_alone():
+    """ADVICE (round 1): a call on tensors of cuda:1 must not switch the thread's current device (one process driving several
+    GPUs); every entry point restores the caller's device (SsdkDeviceGuard)."""
+    if not torch.cuda.is_available() or torch.cuda.device_count() < 2:
+        pytest.skip('needs >= 2 GPUs')
+    import importlib
+    pkg = importlib.import_module('single-shot-detector_b200')
+    torch.cuda.set_device(0)
+    gen = pkg.AnchorGenerator()
+    a1 = gen(128, 160, device=torch.device('cuda', 1))
+    assert a1.device.index == 1 and torch.cuda.current_device() == 0
+    b = torch.rand([5, 4], device='cuda:1')
+    got = pkg.iou(b, a1[:7])
+    assert got.device.index == 1 and torch.cuda.current_device() == 0
+    x = torch.empty(3, device='cuda')
+    assert x.device.index == 0
+    a0 = gen(128, 160, device=torch.device('cuda', 0))
+    assert torch.equal(a0.cpu(), a1.cpu())
