@@ -64,6 +64,14 @@ SSDK_API int ssdk_ctx_set_stream(ssdk_ctx* ctx, void* stream);
 #define SSDK_OPT_FUSED_TRAIN_STEP 1
 #define SSDK_OPT_MATCH_CTAS_PER_SM 2
 #define SSDK_OPT_MATCH_FLAT_SHARE_PCT 3
+/* SSDK_OPT_TRAIN_CTAS_PER_SM (default 0 = as many as fit, six): resident CTAs per SM of the fused training-step kernel.  It is a
+ * persistent kernel that takes every CTA slot of the GPU; a caller that runs another sub-path on a second stream at the same time
+ * (graph.concurrent) can leave room for it with a smaller value. */
+#define SSDK_OPT_TRAIN_CTAS_PER_SM 4
+/* SSDK_OPT_PROGRAMMATIC_LAUNCH (default 1; environment SSDK_PDL): the kernels of the post-processing chain (dense-image filter,
+ * the NMS kernels, pack) are launched with programmatic dependent launch, so that each one's launch and prologue overlap its
+ * predecessor's tail; 0 = plain stream order.  Same results either way. */
+#define SSDK_OPT_PROGRAMMATIC_LAUNCH 5
 SSDK_API int ssdk_ctx_set_option(ssdk_ctx* ctx, int option, int value);
 SSDK_API int ssdk_ctx_destroy(ssdk_ctx* ctx);
 /* Bytes of private workspace currently held (grows on demand, never shrinks). */

@@ -1,0 +1,58 @@
+"""How should the two sub-paths of the bench step share the GPU?  Graph replays of the step with the sub-paths on two streams:
+issue order, stream priorities, resident CTAs per SM of the (persistent) training-step kernel."""
+import importlib, json, os, sys
+import numpy as np, torch
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+pkg = importlib.import_module('single-shot-detector_b200')
+syn = importlib.import_module('single-shot-detector_b200.synthetic')
+L = pkg._lib
+cfg = syn.CONFIGS[2]
+H, W, C, Bt, G = cfg['H'], cfg['W'], cfg['C'], cfg['B'], cfg['G']
+Bi = syn.CONFIGS[3]['B']
+gen = pkg.AnchorGenerator(scale_multipliers=cfg['scale_multipliers'])
+anchors = gen(H, W)
+A = anchors.shape[0]
+g = torch.Generator(device='cuda').manual_seed(2)
+gt = {k: torch.from_numpy(v).cuda() for k, v in syn.make_groundtruth(2, Bt, G, H, W, C).items()}
+tlog = torch.randn([Bt, A, C], device='cuda', generator=g) - 4.595
+tcod = torch.randn([Bt, A, 4], device='cuda', generator=g)
+ilog = torch.randn([Bi, A, C], device='cuda', generator=g) - 7.0
+igt = syn.make_groundtruth(3, Bi, G, H, W, C)
+anc_np = anchors.cpu().numpy()
+for b in range(Bi):
+    sim = syn._pair_iou(igt['boxes'][b], anc_np)
+    for gi in range(G):
+        idx = torch.from_numpy(np.nonzero(sim[gi] >= 0.4)[0]).cuda()
+        ilog[b, idx, int(igt['labels'][b, gi])] = 1.5 + 1.5 * torch.randn([idx.numel()], device='cuda', generator=g)
+icod = torch.randn([Bi, A, 4], device='cuda', generator=g)
+st = pkg.SSD.from_predictions(H, W, {'encoded_boxes': tcod, 'class_predictions': tlog}, gen, C)
+si = pkg.SSD.from_predictions(H, W, {'encoded_boxes': icod, 'class_predictions': ilog}, gen, C)
+params = {'gamma': 2.0, 'alpha': 0.25}
+train = lambda: st.loss(gt, params)
+infer = lambda: si.get_predictions(0.05, 0.5, 100)
+
+def timeit(fn, reps=40):
+    cap = pkg.graph.capture(fn, warmup=2)
+    best = 1e9
+    for _ in range(4):
+        for _ in range(3): cap.replay()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps): cap.replay()
+        e1.record(); torch.cuda.synchronize()
+        best = min(best, e0.elapsed_time(e1) / reps)
+    cap.release()
+    return round(best, 5)
+
+out = {'train': timeit(train), 'infer': timeit(infer), 'sequential': timeit(lambda: (train(), infer()))}
+for ctas in (0, 5, 4, 3):
+    L.set_option(L.SSDK_OPT_TRAIN_CTAS_PER_SM, ctas)
+    out['train_ctas%d' % ctas] = timeit(train)
+    for name, fns, pr in (('train_first', (train, infer), None), ('infer_first', (infer, train), None),
+                          ('infer_first_hi', (infer, train), (-1, 0)), ('train_first_infer_hi', (train, infer), (0, -1)),
+                          ('train_first_hi', (train, infer), (-1, 0))):
+        out['ctas%d_%s' % (ctas, name)] = timeit(pkg.graph.concurrent(*fns, priorities=pr))
+L.set_option(L.SSDK_OPT_TRAIN_CTAS_PER_SM, 0)
+print(json.dumps(out))

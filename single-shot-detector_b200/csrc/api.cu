@@ -175,6 +175,8 @@ int ssdk_ctx_create(int device, void* stream, ssdk_ctx** out) {
     c->tune_loss_ctas = env_int("SSDK_LOSS_CTAS", 0, 1, 8, 1);            // the partials buffer holds num_sms * 8 CTAs
     c->match_ctas_per_sm = env_int("SSDK_MATCH_CTAS", 0, 0, 7, 1);
     c->match_flat_share_pct = env_int("SSDK_MATCH_FLAT_SHARE", -1, -1, 100, 1);
+    c->train_ctas_per_sm = env_int("SSDK_TRAIN_CTAS", 0, 0, 8, 1);
+    c->use_pdl = env_int("SSDK_PDL", 1, 0, 1, 1);
     *out = c;
     return SSDK_OK;
 }
@@ -186,6 +188,11 @@ int ssdk_ctx_set_option(ssdk_ctx* ctx, int option, int value) {
         case SSDK_OPT_MATCH_CTAS_PER_SM:
             SSDK_REQUIRE(value >= 0 && value <= 7, SSDK_ERR_ARG, "SSDK_OPT_MATCH_CTAS_PER_SM must be in [0,7] (got %d)", value);
             ctx->match_ctas_per_sm = value;
+            return SSDK_OK;
+        case SSDK_OPT_PROGRAMMATIC_LAUNCH: ctx->use_pdl = value ? 1 : 0; return SSDK_OK;
+        case SSDK_OPT_TRAIN_CTAS_PER_SM:
+            SSDK_REQUIRE(value >= 0 && value <= 8, SSDK_ERR_ARG, "SSDK_OPT_TRAIN_CTAS_PER_SM must be in [0,8] (got %d)", value);
+            ctx->train_ctas_per_sm = value;
             return SSDK_OK;
         case SSDK_OPT_MATCH_FLAT_SHARE_PCT:
             SSDK_REQUIRE(value >= -1 && value <= 100, SSDK_ERR_ARG, "SSDK_OPT_MATCH_FLAT_SHARE_PCT must be in [-1,100] (got %d)", value);

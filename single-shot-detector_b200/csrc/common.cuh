@@ -4,6 +4,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <stdarg.h>
+#include <string.h>
 
 #include "../../include/ssdk.h"
 
@@ -49,6 +50,8 @@ struct ssdk_ctx {
     int fused_train_step = 1;      // SSDK_OPT_FUSED_TRAIN_STEP
     int match_ctas_per_sm = 0;     // SSDK_OPT_MATCH_CTAS_PER_SM (0 = automatic)
     int match_flat_share_pct = -1; // SSDK_OPT_MATCH_FLAT_SHARE_PCT (-1 = automatic)
+    int train_ctas_per_sm = 0;     // SSDK_OPT_TRAIN_CTAS_PER_SM (0 = as many as fit)
+    int use_pdl = 1;               // SSDK_OPT_PROGRAMMATIC_LAUNCH: chain the post-processing kernels with programmatic dependent launch
     // tuning knobs, read from the environment ONCE (ssdk_ctx_create) and validated there; 0 = automatic
     int tune_head_ctas = 0, tune_loss_rpw = 0, tune_loss_stages = 0, tune_loss_ctas = 0;
     unsigned long long* round_times = nullptr;   // inside ws_counts: phase timestamps of the last dense-segment rounds (ssdk_ctx_round_times)
@@ -235,6 +238,31 @@ __device__ __forceinline__ bool nms_iou_greater(const float4 bi, const float4 bj
     const float iou = f_div(inter, f_sub(f_add(area_i, area_j), inter));
     return iou > thr;
 }
+
+// Programmatic dependent launch (sm_90+): a kernel launched with the programmatic-serialization attribute may start while its
+// predecessor in the stream is still running; it must execute pdl_wait() before it touches anything the predecessor wrote (the
+// wait returns once the predecessor grid has completed and its memory is visible).  pdl_launch_dependents() in the predecessor
+// allows the successor's launch as soon as every one of its own CTAs has got that far.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+#ifdef __CUDACC__
+#include <utility>
+// kernel<<<grid, block, smem, ctx->stream>>>(args...) with the programmatic-serialization attribute when `pdl` (and the context allows it)
+template <typename... KArgs, typename... Args>
+static inline cudaError_t ssdk_launch(ssdk_ctx* ctx, bool pdl, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, Args&&... args) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = ctx->stream;
+    cudaLaunchAttribute at[1];
+    memset(at, 0, sizeof(at));
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = (pdl && ctx->use_pdl) ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
+#endif
 
 // streaming (read-once) 128-bit load that does not allocate in L1
 __device__ __forceinline__ float4 ld_stream_f4(const float4* p) {

@@ -177,6 +177,9 @@ __device__ __forceinline__ void head_decompose(const LevelGeom g, long long e, i
 #ifndef FILTER_MIN_CTAS
 #define FILTER_MIN_CTAS 4              // at most 64 registers
 #endif
+#define FD_U 4
+#define FD_NB 32                       // bins of filter_dense_kernel's per-segment value histograms
+#define FD_RANGE 19.0f                 // logits: sigmoid(lim + 19) rounds to 1 for every usual threshold; scores: (thr, 1] is a subset
 struct FilterEmit {
     unsigned long long* cand;
     int* seg_count;
@@ -227,7 +230,7 @@ __device__ __forceinline__ void filter_group(const FilterEmit* __restrict__ E, u
 // ballot per iteration cost 15 % of the scan's bandwidth).
 template <bool IS_LOGITS, bool HEAD>
 __device__ __forceinline__ void scan_candidates(const float* __restrict__ base, long long count, const FilterEmit* __restrict__ E,
-                                                unsigned* sat, int* dense_flag, int* cta_stop) {
+                                                unsigned* sat, int* dense_flag, int* cta_stop /*[2]: stop, won*/) {
     const int lane = threadIdx.x & 31;
     const float lim = IS_LOGITS ? E->x_lo : E->thr;
     // peel to 16-byte alignment: head scalars | body float4 | tail scalars
@@ -249,37 +252,44 @@ __device__ __forceinline__ void scan_candidates(const float* __restrict__ base, 
 
     const long long stride = (long long)gridDim.x * FILTER_THREADS * FILTER_UNROLL;
     bool stop = false;
-    for (long long i0 = (long long)blockIdx.x * FILTER_THREADS * FILTER_UNROLL; i0 < nbody4 && !stop; i0 += stride) {
+    // the thread's load address advances by a constant (kept as a pointer: recomputing it from the loop index put eight
+    // dependent integer instructions in front of every iteration's first load)
+    const float4* ptr = body + (long long)blockIdx.x * FILTER_THREADS * FILTER_UNROLL + threadIdx.x;
+    for (long long i0 = (long long)blockIdx.x * FILTER_THREADS * FILTER_UNROLL; i0 < nbody4 && !stop; i0 += stride, ptr += stride) {
         float4 v[FILTER_UNROLL];
         bool inb[FILTER_UNROLL];
 #pragma unroll
         for (int u = 0; u < FILTER_UNROLL; ++u) {
             const long long i = i0 + u * FILTER_THREADS + threadIdx.x;
             inb[u] = i < nbody4;
-            v[u] = inb[u] ? ld_stream_f4(body + i) : make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
-        }
-        bool hit[FILTER_UNROLL];
-#pragma unroll
-        for (int u = 0; u < FILTER_UNROLL; ++u) hit[u] = inb[u] && fmaxf(fmaxf(v[u].x, v[u].y), fmaxf(v[u].z, v[u].w)) > lim;
-        if (!HEAD && dense_flag) {
-            // a thread ALL of whose four groups (4 KB apart) hold a possible candidate sits in a dense image: with 5 % of the
-            // elements above the threshold that happens to 0.1 % of the threads, with 20 % to every tenth -- and with a few
-            // confident anchors per image never (their classes cannot line up in all four 4-class windows).  Checked BEFORE
-            // anything is appended: in a dense image every thread would otherwise start with a burst of contended atomics.
-            bool all = true;
-#pragma unroll
-            for (int u = 0; u < FILTER_UNROLL; ++u) all = all && hit[u];
-            if (all) {
-                // one shared-memory exchange per warp, one global store per CTA (hundreds of thousands of stores to one word
-                // take 0.3 ms by themselves)
-                if ((int)(threadIdx.x & 31) == __ffs(__activemask()) - 1 && atomicExch(cta_stop, 1) == 0) *dense_flag = 1;
-                break;
-            }
+            v[u] = inb[u] ? ld_stream_f4(ptr + u * FILTER_THREADS) : make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
         }
 #pragma unroll
         for (int u = 0; u < FILTER_UNROLL; ++u) {
-            if (!hit[u]) continue;
-            if (!HEAD && dense_flag && (*(volatile int*)cta_stop || __ldcg(dense_flag))) { stop = true; continue; }
+            const float mx = fmaxf(fmaxf(v[u].x, v[u].y), fmaxf(v[u].z, v[u].w));
+            if (__builtin_expect(!(inb[u] && (mx > lim)), 1)) continue;   // (the hint moves the candidate code out of the loop body)
+            if (!HEAD && dense_flag) {
+                if (stop) continue;
+                if (u == 0) {
+                    // a thread ALL of whose four groups (4 KB apart) hold a possible candidate sits in a dense image: with 5 %
+                    // of the elements above the threshold that happens to 0.1 % of the threads, with 20 % to every tenth --
+                    // and with a few confident anchors per image never (their classes cannot line up in all four 4-class
+                    // windows).  Checked BEFORE anything is appended: in a dense image every thread would otherwise start
+                    // with a burst of contended atomics.  One shared-memory exchange per warp, one global one per CTA
+                    // (hundreds of thousands of stores to one word take 0.3 ms by themselves).
+                    bool all = true;
+#pragma unroll
+                    for (int w = 1; w < FILTER_UNROLL; ++w)
+                        all = all && inb[w] && fmaxf(fmaxf(v[w].x, v[w].y), fmaxf(v[w].z, v[w].w)) > lim;
+                    if (all) {
+                        if ((int)(threadIdx.x & 31) == __ffs(__activemask()) - 1 && atomicExch(cta_stop, 1) == 0)
+                            cta_stop[1] = atomicExch(dense_flag, 1) == 0 ? 1 : 0;    // the first CTA of the image to notice
+                        stop = true;
+                        continue;
+                    }
+                }
+                if (*(volatile int*)cta_stop || __ldcg(dense_flag)) { stop = true; continue; }
+            }
             filter_group<IS_LOGITS, HEAD>(E, sat, v[u], head + ((i0 + u * FILTER_THREADS + threadIdx.x) << 2));
         }
     }
@@ -289,15 +299,17 @@ __device__ __forceinline__ void scan_candidates(const float* __restrict__ base, 
 template <bool IS_LOGITS>
 __global__ void __launch_bounds__(FILTER_THREADS, FILTER_MIN_CTAS) filter_kernel(
     const float* __restrict__ scores, long long per_image /*A*C*/, int C, float thr, float x_lo, KeyFormat fmt,
-    unsigned long long* __restrict__ cand, int* __restrict__ seg_count /*[B*C]*/, int* __restrict__ img_dense /*[B] or NULL*/) {
+    unsigned long long* __restrict__ cand, int* __restrict__ seg_count /*[B*C]*/, int* __restrict__ img_dense /*[B] or NULL*/,
+    int* __restrict__ seg_count_dense, unsigned* __restrict__ vhist) {
     extern __shared__ unsigned s_sat[];                                 // one bit per class of this image: segment seen past its capacity
     __shared__ FilterEmit s_emit;
-    __shared__ int s_stop;
+    __shared__ int s_stop[2];
+    pdl_launch_dependents();
     const int b = blockIdx.y;
     const int sat_bits = min(C, FILTER_SAT_WORDS * 32);
     for (int i = threadIdx.x; i < (sat_bits + 31) / 32; i += FILTER_THREADS) s_sat[i] = 0u;
     if (threadIdx.x == 0) {
-        s_stop = 0;
+        s_stop[0] = s_stop[1] = 0;
         FilterEmit e;
         e.cand = cand; e.seg_count = seg_count; e.seg0 = (long long)b * C; e.sat_seg0 = e.seg0; e.sat_bits = sat_bits;
         e.C = C; e.head = 0; e.fmt = fmt; e.thr = thr; e.x_lo = x_lo;
@@ -305,7 +317,16 @@ __global__ void __launch_bounds__(FILTER_THREADS, FILTER_MIN_CTAS) filter_kernel
         s_emit = e;
     }
     __syncthreads();
-    scan_candidates<IS_LOGITS, false>(scores + (size_t)b * per_image, per_image, &s_emit, s_sat, img_dense ? img_dense + b : nullptr, &s_stop);
+    scan_candidates<IS_LOGITS, false>(scores + (size_t)b * per_image, per_image, &s_emit, s_sat, img_dense ? img_dense + b : nullptr, s_stop);
+    if (img_dense) {
+        // the CTA that declared the image dense prepares filter_dense_kernel's counters and value histograms for it (they are
+        // not part of the per-call memset: zeroing 128 bytes per segment on every call cost 2-3 us of the sparse path)
+        __syncthreads();
+        if (s_stop[1]) {
+            for (int i = threadIdx.x; i < C * FD_NB; i += FILTER_THREADS) vhist[(size_t)b * C * FD_NB + i] = 0u;
+            for (int c = threadIdx.x; c < C; c += FILTER_THREADS) seg_count_dense[(size_t)b * C + c] = 0;
+        }
+    }
 }
 
 // Head layout (head-layout fusion, see head.cu): grid (gx, num_levels); level blockIdx.y's class tensor [B, n*C, h, w] (or
@@ -317,6 +338,7 @@ __global__ void __launch_bounds__(FILTER_THREADS, FILTER_MIN_CTAS) head_filter_k
                                                                     int* __restrict__ seg_count) {
     extern __shared__ unsigned s_sat[];                                 // one bit per (image, class) segment (the first 65536 of them)
     __shared__ FilterEmit s_emit;
+    pdl_launch_dependents();
     const int l = blockIdx.y;
     const LevelGeom g = level_geom(G, l);
     const long long count = (long long)B * g.per_loc * g.C * g.hw;
@@ -344,9 +366,6 @@ __global__ void __launch_bounds__(FILTER_THREADS, FILTER_MIN_CTAS) head_filter_k
 // At the end the value histograms of the saturated classes are added to the global ones: nms_rounds_kernel uses them to GUESS
 // the value above which a region's worth of the best candidates lies, so that its first round needs no histogram pass of its
 // own; the guess only has to be good, not exact (the collect pass counts).
-#define FD_U 4
-#define FD_NB 32
-#define FD_RANGE 19.0f                 // logits: sigmoid(lim + 19) rounds to 1 for every usual threshold; scores: (thr, 1] is a subset
 __device__ __forceinline__ int value_bin(float v, float lim, float inv_w) {      // bin 0 = the best values
     const int b = FD_NB - 1 - (int)((v - lim) * inv_w);
     return b < 0 ? 0 : (b > FD_NB - 1 ? FD_NB - 1 : b);
@@ -358,6 +377,8 @@ __global__ void __launch_bounds__(FILTER_THREADS) filter_dense_kernel(
     unsigned* __restrict__ vhist /*[B*C][FD_NB]*/) {
     extern __shared__ int s_dense[];
     const int b = blockIdx.y, tid = threadIdx.x;
+    pdl_wait();                                             // img_dense is written by filter_kernel
+    pdl_launch_dependents();
     if (!img_dense[b]) return;
     int* s_cnt = s_dense;                                   // [C]
     int* s_base = s_dense + C;                              // [C]
@@ -581,6 +602,8 @@ __global__ void __launch_bounds__(NMS_SMALL_WARPS * 32) nms_small_kernel(
     __shared__ float s_tile_area[NMS_SMALL_WARPS][32];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const long long seg = (long long)blockIdx.x * NMS_SMALL_WARPS + warp;
+    pdl_wait();                                             // candidates and counters come from the filter kernels
+    pdl_launch_dependents();
     if (seg >= nseg) return;
     const int n = seg_candidates(SC, seg, C);
     if (n <= 0) {
@@ -793,6 +816,8 @@ __global__ void __launch_bounds__(NMS_THREADS) nms_kernel(const unsigned long lo
     unsigned long long* s_sort = (unsigned long long*)nms_smem;     // [SEG_CAP]
     NmsBox* s_kept = (NmsBox*)(s_sort + SEG_CAP);                   // [K]
     float* s_kept_area = (float*)(s_kept + N.K);                    // [K]
+    pdl_wait();                                                     // the queue comes from nms_small_kernel
+    pdl_launch_dependents();
     const int nheavy = hdr[H_HEAVY];
     for (int item = blockIdx.x; item < nheavy; item += gridDim.x) {
         const long long seg = heavy_queue[item];
@@ -1021,6 +1046,8 @@ __global__ void __launch_bounds__(NMS_THREADS, 2) nms_rounds_kernel(const HeadGe
         float slot[4 * FILTER_UNROLL][NMS_THREADS];                  // histogram pass (cta_scan)
         ScanQueueEntry queue[NMS_THREADS / 32][SCAN_QUEUE];          // collect pass (cta_scan_compact)
     } s_scan;
+    pdl_wait();                                                      // queues, counters and kept boxes come from the kernels before
+    pdl_launch_dependents();
     const int npend = R.hdr[H_PEND];
     if (npend == 0) {                                                // the normal case: no segment overflowed its region
         if (blockIdx.x == 0 && threadIdx.x == 0) R.times[0] = 0ull;
@@ -1358,6 +1385,7 @@ __global__ void __launch_bounds__(256) pack_kernel(const float4* __restrict__ se
     extern __shared__ int s_off[];   // [C+1] exclusive prefix sums of the per-class kept counts, then [C] the counts
     int* kept = s_off + C + 1;
     const int b = blockIdx.y;
+    pdl_wait();                      // the per-segment results come from the NMS kernels
     // Post-path consumers folded in (model.py:67-68, inference/detector.py:54-58): boxes /= box_scaler[b], and a final
     // `scores > final_thr` filter.  Inside a class the kept scores are descending, so the survivors of that filter are a
     // prefix of every class segment and the class-major order is preserved, exactly as the reference's boolean mask does.
@@ -1449,6 +1477,7 @@ __global__ void __launch_bounds__(256) pack_by_label_kernel(const float4* __rest
     __shared__ int s_base;
     const int c = blockIdx.x, tid = threadIdx.x;
     const size_t cap = (size_t)B * K;
+    pdl_wait();
     if (tid == 0) s_base = 0;
     __syncthreads();
     for (int b0 = 0; b0 < B; b0 += 256) {
@@ -1552,12 +1581,12 @@ static int postprocess_impl(ssdk_ctx* ctx, const HeadGeom* head, const float* co
     SSDK_TRY(ssdk_ensure(ctx, &ctx->ws_cand, (size_t)nseg * SEG_CAP * sizeof(unsigned long long)));
     // dense images (anchor-major tensors only): redone by filter_dense_kernel with its own counters and value histograms
     const bool use_dense = may_overflow && !head && C <= 1024;
-    // int words zeroed by ONE memset per call: header | round stamps [2B] | dense-image flags [B] | seg_count [nseg] |
-    // seg_count_dense [nseg] | value histograms [nseg][FD_NB]
+    // int words zeroed by ONE memset per call: header | round stamps [2B] | dense-image flags [B] | seg_count [nseg];
+    // seg_count_dense [nseg] and the value histograms [nseg][FD_NB] of a dense image are zeroed by the CTA that flags it
     const size_t n_stamp = may_overflow ? 2 * (size_t)B : 0;
-    const size_t n_dense = use_dense ? (size_t)B + (size_t)nseg + (size_t)nseg * FD_NB : 0;
-    const size_t n_zero = H_WORDS + n_stamp + (size_t)nseg + n_dense;
-    const size_t n_int = n_zero + 3 * (size_t)nseg + (may_overflow ? 6 * (size_t)nseg + 3 * (size_t)B + 4 : 0);
+    const size_t n_dense = use_dense ? (size_t)nseg + (size_t)nseg * FD_NB : 0;
+    const size_t n_zero = H_WORDS + n_stamp + (use_dense ? (size_t)B : 0) + (size_t)nseg;
+    const size_t n_int = n_zero + n_dense + 3 * (size_t)nseg + (may_overflow ? 6 * (size_t)nseg + 3 * (size_t)B + 4 : 0);
     const size_t n_u64 = may_overflow ? 4 * (size_t)nseg + ROUND_TIMES : 0;
     const size_t n_hist = may_overflow ? (size_t)nseg * ROUND_NB : 0;
     SSDK_TRY(ssdk_ensure(ctx, &ctx->ws_counts, 16 + n_u64 * 8 + (n_int + n_hist) * 4));
@@ -1571,7 +1600,7 @@ static int postprocess_impl(ssdk_ctx* ctx, const HeadGeom* head, const float* co
     int* seg_count = stamps + n_stamp + (use_dense ? B : 0);
     int* seg_count_dense = use_dense ? seg_count + nseg : nullptr;
     unsigned* vhist = use_dense ? (unsigned*)(seg_count_dense + nseg) : nullptr;
-    int* seg_kept = hdr + n_zero;
+    int* seg_kept = hdr + n_zero + n_dense;
     int* heavy_queue = seg_kept + nseg;
     int* pend_queue = heavy_queue + nseg;
     float4* seg_box = (float4*)ctx->ws_seg.p;
@@ -1614,8 +1643,8 @@ static int postprocess_impl(ssdk_ctx* ctx, const HeadGeom* head, const float* co
             const dim3 fgrid((unsigned)gx, B);
             const size_t sat_img = sat_bytes(C);
             SSDK_KERNEL(ctx, SSDK_K_FILTER,
-                if (is_logits) filter_kernel<true><<<fgrid, FILTER_THREADS, sat_img, ctx->stream>>>(scores, per_image, C, thr, x_lo, fmt, cand, seg_count, img_dense);
-                else filter_kernel<false><<<fgrid, FILTER_THREADS, sat_img, ctx->stream>>>(scores, per_image, C, thr, x_lo, fmt, cand, seg_count, img_dense));
+                if (is_logits) filter_kernel<true><<<fgrid, FILTER_THREADS, sat_img, ctx->stream>>>(scores, per_image, C, thr, x_lo, fmt, cand, seg_count, img_dense, seg_count_dense, vhist);
+                else filter_kernel<false><<<fgrid, FILTER_THREADS, sat_img, ctx->stream>>>(scores, per_image, C, thr, x_lo, fmt, cand, seg_count, img_dense, seg_count_dense, vhist));
             if (use_dense) {
                 // images that filter_kernel found dense are redone with per-tile aggregation; a no-op otherwise (a small
                 // persistent grid: six CTAs per SM in total, each walks its share of the image's tiles)
@@ -1626,8 +1655,8 @@ static int postprocess_impl(ssdk_ctx* ctx, const HeadGeom* head, const float* co
                 const size_t dsmem = ((size_t)2 * C + (size_t)(C + 31) / 32 + (size_t)C * FD_NB) * sizeof(int);
                 SSDK_TRY(ssdk_set_max_smem(ctx, is_logits ? (const void*)filter_dense_kernel<true> : (const void*)filter_dense_kernel<false>, (int)dsmem));
                 SSDK_KERNEL(ctx, SSDK_K_SORT,
-                    if (is_logits) filter_dense_kernel<true><<<dgrid, FILTER_THREADS, dsmem, ctx->stream>>>(scores, per_image, C, thr, x_lo, fmt, cand, seg_count_dense, img_dense, vhist);
-                    else filter_dense_kernel<false><<<dgrid, FILTER_THREADS, dsmem, ctx->stream>>>(scores, per_image, C, thr, x_lo, fmt, cand, seg_count_dense, img_dense, vhist));
+                    if (is_logits) ssdk_launch(ctx, true, filter_dense_kernel<true>, dgrid, dim3(FILTER_THREADS), dsmem, scores, per_image, C, thr, x_lo, fmt, cand, seg_count_dense, (const int*)img_dense, vhist);
+                    else ssdk_launch(ctx, true, filter_dense_kernel<false>, dgrid, dim3(FILTER_THREADS), dsmem, scores, per_image, C, thr, x_lo, fmt, cand, seg_count_dense, (const int*)img_dense, vhist));
             }
         }
 
@@ -1652,10 +1681,11 @@ static int postprocess_impl(ssdk_ctx* ctx, const HeadGeom* head, const float* co
 #define SSDK_LAUNCH_NMS(DEC)                                                                                                  \
         do {                                                                                                                  \
             SSDK_TRY(ssdk_set_max_smem(ctx, (const void*)nms_kernel<DEC>, (int)nms_smem));                                   \
-            nms_small_kernel<DEC><<<sgrid_nms, NMS_SMALL_WARPS * 32, 0, ctx->stream>>>(                                      \
-                cand, fmt, SC, N.codes, N.anchors, A, nseg, C, K, N.iou_thr, seg_box, seg_score, seg_anchor, seg_kept,        \
-                heavy_queue, pend_queue, hdr);                                                                                \
-            nms_kernel<DEC><<<(int)hgrid, NMS_THREADS, nms_smem, ctx->stream>>>(cand, SC, N, seg_kept, heavy_queue, hdr);    \
+            ssdk_launch(ctx, true, nms_small_kernel<DEC>, dim3(sgrid_nms), dim3(NMS_SMALL_WARPS * 32), 0,                    \
+                        (const unsigned long long*)cand, fmt, SC, N.codes, N.anchors, (long long)A, nseg, C, K, N.iou_thr,    \
+                        seg_box, seg_score, seg_anchor, seg_kept, heavy_queue, pend_queue, hdr);                              \
+            ssdk_launch(ctx, true, nms_kernel<DEC>, dim3((unsigned)hgrid), dim3(NMS_THREADS), nms_smem,                      \
+                        (const unsigned long long*)cand, SC, N, seg_kept, (const int*)heavy_queue, (const int*)hdr);          \
         } while (0)
         if (decoded) SSDK_LAUNCH_NMS(true);
         else SSDK_LAUNCH_NMS(false);
@@ -1710,26 +1740,27 @@ static int postprocess_impl(ssdk_ctx* ctx, const HeadGeom* head, const float* co
             if (occ > 2) occ = 2;
             const int rgrid = ctx->num_sms * occ;                        // all CTAs must be co-resident (grid-wide barriers)
             SSDK_KERNEL(ctx, SSDK_K_NMS_ROUNDS,
-                if (decoded && is_logits) nms_rounds_kernel<true, true><<<rgrid, NMS_THREADS, rsmem, ctx->stream>>>(G, B, thr, x_lo, cand, N, seg_kept, R);
-                else if (decoded) nms_rounds_kernel<true, false><<<rgrid, NMS_THREADS, rsmem, ctx->stream>>>(G, B, thr, x_lo, cand, N, seg_kept, R);
-                else if (is_logits) nms_rounds_kernel<false, true><<<rgrid, NMS_THREADS, rsmem, ctx->stream>>>(G, B, thr, x_lo, cand, N, seg_kept, R);
-                else nms_rounds_kernel<false, false><<<rgrid, NMS_THREADS, rsmem, ctx->stream>>>(G, B, thr, x_lo, cand, N, seg_kept, R));
+                if (decoded && is_logits) ssdk_launch(ctx, true, nms_rounds_kernel<true, true>, dim3(rgrid), dim3(NMS_THREADS), rsmem, G, B, thr, x_lo, cand, N, seg_kept, R);
+                else if (decoded) ssdk_launch(ctx, true, nms_rounds_kernel<true, false>, dim3(rgrid), dim3(NMS_THREADS), rsmem, G, B, thr, x_lo, cand, N, seg_kept, R);
+                else if (is_logits) ssdk_launch(ctx, true, nms_rounds_kernel<false, true>, dim3(rgrid), dim3(NMS_THREADS), rsmem, G, B, thr, x_lo, cand, N, seg_kept, R);
+                else ssdk_launch(ctx, true, nms_rounds_kernel<false, false>, dim3(rgrid), dim3(NMS_THREADS), rsmem, G, B, thr, x_lo, cand, N, seg_kept, R));
         }
     }
     // 5. pack
     if (by_label) {
         SSDK_KERNEL(ctx, SSDK_K_PACK,
-                    pack_by_label_kernel<<<C, 256, 0, ctx->stream>>>(seg_box, seg_score, seg_kept, B, C, K, (const float4*)box_scaler,
-                                                                     (float)final_score_threshold, *by_label));
+                    ssdk_launch(ctx, per_image > 0, pack_by_label_kernel, dim3(C), dim3(256), 0, (const float4*)seg_box, (const float*)seg_score,
+                                (const int*)seg_kept, B, C, K, (const float4*)box_scaler, (float)final_score_threshold, *by_label));
         return SSDK_OK;
     }
     PackCoco pc;
     memset(&pc, 0, sizeof(pc));
     if (coco) pc = *coco;
     SSDK_KERNEL(ctx, SSDK_K_PACK,
-                pack_kernel<<<dim3(ceil_div_i((long long)C * K, PACK_SLOTS_PER_BLOCK), B), 256, (size_t)(2 * C + 1) * sizeof(int), ctx->stream>>>(
-                    seg_box, seg_score, seg_anchor, seg_kept, C, K, (float4*)out_boxes, out_scores, out_classes, out_num,
-                    out_anchor_idx, (const float4*)box_scaler, (float)final_score_threshold, pc));
+                ssdk_launch(ctx, per_image > 0, pack_kernel, dim3(ceil_div_i((long long)C * K, PACK_SLOTS_PER_BLOCK), B), dim3(256),
+                            (size_t)(2 * C + 1) * sizeof(int), (const float4*)seg_box, (const float*)seg_score, (const int*)seg_anchor,
+                            (const int*)seg_kept, C, K, (float4*)out_boxes, out_scores, out_classes, out_num, out_anchor_idx,
+                            (const float4*)box_scaler, (float)final_score_threshold, pc));
     return SSDK_OK;
 }
 

@@ -337,7 +337,8 @@ int ssdk_train_step_impl(ssdk_ctx* ctx, const HeadGeom& G, const float* anchors,
             &occ, variant == 0 ? (const void*)train_step_kernel<0> : (const void*)train_step_kernel<1>, FLAT_THREADS, 0));
         occ_cache[variant] = occ > 0 ? occ : 1;
     }
-    const int occ = occ_cache[variant];
+    int occ = occ_cache[variant];
+    if (ctx->train_ctas_per_sm > 0 && ctx->train_ctas_per_sm < occ) occ = ctx->train_ctas_per_sm;   // leave room for a co-running sub-path
     const int nchunks_img = ceil_div_i(A, MATCH_THREADS);
     int gx = (ctx->num_sms * 6 + B - 1) / B;                               // matcher work items per image (about 6 per SM in total)
     if (gx > nchunks_img) gx = nchunks_img;
@@ -352,9 +353,10 @@ int ssdk_train_step_impl(ssdk_ctx* ctx, const HeadGeom& G, const float* anchors,
     const double t_match = 13.8 + 0.494 * Gmax, t_flat = 0.646 * C;
     int m = ctx->match_ctas_per_sm;
     if (m <= 0) {
-        m = (int)(occ * t_match / (t_match + t_flat) + 0.5);
+        m = (int)(6 * t_match / (t_match + t_flat) + 0.5);                  // of the six CTAs per SM that normally fit
         if (m < 1) m = 1;
         if (m > occ - 1) m = occ - 1;
+        if (m < 1) m = 1;
     }
     if (m > occ) m = occ;
     long long n_match = (long long)ctx->num_sms * m;

@@ -46,23 +46,33 @@ class CapturedStep:
         return False
 
 
-def concurrent(*fns, device=None):
+def concurrent(*fns, device=None, priorities=None, train_ctas_per_sm=5):
     """Returns a function that runs the independent `fns` on one side stream each, forked from and joined to the current
     stream.  Inside `capture` this becomes parallel branches of the CUDA graph, so the ALU- / latency-bound kernels of one
     sub-path (matching, sorting, NMS, packing) hide behind the HBM-bound kernels of another (the loss pass, the score scan).
     The library keeps separate workspace for the training-side and the inference-side sub-paths, so `SSD.loss` and
     `SSD.get_predictions` may overlap; two calls of the SAME sub-path must not."""
     dev = torch.device('cuda', torch.cuda.current_device()) if device is None else torch.device(device)
-    streams = [torch.cuda.Stream(device=dev) for _ in fns]
+    # `priorities`: one CUDA stream priority per function (lower number = scheduled first; -1 is the usual high priority)
+    streams = [torch.cuda.Stream(device=dev, priority=0 if priorities is None else int(priorities[i])) for i in range(len(fns))]
 
     def run():
         cur = torch.cuda.current_stream(dev)
         outs = []
         for st in streams:
             st.wait_stream(cur)
-        for st, fn in zip(streams, fns):
-            with torch.cuda.stream(st):
-                outs.append(fn())
+        # the fused training-step kernel is persistent and takes every CTA slot of the GPU (six per SM); next to another sub-path
+        # it leaves one slot per SM free, so that the other branch's short kernels (sorting, NMS, packing) are scheduled
+        # while it streams (measured for the bench step: 0.355 vs 0.360 ms; 4 or 3 CTAs per SM: 0.358)
+        if train_ctas_per_sm:
+            _lib.set_option(_lib.SSDK_OPT_TRAIN_CTAS_PER_SM, int(train_ctas_per_sm), dev.index)
+        try:
+            for st, fn in zip(streams, fns):
+                with torch.cuda.stream(st):
+                    outs.append(fn())
+        finally:
+            if train_ctas_per_sm:
+                _lib.set_option(_lib.SSDK_OPT_TRAIN_CTAS_PER_SM, 0, dev.index)
         for st in streams:
             cur.wait_stream(st)
         return tuple(outs)
