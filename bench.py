@@ -170,7 +170,8 @@ def cpu_reference(n_train, n_infer, steps, warmup, threads, budget_s=None):
         res = [f.result() for f in futs]
         tr = np.array(res[:n_train], np.float64).sum(axis=0)
         norm = max(tr[2], 1.0)
-        return tr[0] / norm, tr[1] / norm, sum(res[n_train:])
+        # per-image results too: the GPU arm checks its first batch against them (same seeded inputs)
+        return tr[0] / norm, tr[1] / norm, sum(res[n_train:]), np.array(res[:n_train], np.float64), np.array(res[n_train:], np.int64)
 
     with ThreadPoolExecutor(max_workers=threads) as pool:
         t0 = time.perf_counter()
@@ -574,8 +575,18 @@ def run_ours(args):
         os.sched_setaffinity(0, all_cpus)
         threads = host_threads()
         n_t, n_i = cpu_sample_size(threads)
-        ips, sec, _, passes = cpu_reference(n_t, n_i, 3, 1, threads)
+        ips, sec, cpu_out, passes = cpu_reference(n_t, n_i, 3, 1, threads)
         cpu = cpu_baseline_object(ips, threads, n_t, n_i, passes)
+        # the CPU port ran the same seeded images as this rank's batches: compare whole-batch results (the checker role of oracle/)
+        tr = cpu_out[3][:Bt].sum(axis=0)
+        o_loc, o_cls, o_n = tr[0] / max(tr[2], 1.0), tr[1] / max(tr[2], 1.0), tr[2]
+        o_det = cpu_out[4][:Bi]
+        rel = max(abs(check['localization_loss'] - o_loc) / abs(o_loc), abs(check['classification_loss'] - o_cls) / abs(o_cls))
+        det_gpu = pred['num_boxes'].cpu().numpy().astype(np.int64)
+        check['vs_cpu_port'] = {'train_images': int(Bt), 'infer_images': int(Bi), 'losses_max_rel_diff': float(rel),
+                                'num_matches_equal': bool(o_n == check['num_matches_all_ranks']),
+                                'detections_per_image_equal': bool(np.array_equal(det_gpu, o_det)),
+                                'agrees': bool(rel <= 1e-5 and o_n == check['num_matches_all_ranks'] and np.array_equal(det_gpu, o_det))}
 
     small = extras.get('small_cases')
     if small and '_inputs' in small:

@@ -39,5 +39,9 @@ L.set_profiling(True); L.profile_read()
 for _ in range(20):
     fn()
 prof = L.profile_read(); L.set_profiling(False)
+out = fn()
+import hashlib
+sig = hashlib.sha256(b''.join(out[k].cpu().numpy().tobytes() for k in ('boxes', 'scores', 'labels', 'num_boxes'))).hexdigest()[:16]
 print(json.dumps({'lib': os.environ.get('SSDK_LIB', 'default'), 'infer_graph_ms': round(best, 5),
-                  'kernels_ms': {k: round(v[0] / 20, 5) for k, v in prof.items() if v[1]}, 'launches_per_replay': cap.launches_per_replay}))
+                  'kernels_ms': {k: round(v[0] / 20, 5) for k, v in prof.items() if v[1]}, 'launches_per_replay': cap.launches_per_replay, 'pdl': os.environ.get('SSDK_PDL', '1'),
+                  'detections': int(out['num_boxes'].sum()), 'sha': sig}))

@@ -217,18 +217,75 @@ __device__ __forceinline__ void filter_group(const FilterEmit* __restrict__ E, u
     }
 }
 
+// One tile of the streaming scan: SCAN_U 128-bit no-allocate loads per thread (all in flight together), then every group of
+// four elements whose maximum passes the (cheap) pre-test goes to filter_group.  FULL: the whole tile lies inside the array.
+#ifndef SCAN_U
+#define SCAN_U 6                       // anchor-major scan: 96 bytes in flight per thread, 64 registers, four CTAs per SM (profiles/r2b_filter_variants.txt)
+#endif
+#ifndef SCAN_U_HEAD
+#define SCAN_U_HEAD 4                  // head-layout scan (its candidate path needs more registers: four-way index decomposition)
+#endif
+template <bool IS_LOGITS, bool HEAD, bool FULL, int U>
+__device__ __forceinline__ void scan_tile(const float4* __restrict__ ptr, long long i0, long long nbody4, long long head, float lim,
+                                          const FilterEmit* __restrict__ E, unsigned* sat, int* dense_flag, int* cta_stop, bool& stop) {
+    float4 v[U];
+    bool inb[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        inb[u] = FULL || (i0 + u * FILTER_THREADS + threadIdx.x < nbody4);
+        v[u] = inb[u] ? ld_stream_f4(ptr + u * FILTER_THREADS) : make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+    }
+    // ONE test and branch per tile on the common path: the maximum over everything the thread loaded (out-of-bounds groups hold
+    // -inf); only a thread that holds a possible candidate looks at its groups one by one
+    float mx[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) mx[u] = fmaxf(fmaxf(v[u].x, v[u].y), fmaxf(v[u].z, v[u].w));
+    float mall = mx[0];
+#pragma unroll
+    for (int u = 1; u < U; ++u) mall = fmaxf(mall, mx[u]);
+    if (__builtin_expect(!(mall > lim), 1)) return;                       // (the hint moves the candidate code out of the loop body)
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        if (!(mx[u] > lim)) continue;
+        if (!HEAD && dense_flag) {
+            if (stop) continue;
+            if (u == 0) {
+                // a thread ALL of whose groups (4 KB apart) hold a possible candidate sits in a dense image: with 5 %
+                // of the elements above the threshold that happens to 0.1 % of the threads, with 20 % to every tenth --
+                // and with a few confident anchors per image never (their classes cannot line up in all the 4-class
+                // windows).  Checked BEFORE anything is appended: in a dense image every thread would otherwise start
+                // with a burst of contended atomics.  One shared-memory exchange per warp, one global one per CTA
+                // (hundreds of thousands of stores to one word take 0.3 ms by themselves).
+                bool all = true;
+#pragma unroll
+                for (int w = 1; w < U; ++w) all = all && mx[w] > lim;
+                if (all) {
+                    if ((int)(threadIdx.x & 31) == __ffs(__activemask()) - 1 && atomicExch(cta_stop, 1) == 0)
+                        cta_stop[1] = atomicExch(dense_flag, 1) == 0 ? 1 : 0;        // the first CTA of the image to notice
+                    stop = true;
+                    continue;
+                }
+            }
+            if (*(volatile int*)cta_stop || __ldcg(dense_flag)) { stop = true; continue; }
+        }
+        filter_group<IS_LOGITS, HEAD>(E, sat, v[u], head + ((i0 + u * FILTER_THREADS + threadIdx.x) << 2));
+    }
+}
+
 // The streaming scan shared by both layouts: `count` floats at `base` are read once with 128-bit no-allocate loads;
 // every group of four elements whose maximum passes the (cheap) pre-test goes to filter_group.  The candidate code is written
 // fully unrolled and inlined on purpose: the compiler then lays the rare path out of the way of the streaming loop.  Measured
 // on a B200 (cfg3, graph replay of the inference sub-path, profiles/round2_filter_variants.txt): this form 0.228 ms (scan
 // 0.190 ms); the candidate code as an out-of-line function 0.248 ms (0.246 / 0.268 ms when the call forces spills at 48 / 40
 // registers); values parked in shared memory and walked by a rolled loop 0.335 ms; a rolled 4-iteration loop 4.3 vs 6.2 TB/s
-// (round 1).
+// (round 1).  The scan sits at the memory system's limit: same box, same run (profiles/r2b_filter_variants.txt), bounds tests
+// on every load 0.1933 ms, full tiles without them and one branch per tile 0.1910 ms, six loads per thread 0.1881 ms, eight
+// 0.190-0.192 ms, five CTAs per SM at 48 registers 0.198 ms -- 6.4-6.6 TB/s; box-to-box variation is larger (0.188-0.206 ms).
 // `dense_flag` (anchor-major only): set by the first thread that finds possible candidates in all four of its groups; every
 // thread that comes across a possible candidate afterwards stops its scan -- filter_dense_kernel redoes such an image from
 // scratch.  Both checks sit on the candidate path, the streaming loop itself does not know about them (a flag load and a
 // ballot per iteration cost 15 % of the scan's bandwidth).
-template <bool IS_LOGITS, bool HEAD>
+template <bool IS_LOGITS, bool HEAD, int U>
 __device__ __forceinline__ void scan_candidates(const float* __restrict__ base, long long count, const FilterEmit* __restrict__ E,
                                                 unsigned* sat, int* dense_flag, int* cta_stop /*[2]: stop, won*/) {
     const int lane = threadIdx.x & 31;
@@ -250,49 +307,18 @@ __device__ __forceinline__ void scan_candidates(const float* __restrict__ base, 
             filter_group<IS_LOGITS, HEAD>(E, sat, make_float4(base[e], -INFINITY, -INFINITY, -INFINITY), e);
     }
 
-    const long long stride = (long long)gridDim.x * FILTER_THREADS * FILTER_UNROLL;
+    // Full tiles (U x 256 float4 = U x 4 KB per CTA and iteration) are read without any bounds test; the one partial
+    // tile of the array (the last one, met by a single CTA) goes through the bounded form of the same code.
+    const long long tile = (long long)FILTER_THREADS * U;
+    const long long stride = (long long)gridDim.x * tile;
     bool stop = false;
     // the thread's load address advances by a constant (kept as a pointer: recomputing it from the loop index put eight
     // dependent integer instructions in front of every iteration's first load)
-    const float4* ptr = body + (long long)blockIdx.x * FILTER_THREADS * FILTER_UNROLL + threadIdx.x;
-    for (long long i0 = (long long)blockIdx.x * FILTER_THREADS * FILTER_UNROLL; i0 < nbody4 && !stop; i0 += stride, ptr += stride) {
-        float4 v[FILTER_UNROLL];
-        bool inb[FILTER_UNROLL];
-#pragma unroll
-        for (int u = 0; u < FILTER_UNROLL; ++u) {
-            const long long i = i0 + u * FILTER_THREADS + threadIdx.x;
-            inb[u] = i < nbody4;
-            v[u] = inb[u] ? ld_stream_f4(ptr + u * FILTER_THREADS) : make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
-        }
-#pragma unroll
-        for (int u = 0; u < FILTER_UNROLL; ++u) {
-            const float mx = fmaxf(fmaxf(v[u].x, v[u].y), fmaxf(v[u].z, v[u].w));
-            if (__builtin_expect(!(inb[u] && (mx > lim)), 1)) continue;   // (the hint moves the candidate code out of the loop body)
-            if (!HEAD && dense_flag) {
-                if (stop) continue;
-                if (u == 0) {
-                    // a thread ALL of whose four groups (4 KB apart) hold a possible candidate sits in a dense image: with 5 %
-                    // of the elements above the threshold that happens to 0.1 % of the threads, with 20 % to every tenth --
-                    // and with a few confident anchors per image never (their classes cannot line up in all four 4-class
-                    // windows).  Checked BEFORE anything is appended: in a dense image every thread would otherwise start
-                    // with a burst of contended atomics.  One shared-memory exchange per warp, one global one per CTA
-                    // (hundreds of thousands of stores to one word take 0.3 ms by themselves).
-                    bool all = true;
-#pragma unroll
-                    for (int w = 1; w < FILTER_UNROLL; ++w)
-                        all = all && inb[w] && fmaxf(fmaxf(v[w].x, v[w].y), fmaxf(v[w].z, v[w].w)) > lim;
-                    if (all) {
-                        if ((int)(threadIdx.x & 31) == __ffs(__activemask()) - 1 && atomicExch(cta_stop, 1) == 0)
-                            cta_stop[1] = atomicExch(dense_flag, 1) == 0 ? 1 : 0;    // the first CTA of the image to notice
-                        stop = true;
-                        continue;
-                    }
-                }
-                if (*(volatile int*)cta_stop || __ldcg(dense_flag)) { stop = true; continue; }
-            }
-            filter_group<IS_LOGITS, HEAD>(E, sat, v[u], head + ((i0 + u * FILTER_THREADS + threadIdx.x) << 2));
-        }
-    }
+    const float4* ptr = body + (long long)blockIdx.x * tile + threadIdx.x;
+    long long i0 = (long long)blockIdx.x * tile;
+    for (; i0 + tile <= nbody4 && !stop; i0 += stride, ptr += stride)
+        scan_tile<IS_LOGITS, HEAD, true, U>(ptr, i0, nbody4, head, lim, E, sat, dense_flag, cta_stop, stop);
+    if (i0 < nbody4 && !stop) scan_tile<IS_LOGITS, HEAD, false, U>(ptr, i0, nbody4, head, lim, E, sat, dense_flag, cta_stop, stop);
 }
 
 // anchor-major layout: grid (gx, B), image blockIdx.y is the [A,C] array scanned
@@ -317,7 +343,7 @@ __global__ void __launch_bounds__(FILTER_THREADS, FILTER_MIN_CTAS) filter_kernel
         s_emit = e;
     }
     __syncthreads();
-    scan_candidates<IS_LOGITS, false>(scores + (size_t)b * per_image, per_image, &s_emit, s_sat, img_dense ? img_dense + b : nullptr, s_stop);
+    scan_candidates<IS_LOGITS, false, SCAN_U>(scores + (size_t)b * per_image, per_image, &s_emit, s_sat, img_dense ? img_dense + b : nullptr, s_stop);
     if (img_dense) {
         // the CTA that declared the image dense prepares filter_dense_kernel's counters and value histograms for it (they are
         // not part of the per-call memset: zeroing 128 bytes per segment on every call cost 2-3 us of the sparse path)
@@ -351,7 +377,7 @@ __global__ void __launch_bounds__(FILTER_THREADS, FILTER_MIN_CTAS) head_filter_k
         s_emit = e;
     }
     __syncthreads();
-    scan_candidates<IS_LOGITS, true>(G.cls[l], count, &s_emit, s_sat, nullptr, nullptr);
+    scan_candidates<IS_LOGITS, true, SCAN_U_HEAD>(G.cls[l], count, &s_emit, s_sat, nullptr, nullptr);
 }
 
 // ---------------------------------------------------------------------------------------------- 1b. dense images
@@ -1626,7 +1652,7 @@ static int postprocess_impl(ssdk_ctx* ctx, const HeadGeom* head, const float* co
                 const long long cnt = (long long)B * head->per_loc * C * head->hw[l];
                 if (cnt > most) most = cnt;
             }
-            long long chunks = (most / 4 + FILTER_THREADS * FILTER_UNROLL - 1) / (FILTER_THREADS * FILTER_UNROLL);
+            long long chunks = (most / 4 + FILTER_THREADS * SCAN_U_HEAD - 1) / (FILTER_THREADS * SCAN_U_HEAD);
             long long gx = (long long)ctx->num_sms * 16;
             if (gx > chunks) gx = chunks;
             if (gx < 1) gx = 1;
@@ -1636,7 +1662,7 @@ static int postprocess_impl(ssdk_ctx* ctx, const HeadGeom* head, const float* co
                 if (is_logits) head_filter_kernel<true><<<hgrid_f, FILTER_THREADS, sat_head, ctx->stream>>>(*head, B, thr, x_lo, fmt, cand, seg_count);
                 else head_filter_kernel<false><<<hgrid_f, FILTER_THREADS, sat_head, ctx->stream>>>(*head, B, thr, x_lo, fmt, cand, seg_count));
         } else {
-            long long chunks = (per_image / 4 + FILTER_THREADS * FILTER_UNROLL - 1) / (FILTER_THREADS * FILTER_UNROLL);
+            long long chunks = (per_image / 4 + FILTER_THREADS * SCAN_U - 1) / (FILTER_THREADS * SCAN_U);
             long long gx = ((long long)ctx->num_sms * 16 + B - 1) / B;
             if (gx > chunks) gx = chunks;
             if (gx < 1) gx = 1;
