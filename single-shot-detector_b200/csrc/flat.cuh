@@ -42,16 +42,16 @@ __device__ __forceinline__ void flat_load(const FlatSegs& S, FlatChunk& ck, long
     }
 }
 
-// Sum over this thread's FLAT_U float4 of the negative-class focal term (without the (1-alpha) factor), forward only.
+// Sum over FLAT_U float4 of the negative-class focal term (without the (1-alpha) factor), forward only.
 template <int GAMMA_MODE>
-__device__ __forceinline__ float flat_value(const FlatSegs& S, const FlatChunk& ck, long long g, float gamma, int tid) {
+__device__ __forceinline__ float flat_math(const float4 (&v)[FLAT_U], float gamma) {
     float s;
     bool general = (GAMMA_MODE != 0);
     if (GAMMA_MODE == 0) {
         f32x2 a4[4] = {0ull, 0ull, 0ull, 0ull};
         float mx = -INFINITY;
 #pragma unroll
-        for (int u = 0; u < FLAT_U; u += 2) focal_half8(ck.v[u], ck.v[u + 1], a4, mx);
+        for (int u = 0; u < FLAT_U; u += 2) focal_half8(v[u], v[u + 1], a4, mx);
         float s0, s1;
         unpack2(add2(add2(a4[0], a4[1]), add2(a4[2], a4[3])), s0, s1);
         s = s0 + s1;
@@ -61,18 +61,60 @@ __device__ __forceinline__ float flat_value(const FlatSegs& S, const FlatChunk& 
         f32x2 a01 = 0ull, a23 = 0ull;
 #pragma unroll
         for (int u = 0; u < FLAT_U; ++u) {
-            a01 = focal_negative2<GAMMA_MODE>(ck.v[u].x, ck.v[u].y, gamma, a01);
-            a23 = focal_negative2<GAMMA_MODE>(ck.v[u].z, ck.v[u].w, gamma, a23);
+            a01 = focal_negative2<GAMMA_MODE>(v[u].x, v[u].y, gamma, a01);
+            a23 = focal_negative2<GAMMA_MODE>(v[u].z, v[u].w, gamma, a23);
         }
         float s0, s1;
         unpack2(add2(a01, a23), s0, s1);
         s = s0 + s1;
     }
-    // the (< 4) floats of a level beyond its last float4, handled with the level's last chunk
+    return s;
+}
+
+// The same for a loaded chunk, plus the (< 4) floats of a level beyond its last float4 (handled with the level's last chunk).
+template <int GAMMA_MODE>
+__device__ __forceinline__ float flat_value(const FlatSegs& S, const FlatChunk& ck, long long g, float gamma, int tid) {
+    float s = flat_math<GAMMA_MODE>(ck.v, gamma);
     if (g + 1 == S.chunk0[ck.lvl + 1]) {
         const long long n = S.count[ck.lvl];
         const int tail = (int)(n & 3);
         if (tid < tail) s += focal_negative<GAMMA_MODE>(S.src[ck.lvl][(n & ~3ll) + tid], gamma);
     }
     return s;
+}
+
+// This thread's share of the chunks g, g + stride, g + 2 stride, ... < g_end of the class-tensor segments (forward only), in
+// ascending order.  Segment by segment: the FULL chunks of a segment are read through a pointer that advances by a constant,
+// without bounds tests or segment lookups (in the generic form above those cost more instructions per chunk than the focal
+// arithmetic itself: ncu source view of the round-2 training-step kernel, profiles/r2b_ncu_summary.txt); only a segment's last,
+// partial chunk takes the bounded path.  Same per-chunk float sums and the same order of double additions as chunk-by-chunk
+// flat_load + flat_value.
+template <int GAMMA_MODE>
+__device__ __forceinline__ double flat_sum_range(const FlatSegs& S, long long g, long long g_end, long long stride, float gamma, int tid) {
+    double acc = 0.0;
+    const long long pstep = stride * FLAT_CHUNK4;
+#pragma unroll 1
+    for (int sg = 0; sg < S.n && g < g_end; ++sg) {
+        const long long c1 = S.chunk0[sg + 1];
+        if (g >= c1) continue;
+        const long long c0 = S.chunk0[sg];
+        long long full_end = c0 + (S.count[sg] >> 2) / FLAT_CHUNK4;          // chunks [c0, full_end) hold FLAT_CHUNK4 float4 each
+        if (full_end > g_end) full_end = g_end;
+        const float4* p = (const float4*)S.src[sg] + (g - c0) * FLAT_CHUNK4 + tid;
+#pragma unroll 1
+        for (; g < full_end; g += stride, p += pstep) {
+            float4 v[FLAT_U];
+#pragma unroll
+            for (int u = 0; u < FLAT_U; ++u) v[u] = ld_stream_f4(p + u * FLAT_THREADS);
+            acc += (double)flat_math<GAMMA_MODE>(v, gamma);
+        }
+        if (g < c1 && g < g_end) {                                            // the segment's partial last chunk
+            FlatChunk ck;
+            int cursor = sg;
+            flat_load(S, ck, g, cursor, tid);
+            acc += (double)flat_value<GAMMA_MODE>(S, ck, g, gamma, tid);
+            g += stride;
+        }
+    }
+    return acc;
 }

@@ -115,10 +115,7 @@ __global__ void __launch_bounds__(FLAT_THREADS) head_flat_kernel(const FlatSegs 
             // forward: no register double-buffering -- fewer registers give six resident CTAs per SM instead of four; the
             // extra warps hide the load latency just as well (0.1504 vs 0.1600 ms for the forward sub-path).  The read+write
             // pass below does need the prefetch (0.2728 vs 0.2862 ms).
-            for (; g < total; g += step) {
-                load(ca, g);
-                compute(ca, g);
-            }
+            acc += flat_sum_range<GAMMA_MODE>(S, g, total, step, gamma, tid);
         } else if (g < total) {
             load(ca, g);
             while (true) {

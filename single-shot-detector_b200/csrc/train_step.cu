@@ -195,18 +195,14 @@ __global__ void __launch_bounds__(FLAT_THREADS, TRAIN_MIN_CTAS) train_step_kerne
     //      streaming CTAs, chunk rounds_all * grid + (round - rounds_all) * n_flat + (cta - n_match).
     {
         const long long total = T.S.chunk0[T.S.nseg];
-        FlatChunk ck;
-        int cursor = 0;
-        long long g = cta;
-        for (long long r = 0; r < T.rounds_all && g < total; ++r, g += grid) {
-            flat_load(T.S, ck, g, cursor, tid);
-            acc_flat += (double)flat_value<GAMMA_MODE>(T.S, ck, g, T.gamma, tid);
-        }
-        if (!matcher) {
-            for (g = T.rounds_all * grid + (cta - T.n_match); g < total; g += n_flat) {
-                flat_load(T.S, ck, g, cursor, tid);
-                acc_flat += (double)flat_value<GAMMA_MODE>(T.S, ck, g, T.gamma, tid);
-            }
+        long long all_end = T.rounds_all * grid;
+        if (all_end > total) all_end = total;
+#pragma unroll 1
+        for (int phase = 0; phase < (matcher ? 1 : 2); ++phase) {
+            const long long g0 = phase == 0 ? (long long)cta : all_end + (cta - T.n_match);
+            const long long g1 = phase == 0 ? all_end : total;
+            const long long st = phase == 0 ? (long long)grid : (long long)n_flat;
+            acc_flat += flat_sum_range<GAMMA_MODE>(T.S, g0, g1, st, T.gamma, tid);
         }
     }
 
@@ -344,17 +340,18 @@ int ssdk_train_step_impl(ssdk_ctx* ctx, const HeadGeom& G, const float* anchors,
     if (gx > nchunks_img) gx = nchunks_img;
     if (gx < 1) gx = 1;
     long long grid = (long long)ctx->num_sms * occ;
-    // Role split.  Automatic (the options' defaults) from the ratio of the matching work to the streaming work per (image,
-    // anchor), both measured on a B200 with the kernels alone: matching 13.8 ps + 0.494 ps per ground-truth box (23.7 ps at
-    // G = 20, 162 ps at G = 300: ALU-bound), streaming 0.646 ps per class (4C bytes at 0.96 of the HBM peak).  m of the
-    // `occ` resident CTAs per SM start as matchers, m / occ ~ share of the matching in the total work; they finish after
-    // ~0.75 * t_match * occ / m (matching speeds up next to memory-stalled warps) and then stream for the rest of the
-    // kernel: rho = 1 - that / total is their share of the chunk list relative to a streaming CTA's.
+    // Role split.  Automatic (the options' defaults) from the two kernels' costs per (image, anchor), measured alone on a B200:
+    // matching 13.8 ps + 0.494 ps per ground-truth box (23.7 ps at G = 20, 162 ps at G = 300; latency-bound per CTA: with m
+    // matcher CTAs per SM instead of six it takes ~5.7 / m times as long), streaming 0.646 ps per class (4C bytes at 0.96 of the
+    // HBM peak, and four streaming CTAs per SM still reach it).  m grows with r = matching / streaming cost; the matcher CTAs are
+    // done after tm_busy and then stream for the rest of the kernel: rho = 1 - tm_busy / total is their share of the chunk list
+    // relative to a streaming CTA's.  Fitted to the sweep profiles/r2d_split_sweep.json (cfg2: m = 2, rho ~ 0.1 -> 0.1167 ms
+    // = 0.95 of the roofline; 100 boxes per image: m = 4; 20 classes: m = 4-5; stress configuration: m = 4-5, rho = 0).
     const double t_match = 13.8 + 0.494 * Gmax, t_flat = 0.646 * C;
     int m = ctx->match_ctas_per_sm;
     if (m <= 0) {
-        m = (int)(6 * t_match / (t_match + t_flat) + 0.5);                  // of the six CTAs per SM that normally fit
-        if (m < 1) m = 1;
+        const double r = t_match / t_flat;
+        m = (int)(6.0 * r / (r + 0.6) + 0.5);
         if (m > occ - 1) m = occ - 1;
         if (m < 1) m = 1;
     }
@@ -375,8 +372,9 @@ int ssdk_train_step_impl(ssdk_ctx* ctx, const HeadGeom& G, const float* anchors,
     grid = n_match + n_flat;
     double rho = ctx->match_flat_share_pct / 100.0;
     if (ctx->match_flat_share_pct < 0) {
-        const double total = 1.2 * (t_match > t_flat ? t_match : t_flat);
-        rho = 1.0 - 0.75 * t_match * occ / m / total;
+        const double tm_busy = t_match * 5.7 / m;
+        const double t_all = tm_busy > t_flat + 0.65 * t_match ? tm_busy : t_flat + 0.65 * t_match;
+        rho = 1.0 - tm_busy / t_all;
         if (rho < 0.0) rho = 0.0;
         if (rho > 1.0) rho = 1.0;
     }
