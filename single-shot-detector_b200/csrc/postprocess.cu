@@ -720,11 +720,12 @@ struct NmsSegArgs {
     float4* seg_box; float* seg_score; int* seg_anchor;
 };
 
-template <bool DECODED>
+template <bool DECODED, int THREADS = NMS_THREADS>
 __device__ __forceinline__ int nms_sorted_segment(const NmsSegArgs& N, NmsShared& sh, NmsBox* s_kept, float* s_kept_area,
                                                   const unsigned long long* sorted, int navail, long long seg, int kept) {
+    constexpr int TPC = THREADS / NMS_CH;              // threads per candidate (a power of two <= 32)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int c = tid / NMS_TPC, q = tid % NMS_TPC;    // candidate slot in the chunk, position among its threads
+    const int c = tid / TPC, q = tid % TPC;            // candidate slot in the chunk, position among its threads
     const int b = (int)(seg / N.C), K = N.K;
     const size_t obase = (size_t)seg * K;
     const float iou_thr = N.iou_thr, band = fabsf(iou_thr) * 3.814697265625e-06f;
@@ -762,7 +763,7 @@ __device__ __forceinline__ int nms_sorted_segment(const NmsSegArgs& N, NmsShared
         // (a) against the boxes kept so far
         int hit = 0;
         if (alive) {
-            for (int j = q; j < kept; j += NMS_TPC) {
+            for (int j = q; j < kept; j += TPC) {
                 bool y, am;
                 nms_fast(box, area, s_kept[j], s_kept_area[j], iou_thr, band, y, am);
                 if (am) y = nms_exact(box, area, s_kept[j], s_kept_area[j], iou_thr); // rare: within 2^-18 of the threshold
@@ -770,7 +771,7 @@ __device__ __forceinline__ int nms_sorted_segment(const NmsSegArgs& N, NmsShared
             }
         }
 #pragma unroll
-        for (int o = 1; o < NMS_TPC; o <<= 1) hit |= __shfl_xor_sync(0xffffffffu, hit, o);
+        for (int o = 1; o < TPC; o <<= 1) hit |= __shfl_xor_sync(0xffffffffu, hit, o);
         alive = alive && !hit;
         if (q == 0) {
             sh.tile[c] = box;
@@ -783,7 +784,7 @@ __device__ __forceinline__ int nms_sorted_segment(const NmsSegArgs& N, NmsShared
         // (b) column of the chunk's suppression matrix
         unsigned long long col = 0ull;
         if (alive && (alive_mask & (alive_mask - 1ull))) {               // at least two survivors in the chunk
-            for (int t = q; t < c; t += NMS_TPC) {
+            for (int t = q; t < c; t += TPC) {
                 if ((alive_mask >> t) & 1ull) {
                     bool y, am;
                     nms_fast(box, area, sh.tile[t], sh.tile_area[t], iou_thr, band, y, am);
@@ -793,7 +794,7 @@ __device__ __forceinline__ int nms_sorted_segment(const NmsSegArgs& N, NmsShared
             }
         }
 #pragma unroll
-        for (int o = 1; o < NMS_TPC; o <<= 1) col |= __shfl_xor_sync(0xffffffffu, col, o);
+        for (int o = 1; o < TPC; o <<= 1) col |= __shfl_xor_sync(0xffffffffu, col, o);
         if (q == 0) sh.col[c] = col;
         __syncthreads();
         // (c) greedy order by resolution rounds (warp 0: lane l owns candidates l and l + 32)
@@ -832,8 +833,15 @@ __device__ __forceinline__ int nms_sorted_segment(const NmsSegArgs& N, NmsShared
 }
 
 // One CTA per queued (image, class) segment with 33..SEG_CAP candidates: sort in shared memory, then nms_sorted_segment.
-template <bool DECODED>
-__global__ void __launch_bounds__(NMS_THREADS) nms_kernel(const unsigned long long* __restrict__ cand, const SegCounts SC,
+// NMS_HEAVY_THREADS: 512 threads (eight per candidate).  256 threads at 45 registers (a CTA that fits next to five resident CTAs
+// of the fused training-step kernel) was measured for the two-stream step: 0.2353 vs 0.2295 ms for the inference sub-path alone and no
+// gain for the step (0.355 vs 0.351 ms, profiles/r2k_nms256.txt) -- with both sub-paths streaming, the step is bound by the aggregate
+// HBM bandwidth (2.05 GB in 0.351 ms = 5.85 TB/s), whatever the split of the SMs.
+#ifndef NMS_HEAVY_THREADS
+#define NMS_HEAVY_THREADS 512
+#endif
+template <bool DECODED, int THREADS>
+__global__ void __launch_bounds__(THREADS, THREADS == 256 ? 5 : 2) nms_kernel(const unsigned long long* __restrict__ cand, const SegCounts SC,
                                                           const NmsSegArgs N, int* __restrict__ seg_kept,
                                                           const int* __restrict__ heavy_queue, const int* __restrict__ hdr) {
     extern __shared__ __align__(16) unsigned char nms_smem[];
@@ -850,10 +858,10 @@ __global__ void __launch_bounds__(NMS_THREADS) nms_kernel(const unsigned long lo
         const int n = min(seg_candidates(SC, seg, N.C), SEG_CAP);
         const unsigned long long* keys = cand + (size_t)seg * SEG_CAP;
         __syncthreads();
-        for (int i = tid; i < n; i += NMS_THREADS) s_sort[i] = keys[i];
+        for (int i = tid; i < n; i += THREADS) s_sort[i] = keys[i];
         __syncthreads();
-        cta_sort_keys(s_sort, n, tid, NMS_THREADS);                 // score descending, anchor ascending
-        const int kept = nms_sorted_segment<DECODED>(N, sh, s_kept, s_kept_area, s_sort, n, seg, 0);
+        cta_sort_keys(s_sort, n, tid, THREADS);                 // score descending, anchor ascending
+        const int kept = nms_sorted_segment<DECODED, THREADS>(N, sh, s_kept, s_kept_area, s_sort, n, seg, 0);
         if (tid == 0) seg_kept[seg] = kept;
     }
 }
@@ -1706,11 +1714,11 @@ static int postprocess_impl(ssdk_ctx* ctx, const HeadGeom* head, const float* co
         const int nms_slot = ctx->profiling ? ssdk_prof_begin(ctx, SSDK_K_NMS) : -1;
 #define SSDK_LAUNCH_NMS(DEC)                                                                                                  \
         do {                                                                                                                  \
-            SSDK_TRY(ssdk_set_max_smem(ctx, (const void*)nms_kernel<DEC>, (int)nms_smem));                                   \
+            SSDK_TRY(ssdk_set_max_smem(ctx, (const void*)nms_kernel<DEC, NMS_HEAVY_THREADS>, (int)nms_smem));                                   \
             ssdk_launch(ctx, true, nms_small_kernel<DEC>, dim3(sgrid_nms), dim3(NMS_SMALL_WARPS * 32), 0,                    \
                         (const unsigned long long*)cand, fmt, SC, N.codes, N.anchors, (long long)A, nseg, C, K, N.iou_thr,    \
                         seg_box, seg_score, seg_anchor, seg_kept, heavy_queue, pend_queue, hdr);                              \
-            ssdk_launch(ctx, true, nms_kernel<DEC>, dim3((unsigned)hgrid), dim3(NMS_THREADS), nms_smem,                      \
+            ssdk_launch(ctx, true, nms_kernel<DEC, NMS_HEAVY_THREADS>, dim3((unsigned)hgrid), dim3(NMS_HEAVY_THREADS), nms_smem,                      \
                         (const unsigned long long*)cand, SC, N, seg_kept, (const int*)heavy_queue, (const int*)hdr);          \
         } while (0)
         if (decoded) SSDK_LAUNCH_NMS(true);
