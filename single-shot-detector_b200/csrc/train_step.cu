@@ -346,13 +346,13 @@ int ssdk_train_step_impl(ssdk_ctx* ctx, const HeadGeom& G, const float* anchors,
     // HBM peak, and four streaming CTAs per SM still reach it).  m grows with r = matching / streaming cost; the matcher CTAs are
     // done after tm_busy and then stream for the rest of the kernel: rho = 1 - tm_busy / total is their share of the chunk list
     // relative to a streaming CTA's.  Fitted to the sweep profiles/r2d_split_sweep.json (cfg2: m = 2, rho ~ 0.1 -> 0.1167 ms
-    // = 0.95 of the roofline; 100 boxes per image: m = 4; 20 classes: m = 4-5; stress configuration: m = 4-5, rho = 0).
+    // = 0.95 of the roofline; 100 boxes per image: m = 4; 20 classes: m = 4; stress configuration: m = 4, rho = 0).
     const double t_match = 13.8 + 0.494 * Gmax, t_flat = 0.646 * C;
     int m = ctx->match_ctas_per_sm;
     if (m <= 0) {
         const double r = t_match / t_flat;
         m = (int)(6.0 * r / (r + 0.6) + 0.5);
-        if (m > occ - 1) m = occ - 1;
+        if (m > occ - 2) m = occ - 2;                                       // two streaming CTAs per SM at least (five matchers: 3-14 % slower)
         if (m < 1) m = 1;
     }
     if (m > occ) m = occ;
