@@ -11,8 +11,14 @@
 // The device code lives in matcher.cuh (shared with the fused training-step kernel of train_step.cu).
 #include "matcher.cuh"
 
+#ifndef MATCH_MIN_CTAS
+#define MATCH_MIN_CTAS 6               // 40 registers
+#endif
+#ifndef MATCH_GRID_PER_SM
+#define MATCH_GRID_PER_SM 6
+#endif
 template <bool WRITE_TARGETS>
-__global__ void __launch_bounds__(MATCH_THREADS) match_kernel(const MatchArgs M) {
+__global__ void __launch_bounds__(MATCH_THREADS, MATCH_MIN_CTAS) match_kernel(const MatchArgs M) {
     __shared__ MatchSmem sm;
     MatchNoHook hook;
     match_work_item<WRITE_TARGETS>(M, sm, blockIdx.y, blockIdx.x, gridDim.x, hook);
@@ -90,7 +96,7 @@ int ssdk_match_impl(ssdk_ctx* ctx, const float* anchors, int64_t A, const float*
     double* fused_count = tickets ? out_count : nullptr;
     // about six resident CTAs per SM in total; each CTA walks ceil(nchunks / grid.x) chunks of its image
     const int nchunks = ceil_div_i(A, MATCH_THREADS);
-    int gx = (ctx->num_sms * 6 + B - 1) / B;
+    int gx = (ctx->num_sms * MATCH_GRID_PER_SM + B - 1) / B;
     if (gx > nchunks) gx = nchunks;
     if (gx < 1) gx = 1;
     const dim3 grid(gx, B);

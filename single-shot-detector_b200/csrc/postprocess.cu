@@ -287,7 +287,8 @@ __device__ __forceinline__ void scan_tile(const float4* __restrict__ ptr, long l
 // ballot per iteration cost 15 % of the scan's bandwidth).
 template <bool IS_LOGITS, bool HEAD, int U>
 __device__ __forceinline__ void scan_candidates(const float* __restrict__ base, long long count, const FilterEmit* __restrict__ E,
-                                                unsigned* sat, int* dense_flag, int* cta_stop /*[2]: stop, won*/) {
+                                                unsigned* sat, int* dense_flag, int* cta_stop /*[2]: stop, won*/,
+                                                long long first_tile /*of this CTA*/, long long tile_stride /*CTAs sharing the array*/) {
     const int lane = threadIdx.x & 31;
     const float lim = IS_LOGITS ? E->x_lo : E->thr;
     // peel to 16-byte alignment: head scalars | body float4 | tail scalars
@@ -298,7 +299,7 @@ __device__ __forceinline__ void scan_candidates(const float* __restrict__ base, 
     const long long tail0 = head + (nbody4 << 2);
     const float4* body = (const float4*)(base + head);
 
-    if (blockIdx.x == 0 && threadIdx.x < 32) {
+    if (first_tile == 0 && threadIdx.x < 32) {
         // head + tail elements (< 8 in total), one lane each
         long long e = -1;
         if (lane < head) e = lane;
@@ -310,12 +311,12 @@ __device__ __forceinline__ void scan_candidates(const float* __restrict__ base, 
     // Full tiles (U x 256 float4 = U x 4 KB per CTA and iteration) are read without any bounds test; the one partial
     // tile of the array (the last one, met by a single CTA) goes through the bounded form of the same code.
     const long long tile = (long long)FILTER_THREADS * U;
-    const long long stride = (long long)gridDim.x * tile;
+    const long long stride = tile_stride * tile;
     bool stop = false;
     // the thread's load address advances by a constant (kept as a pointer: recomputing it from the loop index put eight
     // dependent integer instructions in front of every iteration's first load)
-    const float4* ptr = body + (long long)blockIdx.x * tile + threadIdx.x;
-    long long i0 = (long long)blockIdx.x * tile;
+    const float4* ptr = body + first_tile * tile + threadIdx.x;
+    long long i0 = first_tile * tile;
     for (; i0 + tile <= nbody4 && !stop; i0 += stride, ptr += stride)
         scan_tile<IS_LOGITS, HEAD, true, U>(ptr, i0, nbody4, head, lim, E, sat, dense_flag, cta_stop, stop);
     if (i0 < nbody4 && !stop) scan_tile<IS_LOGITS, HEAD, false, U>(ptr, i0, nbody4, head, lim, E, sat, dense_flag, cta_stop, stop);
@@ -343,7 +344,8 @@ __global__ void __launch_bounds__(FILTER_THREADS, FILTER_MIN_CTAS) filter_kernel
         s_emit = e;
     }
     __syncthreads();
-    scan_candidates<IS_LOGITS, false, SCAN_U>(scores + (size_t)b * per_image, per_image, &s_emit, s_sat, img_dense ? img_dense + b : nullptr, s_stop);
+    scan_candidates<IS_LOGITS, false, SCAN_U>(scores + (size_t)b * per_image, per_image, &s_emit, s_sat, img_dense ? img_dense + b : nullptr, s_stop,
+                                               (long long)blockIdx.x, (long long)gridDim.x);
     if (img_dense) {
         // the CTA that declared the image dense prepares filter_dense_kernel's counters and value histograms for it (they are
         // not part of the per-call memset: zeroing 128 bytes per segment on every call cost 2-3 us of the sparse path)
@@ -355,17 +357,24 @@ __global__ void __launch_bounds__(FILTER_THREADS, FILTER_MIN_CTAS) filter_kernel
     }
 }
 
-// Head layout (head-layout fusion, see head.cu): grid (gx, num_levels); level blockIdx.y's class tensor [B, n*C, h, w] (or
-// [B, h, w, n*C]) is scanned as ONE flat array; only a candidate pays for the index arithmetic that recovers
-// (image, anchor, class) from its flat position.
+// Head layout (head-layout fusion, see head.cu): level l's class tensor [B, n*C, h, w] (or [B, h, w, n*C]) is scanned as ONE flat
+// array by the CTAs [cta0[l], cta0[l + 1]) of a one-dimensional grid; only a candidate pays for the index arithmetic that
+// recovers (image, anchor, class) from its flat position.  The levels differ fourfold in size from one to the next, so every
+// level gets CTAs in proportion to its tiles (round 1 launched one full grid row per level: three quarters of the 11,840 CTAs
+// found no tile or one; the scan then took 1.07-1.12 times as long as the anchor-major scan of the same bytes on the same box,
+// now 1.04 times: profiles/r2q_bench.json vs r2e / r2p).
+struct HeadCtas {
+    int cta0[SSDK_MAX_LEVELS + 1];
+};
 template <bool IS_LOGITS>
 __global__ void __launch_bounds__(FILTER_THREADS, FILTER_MIN_CTAS) head_filter_kernel(const HeadGeom G, int B, float thr, float x_lo, KeyFormat fmt,
                                                                     unsigned long long* __restrict__ cand,
-                                                                    int* __restrict__ seg_count) {
+                                                                    int* __restrict__ seg_count, const HeadCtas H) {
     extern __shared__ unsigned s_sat[];                                 // one bit per (image, class) segment (the first 65536 of them)
     __shared__ FilterEmit s_emit;
     pdl_launch_dependents();
-    const int l = blockIdx.y;
+    int l = 0;
+    while (l + 1 < G.num_levels && (int)blockIdx.x >= H.cta0[l + 1]) ++l;
     const LevelGeom g = level_geom(G, l);
     const long long count = (long long)B * g.per_loc * g.C * g.hw;
     const int sat_bits = (int)min((long long)B * g.C, (long long)FILTER_SAT_WORDS * 32);
@@ -377,7 +386,8 @@ __global__ void __launch_bounds__(FILTER_THREADS, FILTER_MIN_CTAS) head_filter_k
         s_emit = e;
     }
     __syncthreads();
-    scan_candidates<IS_LOGITS, true, SCAN_U_HEAD>(G.cls[l], count, &s_emit, s_sat, nullptr, nullptr);
+    scan_candidates<IS_LOGITS, true, SCAN_U_HEAD>(G.cls[l], count, &s_emit, s_sat, nullptr, nullptr, (long long)((int)blockIdx.x - H.cta0[l]),
+                                                  (long long)(H.cta0[l + 1] - H.cta0[l]));
 }
 
 // ---------------------------------------------------------------------------------------------- 1b. dense images
@@ -1655,20 +1665,32 @@ static int postprocess_impl(ssdk_ctx* ctx, const HeadGeom* head, const float* co
             }
         }
         if (head) {
-            long long most = 0;                                           // floats of the largest level
+            // CTAs per level in proportion to its tiles, num_sms * 16 in total (at least one per level)
+            long long tiles[SSDK_MAX_LEVELS], total = 0;
             for (int l = 0; l < head->num_levels; ++l) {
                 const long long cnt = (long long)B * head->per_loc * C * head->hw[l];
-                if (cnt > most) most = cnt;
+                tiles[l] = (cnt / 4 + FILTER_THREADS * SCAN_U_HEAD - 1) / (FILTER_THREADS * SCAN_U_HEAD);
+                if (tiles[l] < 1) tiles[l] = 1;
+                total += tiles[l];
             }
-            long long chunks = (most / 4 + FILTER_THREADS * SCAN_U_HEAD - 1) / (FILTER_THREADS * SCAN_U_HEAD);
-            long long gx = (long long)ctx->num_sms * 16;
-            if (gx > chunks) gx = chunks;
-            if (gx < 1) gx = 1;
-            const dim3 hgrid_f((unsigned)gx, head->num_levels);
+            long long budget = (long long)ctx->num_sms * 16;
+            if (budget > total) budget = total;
+            HeadCtas HC;
+            int next = 0;
+            for (int l = 0; l <= SSDK_MAX_LEVELS; ++l) HC.cta0[l] = 0;
+            for (int l = 0; l < head->num_levels; ++l) {
+                long long n = (tiles[l] * budget + total - 1) / total;
+                if (n < 1) n = 1;
+                if (n > tiles[l]) n = tiles[l];
+                HC.cta0[l] = next;
+                next += (int)n;
+            }
+            for (int l = head->num_levels; l <= SSDK_MAX_LEVELS; ++l) HC.cta0[l] = next;
+            const dim3 hgrid_f((unsigned)next);
             const size_t sat_head = sat_bytes(nseg);
             SSDK_KERNEL(ctx, SSDK_K_FILTER,
-                if (is_logits) head_filter_kernel<true><<<hgrid_f, FILTER_THREADS, sat_head, ctx->stream>>>(*head, B, thr, x_lo, fmt, cand, seg_count);
-                else head_filter_kernel<false><<<hgrid_f, FILTER_THREADS, sat_head, ctx->stream>>>(*head, B, thr, x_lo, fmt, cand, seg_count));
+                if (is_logits) head_filter_kernel<true><<<hgrid_f, FILTER_THREADS, sat_head, ctx->stream>>>(*head, B, thr, x_lo, fmt, cand, seg_count, HC);
+                else head_filter_kernel<false><<<hgrid_f, FILTER_THREADS, sat_head, ctx->stream>>>(*head, B, thr, x_lo, fmt, cand, seg_count, HC));
         } else {
             long long chunks = (per_image / 4 + FILTER_THREADS * SCAN_U - 1) / (FILTER_THREADS * SCAN_U);
             long long gx = ((long long)ctx->num_sms * 16 + B - 1) / B;
