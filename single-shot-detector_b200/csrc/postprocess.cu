@@ -563,6 +563,28 @@ __device__ __forceinline__ void cta_sort_keys(unsigned long long* keys, int n, i
     }
 }
 
+// Rank sort for n <= nthreads keys (all distinct: the anchor index is part of the key): a key's rank is the number of smaller
+// keys; `parts` = nthreads / P threads share one key's count (P = n rounded up to a power of two) and add up with shuffles.
+// Two barriers instead of the bitonic network's log^2: a third of nms_kernel's stall samples sat in that network
+// (ncu source view, profiles/r2m_ncu_summary.txt era build) for segments of 60-120 keys.  dst must not overlap src.
+__device__ __forceinline__ void cta_rank_sort_keys(const unsigned long long* __restrict__ src, unsigned long long* __restrict__ dst, int n,
+                                                   int tid, int nthreads) {
+    int P = 32;
+    while (P < n) P <<= 1;
+    const int parts = nthreads / P;                                   // a power of two in [1, 16] (n > 32, nthreads <= 512)
+    const int i = tid / parts, part = tid - i * parts;
+    const int span = P / parts;
+    int rank = 0;
+    if (i < n) {
+        const unsigned long long mine = src[i];
+        const int j1 = min(n, (part + 1) * span);
+        for (int j = part * span; j < j1; ++j) rank += src[j] < mine ? 1 : 0;
+    }
+    for (int o = 1; o < parts; o <<= 1) rank += __shfl_xor_sync(0xffffffffu, rank, o);
+    if (i < n && part == 0) dst[rank] = src[i];
+    __syncthreads();
+}
+
 // ---------------------------------------------------------------------------------------------- 3. NMS
 // Where the four box codes of (image b, anchor a) live: the anchor-major tensor [B,A,4], or the per-level head tensors.
 struct CodeView {
@@ -870,8 +892,14 @@ __global__ void __launch_bounds__(THREADS, THREADS == 256 ? 5 : 2) nms_kernel(co
         __syncthreads();
         for (int i = tid; i < n; i += THREADS) s_sort[i] = keys[i];
         __syncthreads();
-        cta_sort_keys(s_sort, n, tid, THREADS);                 // score descending, anchor ascending
-        const int kept = nms_sorted_segment<DECODED, THREADS>(N, sh, s_kept, s_kept_area, s_sort, n, seg, 0);
+        const unsigned long long* sorted = s_sort;              // score descending, anchor ascending
+        if (n <= THREADS) {
+            cta_rank_sort_keys(s_sort, s_sort + SEG_CAP / 2, n, tid, THREADS);
+            sorted = s_sort + SEG_CAP / 2;
+        } else {
+            cta_sort_keys(s_sort, n, tid, THREADS);
+        }
+        const int kept = nms_sorted_segment<DECODED, THREADS>(N, sh, s_kept, s_kept_area, sorted, n, seg, 0);
         if (tid == 0) seg_kept[seg] = kept;
     }
 }
