@@ -346,6 +346,35 @@ def test_nms_v3_tensorflow_published_vectors(pkg):
         pkg.multiclass_non_max_suppression(cuda(np.asarray(b, np.float32)), cuda(np.asarray(s, np.float32)).reshape(-1, 1), thr, iou, k)
 
 
+@pytest.mark.parametrize('n', [1, 31, 32, 33, 64, 100, 255, 256, 257, 511, 512, 513, 1000, 4095, 4096, 4097, 5000])
+def test_nms_segment_sizes_around_the_kernel_switches(pkg, n):
+    """One class with exactly n candidates (next to an empty class and one with three candidates): the warp kernel takes up to 32, the CTA kernel
+    sorts up to 512 keys by rank and up to 4096 with the bitonic network, more than 4096 overflow the segment's region and go
+    through the rounds.  Kept indices, scores and boxes must equal the oracle's (NonMaxSuppressionV3 restated) bit for bit."""
+    from oracle import nms
+    rng = np.random.default_rng(7000 + n)
+    A = max(n + 50, 6000)
+    # clustered boxes so that suppression really happens: ~n / 12 clusters
+    k = max(1, n // 12)
+    cl = rng.uniform(0.15, 0.85, [k, 2])
+    which = rng.integers(0, k, A)
+    ctr = cl[which] + rng.normal(0, 0.02, [A, 2])
+    size = rng.uniform(0.05, 0.12, [A, 2])
+    boxes = np.clip(np.concatenate([ctr - size / 2, ctr + size / 2], axis=1), 0, 1).astype(np.float32)
+    scores = np.zeros([A, 3], np.float32)
+    pick = rng.permutation(A)[:n]
+    vals = rng.permutation(np.linspace(0.2, 0.99, n)).astype(np.float32)       # distinct scores: no ties
+    scores[pick, 1] = vals
+    scores[rng.permutation(A)[:3], 2] = np.float32([0.5, 0.6, 0.7])
+    K = 40
+    sb, ss, sc, si = pkg.multiclass_non_max_suppression(cuda(boxes), cuda(scores), 0.1, 0.5, K, return_indices=True)
+    ob, os_, oc = nms.multiclass_non_max_suppression(boxes, scores, 0.1, 0.5, K)
+    assert np.array_equal(sc.cpu().numpy(), oc), (n, sc.cpu().numpy(), oc)
+    assert np.array_equal(ss.cpu().numpy(), os_)
+    assert np.array_equal(sb.cpu().numpy(), ob)
+    assert len(oc) > 0 and (oc == 1).sum() <= K
+
+
 @pytest.mark.parametrize('cfg_id,B,kind,K', [(3, 2, 'realistic', 100), (3, 1, 'dense', 100), (5, 1, 'dense', 100),
                                             (1, 1, 'dense', 5)])
 def test_postprocess_full_size(pkg, cfg_id, B, kind, K):
