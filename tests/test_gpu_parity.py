@@ -238,6 +238,51 @@ def test_loss_full_size(pkg, cfg_id, B, kind):
     close(extra['loc_losses'].cpu().numpy(), o['loc_losses'], atol=1e-9)
 
 
+class _FixedAnchors:
+    """An anchor 'generator' that returns a given [A,4] array (SSD only calls it and reads num_anchors_per_feature_map)."""
+    def __init__(self, anchors):
+        self.anchors = anchors
+        self.num_anchors_per_feature_map = [anchors.shape[0]]
+        self.num_anchors_per_location = 1
+
+    def __call__(self, image_height, image_width, device=None):
+        t = torch.from_numpy(self.anchors)
+        return t.cuda() if device is not None else t
+
+
+@pytest.mark.parametrize('B,A,C', [(1, 12288, 1), (1, 12289, 1), (1, 12291, 1), (1, 12292, 1), (1, 12284, 1), (1, 4095, 1), (1, 4097, 1),
+                                   (2, 2048, 3), (3, 4096, 2), (2, 2049, 3), (1, 40960, 5), (5, 1, 7)])
+def test_loss_sizes_around_the_chunk_boundaries(pkg, B, A, C):
+    """The flat pass reads FULL 4096-float chunks through an advancing pointer and only a tensor's last, partial chunk with bounds
+    tests, plus up to three scalar tail floats: tensors of exactly k chunks, k chunks +- one float4, +1 / +3 floats, less than one
+    chunk.  Sums against the oracle (both the fused training step and the separate launches)."""
+    from oracle import ssd as ossd
+    rng = np.random.default_rng(31 * A + C)
+    ctr = rng.uniform(0.05, 0.95, [A, 2])
+    size = rng.uniform(0.05, 0.3, [A, 2])
+    anchors = np.concatenate([ctr - size / 2, ctr + size / 2], axis=1).astype(np.float32)
+    G = 5
+    gctr = rng.uniform(0.2, 0.8, [B, G, 2])
+    gsize = rng.uniform(0.1, 0.3, [B, G, 2])
+    gt = {'boxes': np.concatenate([gctr - gsize / 2, gctr + gsize / 2], axis=2).astype(np.float32),
+          'labels': rng.integers(0, C, [B, G]).astype(np.int32), 'num_boxes': np.full([B], G, np.int32)}
+    logits = (rng.normal(-3.0, 1.5, [B, A, C])).astype(np.float32)
+    codes = rng.normal(0, 1, [B, A, 4]).astype(np.float32)
+    params = {'gamma': 2.0, 'alpha': 0.25}
+    o = ossd.loss(anchors, codes, logits, gt, params, C, return_all=True)
+    ssd = pkg.SSD.from_predictions(64, 64, {'encoded_boxes': cuda(codes), 'class_predictions': cuda(logits)}, _FixedAnchors(anchors), C)
+    dgt = {k: cuda(v) for k, v in gt.items()}
+    for fused in (1, 0):
+        pkg._lib.set_option(pkg._lib.SSDK_OPT_FUSED_TRAIN_STEP, fused)
+        try:
+            sums = ssd.loss_sums(dgt, params).cpu().numpy()
+        finally:
+            pkg._lib.set_option(pkg._lib.SSDK_OPT_FUSED_TRAIN_STEP, 1)
+        assert sums[2] == float(o['num_matches']), (fused, sums[2], o['num_matches'])
+        close(sums[0], o['loc_sum64'])
+        close(sums[1], o['cls_sum64'])
+
+
 def test_loss_properties_full_batch(pkg):
     """cfg2 at its full size (B=16): shard additivity, image-permutation invariance, empty-GT normaliser."""
     syn = load_pkg('synthetic')
@@ -453,6 +498,44 @@ def test_postprocess_edge_cases(pkg, golden):
     sc[0, 6, 1] = float(np.nextafter(np.float32(0.05), np.float32(1)))
     b, s, c, n, a = pkg.batch_multiclass_non_max_suppression(codes[:1], anchors, sc, 0.05, 0.5, 3, return_anchor_indices=True)
     assert n.item() == 1 and a[0, 0].item() == 6 and c[0, 0].item() == 1
+
+
+@pytest.mark.parametrize('B,A,C', [(1, 2048, 3), (2, 2049, 3), (1, 4096, 3), (2, 6143, 1), (2, 6145, 1), (1, 6147, 1), (3, 100, 1), (2, 12288, 2),
+                                   (2, 6144 * 3 + 5, 1)])
+@pytest.mark.parametrize('from_logits', [False, True])
+def test_postprocess_sizes_around_the_tile_boundaries(pkg, B, A, C, from_logits):
+    """The score scan reads FULL tiles (6 x 256 float4 = 6144 floats) without bounds tests and only an image's last, partial tile
+    with them; an image whose A*C is odd starts at a misaligned address (scalar head / tail elements).  Arrays of exactly k tiles,
+    k tiles +- a few floats, less than a tile; candidates planted in the first / last elements of every image.  Against the oracle."""
+    from oracle import losses as olosses, nms as onms
+    rng = np.random.default_rng(977 * A + C + B)
+    ctr = rng.uniform(0.1, 0.9, [A, 2])
+    size = rng.uniform(0.05, 0.2, [A, 2])
+    anchors = np.concatenate([ctr - size / 2, ctr + size / 2], axis=1).astype(np.float32)
+    codes = rng.normal(0, 0.5, [B, A, 4]).astype(np.float32)
+    logits = rng.normal(-6.0, 1.0, [B, A, C]).astype(np.float32)
+    hot = rng.random([B, A, C]) < 0.01
+    logits[hot] = rng.normal(1.0, 1.0, int(hot.sum())).astype(np.float32)
+    flat = logits.reshape(B, -1)
+    flat[:, :3] = np.float32([2.0, 1.5, 2.5])                          # the first and the last elements of every image
+    flat[:, -3:] = np.float32([1.0, 3.0, 0.5])
+    scores = olosses.sigmoid(logits)
+    want = onms.batch_multiclass_non_max_suppression(codes, anchors, scores, 0.05, 0.5, 5, return_anchor_indices=True)
+    if from_logits:
+        ssd = pkg.SSD.from_predictions(64, 64, {'encoded_boxes': cuda(codes), 'class_predictions': cuda(logits)}, _FixedAnchors(anchors), C)
+        p = ssd.get_predictions(0.05, 0.5, 5)
+        got = (p['boxes'], p['scores'], p['labels'], p['num_boxes'])
+        assert np.array_equal(got[3].cpu().numpy(), want[3])
+        assert np.array_equal(got[2].cpu().numpy(), want[2])
+        close(got[1].cpu().numpy(), want[1])
+        close(got[0].cpu().numpy(), want[0], atol=1e-7)
+    else:
+        b, s_, c, n, a = pkg.batch_multiclass_non_max_suppression(cuda(codes), cuda(anchors), cuda(scores), 0.05, 0.5, 5,
+                                                                  return_anchor_indices=True)
+        assert np.array_equal(n.cpu().numpy(), want[3]) and want[3].min() > 0
+        assert np.array_equal(a.cpu().numpy(), want[4])                   # kept anchor indices: bit-exact
+        assert np.array_equal(c.cpu().numpy(), want[2]) and np.array_equal(s_.cpu().numpy(), want[1])
+        close(b.cpu().numpy(), want[0], atol=1e-7)
 
 
 def test_detect_box_scaler_and_final_threshold(pkg, golden):
