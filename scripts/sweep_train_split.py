@@ -47,6 +47,8 @@ def workload(cfg_id, B, G=None, C=None):
 out = {}
 cases = [('cfg2_B16', 2, 16, None, None), ('cfg2_B32', 2, 32, None, None), ('cfg2_B4', 2, 4, None, None), ('cfg2_B16_G100', 2, 16, 100, None),
          ('cfg2_B16_C20', 2, 16, None, 20), ('cfg5_B8_G300', 5, 8, None, None), ('cfg1_B1', 1, 1, None, None)]
+if os.environ.get('SWEEP_SMALL_BATCHES'):
+    cases = [('cfg2_B%d' % b, 2, b, None, None) for b in (1, 2, 3, 4, 6, 8, 12)] + [('cfg1_B%d' % b, 1, b, None, None) for b in (2, 4, 8)]
 for name, cid, B, G, C in cases:
     ssd, gt, A, C, G = workload(cid, B, G, C)
     res = {'A': A, 'C': C, 'G': G, 'B': B}

@@ -348,12 +348,17 @@ int ssdk_train_step_impl(ssdk_ctx* ctx, const HeadGeom& G, const float* anchors,
     // relative to a streaming CTA's.  Fitted to the sweep profiles/r2d_split_sweep.json (cfg2: m = 2, rho ~ 0.1 -> 0.1167 ms
     // = 0.95 of the roofline; 100 boxes per image: m = 4; 20 classes: m = 4; stress configuration: m = 4, rho = 0).
     const double t_match = 13.8 + 0.494 * Gmax, t_flat = 0.646 * C;
+    bool small_batch = false;
     int m = ctx->match_ctas_per_sm;
     if (m <= 0) {
         const double r = t_match / t_flat;
         m = (int)(6.0 * r / (r + 0.6) + 0.5);
         if (m > occ - 2) m = occ - 2;                                       // two streaming CTAs per SM at least (five matchers: 3-14 % slower)
         if (m < 1) m = 1;
+        // Small batches: the matcher's critical path (its chunks one after the other in every matcher CTA, then the forced matches
+        // and the final reduction, ~10 us) is longer than the streaming, so a third matcher CTA per SM pays as long as a matcher
+        // CTA has fewer than ~19 chunks to walk (cfg2: below 12 images; 13-32 % faster at 2-8 images, profiles/r2u_split_sweep_small.json)
+        if (m < 3 && occ >= 5 && (long long)nchunks_img * B < 19ll * ctx->num_sms * m) { m = 3; small_batch = true; }
     }
     if (m > occ) m = occ;
     long long n_match = (long long)ctx->num_sms * m;
@@ -374,7 +379,7 @@ int ssdk_train_step_impl(ssdk_ctx* ctx, const HeadGeom& G, const float* anchors,
     if (ctx->match_flat_share_pct < 0) {
         const double tm_busy = t_match * 5.7 / m;
         const double t_all = tm_busy > t_flat + 0.65 * t_match ? tm_busy : t_flat + 0.65 * t_match;
-        rho = 1.0 - tm_busy / t_all;
+        rho = small_batch ? 0.05 : 1.0 - tm_busy / t_all;
         if (rho < 0.0) rho = 0.0;
         if (rho > 1.0) rho = 1.0;
     }
