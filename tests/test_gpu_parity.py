@@ -283,6 +283,38 @@ def test_loss_sizes_around_the_chunk_boundaries(pkg, B, A, C):
         close(sums[1], o['cls_sum64'])
 
 
+@pytest.mark.parametrize('G', [512, 513, 700])
+def test_more_boxes_than_one_staging_chunk(pkg, G):
+    """More ground-truth boxes per image than the matcher stages at once (512): the boxes are staged chunk by chunk, the forced
+    matches run as their own kernel, and SSD.loss takes the separate-launch route instead of the fused training step.  matches /
+    cls_targets bit-exact, sums to 1e-5."""
+    from oracle import ssd as ossd, training_target_creation as ottc
+    rng = np.random.default_rng(100 + G)
+    B, A, C = 2, 9000, 4
+    ctr = rng.uniform(0.05, 0.95, [A, 2])
+    size = rng.uniform(0.03, 0.25, [A, 2])
+    anchors = np.concatenate([ctr - size / 2, ctr + size / 2], axis=1).astype(np.float32)
+    gctr = rng.uniform(0.1, 0.9, [B, G, 2])
+    gsize = rng.uniform(0.03, 0.2, [B, G, 2])
+    gt = {'boxes': np.concatenate([gctr - gsize / 2, gctr + gsize / 2], axis=2).astype(np.float32),
+          'labels': rng.integers(0, C, [B, G]).astype(np.int32), 'num_boxes': np.int32([G, G - 7])}
+    logits = rng.normal(-3.0, 1.5, [B, A, C]).astype(np.float32)
+    codes = rng.normal(0, 1, [B, A, 4]).astype(np.float32)
+    params = {'gamma': 2.0, 'alpha': 0.25}
+    o = ossd.loss(anchors, codes, logits, gt, params, C, return_all=True)
+    ssd = pkg.SSD.from_predictions(64, 64, {'encoded_boxes': cuda(codes), 'class_predictions': cuda(logits)}, _FixedAnchors(anchors), C)
+    dgt = {k: cuda(v) for k, v in gt.items()}
+    sums = ssd.loss_sums(dgt, params, keep_targets=True).cpu().numpy()
+    for b in range(B):
+        n = int(gt['num_boxes'][b])
+        reg, cls_t, m = ottc.get_training_targets(anchors, gt['boxes'][b, :n], gt['labels'][b, :n], 0.5, 0.5)   # ssd.py:187-188 passes the module constants
+        assert np.array_equal(ssd._saved['matches'][b].cpu().numpy(), m), b
+        assert np.array_equal(ssd._saved['cls_targets'][b].cpu().numpy(), cls_t), b
+    assert sums[2] == float(o['num_matches'])
+    close(sums[0], o['loc_sum64'])
+    close(sums[1], o['cls_sum64'])
+
+
 def test_loss_properties_full_batch(pkg):
     """cfg2 at its full size (B=16): shard additivity, image-permutation invariance, empty-GT normaliser."""
     syn = load_pkg('synthetic')
@@ -536,6 +568,33 @@ def test_postprocess_sizes_around_the_tile_boundaries(pkg, B, A, C, from_logits)
         assert np.array_equal(a.cpu().numpy(), want[4])                   # kept anchor indices: bit-exact
         assert np.array_equal(c.cpu().numpy(), want[2]) and np.array_equal(s_.cpu().numpy(), want[1])
         close(b.cpu().numpy(), want[0], atol=1e-7)
+
+
+@pytest.mark.parametrize('C,A,dense', [(400, 4500, True), (1100, 4400, True), (1100, 3000, False), (330, 5000, True)])
+def test_postprocess_many_classes(pkg, C, A, dense):
+    """More classes than the dense-segment kernel keeps per-class tables for in shared memory (320), and more than the dense-image
+    filter handles (1024): with dense scores every segment overflows its 4096-key region, so the rounds run with their tables in
+    global memory; kept anchor indices bit-exact against the oracle."""
+    from oracle import nms as onms
+    rng = np.random.default_rng(C * 7 + A)
+    B, K = 2, 6
+    ctr = rng.uniform(0.1, 0.9, [A, 2])
+    size = rng.uniform(0.05, 0.25, [A, 2])
+    anchors = np.concatenate([ctr - size / 2, ctr + size / 2], axis=1).astype(np.float32)
+    codes = rng.normal(0, 0.3, [B, A, 4]).astype(np.float32)
+    scores = rng.random([B, A, C], dtype=np.float32)
+    if dense:
+        scores = (0.02 + 0.98 * scores).astype(np.float32)             # ~97 % above 0.05: > 4096 candidates in every segment
+    else:
+        scores = np.where(scores > 0.99, scores, np.float32(0.01)).astype(np.float32)
+    want = onms.batch_multiclass_non_max_suppression(codes, anchors, scores, 0.05, 0.5, K, return_anchor_indices=True)
+    b, s_, c, n, a = pkg.batch_multiclass_non_max_suppression(cuda(codes), cuda(anchors), cuda(scores), 0.05, 0.5, K,
+                                                              return_anchor_indices=True)
+    assert pkg._lib.async_error() == 0
+    assert np.array_equal(n.cpu().numpy(), want[3]) and want[3].min() > 0
+    assert np.array_equal(a.cpu().numpy(), want[4])
+    assert np.array_equal(c.cpu().numpy(), want[2]) and np.array_equal(s_.cpu().numpy(), want[1])
+    close(b.cpu().numpy(), want[0], atol=1e-7)
 
 
 def test_detect_box_scaler_and_final_threshold(pkg, golden):
