@@ -244,6 +244,13 @@ SSDK_API int ssdk_ssd_targets_and_loss_host(ssdk_ctx* ctx, const float* anchors,
 #define SSDK_INPUT_LOGITS 1        /* `scores` are logits; sigmoid is fused (SSD.get_predictions, ssd.py:60) */
 #define SSDK_BOXES_ENCODED 0       /* `codes` are box codes, decoded against `anchors` and clipped (nms.py:76-77) */
 #define SSDK_BOXES_DECODED 2       /* `codes` are final boxes [B,A,4]; anchors ignored (multiclass_nms, nms.py:6) */
+/* Split-phase post-processing (optional): a call with SSDK_POST_SCAN_ONLY enqueues only the HBM-bound part (counters zeroed, the
+ * score scan, the dense-image filter) and writes no output; a following call with SSDK_POST_FINISH_ONLY and otherwise IDENTICAL
+ * arguments, on the same context, with no other post-processing call in between, enqueues the rest (NMS stages, pack).  The two
+ * calls may be issued on different streams (ssdk_ctx_set_stream) when the second stream waits for the first call's work: the
+ * latency-bound second phase can then run next to another sub-path's streaming kernel.  Both flags clear = the whole chain. */
+#define SSDK_POST_SCAN_ONLY 16
+#define SSDK_POST_FINISH_ONLY 32
 /* batch_multiclass_non_max_suppression (nms.py:48-102) with tf.image.non_max_suppression
  * (TF 1.12 NonMaxSuppressionV3) semantics per class: candidates score > score_threshold,
  * greedy in descending score (ties: lower anchor index), suppress iff IoU > iou_threshold,

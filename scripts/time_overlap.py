@@ -46,13 +46,29 @@ def timeit(fn, reps=40):
     cap.release()
     return round(best, 5)
 
-out = {'train': timeit(train), 'infer': timeit(infer), 'sequential': timeit(lambda: (train(), infer()))}
-for ctas in (0, 5, 4, 3):
+scan = lambda: si.get_predictions(0.05, 0.5, 100, phase='scan')
+finish = lambda: si.get_predictions(0.05, 0.5, 100, phase='finish')
+ref = infer()
+scan()
+two = finish()
+out = {'split_phase_equals_whole': bool(all(torch.equal(ref[k], two[k]) for k in ref)),
+       'train': timeit(train), 'infer': timeit(infer), 'infer_split': timeit(lambda: (scan(), finish())),
+       'scan_only': timeit(scan), 'sequential': timeit(lambda: (train(), infer()))}
+# the scan first (alone on the GPU), then the training step next to the latency-bound rest of the post-processing
+for ctas in (0, 5, 4):
+    for name, pr in (('', None), ('_finish_hi', (0, -1)), ('_train_hi', (-1, 0))):
+        conc = pkg.graph.concurrent(train, finish, priorities=pr, train_ctas_per_sm=ctas)
+        out['scan_then_train_and_finish_ctas%d%s' % (ctas, name)] = timeit(lambda: (scan(), conc()))
+    conc2 = pkg.graph.concurrent(finish, train, train_ctas_per_sm=ctas)
+    out['scan_then_finish_and_train_ctas%d' % ctas] = timeit(lambda: (scan(), conc2()))
+# the training step first, then the scan, then the rest
+out['train_scan_finish'] = timeit(lambda: (train(), scan(), finish()))
+for ctas in (0, 5):
     L.set_option(L.SSDK_OPT_TRAIN_CTAS_PER_SM, ctas)
     out['train_ctas%d' % ctas] = timeit(train)
     for name, fns, pr in (('train_first', (train, infer), None), ('infer_first', (infer, train), None),
                           ('infer_first_hi', (infer, train), (-1, 0)), ('train_first_infer_hi', (train, infer), (0, -1)),
                           ('train_first_hi', (train, infer), (-1, 0))):
-        out['ctas%d_%s' % (ctas, name)] = timeit(pkg.graph.concurrent(*fns, priorities=pr))
+        out['ctas%d_%s' % (ctas, name)] = timeit(pkg.graph.concurrent(*fns, priorities=pr, train_ctas_per_sm=ctas))
 L.set_option(L.SSDK_OPT_TRAIN_CTAS_PER_SM, 0)
 print(json.dumps(out))

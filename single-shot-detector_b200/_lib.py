@@ -99,6 +99,7 @@ class SsdkHeadGrads(ctypes.Structure):
 
 SSDK_INPUT_SCORES, SSDK_INPUT_LOGITS = 0, 1
 SSDK_BOXES_ENCODED, SSDK_BOXES_DECODED = 0, 2
+SSDK_POST_SCAN_ONLY, SSDK_POST_FINISH_ONLY = 16, 32
 
 _lib = None
 _lock = threading.Lock()

@@ -1627,9 +1627,11 @@ static int postprocess_impl(ssdk_ctx* ctx, const HeadGeom* head, const float* co
                  iou_threshold);
     if (B == 0) return SSDK_OK;
     SsdkWsGuard ws_guard(ctx, SSDK_WS_POST);
-    SSDK_REQUIRE(by_label || (out_boxes && out_scores && out_classes && out_num), SSDK_ERR_ARG, "ssdk_postprocess: null output");
     const bool decoded = (flags & SSDK_BOXES_DECODED) != 0;
     const bool is_logits = (flags & SSDK_INPUT_LOGITS) != 0;
+    const bool scan_only = (flags & SSDK_POST_SCAN_ONLY) != 0, finish_only = (flags & SSDK_POST_FINISH_ONLY) != 0;
+    SSDK_REQUIRE(!(scan_only && finish_only), SSDK_ERR_ARG, "ssdk_postprocess: SSDK_POST_SCAN_ONLY and SSDK_POST_FINISH_ONLY exclude each other");
+    SSDK_REQUIRE(scan_only || by_label || (out_boxes && out_scores && out_classes && out_num), SSDK_ERR_ARG, "ssdk_postprocess: null output");
     SSDK_REQUIRE(A == 0 || head || (codes && scores), SSDK_ERR_ARG, "ssdk_postprocess: null input");
     SSDK_REQUIRE(A == 0 || decoded || anchors, SSDK_ERR_ARG, "ssdk_postprocess: null anchors");
     SSDK_REQUIRE(!(head && decoded), SSDK_ERR_ARG, "ssdk_head_detect: head tensors hold encoded boxes");
@@ -1678,8 +1680,10 @@ static int postprocess_impl(ssdk_ctx* ctx, const HeadGeom* head, const float* co
     float4* seg_box = (float4*)ctx->ws_seg.p;
     float* seg_score = (float*)(seg_box + seg_elems);
     int* seg_anchor = (int*)(seg_score + seg_elems);
-    SSDK_CHECK_CUDA(cudaMemsetAsync(hdr, 0, n_zero * sizeof(int), ctx->stream));
-    if (per_image == 0) SSDK_CHECK_CUDA(cudaMemsetAsync(seg_kept, 0, (size_t)nseg * sizeof(int), ctx->stream));
+    if (!finish_only) {
+        SSDK_CHECK_CUDA(cudaMemsetAsync(hdr, 0, n_zero * sizeof(int), ctx->stream));
+        if (per_image == 0) SSDK_CHECK_CUDA(cudaMemsetAsync(seg_kept, 0, (size_t)nseg * sizeof(int), ctx->stream));
+    }
 
     const float thr = (float)score_threshold;
     if (per_image > 0) {
@@ -1692,7 +1696,9 @@ static int postprocess_impl(ssdk_ctx* ctx, const HeadGeom* head, const float* co
                 x_lo = (float)(lg - 1e-3 * (1.0 + fabs(lg)));
             }
         }
-        if (head) {
+        if (finish_only) {
+            // the scan of this very call was enqueued by the SSDK_POST_SCAN_ONLY call before
+        } else if (head) {
             // CTAs per level in proportion to its tiles, num_sms * 16 in total (at least one per level)
             long long tiles[SSDK_MAX_LEVELS], total = 0;
             for (int l = 0; l < head->num_levels; ++l) {
@@ -1743,6 +1749,8 @@ static int postprocess_impl(ssdk_ctx* ctx, const HeadGeom* head, const float* co
                     else ssdk_launch(ctx, true, filter_dense_kernel<false>, dgrid, dim3(FILTER_THREADS), dsmem, scores, per_image, C, thr, x_lo, fmt, cand, seg_count_dense, (const int*)img_dense, vhist));
             }
         }
+
+        if (scan_only) return SSDK_OK;
 
         // 2.-3. NMS: one warp per small segment (<= 32 candidates, sorted with shuffles), then one CTA per queued heavy
         //       segment (sorted by the CTA)
@@ -1830,6 +1838,7 @@ static int postprocess_impl(ssdk_ctx* ctx, const HeadGeom* head, const float* co
                 else ssdk_launch(ctx, true, nms_rounds_kernel<false, false>, dim3(rgrid), dim3(NMS_THREADS), rsmem, G, B, thr, x_lo, cand, N, seg_kept, R));
         }
     }
+    if (scan_only) return SSDK_OK;
     // 5. pack
     if (by_label) {
         SSDK_KERNEL(ctx, SSDK_K_PACK,

@@ -174,23 +174,29 @@ class SSD:
 
     # ------------------------------------------------------------------ inference (ssd.py:42-69)
     def get_predictions(self, score_threshold=0.05, iou_threshold=0.5, max_boxes_per_class=20, out=None,
-                        box_scaler=None, final_score_threshold=None):
+                        box_scaler=None, final_score_threshold=None, phase=None):
         """Returns {'boxes' [B,N,4], 'labels' [B,N] int, 'scores' [B,N], 'num_boxes' [B]}, N = C * max_boxes_per_class.
         The sigmoid of ssd.py:60 is fused into the score-threshold pass.  Optional extensions fold in the two consumers
         that follow in the reference: `box_scaler` [B,4] (boxes /= box_scaler, model.py:67-68) and
         `final_score_threshold` (keep score > it, order preserved, inference/detector.py:54-58)."""
         if self._host_mode():
-            assert box_scaler is None and final_score_threshold is None, 'extensions need device tensors' 
+            assert box_scaler is None and final_score_threshold is None and phase is None, 'extensions need device tensors' 
             return self._get_predictions_host(score_threshold, iou_threshold, max_boxes_per_class, out)
         head = self._head()
         if head is not None:
+            assert phase is None, 'split-phase post-processing: anchor-major tensors only'
             return self._get_predictions_head(head, score_threshold, iou_threshold, max_boxes_per_class, box_scaler,
                                               final_score_threshold)
-        boxes, scores, classes, num = batch_multiclass_non_max_suppression(
+        # phase='scan' enqueues only the HBM-bound score scan (returns None), phase='finish' with the same arguments the rest:
+        # a caller that overlaps sub-paths can put the latency-bound NMS stages next to another sub-path's streaming kernel
+        res = batch_multiclass_non_max_suppression(
             self.raw_predictions['encoded_boxes'], self.anchors, self.raw_predictions['class_predictions'],
             score_threshold=score_threshold, iou_threshold=iou_threshold,
             max_boxes_per_class=max_boxes_per_class, scores_are_logits=True,
-            box_scaler=box_scaler, final_score_threshold=final_score_threshold)
+            box_scaler=box_scaler, final_score_threshold=final_score_threshold, phase=phase)
+        if res is None:
+            return None
+        boxes, scores, classes, num = res
         return {'boxes': boxes, 'labels': classes, 'scores': scores, 'num_boxes': num}
 
     def _get_predictions_head(self, head, score_threshold, iou_threshold, max_boxes_per_class, box_scaler=None,

@@ -51,7 +51,7 @@ def multiclass_non_max_suppression(boxes, scores, score_threshold, iou_threshold
 
 def batch_multiclass_non_max_suppression(encoded_boxes, anchors, scores, score_threshold, iou_threshold,
                                          max_boxes_per_class, scores_are_logits=False, return_anchor_indices=False,
-                                         box_scaler=None, final_score_threshold=None):
+                                         box_scaler=None, final_score_threshold=None, phase=None):
     """reference :48-102.  encoded_boxes [B,N,4], anchors [N,4], scores [B,N,C] ->
     boxes [B,N',4], scores [B,N'], classes [B,N'], num_detections [B], N' = C * max_boxes_per_class.
     scores_are_logits=True fuses the sigmoid of ssd.py:60 into the streaming pass."""
@@ -61,8 +61,13 @@ def batch_multiclass_non_max_suppression(encoded_boxes, anchors, scores, score_t
     e = call.tensor(encoded_boxes, torch.float32, (B, A, 4))
     a = call.tensor(anchors, torch.float32, (A, 4))
     flags = (_lib.SSDK_INPUT_LOGITS if scores_are_logits else _lib.SSDK_INPUT_SCORES) | _lib.SSDK_BOXES_ENCODED
-    return call.result(*_postprocess(call, e, a, s, flags, score_threshold, iou_threshold, max_boxes_per_class,
-                                     return_anchor_indices, box_scaler, final_score_threshold))
+    # phase (an extension): 'scan' enqueues only the HBM-bound score scan, a following call with phase='finish' and the same
+    # arguments the latency-bound rest (include/ssdk.h: SSDK_POST_SCAN_ONLY / SSDK_POST_FINISH_ONLY)
+    assert phase in (None, 'scan', 'finish')
+    flags |= {None: 0, 'scan': _lib.SSDK_POST_SCAN_ONLY, 'finish': _lib.SSDK_POST_FINISH_ONLY}[phase]
+    out = _postprocess(call, e, a, s, flags, score_threshold, iou_threshold, max_boxes_per_class,
+                       return_anchor_indices, box_scaler, final_score_threshold)
+    return None if phase == 'scan' else call.result(*out)
 
 
 def batch_detections_by_label(encoded_boxes, anchors, scores, score_threshold, iou_threshold, max_boxes_per_class,

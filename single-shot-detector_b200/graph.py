@@ -46,7 +46,7 @@ class CapturedStep:
         return False
 
 
-def concurrent(*fns, device=None, priorities=None, train_ctas_per_sm=5):
+def concurrent(*fns, device=None, priorities=None, train_ctas_per_sm=None):
     """Returns a function that runs the independent `fns` on one side stream each, forked from and joined to the current
     stream.  Inside `capture` this becomes parallel branches of the CUDA graph, so the ALU- / latency-bound kernels of one
     sub-path (matching, sorting, NMS, packing) hide behind the HBM-bound kernels of another (the loss pass, the score scan).
@@ -61,9 +61,9 @@ def concurrent(*fns, device=None, priorities=None, train_ctas_per_sm=5):
         outs = []
         for st in streams:
             st.wait_stream(cur)
-        # the fused training-step kernel is persistent and takes every CTA slot of the GPU (six per SM); next to another sub-path
-        # it leaves one slot per SM free, so that the other branch's short kernels (sorting, NMS, packing) are scheduled
-        # while it streams (measured for the bench step: 0.355 vs 0.360 ms; 4 or 3 CTAs per SM: 0.358)
+        # train_ctas_per_sm: the fused training-step kernel is persistent and takes every CTA slot of the GPU (six per SM); a smaller
+        # value leaves room for the other branch's short kernels.  Measured for the bench step with the round-2 kernels
+        # (profiles/r3a_overlap.json): six 0.340 ms, five 0.344 ms, four 0.371 ms -- the default leaves it alone.
         if train_ctas_per_sm:
             _lib.set_option(_lib.SSDK_OPT_TRAIN_CTAS_PER_SM, int(train_ctas_per_sm), dev.index)
         try:

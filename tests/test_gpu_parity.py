@@ -597,6 +597,30 @@ def test_postprocess_many_classes(pkg, C, A, dense):
     close(b.cpu().numpy(), want[0], atol=1e-7)
 
 
+def test_split_phase_postprocess(pkg, golden):
+    """SSDK_POST_SCAN_ONLY followed by SSDK_POST_FINISH_ONLY (the second phase on another stream that waits for the first) gives
+    exactly what the whole chain gives; both flags together are refused."""
+    g = golden('postprocess')
+    H, W = [int(v) for v in g['HW']]
+    ssd = _ssd(pkg, H, W, [1.0, 1.4142], g['logits'], g['codes'], int(g['C']))
+    whole = ssd.get_predictions(0.05, 0.5, 10)
+    assert ssd.get_predictions(0.05, 0.5, 10, phase='scan') is None
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        two = ssd.get_predictions(0.05, 0.5, 10, phase='finish')
+    torch.cuda.current_stream().wait_stream(side)
+    assert all(torch.equal(whole[k], two[k]) for k in whole) and int(whole['num_boxes'].sum()) > 0
+    lib = pkg._lib
+    from ctypes import c_void_p
+    t = torch.zeros([1, 8, 4], device='cuda')
+    sc = torch.zeros([1, 8, 2], device='cuda')
+    o4, o1, oi, on = torch.zeros([1, 4, 4], device='cuda'), torch.zeros([1, 4], device='cuda'), torch.zeros([1, 4], dtype=torch.int32, device='cuda'), torch.zeros([1], dtype=torch.int32, device='cuda')
+    rc = lib.load().ssdk_postprocess(lib.context(0), t.data_ptr(), t[0].data_ptr(), sc.data_ptr(), lib.SSDK_POST_SCAN_ONLY | lib.SSDK_POST_FINISH_ONLY,
+                                     1, 8, 2, 0.05, 0.5, 2, o4.data_ptr(), o1.data_ptr(), oi.data_ptr(), on.data_ptr(), None)
+    assert rc == -1                                                      # SSDK_ERR_ARG
+
+
 def test_detect_box_scaler_and_final_threshold(pkg, golden):
     """ssdk_detect == get_predictions followed by the reference's consumers: boxes /= box_scaler (model.py:67-68) and the
     host-side `scores > score_threshold` mask of inference/detector.py:54-58 (order preserved)."""
