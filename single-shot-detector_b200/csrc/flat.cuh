@@ -101,13 +101,16 @@ __device__ __forceinline__ double flat_sum_range(const FlatSegs& S, long long g,
         long long full_end = c0 + (S.count[sg] >> 2) / FLAT_CHUNK4;          // chunks [c0, full_end) hold FLAT_CHUNK4 float4 each
         if (full_end > g_end) full_end = g_end;
         const float4* p = (const float4*)S.src[sg] + (g - c0) * FLAT_CHUNK4 + tid;
+        // a 32-bit trip count instead of 64-bit chunk indices in the loop (the kernel lives on 40 registers)
+        const int n_iter = g < full_end ? (int)((full_end - g + stride - 1) / stride) : 0;
 #pragma unroll 1
-        for (; g < full_end; g += stride, p += pstep) {
+        for (int it = 0; it < n_iter; ++it, p += pstep) {
             float4 v[FLAT_U];
 #pragma unroll
             for (int u = 0; u < FLAT_U; ++u) v[u] = ld_stream_f4(p + u * FLAT_THREADS);
             acc += (double)flat_math<GAMMA_MODE>(v, gamma);
         }
+        g += (long long)n_iter * stride;
         if (g < c1 && g < g_end) {                                            // the segment's partial last chunk
             FlatChunk ck;
             int cursor = sg;

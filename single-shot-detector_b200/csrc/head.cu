@@ -34,7 +34,7 @@ struct HeadGradPtrs {
 
 // ---------------------------------------------------------------------------------------------- 1. flat pass
 template <int GAMMA_MODE, bool WITH_GRAD>
-__global__ void __launch_bounds__(FLAT_THREADS) head_flat_kernel(const FlatSegs S, float gamma, float alpha,
+__global__ void __launch_bounds__(FLAT_THREADS, WITH_GRAD ? 4 : 6) head_flat_kernel(const FlatSegs S, float gamma, float alpha,
                                                                   const double* __restrict__ norm_count,
                                                                   const float* __restrict__ upstream,
                                                                   double* __restrict__ partials /*[grid]*/) {
