@@ -317,6 +317,13 @@ def run_ours(args):
             peer = bool(pkg.parallel.connect_peers())          # NVLink peer-memory all-reduce (csrc/comm.cu); NCCL if it cannot connect
         ssd_t.peer_all_reduce = peer
 
+    # private workspace the inference sub-path needs (bounded candidate regions: 32 KB per (image, class) segment), measured before
+    # anything else touches the context
+    ws_before = lib.workspace_bytes(local_rank)
+    ssd_i.get_predictions(SCORE_THR, IOU_THR, K_PER_CLASS)
+    torch.cuda.synchronize()
+    ws_post = lib.workspace_bytes(local_rank) - ws_before
+
     def step_resident():
         losses = ssd_t.loss(d_gt, PARAMS)
         pred = ssd_i.get_predictions(SCORE_THR, IOU_THR, K_PER_CLASS)
@@ -653,6 +660,8 @@ def run_ours(args):
             'train_fwd_bwd_ms_per_step_with_targets_assigned_earlier': ms_train_fb_pre,
             'train_fwd_bwd_with_targets_assigned_earlier_frac_of_hbm_roofline': ((8 * A * C + 56 * A) * Bt / (ms_train_fb_pre * 1e-3) / 1e9) / peak,
             'workspace_bytes': lib.workspace_bytes(local_rank),
+            'postprocess_workspace_bytes_cfg3': int(ws_post), 'postprocess_workspace_over_logits_bytes': ws_post / float(d_ilog.numel() * 4),
+            'workspace_note': 'workspace_bytes = everything this context ever needed in this run (incl. the staging buffers of the e2e loop and the batch-256 targets of cfg4)',
             'cfg4_strong': extras.get('cfg4_strong'),
             'stress': extras.get('stress'),
             'head_layout': extras.get('head_layout'),
