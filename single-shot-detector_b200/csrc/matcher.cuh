@@ -20,7 +20,9 @@
 #include "common.cuh"
 
 #define MATCH_THREADS 256
+#ifndef GT_CHUNK
 #define GT_CHUNK 512
+#endif
 
 struct MatchSmem {
     float4 box[GT_CHUNK];
