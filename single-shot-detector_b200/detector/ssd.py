@@ -332,7 +332,7 @@ class SSD:
         reg, cls_t, matches = call.empty([B, A, 4], torch.float32), call.empty([B, A], torch.int32), call.empty([B, A], torch.int32)
         sums = call.empty([3], torch.float64)
         d = head.descriptor()
-        # targets (ssd.py:84) + losses (ssd.py:89-133); the matcher runs on the library's side stream behind the flat pass
+        # targets (ssd.py:84) + losses (ssd.py:89-133): one launch of the fused training-step kernel (csrc/train_step.cu)
         _lib.check(_lib.load().ssdk_head_ssd_targets_and_loss(
             call.ctx(), ctypes.byref(d), ptr(anchors), ptr(gt), ptr(labels), ptr(num), B, A, C, G,
             float(this_module.POSITIVES_THRESHOLD), float(this_module.NEGATIVES_THRESHOLD), float(params['gamma']),
