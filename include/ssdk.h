@@ -72,6 +72,12 @@ SSDK_API int ssdk_ctx_set_stream(ssdk_ctx* ctx, void* stream);
  * the NMS kernels, pack) are launched with programmatic dependent launch, so that each one's launch and prologue overlap its
  * predecessor's tail; 0 = plain stream order.  Same results either way. */
 #define SSDK_OPT_PROGRAMMATIC_LAUNCH 5
+/* SSDK_OPT_TRAIN_DYNAMIC_CHUNKS (default 1; environment SSDK_TRAIN_DYNAMIC): the streaming part of the fused training-step kernel
+ * hands out its chunks dynamically (one atomic per four chunks) and adds the flat sum in 2^-32 fixed point, so that the result is
+ * bit-identical from run to run whichever CTA took which chunk; the matcher CTAs join the streaming the moment they are done
+ * (SSDK_OPT_MATCH_FLAT_SHARE_PCT is then unused), and CTAs that start late -- their SM was busy with another sub-path's kernel --
+ * simply take fewer chunks.  0 = the static split (double accumulation in a fixed order); the two modes agree to ~1e-7 relative. */
+#define SSDK_OPT_TRAIN_DYNAMIC_CHUNKS 6
 SSDK_API int ssdk_ctx_set_option(ssdk_ctx* ctx, int option, int value);
 SSDK_API int ssdk_ctx_destroy(ssdk_ctx* ctx);
 /* Bytes of private workspace currently held (grows on demand, never shrinks). */

@@ -48,6 +48,7 @@ def timeit(fn, reps=40):
 
 scan = lambda: si.get_predictions(0.05, 0.5, 100, phase='scan')
 finish = lambda: si.get_predictions(0.05, 0.5, 100, phase='finish')
+lref = train()
 ref = infer()
 scan()
 two = finish()
@@ -55,20 +56,30 @@ out = {'split_phase_equals_whole': bool(all(torch.equal(ref[k], two[k]) for k in
        'train': timeit(train), 'infer': timeit(infer), 'infer_split': timeit(lambda: (scan(), finish())),
        'scan_only': timeit(scan), 'sequential': timeit(lambda: (train(), infer()))}
 # the scan first (alone on the GPU), then the training step next to the latency-bound rest of the post-processing
-for ctas in (0, 5, 4):
-    for name, pr in (('', None), ('_finish_hi', (0, -1)), ('_train_hi', (-1, 0))):
+for ctas in (0,):
+    for name, pr in (('', None), ('_finish_hi', (0, -1))):
         conc = pkg.graph.concurrent(train, finish, priorities=pr, train_ctas_per_sm=ctas)
         out['scan_then_train_and_finish_ctas%d%s' % (ctas, name)] = timeit(lambda: (scan(), conc()))
     conc2 = pkg.graph.concurrent(finish, train, train_ctas_per_sm=ctas)
     out['scan_then_finish_and_train_ctas%d' % ctas] = timeit(lambda: (scan(), conc2()))
+# the same with the training step's chunks handed out dynamically (SSDK_OPT_TRAIN_DYNAMIC_CHUNKS)
+L.set_option(L.SSDK_OPT_TRAIN_DYNAMIC_CHUNKS, 1)
+ld = train()
+out['dyn_loss_equal_to_1e-7'] = bool(abs(float(ld['classification_loss']) - float(lref['classification_loss'])) <= 1e-7 * abs(float(lref['classification_loss'])))
+out['dyn_loss_repeatable'] = bool(all(float(train()['classification_loss']) == float(ld['classification_loss']) for _ in range(5)))
+out['dyn_train'] = timeit(train)
+for mm in (1, 2, 3):
+    L.set_option(L.SSDK_OPT_MATCH_CTAS_PER_SM, mm)
+    out['dyn_train_m%d' % mm] = timeit(train)
+L.set_option(L.SSDK_OPT_MATCH_CTAS_PER_SM, 0)
+for name, fns, pr in (('dyn_scan_then_finish_and_train', (finish, train), None), ('dyn_scan_then_finish_hi_and_train', (finish, train), (-1, 0)),
+                      ('dyn_scan_then_train_and_finish', (train, finish), None), ('dyn_scan_then_train_and_finish_hi', (train, finish), (0, -1))):
+    conc = pkg.graph.concurrent(*fns, priorities=pr)
+    out[name] = timeit(lambda: (scan(), conc()))
+out['dyn_concurrent_infer_first_hi'] = timeit(pkg.graph.concurrent(infer, train, priorities=(-1, 0)))
+out['dyn_concurrent_train_first'] = timeit(pkg.graph.concurrent(train, infer))
+L.set_option(L.SSDK_OPT_TRAIN_DYNAMIC_CHUNKS, 0)
 # the training step first, then the scan, then the rest
 out['train_scan_finish'] = timeit(lambda: (train(), scan(), finish()))
-for ctas in (0, 5):
-    L.set_option(L.SSDK_OPT_TRAIN_CTAS_PER_SM, ctas)
-    out['train_ctas%d' % ctas] = timeit(train)
-    for name, fns, pr in (('train_first', (train, infer), None), ('infer_first', (infer, train), None),
-                          ('infer_first_hi', (infer, train), (-1, 0)), ('train_first_infer_hi', (train, infer), (0, -1)),
-                          ('train_first_hi', (train, infer), (-1, 0))):
-        out['ctas%d_%s' % (ctas, name)] = timeit(pkg.graph.concurrent(*fns, priorities=pr, train_ctas_per_sm=ctas))
 L.set_option(L.SSDK_OPT_TRAIN_CTAS_PER_SM, 0)
 print(json.dumps(out))

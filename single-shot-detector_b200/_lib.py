@@ -169,6 +169,7 @@ def profile_read(device_index=0, reset=True):
 
 SSDK_OPT_FUSED_TRAIN_STEP, SSDK_OPT_MATCH_CTAS_PER_SM, SSDK_OPT_MATCH_FLAT_SHARE_PCT, SSDK_OPT_TRAIN_CTAS_PER_SM = 1, 2, 3, 4
 SSDK_OPT_PROGRAMMATIC_LAUNCH = 5
+SSDK_OPT_TRAIN_DYNAMIC_CHUNKS = 6
 SSDK_STEP_ALL_REDUCE = 1
 SSDK_ASYNC_ROUNDS_TIMEOUT = 1
 

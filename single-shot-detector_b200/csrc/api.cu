@@ -177,6 +177,7 @@ int ssdk_ctx_create(int device, void* stream, ssdk_ctx** out) {
     c->match_flat_share_pct = env_int("SSDK_MATCH_FLAT_SHARE", -1, -1, 100, 1);
     c->train_ctas_per_sm = env_int("SSDK_TRAIN_CTAS", 0, 0, 8, 1);
     c->use_pdl = env_int("SSDK_PDL", 1, 0, 1, 1);
+    c->train_dynamic_chunks = env_int("SSDK_TRAIN_DYNAMIC", 1, 0, 1, 1);
     *out = c;
     return SSDK_OK;
 }
@@ -190,6 +191,7 @@ int ssdk_ctx_set_option(ssdk_ctx* ctx, int option, int value) {
             ctx->match_ctas_per_sm = value;
             return SSDK_OK;
         case SSDK_OPT_PROGRAMMATIC_LAUNCH: ctx->use_pdl = value ? 1 : 0; return SSDK_OK;
+        case SSDK_OPT_TRAIN_DYNAMIC_CHUNKS: ctx->train_dynamic_chunks = value ? 1 : 0; return SSDK_OK;
         case SSDK_OPT_TRAIN_CTAS_PER_SM:
             SSDK_REQUIRE(value >= 0 && value <= 8, SSDK_ERR_ARG, "SSDK_OPT_TRAIN_CTAS_PER_SM must be in [0,8] (got %d)", value);
             ctx->train_ctas_per_sm = value;

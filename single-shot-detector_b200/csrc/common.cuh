@@ -50,6 +50,7 @@ struct ssdk_ctx {
     int fused_train_step = 1;      // SSDK_OPT_FUSED_TRAIN_STEP
     int match_ctas_per_sm = 0;     // SSDK_OPT_MATCH_CTAS_PER_SM (0 = automatic)
     int match_flat_share_pct = -1; // SSDK_OPT_MATCH_FLAT_SHARE_PCT (-1 = automatic)
+    int train_dynamic_chunks = 1;  // SSDK_OPT_TRAIN_DYNAMIC_CHUNKS: the flat pass of the fused training step hands out its chunks dynamically
     int train_ctas_per_sm = 0;     // SSDK_OPT_TRAIN_CTAS_PER_SM (0 = as many as fit)
     int use_pdl = 1;               // SSDK_OPT_PROGRAMMATIC_LAUNCH: chain the post-processing kernels with programmatic dependent launch
     // tuning knobs, read from the environment ONCE (ssdk_ctx_create) and validated there; 0 = automatic

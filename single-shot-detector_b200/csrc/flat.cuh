@@ -83,15 +83,33 @@ __device__ __forceinline__ float flat_value(const FlatSegs& S, const FlatChunk& 
     return s;
 }
 
+// Accumulators of the flat pass.  FlatAccDouble: one double per thread (the order of the additions is part of the result, so the
+// chunk -> thread assignment must be static for reproducible sums).  FlatAccFixed: 2^-32 fixed point in 64 bits -- integer addition
+// is associative, so the sum does not depend on which CTA happened to take which chunk: this is what lets the fused training
+// step hand out chunks DYNAMICALLY and still return bit-identical sums run after run.  Every per-thread chunk sum (a float,
+// 16 elements) is rounded to a multiple of 2^-32 (1.2e-10 absolute; the sums are ~1e-3 and larger, and 1e4 in total); chunk sums
+// of 2^30 and more (never with finite logits of sane size) and NaN go to a double on the side.
+struct FlatAccDouble {
+    double v = 0.0;
+    __device__ __forceinline__ void add(float s) { v += (double)s; }
+};
+struct FlatAccFixed {
+    long long fx = 0;
+    double big = 0.0;
+    __device__ __forceinline__ void add(float s) {
+        if (fabsf(s) < 1073741824.0f) fx += __float2ll_rn(s * 4294967296.0f);
+        else big += (double)s;
+    }
+};
+
 // This thread's share of the chunks g, g + stride, g + 2 stride, ... < g_end of the class-tensor segments (forward only), in
 // ascending order.  Segment by segment: the FULL chunks of a segment are read through a pointer that advances by a constant,
 // without bounds tests or segment lookups (in the generic form above those cost more instructions per chunk than the focal
 // arithmetic itself: ncu source view of the round-2 training-step kernel, profiles/r2b_ncu_summary.txt); only a segment's last,
-// partial chunk takes the bounded path.  Same per-chunk float sums and the same order of double additions as chunk-by-chunk
+// partial chunk takes the bounded path.  Same per-chunk float sums and the same order of additions as chunk-by-chunk
 // flat_load + flat_value.
-template <int GAMMA_MODE>
-__device__ __forceinline__ double flat_sum_range(const FlatSegs& S, long long g, long long g_end, long long stride, float gamma, int tid) {
-    double acc = 0.0;
+template <int GAMMA_MODE, class Acc>
+__device__ __forceinline__ void flat_sum_range(const FlatSegs& S, Acc& acc, long long g, long long g_end, long long stride, float gamma, int tid) {
     const long long pstep = stride * FLAT_CHUNK4;
 #pragma unroll 1
     for (int sg = 0; sg < S.n && g < g_end; ++sg) {
@@ -108,16 +126,21 @@ __device__ __forceinline__ double flat_sum_range(const FlatSegs& S, long long g,
             float4 v[FLAT_U];
 #pragma unroll
             for (int u = 0; u < FLAT_U; ++u) v[u] = ld_stream_f4(p + u * FLAT_THREADS);
-            acc += (double)flat_math<GAMMA_MODE>(v, gamma);
+            acc.add(flat_math<GAMMA_MODE>(v, gamma));
         }
         g += (long long)n_iter * stride;
         if (g < c1 && g < g_end) {                                            // the segment's partial last chunk
             FlatChunk ck;
             int cursor = sg;
             flat_load(S, ck, g, cursor, tid);
-            acc += (double)flat_value<GAMMA_MODE>(S, ck, g, gamma, tid);
+            acc.add(flat_value<GAMMA_MODE>(S, ck, g, gamma, tid));
             g += stride;
         }
     }
-    return acc;
+}
+template <int GAMMA_MODE>
+__device__ __forceinline__ double flat_sum_range(const FlatSegs& S, long long g, long long g_end, long long stride, float gamma, int tid) {
+    FlatAccDouble acc;
+    flat_sum_range<GAMMA_MODE>(S, acc, g, g_end, stride, gamma, tid);
+    return acc.v;
 }

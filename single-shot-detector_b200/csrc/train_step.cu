@@ -34,6 +34,8 @@ struct TrainStepArgs {
     double* partials;             // [grid][4]: flat sum, sum loc, class corrections, matched count
     double* img_partials;         // [B][3]: change of (sum loc, class corrections, matched count) by the forced matches; zero before the launch
     unsigned* ticket;             // zero before the launch
+    unsigned long long* flat_counter;   // DYN: next unclaimed chunk of the flat pass; zero before the launch
+    long long* fx_partials;       // DYN: [grid] fixed-point flat sums
     double* out_sums;             // [3]
     float* out_losses;            // [2] or NULL
     CommPeers P;
@@ -171,18 +173,27 @@ union TrainSmem {
     double fin[FLAT_THREADS][4];
 };
 
-template <int GAMMA_MODE>
+// DYN: the chunks of the flat pass are handed out dynamically (FLAT_CLAIM at a time, one atomic per claim, the next claim in
+// flight while the current one is worked off) instead of by the static split: whoever is free takes the next chunks -- the
+// matcher CTAs as soon as their matching is done, and CTAs that found their SM occupied by another kernel when the grid
+// started (a second sub-path running next to this one) simply take fewer.  The flat sum is accumulated in fixed point
+// (FlatAccFixed), so it is still bit-identical from run to run.
+#define FLAT_CLAIM 4
+template <int GAMMA_MODE, bool DYN>
 __global__ void __launch_bounds__(FLAT_THREADS, TRAIN_MIN_CTAS) train_step_kernel(const __grid_constant__ TrainStepArgs T) {
     static_assert(FLAT_THREADS == MATCH_THREADS, "both roles use the same CTA shape");
     __shared__ TrainSmem sm;
     __shared__ double s_red[FLAT_THREADS / 32][4];
     __shared__ double s_hook[(MATCH_THREADS / 32) * 3];
     __shared__ int s_last;
+    __shared__ long long s_claim[2];
+    __shared__ long long s_fx[FLAT_THREADS / 32];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int grid = (int)gridDim.x, cta = (int)blockIdx.x;
     const bool matcher = cta < T.n_match;
     const int n_flat = grid - T.n_match;
     double acc_flat = 0.0;
+    long long acc_fx = 0;
     LossHook<GAMMA_MODE> hook(T, sm.match, s_hook);
 
     // ---- role 1: target assignment + the matched / ignored anchors' contributions
@@ -193,7 +204,27 @@ __global__ void __launch_bounds__(FLAT_THREADS, TRAIN_MIN_CTAS) train_step_kerne
 
     // ---- role 2: the flat pass.  Rounds [0, rounds_all): every CTA takes chunk round * grid + cta; later rounds: only the
     //      streaming CTAs, chunk rounds_all * grid + (round - rounds_all) * n_flat + (cta - n_match).
-    {
+    if (DYN) {
+        const long long total = T.S.chunk0[T.S.nseg];
+        FlatAccFixed acc;
+        long long next = 0;
+        if (tid == 0) s_claim[0] = (long long)atomicAdd(T.flat_counter, (unsigned long long)FLAT_CLAIM);
+        __syncthreads();
+        int buf = 0;
+        while (true) {
+            const long long g0 = s_claim[buf];
+            if (g0 >= total) break;
+            if (tid == 0) next = (long long)atomicAdd(T.flat_counter, (unsigned long long)FLAT_CLAIM);   // used only after this claim's work
+            long long g1 = g0 + FLAT_CLAIM;
+            if (g1 > total) g1 = total;
+            flat_sum_range<GAMMA_MODE>(T.S, acc, g0, g1, 1, T.gamma, tid);
+            if (tid == 0) s_claim[buf ^ 1] = next;
+            __syncthreads();
+            buf ^= 1;
+        }
+        acc_flat = acc.big;
+        acc_fx = acc.fx;
+    } else {
         const long long total = T.S.chunk0[T.S.nseg];
         long long all_end = T.rounds_all * grid;
         if (all_end > total) all_end = total;
@@ -212,9 +243,21 @@ __global__ void __launch_bounds__(FLAT_THREADS, TRAIN_MIN_CTAS) train_step_kerne
     for (int j = 0; j < 4; ++j)
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) v[j] += __shfl_xor_sync(0xffffffffu, v[j], o);
+    if (DYN) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc_fx += __shfl_xor_sync(0xffffffffu, acc_fx, o);
+        if (lane == 0) s_fx[warp] = acc_fx;
+    }
     if (lane == 0)
         for (int j = 0; j < 4; ++j) s_red[warp][j] = v[j];
     __syncthreads();
+    if (DYN && tid == 4) {
+        long long t = 0;
+#pragma unroll
+        for (int w = 0; w < FLAT_THREADS / 32; ++w) t += s_fx[w];
+        T.fx_partials[cta] = t;
+        __threadfence();
+    }
     if (tid < 4) {
         double t = 0.0;
 #pragma unroll
@@ -248,11 +291,28 @@ __global__ void __launch_bounds__(FLAT_THREADS, TRAIN_MIN_CTAS) train_step_kerne
             for (int j = 0; j < 4; ++j) sm.fin[tid][j] += sm.fin[tid + o][j];
         __syncthreads();
     }
+    const double fin_flat = sm.fin[0][0], fin_loc = sm.fin[0][1], fin_fix = sm.fin[0][2], fin_cnt = sm.fin[0][3];
+    double flat_total = fin_flat;
+    if (DYN) {
+        // the fixed-point flat sums of all CTAs: integer addition, exact in any order
+        __syncthreads();                                                                  // everyone has read sm.fin[0][*]
+        long long* fxfin = (long long*)&sm.fin[0][0];
+        long long t = 0;
+        for (int i = tid; i < grid; i += FLAT_THREADS) t += __ldcg(&T.fx_partials[i]);
+        fxfin[tid] = t;
+        __syncthreads();
+        for (int o = FLAT_THREADS / 2; o > 0; o >>= 1) {
+            if (tid < o) fxfin[tid] += fxfin[tid + o];
+            __syncthreads();
+        }
+        flat_total = fin_flat + (double)fxfin[0] * 2.3283064365386963e-10;               // 2^-32
+    }
     if (tid == 0) {
-        T.out_sums[0] = sm.fin[0][1];                                                     // sum loc_losses
-        T.out_sums[1] = (double)(1.0f - T.alpha) * sm.fin[0][0] + sm.fin[0][2];           // sum cls_losses
-        T.out_sums[2] = sm.fin[0][3];                                                     // num_matches
+        T.out_sums[0] = fin_loc;                                                          // sum loc_losses
+        T.out_sums[1] = (double)(1.0f - T.alpha) * flat_total + fin_fix;                  // sum cls_losses
+        T.out_sums[2] = fin_cnt;                                                          // num_matches
         *T.ticket = 0u;
+        if (DYN) *T.flat_counter = 0ull;
     }
     __syncthreads();
     if (T.use_comm) comm_all_reduce(T.P, T.out_sums, 3);                                  // sums over all image shards (ssd.py:121-122)
@@ -330,7 +390,7 @@ int ssdk_train_step_impl(ssdk_ctx* ctx, const HeadGeom& G, const float* anchors,
     if (occ_cache[variant] == 0) {
         int occ = 0;
         SSDK_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(
-            &occ, variant == 0 ? (const void*)train_step_kernel<0> : (const void*)train_step_kernel<1>, FLAT_THREADS, 0));
+            &occ, variant == 0 ? (const void*)train_step_kernel<0, false> : (const void*)train_step_kernel<1, false>, FLAT_THREADS, 0));
         occ_cache[variant] = occ > 0 ? occ : 1;
     }
     int occ = occ_cache[variant];
@@ -358,7 +418,11 @@ int ssdk_train_step_impl(ssdk_ctx* ctx, const HeadGeom& G, const float* anchors,
         // Small batches: the matcher's critical path (its chunks one after the other in every matcher CTA, then the forced matches
         // and the final reduction, ~10 us) is longer than the streaming, so a third matcher CTA per SM pays as long as a matcher
         // CTA has fewer than ~19 chunks to walk (cfg2: below 12 images; 13-32 % faster at 2-8 images, profiles/r2u_split_sweep_small.json)
-        if (m < 3 && occ >= 5 && (long long)nchunks_img * B < 19ll * ctx->num_sms * m) { m = 3; small_batch = true; }
+        if (m < 3 && occ >= 5 && (long long)nchunks_img * B < 19ll * ctx->num_sms * m) {
+            // (with dynamic chunks the matcher CTAs join the streaming the moment they are done, so a fourth one is free below ~8 images)
+            m = (ctx->train_dynamic_chunks && occ >= 6 && (long long)nchunks_img * B < 10ll * ctx->num_sms * m) ? 4 : 3;
+            small_batch = true;
+        }
     }
     if (m > occ) m = occ;
     long long n_match = (long long)ctx->num_sms * m;
@@ -390,7 +454,7 @@ int ssdk_train_step_impl(ssdk_ctx* ctx, const HeadGeom& G, const float* anchors,
 
     // workspace: [per-CTA partials (fixed size)] [ticket | forced-match deltas | tickets | per-GT keys]: the second part is
     // zero between launches (zeroed when allocated, re-zeroed by the kernel)
-    const size_t part_bytes = (size_t)ctx->num_sms * 8 * 4 * sizeof(double);
+    const size_t part_bytes = (size_t)ctx->num_sms * 8 * (4 * sizeof(double) + sizeof(long long));   // double partials, then the fixed-point flat sums
     const size_t zero_bytes = 16 + (size_t)B * 3 * sizeof(double) + (size_t)B * sizeof(int) + 16 + (size_t)B * Gmax * sizeof(unsigned long long);
     SSDK_REQUIRE(grid <= (long long)ctx->num_sms * 8, SSDK_ERR_CUDA, "targets_and_loss: unexpected occupancy %d", occ);
     if (ctx->ws_train.cap < part_bytes + zero_bytes) {
@@ -399,8 +463,10 @@ int ssdk_train_step_impl(ssdk_ctx* ctx, const HeadGeom& G, const float* anchors,
     }
     char* w = (char*)ctx->ws_train.p;
     T.partials = (double*)w;
+    T.fx_partials = (long long*)(w + (size_t)ctx->num_sms * 8 * 4 * sizeof(double));
     w += part_bytes;
     T.ticket = (unsigned*)w;
+    T.flat_counter = (unsigned long long*)(w + 8);
     T.img_partials = (double*)(w + 16);
     int* tickets = (int*)(w + 16 + (size_t)B * 3 * sizeof(double));
     unsigned long long* best = (unsigned long long*)(((uintptr_t)(tickets + B) + 15) & ~(uintptr_t)15);
@@ -414,8 +480,11 @@ int ssdk_train_step_impl(ssdk_ctx* ctx, const HeadGeom& G, const float* anchors,
     T.out_losses = out_losses;
     T.P = P;
     T.use_comm = use_comm ? 1 : 0;
+    const bool dyn = ctx->train_dynamic_chunks != 0;
     SSDK_KERNEL(ctx, SSDK_K_TRAIN_STEP,
-                if (variant == 0) train_step_kernel<0><<<(int)grid, FLAT_THREADS, 0, ctx->stream>>>(T);
-                else train_step_kernel<1><<<(int)grid, FLAT_THREADS, 0, ctx->stream>>>(T));
+                if (variant == 0 && dyn) train_step_kernel<0, true><<<(int)grid, FLAT_THREADS, 0, ctx->stream>>>(T);
+                else if (variant == 0) train_step_kernel<0, false><<<(int)grid, FLAT_THREADS, 0, ctx->stream>>>(T);
+                else if (dyn) train_step_kernel<1, true><<<(int)grid, FLAT_THREADS, 0, ctx->stream>>>(T);
+                else train_step_kernel<1, false><<<(int)grid, FLAT_THREADS, 0, ctx->stream>>>(T));
     return SSDK_OK;
 }
