@@ -10,9 +10,12 @@
 //     ignored anchors (smooth-L1, count, the positive-class and ignore corrections of head.cu) are added right where the match
 //     is decided -- the [B,A] matches array is never read back, head_rows_kernel is gone from this path; the CTA that finishes
 //     an image applies the forced matches (training_target_creation.py:105-126) and books the resulting CHANGE of the sums.
-//   * all other CTAs stream the class logits (flat.cuh: 16 KB chunks, 128-bit no-allocate loads, e^3 h(e) fast path).  The
-//     chunk list is split statically: the matcher CTAs join the streaming for a share of the chunks once their matching is
-//     done, so every CTA slot of the GPU streams until the end (static, hence deterministic sums).
+//   * all other CTAs stream the class logits (flat.cuh: 16 KB chunks, 128-bit no-allocate loads, e^3 h(e) fast path).  By
+//     default the chunks are handed out DYNAMICALLY (one atomic per four chunks): the matcher CTAs start claiming the moment
+//     their matching is done, so every CTA slot of the GPU streams until the end whatever the ratio of the two kinds of work,
+//     and the flat sum is added in 2^-32 fixed point (integer addition is associative), so it is bit-identical from run to run
+//     although the chunk -> CTA assignment is not.  Option SSDK_OPT_TRAIN_DYNAMIC_CHUNKS = 0: the static split (the matcher CTAs
+//     take a fixed share of the chunk list, double accumulation in a fixed order).
 //   * every CTA writes its partial sums; the CTA that draws the last ticket adds them in a fixed order, performs the peer-memory
 //     all-reduce (comm.cuh) when asked to, and writes sums and losses.  It also leaves the workspace zeroed for the next launch,
 //     so the step is exactly one graph node.
@@ -202,8 +205,8 @@ __global__ void __launch_bounds__(FLAT_THREADS, TRAIN_MIN_CTAS) train_step_kerne
         for (int w = cta; w < items; w += T.n_match) match_work_item<true>(T.M, sm.match, w / T.gx, w % T.gx, T.gx, hook);
     }
 
-    // ---- role 2: the flat pass.  Rounds [0, rounds_all): every CTA takes chunk round * grid + cta; later rounds: only the
-    //      streaming CTAs, chunk rounds_all * grid + (round - rounds_all) * n_flat + (cta - n_match).
+    // ---- role 2: the flat pass.  DYN: claims of FLAT_CLAIM chunks.  Static split: rounds [0, rounds_all): every CTA takes chunk
+    //      round * grid + cta; later rounds: only the streaming CTAs, chunk rounds_all * grid + (round - rounds_all) * n_flat + (cta - n_match).
     if (DYN) {
         const long long total = T.S.chunk0[T.S.nseg];
         FlatAccFixed acc;
