@@ -466,6 +466,13 @@ def run_ours(args):
     lib.set_option(lib.SSDK_OPT_FUSED_TRAIN_STEP, 0, local_rank)
     ms_train_unfused = timed(lambda: ssd_t.loss(d_gt, PARAMS), args.steps)
     lib.set_option(lib.SSDK_OPT_FUSED_TRAIN_STEP, 1, local_rank)
+    # the fused kernel with the static split of the chunk list (double accumulation in a fixed order) instead of dynamically handed-out chunks
+    lib.set_option(lib.SSDK_OPT_TRAIN_DYNAMIC_CHUNKS, 0, local_rank)
+    ms_train_static = timed(lambda: ssd_t.loss(d_gt, PARAMS), args.steps)
+    l_static = ssd_t.loss(d_gt, PARAMS)
+    lib.set_option(lib.SSDK_OPT_TRAIN_DYNAMIC_CHUNKS, 1, local_rank)
+    l_dyn = ssd_t.loss(d_gt, PARAMS)
+    static_vs_dynamic = max(abs(float(l_static[k]) - float(l_dyn[k])) / abs(float(l_dyn[k])) for k in ('localization_loss', 'classification_loss'))
     ms_train_nccl = None
     if world > 1 and peer:                       # the same training sub-path with the library collective, for comparison
         ssd_t.peer_all_reduce = False
@@ -647,6 +654,7 @@ def run_ours(args):
             'sequential_graph_images_per_sec': None if not ms_sequential_graph else (Bt + Bi) * world / (ms_sequential_graph * 1e-3),
             'train_images_per_sec': Bt * world / (ms_train * 1e-3), 'train_ms_per_step': ms_train,
             'train_frac_of_hbm_roofline': (b_train * Bt / (ms_train * 1e-3) / 1e9) / peak,
+            'train_static_split_ms_per_step': ms_train_static, 'train_static_vs_dynamic_losses_rel_diff': static_vs_dynamic,
             'train_unfused_ms_per_step': ms_train_unfused,
             'train_unfused_frac_of_hbm_roofline': (b_train * Bt / (ms_train_unfused * 1e-3) / 1e9) / peak,
             'infer_images_per_sec': Bi * world / (ms_infer * 1e-3), 'infer_ms_per_step': ms_infer,
